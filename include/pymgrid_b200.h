@@ -1,0 +1,229 @@
+/*
+ * pymgrid_b200.h -- C-ABI of the B200-native batched microgrid-step engine.
+ *
+ * The reference (Total-RD/pymgrid @ 7bf3951, pure Python) has no FFI; its "operator API" for this path is the
+ * Python call `Microgrid.run(control, normalized)` (src/pymgrid/microgrid/microgrid.py:227-325) dispatching to
+ * `BaseMicrogridModule.step` (src/pymgrid/modules/base/base_module.py:95-159).  This header is the boundary a
+ * maintainer would bind from Python (ctypes stub in INTEGRATION.md) to replace that loop for a batch of B
+ * independent microgrids.  Each entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C types only: raw DEVICE pointers, sizes, a cudaStream_t passed as void*; no torch types;
+ *   - every array is owned by the caller (the Python host keeps them as torch device tensors); a handle owns
+ *     only a copy of the layout metadata; nothing is allocated on the step path;
+ *   - every call returns 0 on success or a negative MG_E_* code, never throws; mg_last_error() gives the text;
+ *   - calls are asynchronous with respect to the host (work is enqueued on `stream`);
+ *   - a handle is not re-entrant: one call at a time per handle (the reference object is not thread safe
+ *     either); different handles are independent.
+ *
+ * All floating-point data is IEEE f64, the reference's arithmetic type; integers are int32 / uint8 / uint32.
+ */
+#ifndef PYMGRID_B200_H
+#define PYMGRID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_ABI_VERSION 1
+#define MG_MAX_GROUPS 8
+#define MG_N_INFO 12
+#define MG_PLIST_WIDTH 3
+
+/* return codes */
+enum {
+    MG_OK = 0,
+    MG_E_INVALID = -1,     /* bad argument / layout            */
+    MG_E_CUDA = -2,        /* a CUDA runtime call failed       */
+    MG_E_UNSUPPORTED = -3  /* valid but outside the built path */
+};
+
+/* flat observation order: the reference flattens with gym.spaces.flatten
+ * (envs/base/base.py:211-223); real gym sorts Dict keys alphabetically. */
+enum {
+    MG_OBS_GYM_SORTED = 0, /* battery, genset, grid, load, pv                                           */
+    MG_OBS_CONTAINER = 1   /* load, pv, genset, battery, grid (module listing order, module_container.py) */
+};
+
+/* columns of the optional per-env info block (the reference's info dict, microgrid/utils/step.py:22-31) */
+enum {
+    MG_INFO_LOAD_MET = 0, MG_INFO_PV_USED = 1, MG_INFO_CURTAILMENT = 2, MG_INFO_LOSS_LOAD = 3,
+    MG_INFO_OVERGENERATION = 4, MG_INFO_GENSET_PRODUCTION = 5, MG_INFO_GENSET_CO2 = 6,
+    MG_INFO_BATTERY_DISCHARGE = 7, MG_INFO_BATTERY_CHARGE = 8, MG_INFO_GRID_IMPORT = 9,
+    MG_INFO_GRID_EXPORT = 10, MG_INFO_GRID_CO2 = 11
+};
+
+/* per-env event flags: where the reference raises (or, with raise_errors=False, silently clips) */
+enum {
+    MG_FLAG_GENSET_GOAL_RANGE = 1u << 0, /* AssertionError genset_module.py:147                         */
+    MG_FLAG_GENSET_AS_SINK = 1u << 1,    /* AssertionError genset_module.py:208                         */
+    MG_FLAG_BALANCE = 1u << 2,           /* RuntimeError   microgrid.py:321-323                         */
+    MG_FLAG_BATTERY_MIN_CAP = 1u << 3,   /* AssertionError battery_module.py:128                        */
+    MG_FLAG_NEGATIVE_ABSORB = 1u << 4,   /* AssertionError base_module.py:272                           */
+    MG_FLAG_STEP_PAST_END = 1u << 5,     /* IndexError     load_module.py:111 (t >= len(series))        */
+    MG_FLAG_BAD_ACTION = 1u << 6,        /* ValueError     envs/discrete/discrete.py:84 (action not in space) */
+    MG_FLAG_CLIP_GENSET = 1u << 8,       /* ValueError when raise_errors=True, base_module.py:213-221   */
+    MG_FLAG_CLIP_BATTERY = 1u << 9,
+    MG_FLAG_CLIP_GRID = 1u << 10
+};
+
+/* modules in a priority-list element (algos/priority_list/priority_list_element.py) */
+enum { MG_MOD_NONE = -1, MG_MOD_GENSET = 0, MG_MOD_BATTERY = 1, MG_MOD_GRID = 2 };
+
+/*
+ * One microgrid parameter set ("config").  Device array, 320-byte stride, indexed by MgGroup.cfg_index.
+ * Raw parameters are the reference constructors' arguments; the *_low / *_spread members are the
+ * ModuleSpace constants the reference derives once at construction (utils/space.py:183-205), computed by the
+ * host in f64 exactly as the reference does.
+ */
+typedef struct MgConfig {
+    /* BatteryModule, modules/battery_module.py:66-91 */
+    double bat_min_capacity, bat_max_capacity, bat_max_charge, bat_max_discharge, bat_efficiency, bat_cost_cycle;
+    double bat_act_low, bat_act_spread;                      /* :332-338 (note the reference's min/max naming) */
+    double bat_soc_low, bat_soc_spread, bat_charge_spread;   /* :323-330; charge low is bat_min_capacity      */
+    /* GensetModule, modules/genset_module.py:61-92 */
+    double gen_running_min, gen_running_max, gen_cost, gen_co2_per_unit, gen_cost_per_unit_co2;
+    double gen_act_spread, gen_up_spread, gen_down_spread;   /* :503-517 */
+    /* GridModule, modules/grid_module.py:70-132 */
+    double grid_max_import, grid_max_export, grid_cost_per_unit_co2, grid_act_low, grid_act_spread;
+    /* UnbalancedEnergyModule, modules/unbalanced_energy_module.py:14-26 */
+    double loss_load_cost, overgeneration_cost;
+    /* reserved for profile-times-scale series (MicrogridGenerator grids); unused when scale == 1 */
+    double load_scale, pv_scale, load_low, load_spread, pv_low, pv_spread;
+    int32_t gen_start_up_time, gen_wind_down_time, gen_allow_abortion;
+    int32_t load_series, pv_series, grid_series;             /* rows of the series tables                     */
+    int32_t initial_step, final_step;                        /* base_timeseries_module.py:317-330             */
+    int32_t plist_offset, plist_count;                       /* rows of MgLayout.plist owned by this config   */
+    int32_t reserved[6];
+} MgConfig;
+
+/*
+ * One priority list = one discrete action (algos/priority_list/priority_list.py:15-67): up to MG_PLIST_WIDTH
+ * elements (module, genset-goal), deployed in order by mg_step_discrete.
+ */
+typedef struct MgPriorityList {
+    int8_t module[MG_PLIST_WIDTH];   /* MG_MOD_* ; MG_MOD_NONE pads                                           */
+    int8_t action[MG_PLIST_WIDTH];   /* genset: the goal status (0/1); others 0                               */
+    int8_t n_elements, _pad;
+} MgPriorityList;
+
+/*
+ * Architecture group: envs that share (has_genset, has_grid, horizon) and therefore the observation / action
+ * row layout.  pymgrid25 has three (genset-only, grid-only, genset+grid).  State arrays are read AND written.
+ */
+typedef struct MgGroup {
+    int32_t has_genset, has_grid, horizon, obs_order;
+    int32_t n_act, obs_dim;          /* must equal 1+has_grid+2*has_genset, (1+H)(2+4*has_grid)+2+4*has_genset */
+    int64_t n_envs;
+    int32_t act_col_genset, act_col_battery, act_col_grid, _pad;  /* columns of the action row               */
+    /* per-env state (the reference's serialisable state: base_module.py:852-868, genset_module.py:426-427) */
+    int32_t *step;                   /* [n] _current_step                                                     */
+    double *charge;                  /* [n] battery _current_charge (soc is derived)                          */
+    uint32_t *genset;                /* [n] cs | gs<<8 | steps_until_up<<16 | steps_until_down<<24; NULL if no genset */
+    const int32_t *cfg_index;        /* [n] row of MgLayout.cfg                                               */
+    const int32_t *env_initial_step; /* [n] per-env trajectory window (microgrid/trajectory/), or NULL -> cfg  */
+    const int32_t *env_final_step;   /* [n] or NULL -> cfg                                                    */
+} MgGroup;
+
+typedef struct MgLayout {
+    int32_t abi_version;
+    int32_t n_groups;
+    MgGroup groups[MG_MAX_GROUPS];
+    int32_t n_cfg;
+    int32_t series_len;              /* T: rows of every raw series                                           */
+    int32_t max_horizon;             /* normalised tables carry T + max_horizon + 1 rows                      */
+    int32_t n_load, n_pv, n_grid;
+    const MgConfig *cfg;             /* [n_cfg]                                                               */
+    const double *load_raw;          /* [n_load][T]    stored NEGATIVE like the reference (base_timeseries_module.py:68-79) */
+    const double *pv_raw;            /* [n_pv][T]                                                             */
+    const double *grid_raw;          /* [n_grid][T][4] import_price, export_price, co2_per_kwh, grid_status   */
+    /* normalised, end-padded observation tables, FILLED BY mg_create on the device:
+       value = (ts - low) / spread (utils/space.py:207-218) with the bounds of base_timeseries_module.py:81-88 /
+       grid_module.py:125-132; rows >= T hold the forecaster's fill (high+low)/2 (forecast/forecaster.py:95) */
+    double *load_nrm;                /* [n_load][T + max_horizon + 1]                                         */
+    double *pv_nrm;                  /* [n_pv][T + max_horizon + 1]                                           */
+    double *grid_nrm;                /* [n_grid][T + max_horizon + 1][4]                                      */
+    double *bounds;                  /* [(n_load + n_pv + 4*n_grid)][2] low, high of every series column (out) */
+    const MgPriorityList *plist;     /* [n_plist] or NULL when mg_step_discrete is not used                   */
+    int32_t n_plist, _pad;
+} MgLayout;
+
+/* per-group arguments of one step */
+typedef struct MgStepIO {
+    const double *actions;   /* [n, n_act] f64: normalised in [0,1] or unnormalised (mg_step)                  */
+    const int32_t *dactions; /* [n] int32 priority-list index (mg_step_discrete)                              */
+    double *obs;             /* [n, obs_dim] normalised post-step observation, or NULL to skip                */
+    double *reward;          /* [n]                                                                           */
+    uint8_t *done;           /* [n]                                                                           */
+    double *info;            /* [n, MG_N_INFO] or NULL                                                        */
+    uint32_t *flags;         /* [n] MG_FLAG_* or NULL                                                         */
+    const uint8_t *mask;     /* [n] mg_reset only: envs to reset (NULL = all)                                 */
+} MgStepIO;
+
+/* per-group arguments of a multi-step rollout: leading dimension is the step */
+typedef struct MgRolloutIO {
+    const double *actions;   /* [n_steps, n, n_act] (mg_rollout)                                              */
+    const int32_t *dactions; /* [n_steps, n]        (mg_rollout_discrete)                                     */
+    double *obs_ring;        /* [ring, n, obs_dim]: step s writes slot s % ring; NULL to skip observations    */
+    double *reward;          /* [n_steps, n]                                                                  */
+    uint8_t *done;           /* [n_steps, n]                                                                  */
+    double *reward_sum;      /* [n] sum over the rollout in step order, or NULL                               */
+    uint32_t *flags;         /* [n] OR over the rollout, or NULL                                              */
+} MgRolloutIO;
+
+typedef struct MgHandle MgHandle;
+
+/* library / build identification (also the symbol the loader probes first) */
+int mg_abi_version(void);
+const char *mg_build_info(void);
+const char *mg_last_error(void);
+
+/*
+ * mg_create -- replaces Microgrid.__init__ / from_scenario for a batch (microgrid.py:100-128, 958-980):
+ * validates the layout, keeps a device copy of the group table, and fills the normalised observation tables
+ * and `bounds` on `stream` (the reference computes the same bounds in each module's constructor).
+ */
+int mg_create(const MgLayout *layout, void *stream, MgHandle **out);
+int mg_destroy(MgHandle *h);
+
+/*
+ * mg_step -- replaces Microgrid.run(control, normalized) (microgrid.py:227-325) and, with obs != NULL,
+ * BaseMicrogridEnv.step (envs/base/base.py:169-209) for every env of every group, ONE fused kernel launch.
+ * io: array of n_groups.  normalized: same meaning as the reference argument.
+ */
+int mg_step(MgHandle *h, const MgStepIO *io, int normalized, void *stream);
+
+/*
+ * mg_step_discrete -- replaces DiscreteMicrogridEnv.step(action:int) (envs/discrete/discrete.py:109-143):
+ * priority-list expansion (algos/priority_list/priority_list.py:69-116) fused in front of the step.
+ */
+int mg_step_discrete(MgHandle *h, const MgStepIO *io, void *stream);
+
+/*
+ * mg_reset -- replaces Microgrid.reset / BaseMicrogridEnv.reset (microgrid.py:205-225, envs/base/base.py:165-167):
+ * step = initial_step for the masked envs (battery charge and genset status are NOT reset, as in the
+ * reference), then writes the observation of every env of the group to io[g].obs when it is not NULL.
+ */
+int mg_reset(MgHandle *h, const MgStepIO *io, void *stream);
+
+/* mg_observe -- current normalised observation without stepping (BaseMicrogridModule.state normalised,
+ * base_module.py:65-77, 157) */
+int mg_observe(MgHandle *h, const MgStepIO *io, void *stream);
+
+/*
+ * mg_rollout / mg_rollout_discrete -- n_steps consecutive mg_step / mg_step_discrete calls in ONE persistent
+ * kernel: state stays on chip between steps; replaces the caller's `for t in range(T): microgrid.run(...)`
+ * loop (e.g. algos/rbc/rbc.py:87-91).  ring = number of observation slots (>= 1).
+ */
+int mg_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, int normalized, void *stream);
+int mg_rollout_discrete(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, void *stream);
+
+/* number of kernel launches this handle has enqueued since creation (bench.py's gpu_launches claim) */
+int64_t mg_launch_count(const MgHandle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYMGRID_B200_H */

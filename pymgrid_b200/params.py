@@ -1,0 +1,141 @@
+"""Parameter record of ONE microgrid, in the reference's own vocabulary.
+
+A `MicrogridParams` holds exactly what the reference's module constructors take for the modules on the
+hot path plus the mutable state the reference serialises
+(`base_module.py:852-868`, `genset_module.py:426-427`): battery charge, genset status tuple, step.
+It is the neutral hand-over format between the scenario readers (`scenario.py`), the batched engine
+(`engine.py`) and -- in the tests only -- the CPU oracle binding (`oracle/oracle.py`).
+"""
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+DEFAULT_HORIZON = 23  # reference: src/pymgrid/microgrid/__init__.py:1
+
+
+@dataclass
+class BatteryParams:
+    """reference: modules/battery_module.py:66-91"""
+    min_capacity: float
+    max_capacity: float
+    max_charge: float
+    max_discharge: float
+    efficiency: float
+    battery_cost_cycle: float = 0.0
+    current_charge: float = 0.0     # state: _current_charge
+
+    @property
+    def min_soc(self):
+        return self.min_capacity / self.max_capacity
+
+    @property
+    def min_act(self):              # battery_module.py:332-334
+        return -self.max_discharge / self.efficiency
+
+    @property
+    def max_act(self):              # battery_module.py:336-338
+        return self.max_charge * self.efficiency
+
+
+@dataclass
+class GensetParams:
+    """reference: modules/genset_module.py:61-92"""
+    running_min_production: float
+    running_max_production: float
+    genset_cost: float
+    co2_per_unit: float = 0.0
+    cost_per_unit_co2: float = 0.0
+    start_up_time: int = 0
+    wind_down_time: int = 0
+    allow_abortion: bool = True
+    # state (genset_module.py:91-92, :429-433)
+    current_status: int = 1
+    goal_status: int = 1
+    steps_until_up: int = 0
+    steps_until_down: int = 0
+
+    @classmethod
+    def with_init(cls, init_start_up=True, **kw):
+        g = cls(**kw)
+        g.current_status = g.goal_status = int(init_start_up)
+        if g.current_status:
+            g.steps_until_up, g.steps_until_down = 0, g.wind_down_time
+        else:
+            g.steps_until_up, g.steps_until_down = g.start_up_time, 0
+        return g
+
+
+@dataclass
+class GridParams:
+    """reference: modules/grid_module.py:70-123; time_series columns import_price, export_price,
+    co2_per_kwh, grid_status (a 3-column input gets status == 1, grid_module.py:112-118)."""
+    max_import: float
+    max_export: float
+    time_series: np.ndarray         # [T, 4] float64
+    cost_per_unit_co2: float = 0.0
+
+
+@dataclass
+class MicrogridParams:
+    battery: BatteryParams
+    load_ts: np.ndarray             # [T] float64, stored NEGATIVE like the reference (base_timeseries_module.py:68-79)
+    pv_ts: np.ndarray               # [T] float64, >= 0
+    genset: Optional[GensetParams] = None
+    grid: Optional[GridParams] = None
+    loss_load_cost: float = 10.0    # microgrid.py:103-104 defaults 10 / 2; pymgrid25 uses 10 / 1
+    overgeneration_cost: float = 2.0
+    forecast_horizon: int = DEFAULT_HORIZON   # 0 = no forecaster
+    initial_step: int = 0
+    final_step: int = -1            # <= 0 means len(series) (base_timeseries_module.py:317-330)
+    current_step: int = 0
+    name: str = ""
+    meta: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        self.load_ts = -np.abs(np.ascontiguousarray(self.load_ts, dtype=np.float64).reshape(-1))
+        self.pv_ts = np.abs(np.ascontiguousarray(self.pv_ts, dtype=np.float64).reshape(-1))
+        if self.grid is not None:
+            ts = np.asarray(self.grid.time_series, dtype=np.float64)
+            if ts.ndim != 2 or ts.shape[1] not in (3, 4):
+                raise ValueError('Time series must be two dimensional with three or four columns.')
+            if ts.shape[1] == 3:
+                ts = np.concatenate([ts, np.ones((ts.shape[0], 1))], axis=1)
+            elif not ((ts[:, -1] == 0) | (ts[:, -1] == 1)).all():
+                raise ValueError("Last column (grid status) must contain binary values.")
+            if (ts < 0).any():
+                raise ValueError('Time series must be non-negative.')
+            self.grid.time_series = np.ascontiguousarray(ts)
+            if len(ts) != len(self.load_ts):
+                raise ValueError('all time series must have the same length')
+        if len(self.pv_ts) != len(self.load_ts):
+            raise ValueError('all time series must have the same length')
+        if self.final_step <= 0:
+            self.final_step = len(self.load_ts)
+        if self.final_step <= self.initial_step:
+            raise ValueError('final_step value must be greater than initial_step')
+
+    # -- shape of the flat spaces ---------------------------------------------
+    def __len__(self):
+        return len(self.load_ts)
+
+    @property
+    def has_genset(self):
+        return self.genset is not None
+
+    @property
+    def has_grid(self):
+        return self.grid is not None
+
+    @property
+    def arch(self):
+        return (int(self.has_genset), int(self.has_grid), int(self.forecast_horizon))
+
+    @property
+    def obs_dim(self):
+        rows = 1 + self.forecast_horizon
+        return rows * (2 + 4 * self.has_grid) + 2 + 4 * self.has_genset
+
+    @property
+    def n_act(self):
+        return 1 + int(self.has_grid) + 2 * int(self.has_genset)

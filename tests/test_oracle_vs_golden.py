@@ -1,0 +1,161 @@
+"""Pin the C oracle (oracle/mg_oracle.c) to the reference: golden vectors recorded from the live reference
+(tests/golden/make_golden.py) must be reproduced BIT FOR BIT (integers and floats alike)."""
+import numpy as np
+import pytest
+
+from oracle.oracle import MOD_BATTERY, MOD_GENSET, MOD_GRID, OracleBatch, OracleGrid  # noqa: F401
+from pymgrid_b200.scenario import load_pymgrid25
+from tests.helpers import custom_params, jump_to, state_from_oracle
+
+
+def run_and_compare(o, actions, rewards, dones, obs, infos, states, normalized=True):
+    for k in range(len(actions)):
+        ob, r, d, info, _ = o.run(actions[k], normalized=normalized)
+        assert r == rewards[k], (k, r, rewards[k])
+        assert d == bool(dones[k]), k
+        np.testing.assert_array_equal(ob, obs[k], err_msg=f"obs step {k}")
+        np.testing.assert_array_equal(info, infos[k], err_msg=f"info step {k}")
+        np.testing.assert_array_equal(state_from_oracle(o), states[k], err_msg=f"state step {k}")
+
+
+@pytest.mark.parametrize("n", range(25))
+def test_pymgrid25_steps(golden, n):
+    z = golden["pymgrid25_steps"]
+    p = load_pymgrid25(n)
+    o = OracleGrid(p)
+    g = lambda k: z[f"s{n}_{k}"]  # noqa: E731
+    run_and_compare(o, g("a0"), g("r0"), g("d0"), g("o0"), g("i0"), g("s0"))
+    run_and_compare(o, g("au"), g("ru"), g("du"), g("ou"), g("iu"), g("su"), normalized=False)
+    # across the end of the series: forecast padding, done at final_step - 1, last valid step t = T - 1
+    o2 = OracleGrid(jump_to(p, int(z["end_from"])))
+    np.testing.assert_array_equal(o2.reset(), g("reset_obs"))
+    run_and_compare(o2, g("a1"), g("r1"), g("d1"), g("o1"), g("i1"), g("s1"))
+    assert g("d1")[-1] == 1 and g("d1")[0] == 0
+
+
+@pytest.mark.parametrize("n", (0, 1, 2))
+def test_full_year(golden, n):
+    z = golden["pymgrid25_year"]
+    p = load_pymgrid25(n)
+    actions = np.random.default_rng(0).random((8760, p.n_act))
+    b = OracleBatch([p])
+    rewards, dones, _ = b.rollout(actions[:, None, :])
+    np.testing.assert_array_equal(rewards[:, 0], z[f"s{n}_rewards"])
+    assert int(np.argmax(dones[:, 0])) == int(z[f"s{n}_first_done"]) == 8758
+    t, charge, gen = b.state()
+    np.testing.assert_array_equal(np.array([t[0], charge[0], *gen[0]], dtype=np.float64), z[f"s{n}_final_state"])
+
+
+def test_legacy_seed_known_answer(golden):
+    """np.random.seed(0); sample_action(strict_bound=True) on scenario 0."""
+    z = golden["pymgrid25_year"]
+    o = OracleGrid(load_pymgrid25(0))
+    _, r, _, info, _ = o.run(z["legacy_s0_action"])
+    assert r == float(z["legacy_s0_reward"]) == -544.8242524518755
+    np.testing.assert_array_equal(info, z["legacy_s0_info"])
+    assert info[0] == 304.403798960378 and info[9] == 826.3271668700909 and info[4] == 339.9448144937339
+
+
+def test_stepping_past_the_end_is_flagged():
+    from oracle.oracle import lib  # noqa: F401
+    p = jump_to(load_pymgrid25(0), 8759)
+    o = OracleGrid(p)
+    _, r, d, _, err = o.run(np.array([0.5, 0.5]))
+    assert d and err & ~((1 << 9) | (1 << 10) | (1 << 8)) == 0 and o.state["t"] == 8760
+    _, r, d, _, err = o.run(np.array([0.5, 0.5]))
+    assert err & (1 << 5) and np.isnan(r) and o.state["t"] == 8760
+
+
+def test_genset_state_machine(golden):
+    """Exhaustive: U, D in 0..4, both abortion settings, both initial states, all 6-step goal sequences
+    (the reference's TestManyStatusChanges, tests/microgrid/modules/module_tests/test_genset_long_status_changes.py:217-262)."""
+    from oracle.oracle import lib, OrcGrid
+    import ctypes as C
+    z = golden["genset_machine"]
+    params, goals, states = z["params"], z["goals"], z["states"]
+    L = lib()
+    for (U, D, abort, init), gl, st in zip(params, goals, states):
+        g = OrcGrid()
+        g.start_up_time, g.wind_down_time, g.allow_abortion = int(U), int(D), int(abort)
+        g.cs = g.gs = int(init)
+        g.up, g.dn = (0, int(D)) if init else (int(U), 0)
+        for goal, want in zip(gl, st):
+            pred = L.orc_genset_next_status(C.byref(g), int(goal))
+            L.orc_genset_update_status(C.byref(g), float(goal))
+            assert (g.cs, g.gs, g.up, g.dn, pred) == tuple(int(x) for x in want)
+    # Python round(): half to even
+    g = OrcGrid()
+    g.cs = g.gs = 1
+    for f, want in zip(z["frac_goals"], z["frac_status"]):
+        L.orc_genset_update_status(C.byref(g), float(f))
+        assert g.cs == int(want)
+
+
+def test_genset_known_answers_from_reference_tests():
+    """Literal state tuples from the reference's unit tests:
+    test_genset_long_status_changes.py:35-89 (on -> off with wind_down_time=3) and :180-214 (abortion)."""
+    from oracle.oracle import lib, OrcGrid
+    import ctypes as C
+    L = lib()
+    g = OrcGrid()
+    g.start_up_time, g.wind_down_time, g.allow_abortion = 2, 3, 1
+    g.cs = g.gs = 1
+    g.up, g.dn = 0, 3
+    seq = []
+    for _ in range(4):
+        L.orc_genset_update_status(C.byref(g), 0.0)
+        seq.append((g.cs, g.gs, g.up, g.dn))
+    assert seq == [(1, 0, 0, 2), (1, 0, 0, 1), (1, 0, 0, 0), (0, 0, 2, 0)]
+    # abort a shut-down half way: goal back to 1 restores the running state
+    g.cs = g.gs = 1
+    g.up, g.dn = 0, 3
+    L.orc_genset_update_status(C.byref(g), 0.0)
+    L.orc_genset_update_status(C.byref(g), 1.0)
+    assert (g.cs, g.gs, g.up, g.dn) == (1, 1, 0, 3)
+
+
+@pytest.mark.parametrize("i", range(6))
+def test_custom_grids(golden, i):
+    z = golden["custom"]
+    p = custom_params(z, i)
+    o = OracleGrid(p)
+    np.testing.assert_array_equal(o.reset(), z[f"c{i}_reset_obs"])
+    run_and_compare(o, z[f"c{i}_a"], z[f"c{i}_r"], z[f"c{i}_d"], z[f"c{i}_o"], z[f"c{i}_i"], z[f"c{i}_s"])
+    # reset keeps battery charge and genset status
+    charge = o.state["charge"]
+    np.testing.assert_array_equal(o.reset(), z[f"c{i}_after_reset_obs"])
+    assert o.state["charge"] == charge and o.state["t"] == 0
+
+
+def _discrete_cases(z):
+    return sorted({k.rsplit("_", 1)[0] for k in z.files if k.endswith("_actions")})
+
+
+def test_discrete_env(golden):
+    z = golden["discrete"]
+    cases = _discrete_cases(z)
+    assert len(cases) == 40
+    for tag in cases:
+        horizon, n = int(tag.split("_")[0][1:]), int(tag.split("_")[1][1:])
+        p = load_pymgrid25(n)
+        p.forecast_horizon = horizon
+        o = OracleGrid(p)
+        assert o.obs_dim == int(z[f"{tag}_obs_dim"])
+        np.testing.assert_array_equal(o.reset(), z[f"{tag}_reset_obs"])
+        mod, act = z[f"{tag}_table_mod"], z[f"{tag}_table_act"]
+        for k, a in enumerate(z[f"{tag}_actions"]):
+            plist = [(int(m), int(x)) for m, x in zip(mod[a], act[a]) if m >= 0]
+            ctrl = o.priority_control(plist)
+            np.testing.assert_array_equal(ctrl, z[f"{tag}_controls"][k], err_msg=f"{tag} control {k}")
+            ob, r, d, _, _ = o.run(ctrl, normalized=False)
+            assert r == z[f"{tag}_rewards"][k] and d == bool(z[f"{tag}_dones"][k])
+            np.testing.assert_array_equal(ob, z[f"{tag}_obs"][k], err_msg=f"{tag} obs {k}")
+
+
+def test_container_order_is_a_permutation_of_sorted_order():
+    p = load_pymgrid25(1)
+    a, b = OracleGrid(p, order=0), OracleGrid(p, order=1)
+    oa, ob = a.observe(), b.observe()
+    rows = 1 + p.forecast_horizon
+    bat, gen, grid, load, pv = np.split(oa, np.cumsum([2, 4, 4 * rows, rows]))
+    np.testing.assert_array_equal(ob, np.concatenate([load, pv, gen, bat, grid]))
