@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched microgrid step on B200 (BASELINE.json metric).
+
+Workload (config.workload): BASELINE configs[2] -- 65 536 microgrids per GPU tiled from all 25 pymgrid25
+scenarios (env i -> scenario i mod 25; three architecture groups fused in one launch), year-rollout style:
+every step reads that step's own pre-generated U[0,1) actions, advances every env one timestep and writes reward,
+done, state and the FULL normalised observation.  A "step" is one pass of the hot path over the whole batch.
+
+  value      whole-job env-steps/s with actions resident in HBM (CUDA events, max over ranks).  Observation
+             buffers rotate through a ring larger than L2 so the stores reach HBM.
+  e2e        the same metric through the public API `BatchedMicrogrid.step` with HOST buffers: per step the
+             actions go pinned-host -> device and reward + done come back device -> pinned-host inside the
+             timed region (observations stay on the device, where a policy consumes them).
+  roofline   HBM: algorithmic bytes per launch (SURVEY.md 8d per-env-step figure x envs) / average launch time
+             measured with CUDA events in this run, against MEASURED_PEAKS.json's copy bandwidth.
+  cpu_baseline  the C oracle port of the reference step (oracle/mg_oracle.c) on this box's host cores, bounded sample.
+
+`--impl reference` times that CPU port alone (the reference itself is pure Python and cannot travel to the GPU
+box; its measured 1e3 steps/s/core is quoted in BASELINE.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 65536
+METRIC = "microgrid env-steps/sec at batch 65536 (pymgrid25)"
+UNIT = "env-steps/s"
+FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def algorithmic_bytes(has_genset, has_grid, horizon, discrete=False):
+    """act + state r/w + reward + done + obs, f64 parity mode, per env-step.  +8 for the per-env
+    step counter (read + write), which this engine keeps per env so that envs need not run in lock-step."""
+    act = 4 if discrete else 8 * (1 + has_grid + 2 * has_genset)
+    state = 2 * (8 + 4 * has_genset) + 8
+    obs_dim = (1 + horizon) * (2 + 4 * has_grid) + 2 + 4 * has_genset
+    return act + state + 8 + 1 + 8 * obs_dim
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def build_engine(batch, device, discrete=False):
+    from pymgrid_b200.engine import BatchedMicrogrid
+    return BatchedMicrogrid.from_pymgrid25(batch, device=device, with_info=False, with_flags=False)
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def cpu_port_rate(n_envs, n_steps, threads, seed=7):
+    """Time the C oracle port on a bounded sample of the same workload (env i -> scenario i mod 25, U[0,1) actions,
+    full normalised observation computed every step).  Returns env-steps/s."""
+    from oracle.oracle import OracleBatch
+    from pymgrid_b200.scenario import load_pymgrid25
+    configs = [load_pymgrid25(n) for n in range(25)]
+    plist = [configs[e % 25] for e in range(n_envs)]
+    actions = np.random.default_rng(seed).random((n_steps, n_envs, 4))
+    ob = OracleBatch(plist)
+    t0 = time.perf_counter()
+    ob.rollout(actions, normalized=True, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return n_envs * n_steps / dt, dt
+
+
+def run_reference(args):
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    n_envs, n_steps = 4096, 128          # one "step" of this arm = 524 288 env-steps of the workload
+    for _ in range(args.warmup):
+        cpu_port_rate(n_envs, 16, threads)
+    total, total_t = 0, 0.0
+    for k in range(args.steps):
+        _, dt = cpu_port_rate(n_envs, n_steps, threads, seed=100 + k)
+        total += n_envs * n_steps
+        total_t += dt
+    value = total / total_t
+    sample = f"{n_envs} envs (25 pymgrid25 scenarios tiled) x {n_steps} steps per bench step, full obs every step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "pymgrid25 scenario parameters + series (bundled), synthetic U[0,1) actions",
+        "config": {"workload": "pymgrid25 tiled, CPU port of Microgrid.run (C oracle), bounded sample", "batch": n_envs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="envs per GPU")
+    ap.add_argument("--ring", type=int, default=4, help="observation buffers rotated so stores reach HBM")
+    ap.add_argument("--path", default="graph", choices=("graph", "eager", "rollout"),
+                    help="headline path: mg_step launches replayed from a CUDA graph, plain launches, or the persistent rollout kernel")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    B, K, W, R = args.batch, args.steps, args.warmup, args.ring
+
+    bm = build_engine(B, dev)
+    groups = bm.groups
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2 + rank)
+    # this step's own actions for every timed / warm-up step, resident in HBM
+    acts = [torch.rand((W + K, g.n_envs, g.n_act), dtype=torch.float64, device=dev, generator=gen) for g in groups]
+    rings = [torch.empty((R, g.n_envs, g.obs_dim), dtype=torch.float64, device=dev) for g in groups]
+    ring_bytes = sum(r.numel() * 8 for r in rings)
+    state0 = bm.state_dict()
+
+    def one_step(s):
+        bm.step([a[s] for a in acts], obs=[r[s % R] for r in rings])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    with torch.cuda.stream(stream):
+        for s in range(W):
+            one_step(s)
+        torch.cuda.synchronize()
+        launch0 = bm.launch_count
+        if args.path == "graph":
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                for s in range(W, W + K):
+                    one_step(s)
+            captured = bm.launch_count - launch0
+            bm.load_state_dict(state0)
+            for s in range(W):
+                one_step(s)
+            barrier()
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            ev0.record(stream)
+            graph.replay()
+            ev1.record(stream)
+            launches = captured
+        elif args.path == "eager":
+            barrier()
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            ev0.record(stream)
+            for s in range(W, W + K):
+                one_step(s)
+            ev1.record(stream)
+            launches = bm.launch_count - launch0
+        else:   # persistent rollout kernel: K steps in one launch
+            warm = [a[:W].contiguous() for a in acts]
+            timed = [a[W:].contiguous() for a in acts]
+            bm.load_state_dict(state0)
+            bm.rollout(warm, ring=R, keep_obs=True)
+            barrier()
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            launch0 = bm.launch_count
+            ev0.record(stream)
+            out = bm.rollout(timed, ring=R, keep_obs=True)
+            ev1.record(stream)
+            launches = bm.launch_count - launch0
+        barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers -------------------------------------------------
+    Ke = min(K, 50)
+    host_acts = [torch.rand((Ke, g.n_envs, g.n_act), dtype=torch.float64).pin_memory() for g in groups]
+    dev_acts = [torch.empty((g.n_envs, g.n_act), dtype=torch.float64, device=dev) for g in groups]
+    host_reward = torch.empty(bm.n_envs, dtype=torch.float64).pin_memory()
+    host_done = torch.empty(bm.n_envs, dtype=torch.uint8).pin_memory()
+    h2d = sum(a[0].numel() * 8 for a in host_acts)
+    d2h = bm.n_envs * 9
+
+    def e2e_step(s):
+        for d, h in zip(dev_acts, host_acts):
+            d.copy_(h[s], non_blocking=True)
+        bm.step(dev_acts, obs=[r[s % R] for r in rings])
+        host_reward.copy_(bm.reward, non_blocking=True)
+        host_done.copy_(bm.done, non_blocking=True)
+
+    bm.load_state_dict(state0)
+    with torch.cuda.stream(stream):
+        for s in range(3):
+            e2e_step(s)
+        barrier()
+        ev0.record(stream)
+        for s in range(Ke):
+            e2e_step(s)
+        ev1.record(stream)
+        barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * Ke / (t.item() * 1e-3)
+
+    if rank == 0:
+        bytes_per_launch = sum(g.n_envs * algorithmic_bytes(*g.arch) for g in groups)
+        peak, peak_src = measured_peak()
+        achieved = bytes_per_launch / (ms * 1e-3 / K) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "pymgrid25 scenario parameters + series (bundled), synthetic U[0,1) actions",
+            "config": {"workload": "configs[2]: 65536 grids/GPU tiled from all 25 pymgrid25 configs, year-rollout style steps with full obs",
+                       "batch_per_gpu": B, "global_batch": world * B, "forecast_horizon": 23, "path": args.path,
+                       "l2": f"obs ring of {R} buffers = {ring_bytes / 1e6:.0f} MB per GPU (> 126 MB L2), fresh actions every step",
+                       "parallelism": f"batch sharded over {world} GPU(s), no collective on the step path"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "note": "actions pinned-host->device and reward+done device->pinned-host every step; obs stay on device"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "mg_step_kernel" if args.path != "rollout" else "mg_rollout_kernel",
+                         "bytes_per_launch": bytes_per_launch},
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            n_envs, n_steps = 4096, 256
+            cpu_port_rate(n_envs, 8, threads)
+            rate, dt = cpu_port_rate(n_envs, n_steps, threads)
+            rate1, _ = cpu_port_rate(512, 256, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{n_envs} envs x {n_steps} steps of the same workload ({dt:.1f} s), C oracle port, full obs",
+                                    "single_core": rate1}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -177,6 +177,9 @@ typedef struct MgHandle MgHandle;
 
 /* library / build identification (also the symbol the loader probes first) */
 int mg_abi_version(void);
+/* sizeof of an ABI struct as compiled (0 MgConfig, 1 MgPriorityList, 2 MgGroup, 3 MgLayout, 4 MgStepIO,
+ * 5 MgRolloutIO): lets a foreign-language binding verify its struct mirror before the first call */
+int64_t mg_sizeof(int which);
 const char *mg_build_info(void);
 const char *mg_last_error(void);
 

@@ -1,0 +1,863 @@
+// mg_engine.cu -- B200 (sm_100a) batched microgrid-step engine: kernels + the C-ABI of include/pymgrid_b200.h.
+//
+// One fused kernel advances every env of every architecture group one timestep
+// (reference: Microgrid.run, src/pymgrid/microgrid/microgrid.py:227-325):
+//   phase 1  one thread per env: gather ts[t], genset state machine + clamp, battery transition, grid
+//            import/export, energy balance -> pv -> unbalanced, reward, done, state write-back;
+//   phase 2  all warps of the CTA emit the normalised observation rows of the tile with coalesced 16-byte
+//            stores; the time-series part of a row is a window [t+1, t+1+H] of pre-normalised, end-padded
+//            tables (built once by mg_create), the battery/genset part comes from shared memory.
+// The same body runs inside a persistent multi-step kernel (mg_rollout) with the env state held in registers.
+//
+// Compiled with -fmad=false: the reference is plain IEEE f64 Python arithmetic with no fused multiply-add, and
+// clip / snap decisions must be bit-identical (tests/test_gpu_parity.py).  The path is HBM-write bound
+// (obs rows are >= 95% of the bytes), not FP64 bound, so this costs nothing measurable.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "pymgrid_b200.h"
+
+#ifndef MG_THREADS
+#define MG_THREADS 256
+#endif
+#ifndef MG_TILE
+#define MG_TILE 64          // envs per CTA tile
+#endif
+#define MG_STR2(x) #x
+#define MG_STR(x) MG_STR2(x)
+#define MG_WARPS (MG_THREADS / 32)
+#define MG_ROWS_PER_WARP (MG_TILE / MG_WARPS)
+
+enum { KIND_BAT = 0, KIND_GEN = 1, KIND_GRID = 2, KIND_LOAD = 3, KIND_PV = 4 };
+enum { MODE_STEP = 0, MODE_DISCRETE = 1, MODE_OBSERVE = 2, MODE_RESET = 3 };
+
+struct DevGroup {
+    int32_t has_genset, has_grid, horizon, n_act, obs_dim, n_envs;
+    int32_t act_col_genset, act_col_battery, act_col_grid;
+    int32_t tile_begin;                 // first CTA of this group in the fused launch
+    int32_t n_seg;
+    int32_t seg_start[5], seg_kind[5];  // observation row layout: segment starts (ascending) and kinds
+    int32_t *step;
+    double *charge;
+    uint32_t *genset;
+    const int32_t *cfg_index, *env_initial, *env_final;
+    // step io
+    const double *actions;
+    const int32_t *dactions;
+    double *obs, *reward, *info;
+    uint8_t *done;
+    uint32_t *flags;
+    const uint8_t *mask;
+    // rollout io
+    double *reward_sum;
+    int64_t act_step_stride, out_step_stride, obs_slot_stride;
+};
+
+struct LaunchParams {
+    int32_t n_groups, total_tiles, T, Tp, mode, normalized, n_steps, ring;
+    const MgConfig *cfg;
+    const double *load_raw, *pv_raw, *grid_raw;
+    const double *load_nrm, *pv_nrm, *grid_nrm;
+    const MgPriorityList *plist;
+    DevGroup g[MG_MAX_GROUPS];
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_global_v2(double *p, double a, double b) {
+    // 16-byte streaming store: observation rows are written once and never re-read by this kernel
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+
+__device__ __forceinline__ bool np_isclose(double a, double b, double rtol, double atol) {
+    return fabs(a - b) <= (atol + rtol * fabs(b));
+}
+
+// genset_module.py:216-227 _reset_up_down_times
+__device__ __forceinline__ void genset_reset_times(int cs, int U, int D, int &up, int &dn) {
+    if (cs) { up = 0; dn = D; }
+    else { dn = 0; up = U; }
+}
+
+// genset_module.py:360-390 next_status
+__device__ __forceinline__ int genset_next_status(int cs, int up, int dn, int goal) {
+    if (goal) return (cs || up == 0) ? 1 : 0;
+    return (!cs || dn == 0) ? 0 : 1;
+}
+
+// genset_module.py:235-346 update_status (+ _finish_in_progress_change, _non_instantaneous_update)
+__device__ __forceinline__ void genset_update_status(int &cs, int &gs, int &up, int &dn, double goal_status, int U,
+                                                     int D, int abort) {
+    const int goal = (int)rint(goal_status);  // Python round(): half to even
+    if (goal == cs && cs == gs) return;
+    const bool instant_up = (U == 0 && goal == 1);
+    const bool instant_down = (D == 0 && goal == 0);
+    if (goal != gs && (abort || instant_up || instant_down)) gs = goal;
+    if (up == 0 && gs == 1) { cs = 1; genset_reset_times(cs, U, D, up, dn); return; }
+    if (dn == 0 && gs == 0) { cs = 0; genset_reset_times(cs, U, D, up, dn); return; }
+    if (goal == cs && cs != gs && abort) {
+        gs = goal;
+        genset_reset_times(cs, U, D, up, dn);
+    } else if (cs == gs && gs != goal) {
+        genset_reset_times(cs, U, D, up, dn);
+        gs = goal;
+    }
+    if (gs != cs) {
+        if (gs == 0) dn -= 1;
+        else up -= 1;
+    }
+}
+
+struct EnvRegs {      // per-env state carried in registers (across steps in the rollout kernel)
+    int32_t t;
+    int32_t cs, gs, up, dn;
+    double charge;
+};
+
+struct RawRow {       // ts[t] of the env's series (reference: *_module.update reading self._time_series[t])
+    double load, pv, imp, exp_, co2, status;
+};
+
+// PriorityListAlgo._populate_action, algos/priority_list/priority_list.py:69-167.
+// Writes the unnormalised control: gen_goal, gen_energy, bat, grid.
+__device__ __forceinline__ void priority_control(const MgPriorityList pl, const MgConfig *__restrict__ c, const DevGroup &G,
+                                                 const EnvRegs &s, const RawRow &raw, double &gen_goal,
+                                                 double &gen_energy, double &bat, double &grid) {
+    gen_goal = 0.0; gen_energy = 0.0; bat = 0.0; grid = 0.0;
+    double total_load = 0.0;
+    total_load += -1 * raw.load;
+    const double renewable = 0.0 + raw.pv;
+    double remaining = total_load - renewable;
+    bool genset_seen = false;
+#pragma unroll
+    for (int i = 0; i < MG_PLIST_WIDTH; ++i) {
+        const int mod = pl.module[i];
+        const int act = pl.action[i];
+        if (i >= pl.n_elements || mod < 0) continue;
+        if (mod == MG_MOD_GENSET) {
+            if (genset_seen) continue;
+            genset_seen = true;
+            gen_goal = (double)act;
+        }
+        double energy;
+        if (np_isclose(remaining, 0.0, 1e-5, 1e-4)) {
+            energy = 0.0;
+        } else if (remaining > 0) {
+            double mx, mn;
+            if (mod == MG_MOD_GENSET) {
+                const int ns = genset_next_status(s.cs, s.up, s.dn, act);
+                mx = ns * c->gen_running_max;
+                mn = ns * c->gen_running_min;
+            } else if (mod == MG_MOD_BATTERY) {
+                mx = fmin(c->bat_max_discharge, s.charge - c->bat_min_capacity) * c->bat_efficiency;
+                mn = 0.0;
+            } else {
+                mx = c->grid_max_import * raw.status;
+                mn = 0.0;
+            }
+            if (mn <= remaining && remaining <= mx) energy = remaining;
+            else if (remaining < mn) energy = mn;
+            else energy = mx;
+        } else {
+            if (mod == MG_MOD_GENSET) energy = 0.0;
+            else {
+                const double mc = (mod == MG_MOD_BATTERY)
+                                      ? fmin(c->bat_max_charge, c->bat_max_capacity - s.charge) / c->bat_efficiency
+                                      : c->grid_max_export * raw.status;
+                if (-1 * remaining > mc) energy = -1.0 * mc;
+                else energy = remaining;
+            }
+        }
+        if (mod == MG_MOD_GENSET) gen_energy = energy;
+        else if (mod == MG_MOD_BATTERY) bat = energy;
+        else grid = energy;
+        remaining -= energy;
+    }
+}
+
+// One Microgrid.run for one env (microgrid.py:227-325; modules as cited inline).  Dispatch order
+// load -> genset -> battery -> grid -> (balance) -> pv -> unbalanced_energy; reward and energy sums accumulate in
+// exactly that order from 0.0 like MicrogridStep (microgrid/utils/step.py:9-36).
+__device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const DevGroup &G, EnvRegs &s, const RawRow &raw,
+                                         double a_goal, double a_gen, double a_bat, double a_grid, bool normalized,
+                                         int final_step, double &reward_out, int &done_out, uint32_t &flags_out,
+                                         double *__restrict__ info) {
+    uint32_t flags = 0;
+    double reward = 0.0, provided = 0.0, consumed = 0.0;
+    const int done = (s.t >= final_step - 1);   // base_timeseries_module.py:124-125, before t += 1
+    double i_gen = 0.0, i_gen_co2 = 0.0, i_dis = 0.0, i_chg = 0.0, i_imp = 0.0, i_exp = 0.0, i_gco2 = 0.0;
+
+    // LoadModule.update, load_module.py:86-91
+    const double load = -1 * raw.load;
+    consumed += load;
+    reward += 0.0;
+
+    if (G.has_genset) {   // GensetModule.step, genset_module.py:100-149, :183-214
+        if (!(0 <= a_goal && a_goal <= 1)) flags |= MG_FLAG_GENSET_GOAL_RANGE;
+        else genset_update_status(s.cs, s.gs, s.up, s.dn, a_goal, c->gen_start_up_time, c->gen_wind_down_time,
+                                  c->gen_allow_abortion);
+        const double a = normalized ? (0.0 + c->gen_act_spread * a_gen) : a_gen;
+        double p;
+        if (a < 0) {
+            flags |= MG_FLAG_GENSET_AS_SINK;
+            p = 0.0;
+        } else {
+            const double mx = s.cs * c->gen_running_max;
+            const double mn = s.cs * c->gen_running_min;
+            if (a > mx) { p = mx; flags |= MG_FLAG_CLIP_GENSET; }      // base_module.py:213-224, upper test first
+            else if (a < mn) { p = mn; flags |= MG_FLAG_CLIP_GENSET; }
+            else p = a;
+        }
+        const double co2 = c->gen_co2_per_unit * p;
+        const double cost = c->gen_cost * p + c->gen_cost_per_unit_co2 * co2;
+        reward += -1.0 * cost;
+        provided += p;
+        i_gen = p;
+        i_gen_co2 = co2;
+    }
+    {   // BatteryModule, battery_module.py:108-130, :244-291
+        const double a = normalized ? (c->bat_act_low + c->bat_act_spread * a_bat) : a_bat;
+        double internal;
+        if (a > 0 || a == 0) {
+            const double mp = fmin(c->bat_max_discharge, s.charge - c->bat_min_capacity) * c->bat_efficiency;
+            double p;
+            if (a > mp) { p = mp; flags |= MG_FLAG_CLIP_BATTERY; }
+            else p = a;
+            internal = (-1.0 * p) / c->bat_efficiency;
+            provided += p;
+            i_dis = p;
+        } else {
+            double e = -1.0 * a;
+            const double mc = fmin(c->bat_max_charge, c->bat_max_capacity - s.charge) / c->bat_efficiency;
+            if (e > mc) { e = mc; flags |= MG_FLAG_CLIP_BATTERY; }
+            if (!(e >= 0)) flags |= MG_FLAG_NEGATIVE_ABSORB;
+            internal = e * c->bat_efficiency;
+            consumed += e;
+            i_chg = e;
+        }
+        s.charge += internal;
+        if (s.charge < c->bat_min_capacity) {
+            if (!np_isclose(s.charge, c->bat_min_capacity, 1e-5, 1e-8)) flags |= MG_FLAG_BATTERY_MIN_CAP;
+            s.charge = c->bat_min_capacity;
+        }
+        reward += -1.0 * (fabs(internal) * c->bat_cost_cycle);
+    }
+    if (G.has_grid) {   // GridModule, grid_module.py:134-228, :314-320
+        const double a = normalized ? (c->grid_act_low + c->grid_act_spread * a_grid) : a_grid;
+        if (a > 0 || a == 0) {
+            const double mp = c->grid_max_import * raw.status;
+            double p;
+            if (a > mp) { p = mp; flags |= MG_FLAG_CLIP_GRID; }
+            else p = a;
+            const double co2 = p * raw.co2;
+            reward += -1 * raw.imp * p + (-1.0 * c->grid_cost_per_unit_co2 * co2);
+            provided += p;
+            i_imp = p;
+            i_gco2 = co2;
+        } else {
+            double e = -1.0 * a;
+            const double mc = c->grid_max_export * raw.status;
+            if (e > mc) { e = mc; flags |= MG_FLAG_CLIP_GRID; }
+            reward += raw.exp_ * e + (-1.0 * c->grid_cost_per_unit_co2 * 0.0);
+            consumed += e;
+            i_exp = e;
+        }
+    }
+    // flex modules: pv then unbalanced_energy, microgrid.py:277-314
+    const double difference = provided - consumed;
+    double pv_used, loss = 0.0, overgen = 0.0;
+    if (difference > 0) {
+        pv_used = 0.0;
+        provided += pv_used;
+        reward += 0.0;
+        overgen = difference;
+        consumed += overgen;
+        reward += -1.0 * (c->overgeneration_cost * overgen);
+    } else {
+        double needed = -difference;
+        pv_used = (raw.pv < needed) ? raw.pv : needed;
+        provided += pv_used;
+        reward += 0.0;
+        needed -= pv_used;
+        loss = needed;
+        provided += needed;
+        reward += -1.0 * (c->loss_load_cost * needed);
+    }
+    if (!np_isclose(provided, consumed, 1e-5, 1e-8)) flags |= MG_FLAG_BALANCE;
+    s.t += 1;
+    reward_out = reward;
+    done_out = done;
+    flags_out = flags;
+    if (info) {
+        info[MG_INFO_LOAD_MET] = load;
+        info[MG_INFO_PV_USED] = pv_used;
+        info[MG_INFO_CURTAILMENT] = raw.pv - pv_used;
+        info[MG_INFO_LOSS_LOAD] = loss;
+        info[MG_INFO_OVERGENERATION] = overgen;
+        info[MG_INFO_GENSET_PRODUCTION] = i_gen;
+        info[MG_INFO_GENSET_CO2] = i_gen_co2;
+        info[MG_INFO_BATTERY_DISCHARGE] = i_dis;
+        info[MG_INFO_BATTERY_CHARGE] = i_chg;
+        info[MG_INFO_GRID_IMPORT] = i_imp;
+        info[MG_INFO_GRID_EXPORT] = i_exp;
+        info[MG_INFO_GRID_CO2] = i_gco2;
+    }
+}
+
+// shared-memory record of one env of the tile, produced by phase 1 and consumed by phase 2
+struct __align__(16) TileEnv {
+    int32_t off_grid, off_load, off_pv, _pad;   // element offsets of the window start in the *_nrm tables
+    double state[6];                            // normalised battery (soc, charge) and genset (cs, gs, up, dn) obs
+};
+
+__device__ __forceinline__ void publish_env(TileEnv &te, const MgConfig *__restrict__ c, const DevGroup &G, const EnvRegs &s,
+                                            int Tp) {
+    // windows start at the NEW step; rows >= T of the tables hold the forecaster's fill value, so a window that
+    // runs past the end of the series needs no branch (forecast/forecaster.py:120-137)
+    te.off_load = c->load_series * Tp + s.t;
+    te.off_pv = c->pv_series * Tp + s.t;
+    te.off_grid = G.has_grid ? (c->grid_series * Tp + s.t) * 4 : 0;
+    // battery_module.py:323-330 + utils/space.py:207-218
+    const double soc = s.charge / c->bat_max_capacity;
+    te.state[0] = (soc - c->bat_soc_low) / c->bat_soc_spread;
+    te.state[1] = (s.charge - c->bat_min_capacity) / c->bat_charge_spread;
+    // genset_module.py:503-509
+    te.state[2] = ((double)s.cs - 0.0) / 1.0;
+    te.state[3] = ((double)s.gs - 0.0) / 1.0;
+    te.state[4] = G.has_genset ? ((double)s.up - 0.0) / c->gen_up_spread : 0.0;
+    te.state[5] = G.has_genset ? ((double)s.dn - 0.0) / c->gen_down_spread : 0.0;
+}
+
+// phase 2: the CTA's warps write rows [0, n_rows) of the tile, 16 bytes per lane per store
+__device__ __forceinline__ void emit_rows(const LaunchParams &P, const DevGroup &G, const TileEnv *__restrict__ tile,
+                                          double *__restrict__ obs_tile, int n_rows) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = G.obs_dim, pairs = D >> 1;
+    for (int p = lane; p < pairs; p += 32) {
+        // decode the two elements of this lane's pair once; the layout is the same for every row
+        int kind[2], off[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 2 * p + h;
+            int sgi = 0;
+#pragma unroll
+            for (int q = 1; q < 5; ++q)
+                if (q < G.n_seg && j >= G.seg_start[q]) sgi = q;
+            kind[h] = G.seg_kind[sgi];
+            off[h] = j - G.seg_start[sgi] + (kind[h] == KIND_GEN ? 2 : 0);
+        }
+        const double *tab[2];
+        int sel[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            tab[h] = kind[h] == KIND_GRID ? P.grid_nrm : kind[h] == KIND_LOAD ? P.load_nrm : P.pv_nrm;
+            sel[h] = kind[h] == KIND_GRID ? 0 : kind[h] == KIND_LOAD ? 1 : 2;
+        }
+#pragma unroll
+        for (int r = 0; r < MG_ROWS_PER_WARP; ++r) {
+            const int i = warp * MG_ROWS_PER_WARP + r;
+            if (i < n_rows) {
+                const TileEnv &te = tile[i];
+                const int32_t *offs = &te.off_grid;
+                double v[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (kind[h] <= KIND_GEN) v[h] = te.state[off[h]];
+                    else v[h] = __ldg(tab[h] + offs[sel[h]] + off[h]);
+                }
+                st_global_v2(obs_tile + (size_t)i * D + 2 * p, v[0], v[1]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ RawRow gather_raw(const LaunchParams &P, const DevGroup &G, const MgConfig *__restrict__ c, int t) {
+    RawRow r;
+    r.load = __ldg(P.load_raw + (size_t)c->load_series * P.T + t);
+    r.pv = __ldg(P.pv_raw + (size_t)c->pv_series * P.T + t);
+    if (G.has_grid) {
+        const double2 *g2 = reinterpret_cast<const double2 *>(P.grid_raw + ((size_t)c->grid_series * P.T + t) * 4);
+        const double2 a = __ldg(g2), b = __ldg(g2 + 1);
+        r.imp = a.x; r.exp_ = a.y; r.co2 = b.x; r.status = b.y;
+    } else {
+        r.imp = r.exp_ = r.co2 = 0.0;
+        r.status = 1.0;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void unpack_genset(uint32_t w, EnvRegs &s) {
+    s.cs = w & 0xff; s.gs = (w >> 8) & 0xff; s.up = (w >> 16) & 0xff; s.dn = (w >> 24) & 0xff;
+}
+__device__ __forceinline__ uint32_t pack_genset(const EnvRegs &s) {
+    return (uint32_t)s.cs | ((uint32_t)s.gs << 8) | ((uint32_t)s.up << 16) | ((uint32_t)s.dn << 24);
+}
+
+__device__ __forceinline__ int find_group(const LaunchParams &P, int tile) {
+    int g = 0;
+#pragma unroll
+    for (int q = 1; q < MG_MAX_GROUPS; ++q)
+        if (q < P.n_groups && tile >= P.g[q].tile_begin) g = q;
+    return g;
+}
+
+// read one env's action row into the four logical controls
+__device__ __forceinline__ void read_action(const DevGroup &G, const double *__restrict__ row, double &a_goal, double &a_gen,
+                                            double &a_bat, double &a_grid) {
+    a_goal = a_gen = a_grid = 0.0;
+    if (G.n_act == 2) {          // [battery, grid] in either order: one 16-byte load
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(row));
+        const double x[2] = {v.x, v.y};
+        a_bat = x[G.act_col_battery];
+        a_grid = x[G.act_col_grid];
+    } else if (G.n_act == 4) {   // two 16-byte loads
+        const double2 v0 = __ldg(reinterpret_cast<const double2 *>(row));
+        const double2 v1 = __ldg(reinterpret_cast<const double2 *>(row) + 1);
+        const double x[4] = {v0.x, v0.y, v1.x, v1.y};
+        a_goal = x[G.act_col_genset];
+        a_gen = x[G.act_col_genset + 1];
+        a_bat = x[G.act_col_battery];
+        a_grid = x[G.act_col_grid];
+    } else {
+        a_bat = __ldg(row + G.act_col_battery);
+        if (G.has_genset) { a_goal = __ldg(row + G.act_col_genset); a_gen = __ldg(row + G.act_col_genset + 1); }
+        if (G.has_grid) a_grid = __ldg(row + G.act_col_grid);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fused single-step kernel: MODE_STEP / MODE_DISCRETE / MODE_OBSERVE / MODE_RESET
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MG_THREADS) mg_step_kernel(const __grid_constant__ LaunchParams P) {
+    __shared__ TileEnv tile[MG_TILE];
+    const int gi = find_group(P, blockIdx.x);
+    const DevGroup &G = P.g[gi];
+    const int e0 = (blockIdx.x - G.tile_begin) * MG_TILE;
+    const int n_rows = min(MG_TILE, G.n_envs - e0);
+    const int i = threadIdx.x;
+    if (i < n_rows) {
+        const int e = e0 + i;
+        const MgConfig *__restrict__ c = P.cfg + __ldg(G.cfg_index + e);
+        EnvRegs s;
+        s.t = G.step[e];
+        s.charge = G.charge[e];
+        s.cs = s.gs = s.up = s.dn = 0;
+        if (G.has_genset) unpack_genset(G.genset[e], s);
+        if (P.mode == MODE_STEP || P.mode == MODE_DISCRETE) {
+            const int final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
+            double reward;
+            int done;
+            uint32_t flags = 0;
+            if (s.t >= P.T) {   // the reference raises IndexError here; state is left untouched
+                reward = __longlong_as_double(0x7ff8000000000000LL);
+                done = 1;
+                flags = MG_FLAG_STEP_PAST_END;
+            } else {
+                const RawRow raw = gather_raw(P, G, c, s.t);
+                double a_goal, a_gen, a_bat, a_grid;
+                bool normalized = P.normalized != 0;
+                bool ok = true;
+                if (P.mode == MODE_DISCRETE) {
+                    const int a = __ldg(G.dactions + e);
+                    normalized = false;
+                    if (a < 0 || a >= c->plist_count) {
+                        ok = false;
+                    } else {
+                        const MgPriorityList pl = P.plist[c->plist_offset + a];
+                        priority_control(pl, c, G, s, raw, a_goal, a_gen, a_bat, a_grid);
+                    }
+                } else {
+                    read_action(G, G.actions + (size_t)e * G.n_act, a_goal, a_gen, a_bat, a_grid);
+                }
+                if (ok) {
+                    env_step(c, G, s, raw, a_goal, a_gen, a_bat, a_grid, normalized, final_step, reward, done, flags,
+                             G.info ? G.info + (size_t)e * MG_N_INFO : nullptr);
+                    G.step[e] = s.t;
+                    G.charge[e] = s.charge;
+                    if (G.has_genset) G.genset[e] = pack_genset(s);
+                } else {
+                    reward = __longlong_as_double(0x7ff8000000000000LL);
+                    done = 0;
+                    flags = MG_FLAG_BAD_ACTION;
+                }
+            }
+            G.reward[e] = reward;
+            G.done[e] = (uint8_t)done;
+            if (G.flags) G.flags[e] = flags;
+        } else if (P.mode == MODE_RESET) {
+            if (!G.mask || G.mask[e]) {   // Microgrid.reset: only the step counter moves (microgrid.py:205-225)
+                s.t = G.env_initial ? __ldg(G.env_initial + e) : c->initial_step;
+                G.step[e] = s.t;
+            }
+        }
+        if (G.obs) {
+            EnvRegs so = s;
+            if (so.t > P.T) so.t = P.T;
+            publish_env(tile[i], c, G, so, P.Tp);
+        }
+    }
+    if (G.obs) {   // CTA-uniform
+        __syncthreads();
+        emit_rows(P, G, tile, G.obs + (size_t)e0 * G.obs_dim, n_rows);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// persistent multi-step kernel: every CTA owns its tile for all n_steps; env state stays in registers
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MG_THREADS) mg_rollout_kernel(const __grid_constant__ LaunchParams P) {
+    __shared__ TileEnv tile[MG_TILE];
+    const int gi = find_group(P, blockIdx.x);
+    const DevGroup &G = P.g[gi];
+    const int e0 = (blockIdx.x - G.tile_begin) * MG_TILE;
+    const int n_rows = min(MG_TILE, G.n_envs - e0);
+    const int i = threadIdx.x;
+    const bool owner = i < n_rows;
+    const int e = e0 + i;
+    const MgConfig *__restrict__ c = P.cfg;
+    EnvRegs s;
+    s.t = 0; s.charge = 0.0; s.cs = s.gs = s.up = s.dn = 0;
+    int final_step = 0;
+    double rsum = 0.0;
+    uint32_t fsum = 0;
+    if (owner) {
+        c = P.cfg + __ldg(G.cfg_index + e);
+        s.t = G.step[e];
+        s.charge = G.charge[e];
+        if (G.has_genset) unpack_genset(G.genset[e], s);
+        final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
+    }
+    for (int step = 0; step < P.n_steps; ++step) {
+        if (owner) {
+            double reward;
+            int done;
+            uint32_t flags = 0;
+            if (s.t >= P.T) {
+                reward = __longlong_as_double(0x7ff8000000000000LL);
+                done = 1;
+                flags = MG_FLAG_STEP_PAST_END;
+            } else {
+                const RawRow raw = gather_raw(P, G, c, s.t);
+                double a_goal, a_gen, a_bat, a_grid;
+                bool normalized = P.normalized != 0;
+                bool ok = true;
+                if (P.mode == MODE_DISCRETE) {
+                    const int a = __ldg(G.dactions + (size_t)step * G.out_step_stride + e);
+                    normalized = false;
+                    if (a < 0 || a >= c->plist_count) ok = false;
+                    else priority_control(P.plist[c->plist_offset + a], c, G, s, raw, a_goal, a_gen, a_bat, a_grid);
+                } else {
+                    read_action(G, G.actions + (size_t)step * G.act_step_stride + (size_t)e * G.n_act, a_goal, a_gen,
+                                a_bat, a_grid);
+                }
+                if (ok) {
+                    env_step(c, G, s, raw, a_goal, a_gen, a_bat, a_grid, normalized, final_step, reward, done, flags,
+                             nullptr);
+                } else {
+                    reward = __longlong_as_double(0x7ff8000000000000LL);
+                    done = 0;
+                    flags = MG_FLAG_BAD_ACTION;
+                }
+            }
+            G.reward[(size_t)step * G.out_step_stride + e] = reward;
+            G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)done;
+            rsum += reward;
+            fsum |= flags;
+            if (G.obs) {
+                EnvRegs so = s;
+                if (so.t > P.T) so.t = P.T;
+                publish_env(tile[i], c, G, so, P.Tp);
+            }
+        }
+        if (G.obs) {
+            __syncthreads();
+            emit_rows(P, G, tile, G.obs + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim, n_rows);
+            __syncthreads();
+        }
+    }
+    if (owner) {
+        G.step[e] = s.t;
+        G.charge[e] = s.charge;
+        if (G.has_genset) G.genset[e] = pack_genset(s);
+        if (G.reward_sum) G.reward_sum[e] = rsum;
+        if (G.flags) G.flags[e] = fsum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// table construction (mg_create): bounds + normalised, end-padded observation tables
+//   load / pv : low = min(ts), high = max(ts), pulled to include 0 (base_timeseries_module.py:81-88)
+//   grid cols : per-column min / max                               (grid_module.py:125-132)
+//   value     : (ts - low) / spread, spread 0 -> 1                 (utils/space.py:204-218)
+//   rows >= T : the forecaster's fill (high + low) / 2, clipped    (forecast/forecaster.py:95, 120-149)
+// one CTA per series column
+// ------------------------------------------------------------------------------------------------------------------
+struct TableParams {
+    int32_t T, Tp, n_load, n_pv, n_grid;
+    const double *load_raw, *pv_raw, *grid_raw;
+    double *load_nrm, *pv_nrm, *grid_nrm, *bounds;
+};
+
+__global__ void __launch_bounds__(256) mg_build_tables_kernel(const TableParams P) {
+    __shared__ double s_min[256], s_max[256];
+    const int col = blockIdx.x;
+    const double *src;
+    double *dst;
+    int stride;
+    bool pull_zero;
+    if (col < P.n_load) {
+        src = P.load_raw + (size_t)col * P.T; dst = P.load_nrm + (size_t)col * P.Tp; stride = 1; pull_zero = true;
+    } else if (col < P.n_load + P.n_pv) {
+        const int k = col - P.n_load;
+        src = P.pv_raw + (size_t)k * P.T; dst = P.pv_nrm + (size_t)k * P.Tp; stride = 1; pull_zero = true;
+    } else {
+        const int k = col - P.n_load - P.n_pv;
+        src = P.grid_raw + (size_t)(k >> 2) * P.T * 4 + (k & 3);
+        dst = P.grid_nrm + (size_t)(k >> 2) * P.Tp * 4 + (k & 3);
+        stride = 4; pull_zero = false;
+    }
+    double mn = src[0], mx = src[0];
+    for (int r = threadIdx.x; r < P.T; r += blockDim.x) {
+        const double v = src[(size_t)r * stride];
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+    }
+    s_min[threadIdx.x] = mn;
+    s_max[threadIdx.x] = mx;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+            s_min[threadIdx.x] = fmin(s_min[threadIdx.x], s_min[threadIdx.x + w]);
+            s_max[threadIdx.x] = fmax(s_max[threadIdx.x], s_max[threadIdx.x + w]);
+        }
+        __syncthreads();
+    }
+    double low = s_min[0], high = s_max[0];
+    if (pull_zero) {
+        if (low > 0) low = 0;
+        else if (high < 0) high = 0;
+    }
+    double spread = high - low;
+    if (spread == 0.0) spread = 1.0;
+    double fill = (high + low) / 2;
+    if (fill < low) fill = low;
+    if (fill > high) fill = high;
+    for (int r = threadIdx.x; r < P.Tp; r += blockDim.x) {
+        const double v = r < P.T ? src[(size_t)r * stride] : fill;
+        dst[(size_t)r * stride] = (v - low) / spread;
+    }
+    if (threadIdx.x == 0 && P.bounds) {
+        P.bounds[2 * col] = low;
+        P.bounds[2 * col + 1] = high;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side: the C-ABI
+// ------------------------------------------------------------------------------------------------------------------
+struct MgHandle {
+    MgLayout layout;
+    LaunchParams base;      // groups + tables, io fields cleared
+    int64_t launches;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof g_err, fmt, detail);
+    return code;
+}
+
+static int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    return MG_E_CUDA;
+}
+
+extern "C" int mg_abi_version(void) { return MG_ABI_VERSION; }
+
+extern "C" int64_t mg_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(MgConfig);
+        case 1: return sizeof(MgPriorityList);
+        case 2: return sizeof(MgGroup);
+        case 3: return sizeof(MgLayout);
+        case 4: return sizeof(MgStepIO);
+        case 5: return sizeof(MgRolloutIO);
+        default: return -1;
+    }
+}
+
+extern "C" const char *mg_build_info(void) {
+    return "pymgrid_b200 engine, sm_100a, f64, -fmad=false, tile=" MG_STR(MG_TILE) " threads=" MG_STR(MG_THREADS);
+}
+
+extern "C" const char *mg_last_error(void) { return g_err; }
+
+static void layout_segments(const MgGroup &g, DevGroup &d) {
+    const int rows = 1 + g.horizon;
+    int n = 0;
+    int kinds[5], lens[5];
+    if (g.obs_order == MG_OBS_GYM_SORTED) {
+        kinds[n] = KIND_BAT; lens[n++] = 2;
+        if (g.has_genset) { kinds[n] = KIND_GEN; lens[n++] = 4; }
+        if (g.has_grid) { kinds[n] = KIND_GRID; lens[n++] = 4 * rows; }
+        kinds[n] = KIND_LOAD; lens[n++] = rows;
+        kinds[n] = KIND_PV; lens[n++] = rows;
+    } else {
+        kinds[n] = KIND_LOAD; lens[n++] = rows;
+        kinds[n] = KIND_PV; lens[n++] = rows;
+        if (g.has_genset) { kinds[n] = KIND_GEN; lens[n++] = 4; }
+        kinds[n] = KIND_BAT; lens[n++] = 2;
+        if (g.has_grid) { kinds[n] = KIND_GRID; lens[n++] = 4 * rows; }
+    }
+    int start = 0;
+    for (int k = 0; k < 5; ++k) {
+        d.seg_start[k] = k < n ? start : 0x7fffffff;
+        d.seg_kind[k] = k < n ? kinds[k] : KIND_PV;
+        if (k < n) start += lens[k];
+    }
+    d.n_seg = n;
+}
+
+extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
+    if (!L || !out) return fail(MG_E_INVALID, "mg_create: null argument");
+    if (L->abi_version != MG_ABI_VERSION) return fail(MG_E_INVALID, "mg_create: abi_version mismatch");
+    if (L->n_groups < 1 || L->n_groups > MG_MAX_GROUPS) return fail(MG_E_INVALID, "mg_create: n_groups out of range");
+    if (L->series_len < 1 || L->max_horizon < 0 || L->n_cfg < 1 || L->n_load < 1 || L->n_pv < 1 || L->n_grid < 0)
+        return fail(MG_E_INVALID, "mg_create: bad table sizes");
+    if (!L->cfg || !L->load_raw || !L->pv_raw || !L->load_nrm || !L->pv_nrm || (L->n_grid > 0 && (!L->grid_raw || !L->grid_nrm)))
+        return fail(MG_E_INVALID, "mg_create: null table pointer");
+    const int64_t Tp = (int64_t)L->series_len + L->max_horizon + 1;
+    if ((int64_t)L->n_load * Tp >= (1ll << 31) || (int64_t)L->n_pv * Tp >= (1ll << 31) || (int64_t)L->n_grid * Tp * 4 >= (1ll << 31))
+        return fail(MG_E_UNSUPPORTED, "mg_create: series tables exceed 2^31 elements");
+    MgHandle *h = new (std::nothrow) MgHandle();
+    if (!h) return fail(MG_E_INVALID, "mg_create: out of host memory");
+    h->layout = *L;
+    h->launches = 0;
+    LaunchParams &B = h->base;
+    memset(&B, 0, sizeof B);
+    B.n_groups = L->n_groups;
+    B.T = L->series_len;
+    B.Tp = (int32_t)Tp;
+    B.cfg = L->cfg;
+    B.load_raw = L->load_raw; B.pv_raw = L->pv_raw; B.grid_raw = L->grid_raw;
+    B.load_nrm = L->load_nrm; B.pv_nrm = L->pv_nrm; B.grid_nrm = L->grid_nrm;
+    B.plist = L->plist;
+    int tiles = 0;
+    for (int gidx = 0; gidx < L->n_groups; ++gidx) {
+        const MgGroup &g = L->groups[gidx];
+        DevGroup &d = B.g[gidx];
+        if (g.n_envs < 1 || g.n_envs >= (1ll << 31) - MG_TILE) { delete h; return fail(MG_E_INVALID, "mg_create: group n_envs out of range"); }
+        if (g.horizon < 0 || g.horizon > L->max_horizon) { delete h; return fail(MG_E_INVALID, "mg_create: group horizon exceeds max_horizon"); }
+        const int rows = 1 + g.horizon;
+        const int n_act = 1 + (g.has_grid != 0) + 2 * (g.has_genset != 0);
+        const int obs_dim = rows * (2 + 4 * (g.has_grid != 0)) + 2 + 4 * (g.has_genset != 0);
+        if (g.n_act != n_act || g.obs_dim != obs_dim) { delete h; return fail(MG_E_INVALID, "mg_create: n_act / obs_dim do not match the architecture"); }
+        if (!g.step || !g.charge || !g.cfg_index || (g.has_genset && !g.genset)) { delete h; return fail(MG_E_INVALID, "mg_create: null state pointer"); }
+        if (g.has_grid && L->n_grid < 1) { delete h; return fail(MG_E_INVALID, "mg_create: grid group without grid series"); }
+        if (g.obs_order != MG_OBS_GYM_SORTED && g.obs_order != MG_OBS_CONTAINER) { delete h; return fail(MG_E_INVALID, "mg_create: bad obs_order"); }
+        d.has_genset = g.has_genset != 0; d.has_grid = g.has_grid != 0; d.horizon = g.horizon;
+        d.n_act = n_act; d.obs_dim = obs_dim; d.n_envs = (int32_t)g.n_envs;
+        d.act_col_genset = g.act_col_genset; d.act_col_battery = g.act_col_battery; d.act_col_grid = g.act_col_grid;
+        d.tile_begin = tiles;
+        tiles += (int)((g.n_envs + MG_TILE - 1) / MG_TILE);
+        layout_segments(g, d);
+        d.step = g.step; d.charge = g.charge; d.genset = g.genset; d.cfg_index = g.cfg_index;
+        d.env_initial = g.env_initial_step; d.env_final = g.env_final_step;
+    }
+    B.total_tiles = tiles;
+    // normalised tables + bounds
+    TableParams tp;
+    tp.T = L->series_len; tp.Tp = (int32_t)Tp; tp.n_load = L->n_load; tp.n_pv = L->n_pv; tp.n_grid = L->n_grid;
+    tp.load_raw = L->load_raw; tp.pv_raw = L->pv_raw; tp.grid_raw = L->grid_raw;
+    tp.load_nrm = L->load_nrm; tp.pv_nrm = L->pv_nrm; tp.grid_nrm = L->grid_nrm; tp.bounds = L->bounds;
+    const int cols = L->n_load + L->n_pv + 4 * L->n_grid;
+    mg_build_tables_kernel<<<cols, 256, 0, (cudaStream_t)stream>>>(tp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "mg_create: table kernel launch"); }
+    h->launches += 1;
+    *out = h;
+    return MG_OK;
+}
+
+extern "C" int mg_destroy(MgHandle *h) {
+    delete h;
+    return MG_OK;
+}
+
+extern "C" int64_t mg_launch_count(const MgHandle *h) { return h ? h->launches : 0; }
+
+static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized, void *stream) {
+    if (!h || !io) return fail(MG_E_INVALID, "step: null argument");
+    LaunchParams P = h->base;
+    P.mode = mode;
+    P.normalized = normalized;
+    for (int g = 0; g < P.n_groups; ++g) {
+        DevGroup &d = P.g[g];
+        d.actions = io[g].actions; d.dactions = io[g].dactions; d.obs = io[g].obs; d.reward = io[g].reward;
+        d.done = io[g].done; d.info = io[g].info; d.flags = io[g].flags; d.mask = io[g].mask;
+        if (mode == MODE_STEP && !d.actions) return fail(MG_E_INVALID, "mg_step: null actions");
+        if (mode == MODE_DISCRETE && (!d.dactions || !P.plist)) return fail(MG_E_INVALID, "mg_step_discrete: null actions or priority lists");
+        if ((mode == MODE_STEP || mode == MODE_DISCRETE) && (!d.reward || !d.done)) return fail(MG_E_INVALID, "step: null reward / done");
+        if ((mode == MODE_OBSERVE) && !d.obs) return fail(MG_E_INVALID, "mg_observe: null obs");
+        if (d.obs && (((uintptr_t)d.obs) & 15)) return fail(MG_E_INVALID, "step: obs must be 16-byte aligned");
+        if (d.actions && (d.n_act == 2 || d.n_act == 4) && (((uintptr_t)d.actions) & 15))
+            return fail(MG_E_INVALID, "step: actions must be 16-byte aligned");
+    }
+    mg_step_kernel<<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "step kernel launch");
+    h->launches += 1;
+    return MG_OK;
+}
+
+extern "C" int mg_step(MgHandle *h, const MgStepIO *io, int normalized, void *stream) {
+    return launch_step(h, io, MODE_STEP, normalized != 0, stream);
+}
+extern "C" int mg_step_discrete(MgHandle *h, const MgStepIO *io, void *stream) {
+    return launch_step(h, io, MODE_DISCRETE, 0, stream);
+}
+extern "C" int mg_reset(MgHandle *h, const MgStepIO *io, void *stream) { return launch_step(h, io, MODE_RESET, 0, stream); }
+extern "C" int mg_observe(MgHandle *h, const MgStepIO *io, void *stream) { return launch_step(h, io, MODE_OBSERVE, 0, stream); }
+
+static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, int mode, int normalized,
+                          void *stream) {
+    if (!h || !io) return fail(MG_E_INVALID, "rollout: null argument");
+    if (n_steps < 1 || ring < 1) return fail(MG_E_INVALID, "rollout: n_steps and ring must be >= 1");
+    LaunchParams P = h->base;
+    P.mode = mode;
+    P.normalized = normalized;
+    P.n_steps = n_steps;
+    P.ring = ring;
+    for (int g = 0; g < P.n_groups; ++g) {
+        DevGroup &d = P.g[g];
+        d.actions = io[g].actions; d.dactions = io[g].dactions; d.obs = io[g].obs_ring; d.reward = io[g].reward;
+        d.done = io[g].done; d.reward_sum = io[g].reward_sum; d.flags = io[g].flags; d.info = nullptr; d.mask = nullptr;
+        d.act_step_stride = (int64_t)d.n_envs * d.n_act;
+        d.out_step_stride = d.n_envs;
+        d.obs_slot_stride = (int64_t)d.n_envs * d.obs_dim;
+        if (mode == MODE_STEP && !d.actions) return fail(MG_E_INVALID, "mg_rollout: null actions");
+        if (mode == MODE_DISCRETE && (!d.dactions || !P.plist)) return fail(MG_E_INVALID, "mg_rollout_discrete: null actions or priority lists");
+        if (!d.reward || !d.done) return fail(MG_E_INVALID, "rollout: null reward / done");
+        if (d.obs && (((uintptr_t)d.obs) & 15)) return fail(MG_E_INVALID, "rollout: obs_ring must be 16-byte aligned");
+        if (d.actions && (d.n_act == 2 || d.n_act == 4) && ((((uintptr_t)d.actions) & 15) || ((d.act_step_stride * 8) & 15)))
+            return fail(MG_E_INVALID, "rollout: action rows must stay 16-byte aligned across steps");
+    }
+    mg_rollout_kernel<<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "rollout kernel launch");
+    h->launches += 1;
+    return MG_OK;
+}
+
+extern "C" int mg_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, int normalized, void *stream) {
+    return launch_rollout(h, io, n_steps, ring, MODE_STEP, normalized != 0, stream);
+}
+extern "C" int mg_rollout_discrete(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, void *stream) {
+    return launch_rollout(h, io, n_steps, ring, MODE_DISCRETE, 0, stream);
+}

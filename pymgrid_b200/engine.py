@@ -1,0 +1,410 @@
+"""BatchedMicrogrid: the Python host of the B200 engine.
+
+Holds per-module parameters and the load / PV / grid time series as torch DEVICE tensors, groups the envs by
+architecture (has_genset, has_grid, forecast_horizon), and calls the hand-written sm_100a kernels through the
+C-ABI of include/pymgrid_b200.h.  It is the batched counterpart of the reference's `Microgrid`
+(src/pymgrid/microgrid/microgrid.py): `step` = `Microgrid.run` / `BaseMicrogridEnv.step` for B envs at once,
+`step_discrete` = `DiscreteMicrogridEnv.step`, `reset` = `Microgrid.reset`.
+
+torch is plumbing here (device memory, streams); every number is produced by the CUDA extension.  There is no
+CPU path: constructing a BatchedMicrogrid without a CUDA device or without the built extension raises.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import (MG_ABI_VERSION, MG_MAX_GROUPS, MG_N_INFO, MG_OBS_CONTAINER, MG_OBS_GYM_SORTED, EngineError,
+                    MgConfig, MgGroup, MgLayout, MgPriorityList, MgRolloutIO, MgStepIO)
+from .params import MicrogridParams
+from .priority_list import priority_lists
+
+OBS_ORDERS = {"gym_sorted": MG_OBS_GYM_SORTED, "container": MG_OBS_CONTAINER}
+
+
+def _spread(low, high):
+    s = high - low                      # utils/space.py:204-205
+    return 1.0 if s == 0 else s
+
+
+def config_record(p: MicrogridParams, load_series, pv_series, grid_series, plist_offset, plist_count):
+    """MgConfig of one parameter set; derived constants computed in f64 exactly as the reference's ModuleSpace does."""
+    c = MgConfig()
+    b = p.battery
+    c.bat_min_capacity, c.bat_max_capacity = b.min_capacity, b.max_capacity
+    c.bat_max_charge, c.bat_max_discharge = b.max_charge, b.max_discharge
+    c.bat_efficiency, c.bat_cost_cycle = b.efficiency, b.battery_cost_cycle
+    lo, hi = -b.max_discharge / b.efficiency, b.max_charge * b.efficiency
+    c.bat_act_low, c.bat_act_spread = lo, _spread(lo, hi)
+    min_soc = b.min_capacity / b.max_capacity
+    c.bat_soc_low, c.bat_soc_spread = min_soc, _spread(min_soc, 1.0)
+    c.bat_charge_spread = _spread(float(b.min_capacity), float(b.max_capacity))
+    if p.genset is not None:
+        g = p.genset
+        if not (0 <= g.start_up_time <= 255 and 0 <= g.wind_down_time <= 255):
+            raise ValueError("genset start_up_time / wind_down_time must fit in 8 bits")
+        c.gen_running_min, c.gen_running_max, c.gen_cost = g.running_min_production, g.running_max_production, g.genset_cost
+        c.gen_co2_per_unit, c.gen_cost_per_unit_co2 = g.co2_per_unit, g.cost_per_unit_co2
+        c.gen_act_spread = _spread(0.0, float(g.running_max_production))
+        c.gen_up_spread, c.gen_down_spread = _spread(0.0, float(g.start_up_time)), _spread(0.0, float(g.wind_down_time))
+        c.gen_start_up_time, c.gen_wind_down_time, c.gen_allow_abortion = g.start_up_time, g.wind_down_time, int(g.allow_abortion)
+    else:
+        c.gen_act_spread = c.gen_up_spread = c.gen_down_spread = 1.0
+    if p.grid is not None:
+        g = p.grid
+        c.grid_max_import, c.grid_max_export, c.grid_cost_per_unit_co2 = g.max_import, g.max_export, g.cost_per_unit_co2
+        glo = -1 * g.max_export
+        c.grid_act_low, c.grid_act_spread = glo, _spread(glo, float(g.max_import))
+    else:
+        c.grid_act_spread = 1.0
+    c.loss_load_cost, c.overgeneration_cost = p.loss_load_cost, p.overgeneration_cost
+    c.load_scale = c.pv_scale = 1.0
+    c.load_series, c.pv_series, c.grid_series = load_series, pv_series, grid_series
+    c.initial_step, c.final_step = p.initial_step, p.final_step
+    c.plist_offset, c.plist_count = plist_offset, plist_count
+    return c
+
+
+@dataclass
+class Group:
+    """One architecture group: envs sharing the observation / action row layout."""
+    arch: tuple                    # (has_genset, has_grid, horizon)
+    env_ids: np.ndarray            # global env ids, in slot order
+    n_act: int
+    obs_dim: int
+    act_cols: dict                 # module name -> first column of the action row
+    step: torch.Tensor = None      # int32 [n]
+    charge: torch.Tensor = None    # f64 [n]
+    genset: torch.Tensor = None    # int32 [n] (packed cs | gs<<8 | up<<16 | dn<<24) or None
+    cfg_index: torch.Tensor = None
+    env_initial_step: Optional[torch.Tensor] = None
+    env_final_step: Optional[torch.Tensor] = None
+    obs: torch.Tensor = None       # f64 [n, obs_dim] default output buffer
+    reward: torch.Tensor = None
+    done: torch.Tensor = None
+    info: Optional[torch.Tensor] = None
+    flags: Optional[torch.Tensor] = None
+    n_actions: int = 0             # discrete action-space size (max over the group's configs)
+
+    @property
+    def n_envs(self):
+        return len(self.env_ids)
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class BatchedMicrogrid:
+    def __init__(self, configs: Sequence[MicrogridParams], env_config, device=None, obs_order="gym_sorted",
+                 with_info=False, with_flags=True, remove_redundant_gensets=True, action_order=None):
+        """configs: distinct parameter sets; env_config[i] = index of env i's parameter set."""
+        if not torch.cuda.is_available():
+            raise EngineError("BatchedMicrogrid needs a CUDA device: there is no CPU path")
+        self._lib = _cabi.lib()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.obs_order = obs_order
+        self.configs = list(configs)
+        env_config = np.asarray(env_config, dtype=np.int64)
+        if env_config.ndim != 1 or len(env_config) == 0 or env_config.min() < 0 or env_config.max() >= len(self.configs):
+            raise ValueError("env_config must be a non-empty 1-D array of indices into configs")
+        self.n_envs = len(env_config)
+        self.env_config = env_config
+        T = len(self.configs[0])
+        if any(len(p) != T for p in self.configs):
+            raise ValueError("all configs must have time series of the same length")
+        self.series_len = T
+        dev, f64 = self.device, torch.float64
+
+        # ---- series tables (deduplicated by content) -------------------------------------------------------
+        def table(rows, width):
+            keys, index, uniq = {}, [], []
+            for r in rows:
+                if r is None:
+                    index.append(0)
+                    continue
+                k = r.tobytes()
+                if k not in keys:
+                    keys[k] = len(uniq)
+                    uniq.append(r)
+                index.append(keys[k])
+            arr = np.stack(uniq) if uniq else np.zeros((0, T) + ((width,) if width > 1 else ()))
+            return arr, index
+        load_np, load_idx = table([p.load_ts for p in self.configs], 1)
+        pv_np, pv_idx = table([p.pv_ts for p in self.configs], 1)
+        grid_np, grid_idx = table([p.grid.time_series if p.grid is not None else None for p in self.configs], 4)
+        self.max_horizon = max(p.forecast_horizon for p in self.configs)
+        Tp = T + self.max_horizon + 1
+        self.load_raw = torch.from_numpy(load_np).to(dev)
+        self.pv_raw = torch.from_numpy(pv_np).to(dev)
+        self.grid_raw = torch.from_numpy(grid_np).to(dev) if len(grid_np) else None
+        self.load_nrm = torch.empty((len(load_np), Tp), dtype=f64, device=dev)
+        self.pv_nrm = torch.empty((len(pv_np), Tp), dtype=f64, device=dev)
+        self.grid_nrm = torch.empty((len(grid_np), Tp, 4), dtype=f64, device=dev) if len(grid_np) else None
+        self.bounds = torch.empty((len(load_np) + len(pv_np) + 4 * len(grid_np), 2), dtype=f64, device=dev)
+
+        # ---- priority lists + config records ---------------------------------------------------------------
+        plist_rows, plist_key, cfg_recs = [], {}, []
+        self.action_tables = []
+        for k, p in enumerate(self.configs):
+            pls = priority_lists(p.has_genset, p.has_grid,
+                                 p.genset.running_min_production if p.genset is not None else None,
+                                 remove_redundant_gensets)
+            self.action_tables.append(pls)
+            key = tuple(pls)
+            if key not in plist_key:
+                plist_key[key] = len(plist_rows)
+                for pl in pls:
+                    rec = MgPriorityList()
+                    for j in range(_cabi.MG_PLIST_WIDTH):
+                        rec.module[j], rec.action[j] = (pl[j] if j < len(pl) else (_cabi.MG_MOD_NONE, 0))
+                    rec.n_elements = len(pl)
+                    plist_rows.append(rec)
+            cfg_recs.append(config_record(p, load_idx[k], pv_idx[k], grid_idx[k], plist_key[key], len(pls)))
+        cfg_arr = (MgConfig * len(cfg_recs))(*cfg_recs)
+        self.cfg = torch.frombuffer(bytearray(bytes(cfg_arr)), dtype=torch.uint8).to(dev)
+        pl_arr = (MgPriorityList * len(plist_rows))(*plist_rows)
+        self.plist = torch.frombuffer(bytearray(bytes(pl_arr)), dtype=torch.uint8).to(dev)
+
+        # ---- architecture groups ----------------------------------------------------------------------------
+        archs = [p.arch for p in self.configs]
+        order = []
+        for a in (archs[c] for c in env_config):
+            if a not in order:
+                order.append(a)
+        if len(order) > MG_MAX_GROUPS:
+            raise ValueError(f"more than {MG_MAX_GROUPS} architecture groups")
+        env_arch = np.array([order.index(archs[c]) for c in env_config])
+        self.env_group = env_arch
+        self.env_slot = np.empty(self.n_envs, dtype=np.int64)
+        self.groups: List[Group] = []
+        self.reward = torch.zeros(self.n_envs, dtype=f64, device=dev)       # group-major flat buffers
+        self.done = torch.zeros(self.n_envs, dtype=torch.uint8, device=dev)
+        start = 0
+        for gi, arch in enumerate(order):
+            ids = np.nonzero(env_arch == gi)[0]
+            self.env_slot[ids] = np.arange(len(ids))
+            has_genset, has_grid, H = arch
+            n_act = 1 + has_grid + 2 * has_genset
+            obs_dim = (1 + H) * (2 + 4 * has_grid) + 2 + 4 * has_genset
+            names = [m for m, present in (("genset", has_genset), ("battery", 1), ("grid", has_grid)) if present]
+            if action_order is None:
+                act_names = sorted(names) if obs_order == "gym_sorted" else names
+            else:
+                act_names = [m for m in action_order if m in names]
+            cols, col = {}, 0
+            for m in act_names:
+                cols[m] = col
+                col += 2 if m == "genset" else 1
+            cfg_ids = env_config[ids]
+            g = Group(arch=arch, env_ids=ids, n_act=n_act, obs_dim=obs_dim, act_cols=cols)
+            g.cfg_index = torch.from_numpy(cfg_ids.astype(np.int32)).to(dev)
+            g.step = torch.tensor([self.configs[c].current_step for c in cfg_ids], dtype=torch.int32, device=dev)
+            g.charge = torch.tensor([self.configs[c].battery.current_charge for c in cfg_ids], dtype=f64, device=dev)
+            if has_genset:
+                packed = [(s.current_status | (s.goal_status << 8) | (s.steps_until_up << 16) | (s.steps_until_down << 24))
+                          for s in (self.configs[c].genset for c in cfg_ids)]
+                g.genset = torch.tensor(packed, dtype=torch.int32, device=dev)
+            g.obs = torch.empty((len(ids), obs_dim), dtype=f64, device=dev)
+            g.reward = self.reward[start:start + len(ids)]
+            g.done = self.done[start:start + len(ids)]
+            g.info = torch.zeros((len(ids), MG_N_INFO), dtype=f64, device=dev) if with_info else None
+            g.flags = torch.zeros(len(ids), dtype=torch.int32, device=dev) if with_flags else None
+            g.n_actions = max(len(self.action_tables[c]) for c in set(cfg_ids.tolist()))
+            self.groups.append(g)
+            start += len(ids)
+        self._handle = None
+        self._create()
+
+    # ------------------------------------------------------------------------------------------------------
+    def _layout(self):
+        L = MgLayout()
+        L.abi_version, L.n_groups = MG_ABI_VERSION, len(self.groups)
+        for gi, g in enumerate(self.groups):
+            m = L.groups[gi]
+            m.has_genset, m.has_grid, m.horizon = g.arch
+            m.obs_order = OBS_ORDERS[self.obs_order]
+            m.n_act, m.obs_dim, m.n_envs = g.n_act, g.obs_dim, g.n_envs
+            m.act_col_genset = g.act_cols.get("genset", 0)
+            m.act_col_battery = g.act_cols["battery"]
+            m.act_col_grid = g.act_cols.get("grid", 0)
+            m.step, m.charge, m.genset, m.cfg_index = _ptr(g.step), _ptr(g.charge), _ptr(g.genset), _ptr(g.cfg_index)
+            m.env_initial_step, m.env_final_step = _ptr(g.env_initial_step), _ptr(g.env_final_step)
+        L.n_cfg, L.series_len, L.max_horizon = len(self.configs), self.series_len, self.max_horizon
+        L.n_load, L.n_pv = self.load_raw.shape[0], self.pv_raw.shape[0]
+        L.n_grid = 0 if self.grid_raw is None else self.grid_raw.shape[0]
+        L.cfg, L.load_raw, L.pv_raw, L.grid_raw = _ptr(self.cfg), _ptr(self.load_raw), _ptr(self.pv_raw), _ptr(self.grid_raw)
+        L.load_nrm, L.pv_nrm, L.grid_nrm, L.bounds = _ptr(self.load_nrm), _ptr(self.pv_nrm), _ptr(self.grid_nrm), _ptr(self.bounds)
+        L.plist, L.n_plist = _ptr(self.plist), self.plist.numel() // C.sizeof(MgPriorityList)
+        return L
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _create(self):
+        if self._handle is not None:
+            self._lib.mg_destroy(self._handle)
+            self._handle = None
+        L = self._layout()
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.mg_create(C.byref(L), self._stream(), C.byref(h)), "mg_create")
+        self._handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None:
+                self._lib.mg_destroy(self._handle)
+        except Exception:
+            pass
+
+    def set_trajectories(self, initial_step, final_step):
+        """Per-env episode windows (reference: microgrid/trajectory/*, Microgrid._set_trajectory microgrid.py:221-225)."""
+        initial_step = np.asarray(initial_step, dtype=np.int32)
+        final_step = np.asarray(final_step, dtype=np.int32)
+        for g in self.groups:
+            g.env_initial_step = torch.from_numpy(initial_step[g.env_ids]).to(self.device)
+            g.env_final_step = torch.from_numpy(final_step[g.env_ids]).to(self.device)
+        self._create()
+
+    # ------------------------------------------------------------------------------------------------------
+    @property
+    def single_group(self):
+        return len(self.groups) == 1
+
+    def _per_group(self, x, name):
+        if x is None:
+            return [None] * len(self.groups)
+        if isinstance(x, torch.Tensor):
+            if not self.single_group:
+                raise ValueError(f"{name}: pass one tensor per architecture group ({len(self.groups)} groups)")
+            return [x]
+        if len(x) != len(self.groups):
+            raise ValueError(f"{name}: expected {len(self.groups)} per-group tensors")
+        return list(x)
+
+    def _io(self, actions=None, dactions=None, obs=True, mask=None):
+        io = (MgStepIO * len(self.groups))()
+        acts = self._per_group(actions, "actions")
+        dacts = self._per_group(dactions, "actions")
+        masks = self._per_group(mask, "mask")
+        obs_bufs = [g.obs for g in self.groups] if obs is True else self._per_group(obs, "obs") if obs is not False else [None] * len(self.groups)
+        for gi, g in enumerate(self.groups):
+            a, d, m, o = acts[gi], dacts[gi], masks[gi], obs_bufs[gi]
+            if a is not None:
+                if a.dtype != torch.float64 or a.shape != (g.n_envs, g.n_act) or not a.is_contiguous() or a.device != self.device:
+                    raise ValueError(f"group {gi}: actions must be a contiguous float64 [{g.n_envs}, {g.n_act}] tensor on {self.device}")
+            if d is not None:
+                if d.dtype != torch.int32 or d.shape != (g.n_envs,) or not d.is_contiguous() or d.device != self.device:
+                    raise ValueError(f"group {gi}: discrete actions must be a contiguous int32 [{g.n_envs}] tensor on {self.device}")
+            if o is not None and (o.dtype != torch.float64 or o.shape != (g.n_envs, g.obs_dim) or not o.is_contiguous()):
+                raise ValueError(f"group {gi}: obs buffer must be a contiguous float64 [{g.n_envs}, {g.obs_dim}] tensor")
+            if m is not None and (m.dtype != torch.uint8 or m.shape != (g.n_envs,)):
+                raise ValueError(f"group {gi}: mask must be uint8 [{g.n_envs}]")
+            io[gi].actions, io[gi].dactions, io[gi].obs = _ptr(a), _ptr(d), _ptr(o)
+            io[gi].reward, io[gi].done, io[gi].info, io[gi].flags = _ptr(g.reward), _ptr(g.done), _ptr(g.info), _ptr(g.flags)
+            io[gi].mask = _ptr(m)
+        return io, obs_bufs
+
+    def _result(self, obs_bufs):
+        if self.single_group:
+            g = self.groups[0]
+            return obs_bufs[0], g.reward, g.done, g.info
+        return obs_bufs, [g.reward for g in self.groups], [g.done for g in self.groups], [g.info for g in self.groups]
+
+    def step(self, actions, normalized=True, obs=True):
+        """Microgrid.run for every env (reference microgrid.py:227-325).  actions: float64 [n, n_act] per group,
+        columns per `Group.act_cols`.  Returns (obs, reward, done, info) as device tensors (lists for > 1 group)."""
+        io, obs_bufs = self._io(actions=actions, obs=obs)
+        _cabi.check(self._lib.mg_step(self._handle, io, int(bool(normalized)), self._stream()), "mg_step")
+        return self._result(obs_bufs)
+
+    def step_discrete(self, actions, obs=True):
+        """DiscreteMicrogridEnv.step for every env (reference envs/discrete/discrete.py:109-143)."""
+        io, obs_bufs = self._io(dactions=actions, obs=obs)
+        _cabi.check(self._lib.mg_step_discrete(self._handle, io, self._stream()), "mg_step_discrete")
+        return self._result(obs_bufs)
+
+    def reset(self, mask=None, obs=True):
+        """Microgrid.reset (reference microgrid.py:205-225): step = initial_step; battery / genset state is kept."""
+        io, obs_bufs = self._io(obs=obs, mask=mask)
+        _cabi.check(self._lib.mg_reset(self._handle, io, self._stream()), "mg_reset")
+        return obs_bufs[0] if self.single_group else obs_bufs
+
+    def observe(self, obs=True):
+        io, obs_bufs = self._io(obs=obs)
+        _cabi.check(self._lib.mg_observe(self._handle, io, self._stream()), "mg_observe")
+        return obs_bufs[0] if self.single_group else obs_bufs
+
+    def rollout(self, actions, normalized=True, discrete=False, ring=1, keep_obs=True, reward_sum=False):
+        """n_steps consecutive steps in one persistent kernel.  actions: per group [n_steps, n, n_act] float64
+        (or [n_steps, n] int32 when discrete).  Returns dict(reward=[n_steps, n], done=..., obs_ring=[ring, n, D])."""
+        acts = self._per_group(actions, "actions")
+        n_steps = acts[0].shape[0]
+        io = (MgRolloutIO * len(self.groups))()
+        out = []
+        for gi, g in enumerate(self.groups):
+            a = acts[gi]
+            want = (n_steps, g.n_envs) if discrete else (n_steps, g.n_envs, g.n_act)
+            if tuple(a.shape) != want or a.dtype != (torch.int32 if discrete else torch.float64) or not a.is_contiguous():
+                raise ValueError(f"group {gi}: rollout actions must be contiguous {want}")
+            r = dict(reward=torch.empty((n_steps, g.n_envs), dtype=torch.float64, device=self.device),
+                     done=torch.empty((n_steps, g.n_envs), dtype=torch.uint8, device=self.device),
+                     obs_ring=torch.empty((ring, g.n_envs, g.obs_dim), dtype=torch.float64, device=self.device) if keep_obs else None,
+                     reward_sum=torch.empty(g.n_envs, dtype=torch.float64, device=self.device) if reward_sum else None)
+            out.append(r)
+            if discrete:
+                io[gi].dactions = _ptr(a)
+            else:
+                io[gi].actions = _ptr(a)
+            io[gi].obs_ring, io[gi].reward, io[gi].done = _ptr(r["obs_ring"]), _ptr(r["reward"]), _ptr(r["done"])
+            io[gi].reward_sum, io[gi].flags = _ptr(r["reward_sum"]), _ptr(g.flags)
+        if discrete:
+            _cabi.check(self._lib.mg_rollout_discrete(self._handle, io, n_steps, ring, self._stream()), "mg_rollout_discrete")
+        else:
+            _cabi.check(self._lib.mg_rollout(self._handle, io, n_steps, ring, int(bool(normalized)), self._stream()), "mg_rollout")
+        return out[0] if self.single_group else out
+
+    # ------------------------------------------------------------------------------------------------------
+    @property
+    def launch_count(self):
+        return int(self._lib.mg_launch_count(self._handle))
+
+    def state_dict(self):
+        """The reference's serialisable state (base_module.py:852-868, genset_module.py:426-427), per group."""
+        return [dict(step=g.step.clone(), charge=g.charge.clone(), genset=None if g.genset is None else g.genset.clone())
+                for g in self.groups]
+
+    def load_state_dict(self, state):
+        for g, s in zip(self.groups, state):
+            g.step.copy_(s["step"])
+            g.charge.copy_(s["charge"])
+            if g.genset is not None:
+                g.genset.copy_(s["genset"])
+
+    def genset_status(self, gi=0):
+        w = self.groups[gi].genset
+        return torch.stack([w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff, (w >> 24) & 0xff], dim=1)
+
+    def scatter_to_env_order(self, per_group):
+        """Concatenate per-group [n_g, ...] tensors back into global env order (host-side convenience)."""
+        out = torch.empty((self.n_envs,) + tuple(per_group[0].shape[1:]), dtype=per_group[0].dtype, device=self.device)
+        for g, x in zip(self.groups, per_group):
+            out[torch.from_numpy(g.env_ids).to(self.device)] = x
+        return out
+
+    # ------------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_pymgrid25(cls, batch, scenarios=None, forecast_horizon=None, **kw):
+        """`batch` envs tiled over pymgrid25 scenarios: env i -> scenarios[i % len(scenarios)]."""
+        from .scenario import load_pymgrid25
+        scenarios = list(range(25)) if scenarios is None else list(scenarios)
+        configs = [load_pymgrid25(n) for n in scenarios]
+        if forecast_horizon is not None:
+            for p in configs:
+                p.forecast_horizon = forecast_horizon
+        env_config = np.arange(batch) % len(scenarios)
+        return cls(configs, env_config, **kw)

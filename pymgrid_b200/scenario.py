@@ -28,7 +28,10 @@ class _Tagged(dict):
 
 
 class _ScenarioLoader(yaml.SafeLoader):
-    pass
+    # private constructor table: only the standard YAML tags, so that tag handlers another library (e.g. the
+    # reference itself) registered on yaml.SafeLoader never leak into this reader
+    yaml_constructors = {k: v for k, v in yaml.SafeLoader.yaml_constructors.items()
+                         if k is None or str(k).startswith("tag:yaml.org")}
 
 
 def _construct_tagged(loader, suffix, node):

@@ -1,0 +1,397 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the golden vectors recorded from the reference and against
+the C oracle on the same seeded inputs.  Bar: bit-exact for integers (step, done, genset status) AND for floats --
+the kernels are compiled with -fmad=false so every f64 operation matches the reference's un-fused arithmetic;
+the assertions below therefore use exact equality (stricter than the 1e-6 relative the spec allows)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle import OracleBatch
+from pymgrid_b200.scenario import load_pymgrid25
+from tests.helpers import custom_params, jump_to
+
+pytestmark = pytest.mark.gpu
+CONTAINER = ("genset", "battery", "grid")
+
+
+def engine(configs, env_config, **kw):
+    from pymgrid_b200.engine import BatchedMicrogrid
+    kw.setdefault("action_order", CONTAINER)
+    kw.setdefault("with_info", True)
+    return BatchedMicrogrid(configs, env_config, device="cuda:0", **kw)
+
+
+def group_actions(bm, per_env_actions):
+    """per_env_actions: list (env order) of 1-D arrays in container order -> one device tensor per group."""
+    out = []
+    for g in bm.groups:
+        a = np.stack([per_env_actions[e] for e in g.env_ids])
+        out.append(torch.from_numpy(np.ascontiguousarray(a)).cuda())
+    return out
+
+
+def gather(bm, per_group):
+    """per-group device tensors -> list in env order of numpy arrays."""
+    out = [None] * bm.n_envs
+    for g, x in zip(bm.groups, per_group):
+        x = x.cpu().numpy()
+        for slot, e in enumerate(g.env_ids):
+            out[e] = x[slot]
+    return out
+
+
+def state_rows(bm):
+    rows = [None] * bm.n_envs
+    for gi, g in enumerate(bm.groups):
+        step, charge = g.step.cpu().numpy(), g.charge.cpu().numpy()
+        gen = bm.genset_status(gi).cpu().numpy() if g.genset is not None else np.zeros((g.n_envs, 4), dtype=np.int64)
+        for slot, e in enumerate(g.env_ids):
+            rows[e] = np.array([step[slot], charge[slot], *gen[slot]], dtype=np.float64)
+    return rows
+
+
+def as_lists(res):
+    obs, reward, done, info = res
+    if isinstance(obs, torch.Tensor):
+        return [obs], [reward], [done], [info]
+    return obs, reward, done, info
+
+
+def check_against_golden(bm, seq, normalized=True):
+    """seq: per env dict(a, r, d, o, i, s) of golden arrays; all envs have the same number of steps."""
+    n_steps = len(seq[0]["a"])
+    for k in range(n_steps):
+        obs, reward, done, info = as_lists(bm.step(group_actions(bm, [s["a"][k] for s in seq]), normalized=normalized))
+        o, r, d, inf, st = gather(bm, obs), gather(bm, reward), gather(bm, done), gather(bm, info), state_rows(bm)
+        for e, s in enumerate(seq):
+            assert r[e] == s["r"][k], (e, k, r[e], s["r"][k])
+            assert bool(d[e]) == bool(s["d"][k]), (e, k)
+            np.testing.assert_array_equal(o[e], s["o"][k], err_msg=f"obs env {e} step {k}")
+            np.testing.assert_array_equal(inf[e], s["i"][k], err_msg=f"info env {e} step {k}")
+            np.testing.assert_array_equal(st[e], s["s"][k], err_msg=f"state env {e} step {k}")
+
+
+def test_pymgrid25_golden_steps(golden):
+    """All 25 scenarios side by side (three architecture groups in ONE launch): normalised steps from t=0, then
+    unnormalised steps, bit-exact against the reference's recorded outputs."""
+    z = golden["pymgrid25_steps"]
+    configs = [load_pymgrid25(n) for n in range(25)]
+    bm = engine(configs, np.arange(25))
+    assert len(bm.groups) == 3
+    seq = [dict(a=z[f"s{n}_a0"], r=z[f"s{n}_r0"], d=z[f"s{n}_d0"], o=z[f"s{n}_o0"], i=z[f"s{n}_i0"], s=z[f"s{n}_s0"]) for n in range(25)]
+    check_against_golden(bm, seq)
+    seq = [dict(a=z[f"s{n}_au"], r=z[f"s{n}_ru"], d=z[f"s{n}_du"], o=z[f"s{n}_ou"], i=z[f"s{n}_iu"], s=z[f"s{n}_su"]) for n in range(25)]
+    check_against_golden(bm, seq, normalized=False)
+    flags = torch.cat([g.flags for g in bm.groups]).cpu().numpy()
+    assert (flags & 0x7f == 0).all()
+
+
+def test_pymgrid25_golden_end_of_series(golden):
+    """Across the end of the series: forecast padding, done at final_step-1, last valid step, then the past-the-end flag."""
+    z = golden["pymgrid25_steps"]
+    end_from = int(z["end_from"])
+    configs = [jump_to(load_pymgrid25(n), end_from) for n in range(25)]
+    bm = engine(configs, np.arange(25))
+    reset_obs = gather(bm, bm.reset())
+    for n in range(25):
+        np.testing.assert_array_equal(reset_obs[n], z[f"s{n}_reset_obs"])
+    seq = [dict(a=z[f"s{n}_a1"], r=z[f"s{n}_r1"], d=z[f"s{n}_d1"], o=z[f"s{n}_o1"], i=z[f"s{n}_i1"], s=z[f"s{n}_s1"]) for n in range(25)]
+    check_against_golden(bm, seq)
+    # one more step: the reference raises IndexError; the engine flags it and leaves the state untouched
+    before = state_rows(bm)
+    obs, reward, done, info = as_lists(bm.step(group_actions(bm, [s["a"][0] for s in seq])))
+    after = state_rows(bm)
+    for e in range(25):
+        np.testing.assert_array_equal(before[e], after[e])
+    for g, r, d in zip(bm.groups, reward, done):
+        assert torch.isnan(r).all() and (d == 1).all() and ((g.flags & (1 << 5)) != 0).all()
+
+
+@pytest.mark.parametrize("i", range(6))
+def test_custom_grids_golden(golden, i):
+    """Slow gensets (start-up / wind-down, abortion on and off), weak grid, short series, no forecaster."""
+    z = golden["custom"]
+    p = custom_params(z, i)
+    bm = engine([p], np.zeros(3, dtype=np.int64))        # three replicas fed the same actions
+    ro = bm.reset()
+    for e in range(3):
+        np.testing.assert_array_equal(ro[e].cpu().numpy(), z[f"c{i}_reset_obs"])
+    seq = [dict(a=z[f"c{i}_a"], r=z[f"c{i}_r"], d=z[f"c{i}_d"], o=z[f"c{i}_o"], i=z[f"c{i}_i"], s=z[f"c{i}_s"])] * 3
+    check_against_golden(bm, seq)
+    charge = bm.groups[0].charge.clone()
+    ro = bm.reset()
+    np.testing.assert_array_equal(ro[0].cpu().numpy(), z[f"c{i}_after_reset_obs"])
+    assert torch.equal(charge, bm.groups[0].charge) and (bm.groups[0].step == 0).all()
+
+
+def _discrete_cases(z):
+    return sorted({k.rsplit("_", 1)[0] for k in z.files if k.endswith("_actions")})
+
+
+@pytest.mark.parametrize("horizon", (23, 24))
+def test_discrete_env_golden(golden, horizon):
+    """DiscreteMicrogridEnv: action tables, rewards and flat observations of the reference env (H=23: all 25
+    scenarios; H=24 + grid: BASELINE config 4)."""
+    z = golden["discrete"]
+    scen = [int(t.split("_")[1][1:]) for t in _discrete_cases(z) if t.startswith(f"h{horizon}_")]
+    configs = []
+    for n in scen:
+        p = load_pymgrid25(n)
+        p.forecast_horizon = horizon
+        configs.append(p)
+    bm = engine(configs, np.arange(len(scen)))
+    for k, n in enumerate(scen):     # host-side action table == the reference's actions_list
+        tag = f"h{horizon}_s{n}"
+        mod, act = z[f"{tag}_table_mod"], z[f"{tag}_table_act"]
+        table = bm.action_tables[k]
+        assert len(table) == len(mod)
+        for row, pl in enumerate(table):
+            assert [tuple(x) for x in pl] == [(int(m), int(a)) for m, a in zip(mod[row], act[row]) if m >= 0]
+    ro = gather(bm, bm.reset() if not bm.single_group else [bm.reset()])
+    for k, n in enumerate(scen):
+        np.testing.assert_array_equal(ro[k], z[f"h{horizon}_s{n}_reset_obs"])
+    n_steps = len(z[f"h{horizon}_s{scen[0]}_actions"])
+    for s in range(n_steps):
+        acts = []
+        for g in bm.groups:
+            acts.append(torch.tensor([z[f"h{horizon}_s{scen[e]}_actions"][s] for e in g.env_ids], dtype=torch.int32, device="cuda"))
+        obs, reward, done, info = as_lists(bm.step_discrete(acts))
+        o, r, d = gather(bm, obs), gather(bm, reward), gather(bm, done)
+        for k, n in enumerate(scen):
+            tag = f"h{horizon}_s{n}"
+            assert r[k] == z[f"{tag}_rewards"][s], (tag, s)
+            assert bool(d[k]) == bool(z[f"{tag}_dones"][s])
+            np.testing.assert_array_equal(o[k], z[f"{tag}_obs"][s], err_msg=f"{tag} step {s}")
+
+
+def randomise_state(bm, rng, configs, env_config, max_t):
+    """Give every env its own step / charge / genset status so the batch is not in lock-step."""
+    plist = []
+    for e, c in enumerate(env_config):
+        p = copy.copy(configs[c])
+        p.battery = copy.copy(p.battery)
+        p.current_step = int(rng.integers(0, max_t))
+        p.battery.current_charge = float(rng.uniform(p.battery.min_capacity, p.battery.max_capacity))
+        if p.genset is not None:
+            p.genset = copy.copy(p.genset)
+            cs = int(rng.integers(0, 2))
+            p.genset.current_status = p.genset.goal_status = cs
+            p.genset.steps_until_up, p.genset.steps_until_down = (0, p.genset.wind_down_time) if cs else (p.genset.start_up_time, 0)
+        plist.append(p)
+    for gi, g in enumerate(bm.groups):
+        g.step.copy_(torch.tensor([plist[e].current_step for e in g.env_ids], dtype=torch.int32))
+        g.charge.copy_(torch.tensor([plist[e].battery.current_charge for e in g.env_ids], dtype=torch.float64))
+        if g.genset is not None:
+            g.genset.copy_(torch.tensor([plist[e].genset.current_status * 0x101 | (plist[e].genset.steps_until_up << 16)
+                                         | (plist[e].genset.steps_until_down << 24) for e in g.env_ids], dtype=torch.int32))
+    return plist
+
+
+@pytest.mark.parametrize("order", ("gym_sorted", "container"))
+def test_batch_vs_oracle_ragged_state(order):
+    """4099 envs (ragged last tile) over all 25 scenarios, every env at its own step (some inside the last 30
+    steps of the year), own charge, own genset status; 12 normalised steps + 6 unnormalised, engine == oracle."""
+    rng = np.random.default_rng(11)
+    configs = [load_pymgrid25(n) for n in range(25)]
+    B = 4099
+    env_config = rng.integers(0, 25, B)
+    bm = engine(configs, env_config, obs_order=order)
+    plist = randomise_state(bm, rng, configs, env_config, 8748)
+    for e in range(0, B, 7):          # a slice of envs starts close to the end of the series
+        plist[e].current_step = int(rng.integers(8735, 8748))
+    for gi, g in enumerate(bm.groups):
+        g.step.copy_(torch.tensor([plist[e].current_step for e in g.env_ids], dtype=torch.int32))
+    ob = OracleBatch(plist, order=0 if order == "gym_sorted" else 1)
+    for normalized, n_steps in ((True, 12), (False, 6)):
+        acts = []
+        for e in range(B):
+            p = plist[e]
+            a = rng.random((n_steps, p.n_act))
+            if not normalized:
+                col = 0
+                if p.genset is not None:
+                    a[:, 0] = rng.integers(0, 2, n_steps)
+                    a[:, 1] = rng.uniform(0, 1.3, n_steps) * p.genset.running_max_production
+                    col = 2
+                a[:, col] = rng.uniform(-1.5, 1.5, n_steps) * p.battery.max_charge
+                if p.grid is not None:
+                    a[:, col + 1] = rng.uniform(-1.2, 1.2, n_steps) * p.grid.max_import
+            acts.append(a)
+        padded = np.zeros((n_steps, B, 4))
+        for e in range(B):
+            padded[:, e, :acts[e].shape[1]] = acts[e]
+        for k in range(n_steps):
+            obs, reward, done, info = as_lists(bm.step(group_actions(bm, [a[k] for a in acts]), normalized=normalized))
+            o_rew, o_done, o_obs = ob.rollout(padded[k:k + 1], normalized=normalized, n_threads=4)
+            r, d, o = gather(bm, reward), gather(bm, done), gather(bm, obs)
+            np.testing.assert_array_equal(np.array(r), o_rew[0])
+            np.testing.assert_array_equal(np.array(d), o_done[0])
+            for e in range(B):
+                np.testing.assert_array_equal(o[e], o_obs[e, :len(o[e])], err_msg=f"env {e} step {k}")
+        t, charge, gen = ob.state()
+        st = state_rows(bm)
+        np.testing.assert_array_equal(np.array([s[0] for s in st]), t)
+        np.testing.assert_array_equal(np.array([s[1] for s in st]), charge)
+        np.testing.assert_array_equal(np.array([s[2:] for s in st]), gen)
+
+
+def test_rollout_kernel_equals_repeated_steps():
+    """mg_rollout (persistent kernel, state in registers) == n_steps x mg_step, bit for bit, incl. the obs ring."""
+    rng = np.random.default_rng(5)
+    configs = [load_pymgrid25(n) for n in range(25)]
+    B, n_steps, ring = 1000, 17, 4
+    env_config = np.arange(B) % 25
+    a = engine(configs, env_config)
+    b = engine(configs, env_config)
+    randomise_state(a, rng, configs, env_config, 8700)
+    b.load_state_dict(a.state_dict())
+    acts = [torch.rand((n_steps, g.n_envs, g.n_act), dtype=torch.float64, device="cuda") for g in a.groups]
+    out = a.rollout(acts, ring=ring)
+    obs_hist = []
+    for k in range(n_steps):
+        obs, reward, done, _ = as_lists(b.step([x[k].contiguous() for x in acts]))
+        obs_hist.append([o.clone() for o in obs])
+        for gi in range(len(a.groups)):
+            assert torch.equal(out[gi]["reward"][k], reward[gi])
+            assert torch.equal(out[gi]["done"][k], done[gi])
+    for gi in range(len(a.groups)):
+        for k in range(n_steps - ring, n_steps):
+            assert torch.equal(out[gi]["obs_ring"][k % ring], obs_hist[k][gi])
+        assert torch.equal(a.groups[gi].step, b.groups[gi].step) and torch.equal(a.groups[gi].charge, b.groups[gi].charge)
+        if a.groups[gi].genset is not None:
+            assert torch.equal(a.groups[gi].genset, b.groups[gi].genset)
+
+
+def test_discrete_rollout_vs_oracle():
+    """Config 4 shape at small size: discrete actions, H=24, 15 grid scenarios, engine rollout == oracle rollout."""
+    rng = np.random.default_rng(9)
+    scen = [0, 4, 6, 11, 12, 14, 16, 1, 8, 9, 10, 13, 18, 22, 24]
+    configs = []
+    for n in scen:
+        p = load_pymgrid25(n)
+        p.forecast_horizon = 24
+        configs.append(p)
+    B, n_steps = 600, 30
+    env_config = np.arange(B) % len(scen)
+    bm = engine(configs, env_config)
+    plist = randomise_state(bm, rng, configs, env_config, 8700)
+    acts_env = np.stack([rng.integers(0, len(bm.action_tables[c]), n_steps) for c in env_config], axis=1).astype(np.int32)
+    width = 3
+    lut_mod, lut_act, offsets, off = [], [], {}, 0
+    for c, table in enumerate(bm.action_tables):
+        offsets[c] = off
+        for pl in table:
+            lut_mod.append([pl[j][0] if j < len(pl) else -1 for j in range(width)])
+            lut_act.append([pl[j][1] if j < len(pl) else 0 for j in range(width)])
+        off += len(table)
+    ob = OracleBatch(plist)
+    o_rew, o_done, o_obs = ob.rollout_discrete(acts_env, np.array(lut_mod), np.array(lut_act),
+                                               np.array([offsets[c] for c in env_config]), n_threads=4)
+    acts = [torch.from_numpy(np.ascontiguousarray(acts_env[:, g.env_ids])).cuda() for g in bm.groups]
+    out = bm.rollout(acts, discrete=True, ring=1)
+    out = [out] if isinstance(out, dict) else out
+    for g, r in zip(bm.groups, out):
+        np.testing.assert_array_equal(r["reward"].cpu().numpy(), o_rew[:, g.env_ids])
+        np.testing.assert_array_equal(r["done"].cpu().numpy(), o_done[:, g.env_ids])
+        np.testing.assert_array_equal(r["obs_ring"][0].cpu().numpy(), o_obs[g.env_ids][:, :g.obs_dim])
+
+
+@pytest.mark.parametrize("n", (0, 1, 2))
+def test_full_year_golden(golden, n):
+    """BASELINE config 1 on the GPU: the 8760-step year of scenarios 0 / 1 / 2 against the reference's rewards."""
+    z = golden["pymgrid25_year"]
+    p = load_pymgrid25(n)
+    bm = engine([p], np.zeros(2, dtype=np.int64))
+    a = np.random.default_rng(0).random((8760, p.n_act))
+    acts = torch.from_numpy(np.ascontiguousarray(np.repeat(a[:, None, :], 2, axis=1))).cuda()
+    out = bm.rollout(acts, ring=1, reward_sum=True)
+    rewards = out["reward"].cpu().numpy()
+    np.testing.assert_array_equal(rewards[:, 0], z[f"s{n}_rewards"])
+    np.testing.assert_array_equal(rewards[:, 1], z[f"s{n}_rewards"])
+    assert int(np.argmax(out["done"][:, 0].cpu().numpy())) == int(z[f"s{n}_first_done"])
+    st = state_rows(bm)[0]
+    np.testing.assert_array_equal(st, z[f"s{n}_final_state"])
+    # sequential in-kernel sum == sequential host sum
+    assert out["reward_sum"][0].item() == float(np.add.accumulate(z[f"s{n}_rewards"])[-1])
+
+
+def test_full_size_properties():
+    """BASELINE config 3 size (65 536 envs, 25 scenarios tiled): size-independent properties.
+    (1) replicas of one scenario fed identical actions stay identical; (2) the energy balance closes:
+    load_met + charge + export + overgeneration == pv_used + discharge + import + genset + loss_load;
+    (3) sampled envs (one per scenario) equal the oracle; (4) obs in [0, 1]; (5) step counters advance by one."""
+    B, n_steps = 65536, 6
+    configs = [load_pymgrid25(n) for n in range(25)]
+    env_config = np.arange(B) % 25
+    bm = engine(configs, env_config)
+    rng = np.random.default_rng(21)
+    base = {n: rng.random((n_steps, configs[n].n_act)) for n in range(25)}
+    sample = list(range(25))
+    ob = OracleBatch([configs[env_config[e]] for e in sample])
+    for k in range(n_steps):
+        acts = []
+        for g in bm.groups:
+            cfg = env_config[g.env_ids]
+            acts.append(torch.from_numpy(np.stack([base[c][k] for c in cfg])).cuda())
+        obs, reward, done, info = as_lists(bm.step(acts))
+        padded = np.zeros((1, len(sample), 4))
+        for j, e in enumerate(sample):
+            padded[0, j, :configs[env_config[e]].n_act] = base[env_config[e]][k]
+        o_rew, o_done, o_obs = ob.rollout(padded)
+        for g, o, r, inf in zip(bm.groups, obs, reward, info):
+            cfg = torch.from_numpy(env_config[g.env_ids]).cuda()
+            for c in torch.unique(cfg).tolist():
+                rows = (cfg == c).nonzero()[:, 0]
+                assert (r[rows] == r[rows[0]]).all() and (o[rows] == o[rows[0]]).all()
+            lhs = inf[:, 0] + inf[:, 8] + inf[:, 10] + inf[:, 4]
+            rhs = inf[:, 1] + inf[:, 7] + inf[:, 9] + inf[:, 5] + inf[:, 3]
+            assert torch.allclose(lhs, rhs, rtol=1e-12, atol=1e-6)
+            assert (o >= 0).all() and (o <= 1).all()
+            assert (g.step == k + 1).all()
+            for j, e in enumerate(sample):
+                if bm.env_group[e] == bm.groups.index(g):
+                    slot = bm.env_slot[e]
+                    assert r[slot].item() == o_rew[0, j]
+                    np.testing.assert_array_equal(o[slot].cpu().numpy(), o_obs[j, :g.obs_dim])
+    assert bm.launch_count == 1 + n_steps
+
+
+def test_trajectory_windows_and_masked_reset():
+    """Per-env episode windows (reference: tests/envs/test_trajectory.py:134-156: episode length == final - initial)."""
+    p = load_pymgrid25(0)
+    B = 300
+    bm = engine([p], np.zeros(B, dtype=np.int64))
+    rng = np.random.default_rng(2)
+    initial = rng.integers(0, 8000, B).astype(np.int32)
+    length = rng.integers(2, 12, B).astype(np.int32)
+    bm.set_trajectories(initial, initial + length)
+    bm.reset()
+    assert torch.equal(bm.groups[0].step.cpu(), torch.from_numpy(initial))
+    steps_to_done = np.zeros(B, dtype=np.int64)
+    alive = np.ones(B, dtype=bool)
+    for k in range(12):
+        _, _, done, _ = bm.step(torch.rand((B, 2), dtype=torch.float64, device="cuda"))
+        d = done.cpu().numpy().astype(bool)
+        steps_to_done[alive & d] = k + 1
+        alive &= ~d
+    np.testing.assert_array_equal(steps_to_done, length)   # done fires on the step that runs at t = final_step - 1
+    mask = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    mask[::2] = 1
+    before = bm.groups[0].step.clone()
+    bm.reset(mask=mask)
+    after = bm.groups[0].step.cpu().numpy()
+    np.testing.assert_array_equal(after[::2], initial[::2])
+    np.testing.assert_array_equal(after[1::2], before.cpu().numpy()[1::2])
+
+
+def test_bad_discrete_action_is_flagged():
+    p = load_pymgrid25(0)
+    bm = engine([p], np.zeros(4, dtype=np.int64))
+    a = torch.tensor([0, 1, 2, -1], dtype=torch.int32, device="cuda")
+    _, reward, _, _ = bm.step_discrete(a)
+    f = bm.groups[0].flags.cpu().numpy()
+    assert (f[:2] & (1 << 6) == 0).all() and (f[2:] & (1 << 6) != 0).all()
+    assert torch.isnan(reward[2:]).all() and not torch.isnan(reward[:2]).any()
+    assert bm.groups[0].step.cpu().tolist() == [1, 1, 0, 0]
