@@ -22,7 +22,7 @@
 #include "pymgrid_b200.h"
 
 #ifndef MG_THREADS
-#define MG_THREADS 256
+#define MG_THREADS 128
 #endif
 #ifndef MG_TILE
 #define MG_TILE 64          // envs per CTA tile
@@ -31,6 +31,7 @@
 #define MG_STR(x) MG_STR2(x)
 #define MG_WARPS (MG_THREADS / 32)
 #define MG_ROWS_PER_WARP (MG_TILE / MG_WARPS)
+#define MG_MAX_IMG 320      // observation rows up to this many f64 use the TMA store path; longer rows use the LSU path
 
 enum { KIND_BAT = 0, KIND_GEN = 1, KIND_GRID = 2, KIND_LOAD = 3, KIND_PV = 4 };
 enum { MODE_STEP = 0, MODE_DISCRETE = 1, MODE_OBSERVE = 2, MODE_RESET = 3 };
@@ -41,6 +42,10 @@ struct DevGroup {
     int32_t tile_begin;                 // first CTA of this group in the fused launch
     int32_t n_seg;
     int32_t seg_start[5], seg_kind[5];  // observation row layout: segment starts (ascending) and kinds
+    // the same row as runs of 16-byte multiples: "shared" runs are identical for every env that has the same
+    // series and step (the [t, t+H] windows), the single "state" run (battery + genset obs) is per env
+    int32_t n_runs, run_start[3], run_len[3], run_is_state[3];
+    int32_t tma_ok;                     // rows can be written with cp.async.bulk (obs_dim <= MG_MAX_IMG)
     int32_t *step;
     double *charge;
     uint32_t *genset;
@@ -73,6 +78,39 @@ __device__ __forceinline__ void st_global_v2(double *p, double a, double b) {
     // 16-byte streaming store: observation rows are written once and never re-read by this kernel
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
+
+// ---- TMA (cp.async.bulk, SASS UBLKCP) and mbarrier wrappers -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MG_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MG_DONE;\n\t"
+        "bra MG_WAIT;\n\t"
+        "MG_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes and both addresses multiples of 16)
+__device__ __forceinline__ void tma_load(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global bulk copy, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// order generic-proxy shared-memory writes (st.shared) before async-proxy reads (the bulk store)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ bool np_isclose(double a, double b, double rtol, double atol) {
     return fabs(a - b) <= (atol + rtol * fabs(b));
@@ -315,8 +353,16 @@ struct __align__(16) TileEnv {
     double state[6];                            // normalised battery (soc, charge) and genset (cs, gs, up, dn) obs
 };
 
-__device__ __forceinline__ void publish_env(TileEnv &te, const MgConfig *__restrict__ c, const DevGroup &G, const EnvRegs &s,
-                                            int Tp) {
+struct TileShared {
+    alignas(128) double img[2][MG_MAX_IMG];     // the shared runs of an observation row (double buffered for the rollout)
+    alignas(16) double srow[2][MG_TILE][6];     // per-env state run in ROW order
+    TileEnv env[MG_TILE];
+    alignas(8) uint64_t bar[2];                 // completion of the TMA window load into img[b]
+};
+
+__device__ __forceinline__ void publish_env(TileShared &S, int buf, int i, const MgConfig *__restrict__ c, const DevGroup &G,
+                                            const EnvRegs &s, int Tp, bool container_order) {
+    TileEnv &te = S.env[i];
     // windows start at the NEW step; rows >= T of the tables hold the forecaster's fill value, so a window that
     // runs past the end of the series needs no branch (forecast/forecaster.py:120-137)
     te.off_load = c->load_series * Tp + s.t;
@@ -324,41 +370,50 @@ __device__ __forceinline__ void publish_env(TileEnv &te, const MgConfig *__restr
     te.off_grid = G.has_grid ? (c->grid_series * Tp + s.t) * 4 : 0;
     // battery_module.py:323-330 + utils/space.py:207-218
     const double soc = s.charge / c->bat_max_capacity;
-    te.state[0] = (soc - c->bat_soc_low) / c->bat_soc_spread;
-    te.state[1] = (s.charge - c->bat_min_capacity) / c->bat_charge_spread;
+    const double b0 = (soc - c->bat_soc_low) / c->bat_soc_spread;
+    const double b1 = (s.charge - c->bat_min_capacity) / c->bat_charge_spread;
     // genset_module.py:503-509
-    te.state[2] = ((double)s.cs - 0.0) / 1.0;
-    te.state[3] = ((double)s.gs - 0.0) / 1.0;
-    te.state[4] = G.has_genset ? ((double)s.up - 0.0) / c->gen_up_spread : 0.0;
-    te.state[5] = G.has_genset ? ((double)s.dn - 0.0) / c->gen_down_spread : 0.0;
+    const double g0 = ((double)s.cs - 0.0) / 1.0;
+    const double g1 = ((double)s.gs - 0.0) / 1.0;
+    const double g2 = G.has_genset ? ((double)s.up - 0.0) / c->gen_up_spread : 0.0;
+    const double g3 = G.has_genset ? ((double)s.dn - 0.0) / c->gen_down_spread : 0.0;
+    te.state[0] = b0; te.state[1] = b1; te.state[2] = g0; te.state[3] = g1; te.state[4] = g2; te.state[5] = g3;
+    double *r = S.srow[buf][i];
+    if (container_order && G.has_genset) {   // genset, battery
+        r[0] = g0; r[1] = g1; r[2] = g2; r[3] = g3; r[4] = b0; r[5] = b1;
+    } else {                                  // battery, genset (or battery alone)
+        r[0] = b0; r[1] = b1; r[2] = g0; r[3] = g1; r[4] = g2; r[5] = g3;
+    }
 }
 
-// phase 2: the CTA's warps write rows [0, n_rows) of the tile, 16 bytes per lane per store
-__device__ __forceinline__ void emit_rows(const LaunchParams &P, const DevGroup &G, const TileEnv *__restrict__ tile,
-                                          double *__restrict__ obs_tile, int n_rows) {
+// element j of an observation row -> (kind, offset inside the module's obs vector)
+__device__ __forceinline__ void decode_element(const DevGroup &G, int j, int &kind, int &off) {
+    int sgi = 0;
+#pragma unroll
+    for (int q = 1; q < 5; ++q)
+        if (q < G.n_seg && j >= G.seg_start[q]) sgi = q;
+    kind = G.seg_kind[sgi];
+    off = j - G.seg_start[sgi];
+}
+
+// LSU path (any layout, every env at its own step): the CTA's warps write rows [0, n_rows) with 16-byte stores
+__device__ __forceinline__ void emit_rows_lsu(const LaunchParams &P, const DevGroup &G, const TileEnv *__restrict__ tile,
+                                              double *__restrict__ obs_tile, int n_rows) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = G.obs_dim, pairs = D >> 1;
     for (int p = lane; p < pairs; p += 32) {
         // decode the two elements of this lane's pair once; the layout is the same for every row
         int kind[2], off[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int j = 2 * p + h;
-            int sgi = 0;
-#pragma unroll
-            for (int q = 1; q < 5; ++q)
-                if (q < G.n_seg && j >= G.seg_start[q]) sgi = q;
-            kind[h] = G.seg_kind[sgi];
-            off[h] = j - G.seg_start[sgi] + (kind[h] == KIND_GEN ? 2 : 0);
-        }
         const double *tab[2];
         int sel[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            decode_element(G, 2 * p + h, kind[h], off[h]);
+            if (kind[h] == KIND_GEN) off[h] += 2;
             tab[h] = kind[h] == KIND_GRID ? P.grid_nrm : kind[h] == KIND_LOAD ? P.load_nrm : P.pv_nrm;
             sel[h] = kind[h] == KIND_GRID ? 0 : kind[h] == KIND_LOAD ? 1 : 2;
         }
-#pragma unroll
+#pragma unroll 4
         for (int r = 0; r < MG_ROWS_PER_WARP; ++r) {
             const int i = warp * MG_ROWS_PER_WARP + r;
             if (i < n_rows) {
@@ -373,6 +428,67 @@ __device__ __forceinline__ void emit_rows(const LaunchParams &P, const DevGroup 
                 st_global_v2(obs_tile + (size_t)i * D + 2 * p, v[0], v[1]);
             }
         }
+    }
+}
+
+// Phase 2 of a tile.  Called by ALL threads of the CTA after the owners published S.env[] / S.srow[buf][].
+//   uniform tile (every env has the same series and the same step -- the lock-step case): the windows
+//     [t, t+H] are staged ONCE in shared memory (grid window by one TMA bulk load, load / pv by the threads)
+//     and every env's row is written by TMA bulk stores that all read that one image; the SM's load/store
+//     units only move the 16-48 byte state run per env;
+//   ragged tile: LSU path above.
+// `phase` carries the mbarrier parity of each image buffer across calls.
+__device__ __forceinline__ void emit_tile(const LaunchParams &P, const DevGroup &G, TileShared &S, int buf,
+                                          double *__restrict__ obs_tile, int n_rows, uint32_t (&phase)[2]) {
+    const int tid = threadIdx.x;
+    __syncthreads();   // env records visible to everyone
+    bool same = true;
+    if (tid < n_rows) {
+        const TileEnv &a = S.env[tid], &b = S.env[0];
+        same = (a.off_grid == b.off_grid) && (a.off_load == b.off_load) && (a.off_pv == b.off_pv);
+    }
+    const int uniform = __syncthreads_and(same) && G.tma_ok;
+    if (!uniform) {
+        emit_rows_lsu(P, G, S.env, obs_tile, n_rows);
+        __syncthreads();   // S.env[] may be rewritten by the next step of the persistent kernel
+        return;
+    }
+    const TileEnv &e0 = S.env[0];
+    double *img = S.img[buf];
+    const int D = G.obs_dim;
+    int grid_start = -1;
+    if (G.has_grid) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (q < G.n_seg && G.seg_kind[q] == KIND_GRID) grid_start = G.seg_start[q];
+        if (tid == 0) {   // TMA: the grid window is one contiguous, 32-byte aligned run of the normalised table
+            const uint32_t bytes = (uint32_t)(4 * (1 + G.horizon) * sizeof(double));
+            mbar_expect_tx(&S.bar[buf], bytes);
+            tma_load(img + grid_start, P.grid_nrm + e0.off_grid, bytes, &S.bar[buf]);
+        }
+    }
+    for (int j = tid; j < D; j += MG_THREADS) {
+        int kind, off;
+        decode_element(G, j, kind, off);
+        if (kind == KIND_LOAD) img[j] = __ldg(P.load_nrm + e0.off_load + off);
+        else if (kind == KIND_PV) img[j] = __ldg(P.pv_nrm + e0.off_pv + off);
+    }
+    fence_proxy_async();   // this thread's st.shared (img, srow) before the async proxy reads them
+    if (G.has_grid) {
+        mbar_wait(&S.bar[buf], phase[buf]);
+        phase[buf] ^= 1;
+    }
+    __syncthreads();
+    if (tid < n_rows) {
+        double *row = obs_tile + (size_t)tid * D;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (r < G.n_runs) {
+                const void *src = G.run_is_state[r] ? (const void *)S.srow[buf][tid] : (const void *)(img + G.run_start[r]);
+                tma_store(row + G.run_start[r], src, (uint32_t)(G.run_len[r] * sizeof(double)));
+            }
+        }
+        tma_commit();
     }
 }
 
@@ -406,23 +522,22 @@ __device__ __forceinline__ int find_group(const LaunchParams &P, int tile) {
     return g;
 }
 
-// read one env's action row into the four logical controls
+// read one env's action row into the four logical controls (coalesced 16-byte loads where rows allow it)
 __device__ __forceinline__ void read_action(const DevGroup &G, const double *__restrict__ row, double &a_goal, double &a_gen,
                                             double &a_bat, double &a_grid) {
     a_goal = a_gen = a_grid = 0.0;
-    if (G.n_act == 2) {          // [battery, grid] in either order: one 16-byte load
+    if (G.n_act == 2) {          // battery + grid in either order: one 16-byte load
         const double2 v = __ldg(reinterpret_cast<const double2 *>(row));
-        const double x[2] = {v.x, v.y};
-        a_bat = x[G.act_col_battery];
-        a_grid = x[G.act_col_grid];
+        a_bat = G.act_col_battery == 0 ? v.x : v.y;
+        a_grid = G.act_col_grid == 0 ? v.x : v.y;
     } else if (G.n_act == 4) {   // two 16-byte loads
         const double2 v0 = __ldg(reinterpret_cast<const double2 *>(row));
         const double2 v1 = __ldg(reinterpret_cast<const double2 *>(row) + 1);
-        const double x[4] = {v0.x, v0.y, v1.x, v1.y};
-        a_goal = x[G.act_col_genset];
-        a_gen = x[G.act_col_genset + 1];
-        a_bat = x[G.act_col_battery];
-        a_grid = x[G.act_col_grid];
+        const int cg = G.act_col_genset, cb = G.act_col_battery, cr = G.act_col_grid;
+        a_goal = cg == 0 ? v0.x : cg == 1 ? v0.y : v1.x;
+        a_gen = cg == 0 ? v0.y : cg == 1 ? v1.x : v1.y;
+        a_bat = cb == 0 ? v0.x : cb == 1 ? v0.y : cb == 2 ? v1.x : v1.y;
+        a_grid = cr == 0 ? v0.x : cr == 1 ? v0.y : cr == 2 ? v1.x : v1.y;
     } else {
         a_bat = __ldg(row + G.act_col_battery);
         if (G.has_genset) { a_goal = __ldg(row + G.act_col_genset); a_gen = __ldg(row + G.act_col_genset + 1); }
@@ -430,16 +545,47 @@ __device__ __forceinline__ void read_action(const DevGroup &G, const double *__r
     }
 }
 
+// the per-env part of one step, shared by the single-step and the persistent kernel
+__device__ __forceinline__ void owner_step(const LaunchParams &P, const DevGroup &G, const MgConfig *__restrict__ c, EnvRegs &s,
+                                           int e, int step, int final_step, double *__restrict__ info, double &reward,
+                                           int &done, uint32_t &flags) {
+    flags = 0;
+    if (s.t >= P.T) {   // the reference raises IndexError here; the state is left untouched
+        reward = __longlong_as_double(0x7ff8000000000000LL);
+        done = 1;
+        flags = MG_FLAG_STEP_PAST_END;
+        return;
+    }
+    const RawRow raw = gather_raw(P, G, c, s.t);
+    double a_goal, a_gen, a_bat, a_grid;
+    bool normalized = P.normalized != 0;
+    if (P.mode == MODE_DISCRETE) {
+        const int a = __ldg(G.dactions + (size_t)step * G.out_step_stride + e);
+        normalized = false;
+        if (a < 0 || a >= c->plist_count) {   // ValueError in the reference (envs/discrete/discrete.py:84)
+            reward = __longlong_as_double(0x7ff8000000000000LL);
+            done = 0;
+            flags = MG_FLAG_BAD_ACTION;
+            return;
+        }
+        priority_control(P.plist[c->plist_offset + a], c, G, s, raw, a_goal, a_gen, a_bat, a_grid);
+    } else {
+        read_action(G, G.actions + (size_t)step * G.act_step_stride + (size_t)e * G.n_act, a_goal, a_gen, a_bat, a_grid);
+    }
+    env_step(c, G, s, raw, a_goal, a_gen, a_bat, a_grid, normalized, final_step, reward, done, flags, info);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // fused single-step kernel: MODE_STEP / MODE_DISCRETE / MODE_OBSERVE / MODE_RESET
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MG_THREADS) mg_step_kernel(const __grid_constant__ LaunchParams P) {
-    __shared__ TileEnv tile[MG_TILE];
+    __shared__ TileShared S;
     const int gi = find_group(P, blockIdx.x);
     const DevGroup &G = P.g[gi];
     const int e0 = (blockIdx.x - G.tile_begin) * MG_TILE;
     const int n_rows = min(MG_TILE, G.n_envs - e0);
     const int i = threadIdx.x;
+    if (i == 0 && G.obs) mbar_init(&S.bar[0], 1);
     if (i < n_rows) {
         const int e = e0 + i;
         const MgConfig *__restrict__ c = P.cfg + __ldg(G.cfg_index + e);
@@ -450,41 +596,15 @@ __global__ void __launch_bounds__(MG_THREADS) mg_step_kernel(const __grid_consta
         if (G.has_genset) unpack_genset(G.genset[e], s);
         if (P.mode == MODE_STEP || P.mode == MODE_DISCRETE) {
             const int final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
+            const int t_before = s.t;
             double reward;
             int done;
-            uint32_t flags = 0;
-            if (s.t >= P.T) {   // the reference raises IndexError here; state is left untouched
-                reward = __longlong_as_double(0x7ff8000000000000LL);
-                done = 1;
-                flags = MG_FLAG_STEP_PAST_END;
-            } else {
-                const RawRow raw = gather_raw(P, G, c, s.t);
-                double a_goal, a_gen, a_bat, a_grid;
-                bool normalized = P.normalized != 0;
-                bool ok = true;
-                if (P.mode == MODE_DISCRETE) {
-                    const int a = __ldg(G.dactions + e);
-                    normalized = false;
-                    if (a < 0 || a >= c->plist_count) {
-                        ok = false;
-                    } else {
-                        const MgPriorityList pl = P.plist[c->plist_offset + a];
-                        priority_control(pl, c, G, s, raw, a_goal, a_gen, a_bat, a_grid);
-                    }
-                } else {
-                    read_action(G, G.actions + (size_t)e * G.n_act, a_goal, a_gen, a_bat, a_grid);
-                }
-                if (ok) {
-                    env_step(c, G, s, raw, a_goal, a_gen, a_bat, a_grid, normalized, final_step, reward, done, flags,
-                             G.info ? G.info + (size_t)e * MG_N_INFO : nullptr);
-                    G.step[e] = s.t;
-                    G.charge[e] = s.charge;
-                    if (G.has_genset) G.genset[e] = pack_genset(s);
-                } else {
-                    reward = __longlong_as_double(0x7ff8000000000000LL);
-                    done = 0;
-                    flags = MG_FLAG_BAD_ACTION;
-                }
+            uint32_t flags;
+            owner_step(P, G, c, s, e, 0, final_step, G.info ? G.info + (size_t)e * MG_N_INFO : nullptr, reward, done, flags);
+            if (s.t != t_before) {
+                G.step[e] = s.t;
+                G.charge[e] = s.charge;
+                if (G.has_genset) G.genset[e] = pack_genset(s);
             }
             G.reward[e] = reward;
             G.done[e] = (uint8_t)done;
@@ -498,12 +618,13 @@ __global__ void __launch_bounds__(MG_THREADS) mg_step_kernel(const __grid_consta
         if (G.obs) {
             EnvRegs so = s;
             if (so.t > P.T) so.t = P.T;
-            publish_env(tile[i], c, G, so, P.Tp);
+            publish_env(S, 0, i, c, G, so, P.Tp, G.seg_kind[0] != KIND_BAT);
         }
     }
     if (G.obs) {   // CTA-uniform
-        __syncthreads();
-        emit_rows(P, G, tile, G.obs + (size_t)e0 * G.obs_dim, n_rows);
+        uint32_t phase[2] = {0, 0};
+        emit_tile(P, G, S, 0, G.obs + (size_t)e0 * G.obs_dim, n_rows, phase);
+        tma_wait_read<0>();   // shared memory must outlive the bulk stores that read it
     }
 }
 
@@ -511,7 +632,7 @@ __global__ void __launch_bounds__(MG_THREADS) mg_step_kernel(const __grid_consta
 // persistent multi-step kernel: every CTA owns its tile for all n_steps; env state stays in registers
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MG_THREADS) mg_rollout_kernel(const __grid_constant__ LaunchParams P) {
-    __shared__ TileEnv tile[MG_TILE];
+    __shared__ TileShared S;
     const int gi = find_group(P, blockIdx.x);
     const DevGroup &G = P.g[gi];
     const int e0 = (blockIdx.x - G.tile_begin) * MG_TILE;
@@ -525,6 +646,8 @@ __global__ void __launch_bounds__(MG_THREADS) mg_rollout_kernel(const __grid_con
     int final_step = 0;
     double rsum = 0.0;
     uint32_t fsum = 0;
+    uint32_t phase[2] = {0, 0};
+    if (i == 0 && G.obs) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); }
     if (owner) {
         c = P.cfg + __ldg(G.cfg_index + e);
         s.t = G.step[e];
@@ -532,54 +655,29 @@ __global__ void __launch_bounds__(MG_THREADS) mg_rollout_kernel(const __grid_con
         if (G.has_genset) unpack_genset(G.genset[e], s);
         final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
     }
+    const bool container = G.seg_kind[0] != KIND_BAT;
     for (int step = 0; step < P.n_steps; ++step) {
+        const int buf = step & 1;
         if (owner) {
             double reward;
             int done;
-            uint32_t flags = 0;
-            if (s.t >= P.T) {
-                reward = __longlong_as_double(0x7ff8000000000000LL);
-                done = 1;
-                flags = MG_FLAG_STEP_PAST_END;
-            } else {
-                const RawRow raw = gather_raw(P, G, c, s.t);
-                double a_goal, a_gen, a_bat, a_grid;
-                bool normalized = P.normalized != 0;
-                bool ok = true;
-                if (P.mode == MODE_DISCRETE) {
-                    const int a = __ldg(G.dactions + (size_t)step * G.out_step_stride + e);
-                    normalized = false;
-                    if (a < 0 || a >= c->plist_count) ok = false;
-                    else priority_control(P.plist[c->plist_offset + a], c, G, s, raw, a_goal, a_gen, a_bat, a_grid);
-                } else {
-                    read_action(G, G.actions + (size_t)step * G.act_step_stride + (size_t)e * G.n_act, a_goal, a_gen,
-                                a_bat, a_grid);
-                }
-                if (ok) {
-                    env_step(c, G, s, raw, a_goal, a_gen, a_bat, a_grid, normalized, final_step, reward, done, flags,
-                             nullptr);
-                } else {
-                    reward = __longlong_as_double(0x7ff8000000000000LL);
-                    done = 0;
-                    flags = MG_FLAG_BAD_ACTION;
-                }
-            }
+            uint32_t flags;
+            owner_step(P, G, c, s, e, step, final_step, nullptr, reward, done, flags);
             G.reward[(size_t)step * G.out_step_stride + e] = reward;
             G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)done;
             rsum += reward;
             fsum |= flags;
             if (G.obs) {
+                tma_wait_read<1>();   // the bulk stores of step-2 have finished reading srow[buf] / img[buf]
                 EnvRegs so = s;
                 if (so.t > P.T) so.t = P.T;
-                publish_env(tile[i], c, G, so, P.Tp);
+                publish_env(S, buf, i, c, G, so, P.Tp, container);
             }
         }
-        if (G.obs) {
-            __syncthreads();
-            emit_rows(P, G, tile, G.obs + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim, n_rows);
-            __syncthreads();
-        }
+        if (G.obs)
+            emit_tile(P, G, S, buf, G.obs + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim, n_rows, phase);
     }
+    if (G.obs) tma_wait_read<0>();
     if (owner) {
         G.step[e] = s.t;
         G.charge[e] = s.charge;
@@ -722,6 +820,23 @@ static void layout_segments(const MgGroup &g, DevGroup &d) {
         if (k < n) start += lens[k];
     }
     d.n_seg = n;
+    // runs: adjacent time-series segments merge into one shared run; genset + battery obs form the state run
+    int nr = 0;
+    for (int k = 0; k < n; ++k) {
+        const bool is_state = kinds[k] == KIND_BAT || kinds[k] == KIND_GEN;
+        if (nr > 0 && d.run_is_state[nr - 1] == (int)is_state) {
+            d.run_len[nr - 1] += lens[k];
+        } else {
+            d.run_start[nr] = d.seg_start[k];
+            d.run_len[nr] = lens[k];
+            d.run_is_state[nr] = is_state;
+            ++nr;
+        }
+    }
+    d.n_runs = nr;
+    d.tma_ok = 1;
+    for (int r = 0; r < nr; ++r)
+        if ((d.run_start[r] & 1) || (d.run_len[r] & 1)) d.tma_ok = 0;   // bulk copies move multiples of 16 bytes
 }
 
 extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
@@ -767,6 +882,7 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
         d.tile_begin = tiles;
         tiles += (int)((g.n_envs + MG_TILE - 1) / MG_TILE);
         layout_segments(g, d);
+        if (obs_dim > MG_MAX_IMG) d.tma_ok = 0;
         d.step = g.step; d.charge = g.charge; d.genset = g.genset; d.cfg_index = g.cfg_index;
         d.env_initial = g.env_initial_step; d.env_final = g.env_final_step;
     }

@@ -186,6 +186,9 @@ class BatchedMicrogrid:
         start = 0
         for gi, arch in enumerate(order):
             ids = np.nonzero(env_arch == gi)[0]
+            # envs of one config sit next to each other so that a 64-env tile shares its time-series windows
+            # (the kernel stages them once per tile when every env of the tile is at the same step)
+            ids = ids[np.argsort(env_config[ids], kind="stable")]
             self.env_slot[ids] = np.arange(len(ids))
             has_genset, has_grid, H = arch
             n_act = 1 + has_grid + 2 * has_genset
