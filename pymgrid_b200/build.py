@@ -32,6 +32,7 @@ def build(force=False, verbose=False, extra=()):
     if not force and not is_stale():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
+    extra = list(extra) + os.environ.get("PYMGRID_B200_NVCC_EXTRA", "").split()
     cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-I", os.path.join(_ROOT, "include"), "-o", LIB, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas")
