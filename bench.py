@@ -55,37 +55,58 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region.  Polls NVML in-process (sub-millisecond period, a
+    timed region lasts only tens of milliseconds); falls back to the nvidia-smi query of B200_PROFILING.md."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.sm, self.reasons, self._halt = index, [], set(), threading.Event()
+        self.sm_max, self.source = None, "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv, self.source = None, "nvidia-smi"
+
+    def _poll_nvml(self):
+        nv = self._nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _poll_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.sm.append(float(out[0]))
+        self.sm_max = float(out[1])
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
+            if v.strip().lower().startswith("active"):
+                self.reasons.add(name)
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self._poll_nvml() if self._nv else self._poll_smi()
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.0005 if self._nv else 0.1)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def build_engine(batch, device, discrete=False):
@@ -141,7 +162,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="envs per GPU")
@@ -149,6 +170,7 @@ def main():
     ap.add_argument("--path", default="graph", choices=("graph", "eager", "rollout"),
                     help="headline path: mg_step launches replayed from a CUDA graph, plain launches, or the persistent rollout kernel")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--preheat", type=float, default=0.2, help="seconds of untimed steps before the warm-up (0 under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -168,14 +190,21 @@ def main():
     groups = bm.groups
     gen = torch.Generator(device=dev)
     gen.manual_seed(2 + rank)
-    # this step's own actions for every timed / warm-up step, resident in HBM
-    acts = [torch.rand((W + K, g.n_envs, g.n_act), dtype=torch.float64, device=dev, generator=gen) for g in groups]
+    # every step reads its own actions from HBM: a ring of A steps (> 2x L2) reused cyclically
+    A = min(W + K, 256)
+    acts = [torch.rand((A, g.n_envs, g.n_act), dtype=torch.float64, device=dev, generator=gen) for g in groups]
     rings = [torch.empty((R, g.n_envs, g.obs_dim), dtype=torch.float64, device=dev) for g in groups]
     ring_bytes = sum(r.numel() * 8 for r in rings)
+    act_bytes = sum(a.numel() * 8 for a in acts)
     state0 = bm.state_dict()
+    # one pre-bound launcher per (action slot, obs slot) pair that occurs
+    launchers = {}
 
     def one_step(s):
-        bm.step([a[s] for a in acts], obs=[r[s % R] for r in rings])
+        key = (s % A, s % R)
+        if key not in launchers:
+            launchers[key] = bm.prepare_step([a[key[0]] for a in acts], obs=[r[key[1]] for r in rings])
+        launchers[key]()
 
     def barrier():
         torch.cuda.synchronize()
@@ -183,18 +212,35 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def preheat(stream, seconds=0.2):
+        """untimed: bring the clocks to their loaded state before the warm-up + timed region"""
+        t0 = time.perf_counter()
+        s = 0
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(64):
+                one_step(s)
+                s += 1
+            stream.synchronize()
+        bm.load_state_dict(state0)
+
     stream = torch.cuda.Stream(device=dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     with torch.cuda.stream(stream):
-        for s in range(W):
-            one_step(s)
-        torch.cuda.synchronize()
-        launch0 = bm.launch_count
+        if args.preheat > 0:
+            preheat(stream, args.preheat)
         if args.path == "graph":
+            chunk = K
+            if K > 256:
+                chunk = max(d for d in range(1, 257) if K % d == 0)
+            for s in range(W + chunk):      # make every launcher of the chunk exist before capture
+                one_step(s)
+            bm.load_state_dict(state0)
+            torch.cuda.synchronize()
+            launch0 = bm.launch_count
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
-                for s in range(W, W + K):
+                for s in range(W, W + chunk):
                     one_step(s)
             captured = bm.launch_count - launch0
             bm.load_state_dict(state0)
@@ -204,29 +250,45 @@ def main():
             sampler = ClockSampler(local_rank)
             sampler.start()
             ev0.record(stream)
-            graph.replay()
+            for _ in range(K // chunk):
+                graph.replay()
             ev1.record(stream)
-            launches = captured
+            launches = captured * (K // chunk)
         elif args.path == "eager":
-            barrier()
-            sampler = ClockSampler(local_rank)
-            sampler.start()
-            ev0.record(stream)
-            for s in range(W, W + K):
+            for s in range(W + min(K, A * R)):
                 one_step(s)
-            ev1.record(stream)
-            launches = bm.launch_count - launch0
-        else:   # persistent rollout kernel: K steps in one launch
-            warm = [a[:W].contiguous() for a in acts]
-            timed = [a[W:].contiguous() for a in acts]
             bm.load_state_dict(state0)
-            bm.rollout(warm, ring=R, keep_obs=True)
+            for s in range(W):
+                one_step(s)
             barrier()
             sampler = ClockSampler(local_rank)
             sampler.start()
             launch0 = bm.launch_count
             ev0.record(stream)
-            out = bm.rollout(timed, ring=R, keep_obs=True)
+            for s in range(W, W + K):
+                one_step(s)
+            ev1.record(stream)
+            launches = bm.launch_count - launch0
+        else:   # persistent rollout kernel: K steps in one launch (actions [K, n, n_act] resident in HBM)
+            Kc = min(K, 2048)   # bound the action tensor; longer runs repeat the launch
+            gen.manual_seed(3 + rank)
+            timed = [torch.rand((Kc, g.n_envs, g.n_act), dtype=torch.float64, device=dev, generator=gen) for g in groups]
+            warm = [a[:max(W, 3)].contiguous() for a in timed]
+            bm.rollout(warm, ring=R, keep_obs=True)
+            out = bm.rollout(timed, ring=R, keep_obs=True)     # untimed: allocates the [K, n] outputs reused below
+            out = out if isinstance(out, list) else [out]
+            bm.load_state_dict(state0)
+            reps = max(1, K // Kc)
+            K = reps * Kc
+            barrier()
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            launch0 = bm.launch_count
+            ev0.record(stream)
+            for _ in range(reps):
+                bm.rollout(timed, ring=R, keep_obs=True, out=out)
+                if reps > 1:
+                    bm.load_state_dict(state0)
             ev1.record(stream)
             launches = bm.launch_count - launch0
         barrier()
@@ -239,31 +301,22 @@ def main():
     value = world * B * K / (ms * 1e-3)
 
     # ---- end to end through the public API with host buffers -------------------------------------------------
-    Ke = min(K, 50)
-    host_acts = [torch.rand((Ke, g.n_envs, g.n_act), dtype=torch.float64).pin_memory() for g in groups]
-    dev_acts = [torch.empty((g.n_envs, g.n_act), dtype=torch.float64, device=dev) for g in groups]
-    host_reward = torch.empty(bm.n_envs, dtype=torch.float64).pin_memory()
-    host_done = torch.empty(bm.n_envs, dtype=torch.uint8).pin_memory()
-    h2d = sum(a[0].numel() * 8 for a in host_acts)
-    d2h = bm.n_envs * 9
-
-    def e2e_step(s):
-        for d, h in zip(dev_acts, host_acts):
-            d.copy_(h[s], non_blocking=True)
-        bm.step(dev_acts, obs=[r[s % R] for r in rings])
-        host_reward.copy_(bm.reward, non_blocking=True)
-        host_done.copy_(bm.done, non_blocking=True)
-
+    # HostIO.step(): actions pinned-host -> device (one copy), fused kernel, reward + done device -> pinned-host (one copy)
+    Ke = min(K, 200)
     bm.load_state_dict(state0)
+    hio = bm.host_io(normalized=True, obs=[r[0] for r in rings])
+    for a in hio.actions:          # the caller's actions, in pinned host memory
+        a.copy_(torch.rand(tuple(a.shape), dtype=torch.float64))
     with torch.cuda.stream(stream):
         for s in range(3):
-            e2e_step(s)
+            hio.step()
         barrier()
         ev0.record(stream)
         for s in range(Ke):
-            e2e_step(s)
+            hio.step()
         ev1.record(stream)
         barrier()
+    h2d, d2h = hio.h2d_bytes, hio.d2h_bytes
     ms_e2e = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -280,12 +333,13 @@ def main():
             "data": "pymgrid25 scenario parameters + series (bundled), synthetic U[0,1) actions",
             "config": {"workload": "configs[2]: 65536 grids/GPU tiled from all 25 pymgrid25 configs, year-rollout style steps with full obs",
                        "batch_per_gpu": B, "global_batch": world * B, "forecast_horizon": 23, "path": args.path,
-                       "l2": f"obs ring of {R} buffers = {ring_bytes / 1e6:.0f} MB per GPU (> 126 MB L2), fresh actions every step",
+                       "l2": f"inputs larger than L2: obs ring of {R} buffers = {ring_bytes / 1e6:.0f} MB and action ring = {act_bytes / 1e6:.0f} MB per GPU (L2 126 MB)",
                        "parallelism": f"batch sharded over {world} GPU(s), no collective on the step path"},
             "gpu_launches": launches,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "note": "actions pinned-host->device and reward+done device->pinned-host every step; obs stay on device"},
+                    "note": "BatchedMicrogrid.host_io().step(): actions written into pinned host memory by the caller, one H2D copy, "
+                            "fused kernel, one D2H copy of reward+done, every step; observations stay on the device"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "mg_step_kernel" if args.path != "rollout" else "mg_rollout_kernel",
                          "bytes_per_launch": bytes_per_launch},

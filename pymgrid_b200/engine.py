@@ -98,6 +98,49 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+class HostIO:
+    """Host-side view of one step for callers whose actions live in host memory (the reference's callers all do).
+
+    `actions` (list of pinned [n, n_act] float64 host tensors, one per group; int32 [n] when discrete) is filled by
+    the caller; `step()` uploads them with ONE host->device copy, launches the fused kernel and brings reward + done
+    back with ONE device->host copy; `reward` / `done` are pinned host views valid after `sync()`.  Observations stay
+    on the device (`bm.groups[g].obs`) unless `fetch_obs()` is called.
+    """
+
+    def __init__(self, bm, normalized=True, discrete=False, obs=True):
+        self.bm = bm
+        dt = torch.int32 if discrete else torch.float64
+        item = 4 if discrete else 8
+        sizes = [g.n_envs * (1 if discrete else g.n_act) for g in bm.groups]
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += (n * item + 15) // 16 * 16 // item      # keep every group's block 16-byte aligned
+        self._h_act = torch.empty(total, dtype=dt).pin_memory()
+        self._d_act = torch.empty(total, dtype=dt, device=bm.device)
+        shape = (lambda g: (g.n_envs,)) if discrete else (lambda g: (g.n_envs, g.n_act))
+        self.actions = [self._h_act[o:o + n].view(shape(g)) for o, n, g in zip(offs, sizes, bm.groups)]
+        d_views = [self._d_act[o:o + n].view(shape(g)) for o, n, g in zip(offs, sizes, bm.groups)]
+        self._h_out = torch.empty(bm.n_envs * 9, dtype=torch.uint8).pin_memory()
+        self.reward = self._h_out[:bm.n_envs * 8].view(torch.float64)
+        self.done = self._h_out[bm.n_envs * 8:]
+        self._launch = bm.prepare_step(d_views if len(d_views) > 1 else d_views[0], normalized=normalized, obs=obs,
+                                       discrete=discrete)
+        self.h2d_bytes = self._h_act.numel() * item
+        self.d2h_bytes = self._h_out.numel()
+
+    def step(self):
+        self._d_act.copy_(self._h_act, non_blocking=True)
+        self._launch()
+        self._h_out.copy_(self.bm._out, non_blocking=True)
+
+    def sync(self):
+        torch.cuda.current_stream(self.bm.device).synchronize()
+
+    def fetch_obs(self):
+        return [g.obs.cpu() for g in self.bm.groups]
+
+
 class BatchedMicrogrid:
     def __init__(self, configs: Sequence[MicrogridParams], env_config, device=None, obs_order="gym_sorted",
                  with_info=False, with_flags=True, remove_redundant_gensets=True, action_order=None):
@@ -181,8 +224,10 @@ class BatchedMicrogrid:
         self.env_group = env_arch
         self.env_slot = np.empty(self.n_envs, dtype=np.int64)
         self.groups: List[Group] = []
-        self.reward = torch.zeros(self.n_envs, dtype=f64, device=dev)       # group-major flat buffers
-        self.done = torch.zeros(self.n_envs, dtype=torch.uint8, device=dev)
+        # group-major flat outputs; reward and done share one allocation so one D2H copy returns both
+        self._out = torch.zeros(self.n_envs * 9, dtype=torch.uint8, device=dev)
+        self.reward = self._out[:self.n_envs * 8].view(f64)
+        self.done = self._out[self.n_envs * 8:]
         start = 0
         for gi, arch in enumerate(order):
             ids = np.nonzero(env_arch == gi)[0]
@@ -318,6 +363,25 @@ class BatchedMicrogrid:
             return obs_bufs[0], g.reward, g.done, g.info
         return obs_bufs, [g.reward for g in self.groups], [g.done for g in self.groups], [g.info for g in self.groups]
 
+    def prepare_step(self, actions, normalized=True, obs=True, discrete=False):
+        """Bind the argument block of a step ONCE for fixed buffers and return a zero-argument launcher: the per-call
+        host cost drops to one ctypes call (used by HostIO and by loops that step the same buffers repeatedly)."""
+        io, obs_bufs = self._io(dactions=actions, obs=obs) if discrete else self._io(actions=actions, obs=obs)
+        lib, handle, norm = self._lib, self._handle, int(bool(normalized))
+        stream_of, dev = torch.cuda.current_stream, self.device
+        if discrete:
+            def launch():
+                rc = lib.mg_step_discrete(handle, io, stream_of(dev).cuda_stream)
+                if rc:
+                    _cabi.check(rc, "mg_step_discrete")
+        else:
+            def launch():
+                rc = lib.mg_step(handle, io, norm, stream_of(dev).cuda_stream)
+                if rc:
+                    _cabi.check(rc, "mg_step")
+        launch.keepalive = (io, obs_bufs, actions)
+        return launch
+
     def step(self, actions, normalized=True, obs=True):
         """Microgrid.run for every env (reference microgrid.py:227-325).  actions: float64 [n, n_act] per group,
         columns per `Group.act_cols`.  Returns (obs, reward, done, info) as device tensors (lists for > 1 group)."""
@@ -342,23 +406,26 @@ class BatchedMicrogrid:
         _cabi.check(self._lib.mg_observe(self._handle, io, self._stream()), "mg_observe")
         return obs_bufs[0] if self.single_group else obs_bufs
 
-    def rollout(self, actions, normalized=True, discrete=False, ring=1, keep_obs=True, reward_sum=False):
+    def rollout(self, actions, normalized=True, discrete=False, ring=1, keep_obs=True, reward_sum=False, out=None):
         """n_steps consecutive steps in one persistent kernel.  actions: per group [n_steps, n, n_act] float64
-        (or [n_steps, n] int32 when discrete).  Returns dict(reward=[n_steps, n], done=..., obs_ring=[ring, n, D])."""
+        (or [n_steps, n] int32 when discrete).  Returns dict(reward=[n_steps, n], done=..., obs_ring=[ring, n, D]);
+        pass a previous return value (list of dicts) as `out` to reuse its buffers."""
+        if out is not None and isinstance(out, dict):
+            out = [out]
         acts = self._per_group(actions, "actions")
         n_steps = acts[0].shape[0]
         io = (MgRolloutIO * len(self.groups))()
-        out = []
+        outs = []
         for gi, g in enumerate(self.groups):
             a = acts[gi]
             want = (n_steps, g.n_envs) if discrete else (n_steps, g.n_envs, g.n_act)
             if tuple(a.shape) != want or a.dtype != (torch.int32 if discrete else torch.float64) or not a.is_contiguous():
                 raise ValueError(f"group {gi}: rollout actions must be contiguous {want}")
-            r = dict(reward=torch.empty((n_steps, g.n_envs), dtype=torch.float64, device=self.device),
+            r = out[gi] if out is not None else dict(reward=torch.empty((n_steps, g.n_envs), dtype=torch.float64, device=self.device),
                      done=torch.empty((n_steps, g.n_envs), dtype=torch.uint8, device=self.device),
                      obs_ring=torch.empty((ring, g.n_envs, g.obs_dim), dtype=torch.float64, device=self.device) if keep_obs else None,
                      reward_sum=torch.empty(g.n_envs, dtype=torch.float64, device=self.device) if reward_sum else None)
-            out.append(r)
+            outs.append(r)
             if discrete:
                 io[gi].dactions = _ptr(a)
             else:
@@ -369,7 +436,11 @@ class BatchedMicrogrid:
             _cabi.check(self._lib.mg_rollout_discrete(self._handle, io, n_steps, ring, self._stream()), "mg_rollout_discrete")
         else:
             _cabi.check(self._lib.mg_rollout(self._handle, io, n_steps, ring, int(bool(normalized)), self._stream()), "mg_rollout")
-        return out[0] if self.single_group else out
+        return outs[0] if self.single_group else outs
+
+    def host_io(self, normalized=True, discrete=False, obs=True):
+        """Pinned host staging for a host-resident control loop (see HostIO)."""
+        return HostIO(self, normalized=normalized, discrete=discrete, obs=obs)
 
     # ------------------------------------------------------------------------------------------------------
     @property
