@@ -29,7 +29,7 @@ extern "C" {
 
 #define MG_ABI_VERSION 1
 #define MG_MAX_GROUPS 8
-#define MG_N_INFO 12
+#define MG_N_INFO 16
 #define MG_PLIST_WIDTH 3
 
 /* return codes */
@@ -52,7 +52,9 @@ enum {
     MG_INFO_LOAD_MET = 0, MG_INFO_PV_USED = 1, MG_INFO_CURTAILMENT = 2, MG_INFO_LOSS_LOAD = 3,
     MG_INFO_OVERGENERATION = 4, MG_INFO_GENSET_PRODUCTION = 5, MG_INFO_GENSET_CO2 = 6,
     MG_INFO_BATTERY_DISCHARGE = 7, MG_INFO_BATTERY_CHARGE = 8, MG_INFO_GRID_IMPORT = 9,
-    MG_INFO_GRID_EXPORT = 10, MG_INFO_GRID_CO2 = 11
+    MG_INFO_GRID_EXPORT = 10, MG_INFO_GRID_CO2 = 11,
+    /* per-module rewards (the 'reward' column each module logs, base_module.py:276-290); load and pv are 0.0 */
+    MG_INFO_REWARD_GENSET = 12, MG_INFO_REWARD_BATTERY = 13, MG_INFO_REWARD_GRID = 14, MG_INFO_REWARD_UNBALANCED = 15
 };
 
 /* per-env event flags: where the reference raises (or, with raise_errors=False, silently clips) */
@@ -66,7 +68,11 @@ enum {
     MG_FLAG_BAD_ACTION = 1u << 6,        /* ValueError     envs/discrete/discrete.py:84 (action not in space) */
     MG_FLAG_CLIP_GENSET = 1u << 8,       /* ValueError when raise_errors=True, base_module.py:213-221   */
     MG_FLAG_CLIP_BATTERY = 1u << 9,
-    MG_FLAG_CLIP_GRID = 1u << 10
+    MG_FLAG_CLIP_GRID = 1u << 10,
+    /* direction bits (not errors): which info key the reference would have written for this step */
+    MG_FLAG_BATTERY_SINK = 1u << 12,     /* battery acted as a sink: 'absorbed_energy' (else 'provided_energy')      */
+    MG_FLAG_GRID_SINK = 1u << 13,        /* grid exported: 'absorbed_energy'                                          */
+    MG_FLAG_EXCESS = 1u << 14            /* microgrid.py:286 excess branch: unbalanced module absorbed (else provided) */
 };
 
 /* modules in a priority-list element (algos/priority_list/priority_list_element.py) */
@@ -165,12 +171,13 @@ typedef struct MgStepIO {
 /* per-group arguments of a multi-step rollout: leading dimension is the step */
 typedef struct MgRolloutIO {
     const double *actions;   /* [n_steps, n, n_act] (mg_rollout)                                              */
-    const int32_t *dactions; /* [n_steps, n]        (mg_rollout_discrete)                                     */
+    const int32_t *dactions; /* [n_steps, n]        (mg_rollout_discrete); [n] when dactions_const != 0         */
     double *obs_ring;        /* [ring, n, obs_dim]: step s writes slot s % ring; NULL to skip observations    */
     double *reward;          /* [n_steps, n]                                                                  */
     uint8_t *done;           /* [n_steps, n]                                                                  */
     double *reward_sum;      /* [n] sum over the rollout in step order, or NULL                               */
     uint32_t *flags;         /* [n] OR over the rollout, or NULL                                              */
+    int64_t dactions_const;  /* != 0: the same priority list every step -- rule-based control (algos/rbc/rbc.py:64-93) */
 } MgRolloutIO;
 
 typedef struct MgHandle MgHandle;

@@ -234,7 +234,8 @@ void orc_run(OrcGrid *g, const double *control, int normalized, int order, doubl
         }
         double co2 = g->co2_per_unit * p;                                         /* :165 */
         double cost = g->genset_cost * p + g->gen_cost_per_unit_co2 * co2;        /* :186, :181, :205 */
-        reward += -1.0 * cost;                                                    /* :210 */
+        inf[ORC_INFO_REWARD_GENSET] = -1.0 * cost;                                /* :210 */
+        reward += inf[ORC_INFO_REWARD_GENSET];
         provided += p;
         inf[ORC_INFO_GENSET_PRODUCTION] = p;
         inf[ORC_INFO_GENSET_CO2] = co2;
@@ -255,6 +256,7 @@ void orc_run(OrcGrid *g, const double *control, int normalized, int order, doubl
             provided += p;
             inf[ORC_INFO_BATTERY_DISCHARGE] = p;
         } else {
+            err |= ORC_BATTERY_SINK;
             double e = -1.0 * a;
             double mc = fmin(g->max_charge, g->max_capacity - g->charge) / g->efficiency; /* :288-291 */
             if (e > mc) { e = mc; err |= ORC_CLIP_BATTERY; }
@@ -268,7 +270,8 @@ void orc_run(OrcGrid *g, const double *control, int normalized, int order, doubl
             if (!np_isclose(g->charge, g->min_capacity, 1e-5, 1e-8)) err |= ORC_ERR_BATTERY_MIN_CAP;
             g->charge = g->min_capacity;
         }
-        reward += -1.0 * (fabs(internal) * g->battery_cost_cycle); /* :121, get_cost :147 */
+        inf[ORC_INFO_REWARD_BATTERY] = -1.0 * (fabs(internal) * g->battery_cost_cycle); /* :121, get_cost :147 */
+        reward += inf[ORC_INFO_REWARD_BATTERY];
     }
     /* ---- controllable: grid (source_and_sink) grid_module.py ---- */
     if (g->has_grid) {
@@ -282,15 +285,18 @@ void orc_run(OrcGrid *g, const double *control, int normalized, int order, doubl
             if (a > mp) { p = mp; err |= ORC_CLIP_GRID; }
             else p = a;
             double co2 = p * row[2];                                           /* :221-224 */
-            reward += -1 * row[0] * p + (-1.0 * g->grid_cost_per_unit_co2 * co2); /* :167-169, :197 */
+            inf[ORC_INFO_REWARD_GRID] = -1 * row[0] * p + (-1.0 * g->grid_cost_per_unit_co2 * co2); /* :167-169, :197 */
+            reward += inf[ORC_INFO_REWARD_GRID];
             provided += p;
             inf[ORC_INFO_GRID_IMPORT] = p;
             inf[ORC_INFO_GRID_CO2] = co2;
         } else { /* export */
+            err |= ORC_GRID_SINK;
             double e = -1.0 * a;
             double mc = g->max_export * status; /* :318-320 */
             if (e > mc) { e = mc; err |= ORC_CLIP_GRID; }
-            reward += row[1] * e + (-1.0 * g->grid_cost_per_unit_co2 * 0.0); /* :170-172, :225-226 */
+            inf[ORC_INFO_REWARD_GRID] = row[1] * e + (-1.0 * g->grid_cost_per_unit_co2 * 0.0); /* :170-172, :225-226 */
+            reward += inf[ORC_INFO_REWARD_GRID];
             consumed += e;
             inf[ORC_INFO_GRID_EXPORT] = e;
         }
@@ -301,6 +307,7 @@ void orc_run(OrcGrid *g, const double *control, int normalized, int order, doubl
     double difference = provided - consumed;
     double pv = g->pv_ts[t];
     if (difference > 0) {
+        err |= ORC_EXCESS;
         /* pv: not a sink -> step(0.0) -> as_source(0.0) -> provides 0.0, curtailment = pv - 0.0 */
         double pv_used = 0.0;
         inf[ORC_INFO_PV_USED] = pv_used;
@@ -311,7 +318,8 @@ void orc_run(OrcGrid *g, const double *control, int normalized, int order, doubl
         double excess = difference;
         inf[ORC_INFO_OVERGENERATION] = excess;
         consumed += excess;
-        reward += -1.0 * (g->overgeneration_cost * excess); /* unbalanced_energy_module.py:28-36,65-68 */
+        inf[ORC_INFO_REWARD_UNBALANCED] = -1.0 * (g->overgeneration_cost * excess); /* unbalanced_energy_module.py:28-36,65-68 */
+        reward += inf[ORC_INFO_REWARD_UNBALANCED];
     } else {
         double needed = -difference;
         double pv_used = (pv < needed) ? pv : needed; /* microgrid.py:305-310 */
@@ -322,7 +330,8 @@ void orc_run(OrcGrid *g, const double *control, int normalized, int order, doubl
         needed -= pv_used;
         inf[ORC_INFO_LOSS_LOAD] = needed;
         provided += needed;
-        reward += -1.0 * (g->loss_load_cost * needed);
+        inf[ORC_INFO_REWARD_UNBALANCED] = -1.0 * (g->loss_load_cost * needed);
+        reward += inf[ORC_INFO_REWARD_UNBALANCED];
     }
     done |= ts_done; /* pv is a time-series module too */
     if (!np_isclose(provided, consumed, 1e-5, 1e-8)) err |= ORC_ERR_BALANCE; /* microgrid.py:321-323 */

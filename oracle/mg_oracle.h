@@ -33,7 +33,11 @@ enum {
     ORC_INFO_GRID_IMPORT = 9,
     ORC_INFO_GRID_EXPORT = 10,
     ORC_INFO_GRID_CO2 = 11,
-    ORC_N_INFO = 12
+    ORC_INFO_REWARD_GENSET = 12, /* per-module 'reward' log entries, base_module.py:276-290 */
+    ORC_INFO_REWARD_BATTERY = 13,
+    ORC_INFO_REWARD_GRID = 14,
+    ORC_INFO_REWARD_UNBALANCED = 15,
+    ORC_N_INFO = 16
 };
 
 /* error / event flags (the reference raises exceptions or clips silently at these points) */
@@ -46,7 +50,10 @@ enum {
     ORC_ERR_STEP_PAST_END     = 1u << 5,   /* IndexError on ts[t] when t >= len                          */
     ORC_CLIP_GENSET           = 1u << 8,   /* raise_errors=True would raise ValueError here              */
     ORC_CLIP_BATTERY          = 1u << 9,   /*   (base_module.py:213-221, 265-268)                        */
-    ORC_CLIP_GRID             = 1u << 10
+    ORC_CLIP_GRID             = 1u << 10,
+    ORC_BATTERY_SINK          = 1u << 12,  /* direction bits: which info key the reference wrote                 */
+    ORC_GRID_SINK             = 1u << 13,
+    ORC_EXCESS                = 1u << 14
 };
 
 enum { ORC_ORDER_GYM_SORTED = 0, ORC_ORDER_CONTAINER = 1 };

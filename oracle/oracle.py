@@ -11,9 +11,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
-N_INFO = 12
+N_INFO = 16
 INFO_NAMES = ("load_met", "pv_used", "curtailment", "loss_load", "overgeneration", "genset_production",
-              "genset_co2", "battery_discharge", "battery_charge", "grid_import", "grid_export", "grid_co2")
+              "genset_co2", "battery_discharge", "battery_charge", "grid_import", "grid_export", "grid_co2",
+              "reward_genset", "reward_battery", "reward_grid", "reward_unbalanced")
 ORDER_GYM_SORTED, ORDER_CONTAINER = 0, 1
 MOD_GENSET, MOD_BATTERY, MOD_GRID = 0, 1, 2
 

@@ -10,7 +10,7 @@ from . import build as _build
 
 MG_ABI_VERSION = 1
 MG_MAX_GROUPS = 8
-MG_N_INFO = 12
+MG_N_INFO = 16
 MG_PLIST_WIDTH = 3
 MG_OBS_GYM_SORTED, MG_OBS_CONTAINER = 0, 1
 MG_MOD_NONE, MG_MOD_GENSET, MG_MOD_BATTERY, MG_MOD_GRID = -1, 0, 1, 2
@@ -19,11 +19,15 @@ FLAG_NAMES = {
     1 << 0: "GENSET_GOAL_RANGE", 1 << 1: "GENSET_AS_SINK", 1 << 2: "BALANCE", 1 << 3: "BATTERY_MIN_CAP",
     1 << 4: "NEGATIVE_ABSORB", 1 << 5: "STEP_PAST_END", 1 << 6: "BAD_ACTION",
     1 << 8: "CLIP_GENSET", 1 << 9: "CLIP_BATTERY", 1 << 10: "CLIP_GRID",
+    1 << 12: "BATTERY_SINK", 1 << 13: "GRID_SINK", 1 << 14: "EXCESS",
 }
+FLAG_BATTERY_SINK, FLAG_GRID_SINK, FLAG_EXCESS = 1 << 12, 1 << 13, 1 << 14
+FLAG_CLIP_MASK = 0x700
 FLAG_ERROR_MASK = 0x7f      # the reference raises at these; the CLIP_* bits only raise under raise_errors=True
 
 INFO_NAMES = ("load_met", "pv_used", "curtailment", "loss_load", "overgeneration", "genset_production",
-              "genset_co2", "battery_discharge", "battery_charge", "grid_import", "grid_export", "grid_co2")
+              "genset_co2", "battery_discharge", "battery_charge", "grid_import", "grid_export", "grid_co2",
+              "reward_genset", "reward_battery", "reward_grid", "reward_unbalanced")
 
 _d, _i32, _vp = C.c_double, C.c_int32, C.c_void_p
 
@@ -70,7 +74,7 @@ class MgStepIO(C.Structure):
 
 class MgRolloutIO(C.Structure):
     _fields_ = [("actions", _vp), ("dactions", _vp), ("obs_ring", _vp), ("reward", _vp), ("done", _vp),
-                ("reward_sum", _vp), ("flags", _vp)]
+                ("reward_sum", _vp), ("flags", _vp), ("dactions_const", C.c_int64)]
 
 
 class EngineError(RuntimeError):

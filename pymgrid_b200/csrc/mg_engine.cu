@@ -68,7 +68,7 @@ struct DevGroup {
     const uint8_t *mask;
     // rollout io
     double *reward_sum;
-    int64_t act_step_stride, out_step_stride, obs_slot_stride;
+    int64_t act_step_stride, out_step_stride, obs_slot_stride, dact_step_stride;
 };
 
 struct LaunchParams {
@@ -242,6 +242,7 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
     double reward = 0.0, provided = 0.0, consumed = 0.0;
     const int done = (s.t >= final_step - 1);   // base_timeseries_module.py:124-125, before t += 1
     double i_gen = 0.0, i_gen_co2 = 0.0, i_dis = 0.0, i_chg = 0.0, i_imp = 0.0, i_exp = 0.0, i_gco2 = 0.0;
+    double r_gen = 0.0, r_bat = 0.0, r_grid = 0.0, r_unb = 0.0;   // per-module rewards (info block only)
 
     // LoadModule.update, load_module.py:86-91
     const double load = -1 * raw.load;
@@ -266,7 +267,8 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
         }
         const double co2 = c->gen_co2_per_unit * p;
         const double cost = c->gen_cost * p + c->gen_cost_per_unit_co2 * co2;
-        reward += -1.0 * cost;
+        r_gen = -1.0 * cost;
+        reward += r_gen;
         provided += p;
         i_gen = p;
         i_gen_co2 = co2;
@@ -283,6 +285,7 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
             provided += p;
             i_dis = p;
         } else {
+            flags |= MG_FLAG_BATTERY_SINK;
             double e = -1.0 * a;
             const double mc = fmin(c->bat_max_charge, c->bat_max_capacity - s.charge) / c->bat_efficiency;
             if (e > mc) { e = mc; flags |= MG_FLAG_CLIP_BATTERY; }
@@ -296,7 +299,8 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
             if (!np_isclose(s.charge, c->bat_min_capacity, 1e-5, 1e-8)) flags |= MG_FLAG_BATTERY_MIN_CAP;
             s.charge = c->bat_min_capacity;
         }
-        reward += -1.0 * (fabs(internal) * c->bat_cost_cycle);
+        r_bat = -1.0 * (fabs(internal) * c->bat_cost_cycle);
+        reward += r_bat;
     }
     if (G.has_grid) {   // GridModule, grid_module.py:134-228, :314-320
         const double a = normalized ? (c->grid_act_low + c->grid_act_spread * a_grid) : a_grid;
@@ -306,15 +310,18 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
             if (a > mp) { p = mp; flags |= MG_FLAG_CLIP_GRID; }
             else p = a;
             const double co2 = p * raw.co2;
-            reward += -1 * raw.imp * p + (-1.0 * c->grid_cost_per_unit_co2 * co2);
+            r_grid = -1 * raw.imp * p + (-1.0 * c->grid_cost_per_unit_co2 * co2);
+            reward += r_grid;
             provided += p;
             i_imp = p;
             i_gco2 = co2;
         } else {
+            flags |= MG_FLAG_GRID_SINK;
             double e = -1.0 * a;
             const double mc = c->grid_max_export * raw.status;
             if (e > mc) { e = mc; flags |= MG_FLAG_CLIP_GRID; }
-            reward += raw.exp_ * e + (-1.0 * c->grid_cost_per_unit_co2 * 0.0);
+            r_grid = raw.exp_ * e + (-1.0 * c->grid_cost_per_unit_co2 * 0.0);
+            reward += r_grid;
             consumed += e;
             i_exp = e;
         }
@@ -323,12 +330,14 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
     const double difference = provided - consumed;
     double pv_used, loss = 0.0, overgen = 0.0;
     if (difference > 0) {
+        flags |= MG_FLAG_EXCESS;
         pv_used = 0.0;
         provided += pv_used;
         reward += 0.0;
         overgen = difference;
         consumed += overgen;
-        reward += -1.0 * (c->overgeneration_cost * overgen);
+        r_unb = -1.0 * (c->overgeneration_cost * overgen);
+        reward += r_unb;
     } else {
         double needed = -difference;
         pv_used = (raw.pv < needed) ? raw.pv : needed;
@@ -337,7 +346,8 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
         needed -= pv_used;
         loss = needed;
         provided += needed;
-        reward += -1.0 * (c->loss_load_cost * needed);
+        r_unb = -1.0 * (c->loss_load_cost * needed);
+        reward += r_unb;
     }
     if (!np_isclose(provided, consumed, 1e-5, 1e-8)) flags |= MG_FLAG_BALANCE;
     s.t += 1;
@@ -357,6 +367,10 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
         info[MG_INFO_GRID_IMPORT] = i_imp;
         info[MG_INFO_GRID_EXPORT] = i_exp;
         info[MG_INFO_GRID_CO2] = i_gco2;
+        info[MG_INFO_REWARD_GENSET] = r_gen;
+        info[MG_INFO_REWARD_BATTERY] = r_bat;
+        info[MG_INFO_REWARD_GRID] = r_grid;
+        info[MG_INFO_REWARD_UNBALANCED] = r_unb;
     }
 }
 
@@ -620,7 +634,7 @@ __device__ __forceinline__ StepInputs fetch_inputs(const LaunchParams &P, const 
     in.dact = 0;
     in.act.goal = in.act.gen = in.act.bat = in.act.grid = 0.0;
     if (P.mode == MODE_DISCRETE) {
-        in.dact = __ldg(G.dactions + (size_t)step * G.out_step_stride + e);
+        in.dact = __ldg(G.dactions + (size_t)step * G.dact_step_stride + e);
         if (in.valid && (in.dact < 0 || in.dact >= c->plist_count)) {
             in.valid = false;
             in.invalid_flag = MG_FLAG_BAD_ACTION;
@@ -1070,6 +1084,7 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
         d.done = io[g].done; d.reward_sum = io[g].reward_sum; d.flags = io[g].flags; d.info = nullptr; d.mask = nullptr;
         d.act_step_stride = (int64_t)d.n_envs * d.n_act;
         d.out_step_stride = d.n_envs;
+        d.dact_step_stride = io[g].dactions_const ? 0 : d.n_envs;
         d.obs_slot_stride = (int64_t)d.n_envs * d.obs_dim;
         if (mode == MODE_STEP && !d.actions) return fail(MG_E_INVALID, "mg_rollout: null actions");
         if (mode == MODE_DISCRETE && (!d.dactions || !P.plist)) return fail(MG_E_INVALID, "mg_rollout_discrete: null actions or priority lists");

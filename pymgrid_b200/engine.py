@@ -406,19 +406,39 @@ class BatchedMicrogrid:
         _cabi.check(self._lib.mg_observe(self._handle, io, self._stream()), "mg_observe")
         return obs_bufs[0] if self.single_group else obs_bufs
 
-    def rollout(self, actions, normalized=True, discrete=False, ring=1, keep_obs=True, reward_sum=False, out=None):
+    def rbc_actions(self):
+        """Per group: the discrete action (priority-list index) rule-based control uses for every env
+        (reference: RuleBasedControl._get_priority_list, algos/rbc/rbc.py:31-44)."""
+        from .priority_list import rbc_priority_list
+        idx = [self.action_tables[k].index(rbc_priority_list(p)) for k, p in enumerate(self.configs)]
+        idx = np.asarray(idx, dtype=np.int32)
+        return [torch.from_numpy(idx[self.env_config[g.env_ids]]).to(self.device) for g in self.groups]
+
+    def rollout_rbc(self, n_steps, **kw):
+        """Rule-based control for n_steps on the device: one persistent kernel, the same priority list every step
+        (reference: RuleBasedControl.run, algos/rbc/rbc.py:64-93, without its early `break` on done)."""
+        acts = self.rbc_actions()
+        return self.rollout(acts if len(acts) > 1 else acts[0], discrete=True, constant_actions=True, n_steps=n_steps, **kw)
+
+    def rollout(self, actions, normalized=True, discrete=False, ring=1, keep_obs=True, reward_sum=False, out=None,
+                constant_actions=False, n_steps=None):
         """n_steps consecutive steps in one persistent kernel.  actions: per group [n_steps, n, n_act] float64
         (or [n_steps, n] int32 when discrete).  Returns dict(reward=[n_steps, n], done=..., obs_ring=[ring, n, D]);
         pass a previous return value (list of dicts) as `out` to reuse its buffers."""
         if out is not None and isinstance(out, dict):
             out = [out]
         acts = self._per_group(actions, "actions")
-        n_steps = acts[0].shape[0]
+        if constant_actions:
+            if not discrete or n_steps is None:
+                raise ValueError("constant_actions needs discrete=True and n_steps")
+        else:
+            n_steps = acts[0].shape[0]
         io = (MgRolloutIO * len(self.groups))()
         outs = []
         for gi, g in enumerate(self.groups):
             a = acts[gi]
-            want = (n_steps, g.n_envs) if discrete else (n_steps, g.n_envs, g.n_act)
+            io[gi].dactions_const = int(constant_actions)
+            want = (g.n_envs,) if constant_actions else (n_steps, g.n_envs) if discrete else (n_steps, g.n_envs, g.n_act)
             if tuple(a.shape) != want or a.dtype != (torch.int32 if discrete else torch.float64) or not a.is_contiguous():
                 raise ValueError(f"group {gi}: rollout actions must be contiguous {want}")
             r = out[gi] if out is not None else dict(reward=torch.empty((n_steps, g.n_envs), dtype=torch.float64, device=self.device),

@@ -1,0 +1,145 @@
+"""Gym-style environments on the batched engine -- the reference's `pymgrid.envs` surface, for B envs at once.
+
+reference: src/pymgrid/envs/base/base.py (BaseMicrogridEnv: `step`, `reset`, flat `observation_space`),
+src/pymgrid/envs/discrete/discrete.py (DiscreteMicrogridEnv: action = priority list), and
+src/pymgrid/envs/continuous/continuous.py (ContinuousMicrogridEnv; broken at the reference commit -- the intended
+semantics are implemented: flat Box action in [0,1]^n_act = the controllable modules' normalised actions,
+`Microgrid.run(normalized=True)`, flattened normalised observation).
+
+`step(actions)` takes / returns torch DEVICE tensors with a leading batch dimension and follows the old 4-tuple Gym API
+like the reference: `(obs [B, D], reward [B], done [B], info)`.  With `batch=None` the env is a single microgrid and
+`step` takes / returns the reference's host types (int / np.ndarray action, np.ndarray observation, float, bool, dict).
+gym itself is not a dependency: `Box` / `Discrete` below carry the attributes callers read (`shape`, `low`, `high`, `n`,
+`sample`, `contains`).
+"""
+import numpy as np
+import torch
+
+from . import views
+from .engine import BatchedMicrogrid
+from .scenario import load_pymgrid25
+
+
+class Box:
+    def __init__(self, low, high, shape, dtype=np.float64):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self.low = np.full(self.shape, low, dtype=self.dtype)
+        self.high = np.full(self.shape, high, dtype=self.dtype)
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    __contains__ = contains
+
+    def __repr__(self):
+        return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n, self.shape, self.dtype = int(n), (), np.dtype(np.int64)
+
+    def sample(self):
+        return int(np.random.randint(self.n))
+
+    def contains(self, x):
+        return isinstance(x, (int, np.integer)) and 0 <= int(x) < self.n
+
+    __contains__ = contains
+
+    def __repr__(self):
+        return f"Discrete({self.n})"
+
+
+class _BaseEnv:
+    """Shared plumbing: one architecture (all envs share obs / action layout), B replicas or B heterogeneous configs."""
+
+    def __init__(self, configs, env_config=None, batch=None, device=None, obs_order="gym_sorted", with_info=False):
+        configs = list(configs) if isinstance(configs, (list, tuple)) else [configs]
+        self.single = batch is None and env_config is None
+        if env_config is None:
+            env_config = np.arange(1 if batch is None else batch) % len(configs)
+        if len({c.arch for c in configs}) != 1:
+            raise ValueError("an env batch holds one architecture (use BatchedMicrogrid directly for mixed batches)")
+        self.engine = BatchedMicrogrid(configs, env_config, device=device, obs_order=obs_order,
+                                       with_info=with_info or self.single, with_flags=True,
+                                       action_order=None if obs_order == "gym_sorted" else views.CONTROL_ORDER)
+        self.group = self.engine.groups[0]
+        self.params = configs[0]
+        self.n_envs = self.engine.n_envs
+        self.observation_space = Box(0.0, 1.0, (self.group.obs_dim,))     # base.py:161-163
+        self._obs_order = obs_order
+
+    @classmethod
+    def from_scenario(cls, microgrid_number=0, batch=None, **kw):
+        """reference: BaseMicrogridEnv.from_scenario (envs/base/base.py:292-299)."""
+        return cls(load_pymgrid25(microgrid_number), batch=batch, **kw)
+
+    @property
+    def current_step(self):
+        return self.group.step if not self.single else int(self.group.step[0].item())
+
+    def reset(self, mask=None):
+        """reference: BaseMicrogridEnv.reset (base.py:165-167): flat observation after Microgrid.reset."""
+        obs = self.engine.reset(mask=mask)
+        return obs[0].cpu().numpy() if self.single else obs
+
+    def _finish(self, res):
+        obs, reward, done, info = res
+        if not self.single:
+            return obs, reward, done, ({} if info is None else {"info_block": info, "flags": self.group.flags})
+        flags = int(self.group.flags[0].item()) & 0xffffffff
+        return (obs[0].cpu().numpy(), float(reward[0].item()), bool(done[0].item()),
+                views.info_row_to_dict(info[0].cpu().numpy(), flags, self.params))
+
+    def __len__(self):
+        return len(self.params)
+
+
+class DiscreteMicrogridEnv(_BaseEnv):
+    """Action = index of a priority list (reference: envs/discrete/discrete.py:60-143)."""
+
+    def __init__(self, configs, env_config=None, batch=None, remove_redundant_gensets=True, **kw):
+        super().__init__(configs, env_config, batch, **kw)
+        self.actions_list = self.engine.action_tables[0]
+        self.action_space = Discrete(len(self.actions_list))
+        self._a = torch.zeros(self.n_envs, dtype=torch.int32, device=self.engine.device)
+
+    def step(self, action):
+        if self.single:
+            if action not in self.action_space:
+                raise ValueError(f" Action {action} not in action space {self.action_space}")   # discrete.py:84
+            self._a[0] = int(action)
+            action = self._a
+        return self._finish(self.engine.step_discrete(action))
+
+    def sample_action(self):
+        if self.single:
+            return self.action_space.sample()
+        return torch.randint(0, self.action_space.n, (self.n_envs,), dtype=torch.int32, device=self.engine.device)
+
+
+class ContinuousMicrogridEnv(_BaseEnv):
+    """Action = flat vector in [0,1]^n_act, the controllable modules' normalised actions concatenated in the env's
+    module order (`action_layout`); see the module docstring for the relation to the reference's class."""
+
+    def __init__(self, configs, env_config=None, batch=None, **kw):
+        super().__init__(configs, env_config, batch, **kw)
+        self.action_space = Box(0.0, 1.0, (self.group.n_act,))
+        self.action_layout = dict(self.group.act_cols)       # module name -> first column
+        self._a = torch.zeros((self.n_envs, self.group.n_act), dtype=torch.float64, device=self.engine.device)
+
+    def step(self, action, normalized=True):
+        if self.single:
+            self._a.copy_(torch.as_tensor(np.asarray(action, dtype=np.float64)).reshape(1, -1))
+            action = self._a
+        return self._finish(self.engine.step(action, normalized=normalized))
+
+    def sample_action(self):
+        if self.single:
+            return self.action_space.sample()
+        return torch.rand((self.n_envs, self.group.n_act), dtype=torch.float64, device=self.engine.device)

@@ -1,0 +1,303 @@
+"""Drop-in single-microgrid surface: `pymgrid.Microgrid`'s API on top of the batched engine (B = 1).
+
+Mirrors the reference class (src/pymgrid/microgrid/microgrid.py): `Microgrid.from_scenario(n)`, `run(control,
+normalized=True) -> (obs dict, reward float, done bool, info dict)`, `reset()`, `get_log()`, `sample_action()`,
+`get_empty_action()`, `state_dict()`, `state_series()`, `current_step / initial_step / final_step`, `len()`,
+`modules` / `fixed` / `flex` / `controllable` read-only module views.  Return values are the reference's exact Python
+types; every number comes from the CUDA engine (one env, one kernel launch + a small device->host read per call -- this
+wrapper exists for notebooks and control loops written against the reference; throughput lives in
+`BatchedMicrogrid`).  Only what the hot path needs is mirrored: no YAML dump, no plotting, no MPC conversion.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import views
+from ._cabi import FLAG_CLIP_MASK, FLAG_ERROR_MASK, FLAG_NAMES
+from .engine import BatchedMicrogrid
+from .params import MicrogridParams
+from .scenario import load_pymgrid25
+
+
+class ModuleView:
+    """Read-only view of one module: constructor parameters + the live state the reference's callers read
+    (max_production, max_consumption, soc, current_status, ...)."""
+
+    def __init__(self, microgrid, name):
+        self._m, self.name = microgrid, (name, 0)
+
+    def __repr__(self):
+        return f"ModuleView({self.name[0]})"
+
+    @property
+    def _p(self):
+        return self._m.params
+
+    @property
+    def current_step(self):
+        return self._m.current_step
+
+    # -- battery (battery_module.py:283-291) --
+    def _require(self, kind):
+        if self.name[0] != kind:
+            raise AttributeError(f"{self.name[0]} module has no such attribute")
+
+    @property
+    def current_charge(self):
+        self._require("battery")
+        return self._m._state()["charge"]
+
+    @property
+    def soc(self):
+        return self.current_charge / self._p.battery.max_capacity
+
+    @property
+    def max_production(self):
+        n, p, st = self.name[0], self._p, self._m._state()
+        if n == "battery":
+            b = p.battery
+            return min(b.max_discharge, st["charge"] - b.min_capacity) * b.efficiency
+        if n == "genset":       # genset_module.py:466-482
+            return st["genset"][0] * p.genset.running_max_production
+        if n == "grid":         # grid_module.py:314-316
+            return p.grid.max_import * p.grid.time_series[st["t"], 3]
+        if n == "pv":
+            return float(p.pv_ts[st["t"]])
+        if n == "unbalanced_energy":
+            return np.inf
+        raise AttributeError("max_production")
+
+    @property
+    def max_consumption(self):
+        n, p, st = self.name[0], self._p, self._m._state()
+        if n == "battery":
+            b = p.battery
+            return min(b.max_charge, b.max_capacity - st["charge"]) / b.efficiency
+        if n == "grid":
+            return p.grid.max_export * p.grid.time_series[st["t"], 3]
+        if n == "load":
+            return -1 * float(p.load_ts[st["t"]])
+        if n == "unbalanced_energy":
+            return np.inf
+        raise AttributeError("max_consumption")
+
+    @property
+    def min_production(self):
+        if self.name[0] == "genset":
+            return self._m._state()["genset"][0] * self._p.genset.running_min_production
+        return 0
+
+    @property
+    def current_status(self):
+        if self.name[0] == "genset":
+            return self._m._state()["genset"][0]
+        if self.name[0] == "grid":
+            return self._p.grid.time_series[self._m.current_step, 3]
+        raise AttributeError("current_status")
+
+    @property
+    def goal_status(self):
+        self._require("genset")
+        return self._m._state()["genset"][1]
+
+    def __getattr__(self, item):   # constructor parameters, e.g. battery.max_capacity, genset.genset_cost, grid.max_import
+        src = {"battery": self._p.battery, "genset": self._p.genset, "grid": self._p.grid}.get(self.name[0])
+        if src is not None and hasattr(src, item):
+            return getattr(src, item)
+        if item == "time_series":
+            return {"load": self._p.load_ts.reshape(-1, 1), "pv": self._p.pv_ts.reshape(-1, 1)}[self.name[0]]
+        if item == "forecast_horizon" and self.name[0] in ("load", "pv", "grid"):
+            return self._p.forecast_horizon
+        if item in ("loss_load_cost", "overgeneration_cost") and self.name[0] == "unbalanced_energy":
+            return getattr(self._p, item)
+        raise AttributeError(item)
+
+
+class ModuleContainerView(OrderedDict):
+    """`microgrid.modules`: name -> [module]; attribute access and the reference's iteration helpers."""
+
+    def __getattr__(self, item):
+        try:
+            return self[item]
+        except KeyError:
+            raise AttributeError(item)
+
+    def iterdict(self):
+        return self.items()
+
+    def iterlist(self):
+        return [m for lst in self.values() for m in lst]
+
+    def to_dict(self):
+        return dict(self)
+
+
+class Microgrid:
+    def __init__(self, params: MicrogridParams, device=None, obs_order="gym_sorted"):
+        if not isinstance(params, MicrogridParams):
+            raise TypeError("pymgrid_b200.Microgrid is built from MicrogridParams (see scenario.load_pymgrid25 / params.py)")
+        self.params = params
+        self._obs_order = obs_order
+        self._engine = BatchedMicrogrid([params], np.zeros(1, dtype=np.int64), device=device, obs_order=obs_order,
+                                        with_info=True, with_flags=True, action_order=views.CONTROL_ORDER)
+        self._g = self._engine.groups[0]
+        self._actions = torch.zeros((1, params.n_act), dtype=torch.float64, device=self._engine.device)
+        self._log_rows = []
+        self._initial_step, self._final_step = params.initial_step, params.final_step
+        self.raise_errors = False
+        names = ["load", "pv", "unbalanced_energy"] + (["genset"] if params.has_genset else []) + ["battery"] + \
+                (["grid"] if params.has_grid else [])
+        self._modules = ModuleContainerView((n, [ModuleView(self, n)]) for n in names)
+
+    # ---- construction ------------------------------------------------------------------------------------
+    @classmethod
+    def from_scenario(cls, microgrid_number=0, **kw):
+        """reference: Microgrid.from_scenario (microgrid.py:958-980) -- pymgrid25 benchmark grid n."""
+        return cls(load_pymgrid25(microgrid_number), **kw)
+
+    # ---- state -------------------------------------------------------------------------------------------
+    def _state(self):
+        g = self._g
+        gen = tuple(int(x) for x in self._engine.genset_status(0)[0].tolist()) if g.genset is not None else (0, 0, 0, 0)
+        return dict(t=int(g.step[0].item()), charge=float(g.charge[0].item()), genset=gen)
+
+    @property
+    def current_step(self):
+        return int(self._g.step[0].item())
+
+    @property
+    def initial_step(self):
+        return self._initial_step
+
+    @initial_step.setter
+    def initial_step(self, value):
+        self._initial_step = int(value)
+        self._engine.set_trajectories(np.array([self._initial_step]), np.array([self._final_step]))
+
+    @property
+    def final_step(self):
+        return self._final_step
+
+    @final_step.setter
+    def final_step(self, value):
+        self._final_step = int(value)
+        self._engine.set_trajectories(np.array([self._initial_step]), np.array([self._final_step]))
+
+    def __len__(self):
+        return len(self.params)
+
+    @property
+    def modules(self):
+        return self._modules
+
+    def _typed(self, kinds):
+        return ModuleContainerView((n, m) for n, m in self._modules.items() if n in kinds)
+
+    @property
+    def fixed(self):
+        return self._typed(("load",))
+
+    @property
+    def flex(self):
+        return self._typed(("pv", "unbalanced_energy"))
+
+    @property
+    def controllable(self):
+        return ModuleContainerView((n, self._modules[n]) for n in views.CONTROL_ORDER if n in self._modules)
+
+    # ---- the hot path ------------------------------------------------------------------------------------
+    def run(self, control, normalized=True):
+        """reference: Microgrid.run (microgrid.py:227-325).  Same arguments, return types, errors."""
+        p = self.params
+        row = views.control_dict_to_row(control, p, self._g.act_cols)
+        pre = self._state()
+        if pre["t"] >= len(p):
+            raise IndexError(f"index {pre['t']} is out of bounds for axis 0 with size {len(p)}")   # load_module.py:111
+        self._actions.copy_(torch.from_numpy(row).reshape(1, -1))
+        obs, reward, done, info = self._engine.step(self._actions, normalized=normalized)
+        flags = int(self._g.flags[0].item()) & 0xffffffff
+        self._raise_for_flags(flags)
+        obs_row, info_row = obs[0].cpu().numpy(), info[0].cpu().numpy()
+        r = float(reward[0].item())
+        post = self._state()
+        self._log_rows.append(views.log_row(p, views.state_dict(p, pre["t"], pre["charge"], pre["genset"]), info_row, r,
+                                            post["genset"]))
+        return (views.obs_row_to_dict(obs_row, p, self._obs_order), r, bool(done[0].item()),
+                views.info_row_to_dict(info_row, flags, p))
+
+    def _raise_for_flags(self, flags):
+        err = flags & FLAG_ERROR_MASK
+        if err:
+            names = [n for bit, n in FLAG_NAMES.items() if err & bit]
+            if err & (1 << 2):
+                raise RuntimeError("Microgrid modules unable to balance energy production with consumption.\n")
+            raise AssertionError(f"step rejected: {names}")
+        if self.raise_errors and flags & FLAG_CLIP_MASK:
+            names = [n for bit, n in FLAG_NAMES.items() if flags & FLAG_CLIP_MASK & bit]
+            raise ValueError(f"requested value outside the module's limits: {names}")    # base_module.py:79-93
+
+    def reset(self):
+        """reference: Microgrid.reset (microgrid.py:205-225): step = initial_step, logs flushed, battery / genset kept."""
+        obs = self._engine.reset()
+        self._log_rows = []
+        out = views.obs_row_to_dict(obs[0].cpu().numpy(), self.params, self._obs_order)
+        out["balance"], out["other"] = {}, {}
+        return out
+
+    # ---- actions -----------------------------------------------------------------------------------------
+    def sample_action(self, strict_bound=False, sample_flex_modules=False):
+        """reference: Microgrid.sample_action (microgrid.py:337-362): np.random.rand() per controllable module, genset
+        first (goal, energy).  `strict_bound` is only defined for grids without a genset, like in the reference."""
+        if strict_bound and self.params.has_genset:
+            raise TypeError("Unable to normalize scalar value, expected array-like of shape 2")   # utils/space.py:146-147
+        out = {}
+        for name in views.control_names(self.params):
+            if name == "genset":
+                out[name] = [np.array([np.random.rand(), np.random.rand()])]
+            else:
+                lo, hi = 0.0, 1.0
+                if strict_bound:
+                    m = self._modules[name][0]
+                    act_lo = {"battery": self.params.battery.min_act, "grid": -1 * self.params.grid.max_export if self.params.grid else 0}[name]
+                    act_hi = {"battery": self.params.battery.max_act, "grid": self.params.grid.max_import if self.params.grid else 0}[name]
+                    spread = (act_hi - act_lo) or 1.0
+                    lo = (-1 * m.max_consumption - act_lo) / spread
+                    hi = (m.max_production - act_lo) / spread
+                out[name] = [np.random.rand() * (hi - lo) + lo]
+        return out
+
+    def get_empty_action(self, sample_flex_modules=False):
+        return {name: [None] for name in views.control_names(self.params)}
+
+    # ---- introspection -----------------------------------------------------------------------------------
+    def state_dict(self, normalized=False):
+        st = self._state()
+        sd = views.state_dict(self.params, st["t"], st["charge"], st["genset"])
+        return {name: [dict(d)] for name, d in sd.items()}
+
+    def state_series(self, normalized=False):
+        import pandas as pd
+        st = self._state()
+        sd = views.state_dict(self.params, st["t"], st["charge"], st["genset"])
+        data = OrderedDict(((name, 0, k), v) for name, d in sd.items() for k, v in d.items())
+        return pd.Series(data)
+
+    def get_log(self, as_frame=True, drop_singleton_key=False):
+        """reference: Microgrid.get_log (microgrid.py:434-475): one row per step since the last reset."""
+        import pandas as pd
+        start = self.current_step - len(self._log_rows)
+        cols = list(self._log_rows[0].keys()) if self._log_rows else []
+        df = pd.DataFrame([list(r.values()) for r in self._log_rows], columns=pd.MultiIndex.from_tuples(
+            cols, names=["module_name", "module_number", "field"]) if cols else None,
+            index=pd.RangeIndex(start=start, stop=self.current_step))
+        if drop_singleton_key and cols:
+            df.columns = df.columns.remove_unused_levels()
+        return df if as_frame else df.to_dict()
+
+    @property
+    def log(self):
+        return self.get_log()
+
+    def __repr__(self):
+        return "Microgrid([" + ", ".join(f"{n} x 1" for n in self._modules) + "])"

@@ -36,3 +36,25 @@ def priority_lists(has_genset, has_grid, genset_running_min=None, remove_redunda
     if remove_redundant_gensets and has_genset and genset_running_min == 0:
         out = [pl for pl in out if (GENSET, 0) not in pl]
     return out
+
+
+def marginal_costs(p):
+    """`module.marginal_cost` of the controllable modules as the reference evaluates them when the controller is built:
+    battery_module.py:340-346, genset_module.py:519-521 (get_cost(1.0)), grid_module.py:322-324 (current import price)."""
+    out = {BATTERY: p.battery.battery_cost_cycle}
+    if p.genset is not None:
+        g = p.genset
+        out[GENSET] = g.genset_cost * 1.0 + g.cost_per_unit_co2 * (g.co2_per_unit * 1.0)
+    if p.grid is not None:
+        out[GRID] = float(p.grid.time_series[p.current_step, 0])
+    return out
+
+
+def rbc_priority_list(p, remove_redundant_gensets=True):
+    """RuleBasedControl's automatic list (algos/rbc/rbc.py:31-44): the FIRST priority list sorted by marginal cost,
+    ties broken towards the higher action number (priority_list_element.py:73-80).  Note the reference quirk kept
+    here: on genset grids the first list carries genset goal 0 (unless it was removed as redundant)."""
+    first = priority_lists(p.has_genset, p.has_grid, p.genset.running_min_production if p.genset is not None else None,
+                           remove_redundant_gensets)[0]
+    cost = marginal_costs(p)
+    return tuple(sorted(first, key=lambda el: (cost[el[0]], -el[1])))

@@ -33,14 +33,21 @@ from pymgrid.modules import BatteryModule, GensetModule, GridModule, LoadModule,
 
 SORTED_KEYS = ("battery", "genset", "grid", "load", "pv", "renewable")   # alphabetical, as gym.spaces.Dict sorts
 CONTROL_KEYS = ("genset", "battery", "grid")                            # container order of controllables
-INFO_COLS = 12
+INFO_COLS = 16
 
 
 def flat_obs(obs):
     return np.concatenate([np.asarray(x, dtype=np.float64).ravel() for k in SORTED_KEYS if k in obs for x in obs[k]])
 
 
-def info_vec(info):
+def module_reward(m, name):
+    """reward the module logged for the step just taken (ModularLogger, utils/logger.py:18-28)"""
+    if not hasattr(m.modules, name):
+        return 0.0
+    return float(getattr(m.modules, name)[0].log_dict()["reward"][-1])
+
+
+def info_vec(info, m=None):
     v = np.zeros(INFO_COLS)
     g = lambda name, key: float(info[name][0].get(key, 0.0)) if name in info else 0.0  # noqa: E731
     pv = "pv" if "pv" in info else "renewable"
@@ -51,6 +58,10 @@ def info_vec(info):
     v[5], v[6] = g("genset", "provided_energy"), g("genset", "co2_production")
     v[7], v[8] = g("battery", "provided_energy"), g("battery", "absorbed_energy")
     v[9], v[10], v[11] = g("grid", "provided_energy"), g("grid", "absorbed_energy"), g("grid", "co2_production")
+    if m is not None:
+        ub_name = "unbalanced_energy" if hasattr(m.modules, "unbalanced_energy") else "balancing"
+        v[12], v[13], v[14], v[15] = (module_reward(m, "genset"), module_reward(m, "battery"), module_reward(m, "grid"),
+                                      module_reward(m, ub_name))
     return v
 
 
@@ -86,7 +97,7 @@ def run_segment(m, actions, normalized=True):
     rewards, dones, obs, infos, states = [], [], [], [], []
     for a in actions:
         o, r, d, info = m.run(control_from_flat(m, a), normalized=normalized)
-        rewards.append(r); dones.append(d); obs.append(flat_obs(o)); infos.append(info_vec(info)); states.append(state_vec(m))
+        rewards.append(r); dones.append(d); obs.append(flat_obs(o)); infos.append(info_vec(info, m)); states.append(state_vec(m))
     return (np.array(rewards), np.array(dones, dtype=np.uint8), np.stack(obs), np.stack(infos), np.stack(states))
 
 
@@ -155,7 +166,7 @@ def make_year():
     _, r, _, info = m.run(a)
     out["legacy_s0_action"] = np.array([a["battery"][0], a["grid"][0]])
     out["legacy_s0_reward"] = np.array(r)
-    out["legacy_s0_info"] = info_vec(info)
+    out["legacy_s0_info"] = info_vec(info, m)
     np.savez_compressed(os.path.join(HERE, "pymgrid25_year.npz"), **out)
 
 
@@ -306,8 +317,51 @@ def make_custom():
     np.savez_compressed(os.path.join(HERE, "custom.npz"), **out)
 
 
+def make_log():
+    """Microgrid.get_log() after 30 random steps + a reset + 5 more steps, scenarios 0 / 1 / 2 (the three architectures)."""
+    out = {}
+    for n in (0, 1, 2):
+        m = Microgrid.from_scenario(n)
+        rng = np.random.default_rng(900 + n)
+        a = rng.random((30, n_act(m)))
+        run_segment(m, a)
+        df = m.get_log()
+        out[f"s{n}_actions"] = a
+        out[f"s{n}_columns"] = np.array(["|".join(map(str, c)) for c in df.columns])
+        out[f"s{n}_values"] = df.values.astype(np.float64)
+        out[f"s{n}_index"] = df.index.values
+        ser = m.state_series()
+        out[f"s{n}_state_series_index"] = np.array(["|".join(map(str, c)) for c in ser.index])
+        out[f"s{n}_state_series_values"] = ser.values.astype(np.float64)
+        m.reset()
+        assert len(m.get_log()) == 0
+        print("log", n, df.shape)
+    np.savez_compressed(os.path.join(HERE, "log.npz"), **out)
+
+
+def make_rbc():
+    """RuleBasedControl (algos/rbc/rbc.py): the automatically chosen priority list and the rewards it earns."""
+    from pymgrid.algos import RuleBasedControl
+    out = {}
+    for n in (0, 1, 2, 5, 9, 13):
+        m = Microgrid.from_scenario(n)
+        rbc = RuleBasedControl(m)
+        out[f"s{n}_list_mod"] = np.array([MOD_ID[el.module[0]] for el in rbc.priority_list], dtype=np.int8)
+        out[f"s{n}_list_act"] = np.array([el.action for el in rbc.priority_list], dtype=np.int8)
+        steps = None if n == 0 else 300
+        df = rbc.run(max_steps=steps)
+        out[f"s{n}_rewards"] = df[("balance", 0, "reward")].values.astype(np.float64)
+        out[f"s{n}_final_state"] = state_vec(rbc.microgrid)
+        print("rbc", n, [(el.module[0], el.action, el.marginal_cost) for el in rbc.priority_list], len(df), df[("balance", 0, "reward")].sum())
+    np.savez_compressed(os.path.join(HERE, "rbc.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["steps", "year", "discrete", "genset", "custom"]
+    which = sys.argv[1:] or ["steps", "year", "discrete", "genset", "custom", "log", "rbc"]
+    if "rbc" in which:
+        make_rbc()
+    if "log" in which:
+        make_log()
     if "steps" in which:
         make_pymgrid25_steps()
     if "year" in which:

@@ -73,3 +73,35 @@ def test_priority_tables_match_the_reference_action_lists(golden):
             assert list(pl) == [(int(m), int(a)) for m, a in zip(mod[row], act[row]) if m >= 0]
     assert len(priority_lists(True, True, 0.0)) == 6          # redundant genset-off lists removed (priority_list.py:53-67)
     assert len(priority_lists(True, True, 0.0, remove_redundant_gensets=False)) == 12
+
+
+def test_rbc_priority_list_matches_reference(golden):
+    """RuleBasedControl's automatic priority list (algos/rbc/rbc.py:31-44) for the recorded scenarios."""
+    from pymgrid_b200.priority_list import priority_lists, rbc_priority_list
+    from pymgrid_b200.scenario import load_pymgrid25
+    z = golden["rbc"]
+    for n in (0, 1, 2, 5, 9, 13):
+        p = load_pymgrid25(n)
+        pl = rbc_priority_list(p)
+        assert [m for m, _ in pl] == list(z[f"s{n}_list_mod"]) and [a for _, a in pl] == list(z[f"s{n}_list_act"])
+        assert pl in priority_lists(p.has_genset, p.has_grid, p.genset.running_min_production if p.genset else None)
+
+
+def test_oracle_rbc_rollout_matches_reference(golden):
+    """The oracle driven with the RBC list reproduces the reference controller's rewards (incl. the full year of
+    scenario 0: sum -956 059.6622849072)."""
+    import numpy as np
+    from oracle.oracle import OracleGrid
+    from pymgrid_b200.priority_list import rbc_priority_list
+    from pymgrid_b200.scenario import load_pymgrid25
+    z = golden["rbc"]
+    for n in (0, 1, 2, 5, 9, 13):
+        p = load_pymgrid25(n)
+        o = OracleGrid(p)
+        pl = rbc_priority_list(p)
+        want = z[f"s{n}_rewards"]
+        got = np.empty(len(want))
+        for k in range(len(want)):
+            _, got[k], _, _, _ = o.run(o.priority_control(list(pl)), normalized=False)
+        np.testing.assert_array_equal(got, want)
+    assert float(np.add.reduce(z["s0_rewards"])) == -956059.6622849072 or abs(z["s0_rewards"].sum() + 956059.6622849072) < 1e-6

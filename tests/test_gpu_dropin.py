@@ -1,0 +1,154 @@
+"""Drop-in surface on the GPU: `pymgrid_b200.Microgrid` (B = 1, reference Python types) and the env classes against
+the golden vectors recorded from the reference."""
+import numpy as np
+import pytest
+import torch
+
+from pymgrid_b200.scenario import load_pymgrid25
+
+pytestmark = pytest.mark.gpu
+SORTED = ("battery", "genset", "grid", "load", "pv")
+
+
+def control(p, flat):
+    out, i = {}, 0
+    if p.has_genset:
+        out["genset"] = [np.array(flat[i:i + 2])]
+        i += 2
+    out["battery"] = [float(flat[i])]
+    i += 1
+    if p.has_grid:
+        out["grid"] = [float(flat[i])]
+    return out
+
+
+@pytest.mark.parametrize("n", (0, 1, 2))
+def test_microgrid_run_returns_reference_types_and_values(golden, n):
+    from pymgrid_b200.microgrid import Microgrid
+    z = golden["pymgrid25_steps"]
+    m = Microgrid.from_scenario(n)
+    assert len(m) == 8760 and m.current_step == 0 and m.final_step == 8759
+    for k, a in enumerate(z[f"s{n}_a0"][:20]):
+        obs, reward, done, info = m.run(control(m.params, a))
+        assert isinstance(reward, float) and isinstance(done, bool) and isinstance(obs, dict) and isinstance(info, dict)
+        assert list(obs.keys()) == [x for x in ("load", "genset", "battery", "grid", "pv", "unbalanced_energy")
+                                    if x in ("load", "battery", "pv", "unbalanced_energy") or hasattr(m.modules, x)]
+        flat = np.concatenate([obs[name][0] for name in SORTED if name in obs])
+        np.testing.assert_array_equal(flat, z[f"s{n}_o0"][k])
+        assert reward == z[f"s{n}_r0"][k] and done == bool(z[f"s{n}_d0"][k])
+        assert info["load"][0]["absorbed_energy"] == z[f"s{n}_i0"][k][0]
+    assert m.current_step == 20
+    assert m.modules.battery[0].current_charge == z[f"s{n}_s0"][19][1]
+    if m.params.has_genset:
+        assert m.modules.genset[0].current_status == int(z[f"s{n}_s0"][19][2])
+    with pytest.raises(ValueError):
+        m.run({"grid": [0.5]})
+
+
+@pytest.mark.parametrize("n", (0, 1, 2))
+def test_get_log_matches_reference(golden, n):
+    from pymgrid_b200.microgrid import Microgrid
+    z = golden["log"]
+    m = Microgrid.from_scenario(n)
+    for a in z[f"s{n}_actions"]:
+        m.run(control(m.params, a))
+    df = m.get_log()
+    assert ["|".join(map(str, c)) for c in df.columns] == list(z[f"s{n}_columns"])
+    assert list(df.columns.names) == ["module_name", "module_number", "field"]
+    np.testing.assert_array_equal(df.values.astype(float), z[f"s{n}_values"])
+    np.testing.assert_array_equal(df.index.values, z[f"s{n}_index"])
+    ser = m.state_series()
+    assert ["|".join(map(str, c)) for c in ser.index] == list(z[f"s{n}_state_series_index"])
+    np.testing.assert_array_equal(ser.values.astype(float), z[f"s{n}_state_series_values"])
+    charge = m.modules.battery[0].current_charge
+    out = m.reset()
+    assert len(m.get_log()) == 0 and m.current_step == 0 and m.modules.battery[0].current_charge == charge
+    assert "balance" in out and "load" in out
+
+
+def test_legacy_seed_sample_action_known_answer(golden):
+    """np.random.seed(0); m.sample_action(strict_bound=True); m.run(...) on scenario 0."""
+    from pymgrid_b200.microgrid import Microgrid
+    z = golden["pymgrid25_year"]
+    m = Microgrid.from_scenario(0)
+    np.random.seed(0)
+    a = m.sample_action(strict_bound=True)
+    assert a == {"battery": [0.3032118806228314], "grid": [0.7151893663724195]}
+    _, reward, _, info = m.run(a)
+    assert reward == -544.8242524518755 == float(z["legacy_s0_reward"])
+    assert info["grid"][0] == {"provided_energy": 826.3271668700909, "co2_production": 198.1184728523399}
+    assert info["unbalanced_energy"][0] == {"absorbed_energy": 339.9448144937339}
+    assert m.get_empty_action() == {"battery": [None], "grid": [None]}
+
+
+def test_running_past_the_end_raises_like_the_reference():
+    from pymgrid_b200.microgrid import Microgrid
+    from tests.helpers import jump_to
+    m = Microgrid(jump_to(load_pymgrid25(0), 8759))
+    _, _, done, _ = m.run({"battery": [0.5], "grid": [0.5]})
+    assert done and m.current_step == 8760
+    with pytest.raises(IndexError):
+        m.run({"battery": [0.5], "grid": [0.5]})
+
+
+def test_discrete_env_single_and_batched(golden):
+    from pymgrid_b200.envs import DiscreteMicrogridEnv
+    z = golden["discrete"]
+    for n in (0, 2, 9):
+        tag = f"h23_s{n}"
+        env = DiscreteMicrogridEnv.from_scenario(n)
+        assert env.action_space.n == len(z[f"{tag}_table_mod"]) and env.observation_space.shape == (int(z[f"{tag}_obs_dim"]),)
+        np.testing.assert_array_equal(env.reset(), z[f"{tag}_reset_obs"])
+        for k, a in enumerate(z[f"{tag}_actions"][:15]):
+            obs, r, d, info = env.step(int(a))
+            assert isinstance(obs, np.ndarray) and r == z[f"{tag}_rewards"][k] and d == bool(z[f"{tag}_dones"][k])
+            np.testing.assert_array_equal(obs, z[f"{tag}_obs"][k])
+        with pytest.raises(ValueError):
+            env.step(env.action_space.n)
+        # the same actions on 257 replicas at once
+        benv = DiscreteMicrogridEnv.from_scenario(n, batch=257)
+        benv.reset()
+        for k, a in enumerate(z[f"{tag}_actions"][:15]):
+            obs, r, d, _ = benv.step(torch.full((257,), int(a), dtype=torch.int32, device="cuda"))
+            assert obs.shape == (257, env.observation_space.shape[0])
+            assert (r == z[f"{tag}_rewards"][k]).all() and (obs == torch.from_numpy(z[f"{tag}_obs"][k]).cuda()).all()
+
+
+def test_continuous_env_config2_shape(golden):
+    """BASELINE config 2: 4096 replicas of microgrid_0, ContinuousMicrogridEnv.step; replicas fed the golden actions."""
+    from pymgrid_b200.envs import ContinuousMicrogridEnv
+    z = golden["pymgrid25_steps"]
+    env = ContinuousMicrogridEnv.from_scenario(0, batch=4096)
+    assert env.action_space.shape == (2,) and env.observation_space.shape == (146,)
+    assert env.action_layout == {"battery": 0, "grid": 1}
+    env.reset()
+    for k, a in enumerate(z["s0_a0"][:25]):
+        act = torch.from_numpy(np.tile(a, (4096, 1))).cuda()
+        obs, r, d, _ = env.step(act)
+        assert (r == z["s0_r0"][k]).all() and (obs == torch.from_numpy(z["s0_o0"][k]).cuda()).all()
+    single = ContinuousMicrogridEnv.from_scenario(1)          # gym-sorted action layout: battery, genset(2), grid
+    assert single.action_layout == {"battery": 0, "genset": 1, "grid": 3}
+    a = z["s1_a0"][0]                                          # golden actions are in container order: genset, battery, grid
+    obs, r, d, info = single.step(np.array([a[2], a[0], a[1], a[3]]))
+    assert r == z["s1_r0"][0]
+    np.testing.assert_array_equal(obs, z["s1_o0"][0])
+
+
+def test_rule_based_control_on_device(golden):
+    """On-device RuleBasedControl: one persistent kernel per rollout, the reference controller's
+    rewards bit for bit, including the full year of scenario 0."""
+    from pymgrid_b200.engine import BatchedMicrogrid
+    z = golden["rbc"]
+    scen = [0, 1, 2, 5, 9, 13]
+    bm = BatchedMicrogrid([load_pymgrid25(n) for n in scen], np.arange(12) % 6, device="cuda:0")
+    out = bm.rollout_rbc(300, keep_obs=False)
+    for g, r in zip(bm.groups, out):
+        rew = r["reward"].cpu().numpy()
+        for slot, e in enumerate(g.env_ids):
+            np.testing.assert_array_equal(rew[:, slot], z[f"s{scen[e % 6]}_rewards"][:300])
+    year = BatchedMicrogrid([load_pymgrid25(0)], np.zeros(3, dtype=np.int64), device="cuda:0")
+    res = year.rollout_rbc(8759, keep_obs=False, reward_sum=True)
+    np.testing.assert_array_equal(res["reward"][:, 1].cpu().numpy(), z["s0_rewards"])
+    assert bool(res["done"][8758, 0]) and not bool(res["done"][8757, 0])
+    st = np.array([year.groups[0].step[0].item(), year.groups[0].charge[0].item(), 0, 0, 0, 0], dtype=np.float64)
+    np.testing.assert_array_equal(st, z["s0_final_state"])
