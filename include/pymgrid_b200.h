@@ -44,7 +44,9 @@ enum {
  * (envs/base/base.py:211-223); real gym sorts Dict keys alphabetically. */
 enum {
     MG_OBS_GYM_SORTED = 0, /* battery, genset, grid, load, pv                                           */
-    MG_OBS_CONTAINER = 1   /* load, pv, genset, battery, grid (module listing order, module_container.py) */
+    MG_OBS_CONTAINER = 1,  /* load, pv, genset, battery, grid (module listing order, module_container.py) */
+    MG_OBS_GYM_SORTED_PV_FIRST = 2 /* PV, battery, genset, grid, load: MicrogridGenerator grids name the renewable
+                                      module 'PV' (convert/convert.py), which sorts before the lower-case names */
 };
 
 /* columns of the optional per-env info block (the reference's info dict, microgrid/utils/step.py:22-31) */
@@ -79,7 +81,7 @@ enum {
 enum { MG_MOD_NONE = -1, MG_MOD_GENSET = 0, MG_MOD_BATTERY = 1, MG_MOD_GRID = 2 };
 
 /*
- * One microgrid parameter set ("config").  Device array, 320-byte stride, indexed by MgGroup.cfg_index.
+ * One microgrid parameter set ("config").  Device array, 336-byte stride, indexed by MgGroup.cfg_index.
  * Raw parameters are the reference constructors' arguments; the *_low / *_spread members are the
  * ModuleSpace constants the reference derives once at construction (utils/space.py:183-205), computed by the
  * host in f64 exactly as the reference does.
@@ -96,13 +98,18 @@ typedef struct MgConfig {
     double grid_max_import, grid_max_export, grid_cost_per_unit_co2, grid_act_low, grid_act_spread;
     /* UnbalancedEnergyModule, modules/unbalanced_energy_module.py:14-26 */
     double loss_load_cost, overgeneration_cost;
-    /* reserved for profile-times-scale series (MicrogridGenerator grids); unused when scale == 1 */
-    double load_scale, pv_scale, load_low, load_spread, pv_low, pv_spread;
+    /* profile-times-scale series (MicrogridGenerator grids, MicrogridGenerator.py:137-148: ts = profile * (size/max)):
+       series value = table value * scale.  With series_scaled != 0 the load / pv observation windows are normalised
+       on the fly with these bounds ((v - low) / spread, rows past the end = *_fill_nrm) instead of read from the
+       pre-normalised tables, which only exist per PROFILE.  scale == 1 and series_scaled == 0 for table-backed grids. */
+    double load_scale, pv_scale, load_low, load_spread, pv_low, pv_spread, load_fill_nrm, pv_fill_nrm;
     int32_t gen_start_up_time, gen_wind_down_time, gen_allow_abortion;
     int32_t load_series, pv_series, grid_series;             /* rows of the series tables                     */
     int32_t initial_step, final_step;                        /* base_timeseries_module.py:317-330             */
     int32_t plist_offset, plist_count;                       /* rows of MgLayout.plist owned by this config   */
-    int32_t reserved[6];
+    int32_t series_scaled;                                   /* see load_scale                                */
+    int32_t grid_status_weak;                                /* per-env status bits: 1 if any outage (obs bounds 0..1), 0 if all ones */
+    int32_t reserved[4];
 } MgConfig;
 
 /*
@@ -131,6 +138,10 @@ typedef struct MgGroup {
     const int32_t *cfg_index;        /* [n] row of MgLayout.cfg                                               */
     const int32_t *env_initial_step; /* [n] per-env trajectory window (microgrid/trajectory/), or NULL -> cfg  */
     const int32_t *env_final_step;   /* [n] or NULL -> cfg                                                    */
+    /* optional per-env grid status (weak grids, MicrogridGenerator.py:321-340): bit t of row e = grid_status[t];
+       [n][status_words] uint32, rows cover T + max_horizon + 1 bits (bits >= T unused).  NULL -> column 3 of grid_raw */
+    const uint32_t *grid_status_bits;
+    int64_t status_words;
 } MgGroup;
 
 typedef struct MgLayout {

@@ -88,8 +88,9 @@ def _dp(a):
 def fill_struct(g, p, keep):
     """Fill an OrcGrid from any object with the attribute layout of pymgrid_b200.params.MicrogridParams.
     `keep` collects the numpy arrays whose memory the struct points into."""
-    load = np.ascontiguousarray(p.load_ts, dtype=np.float64)
-    pv = np.ascontiguousarray(p.pv_ts, dtype=np.float64)
+    # the oracle always works on explicit series: profile * scale is materialised here (MicrogridGenerator grids)
+    load = np.ascontiguousarray(getattr(p, "effective_load_ts", p.load_ts), dtype=np.float64)
+    pv = np.ascontiguousarray(getattr(p, "effective_pv_ts", p.pv_ts), dtype=np.float64)
     keep += [load, pv]
     g.has_genset, g.has_grid = int(p.genset is not None), int(p.grid is not None)
     g.horizon, g.T = int(p.forecast_horizon), len(load)
@@ -105,7 +106,8 @@ def fill_struct(g, p, keep):
         g.start_up_time, g.wind_down_time, g.allow_abortion = s.start_up_time, s.wind_down_time, int(s.allow_abortion)
         g.cs, g.gs, g.up, g.dn = s.current_status, s.goal_status, s.steps_until_up, s.steps_until_down
     if p.grid is not None:
-        ts = np.ascontiguousarray(p.grid.time_series, dtype=np.float64)
+        ts = p.grid.effective_time_series() if hasattr(p.grid, "effective_time_series") else p.grid.time_series
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
         keep.append(ts)
         g.max_import, g.max_export, g.grid_cost_per_unit_co2 = p.grid.max_import, p.grid.max_export, p.grid.cost_per_unit_co2
         g.grid_ts = _dp(ts)

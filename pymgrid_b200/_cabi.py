@@ -12,7 +12,7 @@ MG_ABI_VERSION = 1
 MG_MAX_GROUPS = 8
 MG_N_INFO = 16
 MG_PLIST_WIDTH = 3
-MG_OBS_GYM_SORTED, MG_OBS_CONTAINER = 0, 1
+MG_OBS_GYM_SORTED, MG_OBS_CONTAINER, MG_OBS_GYM_SORTED_PV_FIRST = 0, 1, 2
 MG_MOD_NONE, MG_MOD_GENSET, MG_MOD_BATTERY, MG_MOD_GRID = -1, 0, 1, 2
 
 FLAG_NAMES = {
@@ -40,9 +40,9 @@ class MgConfig(C.Structure):
         "gen_act_spread", "gen_up_spread", "gen_down_spread",
         "grid_max_import", "grid_max_export", "grid_cost_per_unit_co2", "grid_act_low", "grid_act_spread",
         "loss_load_cost", "overgeneration_cost",
-        "load_scale", "pv_scale", "load_low", "load_spread", "pv_low", "pv_spread")] + [(n, _i32) for n in (
+        "load_scale", "pv_scale", "load_low", "load_spread", "pv_low", "pv_spread", "load_fill_nrm", "pv_fill_nrm")] + [(n, _i32) for n in (
         "gen_start_up_time", "gen_wind_down_time", "gen_allow_abortion", "load_series", "pv_series", "grid_series",
-        "initial_step", "final_step", "plist_offset", "plist_count")] + [("reserved", _i32 * 6)]
+        "initial_step", "final_step", "plist_offset", "plist_count", "series_scaled", "grid_status_weak")] + [("reserved", _i32 * 4)]
 
 
 class MgPriorityList(C.Structure):
@@ -55,7 +55,7 @@ class MgGroup(C.Structure):
                 ("n_act", _i32), ("obs_dim", _i32), ("n_envs", C.c_int64),
                 ("act_col_genset", _i32), ("act_col_battery", _i32), ("act_col_grid", _i32), ("_pad", _i32),
                 ("step", _vp), ("charge", _vp), ("genset", _vp), ("cfg_index", _vp),
-                ("env_initial_step", _vp), ("env_final_step", _vp)]
+                ("env_initial_step", _vp), ("env_final_step", _vp), ("grid_status_bits", _vp), ("status_words", C.c_int64)]
 
 
 class MgLayout(C.Structure):

@@ -55,10 +55,13 @@ struct DevGroup {
     int32_t n_runs, run_start[3], run_len[3], run_is_state[3];
     int32_t tma_ok;                     // the grid window can be staged with cp.async.bulk (16-byte aligned image slot)
     int32_t state_start, state_genset_first;   // the battery + genset run: first element and order
+    int32_t long_path;                         // rows too long for the staged path, or a state run at an odd element
     int32_t *step;
     double *charge;
     uint32_t *genset;
     const int32_t *cfg_index, *env_initial, *env_final;
+    const uint32_t *status_bits;        // optional per-env grid status bitmask [n][status_words]
+    int64_t status_words;
     // step io
     const double *actions;
     const int32_t *dactions;
@@ -377,7 +380,8 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
 // shared-memory record of one env of the tile, published by the env's owner thread after the physics: where its
 // observation windows start in the *_nrm tables, and its battery / genset observation.
 struct __align__(16) TileEnv {
-    int32_t off_grid, off_load, off_pv, _pad;
+    int32_t off_grid, off_load, off_pv;
+    int32_t special;   // -1: plain table-backed row; >= 0: row needs per-env work (scaled series / status bits), value = t_obs
     double state[6];   // battery (soc, charge) and genset (cs, gs, up, dn) observation in ROW order
 };
 
@@ -395,6 +399,7 @@ __device__ __forceinline__ void publish_env(TileEnv &te, const MgConfig *__restr
     te.off_load = c->load_series * Tp + t_obs;
     te.off_pv = c->pv_series * Tp + t_obs;
     te.off_grid = G.has_grid ? (c->grid_series * Tp + t_obs) * 4 : 0;
+    te.special = (c->series_scaled || (G.has_grid && G.status_bits)) ? t_obs : -1;
     // battery_module.py:323-330, genset_module.py:503-509, utils/space.py:207-218
     const double soc = s.charge / c->bat_max_capacity;
     const double b0 = (soc - c->bat_soc_low) / c->bat_soc_spread;
@@ -436,7 +441,7 @@ __device__ __forceinline__ void decode_element(const DevGroup &G, int j, int &ki
 // (a separate writer for those 48 bytes costs ~20% of the store bandwidth: partial-sector merging in L2).
 template <int SLOTS>
 __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const DevGroup &G, TileShared &S, int ebuf,
-                                                 double *__restrict__ obs_tile, int n_rows, uint32_t &phase) {
+                                                 double *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r_end = min((warp + 1) * MG_ROWS_PER_WARP, n_rows);
     const int D = G.obs_dim, pairs = D >> 1;
@@ -468,7 +473,7 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
         bool brk = false;
         if (lane > 0 && lane < MG_ROWS_PER_WARP && rr < r_end) {
             const TileEnv a = env[rr], b = env[rr - 1];
-            brk = a.off_grid != b.off_grid || a.off_load != b.off_load || a.off_pv != b.off_pv;
+            brk = a.off_grid != b.off_grid || a.off_load != b.off_load || a.off_pv != b.off_pv || a.special >= 0 || b.special >= 0;
         }
         starts = __ballot_sync(0xffffffffu, brk) | (r_end > r_begin ? (1u << (r_end - r_begin)) : 0u);
     }
@@ -495,6 +500,35 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
                     if (kind == KIND_LOAD) v[k][h] = __ldg(P.load_nrm + sig.off_load + off);
                     else if (kind == KIND_PV) v[k][h] = __ldg(P.pv_nrm + sig.off_pv + off);
                     else if (kind == KIND_GRID && !stage) v[k][h] = __ldg(P.grid_nrm + sig.off_grid + off);
+                }
+            }
+        }
+        if (sig.special >= 0) {
+            // per-env series: profile * scale normalised on the fly (MicrogridGenerator grids) and / or the env's own
+            // grid-status bits; such a row never shares its windows, so it is a run of one
+            const int e = e_base + r;
+            const MgConfig *__restrict__ c = P.cfg + __ldg(G.cfg_index + e);
+            const int t_obs = sig.special;
+#pragma unroll
+            for (int k = 0; k < SLOTS; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int kind = code[k][h] >> 16, off = code[k][h] & 0xffff;
+                    if (!act[k] || st_lane[k]) continue;
+                    if (kind == KIND_LOAD && c->series_scaled) {
+                        const int idx = t_obs + off;
+                        v[k][h] = idx < P.T ? (__ldg(P.load_raw + (size_t)c->load_series * P.T + idx) * c->load_scale - c->load_low) / c->load_spread
+                                            : c->load_fill_nrm;
+                    } else if (kind == KIND_PV && c->series_scaled) {
+                        const int idx = t_obs + off;
+                        v[k][h] = idx < P.T ? (__ldg(P.pv_raw + (size_t)c->pv_series * P.T + idx) * c->pv_scale - c->pv_low) / c->pv_spread
+                                            : c->pv_fill_nrm;
+                    } else if (kind == KIND_GRID && G.status_bits && (off & 3) == 3) {
+                        const int idx = t_obs + (off >> 2);
+                        const double bit = (double)((__ldg(G.status_bits + (size_t)e * G.status_words + (idx >> 5)) >> (idx & 31)) & 1u);
+                        // bounds of the status column: (0, 1) on a weak grid, (1, 1) -> spread 1 otherwise (utils/space.py:204-205)
+                        v[k][h] = c->grid_status_weak ? (idx < P.T ? bit : 0.5) : 0.0;
+                    }
                 }
             }
         }
@@ -527,10 +561,10 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
 }
 
 __device__ __forceinline__ void warp_emit_rows(const LaunchParams &P, const DevGroup &G, TileShared &S, int ebuf,
-                                               double *__restrict__ obs_tile, int n_rows, uint32_t &phase) {
+                                               double *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
     const int pairs = G.obs_dim >> 1;
-    if (pairs <= 32) warp_emit_rows_t<1>(P, G, S, ebuf, obs_tile, n_rows, phase);
-    else warp_emit_rows_t<3>(P, G, S, ebuf, obs_tile, n_rows, phase);
+    if (pairs <= 32) warp_emit_rows_t<1>(P, G, S, ebuf, obs_tile, n_rows, e_base, phase);
+    else warp_emit_rows_t<3>(P, G, S, ebuf, obs_tile, n_rows, e_base, phase);
 }
 
 // rows longer than MG_MAX_IMG: element-wise path straight from the tables (no staging)
@@ -557,14 +591,16 @@ __device__ __forceinline__ void warp_emit_rows_long(const LaunchParams &P, const
     }
 }
 
-__device__ __forceinline__ RawRow gather_raw(const LaunchParams &P, const DevGroup &G, const MgConfig *__restrict__ c, int t) {
+__device__ __forceinline__ RawRow gather_raw(const LaunchParams &P, const DevGroup &G, const MgConfig *__restrict__ c, int e, int t) {
     RawRow r;
-    r.load = __ldg(P.load_raw + (size_t)c->load_series * P.T + t);
-    r.pv = __ldg(P.pv_raw + (size_t)c->pv_series * P.T + t);
+    // series value = table value * scale (scale == 1.0, an exact no-op, for table-backed grids)
+    r.load = __ldg(P.load_raw + (size_t)c->load_series * P.T + t) * c->load_scale;
+    r.pv = __ldg(P.pv_raw + (size_t)c->pv_series * P.T + t) * c->pv_scale;
     if (G.has_grid) {
         const double2 *g2 = reinterpret_cast<const double2 *>(P.grid_raw + ((size_t)c->grid_series * P.T + t) * 4);
         const double2 a = __ldg(g2), b = __ldg(g2 + 1);
         r.imp = a.x; r.exp_ = a.y; r.co2 = b.x; r.status = b.y;
+        if (G.status_bits) r.status = (double)((__ldg(G.status_bits + (size_t)e * G.status_words + (t >> 5)) >> (t & 31)) & 1u);
     } else {
         r.imp = r.exp_ = r.co2 = 0.0;
         r.status = 1.0;
@@ -642,7 +678,7 @@ __device__ __forceinline__ StepInputs fetch_inputs(const LaunchParams &P, const 
     } else {
         in.act = read_action(G, G.actions + (size_t)step * G.act_step_stride + (size_t)e * G.n_act);
     }
-    if (in.valid) in.raw = gather_raw(P, G, c, t);
+    if (in.valid) in.raw = gather_raw(P, G, c, e, t);
     else in.raw.load = in.raw.pv = in.raw.imp = in.raw.exp_ = in.raw.co2 = in.raw.status = 0.0;
     return in;
 }
@@ -721,7 +757,7 @@ __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_step_kernel(const 
         __syncthreads();
         uint32_t phase = 0;
         double *obs_tile = G.obs + (size_t)e0 * G.obs_dim;
-        if (G.obs_dim <= MG_MAX_IMG) warp_emit_rows(P, G, S, 0, obs_tile, n_rows, phase);
+        if (!G.long_path) warp_emit_rows(P, G, S, 0, obs_tile, n_rows, e0, phase);
         else warp_emit_rows_long(P, G, S, 0, obs_tile, n_rows);
     }
 }
@@ -772,7 +808,7 @@ __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_rollout_kernel(con
             // step s+1 after it has finished reading env[s & 1], so the owners may overwrite it at step s+2
             __syncthreads();
             double *obs_tile = G.obs + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim;
-            if (G.obs_dim <= MG_MAX_IMG) warp_emit_rows(P, G, S, ebuf, obs_tile, n_rows, phase);
+            if (!G.long_path) warp_emit_rows(P, G, S, ebuf, obs_tile, n_rows, e0, phase);
             else warp_emit_rows_long(P, G, S, ebuf, obs_tile, n_rows);
         }
     }
@@ -902,12 +938,13 @@ static void layout_segments(const MgGroup &g, DevGroup &d) {
     const int rows = 1 + g.horizon;
     int n = 0;
     int kinds[5], lens[5];
-    if (g.obs_order == MG_OBS_GYM_SORTED) {
+    if (g.obs_order == MG_OBS_GYM_SORTED || g.obs_order == MG_OBS_GYM_SORTED_PV_FIRST) {
+        if (g.obs_order == MG_OBS_GYM_SORTED_PV_FIRST) { kinds[n] = KIND_PV; lens[n++] = rows; }
         kinds[n] = KIND_BAT; lens[n++] = 2;
         if (g.has_genset) { kinds[n] = KIND_GEN; lens[n++] = 4; }
         if (g.has_grid) { kinds[n] = KIND_GRID; lens[n++] = 4 * rows; }
         kinds[n] = KIND_LOAD; lens[n++] = rows;
-        kinds[n] = KIND_PV; lens[n++] = rows;
+        if (g.obs_order == MG_OBS_GYM_SORTED) { kinds[n] = KIND_PV; lens[n++] = rows; }
     } else {
         kinds[n] = KIND_LOAD; lens[n++] = rows;
         kinds[n] = KIND_PV; lens[n++] = rows;
@@ -985,7 +1022,7 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
         if (g.n_act != n_act || g.obs_dim != obs_dim) { delete h; return fail(MG_E_INVALID, "mg_create: n_act / obs_dim do not match the architecture"); }
         if (!g.step || !g.charge || !g.cfg_index || (g.has_genset && !g.genset)) { delete h; return fail(MG_E_INVALID, "mg_create: null state pointer"); }
         if (g.has_grid && L->n_grid < 1) { delete h; return fail(MG_E_INVALID, "mg_create: grid group without grid series"); }
-        if (g.obs_order != MG_OBS_GYM_SORTED && g.obs_order != MG_OBS_CONTAINER) { delete h; return fail(MG_E_INVALID, "mg_create: bad obs_order"); }
+        if (g.obs_order < MG_OBS_GYM_SORTED || g.obs_order > MG_OBS_GYM_SORTED_PV_FIRST) { delete h; return fail(MG_E_INVALID, "mg_create: bad obs_order"); }
         d.has_genset = g.has_genset != 0; d.has_grid = g.has_grid != 0; d.horizon = g.horizon;
         d.n_act = n_act; d.obs_dim = obs_dim; d.n_envs = (int32_t)g.n_envs;
         d.act_col_genset = g.act_col_genset; d.act_col_battery = g.act_col_battery; d.act_col_grid = g.act_col_grid;
@@ -993,8 +1030,12 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
         tiles += (int)((g.n_envs + MG_TILE - 1) / MG_TILE);
         layout_segments(g, d);
         if (obs_dim > MG_MAX_IMG) d.tma_ok = 0;
+        d.long_path = (obs_dim > MG_MAX_IMG) || (d.state_start & 1);
+        if (d.long_path && g.grid_status_bits) { delete h; return fail(MG_E_UNSUPPORTED, "mg_create: per-env grid status needs the staged row path (obs_dim <= 192, even forecast rows)"); }
         d.step = g.step; d.charge = g.charge; d.genset = g.genset; d.cfg_index = g.cfg_index;
         d.env_initial = g.env_initial_step; d.env_final = g.env_final_step;
+        d.status_bits = g.grid_status_bits; d.status_words = g.status_words;
+        if (g.grid_status_bits && g.status_words * 32 < Tp) { delete h; return fail(MG_E_INVALID, "mg_create: grid_status_bits rows are shorter than T + max_horizon + 1 bits"); }
     }
     B.total_tiles = tiles;
     // normalised tables + bounds

@@ -22,12 +22,28 @@ from ._cabi import (MG_ABI_VERSION, MG_MAX_GROUPS, MG_N_INFO, MG_OBS_CONTAINER, 
 from .params import MicrogridParams
 from .priority_list import priority_lists
 
-OBS_ORDERS = {"gym_sorted": MG_OBS_GYM_SORTED, "container": MG_OBS_CONTAINER}
+OBS_ORDERS = {"gym_sorted": MG_OBS_GYM_SORTED, "container": MG_OBS_CONTAINER,
+              "gym_sorted_pv_first": _cabi.MG_OBS_GYM_SORTED_PV_FIRST}
 
 
 def _spread(low, high):
     s = high - low                      # utils/space.py:204-205
     return 1.0 if s == 0 else s
+
+
+def scaled_bounds(ts_min, ts_max, scale):
+    """Observation bounds of the series `profile * scale` from the profile's extremes (multiplication by a positive
+    scale is monotonic in IEEE arithmetic, so min / max commute with it exactly), then the reference's rules:
+    pull towards zero (base_timeseries_module.py:81-88), spread 0 -> 1 (utils/space.py:204-205), forecaster fill
+    (high + low) / 2 clipped to the bounds (forecast/forecaster.py:95, 139-149) and normalised."""
+    low, high = ts_min * scale, ts_max * scale
+    if low > 0:
+        low = 0.0
+    elif high < 0:
+        high = 0.0
+    spread = _spread(low, high)
+    fill = min(max((high + low) / 2, low), high)
+    return low, high, spread, (fill - low) / spread
 
 
 def config_record(p: MicrogridParams, load_series, pv_series, grid_series, plist_offset, plist_count):
@@ -61,7 +77,16 @@ def config_record(p: MicrogridParams, load_series, pv_series, grid_series, plist
     else:
         c.grid_act_spread = 1.0
     c.loss_load_cost, c.overgeneration_cost = p.loss_load_cost, p.overgeneration_cost
-    c.load_scale = c.pv_scale = 1.0
+    c.load_scale, c.pv_scale = p.load_scale, p.pv_scale
+    if p.scaled:
+        c.series_scaled = 1
+        for name, ts, scale in (("load", p.load_ts, p.load_scale), ("pv", p.pv_ts, p.pv_scale)):
+            low, high, spread, fill_nrm = scaled_bounds(float(ts.min()), float(ts.max()), scale)
+            setattr(c, f"{name}_low", low)
+            setattr(c, f"{name}_spread", spread)
+            setattr(c, f"{name}_fill_nrm", fill_nrm)
+    if p.grid is not None and p.grid.status is not None:
+        c.grid_status_weak = int(np.min(p.grid.status) < 1)
     c.load_series, c.pv_series, c.grid_series = load_series, pv_series, grid_series
     c.initial_step, c.final_step = p.initial_step, p.final_step
     c.plist_offset, c.plist_count = plist_offset, plist_count
@@ -82,6 +107,8 @@ class Group:
     cfg_index: torch.Tensor = None
     env_initial_step: Optional[torch.Tensor] = None
     env_final_step: Optional[torch.Tensor] = None
+    status_bits: Optional[torch.Tensor] = None   # int32 [n, status_words] per-env grid status bitmask (weak grids)
+    status_words: int = 0
     obs: torch.Tensor = None       # f64 [n, obs_dim] default output buffer
     reward: torch.Tensor = None
     done: torch.Tensor = None
@@ -145,22 +172,13 @@ class BatchedMicrogrid:
     def __init__(self, configs: Sequence[MicrogridParams], env_config, device=None, obs_order="gym_sorted",
                  with_info=False, with_flags=True, remove_redundant_gensets=True, action_order=None):
         """configs: distinct parameter sets; env_config[i] = index of env i's parameter set."""
-        if not torch.cuda.is_available():
-            raise EngineError("BatchedMicrogrid needs a CUDA device: there is no CPU path")
-        self._lib = _cabi.lib()
-        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.obs_order = obs_order
         self.configs = list(configs)
         env_config = np.asarray(env_config, dtype=np.int64)
         if env_config.ndim != 1 or len(env_config) == 0 or env_config.min() < 0 or env_config.max() >= len(self.configs):
             raise ValueError("env_config must be a non-empty 1-D array of indices into configs")
-        self.n_envs = len(env_config)
-        self.env_config = env_config
         T = len(self.configs[0])
         if any(len(p) != T for p in self.configs):
             raise ValueError("all configs must have time series of the same length")
-        self.series_len = T
-        dev, f64 = self.device, torch.float64
 
         # ---- series tables (deduplicated by content) -------------------------------------------------------
         def table(rows, width):
@@ -169,7 +187,7 @@ class BatchedMicrogrid:
                 if r is None:
                     index.append(0)
                     continue
-                k = r.tobytes()
+                k = (r.ctypes.data, r.shape) if False else r.tobytes()
                 if k not in keys:
                     keys[k] = len(uniq)
                     uniq.append(r)
@@ -179,24 +197,14 @@ class BatchedMicrogrid:
         load_np, load_idx = table([p.load_ts for p in self.configs], 1)
         pv_np, pv_idx = table([p.pv_ts for p in self.configs], 1)
         grid_np, grid_idx = table([p.grid.time_series if p.grid is not None else None for p in self.configs], 4)
-        self.max_horizon = max(p.forecast_horizon for p in self.configs)
-        Tp = T + self.max_horizon + 1
-        self.load_raw = torch.from_numpy(load_np).to(dev)
-        self.pv_raw = torch.from_numpy(pv_np).to(dev)
-        self.grid_raw = torch.from_numpy(grid_np).to(dev) if len(grid_np) else None
-        self.load_nrm = torch.empty((len(load_np), Tp), dtype=f64, device=dev)
-        self.pv_nrm = torch.empty((len(pv_np), Tp), dtype=f64, device=dev)
-        self.grid_nrm = torch.empty((len(grid_np), Tp, 4), dtype=f64, device=dev) if len(grid_np) else None
-        self.bounds = torch.empty((len(load_np) + len(pv_np) + 4 * len(grid_np), 2), dtype=f64, device=dev)
 
         # ---- priority lists + config records ---------------------------------------------------------------
-        plist_rows, plist_key, cfg_recs = [], {}, []
-        self.action_tables = []
+        plist_rows, plist_key, cfg_recs, action_tables = [], {}, [], []
         for k, p in enumerate(self.configs):
             pls = priority_lists(p.has_genset, p.has_grid,
                                  p.genset.running_min_production if p.genset is not None else None,
                                  remove_redundant_gensets)
-            self.action_tables.append(pls)
+            action_tables.append(pls)
             key = tuple(pls)
             if key not in plist_key:
                 plist_key[key] = len(plist_rows)
@@ -207,20 +215,67 @@ class BatchedMicrogrid:
                     rec.n_elements = len(pl)
                     plist_rows.append(rec)
             cfg_recs.append(config_record(p, load_idx[k], pv_idx[k], grid_idx[k], plist_key[key], len(pls)))
-        cfg_arr = (MgConfig * len(cfg_recs))(*cfg_recs)
-        self.cfg = torch.frombuffer(bytearray(bytes(cfg_arr)), dtype=torch.uint8).to(dev)
-        pl_arr = (MgPriorityList * len(plist_rows))(*plist_rows)
-        self.plist = torch.frombuffer(bytearray(bytes(pl_arr)), dtype=torch.uint8).to(dev)
+        cfg_np = np.frombuffer(bytes((MgConfig * len(cfg_recs))(*cfg_recs)), dtype=np.dtype(MgConfig)).copy()
+        plist_np = np.frombuffer(bytes((MgPriorityList * len(plist_rows))(*plist_rows)), dtype=np.uint8).copy()
+        names = {p.renewable_name for p in self.configs}
+        if len(names) != 1:
+            raise ValueError("all configs must name the renewable module the same way")
+        if obs_order == "gym_sorted" and names == {"PV"}:
+            obs_order = "gym_sorted_pv_first"
+        status = None
+        if any(p.grid is not None and p.grid.status is not None for p in self.configs):
+            status = [None if p.grid is None else (p.grid.status if p.grid.status is not None else p.grid.time_series[:, 3])
+                      for p in self.configs]
+        self._setup(cfg_np=cfg_np, plist_np=plist_np, action_tables=action_tables, env_config=env_config,
+                    cfg_arch=np.array([p.arch for p in self.configs], dtype=np.int64),
+                    cfg_step=np.array([p.current_step for p in self.configs], dtype=np.int32),
+                    cfg_charge=np.array([p.battery.current_charge for p in self.configs], dtype=np.float64),
+                    cfg_genset=np.array([0 if p.genset is None else (p.genset.current_status | (p.genset.goal_status << 8)
+                                         | (p.genset.steps_until_up << 16) | (p.genset.steps_until_down << 24))
+                                         for p in self.configs], dtype=np.int64).astype(np.int32),
+                    load_np=load_np, pv_np=pv_np, grid_np=grid_np, cfg_status=status, device=device, obs_order=obs_order,
+                    with_info=with_info, with_flags=with_flags, action_order=action_order)
+
+    def _setup(self, cfg_np, plist_np, action_tables, env_config, cfg_arch, cfg_step, cfg_charge, cfg_genset, load_np,
+               pv_np, grid_np, cfg_status, device, obs_order, with_info, with_flags, action_order):
+        """Common construction from array-form inputs (also used by the vectorised generator front end):
+        cfg_np structured MgConfig records; cfg_arch [n_cfg, 3]; cfg_* initial state per config; series tables;
+        cfg_status: None or per-config 0/1 status rows ([n_cfg, T] array or list with None for grid-less configs)."""
+        if not torch.cuda.is_available():
+            raise EngineError("BatchedMicrogrid needs a CUDA device: there is no CPU path")
+        self._lib = _cabi.lib()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.obs_order = obs_order
+        self.n_envs = len(env_config)
+        self.env_config = env_config
+        self.action_tables = action_tables
+        T = load_np.shape[1]
+        self.series_len = T
+        dev, f64 = self.device, torch.float64
+        self.max_horizon = int(cfg_arch[:, 2].max())
+        Tp = T + self.max_horizon + 1
+        self.load_raw = torch.from_numpy(np.ascontiguousarray(load_np)).to(dev)
+        self.pv_raw = torch.from_numpy(np.ascontiguousarray(pv_np)).to(dev)
+        self.grid_raw = torch.from_numpy(np.ascontiguousarray(grid_np)).to(dev) if len(grid_np) else None
+        self.load_nrm = torch.empty((len(load_np), Tp), dtype=f64, device=dev)
+        self.pv_nrm = torch.empty((len(pv_np), Tp), dtype=f64, device=dev)
+        self.grid_nrm = torch.empty((len(grid_np), Tp, 4), dtype=f64, device=dev) if len(grid_np) else None
+        self.bounds = torch.empty((len(load_np) + len(pv_np) + 4 * len(grid_np), 2), dtype=f64, device=dev)
+        self.cfg = torch.from_numpy(cfg_np.view(np.uint8).reshape(-1).copy()).to(dev)
+        self.n_cfg = len(cfg_np)
+        self.plist = torch.from_numpy(np.ascontiguousarray(plist_np)).to(dev)
+        scaled_or_status = bool(cfg_np["series_scaled"].any()) or cfg_status is not None
 
         # ---- architecture groups ----------------------------------------------------------------------------
-        archs = [p.arch for p in self.configs]
-        order = []
-        for a in (archs[c] for c in env_config):
-            if a not in order:
-                order.append(a)
+        env_arch_rows = cfg_arch[env_config]
+        uniq, first, inverse = np.unique(env_arch_rows, axis=0, return_index=True, return_inverse=True)
+        order_of_first = np.argsort(first)                       # groups in order of first appearance
+        rank = np.empty(len(uniq), dtype=np.int64)
+        rank[order_of_first] = np.arange(len(uniq))
+        env_arch = rank[inverse.reshape(-1)]
+        order = [tuple(int(x) for x in uniq[i]) for i in order_of_first]
         if len(order) > MG_MAX_GROUPS:
             raise ValueError(f"more than {MG_MAX_GROUPS} architecture groups")
-        env_arch = np.array([order.index(archs[c]) for c in env_config])
         self.env_group = env_arch
         self.env_slot = np.empty(self.n_envs, dtype=np.int64)
         self.groups: List[Group] = []
@@ -229,18 +284,21 @@ class BatchedMicrogrid:
         self.reward = self._out[:self.n_envs * 8].view(f64)
         self.done = self._out[self.n_envs * 8:]
         start = 0
+        n_actions_cfg = None if isinstance(action_tables, dict) else np.array([len(t) for t in action_tables])
         for gi, arch in enumerate(order):
             ids = np.nonzero(env_arch == gi)[0]
             # envs of one config sit next to each other so that a 64-env tile shares its time-series windows
-            # (the kernel stages them once per tile when every env of the tile is at the same step)
+            # (the kernel stages them once per run of rows that are at the same step)
             ids = ids[np.argsort(env_config[ids], kind="stable")]
             self.env_slot[ids] = np.arange(len(ids))
             has_genset, has_grid, H = arch
             n_act = 1 + has_grid + 2 * has_genset
             obs_dim = (1 + H) * (2 + 4 * has_grid) + 2 + 4 * has_genset
+            if scaled_or_status and (obs_dim > 192 or H % 2 == 0):
+                raise ValueError("profile-times-scale series / per-env grid status need an odd forecast horizon and obs_dim <= 192")
             names = [m for m, present in (("genset", has_genset), ("battery", 1), ("grid", has_grid)) if present]
             if action_order is None:
-                act_names = sorted(names) if obs_order == "gym_sorted" else names
+                act_names = sorted(names) if obs_order.startswith("gym_sorted") else names
             else:
                 act_names = [m for m in action_order if m in names]
             cols, col = {}, 0
@@ -250,18 +308,28 @@ class BatchedMicrogrid:
             cfg_ids = env_config[ids]
             g = Group(arch=arch, env_ids=ids, n_act=n_act, obs_dim=obs_dim, act_cols=cols)
             g.cfg_index = torch.from_numpy(cfg_ids.astype(np.int32)).to(dev)
-            g.step = torch.tensor([self.configs[c].current_step for c in cfg_ids], dtype=torch.int32, device=dev)
-            g.charge = torch.tensor([self.configs[c].battery.current_charge for c in cfg_ids], dtype=f64, device=dev)
+            g.step = torch.from_numpy(cfg_step[cfg_ids].astype(np.int32)).to(dev)
+            g.charge = torch.from_numpy(cfg_charge[cfg_ids].astype(np.float64)).to(dev)
             if has_genset:
-                packed = [(s.current_status | (s.goal_status << 8) | (s.steps_until_up << 16) | (s.steps_until_down << 24))
-                          for s in (self.configs[c].genset for c in cfg_ids)]
-                g.genset = torch.tensor(packed, dtype=torch.int32, device=dev)
+                g.genset = torch.from_numpy(cfg_genset[cfg_ids].astype(np.int32)).to(dev)
+            if has_grid and cfg_status is not None:
+                W = (Tp + 31) // 32
+                if isinstance(cfg_status, np.ndarray):
+                    rows = cfg_status[cfg_ids]
+                else:
+                    rows = np.stack([cfg_status[c] for c in cfg_ids])
+                bits = np.zeros((len(ids), W * 32), dtype=np.uint8)
+                bits[:, :T] = rows.astype(np.uint8)
+                packed = np.packbits(bits, axis=1, bitorder="little").view(np.uint32)
+                g.status_bits = torch.from_numpy(packed.view(np.int32).copy()).to(dev)
+                g.status_words = W
             g.obs = torch.empty((len(ids), obs_dim), dtype=f64, device=dev)
             g.reward = self.reward[start:start + len(ids)]
             g.done = self.done[start:start + len(ids)]
             g.info = torch.zeros((len(ids), MG_N_INFO), dtype=f64, device=dev) if with_info else None
             g.flags = torch.zeros(len(ids), dtype=torch.int32, device=dev) if with_flags else None
-            g.n_actions = max(len(self.action_tables[c]) for c in set(cfg_ids.tolist()))
+            g.n_actions = (int(n_actions_cfg[np.unique(cfg_ids)].max()) if n_actions_cfg is not None
+                           else len(action_tables[(int(has_genset), int(has_grid))]))
             self.groups.append(g)
             start += len(ids)
         self._handle = None
@@ -281,7 +349,8 @@ class BatchedMicrogrid:
             m.act_col_grid = g.act_cols.get("grid", 0)
             m.step, m.charge, m.genset, m.cfg_index = _ptr(g.step), _ptr(g.charge), _ptr(g.genset), _ptr(g.cfg_index)
             m.env_initial_step, m.env_final_step = _ptr(g.env_initial_step), _ptr(g.env_final_step)
-        L.n_cfg, L.series_len, L.max_horizon = len(self.configs), self.series_len, self.max_horizon
+            m.grid_status_bits, m.status_words = _ptr(g.status_bits), g.status_words
+        L.n_cfg, L.series_len, L.max_horizon = self.n_cfg, self.series_len, self.max_horizon
         L.n_load, L.n_pv = self.load_raw.shape[0], self.pv_raw.shape[0]
         L.n_grid = 0 if self.grid_raw is None else self.grid_raw.shape[0]
         L.cfg, L.load_raw, L.pv_raw, L.grid_raw = _ptr(self.cfg), _ptr(self.load_raw), _ptr(self.pv_raw), _ptr(self.grid_raw)

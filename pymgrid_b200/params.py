@@ -74,6 +74,16 @@ class GridParams:
     max_export: float
     time_series: np.ndarray         # [T, 4] float64
     cost_per_unit_co2: float = 0.0
+    # optional per-grid status (0/1, [T]) overriding column 3 of a SHARED time_series table: weak grids of
+    # MicrogridGenerator (MicrogridGenerator.py:321-340) differ only in this column
+    status: Optional[np.ndarray] = None
+
+    def effective_time_series(self):
+        if self.status is None:
+            return self.time_series
+        ts = np.array(self.time_series, dtype=np.float64)
+        ts[:, 3] = self.status
+        return ts
 
 
 @dataclass
@@ -91,8 +101,15 @@ class MicrogridParams:
     current_step: int = 0
     name: str = ""
     meta: dict = field(default_factory=dict)
+    # profile-times-scale series (MicrogridGenerator._scale_ts, MicrogridGenerator.py:137-148): the module's series is
+    # load_ts * load_scale / pv_ts * pv_scale, with load_ts / pv_ts a shared profile.  1.0 for table-backed grids.
+    load_scale: float = 1.0
+    pv_scale: float = 1.0
+    renewable_name: str = "pv"      # 'PV' for MicrogridGenerator grids: decides the gym-sorted observation order
 
     def __post_init__(self):
+        if not (self.load_scale > 0 and self.pv_scale > 0):
+            raise ValueError("series scales must be positive")
         self.load_ts = -np.abs(np.ascontiguousarray(self.load_ts, dtype=np.float64).reshape(-1))
         self.pv_ts = np.abs(np.ascontiguousarray(self.pv_ts, dtype=np.float64).reshape(-1))
         if self.grid is not None:
@@ -114,6 +131,18 @@ class MicrogridParams:
             self.final_step = len(self.load_ts)
         if self.final_step <= self.initial_step:
             raise ValueError('final_step value must be greater than initial_step')
+
+    @property
+    def scaled(self):
+        return self.load_scale != 1.0 or self.pv_scale != 1.0
+
+    @property
+    def effective_load_ts(self):
+        return self.load_ts * self.load_scale if self.load_scale != 1.0 else self.load_ts
+
+    @property
+    def effective_pv_ts(self):
+        return self.pv_ts * self.pv_scale if self.pv_scale != 1.0 else self.pv_ts
 
     # -- shape of the flat spaces ---------------------------------------------
     def __len__(self):

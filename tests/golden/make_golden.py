@@ -356,8 +356,73 @@ def make_rbc():
     np.savez_compressed(os.path.join(HERE, "rbc.npz"), **out)
 
 
+def make_generator():
+    """Real MicrogridGenerator grids (MicrogridGenerator.py, convert/): their module parameters, the (profile, scale)
+    factorisation of their load / PV series -- verified bit-exact here -- and short rollouts."""
+    import glob
+    import pandas as pd
+    from pymgrid.MicrogridGenerator import MicrogridGenerator
+    D = os.path.join(os.path.dirname(sys.modules["pymgrid"].__file__), "data")
+    loads = [pd.read_csv(f).values[:, 0].astype(float) for f in sorted(glob.glob(D + "/load/*.csv"))]
+    pvs = [pd.read_csv(f).values[:, 0].astype(float) for f in sorted(glob.glob(D + "/pv/*.csv"))]
+    co2s = [pd.read_csv(f).values[:, 0].astype(float) for f in sorted(glob.glob(D + "/co2/*.csv"))]
+    gen = MicrogridGenerator(nb_microgrid=24, random_seed=7).generate_microgrid()
+    out = {"n": np.array(len(gen.microgrids))}
+    for i, m in enumerate(gen.microgrids):
+        names = [n for n, _ in m.modules.iterdict()]
+        assert names[1] == "PV"
+        L, P = m.modules.load[0].time_series[:, 0], m.modules["PV"][0].time_series[:, 0]
+        lp = [k for k, b in enumerate(loads) if np.allclose(-L / b, (-L / b)[0], rtol=1e-9)]
+        assert len(lp) == 1
+        size = round(float((-L).max()))
+        load_scale = size / loads[lp[0]].max()
+        assert (-(loads[lp[0]] * load_scale) == L).all()
+        pp = [k for k, b in enumerate(pvs) if np.allclose(P[b > 0] / b[b > 0], (P[b > 0] / b[b > 0])[0], rtol=1e-9)]
+        assert len(pp) == 1
+        ks = [k for k in range(30, 151) if (pvs[pp[0]] * ((-L).max() * (k / 100) / pvs[pp[0]].max()) == P).all()]
+        assert len(ks) >= 1
+        pv_scale = (-L).max() * (ks[0] / 100) / pvs[pp[0]].max()
+        b = m.modules.battery[0]
+        rec = [lp[0], load_scale, pp[0], pv_scale, b.min_capacity, b.max_capacity, b.max_charge, b.max_discharge, b.efficiency,
+               b.battery_cost_cycle, b.current_charge]
+        has_gen, has_grid = hasattr(m.modules, "genset"), hasattr(m.modules, "grid")
+        if has_gen:
+            g = m.modules.genset[0]
+            rec += [1, g.running_min_production, g.running_max_production, g.genset_cost, g.co2_per_unit, g.cost_per_unit_co2]
+        else:
+            rec += [0, 0, 0, 0, 0, 0]
+        if has_grid:
+            g = m.modules.grid[0]
+            ts = np.asarray(g.time_series, dtype=float)
+            tariff = 1 if ts[:, 0].max() > 0.5 else 2
+            cid = [k for k, c in enumerate(co2s) if np.array_equal(c, ts[:, 2])]
+            assert len(cid) == 1 and (ts[:, 1] == 0).all()
+            rec += [1, g.max_import, g.max_export, g.cost_per_unit_co2, tariff, cid[0]]
+            out[f"g{i}_status"] = np.packbits(ts[:, 3].astype(np.uint8))
+            out[f"g{i}_import_price"] = ts[:, 0]
+        else:
+            rec += [0, 0, 0, 0, 0, 0]
+        ub = m.modules.unbalanced_energy[0]
+        rec += [ub.loss_load_cost, ub.overgeneration_cost, m.modules.load[0].forecast_horizon, m.final_step]
+        out[f"g{i}_rec"] = np.array(rec, dtype=np.float64)
+        rng = np.random.default_rng(4000 + i)
+        a = rng.random((60, n_act(m)))
+        rewards, dones, obs_rows, states = [], [], [], []
+        for row in a:
+            o, r, d, info = m.run(control_from_flat(m, row))
+            rewards.append(r); dones.append(d); states.append(state_vec(m))
+            obs_rows.append(np.concatenate([np.asarray(x, dtype=np.float64).ravel() for k in ("PV", "battery", "genset", "grid", "load")
+                                            if k in o for x in o[k]]))
+        out[f"g{i}_a"], out[f"g{i}_r"], out[f"g{i}_d"] = a, np.array(rewards), np.array(dones, dtype=np.uint8)
+        out[f"g{i}_o"], out[f"g{i}_s"] = np.stack(obs_rows), np.stack(states)
+        print("generator", i, names, lp, pp, ks[:1], rewards[0])
+    np.savez_compressed(os.path.join(HERE, "generator.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["steps", "year", "discrete", "genset", "custom", "log", "rbc"]
+    which = sys.argv[1:] or ["steps", "year", "discrete", "genset", "custom", "log", "rbc", "generator"]
+    if "generator" in which:
+        make_generator()
     if "rbc" in which:
         make_rbc()
     if "log" in which:

@@ -37,3 +37,25 @@ def jump_to(params, step):
     p.initial_step = step
     p.current_step = step
     return p
+
+
+def generator_params(z, i):
+    """Rebuild real MicrogridGenerator grid i of tests/golden/generator.npz in (profile, scale) form."""
+    from pymgrid_b200 import generator
+    pr = generator.load_profiles()
+    rec = z[f"g{i}_rec"]
+    (lp, lscale, pp, pscale, bmin, bmax, bch, bdis, beff, bcc, bcharge, has_gen, gmin, gmax, gcost, gco2, gcc,
+     has_grid, gimp, gexp, grcc, tariff, cid, llc, ogc, H, final_step) = rec
+    battery = BatteryParams(bmin, bmax, bch, bdis, beff, bcc, bcharge)
+    genset = grid = None
+    if has_gen:
+        genset = GensetParams.with_init(running_min_production=gmin, running_max_production=gmax, genset_cost=gcost,
+                                        co2_per_unit=gco2, cost_per_unit_co2=gcc)
+    if has_grid:
+        status = np.unpackbits(z[f"g{i}_status"])[:8760].astype(np.float64)
+        ts = generator.grid_table(pr, int(tariff), int(cid))
+        assert np.array_equal(ts[:, 0], z[f"g{i}_import_price"])
+        grid = GridParams(max_import=gimp, max_export=gexp, time_series=ts, cost_per_unit_co2=grcc, status=status)
+    return MicrogridParams(battery=battery, genset=genset, grid=grid, load_ts=pr["load"][int(lp)], pv_ts=pr["pv"][int(pp)],
+                           load_scale=float(lscale), pv_scale=float(pscale), loss_load_cost=llc, overgeneration_cost=ogc,
+                           forecast_horizon=int(H), final_step=int(final_step), renewable_name="PV")

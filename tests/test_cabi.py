@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert set(declared_functions()) == set(_cabi.EXPORTED_SYMBOLS)
     assert L.mg_abi_version() == _cabi.MG_ABI_VERSION
     assert b"sm_100a" in L.mg_build_info()
-    assert L.mg_sizeof(0) == 320 == C.sizeof(_cabi.MgConfig)
+    assert L.mg_sizeof(0) == 336 == C.sizeof(_cabi.MgConfig)
     assert L.mg_sizeof(99) == -1
 
 

@@ -424,3 +424,58 @@ def test_overlapped_launches_equal_serial():
         assert torch.equal(ga.step, gb.step) and torch.equal(ga.charge, gb.charge)
         if ga.genset is not None:
             assert torch.equal(ga.genset, gb.genset)
+
+
+def test_generator_grids_scaled_series_and_weak_grid_bits(golden):
+    """BASELINE config 5 machinery: real MicrogridGenerator grids in (profile, scale) form with per-env grid-status bits:
+    engine == the reference's recorded outputs, bit for bit (PV-first observation order)."""
+    from tests.helpers import generator_params
+    z = golden["generator"]
+    n = int(z["n"])
+    configs = [generator_params(z, i) for i in range(n)]
+    bm = engine(configs, np.arange(n))
+    assert bm.obs_order == "gym_sorted_pv_first"
+    for k in range(60):
+        obs, reward, done, info = as_lists(bm.step(group_actions(bm, [z[f"g{i}_a"][k] for i in range(n)])))
+        o, r, d = gather(bm, obs), gather(bm, reward), gather(bm, done)
+        for i in range(n):
+            assert r[i] == z[f"g{i}_r"][k] and bool(d[i]) == bool(z[f"g{i}_d"][k]), (i, k)
+            np.testing.assert_array_equal(o[i], z[f"g{i}_o"][k], err_msg=f"grid {i} step {k}")
+    st = state_rows(bm)
+    for i in range(n):
+        np.testing.assert_array_equal(st[i], z[f"g{i}_s"][-1])
+
+
+def test_vectorised_generator_batch_vs_oracle():
+    """5 000 heterogeneous grids built in array form (one config record per env) == the oracle on each grid's explicit
+    form, over a rollout that crosses the end of the series for envs started late."""
+    from pymgrid_b200 import generator
+    gb = generator.sample(5000, seed=11)
+    bm = generator.engine_from_batch(gb, device="cuda:0", action_order=CONTAINER)
+    rng = np.random.default_rng(8)
+    plist = [gb.to_params(i) for i in range(gb.n)]
+    starts = rng.integers(0, 8700, gb.n)
+    starts[::5] = rng.integers(8735, 8745, len(starts[::5]))
+    for p, s in zip(plist, starts):
+        p.current_step = int(s)
+    for g in bm.groups:
+        g.step.copy_(torch.from_numpy(starts[g.env_ids].astype(np.int32)))
+    ob = OracleBatch(plist)
+    n_steps = 14
+    padded = np.zeros((n_steps, gb.n, 4))
+    for e, p in enumerate(plist):
+        padded[:, e, :p.n_act] = rng.random((n_steps, p.n_act))
+    o_rew, o_done, o_obs = ob.rollout(padded, n_threads=4)
+    acts = [torch.from_numpy(np.ascontiguousarray(padded[:, g.env_ids, :g.n_act])).cuda() for g in bm.groups]
+    out = bm.rollout(acts, ring=1)
+    out = [out] if isinstance(out, dict) else out
+    from tests.test_generator import pv_first
+    for g, r in zip(bm.groups, out):
+        np.testing.assert_array_equal(r["reward"].cpu().numpy(), o_rew[:, g.env_ids])
+        np.testing.assert_array_equal(r["done"].cpu().numpy(), o_done[:, g.env_ids])
+        got = r["obs_ring"][0].cpu().numpy()
+        for slot, e in enumerate(g.env_ids):
+            np.testing.assert_array_equal(got[slot], pv_first(o_obs[e, :g.obs_dim], plist[e]), err_msg=f"env {e}")
+    t, charge, gen = ob.state()
+    st = state_rows(bm)
+    np.testing.assert_array_equal(np.array([s[1] for s in st]), charge)
