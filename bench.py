@@ -109,10 +109,36 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
-def build_engine(batch, device, rank=0, world=1):
-    """This rank's slice of the global batch world*batch, env i -> pymgrid25 scenario i mod 25 (global numbering)."""
-    from pymgrid_b200.sharding import sharded_pymgrid25
-    return sharded_pymgrid25(world * batch, rank, world, device=device, with_info=False, with_flags=False)
+WORKLOADS = {
+    "pymgrid25": "configs[2]: 65536 grids/GPU tiled from all 25 pymgrid25 configs, year-rollout style steps with full obs",
+    "replicas": "configs[1]: replicas of pymgrid25 microgrid_0, continuous normalised step (default batch 4096)",
+    "discrete": "configs[3]: DiscreteMicrogridEnv step (priority-list actions), forecast_horizon=24, the 15 pymgrid25 grids with a GridModule tiled",
+    "generator": "configs[4]: heterogeneous MicrogridGenerator grids (profile*scale series, weak-grid outages), one parameter set per env",
+}
+GRID_SCENARIOS = [0, 4, 6, 11, 12, 14, 16, 1, 8, 9, 10, 13, 18, 22, 24]
+
+
+def build_engine(batch, device, rank=0, world=1, workload="pymgrid25"):
+    """This rank's contiguous slice of the global batch world*batch (global env numbering, independent of the sharding)."""
+    from pymgrid_b200.sharding import shard_range, sharded_pymgrid25
+    kw = dict(device=device, with_info=False, with_flags=False)
+    if workload == "pymgrid25":     # env i -> scenario i mod 25
+        return sharded_pymgrid25(world * batch, rank, world, **kw)
+    from pymgrid_b200.engine import BatchedMicrogrid
+    from pymgrid_b200.scenario import load_pymgrid25
+    lo, hi = shard_range(world * batch, rank, world)
+    if workload == "replicas":
+        return BatchedMicrogrid([load_pymgrid25(0)], np.zeros(hi - lo, dtype=np.int64), **kw)
+    if workload == "discrete":
+        configs = []
+        for n in GRID_SCENARIOS:
+            p = load_pymgrid25(n)
+            p.forecast_horizon = 24
+            configs.append(p)
+        return BatchedMicrogrid(configs, np.arange(lo, hi) % len(configs), **kw)
+    from pymgrid_b200 import generator
+    gb = generator.sample(hi - lo, seed=1000 + rank)        # every rank samples its own shard
+    return generator.engine_from_batch(gb, **kw)
 
 
 def dist_env():
@@ -177,7 +203,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="envs per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="envs per GPU (default 65536; replicas 4096; generator 131072)")
+    ap.add_argument("--workload", default="pymgrid25", choices=tuple(WORKLOADS), help="default = the BASELINE metric's workload")
     ap.add_argument("--ring", type=int, default=4, help="observation buffers rotated so stores reach HBM")
     ap.add_argument("--path", default="rollout", choices=("rollout", "graph", "eager"),
                     help="headline path: the persistent rollout kernel (BASELINE configs[2] is a year rollout with pre-generated "
@@ -198,15 +225,23 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    if args.batch is None:
+        args.batch = {"replicas": 4096, "generator": 131072}.get(args.workload, BATCH_PER_GPU)
     B, K, W, R = args.batch, args.steps, args.warmup, args.ring
+    discrete = args.workload == "discrete"
 
-    bm = build_engine(B, dev, rank, world)
+    bm = build_engine(B, dev, rank, world, args.workload)
     groups = bm.groups
+
+    def rand_actions(steps, g):
+        if discrete:
+            return torch.randint(0, g.n_actions, (steps, g.n_envs), dtype=torch.int32, device=dev, generator=gen)
+        return torch.rand((steps, g.n_envs, g.n_act), dtype=torch.float64, device=dev, generator=gen)
     gen = torch.Generator(device=dev)
     gen.manual_seed(2 + rank)
     # every step reads its own actions from HBM: a ring of A steps (> 2x L2) reused cyclically
     A = min(W + K, 256)
-    acts = [torch.rand((A, g.n_envs, g.n_act), dtype=torch.float64, device=dev, generator=gen) for g in groups]
+    acts = [rand_actions(A, g) for g in groups]
     rings = [torch.empty((R, g.n_envs, g.obs_dim), dtype=torch.float64, device=dev) for g in groups]
     ring_bytes = sum(r.numel() * 8 for r in rings)
     act_bytes = sum(a.numel() * 8 for a in acts)
@@ -216,7 +251,7 @@ def main():
     def one_step(s):
         key = (s % A, s % R)
         if key not in launchers:
-            launchers[key] = bm.prepare_step([a[key[0]] for a in acts], obs=[r[key[1]] for r in rings])
+            launchers[key] = bm.prepare_step([a[key[0]] for a in acts], obs=[r[key[1]] for r in rings], discrete=discrete)
         launchers[key]()
 
     def barrier():
@@ -240,10 +275,10 @@ def main():
         if path == "rollout":    # persistent kernel: the K steps run in ceil(K / 2048) launches
             Kc = min(K, 2048)
             gen.manual_seed(3 + rank)
-            timed = [torch.rand((Kc, g.n_envs, g.n_act), dtype=torch.float64, device=dev, generator=gen) for g in groups]
+            timed = [rand_actions(Kc, g) for g in groups]
             chunks = [Kc] * (K // Kc) + ([K % Kc] if K % Kc else [])
-            bm.rollout([a[:max(W, 3)] for a in timed], ring=R, keep_obs=True)             # warm-up steps
-            outs = {n: bm.rollout([a[:n] for a in timed], ring=R, keep_obs=True) for n in set(chunks)}   # untimed: allocates outputs
+            bm.rollout([a[:max(W, 3)] for a in timed], ring=R, keep_obs=True, discrete=discrete)             # warm-up steps
+            outs = {n: bm.rollout([a[:n] for a in timed], ring=R, keep_obs=True, discrete=discrete) for n in set(chunks)}   # untimed: allocates outputs
             outs = {n: (o if isinstance(o, list) else [o]) for n, o in outs.items()}
             bm.load_state_dict(state0)
             barrier()
@@ -252,7 +287,7 @@ def main():
             launch0 = bm.launch_count
             ev0.record(stream)
             for n in chunks:
-                bm.rollout([a[:n] for a in timed], ring=R, keep_obs=True, out=outs[n])
+                bm.rollout([a[:n] for a in timed], ring=R, keep_obs=True, out=outs[n], discrete=discrete)
             ev1.record(stream)
         elif path == "graph":    # one mg_step launch per step, replayed from a CUDA graph
             chunk = K if K <= 256 else max(d for d in range(1, 257) if K % d == 0)
@@ -317,9 +352,9 @@ def main():
     # HostIO.step(): actions pinned-host -> device (one copy), fused kernel, reward + done device -> pinned-host (one copy)
     Ke = min(K, 200)
     bm.load_state_dict(state0)
-    hio = bm.host_io(normalized=True, obs=[r[0] for r in rings])
-    for a in hio.actions:          # the caller's actions, in pinned host memory
-        a.copy_(torch.rand(tuple(a.shape), dtype=torch.float64))
+    hio = bm.host_io(normalized=True, obs=[r[0] for r in rings], discrete=discrete)
+    for a, g in zip(hio.actions, groups):          # the caller's actions, in pinned host memory
+        a.copy_(torch.randint(0, g.n_actions, tuple(a.shape), dtype=torch.int32) if discrete else torch.rand(tuple(a.shape), dtype=torch.float64))
     with torch.cuda.stream(stream):
         for s in range(3):
             hio.step()
@@ -333,7 +368,9 @@ def main():
     e2e_value = world * B * Ke / (max_over_ranks(ev0.elapsed_time(ev1)) * 1e-3)
 
     if rank == 0:
-        bytes_per_launch = sum(g.n_envs * algorithmic_bytes(*g.arch) for g in groups)
+        bytes_per_launch = sum(g.n_envs * algorithmic_bytes(*g.arch, discrete=discrete) for g in groups)
+        if args.workload == "generator":   # + the env's own parameter record and status word(s), re-read every step
+            bytes_per_launch += sum(g.n_envs * (336 + 8 * g.arch[1]) for g in groups)
         peak, peak_src = measured_peak()
         bytes_per_step = bytes_per_launch
         steps_per_launch = K / max(launches, 1)
@@ -343,7 +380,7 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tr = json.load(f)["mg_rollout_kernel" if args.path == "rollout" else "mg_step_kernel"]
-            if tr["dram_bytes_per_step"] and B == BATCH_PER_GPU:
+            if tr["dram_bytes_per_step"] and B == BATCH_PER_GPU and args.workload == "pymgrid25":
                 traffic, traffic_src = tr["dram_bytes_per_step"] * steps_per_launch, tr["source"]
         except Exception:
             pass
@@ -351,7 +388,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "pymgrid25 scenario parameters + series (bundled), synthetic U[0,1) actions",
-            "config": {"workload": "configs[2]: 65536 grids/GPU tiled from all 25 pymgrid25 configs, year-rollout style steps with full obs",
+            "config": {"workload": WORKLOADS[args.workload],
                        "batch_per_gpu": B, "global_batch": world * B, "forecast_horizon": 23, "path": args.path,
                        "l2": f"inputs larger than L2: obs ring of {R} buffers = {ring_bytes / 1e6:.0f} MB and action ring = {act_bytes / 1e6:.0f} MB per GPU (L2 126 MB)",
                        "parallelism": f"batch sharded over {world} GPU(s), no collective on the step path"},

@@ -144,6 +144,9 @@ typedef struct MgGroup {
     int64_t status_words;
 } MgGroup;
 
+/* MgLayout.flags */
+#define MG_LAYOUT_SCALED_SERIES 1    /* some MgConfig has series_scaled != 0: selects the kernels with the per-env series path */
+
 typedef struct MgLayout {
     int32_t abi_version;
     int32_t n_groups;
@@ -164,7 +167,8 @@ typedef struct MgLayout {
     double *grid_nrm;                /* [n_grid][T + max_horizon + 1][4]                                      */
     double *bounds;                  /* [(n_load + n_pv + 4*n_grid)][2] low, high of every series column (out) */
     const MgPriorityList *plist;     /* [n_plist] or NULL when mg_step_discrete is not used                   */
-    int32_t n_plist, _pad;
+    int32_t n_plist;
+    int32_t flags;                   /* MG_LAYOUT_*                                                           */
 } MgLayout;
 
 /* per-group arguments of one step */
@@ -177,6 +181,8 @@ typedef struct MgStepIO {
     double *info;            /* [n, MG_N_INFO] or NULL                                                        */
     uint32_t *flags;         /* [n] MG_FLAG_* or NULL                                                         */
     const uint8_t *mask;     /* [n] mg_reset only: envs to reset (NULL = all)                                 */
+    double *reward_total;    /* [1] or NULL: += sum of this step's rewards over the group (logging aggregate: warp-shuffle
+                                reduction + one atomicAdd per warp; the caller zeroes it; summation order is not fixed) */
 } MgStepIO;
 
 /* per-group arguments of a multi-step rollout: leading dimension is the step */
@@ -189,6 +195,7 @@ typedef struct MgRolloutIO {
     double *reward_sum;      /* [n] sum over the rollout in step order, or NULL                               */
     uint32_t *flags;         /* [n] OR over the rollout, or NULL                                              */
     int64_t dactions_const;  /* != 0: the same priority list every step -- rule-based control (algos/rbc/rbc.py:64-93) */
+    double *reward_total;    /* [n_steps] or NULL: [s] += sum over the group of step s's rewards (see MgStepIO)        */
 } MgRolloutIO;
 
 typedef struct MgHandle MgHandle;

@@ -64,17 +64,17 @@ class MgLayout(C.Structure):
                 ("n_load", _i32), ("n_pv", _i32), ("n_grid", _i32),
                 ("cfg", _vp), ("load_raw", _vp), ("pv_raw", _vp), ("grid_raw", _vp),
                 ("load_nrm", _vp), ("pv_nrm", _vp), ("grid_nrm", _vp), ("bounds", _vp),
-                ("plist", _vp), ("n_plist", _i32), ("_pad", _i32)]
+                ("plist", _vp), ("n_plist", _i32), ("flags", _i32)]
 
 
 class MgStepIO(C.Structure):
     _fields_ = [("actions", _vp), ("dactions", _vp), ("obs", _vp), ("reward", _vp), ("done", _vp), ("info", _vp),
-                ("flags", _vp), ("mask", _vp)]
+                ("flags", _vp), ("mask", _vp), ("reward_total", _vp)]
 
 
 class MgRolloutIO(C.Structure):
     _fields_ = [("actions", _vp), ("dactions", _vp), ("obs_ring", _vp), ("reward", _vp), ("done", _vp),
-                ("reward_sum", _vp), ("flags", _vp), ("dactions_const", C.c_int64)]
+                ("reward_sum", _vp), ("flags", _vp), ("dactions_const", C.c_int64), ("reward_total", _vp)]
 
 
 class EngineError(RuntimeError):

@@ -69,6 +69,7 @@ struct DevGroup {
     uint8_t *done;
     uint32_t *flags;
     const uint8_t *mask;
+    double *reward_total;               // optional aggregate of the step's rewards over the group (logging)
     // rollout io
     double *reward_sum;
     int64_t act_step_stride, out_step_stride, obs_slot_stride, dact_step_stride;
@@ -123,6 +124,15 @@ template <int N>
 __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 // order generic-proxy shared-memory writes (st.shared) before async-proxy reads (the bulk store)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Aggregate reward of the tile's envs for logging: butterfly reduction with warp shuffles, one atomicAdd per warp.
+// Called by whole warps (all 32 lanes); lanes without an env (or with a rejected step, reward NaN) contribute 0.
+__device__ __forceinline__ void add_reward_total(double *total, double reward, bool has) {
+    double v = (has && reward == reward) ? reward : 0.0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(total, v);
+}
 
 // programmatic dependent launch (PDL): wait for the preceding grid's trigger / let the following grid start
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -385,21 +395,54 @@ struct __align__(16) TileEnv {
     double state[6];   // battery (soc, charge) and genset (cs, gs, up, dn) observation in ROW order
 };
 
+// per-env series parameters of a MicrogridGenerator-style grid, published next to TileEnv (kHetero kernels only) so
+// that the emission lanes need no dependent global loads to normalise the env's own load / pv window
+struct __align__(16) HeteroEnv {
+    double load_scale, load_low, load_spread, load_fill, pv_scale, pv_low, pv_spread, pv_fill;
+    int32_t load_base, pv_base, scaled, weak;   // element offsets of the profiles in the raw tables; flags
+};
+
 struct TileShared {
     alignas(128) double img[MG_WARPS][MG_MAX_IMG];   // per-warp staging of one observation row's time-series part
     TileEnv env[2][MG_TILE];                         // double buffered across the steps of the persistent kernel
     alignas(8) uint64_t bar[MG_WARPS];               // per-warp completion of the TMA window load
 };
 
-__device__ __forceinline__ void publish_env(TileEnv &te, const MgConfig *__restrict__ c, const DevGroup &G, const EnvRegs &s,
-                                            int T, int Tp) {
+struct TileSharedHetero {
+    HeteroEnv het[2][MG_TILE];
+};
+struct Empty {
+    int unused;
+};
+template <bool kHetero>
+struct HeteroStorage;
+template <>
+struct HeteroStorage<true> {
+    typedef TileSharedHetero type;
+    __device__ static __forceinline__ HeteroEnv *rows(type &s, int buf) { return s.het[buf]; }
+};
+template <>
+struct HeteroStorage<false> {
+    typedef Empty type;
+    __device__ static __forceinline__ HeteroEnv *rows(type &, int) { return nullptr; }
+};
+
+template <bool kHetero>
+__device__ __forceinline__ void publish_env(TileEnv &te, HeteroEnv *het, const MgConfig *__restrict__ c, const DevGroup &G,
+                                            const EnvRegs &s, int T, int Tp) {
     // rows >= T of the tables hold the forecaster's fill value, so a window that runs past the end of the series
     // needs no branch (forecast/forecaster.py:120-137)
     const int t_obs = min(s.t, T);
     te.off_load = c->load_series * Tp + t_obs;
     te.off_pv = c->pv_series * Tp + t_obs;
     te.off_grid = G.has_grid ? (c->grid_series * Tp + t_obs) * 4 : 0;
-    te.special = (c->series_scaled || (G.has_grid && G.status_bits)) ? t_obs : -1;
+    te.special = (kHetero && (c->series_scaled || (G.has_grid && G.status_bits))) ? t_obs : -1;
+    if (kHetero && het) {
+        het->load_scale = c->load_scale; het->load_low = c->load_low; het->load_spread = c->load_spread; het->load_fill = c->load_fill_nrm;
+        het->pv_scale = c->pv_scale; het->pv_low = c->pv_low; het->pv_spread = c->pv_spread; het->pv_fill = c->pv_fill_nrm;
+        het->load_base = c->load_series * T; het->pv_base = c->pv_series * T;
+        het->scaled = c->series_scaled; het->weak = c->grid_status_weak;
+    }
     // battery_module.py:323-330, genset_module.py:503-509, utils/space.py:207-218
     const double soc = s.charge / c->bat_max_capacity;
     const double b0 = (soc - c->bat_soc_low) / c->bat_soc_spread;
@@ -439,9 +482,9 @@ __device__ __forceinline__ void decode_element(const DevGroup &G, int j, int &ki
 // The 1-3 lanes that own the battery / genset pairs take them from the env's shared-memory record instead, so every
 // byte of a row -- and of the contiguous 19 KB chunk of 16 rows -- is written by one warp in consecutive instructions
 // (a separate writer for those 48 bytes costs ~20% of the store bandwidth: partial-sector merging in L2).
-template <int SLOTS>
-__device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const DevGroup &G, TileShared &S, int ebuf,
-                                                 double *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
+template <int SLOTS, bool kHetero>
+__device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const DevGroup &G, TileShared &S, const HeteroEnv *het,
+                                                 int ebuf, double *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r_end = min((warp + 1) * MG_ROWS_PER_WARP, n_rows);
     const int D = G.obs_dim, pairs = D >> 1;
@@ -473,7 +516,8 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
         bool brk = false;
         if (lane > 0 && lane < MG_ROWS_PER_WARP && rr < r_end) {
             const TileEnv a = env[rr], b = env[rr - 1];
-            brk = a.off_grid != b.off_grid || a.off_load != b.off_load || a.off_pv != b.off_pv || a.special >= 0 || b.special >= 0;
+            brk = a.off_grid != b.off_grid || a.off_load != b.off_load || a.off_pv != b.off_pv ||
+                  (kHetero && (a.special >= 0 || b.special >= 0));
         }
         starts = __ballot_sync(0xffffffffu, brk) | (r_end > r_begin ? (1u << (r_end - r_begin)) : 0u);
     }
@@ -490,44 +534,50 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
             }
         }
         double v[SLOTS][2];
-#pragma unroll
-        for (int k = 0; k < SLOTS; ++k) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int kind = code[k][h] >> 16, off = code[k][h] & 0xffff;
-                v[k][h] = 0.0;
-                if (act[k] && !st_lane[k]) {
-                    if (kind == KIND_LOAD) v[k][h] = __ldg(P.load_nrm + sig.off_load + off);
-                    else if (kind == KIND_PV) v[k][h] = __ldg(P.pv_nrm + sig.off_pv + off);
-                    else if (kind == KIND_GRID && !stage) v[k][h] = __ldg(P.grid_nrm + sig.off_grid + off);
-                }
-            }
-        }
-        if (sig.special >= 0) {
+        if (kHetero && sig.special >= 0) {
             // per-env series: profile * scale normalised on the fly (MicrogridGenerator grids) and / or the env's own
             // grid-status bits; such a row never shares its windows, so it is a run of one
             const int e = e_base + r;
-            const MgConfig *__restrict__ c = P.cfg + __ldg(G.cfg_index + e);
+            const HeteroEnv hv = het[r];
             const int t_obs = sig.special;
 #pragma unroll
             for (int k = 0; k < SLOTS; ++k) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int kind = code[k][h] >> 16, off = code[k][h] & 0xffff;
+                    v[k][h] = 0.0;
                     if (!act[k] || st_lane[k]) continue;
-                    if (kind == KIND_LOAD && c->series_scaled) {
+                    const bool is_load = kind == KIND_LOAD;
+                    if ((is_load || kind == KIND_PV) && hv.scaled) {   // one normalisation site for both series
                         const int idx = t_obs + off;
-                        v[k][h] = idx < P.T ? (__ldg(P.load_raw + (size_t)c->load_series * P.T + idx) * c->load_scale - c->load_low) / c->load_spread
-                                            : c->load_fill_nrm;
-                    } else if (kind == KIND_PV && c->series_scaled) {
-                        const int idx = t_obs + off;
-                        v[k][h] = idx < P.T ? (__ldg(P.pv_raw + (size_t)c->pv_series * P.T + idx) * c->pv_scale - c->pv_low) / c->pv_spread
-                                            : c->pv_fill_nrm;
+                        const double *src = is_load ? P.load_raw + hv.load_base : P.pv_raw + hv.pv_base;
+                        const double scale = is_load ? hv.load_scale : hv.pv_scale;
+                        const double low = is_load ? hv.load_low : hv.pv_low;
+                        const double spread = is_load ? hv.load_spread : hv.pv_spread;
+                        const double raw = idx < P.T ? __ldg(src + idx) : 0.0;
+                        const double nrm = (raw * scale - low) / spread;
+                        v[k][h] = idx < P.T ? nrm : (is_load ? hv.load_fill : hv.pv_fill);
                     } else if (kind == KIND_GRID && G.status_bits && (off & 3) == 3) {
                         const int idx = t_obs + (off >> 2);
                         const double bit = (double)((__ldg(G.status_bits + (size_t)e * G.status_words + (idx >> 5)) >> (idx & 31)) & 1u);
                         // bounds of the status column: (0, 1) on a weak grid, (1, 1) -> spread 1 otherwise (utils/space.py:204-205)
-                        v[k][h] = c->grid_status_weak ? (idx < P.T ? bit : 0.5) : 0.0;
+                        v[k][h] = hv.weak ? (idx < P.T ? bit : 0.5) : 0.0;
+                    } else if (kind == KIND_LOAD) v[k][h] = __ldg(P.load_nrm + sig.off_load + off);
+                    else if (kind == KIND_PV) v[k][h] = __ldg(P.pv_nrm + sig.off_pv + off);
+                    else if (kind == KIND_GRID) v[k][h] = __ldg(P.grid_nrm + sig.off_grid + off);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SLOTS; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int kind = code[k][h] >> 16, off = code[k][h] & 0xffff;
+                    v[k][h] = 0.0;
+                    if (act[k] && !st_lane[k]) {
+                        if (kind == KIND_LOAD) v[k][h] = __ldg(P.load_nrm + sig.off_load + off);
+                        else if (kind == KIND_PV) v[k][h] = __ldg(P.pv_nrm + sig.off_pv + off);
+                        else if (kind == KIND_GRID && !stage) v[k][h] = __ldg(P.grid_nrm + sig.off_grid + off);
                     }
                 }
             }
@@ -560,11 +610,12 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
     }
 }
 
-__device__ __forceinline__ void warp_emit_rows(const LaunchParams &P, const DevGroup &G, TileShared &S, int ebuf,
-                                               double *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
+template <bool kHetero>
+__device__ __forceinline__ void warp_emit_rows(const LaunchParams &P, const DevGroup &G, TileShared &S, const HeteroEnv *het,
+                                               int ebuf, double *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
     const int pairs = G.obs_dim >> 1;
-    if (pairs <= 32) warp_emit_rows_t<1>(P, G, S, ebuf, obs_tile, n_rows, e_base, phase);
-    else warp_emit_rows_t<3>(P, G, S, ebuf, obs_tile, n_rows, e_base, phase);
+    if (pairs <= 32) warp_emit_rows_t<1, kHetero>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase);
+    else warp_emit_rows_t<3, kHetero>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase);
 }
 
 // rows longer than MG_MAX_IMG: element-wise path straight from the tables (no staging)
@@ -591,16 +642,21 @@ __device__ __forceinline__ void warp_emit_rows_long(const LaunchParams &P, const
     }
 }
 
+template <bool kHetero>
 __device__ __forceinline__ RawRow gather_raw(const LaunchParams &P, const DevGroup &G, const MgConfig *__restrict__ c, int e, int t) {
     RawRow r;
-    // series value = table value * scale (scale == 1.0, an exact no-op, for table-backed grids)
-    r.load = __ldg(P.load_raw + (size_t)c->load_series * P.T + t) * c->load_scale;
-    r.pv = __ldg(P.pv_raw + (size_t)c->pv_series * P.T + t) * c->pv_scale;
+    r.load = __ldg(P.load_raw + (size_t)c->load_series * P.T + t);
+    r.pv = __ldg(P.pv_raw + (size_t)c->pv_series * P.T + t);
+    if (kHetero) {   // series value = profile value * scale (MicrogridGenerator grids)
+        r.load *= c->load_scale;
+        r.pv *= c->pv_scale;
+    }
     if (G.has_grid) {
         const double2 *g2 = reinterpret_cast<const double2 *>(P.grid_raw + ((size_t)c->grid_series * P.T + t) * 4);
         const double2 a = __ldg(g2), b = __ldg(g2 + 1);
         r.imp = a.x; r.exp_ = a.y; r.co2 = b.x; r.status = b.y;
-        if (G.status_bits) r.status = (double)((__ldg(G.status_bits + (size_t)e * G.status_words + (t >> 5)) >> (t & 31)) & 1u);
+        if (kHetero && G.status_bits)
+            r.status = (double)((__ldg(G.status_bits + (size_t)e * G.status_words + (t >> 5)) >> (t & 31)) & 1u);
     } else {
         r.imp = r.exp_ = r.co2 = 0.0;
         r.status = 1.0;
@@ -662,6 +718,7 @@ struct StepInputs {
     RawRow raw;
 };
 
+template <bool kHetero>
 __device__ __forceinline__ StepInputs fetch_inputs(const LaunchParams &P, const DevGroup &G, const MgConfig *__restrict__ c,
                                                    int e, int step, int t) {
     StepInputs in;
@@ -678,7 +735,7 @@ __device__ __forceinline__ StepInputs fetch_inputs(const LaunchParams &P, const 
     } else {
         in.act = read_action(G, G.actions + (size_t)step * G.act_step_stride + (size_t)e * G.n_act);
     }
-    if (in.valid) in.raw = gather_raw(P, G, c, e, t);
+    if (in.valid) in.raw = gather_raw<kHetero>(P, G, c, e, t);
     else in.raw.load = in.raw.pv = in.raw.imp = in.raw.exp_ = in.raw.co2 = in.raw.status = 0.0;
     return in;
 }
@@ -709,8 +766,12 @@ __device__ __forceinline__ void owner_step(const LaunchParams &P, const DevGroup
 // The latency-bound part comes first and the stores last: stores are fire-and-forget, so a CTA retires as soon as
 // its rows are issued and the drain overlaps the next launch (measured: 18.4 us/step against 22.9 the other way round).
 // ------------------------------------------------------------------------------------------------------------------
+// kHetero = true adds the per-env series paths (profile * scale, status bits); table-backed batches run the lean kernel
+template <bool kHetero>
 __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_step_kernel(const __grid_constant__ LaunchParams P) {
     __shared__ TileShared S;
+    __shared__ typename HeteroStorage<kHetero>::type SH;
+    HeteroEnv *het0 = HeteroStorage<kHetero>::rows(SH, 0);
     const int gi = find_group(P, blockIdx.x);
     const DevGroup &G = P.g[gi];
     const int e0 = (blockIdx.x - G.tile_begin) * MG_TILE;
@@ -719,6 +780,8 @@ __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_step_kernel(const 
     const int e = e0 + tid;
     if ((tid & 31) == 0 && G.obs) mbar_init(&S.bar[tid >> 5], 1);
     pdl_wait();   // nothing above touches global memory; everything below may read what the previous launch wrote
+    double my_reward = 0.0;
+    bool stepped = false;
     if (tid < n_rows) {
         const MgConfig *__restrict__ c = P.cfg + __ldg(G.cfg_index + e);
         EnvRegs s;
@@ -727,7 +790,7 @@ __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_step_kernel(const 
         s.cs = s.gs = s.up = s.dn = 0;
         if (G.has_genset) unpack_genset(G.genset[e], s);
         if (P.mode == MODE_STEP || P.mode == MODE_DISCRETE) {
-            const StepInputs in = fetch_inputs(P, G, c, e, 0, s.t);
+            const StepInputs in = fetch_inputs<kHetero>(P, G, c, e, 0, s.t);
             const int final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
             double reward;
             int done;
@@ -741,14 +804,17 @@ __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_step_kernel(const 
             G.reward[e] = reward;
             G.done[e] = (uint8_t)done;
             if (G.flags) G.flags[e] = flags;
+            my_reward = reward;
+            stepped = true;
         } else if (P.mode == MODE_RESET) {
             if (!G.mask || G.mask[e]) {   // Microgrid.reset: only the step counter moves (microgrid.py:205-225)
                 s.t = G.env_initial ? __ldg(G.env_initial + e) : c->initial_step;
                 G.step[e] = s.t;
             }
         }
-        if (G.obs) publish_env(S.env[0][tid], c, G, s, P.T, P.Tp);
+        if (G.obs) publish_env<kHetero>(S.env[0][tid], het0 ? het0 + tid : nullptr, c, G, s, P.T, P.Tp);
     }
+    if (G.reward_total && tid < MG_TILE) add_reward_total(G.reward_total, my_reward, stepped);   // warps 0..1, uniformly
     // Every write a following step depends on (state, reward, done, flags, info) is issued: let the next launch's CTAs
     // start their latency-bound part on SMs as they free up while this grid is still streaming observation rows.
     // The host only opts the next launch into this when it writes different observation buffers (launch_step).
@@ -757,7 +823,7 @@ __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_step_kernel(const 
         __syncthreads();
         uint32_t phase = 0;
         double *obs_tile = G.obs + (size_t)e0 * G.obs_dim;
-        if (!G.long_path) warp_emit_rows(P, G, S, 0, obs_tile, n_rows, e0, phase);
+        if (!G.long_path) warp_emit_rows<kHetero>(P, G, S, het0, 0, obs_tile, n_rows, e0, phase);
         else warp_emit_rows_long(P, G, S, 0, obs_tile, n_rows);
     }
 }
@@ -765,8 +831,10 @@ __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_step_kernel(const 
 // ------------------------------------------------------------------------------------------------------------------
 // persistent multi-step kernel: every CTA owns its tile for all n_steps; env state stays in registers
 // ------------------------------------------------------------------------------------------------------------------
+template <bool kHetero>
 __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_rollout_kernel(const __grid_constant__ LaunchParams P) {
     __shared__ TileShared S;
+    __shared__ typename HeteroStorage<kHetero>::type SH;
     const int gi = find_group(P, blockIdx.x);
     const DevGroup &G = P.g[gi];
     const int e0 = (blockIdx.x - G.tile_begin) * MG_TILE;
@@ -791,8 +859,9 @@ __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_rollout_kernel(con
     }
     for (int step = 0; step < P.n_steps; ++step) {
         const int ebuf = step & 1;
+        double my_reward = 0.0;
         if (owner) {
-            const StepInputs in = fetch_inputs(P, G, c, e, step, s.t);
+            const StepInputs in = fetch_inputs<kHetero>(P, G, c, e, step, s.t);
             double reward;
             int done;
             uint32_t flags;
@@ -801,14 +870,16 @@ __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_rollout_kernel(con
             G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)done;
             rsum += reward;
             fsum |= flags;
-            if (G.obs) publish_env(S.env[ebuf][tid], c, G, s, P.T, P.Tp);
+            my_reward = reward;
+            if (G.obs) publish_env<kHetero>(S.env[ebuf][tid], kHetero ? HeteroStorage<kHetero>::rows(SH, ebuf) + tid : nullptr, c, G, s, P.T, P.Tp);
         }
+        if (G.reward_total && tid < MG_TILE) add_reward_total(G.reward_total + step, my_reward, owner);
         if (G.obs) {
             // one barrier per step: the records of step s live in env[s & 1]; a warp can only reach the barrier of
             // step s+1 after it has finished reading env[s & 1], so the owners may overwrite it at step s+2
             __syncthreads();
             double *obs_tile = G.obs + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim;
-            if (!G.long_path) warp_emit_rows(P, G, S, ebuf, obs_tile, n_rows, e0, phase);
+            if (!G.long_path) warp_emit_rows<kHetero>(P, G, S, HeteroStorage<kHetero>::rows(SH, ebuf), ebuf, obs_tile, n_rows, e0, phase);
             else warp_emit_rows_long(P, G, S, ebuf, obs_tile, n_rows);
         }
     }
@@ -900,6 +971,7 @@ struct MgHandle {
     const double *last_obs[MG_MAX_GROUPS];
     void *last_stream;
     bool last_was_step;
+    bool hetero;            // per-env series (profile * scale) or per-env grid status present: run the kHetero kernels
 };
 
 static thread_local char g_err[512] = "";
@@ -999,6 +1071,7 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
     h->layout = *L;
     h->launches = 0;
     h->last_was_step = false;
+    h->hetero = (L->flags & MG_LAYOUT_SCALED_SERIES) != 0;
     h->last_stream = nullptr;
     for (int g = 0; g < MG_MAX_GROUPS; ++g) h->last_obs[g] = nullptr;
     LaunchParams &B = h->base;
@@ -1035,6 +1108,7 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
         d.step = g.step; d.charge = g.charge; d.genset = g.genset; d.cfg_index = g.cfg_index;
         d.env_initial = g.env_initial_step; d.env_final = g.env_final_step;
         d.status_bits = g.grid_status_bits; d.status_words = g.status_words;
+        if (g.grid_status_bits) h->hetero = true;
         if (g.grid_status_bits && g.status_words * 32 < Tp) { delete h; return fail(MG_E_INVALID, "mg_create: grid_status_bits rows are shorter than T + max_horizon + 1 bits"); }
     }
     B.total_tiles = tiles;
@@ -1068,6 +1142,7 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
         DevGroup &d = P.g[g];
         d.actions = io[g].actions; d.dactions = io[g].dactions; d.obs = io[g].obs; d.reward = io[g].reward;
         d.done = io[g].done; d.info = io[g].info; d.flags = io[g].flags; d.mask = io[g].mask;
+        d.reward_total = io[g].reward_total;
         if (mode == MODE_STEP && !d.actions) return fail(MG_E_INVALID, "mg_step: null actions");
         if (mode == MODE_DISCRETE && (!d.dactions || !P.plist)) return fail(MG_E_INVALID, "mg_step_discrete: null actions or priority lists");
         if ((mode == MODE_STEP || mode == MODE_DISCRETE) && (!d.reward || !d.done)) return fail(MG_E_INVALID, "step: null reward / done");
@@ -1092,7 +1167,7 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = overlap ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, mg_step_kernel, P);
+    cudaError_t e = h->hetero ? cudaLaunchKernelEx(&cfg, mg_step_kernel<true>, P) : cudaLaunchKernelEx(&cfg, mg_step_kernel<false>, P);
     if (e != cudaSuccess) return cuda_fail(e, "step kernel launch");
     h->launches += 1;
     h->last_was_step = true;
@@ -1123,6 +1198,7 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
         DevGroup &d = P.g[g];
         d.actions = io[g].actions; d.dactions = io[g].dactions; d.obs = io[g].obs_ring; d.reward = io[g].reward;
         d.done = io[g].done; d.reward_sum = io[g].reward_sum; d.flags = io[g].flags; d.info = nullptr; d.mask = nullptr;
+        d.reward_total = io[g].reward_total;
         d.act_step_stride = (int64_t)d.n_envs * d.n_act;
         d.out_step_stride = d.n_envs;
         d.dact_step_stride = io[g].dactions_const ? 0 : d.n_envs;
@@ -1134,7 +1210,8 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
         if (d.actions && (d.n_act == 2 || d.n_act == 4) && ((((uintptr_t)d.actions) & 15) || ((d.act_step_stride * 8) & 15)))
             return fail(MG_E_INVALID, "rollout: action rows must stay 16-byte aligned across steps");
     }
-    mg_rollout_kernel<<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+    if (h->hetero) mg_rollout_kernel<true><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+    else mg_rollout_kernel<false><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "rollout kernel launch");
     h->launches += 1;

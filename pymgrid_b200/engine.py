@@ -264,7 +264,8 @@ class BatchedMicrogrid:
         self.cfg = torch.from_numpy(cfg_np.view(np.uint8).reshape(-1).copy()).to(dev)
         self.n_cfg = len(cfg_np)
         self.plist = torch.from_numpy(np.ascontiguousarray(plist_np)).to(dev)
-        scaled_or_status = bool(cfg_np["series_scaled"].any()) or cfg_status is not None
+        self._scaled = bool(cfg_np["series_scaled"].any())
+        scaled_or_status = self._scaled or cfg_status is not None
 
         # ---- architecture groups ----------------------------------------------------------------------------
         env_arch_rows = cfg_arch[env_config]
@@ -356,6 +357,7 @@ class BatchedMicrogrid:
         L.cfg, L.load_raw, L.pv_raw, L.grid_raw = _ptr(self.cfg), _ptr(self.load_raw), _ptr(self.pv_raw), _ptr(self.grid_raw)
         L.load_nrm, L.pv_nrm, L.grid_nrm, L.bounds = _ptr(self.load_nrm), _ptr(self.pv_nrm), _ptr(self.grid_nrm), _ptr(self.bounds)
         L.plist, L.n_plist = _ptr(self.plist), self.plist.numel() // C.sizeof(MgPriorityList)
+        L.flags = 1 if self._scaled else 0
         return L
 
     def _stream(self):
@@ -403,7 +405,7 @@ class BatchedMicrogrid:
             raise ValueError(f"{name}: expected {len(self.groups)} per-group tensors")
         return list(x)
 
-    def _io(self, actions=None, dactions=None, obs=True, mask=None):
+    def _io(self, actions=None, dactions=None, obs=True, mask=None, reward_total=None):
         io = (MgStepIO * len(self.groups))()
         acts = self._per_group(actions, "actions")
         dacts = self._per_group(dactions, "actions")
@@ -424,6 +426,8 @@ class BatchedMicrogrid:
             io[gi].actions, io[gi].dactions, io[gi].obs = _ptr(a), _ptr(d), _ptr(o)
             io[gi].reward, io[gi].done, io[gi].info, io[gi].flags = _ptr(g.reward), _ptr(g.done), _ptr(g.info), _ptr(g.flags)
             io[gi].mask = _ptr(m)
+            if reward_total is not None:      # one f64 accumulator shared by every group: the whole batch's reward
+                io[gi].reward_total = _ptr(reward_total)
         return io, obs_bufs
 
     def _result(self, obs_bufs):
@@ -451,10 +455,11 @@ class BatchedMicrogrid:
         launch.keepalive = (io, obs_bufs, actions)
         return launch
 
-    def step(self, actions, normalized=True, obs=True):
+    def step(self, actions, normalized=True, obs=True, reward_total=None):
         """Microgrid.run for every env (reference microgrid.py:227-325).  actions: float64 [n, n_act] per group,
-        columns per `Group.act_cols`.  Returns (obs, reward, done, info) as device tensors (lists for > 1 group)."""
-        io, obs_bufs = self._io(actions=actions, obs=obs)
+        columns per `Group.act_cols`.  Returns (obs, reward, done, info) as device tensors (lists for > 1 group).
+        reward_total: optional f64 [1] device tensor that the kernel adds the batch's summed reward to (logging)."""
+        io, obs_bufs = self._io(actions=actions, obs=obs, reward_total=reward_total)
         _cabi.check(self._lib.mg_step(self._handle, io, int(bool(normalized)), self._stream()), "mg_step")
         return self._result(obs_bufs)
 
@@ -490,7 +495,7 @@ class BatchedMicrogrid:
         return self.rollout(acts if len(acts) > 1 else acts[0], discrete=True, constant_actions=True, n_steps=n_steps, **kw)
 
     def rollout(self, actions, normalized=True, discrete=False, ring=1, keep_obs=True, reward_sum=False, out=None,
-                constant_actions=False, n_steps=None):
+                constant_actions=False, n_steps=None, reward_total=None):
         """n_steps consecutive steps in one persistent kernel.  actions: per group [n_steps, n, n_act] float64
         (or [n_steps, n] int32 when discrete).  Returns dict(reward=[n_steps, n], done=..., obs_ring=[ring, n, D]);
         pass a previous return value (list of dicts) as `out` to reuse its buffers."""
@@ -521,6 +526,7 @@ class BatchedMicrogrid:
                 io[gi].actions = _ptr(a)
             io[gi].obs_ring, io[gi].reward, io[gi].done = _ptr(r["obs_ring"]), _ptr(r["reward"]), _ptr(r["done"])
             io[gi].reward_sum, io[gi].flags = _ptr(r["reward_sum"]), _ptr(g.flags)
+            io[gi].reward_total = _ptr(reward_total)
         if discrete:
             _cabi.check(self._lib.mg_rollout_discrete(self._handle, io, n_steps, ring, self._stream()), "mg_rollout_discrete")
         else:

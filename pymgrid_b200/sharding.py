@@ -45,7 +45,8 @@ def sharded_pymgrid25(global_batch, rank, world, device=None, **kw):
     return bm
 
 
-def total_reward(bm, reward=None):
-    """Aggregate reward of the whole job for the last step (logging only): local sum on the device, then all-reduce."""
-    r = bm.reward if reward is None else reward
-    return aggregate_sum(torch.nansum(r).reshape(1))
+def total_reward(local_total):
+    """Whole-job aggregate reward for logging: `local_total` is this rank's accumulator filled by the kernel
+    (`BatchedMicrogrid.step(..., reward_total=t)` / `rollout(..., reward_total=t[n_steps])`: warp-shuffle reduction + one
+    atomicAdd per warp); the only collective is this all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+    return aggregate_sum(local_total)

@@ -479,3 +479,22 @@ def test_vectorised_generator_batch_vs_oracle():
     t, charge, gen = ob.state()
     st = state_rows(bm)
     np.testing.assert_array_equal(np.array([s[1] for s in st]), charge)
+
+
+def test_aggregate_reward_shuffle_reduction():
+    """Optional logging aggregate: the kernel's warp-shuffle + atomicAdd total == sum of the per-env rewards
+    (floating-point summation order differs: tolerance 1e-12 relative)."""
+    configs = [load_pymgrid25(n) for n in range(25)]
+    B = 10007
+    bm = engine(configs, np.arange(B) % 25, with_info=False)
+    total = torch.zeros(1, dtype=torch.float64, device="cuda")
+    acts = [torch.rand((g.n_envs, g.n_act), dtype=torch.float64, device="cuda") for g in bm.groups]
+    _, reward, _, _ = as_lists(bm.step(acts, reward_total=total))
+    want = sum(float(r.sum()) for r in reward)
+    assert abs(total.item() - want) <= 1e-12 * abs(want)
+    n_steps = 9
+    per_step = torch.zeros(n_steps, dtype=torch.float64, device="cuda")
+    racts = [torch.rand((n_steps, g.n_envs, g.n_act), dtype=torch.float64, device="cuda") for g in bm.groups]
+    out = bm.rollout(racts, keep_obs=False, reward_total=per_step)
+    want = sum(r["reward"].sum(dim=1) for r in out)
+    assert torch.allclose(per_step, want, rtol=1e-12, atol=0)
