@@ -35,6 +35,9 @@
 #ifndef MG_PDL
 #define MG_PDL 0            // programmatic dependent launch between consecutive step launches: measured SLOWER (18.6 vs 16.9 us/step), off
 #endif
+#ifndef MG_MIN_CTAS_HETERO
+#define MG_MIN_CTAS_HETERO 7
+#endif
 #define MG_MIN_CTAS 7       // resident CTAs per SM the register budget must allow (65 536 envs = 1 024 tiles = one wave)
 #ifndef MG_TMA_MIN_RUN
 #define MG_TMA_MIN_RUN 2
@@ -50,9 +53,6 @@ struct DevGroup {
     int32_t tile_begin;                 // first CTA of this group in the fused launch
     int32_t n_seg;
     int32_t seg_start[5], seg_kind[5];  // observation row layout: segment starts (ascending) and kinds
-    // the same row as runs of 16-byte multiples: "shared" runs are identical for every env that has the same
-    // series and step (the [t, t+H] windows), the single "state" run (battery + genset obs) is per env
-    int32_t n_runs, run_start[3], run_len[3], run_is_state[3];
     int32_t tma_ok;                     // the grid window can be staged with cp.async.bulk (16-byte aligned image slot)
     int32_t state_start, state_genset_first;   // the battery + genset run: first element and order
     int32_t long_path;                         // rows too long for the staged path, or a state run at an odd element
@@ -115,16 +115,6 @@ __device__ __forceinline__ void tma_load(void *sdst, const void *gsrc, uint32_t 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// shared -> global bulk copy, tracked by the issuing thread's bulk async-group
-__device__ __forceinline__ void tma_store(void *gdst, const void *ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-// order generic-proxy shared-memory writes (st.shared) before async-proxy reads (the bulk store)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // Aggregate reward of the tile's envs for logging: butterfly reduction with warp shuffles, one atomicAdd per warp.
 // Called by whole warps (all 32 lanes); lanes without an env (or with a rejected step, reward NaN) contribute 0.
 __device__ __forceinline__ void add_reward_total(double *total, double reward, bool has) {
@@ -403,7 +393,7 @@ struct __align__(16) HeteroEnv {
 };
 
 struct TileShared {
-    alignas(128) double img[MG_WARPS][MG_MAX_IMG];   // per-warp staging of one observation row's time-series part
+    alignas(128) double img[MG_WARPS][MG_MAX_IMG];   // per-warp TMA staging of a run's grid window (4 * (1 + H) <= MG_MAX_IMG f64)
     TileEnv env[2][MG_TILE];                         // double buffered across the steps of the persistent kernel
     alignas(8) uint64_t bar[MG_WARPS];               // per-warp completion of the TMA window load
 };
@@ -472,6 +462,58 @@ __device__ __forceinline__ void decode_element(const DevGroup &G, int j, int &ki
     off = j - G.seg_start[sgi];
 }
 
+#define MG_HET_SLOTS (MG_MAX_IMG / 32)   // elements per lane of the longest staged row
+
+// One observation row of an env with per-env series (MicrogridGenerator grids: load / pv = profile * scale normalised
+// on the fly, grid status from the env's own bit row).  Warp-cooperative: lane l builds elements l, l+32, ... of the
+// row in the warp's shared-memory image -- so the 48 f64 normalisations of a row cost two division sites per lane --
+// then the row is streamed out with the same 16-byte stores as every other row.
+// hcode[q] = kind << 16 | offset of element lane + 32 q (row layout is static; decoded once per warp by the caller).
+// (A two-pass variant -- all loads first, arithmetic second -- measured slower: 160 vs 137 us/step at 131 072 envs.)
+__device__ __forceinline__ void emit_row_hetero(const LaunchParams &P, const DevGroup &G, const TileEnv &te, const HeteroEnv &hv,
+                                                const int (&hcode)[MG_HET_SLOTS], double *__restrict__ img, int e,
+                                                double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int D = G.obs_dim, t_obs = te.special;
+    __syncwarp();   // the previous row has been read out of the image
+#pragma unroll
+    for (int q = 0; q < MG_HET_SLOTS; ++q) {
+        const int j = lane + 32 * q, kind = hcode[q] >> 16, off = hcode[q] & 0xffff;
+        if (j >= D) continue;
+        double v;
+        if (kind <= KIND_GEN) {
+            v = te.state[j - G.state_start];
+        } else if (kind == KIND_GRID) {
+            if (G.status_bits && (off & 3) == 3) {
+                const int idx = t_obs + (off >> 2);
+                const double bit = (double)((__ldg(G.status_bits + (size_t)e * G.status_words + (idx >> 5)) >> (idx & 31)) & 1u);
+                // bounds of the status column: (0, 1) on a weak grid, (1, 1) -> spread 1 otherwise (utils/space.py:204-205)
+                v = hv.weak ? (idx < P.T ? bit : 0.5) : 0.0;
+            } else {
+                v = __ldg(P.grid_nrm + te.off_grid + off);
+            }
+        } else {
+            const bool is_load = kind == KIND_LOAD;
+            if (hv.scaled) {   // (profile * scale - low) / spread, or the normalised forecaster fill past the end
+                const int idx = t_obs + off;
+                const double *src = is_load ? P.load_raw + hv.load_base : P.pv_raw + hv.pv_base;
+                const double raw = idx < P.T ? __ldg(src + idx) : 0.0;
+                const double nrm = (raw * (is_load ? hv.load_scale : hv.pv_scale) - (is_load ? hv.load_low : hv.pv_low)) /
+                                   (is_load ? hv.load_spread : hv.pv_spread);
+                v = idx < P.T ? nrm : (is_load ? hv.load_fill : hv.pv_fill);
+            } else {
+                v = is_load ? __ldg(P.load_nrm + te.off_load + off) : __ldg(P.pv_nrm + te.off_pv + off);
+            }
+        }
+        img[j] = v;
+    }
+    __syncwarp();
+    for (int p = lane; p < (D >> 1); p += 32) {
+        const double2 v2 = *reinterpret_cast<const double2 *>(img + 2 * p);
+        st_global_v2(out + 2 * p, v2.x, v2.y);
+    }
+}
+
 // Time-series part of the observation rows of one tile.  Each warp owns MG_ROWS_PER_WARP consecutive rows, i.e. one
 // contiguous chunk of the [n, obs_dim] output; lane l owns the 16-byte pairs l, l+32, ... of every row.
 // Consecutive rows whose windows coincide (same series, same step -- every row of the tile in the lock-step case)
@@ -506,6 +548,15 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
             code[k][h] = (kind << 16) | off;
         }
     }
+    int hcode[MG_HET_SLOTS];   // element-wise layout for rows with per-env series (kHetero kernels only)
+    if (kHetero) {
+#pragma unroll
+        for (int q = 0; q < MG_HET_SLOTS; ++q) {
+            int kind, off;
+            decode_element(G, min(lane + 32 * q, D - 1), kind, off);
+            hcode[q] = (kind << 16) | off;
+        }
+    }
     const bool tma_grid = G.has_grid && G.tma_ok;
     const uint32_t grid_bytes = (uint32_t)(4 * (1 + G.horizon) * sizeof(double));
     // run boundaries of this warp's rows in one vote: bit l set <=> row l starts a new run
@@ -533,41 +584,13 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
                 tma_load(img, P.grid_nrm + sig.off_grid, grid_bytes, &S.bar[warp]);
             }
         }
+        if (kHetero && sig.special >= 0) {   // a row with per-env series: always a run of one
+            emit_row_hetero(P, G, env[r], het[r], hcode, img, e_base + r, obs_tile + (size_t)r * D);
+            r += 1;
+            continue;
+        }
         double v[SLOTS][2];
-        if (kHetero && sig.special >= 0) {
-            // per-env series: profile * scale normalised on the fly (MicrogridGenerator grids) and / or the env's own
-            // grid-status bits; such a row never shares its windows, so it is a run of one
-            const int e = e_base + r;
-            const HeteroEnv hv = het[r];
-            const int t_obs = sig.special;
-#pragma unroll
-            for (int k = 0; k < SLOTS; ++k) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int kind = code[k][h] >> 16, off = code[k][h] & 0xffff;
-                    v[k][h] = 0.0;
-                    if (!act[k] || st_lane[k]) continue;
-                    const bool is_load = kind == KIND_LOAD;
-                    if ((is_load || kind == KIND_PV) && hv.scaled) {   // one normalisation site for both series
-                        const int idx = t_obs + off;
-                        const double *src = is_load ? P.load_raw + hv.load_base : P.pv_raw + hv.pv_base;
-                        const double scale = is_load ? hv.load_scale : hv.pv_scale;
-                        const double low = is_load ? hv.load_low : hv.pv_low;
-                        const double spread = is_load ? hv.load_spread : hv.pv_spread;
-                        const double raw = idx < P.T ? __ldg(src + idx) : 0.0;
-                        const double nrm = (raw * scale - low) / spread;
-                        v[k][h] = idx < P.T ? nrm : (is_load ? hv.load_fill : hv.pv_fill);
-                    } else if (kind == KIND_GRID && G.status_bits && (off & 3) == 3) {
-                        const int idx = t_obs + (off >> 2);
-                        const double bit = (double)((__ldg(G.status_bits + (size_t)e * G.status_words + (idx >> 5)) >> (idx & 31)) & 1u);
-                        // bounds of the status column: (0, 1) on a weak grid, (1, 1) -> spread 1 otherwise (utils/space.py:204-205)
-                        v[k][h] = hv.weak ? (idx < P.T ? bit : 0.5) : 0.0;
-                    } else if (kind == KIND_LOAD) v[k][h] = __ldg(P.load_nrm + sig.off_load + off);
-                    else if (kind == KIND_PV) v[k][h] = __ldg(P.pv_nrm + sig.off_pv + off);
-                    else if (kind == KIND_GRID) v[k][h] = __ldg(P.grid_nrm + sig.off_grid + off);
-                }
-            }
-        } else {
+        {
 #pragma unroll
             for (int k = 0; k < SLOTS; ++k) {
 #pragma unroll
@@ -768,7 +791,7 @@ __device__ __forceinline__ void owner_step(const LaunchParams &P, const DevGroup
 // ------------------------------------------------------------------------------------------------------------------
 // kHetero = true adds the per-env series paths (profile * scale, status bits); table-backed batches run the lean kernel
 template <bool kHetero>
-__global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_step_kernel(const __grid_constant__ LaunchParams P) {
+__global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_MIN_CTAS) mg_step_kernel(const __grid_constant__ LaunchParams P) {
     __shared__ TileShared S;
     __shared__ typename HeteroStorage<kHetero>::type SH;
     HeteroEnv *het0 = HeteroStorage<kHetero>::rows(SH, 0);
@@ -832,7 +855,7 @@ __global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_step_kernel(const 
 // persistent multi-step kernel: every CTA owns its tile for all n_steps; env state stays in registers
 // ------------------------------------------------------------------------------------------------------------------
 template <bool kHetero>
-__global__ void __launch_bounds__(MG_THREADS, MG_MIN_CTAS) mg_rollout_kernel(const __grid_constant__ LaunchParams P) {
+__global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_MIN_CTAS) mg_rollout_kernel(const __grid_constant__ LaunchParams P) {
     __shared__ TileShared S;
     __shared__ typename HeteroStorage<kHetero>::type SH;
     const int gi = find_group(P, blockIdx.x);
@@ -1031,20 +1054,6 @@ static void layout_segments(const MgGroup &g, DevGroup &d) {
         if (k < n) start += lens[k];
     }
     d.n_seg = n;
-    // runs: adjacent time-series segments merge into one shared run; genset + battery obs form the state run
-    int nr = 0;
-    for (int k = 0; k < n; ++k) {
-        const bool is_state = kinds[k] == KIND_BAT || kinds[k] == KIND_GEN;
-        if (nr > 0 && d.run_is_state[nr - 1] == (int)is_state) {
-            d.run_len[nr - 1] += lens[k];
-        } else {
-            d.run_start[nr] = d.seg_start[k];
-            d.run_len[nr] = lens[k];
-            d.run_is_state[nr] = is_state;
-            ++nr;
-        }
-    }
-    d.n_runs = nr;
     d.tma_ok = 1;
     for (int k = 0; k < n; ++k) {
         if (kinds[k] == KIND_GRID && (d.seg_start[k] & 1)) d.tma_ok = 0;   // bulk copies need 16-byte aligned addresses
