@@ -18,7 +18,7 @@ import torch
 
 from . import _cabi
 from ._cabi import (MG_ABI_VERSION, MG_MAX_GROUPS, MG_N_INFO, MG_OBS_CONTAINER, MG_OBS_GYM_SORTED, EngineError,
-                    MgConfig, MgGroup, MgLayout, MgPriorityList, MgRolloutIO, MgStepIO)
+                    MgConfig, MgLayout, MgPriorityList, MgRolloutIO, MgStepIO)
 from .params import MicrogridParams
 from .priority_list import priority_lists
 
@@ -187,7 +187,7 @@ class BatchedMicrogrid:
                 if r is None:
                     index.append(0)
                     continue
-                k = (r.ctypes.data, r.shape) if False else r.tobytes()
+                k = r.tobytes()
                 if k not in keys:
                     keys[k] = len(uniq)
                     uniq.append(r)

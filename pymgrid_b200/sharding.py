@@ -3,7 +3,7 @@ step path (envs are independent: SURVEY.md section 8e).  The only collective is 
 logging (total reward per step / per rollout), an all-reduce over torch.distributed (NCCL on GPUs, gloo in the CPU tests).
 """
 import numpy as np
-import torch
+
 
 
 def shard_range(n_envs, rank, world):

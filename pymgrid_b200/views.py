@@ -80,7 +80,7 @@ def control_dict_to_row(control, p, act_cols):
             v = control.pop(name)
         except KeyError:
             raise ValueError(f'Control for module "{name}" not found. Available controls:\n\t{control.keys()}')
-        if isinstance(v, (list, tuple)) and len(v) == 1 and not (name == "genset" and np.ndim(v[0]) == 0 and False):
+        if isinstance(v, (list, tuple)) and len(v) == 1:      # {name: [value]} -> value (one module per name)
             v = v[0]
         arr = np.asarray(v, dtype=np.float64).reshape(-1)
         col = act_cols[name]
