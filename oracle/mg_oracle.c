@@ -424,9 +424,10 @@ static void *rollout_worker(void *arg) {
     double ctrl[4];
     for (int64_t i = j->lo; i < j->hi; ++i)
         if (!j->grids[i].prepared) orc_prepare(&j->grids[i]);
-    for (int32_t s = 0; s < j->n_steps; ++s) {
-        for (int64_t i = j->lo; i < j->hi; ++i) {
-            OrcGrid *g = &j->grids[i];
+    /* env-major: one grid runs all its steps back to back (its record and series window stay in L1) */
+    for (int64_t i = j->lo; i < j->hi; ++i) {
+        OrcGrid *g = &j->grids[i];
+        for (int32_t s = 0; s < j->n_steps; ++s) {
             double r;
             int32_t d;
             double *obs = (s == j->n_steps - 1 && j->obs_last) ? j->obs_last + (size_t)i * j->obs_stride : scratch;
