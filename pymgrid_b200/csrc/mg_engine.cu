@@ -462,51 +462,71 @@ __device__ __forceinline__ void decode_element(const DevGroup &G, int j, int &ki
     off = j - G.seg_start[sgi];
 }
 
-#define MG_HET_SLOTS (MG_MAX_IMG / 32)   // elements per lane of the longest staged row
+// Where each module's block starts inside an observation row (the row layout is static per group).
+struct RowStarts {
+    int load, pv, grid, state;
+};
+__device__ __forceinline__ RowStarts row_starts(const DevGroup &G) {
+    RowStarts st;
+    st.load = st.pv = st.grid = 0;
+    st.state = G.state_start;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        if (q < G.n_seg) {
+            if (G.seg_kind[q] == KIND_LOAD) st.load = G.seg_start[q];
+            else if (G.seg_kind[q] == KIND_PV) st.pv = G.seg_start[q];
+            else if (G.seg_kind[q] == KIND_GRID) st.grid = G.seg_start[q];
+        }
+    }
+    return st;
+}
 
 // One observation row of an env with per-env series (MicrogridGenerator grids: load / pv = profile * scale normalised
-// on the fly, grid status from the env's own bit row).  Warp-cooperative: lane l builds elements l, l+32, ... of the
-// row in the warp's shared-memory image -- so the 48 f64 normalisations of a row cost two division sites per lane --
-// then the row is streamed out with the same 16-byte stores as every other row.
-// hcode[q] = kind << 16 | offset of element lane + 32 q (row layout is static; decoded once per warp by the caller).
-// (A two-pass variant -- all loads first, arithmetic second -- measured slower: 160 vs 137 us/step at 131 072 envs.)
+// on the fly, grid status from the env's own bit row).  Warp-cooperative, one block of the row at a time so that every
+// lane of a block runs the same code: lane l normalises window element l (+32) of the pv block, then of the load block
+// (one f64 division site each), copies grid elements l, l+32, ... (a lane always sees the same grid column because 32 is
+// a multiple of 4: the lanes with (l & 3) == 3 read the env's status bits instead of the table), lanes 0..5 copy the
+// battery / genset pairs; the row is assembled in the warp's shared-memory image and streamed out with 16-byte stores.
 __device__ __forceinline__ void emit_row_hetero(const LaunchParams &P, const DevGroup &G, const TileEnv &te, const HeteroEnv &hv,
-                                                const int (&hcode)[MG_HET_SLOTS], double *__restrict__ img, int e,
-                                                double *__restrict__ out) {
+                                                const RowStarts &rs, double *__restrict__ img, int e, double *__restrict__ out) {
     const int lane = threadIdx.x & 31;
-    const int D = G.obs_dim, t_obs = te.special;
+    const int D = G.obs_dim, rows = 1 + G.horizon, t_obs = te.special;
     __syncwarp();   // the previous row has been read out of the image
-#pragma unroll
-    for (int q = 0; q < MG_HET_SLOTS; ++q) {
-        const int j = lane + 32 * q, kind = hcode[q] >> 16, off = hcode[q] & 0xffff;
-        if (j >= D) continue;
-        double v;
-        if (kind <= KIND_GEN) {
-            v = te.state[j - G.state_start];
-        } else if (kind == KIND_GRID) {
-            if (G.status_bits && (off & 3) == 3) {
-                const int idx = t_obs + (off >> 2);
-                const double bit = (double)((__ldg(G.status_bits + (size_t)e * G.status_words + (idx >> 5)) >> (idx & 31)) & 1u);
+    for (int k = lane; k < rows; k += 32) {   // pv and load windows
+        const int idx = t_obs + k;
+        double pv, ld;
+        if (hv.scaled) {   // (profile * scale - low) / spread, or the normalised forecaster fill past the end
+            const bool in = idx < P.T;
+            const double rp = in ? __ldg(P.pv_raw + hv.pv_base + idx) : 0.0;
+            const double rl = in ? __ldg(P.load_raw + hv.load_base + idx) : 0.0;
+            const double np_ = (rp * hv.pv_scale - hv.pv_low) / hv.pv_spread;
+            const double nl = (rl * hv.load_scale - hv.load_low) / hv.load_spread;
+            pv = in ? np_ : hv.pv_fill;
+            ld = in ? nl : hv.load_fill;
+        } else {
+            pv = __ldg(P.pv_nrm + te.off_pv + k);
+            ld = __ldg(P.load_nrm + te.off_load + k);
+        }
+        img[rs.pv + k] = pv;
+        img[rs.load + k] = ld;
+    }
+    if (G.has_grid) {
+        const bool status_lane = G.status_bits != nullptr && (lane & 3) == 3;
+        const uint32_t *bits = G.status_bits + (size_t)e * G.status_words;
+        for (int g = lane; g < 4 * rows; g += 32) {
+            double v;
+            if (status_lane) {
+                const int idx = t_obs + (g >> 2);
+                const double bit = (double)((__ldg(bits + (idx >> 5)) >> (idx & 31)) & 1u);
                 // bounds of the status column: (0, 1) on a weak grid, (1, 1) -> spread 1 otherwise (utils/space.py:204-205)
                 v = hv.weak ? (idx < P.T ? bit : 0.5) : 0.0;
             } else {
-                v = __ldg(P.grid_nrm + te.off_grid + off);
+                v = __ldg(P.grid_nrm + te.off_grid + g);
             }
-        } else {
-            const bool is_load = kind == KIND_LOAD;
-            if (hv.scaled) {   // (profile * scale - low) / spread, or the normalised forecaster fill past the end
-                const int idx = t_obs + off;
-                const double *src = is_load ? P.load_raw + hv.load_base : P.pv_raw + hv.pv_base;
-                const double raw = idx < P.T ? __ldg(src + idx) : 0.0;
-                const double nrm = (raw * (is_load ? hv.load_scale : hv.pv_scale) - (is_load ? hv.load_low : hv.pv_low)) /
-                                   (is_load ? hv.load_spread : hv.pv_spread);
-                v = idx < P.T ? nrm : (is_load ? hv.load_fill : hv.pv_fill);
-            } else {
-                v = is_load ? __ldg(P.load_nrm + te.off_load + off) : __ldg(P.pv_nrm + te.off_pv + off);
-            }
+            img[rs.grid + g] = v;
         }
-        img[j] = v;
     }
+    if (lane < 2 + 4 * G.has_genset) img[rs.state + lane] = te.state[lane];
     __syncwarp();
     for (int p = lane; p < (D >> 1); p += 32) {
         const double2 v2 = *reinterpret_cast<const double2 *>(img + 2 * p);
@@ -548,15 +568,7 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
             code[k][h] = (kind << 16) | off;
         }
     }
-    int hcode[MG_HET_SLOTS];   // element-wise layout for rows with per-env series (kHetero kernels only)
-    if (kHetero) {
-#pragma unroll
-        for (int q = 0; q < MG_HET_SLOTS; ++q) {
-            int kind, off;
-            decode_element(G, min(lane + 32 * q, D - 1), kind, off);
-            hcode[q] = (kind << 16) | off;
-        }
-    }
+    const RowStarts rs = row_starts(G);   // used by rows with per-env series (kHetero kernels only)
     const bool tma_grid = G.has_grid && G.tma_ok;
     const uint32_t grid_bytes = (uint32_t)(4 * (1 + G.horizon) * sizeof(double));
     // run boundaries of this warp's rows in one vote: bit l set <=> row l starts a new run
@@ -585,7 +597,7 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
             }
         }
         if (kHetero && sig.special >= 0) {   // a row with per-env series: always a run of one
-            emit_row_hetero(P, G, env[r], het[r], hcode, img, e_base + r, obs_tile + (size_t)r * D);
+            emit_row_hetero(P, G, env[r], het[r], rs, img, e_base + r, obs_tile + (size_t)r * D);
             r += 1;
             continue;
         }
