@@ -211,6 +211,8 @@ def main():
                          "actions), one mg_step launch per step replayed from a CUDA graph, or plain launches from Python")
     ap.add_argument("--single-path", action="store_true", help="time only the headline path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ragged", action="store_true",
+                    help="start every env at its own random step (envs that reset independently): no two rows of a tile share a window")
     ap.add_argument("--preheat", type=float, default=0.2, help="seconds of untimed steps before the warm-up (0 under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -247,6 +249,9 @@ def main():
     rings = [torch.empty((R, g.n_envs, g.obs_dim), dtype=torch.float64, device=dev) for g in groups]
     ring_bytes = sum(r.numel() * 8 for r in rings)
     act_bytes = sum(a.numel() * 8 for a in acts)
+    if args.ragged:
+        for g in groups:
+            g.step.copy_(torch.randint(0, 8760 - 2 * (W + K) - 64 if 2 * (W + K) < 4000 else 100, (g.n_envs,), dtype=torch.int32, device=dev, generator=gen))
     state0 = bm.state_dict()
     launchers = {}   # one pre-bound launcher per (action slot, obs slot)
 
@@ -391,7 +396,7 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "pymgrid25 scenario parameters + series (bundled), synthetic U[0,1) actions",
             "config": {"workload": WORKLOADS[args.workload],
-                       "batch_per_gpu": B, "global_batch": world * B, "forecast_horizon": 23, "path": args.path,
+                       "batch_per_gpu": B, "global_batch": world * B, "forecast_horizon": 23, "path": args.path, "ragged_steps": bool(args.ragged),
                        "l2": f"inputs larger than L2: obs ring of {R} buffers = {ring_bytes / 1e6:.0f} MB and action ring = {act_bytes / 1e6:.0f} MB per GPU (L2 126 MB)",
                        "parallelism": f"batch sharded over {world} GPU(s), no collective on the step path"},
             "gpu_launches": launches,
