@@ -168,6 +168,73 @@ class HostIO:
         return [g.obs.cpu() for g in self.bm.groups]
 
 
+class LogRecorder:
+    """Opt-in log for a SUBSET of a batch (reference: Microgrid.get_log, microgrid.py:434-475; the full log is 169-176 f64
+    columns per env-step, ~800 GB per year at 65 536 envs, so it cannot be always-on -- SURVEY.md section 5).
+
+        rec = bm.recorder([3, 17, 4242])
+        for ...:  rec.step(actions)          # instead of bm.step(actions); same return value
+        df = rec.get_log(17)                 # the reference's DataFrame for that env
+
+    Per step it gathers the selected envs' pre-step state and their info / reward rows on the device and appends them to
+    host lists (one small device->host copy per group per step); the DataFrame is built with views.log_row."""
+
+    def __init__(self, bm, env_ids):
+        if any(g.info is None for g in bm.groups):
+            raise ValueError("LogRecorder needs an engine built with with_info=True")
+        if bm.configs is None:
+            raise ValueError("LogRecorder needs per-config MicrogridParams (not available for array-form batches)")
+        self.bm = bm
+        self.env_ids = [int(e) for e in env_ids]
+        self._sel = []
+        for gi, g in enumerate(bm.groups):
+            mine = [(e, int(bm.env_slot[e])) for e in self.env_ids if bm.env_group[e] == gi]
+            slots = torch.tensor([s for _, s in mine], dtype=torch.long, device=bm.device)
+            self._sel.append(([e for e, _ in mine], slots))
+        self.rows = {e: [] for e in self.env_ids}
+        self.first_step = {}
+
+    def _snapshot(self):
+        out = []
+        for (envs, slots), g in zip(self._sel, self.bm.groups):
+            gen = g.genset[slots].cpu().numpy() if g.genset is not None else None
+            out.append((g.step[slots].cpu().numpy(), g.charge[slots].cpu().numpy(), gen))
+        return out
+
+    def step(self, actions, normalized=True, discrete=False, obs=True):
+        from . import views
+        pre = self._snapshot()
+        res = self.bm.step_discrete(actions, obs=obs) if discrete else self.bm.step(actions, normalized=normalized, obs=obs)
+        post = self._snapshot()
+        for gi, ((envs, slots), g) in enumerate(zip(self._sel, self.bm.groups)):
+            if not envs:
+                continue
+            info, reward = g.info[slots].cpu().numpy(), g.reward[slots].cpu().numpy()
+            for k, e in enumerate(envs):
+                p = self.bm.configs[self.bm.env_config[e]]
+                unpack = lambda w: (int(w) & 0xff, (int(w) >> 8) & 0xff, (int(w) >> 16) & 0xff, (int(w) >> 24) & 0xff)  # noqa: E731
+                gen_pre = unpack(pre[gi][2][k]) if pre[gi][2] is not None else (0, 0, 0, 0)
+                gen_post = unpack(post[gi][2][k]) if post[gi][2] is not None else (0, 0, 0, 0)
+                t = int(pre[gi][0][k])
+                self.first_step.setdefault(e, t)
+                state = views.state_dict(p, t, float(pre[gi][1][k]), gen_pre)
+                self.rows[e].append(views.log_row(p, state, info[k], float(reward[k]), gen_post))
+        return res
+
+    def get_log(self, env_id):
+        import pandas as pd
+        rows = self.rows[int(env_id)]
+        if not rows:
+            return pd.DataFrame()
+        cols = pd.MultiIndex.from_tuples(list(rows[0].keys()), names=["module_name", "module_number", "field"])
+        start = self.first_step[int(env_id)]
+        return pd.DataFrame([list(r.values()) for r in rows], columns=cols, index=pd.RangeIndex(start, start + len(rows)))
+
+    def flush(self):
+        self.rows = {e: [] for e in self.env_ids}
+        self.first_step = {}
+
+
 class BatchedMicrogrid:
     def __init__(self, configs: Sequence[MicrogridParams], env_config, device=None, obs_order="gym_sorted",
                  with_info=False, with_flags=True, remove_redundant_gensets=True, action_order=None):
@@ -532,6 +599,10 @@ class BatchedMicrogrid:
         else:
             _cabi.check(self._lib.mg_rollout(self._handle, io, n_steps, ring, int(bool(normalized)), self._stream()), "mg_rollout")
         return outs[0] if self.single_group else outs
+
+    def recorder(self, env_ids):
+        """Opt-in reference-format log for a subset of envs (see LogRecorder)."""
+        return LogRecorder(self, env_ids)
 
     def host_io(self, normalized=True, discrete=False, obs=True):
         """Pinned host staging for a host-resident control loop (see HostIO)."""

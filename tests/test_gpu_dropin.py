@@ -152,3 +152,31 @@ def test_rule_based_control_on_device(golden):
     assert bool(res["done"][8758, 0]) and not bool(res["done"][8757, 0])
     st = np.array([year.groups[0].step[0].item(), year.groups[0].charge[0].item(), 0, 0, 0, 0], dtype=np.float64)
     np.testing.assert_array_equal(st, z["s0_final_state"])
+
+
+def test_batched_log_recorder_matches_reference_log(golden):
+    """Opt-in log for selected envs of a mixed batch == the reference's get_log() DataFrame (columns, index, values)."""
+    from pymgrid_b200.engine import BatchedMicrogrid
+    z = golden["log"]
+    configs = [load_pymgrid25(n) for n in (0, 1, 2)]
+    B = 300
+    env_config = np.arange(B) % 3
+    bm = BatchedMicrogrid(configs, env_config, device="cuda:0", with_info=True, action_order=("genset", "battery", "grid"))
+    watched = [0, 1, 2, 150, 151, 152]
+    rec = bm.recorder(watched)
+    rng = np.random.default_rng(0)
+    for k in range(30):
+        acts = []
+        for g in bm.groups:
+            a = rng.random((g.n_envs, g.n_act))
+            for slot, e in enumerate(g.env_ids):
+                if e in watched:
+                    a[slot] = z[f"s{env_config[e]}_actions"][k]
+            acts.append(torch.from_numpy(a).cuda())
+        rec.step(acts)
+    for e in watched:
+        n = env_config[e]
+        df = rec.get_log(e)
+        assert ["|".join(map(str, c)) for c in df.columns] == list(z[f"s{n}_columns"])
+        np.testing.assert_array_equal(df.values.astype(float), z[f"s{n}_values"])
+        np.testing.assert_array_equal(df.index.values, z[f"s{n}_index"])
