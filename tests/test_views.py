@@ -73,3 +73,18 @@ def test_dict_views_match_live_reference():
             for k in info:
                 assert {kk: float(vv) for kk, vv in info[k][0].items()} == mine_info[k][0], k
             assert r == orr and d == od
+
+
+def test_trajectory_rules():
+    """reference: tests/envs/test_trajectory.py -- windows inside [initial, final), fixed length honoured."""
+    from pymgrid_b200 import trajectory as tr
+    rng = np.random.default_rng(0)
+    i, f = tr.StochasticTrajectory()(0, 8759, n=5000, rng=rng)
+    assert (i >= 0).all() and (i <= 8759 - 3).all() and (f > i).all() and (f <= 8758).all()
+    i, f = tr.FixedLengthStochasticTrajectory(24)(10, 500, n=2000, rng=rng)
+    assert (f - i == 24).all() and (i >= 10).all() and (f <= 500).all()
+    with pytest.raises(ValueError):
+        tr.FixedLengthStochasticTrajectory(600)(10, 500, n=4)
+    i, f = tr.DeterministicTrajectory(7, 99)(0, 8759, n=3)
+    assert i.tolist() == [7, 7, 7] and f.tolist() == [99, 99, 99]
+    assert tr.DeterministicTrajectory(7, 99)(0, 8759) == (7, 99)
