@@ -134,8 +134,9 @@ class HostIO:
     on the device (`bm.groups[g].obs`) unless `fetch_obs()` is called.
     """
 
-    def __init__(self, bm, normalized=True, discrete=False, obs=True):
+    def __init__(self, bm, normalized=True, discrete=False, obs=True, use_graph=False):
         self.bm = bm
+        self._use_graph, self._graph = use_graph, None
         dt = torch.int32 if discrete else torch.float64
         item = 4 if discrete else 8
         sizes = [g.n_envs * (1 if discrete else g.n_act) for g in bm.groups]
@@ -156,10 +157,24 @@ class HostIO:
         self.h2d_bytes = self._h_act.numel() * item
         self.d2h_bytes = self._h_out.numel()
 
-    def step(self):
+    def _body(self):
         self._d_act.copy_(self._h_act, non_blocking=True)
         self._launch()
         self._h_out.copy_(self.bm._out, non_blocking=True)
+
+    def step(self):
+        """One H2D copy, the fused kernel, one D2H copy.  With use_graph=True the three are replayed from a CUDA graph
+        (captured on first use; capture executes nothing) -- measured no faster on B200 (the PCIe copies dominate), so
+        the default is the plain sequence."""
+        if not self._use_graph:
+            return self._body()
+        if self._graph is None:
+            torch.cuda.current_stream(self.bm.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self._graph = g
+        self._graph.replay()
 
     def sync(self):
         torch.cuda.current_stream(self.bm.device).synchronize()
@@ -561,8 +576,12 @@ class BatchedMicrogrid:
         acts = self.rbc_actions()
         return self.rollout(acts if len(acts) > 1 else acts[0], discrete=True, constant_actions=True, n_steps=n_steps, **kw)
 
+    def prepare_rollout(self, actions, **kw):
+        """Bind a rollout once and return a zero-argument launcher (`launcher.result` holds the output buffers)."""
+        return self.rollout(actions, bind_only=True, **kw)
+
     def rollout(self, actions, normalized=True, discrete=False, ring=1, keep_obs=True, reward_sum=False, out=None,
-                constant_actions=False, n_steps=None, reward_total=None):
+                constant_actions=False, n_steps=None, reward_total=None, bind_only=False):
         """n_steps consecutive steps in one persistent kernel.  actions: per group [n_steps, n, n_act] float64
         (or [n_steps, n] int32 when discrete).  Returns dict(reward=[n_steps, n], done=..., obs_ring=[ring, n, D]);
         pass a previous return value (list of dicts) as `out` to reuse its buffers."""
@@ -594,19 +613,29 @@ class BatchedMicrogrid:
             io[gi].obs_ring, io[gi].reward, io[gi].done = _ptr(r["obs_ring"]), _ptr(r["reward"]), _ptr(r["done"])
             io[gi].reward_sum, io[gi].flags = _ptr(r["reward_sum"]), _ptr(g.flags)
             io[gi].reward_total = _ptr(reward_total)
-        if discrete:
-            _cabi.check(self._lib.mg_rollout_discrete(self._handle, io, n_steps, ring, self._stream()), "mg_rollout_discrete")
-        else:
-            _cabi.check(self._lib.mg_rollout(self._handle, io, n_steps, ring, int(bool(normalized)), self._stream()), "mg_rollout")
-        return outs[0] if self.single_group else outs
+        lib, handle, norm, dev = self._lib, self._handle, int(bool(normalized)), self.device
+
+        def launch():
+            st = torch.cuda.current_stream(dev).cuda_stream
+            rc = (lib.mg_rollout_discrete(handle, io, n_steps, ring, st) if discrete
+                  else lib.mg_rollout(handle, io, n_steps, ring, norm, st))
+            if rc:
+                _cabi.check(rc, "mg_rollout")
+        result = outs[0] if self.single_group else outs
+        if bind_only:      # the caller launches (repeatedly) with minimal host overhead; buffers are kept alive here
+            launch.keepalive = (io, acts, outs, reward_total)
+            launch.result = result
+            return launch
+        launch()
+        return result
 
     def recorder(self, env_ids):
         """Opt-in reference-format log for a subset of envs (see LogRecorder)."""
         return LogRecorder(self, env_ids)
 
-    def host_io(self, normalized=True, discrete=False, obs=True):
+    def host_io(self, normalized=True, discrete=False, obs=True, use_graph=False):
         """Pinned host staging for a host-resident control loop (see HostIO)."""
-        return HostIO(self, normalized=normalized, discrete=discrete, obs=obs)
+        return HostIO(self, normalized=normalized, discrete=discrete, obs=obs, use_graph=use_graph)
 
     # ------------------------------------------------------------------------------------------------------
     @property

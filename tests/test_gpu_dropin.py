@@ -180,3 +180,28 @@ def test_batched_log_recorder_matches_reference_log(golden):
         assert ["|".join(map(str, c)) for c in df.columns] == list(z[f"s{n}_columns"])
         np.testing.assert_array_equal(df.values.astype(float), z[f"s{n}_values"])
         np.testing.assert_array_equal(df.index.values, z[f"s{n}_index"])
+
+
+def test_host_io_graph_replay_equals_eager():
+    """HostIO.step(): pinned-host actions in, reward + done out; the CUDA-graph replay gives the same results as the
+    eager sequence and as BatchedMicrogrid.step on the same actions."""
+    from pymgrid_b200.engine import BatchedMicrogrid
+    configs = [load_pymgrid25(n) for n in range(25)]
+    env_config = np.arange(3000) % 25
+    a = BatchedMicrogrid(configs, env_config, device="cuda:0")
+    b = BatchedMicrogrid(configs, env_config, device="cuda:0")
+    c = BatchedMicrogrid(configs, env_config, device="cuda:0")
+    ha, hb = a.host_io(use_graph=True), b.host_io(use_graph=False)
+    rng = np.random.default_rng(1)
+    for k in range(6):
+        acts = [rng.random(tuple(x.shape)) for x in ha.actions]
+        for dst_a, dst_b, src in zip(ha.actions, hb.actions, acts):
+            dst_a.copy_(torch.from_numpy(src))
+            dst_b.copy_(torch.from_numpy(src))
+        ha.step(); hb.step()
+        ha.sync(); hb.sync()
+        _, reward, done, _ = c.step([torch.from_numpy(x).cuda() for x in acts])
+        assert torch.equal(ha.reward, hb.reward) and torch.equal(ha.done, hb.done)
+        assert torch.equal(ha.reward, c.reward.cpu()) and torch.equal(ha.done, c.done.cpu())
+    for ga, gc in zip(a.groups, c.groups):
+        assert torch.equal(ga.obs, gc.obs) and torch.equal(ga.charge, gc.charge)
