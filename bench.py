@@ -37,13 +37,13 @@ UNIT = "env-steps/s"
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 
 
-def algorithmic_bytes(has_genset, has_grid, horizon, discrete=False):
+def algorithmic_bytes(has_genset, has_grid, horizon, discrete=False, obs_bytes=8):
     """act + state r/w + reward + done + obs, f64 parity mode, per env-step.  +8 for the per-env
     step counter (read + write), which this engine keeps per env so that envs need not run in lock-step."""
     act = 4 if discrete else 8 * (1 + has_grid + 2 * has_genset)
     state = 2 * (8 + 4 * has_genset) + 8
     obs_dim = (1 + horizon) * (2 + 4 * has_grid) + 2 + 4 * has_genset
-    return act + state + 8 + 1 + 8 * obs_dim
+    return act + state + 8 + 1 + obs_bytes * obs_dim
 
 
 def measured_peak():
@@ -118,10 +118,11 @@ WORKLOADS = {
 GRID_SCENARIOS = [0, 4, 6, 11, 12, 14, 16, 1, 8, 9, 10, 13, 18, 22, 24]
 
 
-def build_engine(batch, device, rank=0, world=1, workload="pymgrid25"):
+def build_engine(batch, device, rank=0, world=1, workload="pymgrid25", obs_f32=False):
     """This rank's contiguous slice of the global batch world*batch (global env numbering, independent of the sharding)."""
     from pymgrid_b200.sharding import shard_range, sharded_pymgrid25
-    kw = dict(device=device, with_info=False, with_flags=False)
+    import torch
+    kw = dict(device=device, with_info=False, with_flags=False, obs_dtype=torch.float32 if obs_f32 else torch.float64)
     if workload == "pymgrid25":     # env i -> scenario i mod 25
         return sharded_pymgrid25(world * batch, rank, world, **kw)
     from pymgrid_b200.engine import BatchedMicrogrid
@@ -211,6 +212,8 @@ def main():
                          "actions), one mg_step launch per step replayed from a CUDA graph, or plain launches from Python")
     ap.add_argument("--single-path", action="store_true", help="time only the headline path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--obs-f32", action="store_true",
+                    help="NON-CANONICAL secondary mode: observations written as float32 (half the dominant bytes); reported with dtype f64+f32obs")
     ap.add_argument("--ragged", action="store_true",
                     help="start every env at its own random step (envs that reset independently): no two rows of a tile share a window")
     ap.add_argument("--preheat", type=float, default=0.2, help="seconds of untimed steps before the warm-up (0 under ncu)")
@@ -234,7 +237,7 @@ def main():
     B, K, W, R = args.batch, args.steps, args.warmup, args.ring
     discrete = args.workload == "discrete"
 
-    bm = build_engine(B, dev, rank, world, args.workload)
+    bm = build_engine(B, dev, rank, world, args.workload, args.obs_f32)
     groups = bm.groups
 
     def rand_actions(steps, g):
@@ -246,8 +249,8 @@ def main():
     # every step reads its own actions from HBM: a ring of A steps (> 2x L2) reused cyclically
     A = min(W + K, 256)
     acts = [rand_actions(A, g) for g in groups]
-    rings = [torch.empty((R, g.n_envs, g.obs_dim), dtype=torch.float64, device=dev) for g in groups]
-    ring_bytes = sum(r.numel() * 8 for r in rings)
+    rings = [torch.empty((R, g.n_envs, g.obs_dim), dtype=bm.obs_dtype, device=dev) for g in groups]
+    ring_bytes = sum(r.numel() * r.element_size() for r in rings)
     act_bytes = sum(a.numel() * 8 for a in acts)
     if args.ragged:
         for g in groups:
@@ -375,7 +378,7 @@ def main():
     e2e_value = world * B * Ke / (max_over_ranks(ev0.elapsed_time(ev1)) * 1e-3)
 
     if rank == 0:
-        bytes_per_launch = sum(g.n_envs * algorithmic_bytes(*g.arch, discrete=discrete) for g in groups)
+        bytes_per_launch = sum(g.n_envs * algorithmic_bytes(*g.arch, discrete=discrete, obs_bytes=4 if args.obs_f32 else 8) for g in groups)
         if args.workload == "generator":   # + the env's own parameter record and status word(s), re-read every step
             bytes_per_launch += sum(g.n_envs * (336 + 8 * g.arch[1]) for g in groups)
         peak, peak_src = measured_peak()
@@ -387,13 +390,14 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tr = json.load(f)["mg_rollout_kernel" if args.path == "rollout" else "mg_step_kernel"]
-            if tr["dram_bytes_per_step"] and B == BATCH_PER_GPU and args.workload == "pymgrid25":
+            if tr["dram_bytes_per_step"] and B == BATCH_PER_GPU and args.workload == "pymgrid25" and not args.obs_f32 and not args.ragged:
                 traffic, traffic_src = tr["dram_bytes_per_step"] * steps_per_launch, tr["source"]
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if not args.obs_f32 else "f64 arithmetic, f32 observation output (non-canonical)",
             "data": "pymgrid25 scenario parameters + series (bundled), synthetic U[0,1) actions",
             "config": {"workload": WORKLOADS[args.workload],
                        "batch_per_gpu": B, "global_batch": world * B, "forecast_horizon": 23, "path": args.path, "ragged_steps": bool(args.ragged),

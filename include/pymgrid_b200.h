@@ -146,6 +146,9 @@ typedef struct MgGroup {
 
 /* MgLayout.flags */
 #define MG_LAYOUT_SCALED_SERIES 1    /* some MgConfig has series_scaled != 0: selects the kernels with the per-env series path */
+#define MG_LAYOUT_OBS_F32 2          /* every obs / obs_ring buffer is float32 [n, obs_dim] (the f64 observation rounded to
+                                        nearest); halves the dominant traffic for consumers that feed fp32 policies.
+                                        State, actions, reward and all arithmetic stay f64. */
 
 typedef struct MgLayout {
     int32_t abi_version;
@@ -175,7 +178,7 @@ typedef struct MgLayout {
 typedef struct MgStepIO {
     const double *actions;   /* [n, n_act] f64: normalised in [0,1] or unnormalised (mg_step)                  */
     const int32_t *dactions; /* [n] int32 priority-list index (mg_step_discrete)                              */
-    double *obs;             /* [n, obs_dim] normalised post-step observation, or NULL to skip                */
+    double *obs;             /* [n, obs_dim] normalised post-step observation (float* with MG_LAYOUT_OBS_F32), or NULL to skip */
     double *reward;          /* [n]                                                                           */
     uint8_t *done;           /* [n]                                                                           */
     double *info;            /* [n, MG_N_INFO] or NULL                                                        */

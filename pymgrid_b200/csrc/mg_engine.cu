@@ -91,6 +91,10 @@ __device__ __forceinline__ void st_global_v2(double *p, double a, double b) {
     // 16-byte streaming store: observation rows are written once and never re-read by this kernel
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
+// float32 observation rows (MG_LAYOUT_OBS_F32): the f64 value rounded to nearest, 8-byte stores
+__device__ __forceinline__ void st_global_v2(float *p, double a, double b) {
+    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(__double2float_rn(a)), "f"(__double2float_rn(b)) : "memory");
+}
 
 // ---- TMA (cp.async.bulk, SASS UBLKCP) and mbarrier wrappers -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -487,8 +491,9 @@ __device__ __forceinline__ RowStarts row_starts(const DevGroup &G) {
 // (one f64 division site each), copies grid elements l, l+32, ... (a lane always sees the same grid column because 32 is
 // a multiple of 4: the lanes with (l & 3) == 3 read the env's status bits instead of the table), lanes 0..5 copy the
 // battery / genset pairs; the row is assembled in the warp's shared-memory image and streamed out with 16-byte stores.
+template <typename TO>
 __device__ __forceinline__ void emit_row_hetero(const LaunchParams &P, const DevGroup &G, const TileEnv &te, const HeteroEnv &hv,
-                                                const RowStarts &rs, double *__restrict__ img, int e, double *__restrict__ out) {
+                                                const RowStarts &rs, double *__restrict__ img, int e, TO *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int D = G.obs_dim, rows = 1 + G.horizon, t_obs = te.special;
     __syncwarp();   // the previous row has been read out of the image
@@ -544,9 +549,9 @@ __device__ __forceinline__ void emit_row_hetero(const LaunchParams &P, const Dev
 // The 1-3 lanes that own the battery / genset pairs take them from the env's shared-memory record instead, so every
 // byte of a row -- and of the contiguous 19 KB chunk of 16 rows -- is written by one warp in consecutive instructions
 // (a separate writer for those 48 bytes costs ~20% of the store bandwidth: partial-sector merging in L2).
-template <int SLOTS, bool kHetero>
+template <int SLOTS, bool kHetero, typename TO>
 __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const DevGroup &G, TileShared &S, const HeteroEnv *het,
-                                                 int ebuf, double *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
+                                                 int ebuf, TO *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r_end = min((warp + 1) * MG_ROWS_PER_WARP, n_rows);
     const int D = G.obs_dim, pairs = D >> 1;
@@ -629,7 +634,7 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
                 }
             }
         }
-        double *out = obs_tile + (size_t)r * D + 2 * lane;
+        TO *out = obs_tile + (size_t)r * D + 2 * lane;
         for (int row = 0; row < n; ++row, out += D) {
 #pragma unroll
             for (int k = 0; k < SLOTS; ++k) {
@@ -645,17 +650,18 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
     }
 }
 
-template <bool kHetero>
+template <bool kHetero, typename TO>
 __device__ __forceinline__ void warp_emit_rows(const LaunchParams &P, const DevGroup &G, TileShared &S, const HeteroEnv *het,
-                                               int ebuf, double *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
+                                               int ebuf, TO *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
     const int pairs = G.obs_dim >> 1;
-    if (pairs <= 32) warp_emit_rows_t<1, kHetero>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase);
-    else warp_emit_rows_t<3, kHetero>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase);
+    if (pairs <= 32) warp_emit_rows_t<1, kHetero, TO>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase);
+    else warp_emit_rows_t<3, kHetero, TO>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase);
 }
 
 // rows longer than MG_MAX_IMG: element-wise path straight from the tables (no staging)
+template <typename TO>
 __device__ __forceinline__ void warp_emit_rows_long(const LaunchParams &P, const DevGroup &G, TileShared &S, int ebuf,
-                                                    double *__restrict__ obs_tile, int n_rows) {
+                                                    TO *__restrict__ obs_tile, int n_rows) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r_end = min((warp + 1) * MG_ROWS_PER_WARP, n_rows);
     const int D = G.obs_dim, pairs = D >> 1;
@@ -802,7 +808,7 @@ __device__ __forceinline__ void owner_step(const LaunchParams &P, const DevGroup
 // its rows are issued and the drain overlaps the next launch (measured: 18.4 us/step against 22.9 the other way round).
 // ------------------------------------------------------------------------------------------------------------------
 // kHetero = true adds the per-env series paths (profile * scale, status bits); table-backed batches run the lean kernel
-template <bool kHetero>
+template <bool kHetero, typename TO>
 __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_MIN_CTAS) mg_step_kernel(const __grid_constant__ LaunchParams P) {
     __shared__ TileShared S;
     __shared__ typename HeteroStorage<kHetero>::type SH;
@@ -857,16 +863,16 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
     if (G.obs) {   // CTA-uniform
         __syncthreads();
         uint32_t phase = 0;
-        double *obs_tile = G.obs + (size_t)e0 * G.obs_dim;
-        if (!G.long_path) warp_emit_rows<kHetero>(P, G, S, het0, 0, obs_tile, n_rows, e0, phase);
-        else warp_emit_rows_long(P, G, S, 0, obs_tile, n_rows);
+        TO *obs_tile = reinterpret_cast<TO *>(G.obs) + (size_t)e0 * G.obs_dim;
+        if (!G.long_path) warp_emit_rows<kHetero, TO>(P, G, S, het0, 0, obs_tile, n_rows, e0, phase);
+        else warp_emit_rows_long<TO>(P, G, S, 0, obs_tile, n_rows);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // persistent multi-step kernel: every CTA owns its tile for all n_steps; env state stays in registers
 // ------------------------------------------------------------------------------------------------------------------
-template <bool kHetero>
+template <bool kHetero, typename TO>
 __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_MIN_CTAS) mg_rollout_kernel(const __grid_constant__ LaunchParams P) {
     __shared__ TileShared S;
     __shared__ typename HeteroStorage<kHetero>::type SH;
@@ -915,9 +921,9 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
             // one barrier per step: the records of step s live in env[s & 1]; a warp can only reach the barrier of
             // step s+1 after it has finished reading env[s & 1], so the owners may overwrite it at step s+2
             __syncthreads();
-            double *obs_tile = G.obs + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim;
-            if (!G.long_path) warp_emit_rows<kHetero>(P, G, S, HeteroStorage<kHetero>::rows(SH, ebuf), ebuf, obs_tile, n_rows, e0, phase);
-            else warp_emit_rows_long(P, G, S, ebuf, obs_tile, n_rows);
+            TO *obs_tile = reinterpret_cast<TO *>(G.obs) + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim;
+            if (!G.long_path) warp_emit_rows<kHetero, TO>(P, G, S, HeteroStorage<kHetero>::rows(SH, ebuf), ebuf, obs_tile, n_rows, e0, phase);
+            else warp_emit_rows_long<TO>(P, G, S, ebuf, obs_tile, n_rows);
         }
     }
     if (owner) {
@@ -1009,6 +1015,7 @@ struct MgHandle {
     void *last_stream;
     bool last_was_step;
     bool hetero;            // per-env series (profile * scale) or per-env grid status present: run the kHetero kernels
+    bool obs_f32;           // observation buffers are float32 (MG_LAYOUT_OBS_F32)
 };
 
 static thread_local char g_err[512] = "";
@@ -1095,6 +1102,7 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
     h->launches = 0;
     h->last_was_step = false;
     h->hetero = (L->flags & MG_LAYOUT_SCALED_SERIES) != 0;
+    h->obs_f32 = (L->flags & MG_LAYOUT_OBS_F32) != 0;
     h->last_stream = nullptr;
     for (int g = 0; g < MG_MAX_GROUPS; ++g) h->last_obs[g] = nullptr;
     LaunchParams &B = h->base;
@@ -1190,7 +1198,9 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = overlap ? 1 : 0;
-    cudaError_t e = h->hetero ? cudaLaunchKernelEx(&cfg, mg_step_kernel<true>, P) : cudaLaunchKernelEx(&cfg, mg_step_kernel<false>, P);
+    cudaError_t e;
+    if (h->obs_f32) e = h->hetero ? cudaLaunchKernelEx(&cfg, mg_step_kernel<true, float>, P) : cudaLaunchKernelEx(&cfg, mg_step_kernel<false, float>, P);
+    else e = h->hetero ? cudaLaunchKernelEx(&cfg, mg_step_kernel<true, double>, P) : cudaLaunchKernelEx(&cfg, mg_step_kernel<false, double>, P);
     if (e != cudaSuccess) return cuda_fail(e, "step kernel launch");
     h->launches += 1;
     h->last_was_step = true;
@@ -1233,8 +1243,13 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
         if (d.actions && (d.n_act == 2 || d.n_act == 4) && ((((uintptr_t)d.actions) & 15) || ((d.act_step_stride * 8) & 15)))
             return fail(MG_E_INVALID, "rollout: action rows must stay 16-byte aligned across steps");
     }
-    if (h->hetero) mg_rollout_kernel<true><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
-    else mg_rollout_kernel<false><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+    if (h->obs_f32) {
+        if (h->hetero) mg_rollout_kernel<true, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+        else mg_rollout_kernel<false, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+    } else {
+        if (h->hetero) mg_rollout_kernel<true, double><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+        else mg_rollout_kernel<false, double><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "rollout kernel launch");
     h->launches += 1;

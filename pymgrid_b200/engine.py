@@ -252,8 +252,11 @@ class LogRecorder:
 
 class BatchedMicrogrid:
     def __init__(self, configs: Sequence[MicrogridParams], env_config, device=None, obs_order="gym_sorted",
-                 with_info=False, with_flags=True, remove_redundant_gensets=True, action_order=None):
-        """configs: distinct parameter sets; env_config[i] = index of env i's parameter set."""
+                 with_info=False, with_flags=True, remove_redundant_gensets=True, action_order=None,
+                 obs_dtype=torch.float64):
+        """configs: distinct parameter sets; env_config[i] = index of env i's parameter set.
+        obs_dtype: torch.float64 (the reference's type, bit-exact) or torch.float32 (the same values rounded to nearest:
+        half the dominant memory traffic, for consumers that feed fp32 policies; everything else stays f64)."""
         self.configs = list(configs)
         env_config = np.asarray(env_config, dtype=np.int64)
         if env_config.ndim != 1 or len(env_config) == 0 or env_config.min() < 0 or env_config.max() >= len(self.configs):
@@ -316,10 +319,11 @@ class BatchedMicrogrid:
                                          | (p.genset.steps_until_up << 16) | (p.genset.steps_until_down << 24))
                                          for p in self.configs], dtype=np.int64).astype(np.int32),
                     load_np=load_np, pv_np=pv_np, grid_np=grid_np, cfg_status=status, device=device, obs_order=obs_order,
-                    with_info=with_info, with_flags=with_flags, action_order=action_order)
+                    with_info=with_info, with_flags=with_flags, action_order=action_order, obs_dtype=obs_dtype)
 
     def _setup(self, cfg_np, plist_np, action_tables, env_config, cfg_arch, cfg_step, cfg_charge, cfg_genset, load_np,
-               pv_np, grid_np, cfg_status, device, obs_order, with_info, with_flags, action_order):
+               pv_np, grid_np, cfg_status, device, obs_order, with_info, with_flags, action_order,
+               obs_dtype=torch.float64):
         """Common construction from array-form inputs (also used by the vectorised generator front end):
         cfg_np structured MgConfig records; cfg_arch [n_cfg, 3]; cfg_* initial state per config; series tables;
         cfg_status: None or per-config 0/1 status rows ([n_cfg, T] array or list with None for grid-less configs)."""
@@ -328,6 +332,9 @@ class BatchedMicrogrid:
         self._lib = _cabi.lib()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.obs_order = obs_order
+        if obs_dtype not in (torch.float64, torch.float32):
+            raise ValueError("obs_dtype must be torch.float64 or torch.float32")
+        self.obs_dtype = obs_dtype
         self.n_envs = len(env_config)
         self.env_config = env_config
         self.action_tables = action_tables
@@ -406,7 +413,7 @@ class BatchedMicrogrid:
                 packed = np.packbits(bits, axis=1, bitorder="little").view(np.uint32)
                 g.status_bits = torch.from_numpy(packed.view(np.int32).copy()).to(dev)
                 g.status_words = W
-            g.obs = torch.empty((len(ids), obs_dim), dtype=f64, device=dev)
+            g.obs = torch.empty((len(ids), obs_dim), dtype=obs_dtype, device=dev)
             g.reward = self.reward[start:start + len(ids)]
             g.done = self.done[start:start + len(ids)]
             g.info = torch.zeros((len(ids), MG_N_INFO), dtype=f64, device=dev) if with_info else None
@@ -439,7 +446,7 @@ class BatchedMicrogrid:
         L.cfg, L.load_raw, L.pv_raw, L.grid_raw = _ptr(self.cfg), _ptr(self.load_raw), _ptr(self.pv_raw), _ptr(self.grid_raw)
         L.load_nrm, L.pv_nrm, L.grid_nrm, L.bounds = _ptr(self.load_nrm), _ptr(self.pv_nrm), _ptr(self.grid_nrm), _ptr(self.bounds)
         L.plist, L.n_plist = _ptr(self.plist), self.plist.numel() // C.sizeof(MgPriorityList)
-        L.flags = 1 if self._scaled else 0
+        L.flags = (1 if self._scaled else 0) | (2 if self.obs_dtype == torch.float32 else 0)
         return L
 
     def _stream(self):
@@ -501,8 +508,8 @@ class BatchedMicrogrid:
             if d is not None:
                 if d.dtype != torch.int32 or d.shape != (g.n_envs,) or not d.is_contiguous() or d.device != self.device:
                     raise ValueError(f"group {gi}: discrete actions must be a contiguous int32 [{g.n_envs}] tensor on {self.device}")
-            if o is not None and (o.dtype != torch.float64 or o.shape != (g.n_envs, g.obs_dim) or not o.is_contiguous()):
-                raise ValueError(f"group {gi}: obs buffer must be a contiguous float64 [{g.n_envs}, {g.obs_dim}] tensor")
+            if o is not None and (o.dtype != self.obs_dtype or o.shape != (g.n_envs, g.obs_dim) or not o.is_contiguous()):
+                raise ValueError(f"group {gi}: obs buffer must be a contiguous {self.obs_dtype} [{g.n_envs}, {g.obs_dim}] tensor")
             if m is not None and (m.dtype != torch.uint8 or m.shape != (g.n_envs,)):
                 raise ValueError(f"group {gi}: mask must be uint8 [{g.n_envs}]")
             io[gi].actions, io[gi].dactions, io[gi].obs = _ptr(a), _ptr(d), _ptr(o)
@@ -603,7 +610,7 @@ class BatchedMicrogrid:
                 raise ValueError(f"group {gi}: rollout actions must be contiguous {want}")
             r = out[gi] if out is not None else dict(reward=torch.empty((n_steps, g.n_envs), dtype=torch.float64, device=self.device),
                      done=torch.empty((n_steps, g.n_envs), dtype=torch.uint8, device=self.device),
-                     obs_ring=torch.empty((ring, g.n_envs, g.obs_dim), dtype=torch.float64, device=self.device) if keep_obs else None,
+                     obs_ring=torch.empty((ring, g.n_envs, g.obs_dim), dtype=self.obs_dtype, device=self.device) if keep_obs else None,
                      reward_sum=torch.empty(g.n_envs, dtype=torch.float64, device=self.device) if reward_sum else None)
             outs.append(r)
             if discrete:

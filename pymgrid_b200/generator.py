@@ -141,7 +141,7 @@ def sample(n, seed=0):
 
 
 def engine_from_batch(gb, device=None, obs_order="gym_sorted", with_info=False, with_flags=True, action_order=None,
-                      env_slice=None):
+                      env_slice=None, obs_dtype=None):
     """Array-form construction of a BatchedMicrogrid from a GeneratorBatch (one config record per env, built with numpy).
     env_slice: (lo, hi) to build only this rank's contiguous shard of the batch."""
     from .engine import BatchedMicrogrid
@@ -226,6 +226,7 @@ def engine_from_batch(gb, device=None, obs_order="gym_sorted", with_info=False, 
               cfg_step=np.zeros(n, dtype=np.int32), cfg_charge=gb.bat_soc0[sel] * cap,
               cfg_genset=np.where(hg, 0x0101, 0).astype(np.int32), load_np=load_tab, pv_np=pv_tab, grid_np=grid_np,
               cfg_status=status, device=device, obs_order="gym_sorted_pv_first" if obs_order == "gym_sorted" else obs_order,
-              with_info=with_info, with_flags=with_flags, action_order=action_order)
+              with_info=with_info, with_flags=with_flags, action_order=action_order,
+              **({} if obs_dtype is None else {"obs_dtype": obs_dtype}))
     bm.global_env_ids = np.arange(lo, hi)
     return bm

@@ -498,3 +498,36 @@ def test_aggregate_reward_shuffle_reduction():
     out = bm.rollout(racts, keep_obs=False, reward_total=per_step)
     want = sum(r["reward"].sum(dim=1) for r in out)
     assert torch.allclose(per_step, want, rtol=1e-12, atol=0)
+
+
+def test_float32_observation_output_is_the_rounded_f64_observation():
+    """Secondary mode (MG_LAYOUT_OBS_F32): obs rows written as float32 == the bit-exact f64 observation rounded to
+    nearest; rewards / state are untouched.  Step kernel, persistent kernel, ragged steps, generator grids."""
+    from pymgrid_b200 import generator
+    rng = np.random.default_rng(3)
+    configs = [load_pymgrid25(n) for n in range(25)]
+    B = 3001
+    env_config = np.arange(B) % 25
+    a = engine(configs, env_config, with_info=False)
+    b = engine(configs, env_config, with_info=False, obs_dtype=torch.float32)
+    randomise_state(a, rng, configs, env_config, 8700)
+    b.load_state_dict(a.state_dict())
+    for k in range(5):
+        acts = [torch.rand((g.n_envs, g.n_act), dtype=torch.float64, device="cuda") for g in a.groups]
+        oa, ra, _, _ = as_lists(a.step(acts))
+        ob, rb, _, _ = as_lists(b.step(acts))
+        for x, y, r1, r2 in zip(oa, ob, ra, rb):
+            assert y.dtype == torch.float32 and torch.equal(x.to(torch.float32), y) and torch.equal(r1, r2)
+    racts = [torch.rand((7, g.n_envs, g.n_act), dtype=torch.float64, device="cuda") for g in a.groups]
+    out_a, out_b = a.rollout(racts, ring=2), b.rollout(racts, ring=2)
+    for x, y in zip(out_a, out_b):
+        assert torch.equal(x["obs_ring"].to(torch.float32), y["obs_ring"]) and torch.equal(x["reward"], y["reward"])
+    gb = generator.sample(700, seed=5)
+    ga = generator.engine_from_batch(gb, device="cuda:0")
+    gf = generator.engine_from_batch(gb, device="cuda:0", obs_dtype=torch.float32)
+    for k in range(4):
+        acts = [torch.rand((g.n_envs, g.n_act), dtype=torch.float64, device="cuda") for g in ga.groups]
+        oa, _, _, _ = as_lists(ga.step(acts))
+        ob, _, _, _ = as_lists(gf.step(acts))
+        for x, y in zip(oa, ob):
+            assert torch.equal(x.to(torch.float32), y)
