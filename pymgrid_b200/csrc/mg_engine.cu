@@ -35,6 +35,9 @@
 #ifndef MG_PDL
 #define MG_PDL 0            // programmatic dependent launch between consecutive step launches: measured SLOWER (18.6 vs 16.9 us/step), off
 #endif
+#ifndef MG_ROLLOUT_WS
+#define MG_ROLLOUT_WS 1     // persistent kernel: owner warps / emitter warps pipeline (see mg_rollout_ws_kernel)
+#endif
 #ifndef MG_MIN_CTAS_HETERO
 #define MG_MIN_CTAS_HETERO 7
 #endif
@@ -551,9 +554,11 @@ __device__ __forceinline__ void emit_row_hetero(const LaunchParams &P, const Dev
 // (a separate writer for those 48 bytes costs ~20% of the store bandwidth: partial-sector merging in L2).
 template <int SLOTS, bool kHetero, typename TO>
 __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const DevGroup &G, TileShared &S, const HeteroEnv *het,
-                                                 int ebuf, TO *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
+                                                 int ebuf, TO *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase,
+                                                 int r_begin) {
+    // rows [r_begin, r_begin + MG_ROWS_PER_WARP) of the tile; staging slot and mbarrier are the calling warp's own
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r_end = min((warp + 1) * MG_ROWS_PER_WARP, n_rows);
+    const int r_end = min(r_begin + MG_ROWS_PER_WARP, n_rows);
     const int D = G.obs_dim, pairs = D >> 1;
     const int sp0 = G.state_start >> 1, sp1 = sp0 + 1 + 2 * G.has_genset;
     const TileEnv *env = S.env[ebuf];
@@ -577,7 +582,6 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
     const bool tma_grid = G.has_grid && G.tma_ok;
     const uint32_t grid_bytes = (uint32_t)(4 * (1 + G.horizon) * sizeof(double));
     // run boundaries of this warp's rows in one vote: bit l set <=> row l starts a new run
-    const int r_begin = warp * MG_ROWS_PER_WARP;
     uint32_t starts;
     {
         const int rr = r_begin + lane;
@@ -652,10 +656,11 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
 
 template <bool kHetero, typename TO>
 __device__ __forceinline__ void warp_emit_rows(const LaunchParams &P, const DevGroup &G, TileShared &S, const HeteroEnv *het,
-                                               int ebuf, TO *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase) {
+                                               int ebuf, TO *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase,
+                                               int r_begin) {
     const int pairs = G.obs_dim >> 1;
-    if (pairs <= 32) warp_emit_rows_t<1, kHetero, TO>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase);
-    else warp_emit_rows_t<3, kHetero, TO>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase);
+    if (pairs <= 32) warp_emit_rows_t<1, kHetero, TO>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase, r_begin);
+    else warp_emit_rows_t<3, kHetero, TO>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase, r_begin);
 }
 
 // rows longer than MG_MAX_IMG: element-wise path straight from the tables (no staging)
@@ -864,7 +869,7 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
         __syncthreads();
         uint32_t phase = 0;
         TO *obs_tile = reinterpret_cast<TO *>(G.obs) + (size_t)e0 * G.obs_dim;
-        if (!G.long_path) warp_emit_rows<kHetero, TO>(P, G, S, het0, 0, obs_tile, n_rows, e0, phase);
+        if (!G.long_path) warp_emit_rows<kHetero, TO>(P, G, S, het0, 0, obs_tile, n_rows, e0, phase, (tid >> 5) * MG_ROWS_PER_WARP);
         else warp_emit_rows_long<TO>(P, G, S, 0, obs_tile, n_rows);
     }
 }
@@ -922,7 +927,7 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
             // step s+1 after it has finished reading env[s & 1], so the owners may overwrite it at step s+2
             __syncthreads();
             TO *obs_tile = reinterpret_cast<TO *>(G.obs) + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim;
-            if (!G.long_path) warp_emit_rows<kHetero, TO>(P, G, S, HeteroStorage<kHetero>::rows(SH, ebuf), ebuf, obs_tile, n_rows, e0, phase);
+            if (!G.long_path) warp_emit_rows<kHetero, TO>(P, G, S, HeteroStorage<kHetero>::rows(SH, ebuf), ebuf, obs_tile, n_rows, e0, phase, (tid >> 5) * MG_ROWS_PER_WARP);
             else warp_emit_rows_long<TO>(P, G, S, ebuf, obs_tile, n_rows);
         }
     }
@@ -932,6 +937,111 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
         if (G.has_genset) G.genset[e] = pack_genset(s);
         if (G.reward_sum) G.reward_sum[e] = rsum;
         if (G.flags) G.flags[e] = fsum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// warp-specialised persistent kernel (used when observations are written and rows take the staged path):
+//   warps 0-1  owners : physics of step s, publish the tile record into env[s & 1], signal FULL[s & 1]
+//   warps 2-3  emitters: wait FULL[s & 1], stream the 64 rows of step s (32 rows per warp), signal EMPTY[s & 1]
+// The co-resident CTAs of an SM run in lock-step, so without this split every CTA is in its latency-bound physics at the
+// same time and nothing is storing; here the owners compute step s+1 while the emitters stream step s.
+// Named barriers (bar.sync / bar.arrive, 128 threads each): a barrier completes when the 64 threads of one role have
+// arrived and the 64 of the other role have synced.
+// ------------------------------------------------------------------------------------------------------------------
+enum { BAR_FULL0 = 1, BAR_FULL1 = 2, BAR_EMPTY0 = 3, BAR_EMPTY1 = 4 };
+// immediate barrier ids (a register id would make ptxas reserve all 16 hardware barriers of the CTA)
+__device__ __forceinline__ void named_bar_sync(int base, int buf) {
+    if (base == BAR_FULL0) {
+        if (buf) asm volatile("bar.sync 2, 128;" ::: "memory");
+        else asm volatile("bar.sync 1, 128;" ::: "memory");
+    } else {
+        if (buf) asm volatile("bar.sync 4, 128;" ::: "memory");
+        else asm volatile("bar.sync 3, 128;" ::: "memory");
+    }
+}
+__device__ __forceinline__ void named_bar_arrive(int base, int buf) {
+    if (base == BAR_FULL0) {
+        if (buf) asm volatile("bar.arrive 2, 128;" ::: "memory");
+        else asm volatile("bar.arrive 1, 128;" ::: "memory");
+    } else {
+        if (buf) asm volatile("bar.arrive 4, 128;" ::: "memory");
+        else asm volatile("bar.arrive 3, 128;" ::: "memory");
+    }
+}
+
+template <bool kHetero, typename TO>
+__global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_MIN_CTAS) mg_rollout_ws_kernel(const __grid_constant__ LaunchParams P) {
+    static_assert(MG_THREADS == 128 && MG_TILE == 64, "role split assumes 2 owner warps + 2 emitter warps");
+    __shared__ TileShared S;
+    __shared__ typename HeteroStorage<kHetero>::type SH;
+    const int gi = find_group(P, blockIdx.x);
+    const DevGroup &G = P.g[gi];
+    const int e0 = (blockIdx.x - G.tile_begin) * MG_TILE;
+    const int n_rows = min(MG_TILE, G.n_envs - e0);
+    const int tid = threadIdx.x;
+    if ((tid & 31) == 0) mbar_init(&S.bar[tid >> 5], 1);
+    __syncthreads();
+    if (tid < MG_TILE) {   // ---------------- owners ----------------
+        const bool owner = tid < n_rows;
+        const int e = e0 + tid;
+        const MgConfig *__restrict__ c = P.cfg;
+        EnvRegs s;
+        s.t = 0; s.charge = 0.0; s.cs = s.gs = s.up = s.dn = 0;
+        int final_step = 0;
+        double rsum = 0.0;
+        uint32_t fsum = 0;
+        if (owner) {
+            c = P.cfg + __ldg(G.cfg_index + e);
+            s.t = G.step[e];
+            s.charge = G.charge[e];
+            if (G.has_genset) unpack_genset(G.genset[e], s);
+            final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
+        }
+        for (int step = 0; step < P.n_steps; ++step) {
+            const int ebuf = step & 1;
+            double my_reward = 0.0;
+            StepInputs in;
+            in.valid = false;
+            if (owner) in = fetch_inputs<kHetero>(P, G, c, e, step, s.t);
+            if (step >= 2) named_bar_sync(BAR_EMPTY0, ebuf);   // the emitters are done with env[ebuf] of step - 2
+            if (owner) {
+                double reward;
+                int done;
+                uint32_t flags;
+                owner_step(P, G, c, s, in, final_step, nullptr, reward, done, flags);
+                G.reward[(size_t)step * G.out_step_stride + e] = reward;
+                G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)done;
+                rsum += reward;
+                fsum |= flags;
+                my_reward = reward;
+                publish_env<kHetero>(S.env[ebuf][tid], kHetero ? HeteroStorage<kHetero>::rows(SH, ebuf) + tid : nullptr, c, G, s, P.T, P.Tp);
+            }
+            __threadfence_block();   // the tile record is visible before the emitters are released
+            named_bar_arrive(BAR_FULL0, ebuf);
+            if (G.reward_total) add_reward_total(G.reward_total + step, my_reward, owner);
+        }
+        if (owner) {
+            G.step[e] = s.t;
+            G.charge[e] = s.charge;
+            if (G.has_genset) G.genset[e] = pack_genset(s);
+            if (G.reward_sum) G.reward_sum[e] = rsum;
+            if (G.flags) G.flags[e] = fsum;
+        }
+    } else {               // ---------------- emitters ----------------
+        uint32_t phase = 0;
+        const int half = (tid >> 5) - 2;   // 0 or 1: rows [32 half, 32 half + 32)
+        for (int step = 0; step < P.n_steps; ++step) {
+            const int ebuf = step & 1;
+            named_bar_sync(BAR_FULL0, ebuf);
+            TO *obs_tile = reinterpret_cast<TO *>(G.obs) + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim;
+            const HeteroEnv *het = HeteroStorage<kHetero>::rows(SH, ebuf);
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q)
+                warp_emit_rows<kHetero, TO>(P, G, S, het, ebuf, obs_tile, n_rows, e0, phase, 32 * half + MG_ROWS_PER_WARP * q);
+            __threadfence_block();   // every read of env[ebuf] / het[ebuf] has completed before the owners may overwrite them
+            named_bar_arrive(BAR_EMPTY0, ebuf);
+        }
     }
 }
 
@@ -1243,7 +1353,18 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
         if (d.actions && (d.n_act == 2 || d.n_act == 4) && ((((uintptr_t)d.actions) & 15) || ((d.act_step_stride * 8) & 15)))
             return fail(MG_E_INVALID, "rollout: action rows must stay 16-byte aligned across steps");
     }
-    if (h->obs_f32) {
+    bool ws = MG_ROLLOUT_WS != 0;
+    for (int g = 0; g < P.n_groups; ++g)
+        if (!P.g[g].obs || P.g[g].long_path) ws = false;
+    if (ws) {
+        if (h->obs_f32) {
+            if (h->hetero) mg_rollout_ws_kernel<true, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+            else mg_rollout_ws_kernel<false, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+        } else {
+            if (h->hetero) mg_rollout_ws_kernel<true, double><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+            else mg_rollout_ws_kernel<false, double><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+        }
+    } else if (h->obs_f32) {
         if (h->hetero) mg_rollout_kernel<true, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
         else mg_rollout_kernel<false, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
     } else {
