@@ -146,6 +146,32 @@ def engine_from_batch(gb, device=None, obs_order="gym_sorted", with_info=False, 
     env_slice: (lo, hi) to build only this rank's contiguous shard of the batch."""
     from .engine import BatchedMicrogrid
     lo, hi = (0, gb.n) if env_slice is None else env_slice
+    n = hi - lo
+    pr = gb.profiles
+    cfg, tables, plist_rows, load_tab, pv_tab, grid_np = batch_config_records(gb, lo, hi)
+    sel = slice(lo, hi)
+    hg, hr = gb.has_genset[sel], gb.has_grid[sel]
+    cap = gb.bat_capacity[sel].astype(np.float64)
+    status = gb.status[sel]
+    bm = BatchedMicrogrid.__new__(BatchedMicrogrid)
+    bm.configs = None
+    bm.generator_batch = gb
+    bm._setup(cfg_np=cfg, plist_np=np.concatenate(plist_rows).view(np.uint8), action_tables=tables,
+              env_config=np.arange(n), cfg_arch=np.stack([hg.astype(np.int64), hr.astype(np.int64), np.full(n, HORIZON)], axis=1),
+              cfg_step=np.zeros(n, dtype=np.int32), cfg_charge=gb.bat_soc0[sel] * cap,
+              cfg_genset=np.where(hg, 0x0101, 0).astype(np.int32), load_np=load_tab, pv_np=pv_tab, grid_np=grid_np,
+              cfg_status=status, device=device, obs_order="gym_sorted_pv_first" if obs_order == "gym_sorted" else obs_order,
+              with_info=with_info, with_flags=with_flags, action_order=action_order,
+              **({} if obs_dtype is None else {"obs_dtype": obs_dtype}))
+    bm.global_env_ids = np.arange(lo, hi)
+    return bm
+
+
+def batch_config_records(gb, lo=0, hi=None):
+    """The MgConfig records of grids [lo, hi) of a GeneratorBatch, built with numpy (no device needed), plus the shared
+    tables they index: (cfg, action tables per architecture, priority-list rows, load table, pv table, grid tables).
+    Field for field the same as engine.config_record(gb.to_params(i), ...) (tests/test_generator.py)."""
+    hi = gb.n if hi is None else hi
     sel = slice(lo, hi)
     n = hi - lo
     pr = gb.profiles
@@ -174,7 +200,7 @@ def engine_from_batch(gb, device=None, obs_order="gym_sorted", with_info=False, 
     sp = cfg["gen_running_max"] - 0.0
     cfg["gen_act_spread"] = np.where(sp == 0, 1.0, sp)
     cfg["gen_up_spread"] = cfg["gen_down_spread"] = 1.0
-    cfg["gen_allow_abortion"] = 1
+    cfg["gen_allow_abortion"] = hg.astype(np.int32)
     gp = gb.grid_power[sel].astype(np.float64)
     cfg["grid_max_import"] = cfg["grid_max_export"] = np.where(hr, gp, 0.0)
     cfg["grid_cost_per_unit_co2"] = np.where(hr, 0.1, 0.0)
@@ -218,15 +244,4 @@ def engine_from_batch(gb, device=None, obs_order="gym_sorted", with_info=False, 
     arch_key = hg.astype(np.int64) * 2 + hr.astype(np.int64)
     cfg["plist_offset"] = np.select([arch_key == 2, arch_key == 1, arch_key == 3], [offsets[(1, 0)], offsets[(0, 1)], offsets[(1, 1)]])
     cfg["plist_count"] = np.select([arch_key == 2, arch_key == 1, arch_key == 3], [len(tables[(1, 0)]), len(tables[(0, 1)]), len(tables[(1, 1)])])
-    bm = BatchedMicrogrid.__new__(BatchedMicrogrid)
-    bm.configs = None
-    bm.generator_batch = gb
-    bm._setup(cfg_np=cfg, plist_np=np.concatenate(plist_rows).view(np.uint8), action_tables=tables,
-              env_config=np.arange(n), cfg_arch=np.stack([hg.astype(np.int64), hr.astype(np.int64), np.full(n, HORIZON)], axis=1),
-              cfg_step=np.zeros(n, dtype=np.int32), cfg_charge=gb.bat_soc0[sel] * cap,
-              cfg_genset=np.where(hg, 0x0101, 0).astype(np.int32), load_np=load_tab, pv_np=pv_tab, grid_np=grid_np,
-              cfg_status=status, device=device, obs_order="gym_sorted_pv_first" if obs_order == "gym_sorted" else obs_order,
-              with_info=with_info, with_flags=with_flags, action_order=action_order,
-              **({} if obs_dtype is None else {"obs_dtype": obs_dtype}))
-    bm.global_env_ids = np.arange(lo, hi)
-    return bm
+    return cfg, tables, plist_rows, load_tab, pv_tab, grid_np

@@ -48,3 +48,25 @@ def test_sampler_distributions_and_explicit_form():
     o = OracleGrid(p)
     obs, r, d, _, flags = o.run(np.array([1.0, 0.5, 0.5, 0.5]))
     assert np.isfinite(r) and not d and (obs >= 0).all() and (obs <= 1).all()
+
+
+def test_vectorised_config_records_equal_the_scalar_builder():
+    """generator.batch_config_records (numpy, one record per env) == engine.config_record(to_params(i)) field for field."""
+    from pymgrid_b200 import _cabi
+    from pymgrid_b200.engine import config_record
+    gb = generator.sample(300, seed=9)
+    cfg, tables, plist_rows, load_tab, pv_tab, grid_np = generator.batch_config_records(gb)
+    n_co2 = gb.profiles["co2"].shape[0]
+    skip = {"reserved", "plist_offset"}
+    for i in range(gb.n):
+        p = gb.to_params(i)
+        grid_series = (int(gb.tariff[i]) - 1) * n_co2 + int(gb.co2_profile[i]) if p.has_grid else 0
+        want = config_record(p, int(gb.load_profile[i]), int(gb.pv_profile[i]), grid_series, 0, len(tables[(int(p.has_genset), int(p.has_grid))]))
+        for name, _ in _cabi.MgConfig._fields_:
+            if name in skip:
+                continue
+            assert cfg[name][i] == getattr(want, name), (i, name, cfg[name][i], getattr(want, name))
+        if p.has_grid:
+            np.testing.assert_array_equal(grid_np[grid_series], p.grid.time_series)
+        np.testing.assert_array_equal(load_tab[gb.load_profile[i]], p.load_ts)
+        np.testing.assert_array_equal(pv_tab[gb.pv_profile[i]], p.pv_ts)
