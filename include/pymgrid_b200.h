@@ -251,6 +251,13 @@ int mg_observe(MgHandle *h, const MgStepIO *io, void *stream);
 int mg_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, int normalized, void *stream);
 int mg_rollout_discrete(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, void *stream);
 
+/* Tuning knobs.  MG_OPT_ROLLOUT_SPECIALISED (default 1): run mg_rollout with the owner / emitter warp-specialised
+ * kernel when every group writes observations.  It wins when the envs of a tile advance in lock-step (11.5 vs 12.4
+ * us/step at 65 536 envs) and loses when every env is at its own step (39.6 vs 29 us/step): hosts that install per-env
+ * trajectory windows turn it off. */
+enum { MG_OPT_ROLLOUT_SPECIALISED = 1 };
+int mg_set_option(MgHandle *h, int option, int value);
+
 /* number of kernel launches this handle has enqueued since creation (bench.py's gpu_launches claim) */
 int64_t mg_launch_count(const MgHandle *h);
 

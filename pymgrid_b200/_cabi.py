@@ -14,6 +14,7 @@ MG_N_INFO = 16
 MG_PLIST_WIDTH = 3
 MG_OBS_GYM_SORTED, MG_OBS_CONTAINER, MG_OBS_GYM_SORTED_PV_FIRST = 0, 1, 2
 MG_MOD_NONE, MG_MOD_GENSET, MG_MOD_BATTERY, MG_MOD_GRID = -1, 0, 1, 2
+MG_OPT_ROLLOUT_SPECIALISED = 1
 
 FLAG_NAMES = {
     1 << 0: "GENSET_GOAL_RANGE", 1 << 1: "GENSET_AS_SINK", 1 << 2: "BALANCE", 1 << 3: "BATTERY_MIN_CAP",
@@ -110,6 +111,7 @@ def lib():
     L.mg_observe.argtypes = [_vp, C.POINTER(MgStepIO), _vp]
     L.mg_rollout.argtypes = [_vp, C.POINTER(MgRolloutIO), _i32, _i32, C.c_int, _vp]
     L.mg_rollout_discrete.argtypes = [_vp, C.POINTER(MgRolloutIO), _i32, _i32, _vp]
+    L.mg_set_option.argtypes = [_vp, C.c_int, C.c_int]
     L.mg_launch_count.argtypes = [_vp]
     L.mg_launch_count.restype = C.c_int64
     if L.mg_abi_version() != MG_ABI_VERSION:
@@ -123,7 +125,7 @@ def lib():
 
 EXPORTED_SYMBOLS = ("mg_abi_version", "mg_sizeof", "mg_build_info", "mg_last_error", "mg_create", "mg_destroy",
                     "mg_step", "mg_step_discrete", "mg_reset", "mg_observe", "mg_rollout", "mg_rollout_discrete",
-                    "mg_launch_count")
+                    "mg_launch_count", "mg_set_option")
 
 
 def check(code, what):

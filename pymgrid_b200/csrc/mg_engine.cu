@@ -1126,6 +1126,7 @@ struct MgHandle {
     bool last_was_step;
     bool hetero;            // per-env series (profile * scale) or per-env grid status present: run the kHetero kernels
     bool obs_f32;           // observation buffers are float32 (MG_LAYOUT_OBS_F32)
+    bool rollout_specialised;   // MG_OPT_ROLLOUT_SPECIALISED
 };
 
 static thread_local char g_err[512] = "";
@@ -1213,6 +1214,7 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
     h->last_was_step = false;
     h->hetero = (L->flags & MG_LAYOUT_SCALED_SERIES) != 0;
     h->obs_f32 = (L->flags & MG_LAYOUT_OBS_F32) != 0;
+    h->rollout_specialised = true;
     h->last_stream = nullptr;
     for (int g = 0; g < MG_MAX_GROUPS; ++g) h->last_obs[g] = nullptr;
     LaunchParams &B = h->base;
@@ -1273,6 +1275,15 @@ extern "C" int mg_destroy(MgHandle *h) {
 }
 
 extern "C" int64_t mg_launch_count(const MgHandle *h) { return h ? h->launches : 0; }
+
+extern "C" int mg_set_option(MgHandle *h, int option, int value) {
+    if (!h) return fail(MG_E_INVALID, "mg_set_option: null handle");
+    if (option == MG_OPT_ROLLOUT_SPECIALISED) {
+        h->rollout_specialised = value != 0;
+        return MG_OK;
+    }
+    return fail(MG_E_INVALID, "mg_set_option: unknown option");
+}
 
 static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized, void *stream) {
     if (!h || !io) return fail(MG_E_INVALID, "step: null argument");
@@ -1354,7 +1365,7 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
             return fail(MG_E_INVALID, "rollout: action rows must stay 16-byte aligned across steps");
     }
     // per-env series rows are expensive to assemble: four emitting warps beat two there (98 vs 120 us/step measured)
-    bool ws = MG_ROLLOUT_WS != 0 && !h->hetero;
+    bool ws = MG_ROLLOUT_WS != 0 && !h->hetero && h->rollout_specialised;
     for (int g = 0; g < P.n_groups; ++g)
         if (!P.g[g].obs || P.g[g].long_path) ws = false;
     if (ws) {

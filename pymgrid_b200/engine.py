@@ -461,6 +461,15 @@ class BatchedMicrogrid:
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.mg_create(C.byref(L), self._stream(), C.byref(h)), "mg_create")
         self._handle = h
+        # envs with their own episode windows do not advance in lock-step: the plain persistent kernel is faster there
+        ragged = any(g.env_initial_step is not None for g in self.groups)
+        self.set_rollout_specialised(not ragged)
+
+    def set_rollout_specialised(self, on):
+        """Owner / emitter warp-specialised persistent kernel for `rollout` (default: on unless per-env trajectory windows
+        are installed).  Best when the envs of a tile are at the same step; turn it off for batches whose envs were
+        started at unrelated steps."""
+        _cabi.check(self._lib.mg_set_option(self._handle, _cabi.MG_OPT_ROLLOUT_SPECIALISED, int(bool(on))), "mg_set_option")
 
     def __del__(self):
         try:

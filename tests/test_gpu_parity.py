@@ -237,13 +237,16 @@ def test_batch_vs_oracle_ragged_state(order):
         np.testing.assert_array_equal(np.array([s[2:] for s in st]), gen)
 
 
-def test_rollout_kernel_equals_repeated_steps():
-    """mg_rollout (persistent kernel, state in registers) == n_steps x mg_step, bit for bit, incl. the obs ring."""
+@pytest.mark.parametrize("specialised", [True, False])
+def test_rollout_kernel_equals_repeated_steps(specialised):
+    """mg_rollout (persistent kernel, state in registers; warp-specialised or plain, MG_OPT_ROLLOUT_SPECIALISED)
+    == n_steps x mg_step, bit for bit, incl. the obs ring."""
     rng = np.random.default_rng(5)
     configs = [load_pymgrid25(n) for n in range(25)]
     B, n_steps, ring = 1000, 17, 4
     env_config = np.arange(B) % 25
     a = engine(configs, env_config)
+    a.set_rollout_specialised(specialised)
     b = engine(configs, env_config)
     randomise_state(a, rng, configs, env_config, 8700)
     b.load_state_dict(a.state_dict())
