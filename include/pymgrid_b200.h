@@ -68,6 +68,7 @@ enum {
     MG_FLAG_NEGATIVE_ABSORB = 1u << 4,   /* AssertionError base_module.py:272                           */
     MG_FLAG_STEP_PAST_END = 1u << 5,     /* IndexError     load_module.py:111 (t >= len(series))        */
     MG_FLAG_BAD_ACTION = 1u << 6,        /* ValueError     envs/discrete/discrete.py:84 (action not in space) */
+    MG_FLAG_SHAPER_RANGE = 1u << 7,      /* AssertionError reward_shaping/battery_discharge_shaper.py:33 (value outside [-1, 1]) */
     MG_FLAG_CLIP_GENSET = 1u << 8,       /* ValueError when raise_errors=True, base_module.py:213-221   */
     MG_FLAG_CLIP_BATTERY = 1u << 9,
     MG_FLAG_CLIP_GRID = 1u << 10,
@@ -109,8 +110,16 @@ typedef struct MgConfig {
     int32_t plist_offset, plist_count;                       /* rows of MgLayout.plist owned by this config   */
     int32_t series_scaled;                                   /* see load_scale                                */
     int32_t grid_status_weak;                                /* per-env status bits: 1 if any outage (obs bounds 0..1), 0 if all ones */
-    int32_t reserved[4];
+    int32_t reward_shaper;                                   /* MG_SHAPER_*: what `reward` carries (microgrid/utils/step.py:41-46) */
+    int32_t reserved[3];
 } MgConfig;
+
+/* Microgrid(reward_shaping_func=...): the reference's two built-in shapers replace the step reward (the sum of module
+ * rewards stays available through the info block's per-module rewards).
+ *   PV_CURTAILMENT     reward = -1.0 * curtailment                       reward_shaping/pv_curtailment_shaper.py:16-18
+ *   BATTERY_DISCHARGE  reward = (battery discharge - loss load) / load   reward_shaping/battery_discharge_shaper.py:23-35
+ *                      (IEEE division; MG_FLAG_SHAPER_RANGE where the reference's assert on [-1, 1] fires, nan included) */
+enum { MG_SHAPER_NONE = 0, MG_SHAPER_PV_CURTAILMENT = 1, MG_SHAPER_BATTERY_DISCHARGE = 2 };
 
 /*
  * One priority list = one discrete action (algos/priority_list/priority_list.py:15-67): up to MG_PLIST_WIDTH
@@ -250,6 +259,33 @@ int mg_observe(MgHandle *h, const MgStepIO *io, void *stream);
  */
 int mg_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, int normalized, void *stream);
 int mg_rollout_discrete(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, void *stream);
+
+/*
+ * mg_forecast_noise -- GaussianNoiseForecaster (forecast/forecaster.py:220-262) applied to observation rows that
+ * mg_step / mg_step_discrete / mg_reset / mg_observe have just written on the same stream.
+ *
+ * The reference adds N(0, std_k) to every REAL row k of a module's forecast window (rows past the end of the series are
+ * padded afterwards and carry no noise, :120-132), clips to the column's bounds (:139-149) and normalises.  In normalised
+ * units that is  obs <- min(max(obs + z * sigma * scale_k, 0), 1)  with sigma = std / (high - low) of the column and
+ * scale_k = 1 + log(1 + k) when increase_uncertainty is set (:244-248), 1 otherwise.  The host fills MgForecastNoise per
+ * config: relative_noise (std * |mean(series)|, :239-242) is already folded into sigma, and sigma = 0 for a constant
+ * column (the clip pins it to its bound) and for modules with the oracle forecaster.  The current values (the first row of
+ * every module block), the battery / genset entries and the physics are untouched.
+ *
+ * z is standard normal (Box-Muller over Philox4x32-10), a pure function of (seed, call, global env id, the env's step,
+ * element): reproducible, independent of the launch shape, and independent between envs, steps and calls -- where the
+ * reference draws from numpy's global generator.  Parity with the reference is therefore distributional.
+ * `env_base[g]` is the global id of group g's first env (group slots are consecutive ids), so that shards of one batch
+ * on different GPUs draw different noise.  `obs[g]` may be NULL to skip a group.
+ */
+typedef struct MgForecastNoise {
+    double load_sigma, pv_sigma, grid_sigma[4];              /* normalised units; 0 = leave the column alone */
+    int32_t load_increase, pv_increase, grid_increase, _pad; /* increase_uncertainty per module               */
+} MgForecastNoise;
+
+int mg_forecast_noise(MgHandle *h, const MgForecastNoise *noise /* DEVICE [n_cfg] */, void *const *obs /* [n_groups] */,
+                      const int64_t *env_base /* HOST [n_groups] or NULL -> 0, n_0, n_0 + n_1, ... */,
+                      uint64_t seed, uint64_t call, void *stream);
 
 /* Tuning knobs.  MG_OPT_ROLLOUT_SPECIALISED (default 1): run mg_rollout with the owner / emitter warp-specialised
  * kernel when every group writes observations.  It wins when the envs of a tile advance in lock-step (11.5 vs 12.4

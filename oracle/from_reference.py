@@ -32,7 +32,10 @@ def params_from_reference(m):
                                cost_per_unit_co2=g.cost_per_unit_co2)
     load, pv = mods.load[0], mods.pv[0] if hasattr(mods, "pv") else mods.renewable[0]
     unb = mods.unbalanced_energy[0] if hasattr(mods, "unbalanced_energy") else mods.balancing[0]
-    return SimpleNamespace(battery=battery, genset=genset, grid=grid,
+    shaper = getattr(m, "reward_shaping_func", None)
+    shaper = {None: None, "PVCurtailmentShaper": "pv_curtailment",
+              "BatteryDischargeShaper": "battery_discharge"}[None if shaper is None else type(shaper).__name__]
+    return SimpleNamespace(battery=battery, genset=genset, grid=grid, reward_shaper=shaper,
                            load_ts=np.array(load.time_series[:, 0], dtype=np.float64),
                            pv_ts=np.array(pv.time_series[:, 0], dtype=np.float64),
                            loss_load_cost=unb.loss_load_cost, overgeneration_cost=unb.overgeneration_cost,

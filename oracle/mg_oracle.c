@@ -27,6 +27,11 @@ static double space_normalize(double v, double low, double high) { return (v - l
 static double space_denormalize(double x, double low, double high) { return low + space_spread(low, high) * x; }
 
 /* numpy.isclose(a, b) with default rtol=1e-5, atol=1e-8 */
+static int np_isclose(double a, double b, double rtol, double atol);
+static int shaper_in_range(double v) {
+    return (-1 <= v && v <= 1) || np_isclose(v, 1.0, 1e-5, 1e-8) || np_isclose(v, 0.0, 1e-5, 1e-8);
+}
+
 static int np_isclose(double a, double b, double rtol, double atol) {
     return fabs(a - b) <= (atol + rtol * fabs(b));
 }
@@ -337,6 +342,17 @@ void orc_run(OrcGrid *g, const double *control, int normalized, int order, doubl
     if (!np_isclose(provided, consumed, 1e-5, 1e-8)) err |= ORC_ERR_BALANCE; /* microgrid.py:321-323 */
 
     g->t = t + 1; /* every module: _update_step, base_module.py:292-296 */
+
+    /* MicrogridStep.output -> shaped_reward, microgrid/utils/step.py:38-46 */
+    if (g->reward_shaper == ORC_SHAPER_PV_CURTAILMENT)          /* reward_shaping/pv_curtailment_shaper.py:16-18 */
+        reward = -1.0 * inf[ORC_INFO_CURTAILMENT];
+    else if (g->reward_shaper == ORC_SHAPER_BATTERY_DISCHARGE) { /* reward_shaping/battery_discharge_shaper.py:23-35 */
+        /* the reference calls the shaper twice: in balance() before the flex modules (microgrid.py:277; no
+           unbalanced_energy entry yet -> loss load 0.0) and for the output; both run the assert at :33 */
+        double mid = (inf[ORC_INFO_BATTERY_DISCHARGE] - 0.0) / inf[ORC_INFO_LOAD_MET];
+        reward = (inf[ORC_INFO_BATTERY_DISCHARGE] - inf[ORC_INFO_LOSS_LOAD]) / inf[ORC_INFO_LOAD_MET];
+        if (!shaper_in_range(mid) || !shaper_in_range(reward)) err |= ORC_ERR_SHAPER_RANGE;
+    }
 
     if (obs) orc_observe(g, order, obs);
     if (reward_out) *reward_out = reward;

@@ -48,6 +48,7 @@ enum {
     ORC_ERR_BATTERY_MIN_CAP   = 1u << 3,   /* battery_module.py:128 assert isclose                       */
     ORC_ERR_NEGATIVE_ABSORB   = 1u << 4,   /* base_module.py:272 assert absorbed_energy >= 0             */
     ORC_ERR_STEP_PAST_END     = 1u << 5,   /* IndexError on ts[t] when t >= len                          */
+    ORC_ERR_SHAPER_RANGE      = 1u << 7,   /* reward_shaping/battery_discharge_shaper.py:33 assert       */
     ORC_CLIP_GENSET           = 1u << 8,   /* raise_errors=True would raise ValueError here              */
     ORC_CLIP_BATTERY          = 1u << 9,   /*   (base_module.py:213-221, 265-268)                        */
     ORC_CLIP_GRID             = 1u << 10,
@@ -57,6 +58,7 @@ enum {
 };
 
 enum { ORC_ORDER_GYM_SORTED = 0, ORC_ORDER_CONTAINER = 1 };
+enum { ORC_SHAPER_NONE = 0, ORC_SHAPER_PV_CURTAILMENT = 1, ORC_SHAPER_BATTERY_DISCHARGE = 2 };
 
 typedef struct OrcGrid {
     /* architecture */
@@ -68,7 +70,8 @@ typedef struct OrcGrid {
     double min_capacity, max_capacity, max_charge, max_discharge, efficiency, battery_cost_cycle;
     /* genset_module.py:61-92 */
     double running_min_production, running_max_production, genset_cost, co2_per_unit, gen_cost_per_unit_co2;
-    int32_t start_up_time, wind_down_time, allow_abortion, _pad0;
+    int32_t start_up_time, wind_down_time, allow_abortion;
+    int32_t reward_shaper;        /* ORC_SHAPER_*: Microgrid(reward_shaping_func=...), microgrid/utils/step.py:41-46 */
     /* grid_module.py:70-101 */
     double max_import, max_export, grid_cost_per_unit_co2;
     /* unbalanced_energy_module.py:14-26 */

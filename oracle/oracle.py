@@ -27,7 +27,7 @@ class OrcGrid(C.Structure):
         ("max_discharge", C.c_double), ("efficiency", C.c_double), ("battery_cost_cycle", C.c_double),
         ("running_min_production", C.c_double), ("running_max_production", C.c_double), ("genset_cost", C.c_double),
         ("co2_per_unit", C.c_double), ("gen_cost_per_unit_co2", C.c_double),
-        ("start_up_time", C.c_int32), ("wind_down_time", C.c_int32), ("allow_abortion", C.c_int32), ("_pad0", C.c_int32),
+        ("start_up_time", C.c_int32), ("wind_down_time", C.c_int32), ("allow_abortion", C.c_int32), ("reward_shaper", C.c_int32),
         ("max_import", C.c_double), ("max_export", C.c_double), ("grid_cost_per_unit_co2", C.c_double),
         ("loss_load_cost", C.c_double), ("overgeneration_cost", C.c_double),
         ("load_ts", C.POINTER(C.c_double)), ("pv_ts", C.POINTER(C.c_double)), ("grid_ts", C.POINTER(C.c_double)),
@@ -112,6 +112,7 @@ def fill_struct(g, p, keep):
         g.max_import, g.max_export, g.grid_cost_per_unit_co2 = p.grid.max_import, p.grid.max_export, p.grid.cost_per_unit_co2
         g.grid_ts = _dp(ts)
     g.loss_load_cost, g.overgeneration_cost = p.loss_load_cost, p.overgeneration_cost
+    g.reward_shaper = {None: 0, "pv_curtailment": 1, "battery_discharge": 2}[getattr(p, "reward_shaper", None)]
     g.load_ts, g.pv_ts = _dp(load), _dp(pv)
     g.t = int(p.current_step)
     g.prepared = 0

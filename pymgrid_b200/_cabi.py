@@ -18,13 +18,13 @@ MG_OPT_ROLLOUT_SPECIALISED = 1
 
 FLAG_NAMES = {
     1 << 0: "GENSET_GOAL_RANGE", 1 << 1: "GENSET_AS_SINK", 1 << 2: "BALANCE", 1 << 3: "BATTERY_MIN_CAP",
-    1 << 4: "NEGATIVE_ABSORB", 1 << 5: "STEP_PAST_END", 1 << 6: "BAD_ACTION",
+    1 << 4: "NEGATIVE_ABSORB", 1 << 5: "STEP_PAST_END", 1 << 6: "BAD_ACTION", 1 << 7: "SHAPER_RANGE",
     1 << 8: "CLIP_GENSET", 1 << 9: "CLIP_BATTERY", 1 << 10: "CLIP_GRID",
     1 << 12: "BATTERY_SINK", 1 << 13: "GRID_SINK", 1 << 14: "EXCESS",
 }
 FLAG_BATTERY_SINK, FLAG_GRID_SINK, FLAG_EXCESS = 1 << 12, 1 << 13, 1 << 14
 FLAG_CLIP_MASK = 0x700
-FLAG_ERROR_MASK = 0x7f      # the reference raises at these; the CLIP_* bits only raise under raise_errors=True
+FLAG_ERROR_MASK = 0xff      # the reference raises at these; the CLIP_* bits only raise under raise_errors=True
 
 INFO_NAMES = ("load_met", "pv_used", "curtailment", "loss_load", "overgeneration", "genset_production",
               "genset_co2", "battery_discharge", "battery_charge", "grid_import", "grid_export", "grid_co2",
@@ -43,7 +43,7 @@ class MgConfig(C.Structure):
         "loss_load_cost", "overgeneration_cost",
         "load_scale", "pv_scale", "load_low", "load_spread", "pv_low", "pv_spread", "load_fill_nrm", "pv_fill_nrm")] + [(n, _i32) for n in (
         "gen_start_up_time", "gen_wind_down_time", "gen_allow_abortion", "load_series", "pv_series", "grid_series",
-        "initial_step", "final_step", "plist_offset", "plist_count", "series_scaled", "grid_status_weak")] + [("reserved", _i32 * 4)]
+        "initial_step", "final_step", "plist_offset", "plist_count", "series_scaled", "grid_status_weak", "reward_shaper")] + [("reserved", _i32 * 3)]
 
 
 class MgPriorityList(C.Structure):
@@ -76,6 +76,11 @@ class MgStepIO(C.Structure):
 class MgRolloutIO(C.Structure):
     _fields_ = [("actions", _vp), ("dactions", _vp), ("obs_ring", _vp), ("reward", _vp), ("done", _vp),
                 ("reward_sum", _vp), ("flags", _vp), ("dactions_const", C.c_int64), ("reward_total", _vp)]
+
+
+class MgForecastNoise(C.Structure):
+    _fields_ = [("load_sigma", _d), ("pv_sigma", _d), ("grid_sigma", _d * 4),
+                ("load_increase", _i32), ("pv_increase", _i32), ("grid_increase", _i32), ("_pad", _i32)]
 
 
 class EngineError(RuntimeError):
@@ -112,11 +117,12 @@ def lib():
     L.mg_rollout.argtypes = [_vp, C.POINTER(MgRolloutIO), _i32, _i32, C.c_int, _vp]
     L.mg_rollout_discrete.argtypes = [_vp, C.POINTER(MgRolloutIO), _i32, _i32, _vp]
     L.mg_set_option.argtypes = [_vp, C.c_int, C.c_int]
+    L.mg_forecast_noise.argtypes = [_vp, _vp, C.POINTER(_vp), C.POINTER(C.c_int64), C.c_uint64, C.c_uint64, _vp]
     L.mg_launch_count.argtypes = [_vp]
     L.mg_launch_count.restype = C.c_int64
     if L.mg_abi_version() != MG_ABI_VERSION:
         raise EngineError(f"ABI mismatch: library {L.mg_abi_version()} vs binding {MG_ABI_VERSION}")
-    for which, struct in enumerate((MgConfig, MgPriorityList, MgGroup, MgLayout, MgStepIO, MgRolloutIO)):
+    for which, struct in enumerate((MgConfig, MgPriorityList, MgGroup, MgLayout, MgStepIO, MgRolloutIO, MgForecastNoise)):
         if L.mg_sizeof(which) != C.sizeof(struct):
             raise EngineError(f"struct {struct.__name__}: library sizeof {L.mg_sizeof(which)} != binding {C.sizeof(struct)}")
     _lib = L
@@ -125,7 +131,7 @@ def lib():
 
 EXPORTED_SYMBOLS = ("mg_abi_version", "mg_sizeof", "mg_build_info", "mg_last_error", "mg_create", "mg_destroy",
                     "mg_step", "mg_step_discrete", "mg_reset", "mg_observe", "mg_rollout", "mg_rollout_discrete",
-                    "mg_launch_count", "mg_set_option")
+                    "mg_launch_count", "mg_set_option", "mg_forecast_noise")
 
 
 def check(code, what):

@@ -244,6 +244,10 @@ __device__ __forceinline__ void priority_control(const MgPriorityList pl, const 
 // One Microgrid.run for one env (microgrid.py:227-325; modules as cited inline).  Dispatch order
 // load -> genset -> battery -> grid -> (balance) -> pv -> unbalanced_energy; reward and energy sums accumulate in
 // exactly that order from 0.0 like MicrogridStep (microgrid/utils/step.py:9-36).
+__device__ __forceinline__ bool shaper_in_range(double v) {
+    return (-1 <= v && v <= 1) || np_isclose(v, 1.0, 1e-5, 1e-8) || np_isclose(v, 0.0, 1e-5, 1e-8);
+}
+
 __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const DevGroup &G, EnvRegs &s, const RawRow &raw,
                                          double a_goal, double a_gen, double a_bat, double a_grid, bool normalized,
                                          int final_step, double &reward_out, int &done_out, uint32_t &flags_out,
@@ -361,6 +365,16 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
     }
     if (!np_isclose(provided, consumed, 1e-5, 1e-8)) flags |= MG_FLAG_BALANCE;
     s.t += 1;
+    // MicrogridStep.shaped_reward, microgrid/utils/step.py:41-46: a built-in shaper replaces the reward
+    const int shaper = c->reward_shaper;
+    if (shaper == MG_SHAPER_PV_CURTAILMENT) reward = -1.0 * (raw.pv - pv_used);
+    else if (shaper == MG_SHAPER_BATTERY_DISCHARGE) {
+        // evaluated twice by the reference: in the mid-step balance() before the flex modules (microgrid.py:277, no loss
+        // load yet) and at the end; either assert raises (battery_discharge_shaper.py:33)
+        const double mid = (i_dis - 0.0) / load;
+        reward = (i_dis - loss) / load;
+        if (!shaper_in_range(mid) || !shaper_in_range(reward)) flags |= MG_FLAG_SHAPER_RANGE;
+    }
     reward_out = reward;
     done_out = done;
     flags_out = flags;
@@ -1114,6 +1128,88 @@ __global__ void __launch_bounds__(256) mg_build_tables_kernel(const TableParams 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// GaussianNoiseForecaster as a post-pass over freshly written observation rows (include/pymgrid_b200.h, mg_forecast_noise)
+// reference: forecast/forecaster.py:220-262 (noise), :120-149 (pad rows carry no noise, clip to the bounds)
+// One warp per env row; lane l draws for element pairs l, l + 32, ... of the row's forecast entries.
+// ------------------------------------------------------------------------------------------------------------------
+struct NoiseGroup {
+    int32_t n_envs, obs_dim, horizon, has_grid, load_start, pv_start, grid_start, first_block;
+    int64_t env_base;
+    const int32_t *step, *cfg_index;
+    void *obs;
+};
+struct NoiseParams {
+    int32_t n_groups, T;
+    uint32_t k0, k1, c3, _pad;
+    const MgForecastNoise *noise;
+    NoiseGroup g[MG_MAX_GROUPS];
+};
+
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11), counter c, key (k0, k1)
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        c[0] = hi1 ^ c[1] ^ k0;
+        c[1] = lo1;
+        c[2] = hi0 ^ c[3] ^ k1;
+        c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(128) mg_forecast_noise_kernel(const __grid_constant__ NoiseParams P) {
+    int gi = 0;
+#pragma unroll
+    for (int q = 1; q < MG_MAX_GROUPS; ++q)
+        if (q < P.n_groups && (int)blockIdx.x >= P.g[q].first_block) gi = q;
+    const NoiseGroup &G = P.g[gi];
+    const int e = ((int)blockIdx.x - G.first_block) * 4 + (int)(threadIdx.x >> 5);
+    if (e >= G.n_envs) return;
+    const int lane = threadIdx.x & 31;
+    const int t = G.step[e];                  // the step the row observes (post-step state)
+    const int H = G.horizon;
+    int n_real = P.T - (t + 1);               // forecast rows that exist in the series: t + 1 + k < T
+    n_real = n_real < 0 ? 0 : (n_real > H ? H : n_real);
+    if (n_real == 0) return;                  // past the end everything is padding (base_timeseries_module.py:113-116)
+    const MgForecastNoise *__restrict__ nz = P.noise + G.cfg_index[e];
+    TO *__restrict__ row = reinterpret_cast<TO *>(G.obs) + (size_t)e * G.obs_dim;
+    const int n_fc = H * (2 + 4 * G.has_grid);
+    const uint64_t env = (uint64_t)(G.env_base + e);
+    for (int p = lane; 2 * p < n_fc; p += 32) {
+        uint32_t c[4] = {(uint32_t)env, ((uint32_t)(env >> 32) & 0xffffu) | ((uint32_t)p << 16), (uint32_t)t, P.c3};
+        philox4x32_10(c, P.k0, P.k1);
+        // two 53-bit uniforms, u1 in (0, 1], u2 in [0, 1); Box-Muller
+        const double u1 = ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6) + 1.0) * (1.0 / 9007199254740992.0);
+        const double u2 = ((double)(c[2] >> 5) * 67108864.0 + (double)(c[3] >> 6)) * (1.0 / 9007199254740992.0);
+        const double radius = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int f = 2 * p + h;
+            if (f >= n_fc) break;
+            int k, off, inc;
+            double sigma;
+            if (f < H) { k = f; off = G.load_start + 1 + k; sigma = nz->load_sigma; inc = nz->load_increase; }
+            else if (f < 2 * H) { k = f - H; off = G.pv_start + 1 + k; sigma = nz->pv_sigma; inc = nz->pv_increase; }
+            else {
+                const int q = f - 2 * H;
+                k = q >> 2; off = G.grid_start + 4 + q; sigma = nz->grid_sigma[q & 3]; inc = nz->grid_increase;
+            }
+            if (k >= n_real || sigma == 0.0) continue;
+            if (inc) sigma = sigma * (1.0 + log(1.0 + (double)k));      // forecaster.py:244-248
+            double v = (double)row[off] + (radius * (h ? sn : cs)) * sigma;
+            v = fmin(fmax(v, 0.0), 1.0);                                // the clip to [low, high] in normalised units
+            row[off] = (TO)v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // host side: the C-ABI
 // ------------------------------------------------------------------------------------------------------------------
 struct MgHandle {
@@ -1151,6 +1247,7 @@ extern "C" int64_t mg_sizeof(int which) {
         case 3: return sizeof(MgLayout);
         case 4: return sizeof(MgStepIO);
         case 5: return sizeof(MgRolloutIO);
+        case 6: return sizeof(MgForecastNoise);
         default: return -1;
     }
 }
@@ -1275,6 +1372,47 @@ extern "C" int mg_destroy(MgHandle *h) {
 }
 
 extern "C" int64_t mg_launch_count(const MgHandle *h) { return h ? h->launches : 0; }
+
+extern "C" int mg_forecast_noise(MgHandle *h, const MgForecastNoise *noise, void *const *obs, const int64_t *env_base,
+                                 uint64_t seed, uint64_t call, void *stream) {
+    if (!h || !noise || !obs) return fail(MG_E_INVALID, "mg_forecast_noise: null argument");
+    NoiseParams P;
+    memset(&P, 0, sizeof P);
+    P.n_groups = h->base.n_groups;
+    P.T = h->base.T;
+    P.k0 = (uint32_t)seed;
+    P.k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(call >> 32);
+    P.c3 = (uint32_t)call;
+    P.noise = noise;
+    int blocks = 0;
+    int64_t base = 0;
+    for (int g = 0; g < P.n_groups; ++g) {
+        const DevGroup &d = h->base.g[g];
+        NoiseGroup &n = P.g[g];
+        n.n_envs = obs[g] ? d.n_envs : 0;
+        n.obs_dim = d.obs_dim; n.horizon = d.horizon; n.has_grid = d.has_grid;
+        if (d.horizon * (2 + 4 * d.has_grid) > 2 * 65535) return fail(MG_E_UNSUPPORTED, "mg_forecast_noise: horizon too long");
+        for (int q = 0; q < d.n_seg; ++q) {
+            if (d.seg_kind[q] == KIND_LOAD) n.load_start = d.seg_start[q];
+            else if (d.seg_kind[q] == KIND_PV) n.pv_start = d.seg_start[q];
+            else if (d.seg_kind[q] == KIND_GRID) n.grid_start = d.seg_start[q];
+        }
+        n.first_block = blocks;
+        n.env_base = env_base ? env_base[g] : base;
+        n.step = d.step; n.cfg_index = d.cfg_index; n.obs = obs[g];
+        blocks += (n.n_envs + 3) / 4;
+        base += d.n_envs;
+    }
+    if (blocks == 0) return MG_OK;
+    if (h->obs_f32) mg_forecast_noise_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>(P);
+    else mg_forecast_noise_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "mg_forecast_noise: launch");
+    h->launches += 1;
+    h->last_was_step = false;
+    return MG_OK;
+}
+
 
 extern "C" int mg_set_option(MgHandle *h, int option, int value) {
     if (!h) return fail(MG_E_INVALID, "mg_set_option: null handle");

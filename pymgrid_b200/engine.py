@@ -17,9 +17,9 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import (MG_ABI_VERSION, MG_MAX_GROUPS, MG_N_INFO, MG_OBS_CONTAINER, MG_OBS_GYM_SORTED, EngineError,
+from ._cabi import (MgForecastNoise, MG_ABI_VERSION, MG_MAX_GROUPS, MG_N_INFO, MG_OBS_CONTAINER, MG_OBS_GYM_SORTED, EngineError,
                     MgConfig, MgLayout, MgPriorityList, MgRolloutIO, MgStepIO)
-from .params import MicrogridParams
+from .params import REWARD_SHAPERS, MicrogridParams
 from .priority_list import priority_lists
 
 OBS_ORDERS = {"gym_sorted": MG_OBS_GYM_SORTED, "container": MG_OBS_CONTAINER,
@@ -77,6 +77,7 @@ def config_record(p: MicrogridParams, load_series, pv_series, grid_series, plist
     else:
         c.grid_act_spread = 1.0
     c.loss_load_cost, c.overgeneration_cost = p.loss_load_cost, p.overgeneration_cost
+    c.reward_shaper = REWARD_SHAPERS[p.reward_shaper]
     c.load_scale, c.pv_scale = p.load_scale, p.pv_scale
     if p.scaled:
         c.series_scaled = 1
@@ -91,6 +92,40 @@ def config_record(p: MicrogridParams, load_series, pv_series, grid_series, plist
     c.initial_step, c.final_step = p.initial_step, p.final_step
     c.plist_offset, c.plist_count = plist_offset, plist_count
     return c
+
+
+def forecast_noise_record(p: MicrogridParams):
+    """MgForecastNoise of one config: the reference's per-module noise standard deviation (GaussianNoiseForecaster.
+    _get_noise_std, forecast/forecaster.py:237-250; series window of set_forecaster, base_timeseries_module.py:233-240)
+    divided by the column's observation spread, 0 for constant columns (the forecaster's clip pins them)."""
+    rec = MgForecastNoise()
+    stop = p.final_step if p.final_step > 0 else len(p)
+
+    def sigmas(name, ts, pull_zero):
+        f = p.forecasters.get(name)
+        ts = ts.reshape(len(ts), -1)
+        if f is None or f.noise_std == 0:
+            return [0.0] * ts.shape[1], 0
+        std = float(f.noise_std)
+        if f.relative_noise:
+            std = std * float(np.abs(ts[p.initial_step:stop].mean()))
+        out = []
+        for c in range(ts.shape[1]):
+            low, high = float(ts[:, c].min()), float(ts[:, c].max())
+            if pull_zero:
+                low, high = min(low, 0.0), max(high, 0.0)
+            out.append(std / (high - low) if high > low else 0.0)
+        return out, int(bool(f.increase_uncertainty))
+
+    (rec.load_sigma,), rec.load_increase = sigmas("load", p.load_ts * p.load_scale, True)
+    (rec.pv_sigma,), rec.pv_increase = sigmas("pv", p.pv_ts * p.pv_scale, True)
+    if p.grid is not None:
+        g, rec.grid_increase = sigmas("grid", p.grid.effective_time_series(), False)
+        for c in range(4):
+            rec.grid_sigma[c] = g[c]
+    elif "grid" in p.forecasters:
+        raise ValueError("forecasters: this microgrid has no grid module")
+    return rec
 
 
 @dataclass
@@ -320,6 +355,8 @@ class BatchedMicrogrid:
                                          for p in self.configs], dtype=np.int64).astype(np.int32),
                     load_np=load_np, pv_np=pv_np, grid_np=grid_np, cfg_status=status, device=device, obs_order=obs_order,
                     with_info=with_info, with_flags=with_flags, action_order=action_order, obs_dtype=obs_dtype)
+        if any(f.noise_std != 0 for p in self.configs for f in p.forecasters.values()):
+            self.set_forecast_noise(seed=0)
 
     def _setup(self, cfg_np, plist_np, action_tables, env_config, cfg_arch, cfg_step, cfg_charge, cfg_genset, load_np,
                pv_np, grid_np, cfg_status, device, obs_order, with_info, with_flags, action_order,
@@ -330,6 +367,8 @@ class BatchedMicrogrid:
         if not torch.cuda.is_available():
             raise EngineError("BatchedMicrogrid needs a CUDA device: there is no CPU path")
         self._lib = _cabi.lib()
+        self._noise = None              # forecast noise: (device records, seed, env id offset) once set_forecast_noise ran
+        self._noise_calls = 0
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.obs_order = obs_order
         if obs_dtype not in (torch.float64, torch.float32):
@@ -465,6 +504,37 @@ class BatchedMicrogrid:
         ragged = any(g.env_initial_step is not None for g in self.groups)
         self.set_rollout_specialised(not ragged)
 
+    def set_forecast_noise(self, seed=0, env_offset=0, records=None):
+        """Turn on the Gaussian-noise forecasters of the configs (`MicrogridParams.forecasters`; reference:
+        GaussianNoiseForecaster, forecast/forecaster.py:220-262): after every step / reset / observe the forecast
+        entries of the freshly written observation rows get N(0, std_k) added and are clipped to their bounds
+        (`mg_forecast_noise`).  The draw is a pure function of (seed, call number, env, the env's step, element);
+        `env_offset` shifts the env ids so that shards of one batch on different GPUs draw differently.
+        `records`: optional explicit list of MgForecastNoise, one per config (array-form front ends).
+        `mg_rollout` keeps the oracle forecast: its observation ring is written inside the persistent kernel."""
+        if records is None:
+            records = [forecast_noise_record(p) for p in self.configs]
+        raw = np.frombuffer(bytes((MgForecastNoise * len(records))(*records)), dtype=np.uint8).copy()
+        dev_records = torch.from_numpy(raw).to(self.device)
+        base, bases = int(env_offset), []
+        for g in self.groups:
+            bases.append(base)
+            base += g.n_envs
+        self._noise = (dev_records, int(seed) & (2 ** 64 - 1), (C.c_int64 * len(bases))(*bases))
+
+    def clear_forecast_noise(self):
+        self._noise = None
+
+    def _apply_noise(self, obs_bufs):
+        """enqueue mg_forecast_noise on the observation buffers a step / reset / observe call has just written"""
+        if self._noise is None or all(o is None for o in obs_bufs):
+            return
+        records, seed, bases = self._noise
+        ptrs = (C.c_void_p * len(obs_bufs))(*[_ptr(o) for o in obs_bufs])
+        self._noise_calls += 1
+        _cabi.check(self._lib.mg_forecast_noise(self._handle, records.data_ptr(), ptrs, bases, seed, self._noise_calls,
+                                                self._stream()), "mg_forecast_noise")
+
     def set_rollout_specialised(self, on):
         """Owner / emitter warp-specialised persistent kernel for `rollout` (default: on unless per-env trajectory windows
         are installed).  Best when the envs of a tile are at the same step; turn it off for batches whose envs were
@@ -540,16 +610,21 @@ class BatchedMicrogrid:
         io, obs_bufs = self._io(dactions=actions, obs=obs) if discrete else self._io(actions=actions, obs=obs)
         lib, handle, norm = self._lib, self._handle, int(bool(normalized))
         stream_of, dev = torch.cuda.current_stream, self.device
+        noise = self._apply_noise if self._noise is not None else None   # (a captured graph replays one call number)
         if discrete:
             def launch():
                 rc = lib.mg_step_discrete(handle, io, stream_of(dev).cuda_stream)
                 if rc:
                     _cabi.check(rc, "mg_step_discrete")
+                if noise:
+                    noise(obs_bufs)
         else:
             def launch():
                 rc = lib.mg_step(handle, io, norm, stream_of(dev).cuda_stream)
                 if rc:
                     _cabi.check(rc, "mg_step")
+                if noise:
+                    noise(obs_bufs)
         launch.keepalive = (io, obs_bufs, actions)
         return launch
 
@@ -559,23 +634,27 @@ class BatchedMicrogrid:
         reward_total: optional f64 [1] device tensor that the kernel adds the batch's summed reward to (logging)."""
         io, obs_bufs = self._io(actions=actions, obs=obs, reward_total=reward_total)
         _cabi.check(self._lib.mg_step(self._handle, io, int(bool(normalized)), self._stream()), "mg_step")
+        self._apply_noise(obs_bufs)
         return self._result(obs_bufs)
 
     def step_discrete(self, actions, obs=True):
         """DiscreteMicrogridEnv.step for every env (reference envs/discrete/discrete.py:109-143)."""
         io, obs_bufs = self._io(dactions=actions, obs=obs)
         _cabi.check(self._lib.mg_step_discrete(self._handle, io, self._stream()), "mg_step_discrete")
+        self._apply_noise(obs_bufs)
         return self._result(obs_bufs)
 
     def reset(self, mask=None, obs=True):
         """Microgrid.reset (reference microgrid.py:205-225): step = initial_step; battery / genset state is kept."""
         io, obs_bufs = self._io(obs=obs, mask=mask)
         _cabi.check(self._lib.mg_reset(self._handle, io, self._stream()), "mg_reset")
+        self._apply_noise(obs_bufs)
         return obs_bufs[0] if self.single_group else obs_bufs
 
     def observe(self, obs=True):
         io, obs_bufs = self._io(obs=obs)
         _cabi.check(self._lib.mg_observe(self._handle, io, self._stream()), "mg_observe")
+        self._apply_noise(obs_bufs)
         return obs_bufs[0] if self.single_group else obs_bufs
 
     def rbc_actions(self):

@@ -134,9 +134,16 @@ class ModuleContainerView(OrderedDict):
 
 
 class Microgrid:
-    def __init__(self, params: MicrogridParams, device=None, obs_order="gym_sorted"):
+    def __init__(self, params: MicrogridParams, device=None, obs_order="gym_sorted", reward_shaping_func=None):
+        """`reward_shaping_func` (reference: Microgrid.__init__, microgrid.py:100-106): None, "pv_curtailment" /
+        "battery_discharge", or an object of the reference's PVCurtailmentShaper / BatteryDischargeShaper classes (matched
+        by class name); arbitrary Python callables cannot run inside the kernel and are rejected."""
         if not isinstance(params, MicrogridParams):
             raise TypeError("pymgrid_b200.Microgrid is built from MicrogridParams (see scenario.load_pymgrid25 / params.py)")
+        if reward_shaping_func is not None:
+            import dataclasses
+            name = reward_shaping_func if isinstance(reward_shaping_func, str) else type(reward_shaping_func).__name__
+            params = dataclasses.replace(params, reward_shaper=name)
         self.params = params
         self._obs_order = obs_order
         self._engine = BatchedMicrogrid([params], np.zeros(1, dtype=np.int64), device=device, obs_order=obs_order,

@@ -87,6 +87,20 @@ class GridParams:
 
 
 @dataclass
+class ForecasterParams:
+    """Gaussian-noise forecaster of one time-series module: what the reference builds when a module's `forecaster`
+    argument is a number (forecast/forecaster.py:10-89 get_forecaster, :220-250 GaussianNoiseForecaster)."""
+    noise_std: float = 0.0                 # 0 = oracle forecaster (perfect forecast)
+    increase_uncertainty: bool = False     # std_k = std * (1 + log(1 + k)) for forecast row k
+    relative_noise: bool = False           # std *= |mean(time_series[initial_step:final_step])|
+
+
+REWARD_SHAPERS = {None: 0, "pv_curtailment": 1, "battery_discharge": 2}     # MG_SHAPER_* / ORC_SHAPER_*
+REWARD_SHAPER_ALIASES = {"PVCurtailmentShaper": "pv_curtailment", "!PVCurtailmentShaper": "pv_curtailment",
+                         "BatteryDischargeShaper": "battery_discharge", "!BatteryDischargeShaper": "battery_discharge"}
+
+
+@dataclass
 class MicrogridParams:
     battery: BatteryParams
     load_ts: np.ndarray             # [T] float64, stored NEGATIVE like the reference (base_timeseries_module.py:68-79)
@@ -106,10 +120,27 @@ class MicrogridParams:
     load_scale: float = 1.0
     pv_scale: float = 1.0
     renewable_name: str = "pv"      # 'PV' for MicrogridGenerator grids: decides the gym-sorted observation order
+    # Microgrid(reward_shaping_func=...): None, "pv_curtailment" (PVCurtailmentShaper) or "battery_discharge"
+    # (BatteryDischargeShaper), microgrid/reward_shaping/*.py; the shaped value replaces the step reward (utils/step.py:38-46)
+    reward_shaper: Optional[str] = None
+    # per-module forecasters, keys among 'load', 'pv', 'grid'; a missing key is the oracle forecaster (pymgrid25's setting).
+    # Noise only changes the forecast entries of the observation, never the physics (forecast/forecaster.py).
+    forecasters: dict = field(default_factory=dict)
 
     def __post_init__(self):
         if not (self.load_scale > 0 and self.pv_scale > 0):
             raise ValueError("series scales must be positive")
+        bad = set(self.forecasters) - {"load", "pv", "grid"}
+        if bad:
+            raise ValueError(f"forecasters: unknown module(s) {sorted(bad)}; time-series modules are load, pv, grid")
+        self.forecasters = {k: (v if isinstance(v, ForecasterParams) else ForecasterParams(float(v)))
+                            for k, v in self.forecasters.items()}
+        self.reward_shaper = REWARD_SHAPER_ALIASES.get(self.reward_shaper, self.reward_shaper)
+        if self.reward_shaper not in REWARD_SHAPERS:
+            raise ValueError(f"unknown reward shaper {self.reward_shaper!r}; built in: {sorted(k for k in REWARD_SHAPERS if k)}")
+        if self.reward_shaper == "pv_curtailment" and self.renewable_name != "pv":
+            # sum_module_val(info, 'pv', ...) finds no such module and returns 0.0 (reward_shaping/base.py:11-16)
+            raise ValueError("PVCurtailmentShaper reads the module named 'pv'; this grid names it " + repr(self.renewable_name))
         self.load_ts = -np.abs(np.ascontiguousarray(self.load_ts, dtype=np.float64).reshape(-1))
         self.pv_ts = np.abs(np.ascontiguousarray(self.pv_ts, dtype=np.float64).reshape(-1))
         if self.grid is not None:

@@ -182,7 +182,14 @@ def log_row(p, pre_state, info, reward, genset_after=None):
     ctrl_absorbed = consumed - fixed_absorbed
     overall_provided = provided + float(info[1]) + float(info[3])
     overall_absorbed = consumed + float(info[4])
-    row[("balance", 0, "reward")] = reward
+    # with a reward shaper, `reward` (what run() returned) is the shaped value and the balance log keeps the plain sum of
+    # the module rewards beside it, added in dispatch order (utils/step.py:18, microgrid.py:316-319)
+    unshaped = reward
+    if getattr(p, "reward_shaper", None) is not None:
+        unshaped = 0.0
+        for col in ([12] if p.has_genset else []) + [13] + ([14] if p.has_grid else []) + [15]:
+            unshaped += float(info[col])
+    row[("balance", 0, "reward")] = unshaped
     row[("balance", 0, "shaped_reward")] = reward
     row[("balance", 0, "overall_provided_to_microgrid")] = overall_provided
     row[("balance", 0, "overall_absorbed_from_microgrid")] = overall_absorbed

@@ -12,6 +12,9 @@ to the reference's actual outputs:
                         (BASELINE config 4): action tables, expanded controls, rewards, flat observations
   genset_machine.npz    exhaustive genset status transitions, U, D in 0..4, both abortion settings
   custom.npz            small hand-built microgrids: slow gensets, weak grid, short series, no forecaster
+  shaped.npz            the two built-in reward shapers (microgrid/reward_shaping/) on the three architectures
+  noisy_forecast.npz    GaussianNoiseForecaster (forecast/forecaster.py:220-275) under the legacy numpy seed: flat
+                        observations after reset and after each step, at the start and across the end of the series
 """
 import itertools
 import os
@@ -419,8 +422,107 @@ def make_generator():
     np.savez_compressed(os.path.join(HERE, "generator.npz"), **out)
 
 
+def make_shaped():
+    """Microgrid(reward_shaping_func=...): run returns the shaped reward, the balance log keeps both (microgrid.py:316-319).
+
+    BatteryDischargeShaper asserts its value is in [-1, 1] (battery_discharge_shaper.py:33) and the reference evaluates
+    the shaper twice per step: once in the mid-step balance() before the flex modules (microgrid.py:277, loss load not
+    yet known) and once at the end.  A failed assert leaves the microgrid half stepped, so each segment stops at the
+    first one; `raised` marks it."""
+    from pymgrid.microgrid.reward_shaping import BatteryDischargeShaper, PVCurtailmentShaper
+    out = {}
+    n_seg, seg_len = 6, 40
+    for n in (0, 1, 2, 13):
+        for tag, shaper in (("pv", PVCurtailmentShaper), ("bat", BatteryDischargeShaper)):
+            rng = np.random.default_rng(7000 + n)
+            for seg in range(n_seg):
+                m = Microgrid.from_scenario(n)
+                m.reward_shaping_func = shaper()
+                m.initial_step = int(rng.integers(0, 8000))
+                m.reset()
+                a = rng.random((seg_len, n_act(m)))
+                if tag == "bat" and seg % 2 == 0:      # keep the battery near idle so that long stretches pass the assert
+                    a[:, -2 if hasattr(m.modules, "grid") else -1] = rng.uniform(0.35, 0.55, seg_len)
+                r, s, raised = [], [], -1
+                for k, row in enumerate(a):
+                    try:
+                        r.append(m.run(control_from_flat(m, row))[1])
+                    except AssertionError:
+                        raised = k
+                        break
+                    s.append(state_vec(m))
+                log = m._balance_logger.to_dict()      # get_log cannot assemble a half-stepped microgrid
+                key = f"s{n}_{tag}_{seg}"
+                out[key + "_t0"], out[key + "_a"], out[key + "_r"] = np.array(m.initial_step), a, np.array(r)
+                out[key + "_s"], out[key + "_raised"] = np.array(s).reshape(len(s), 6), np.array(raised)
+                out[key + "_log_reward"] = np.array(log.get("reward", []), dtype=np.float64)
+                out[key + "_log_shaped"] = np.array(log.get("shaped_reward", []), dtype=np.float64)
+                print("shaped", n, tag, seg, len(r), raised, r[:2])
+    # priority-list dispatch keeps the battery within the load, so BatteryDischargeShaper runs for long stretches
+    for n in (0, 1, 2, 13):
+        rng = np.random.default_rng(7100 + n)
+        env = DiscreteMicrogridEnv.from_scenario(n)
+        env.reward_shaping_func = BatteryDischargeShaper()
+        env.initial_step = int(rng.integers(0, 8000))
+        env.reset()
+        acts = rng.integers(0, env.action_space.n, 150)
+        ctrls, r, s, raised = [], [], [], -1
+        for k, a in enumerate(acts):
+            ctrls.append(flat_control(env, env._get_action(int(a))))
+            try:
+                r.append(env.step(int(a))[1])
+            except AssertionError:
+                raised = k
+                break
+            s.append(state_vec(env))
+        log = env._balance_logger.to_dict()
+        key = f"s{n}_batd"
+        out[key + "_t0"], out[key + "_actions"], out[key + "_controls"] = np.array(env.initial_step), acts.astype(np.int32), np.stack(ctrls)
+        out[key + "_r"], out[key + "_s"], out[key + "_raised"] = np.array(r), np.array(s).reshape(len(s), 6), np.array(raised)
+        out[key + "_log_reward"] = np.array(log.get("reward", []), dtype=np.float64)
+        print("shaped discrete", n, len(r), raised, r[:4])
+    out["n_seg"] = np.array(n_seg)
+    np.savez_compressed(os.path.join(HERE, "shaped.npz"), **out)
+
+
+NOISE_CASES = (   # scenario, {module: (std, increase_uncertainty, relative_noise)}
+    (0, dict(load=(40.0, False, False), pv=(0.15, True, True), grid=(0.05, True, False))),
+    (2, dict(load=(0.1, True, True), pv=(25.0, False, False))),
+    (1, dict(load=(0.2, False, True), pv=(0.3, True, True), grid=(0.02, False, True))),
+)
+
+
+def make_noisy_forecast():
+    out = {}
+    for ci, (n, spec) in enumerate(NOISE_CASES):
+        for seg, t0 in enumerate((0, 8740)):
+            m = Microgrid.from_scenario(n)
+            m.initial_step = t0
+            for name, (std, inc, rel) in spec.items():
+                getattr(m.modules, name)[0].set_forecaster(std, forecast_horizon=23, forecaster_increase_uncertainty=inc,
+                                                           forecaster_relative_noise=rel)
+            rng = np.random.default_rng(8000 + n)
+            a = rng.random((19 if t0 else 12, n_act(m)))
+            np.random.seed(500 + ci)
+            reset_obs = flat_obs(m.reset())
+            obs, rewards = [], []
+            for row in a:
+                o, r, _, _ = m.run(control_from_flat(m, row))
+                obs.append(flat_obs(o)); rewards.append(r)
+            key = f"c{ci}_{seg}"
+            out[key + "_t0"], out[key + "_a"], out[key + "_reset_obs"] = np.array(t0), a, reset_obs
+            out[key + "_o"], out[key + "_r"] = np.stack(obs), np.array(rewards)
+            out[key + "_noise_std"] = np.array([np.mean(getattr(m.modules, name)[0].forecaster.noise_std) for name in spec])
+            print("noisy", n, t0, reset_obs[:3], out[key + "_noise_std"])
+    np.savez_compressed(os.path.join(HERE, "noisy_forecast.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["steps", "year", "discrete", "genset", "custom", "log", "rbc", "generator"]
+    which = sys.argv[1:] or ["noisy", "steps", "year", "discrete", "genset", "custom", "log", "rbc", "generator", "shaped"]
+    if "shaped" in which:
+        make_shaped()
+    if "noisy" in which:
+        make_noisy_forecast()
     if "generator" in which:
         make_generator()
     if "rbc" in which:

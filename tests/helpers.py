@@ -59,3 +59,57 @@ def generator_params(z, i):
     return MicrogridParams(battery=battery, genset=genset, grid=grid, load_ts=pr["load"][int(lp)], pv_ts=pr["pv"][int(pp)],
                            load_scale=float(lscale), pv_scale=float(pscale), loss_load_cost=llc, overgeneration_cost=ogc,
                            forecast_horizon=int(H), final_step=int(final_step), renewable_name="PV")
+
+
+# ---- numpy restatement of the engine's forecast-noise generator (include/pymgrid_b200.h, mg_forecast_noise) ----------
+def philox4x32_10(counter, key):
+    """counter [..., 4] uint32, key (k0, k1) -> [..., 4] uint32.  Philox4x32-10, Salmon et al. SC'11."""
+    c = np.array(counter, dtype=np.uint64) & 0xffffffff
+    k0, k1 = np.uint64(key[0] & 0xffffffff), np.uint64(key[1] & 0xffffffff)
+    M0, M1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xffffffff)
+    for _ in range(10):
+        p0, p1 = M0 * c[..., 0], M1 * c[..., 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = np.stack([hi1 ^ c[..., 1] ^ k0, lo1, hi0 ^ c[..., 3] ^ k1, lo0], axis=-1)
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return c.astype(np.uint32)
+
+
+def engine_noise_normals(env, t, n_pairs, seed, call):
+    """the standard normals the kernel draws for env id `env` at step `t`: [2 * n_pairs] (element f uses entry f)"""
+    p = np.arange(n_pairs, dtype=np.uint64)
+    ctr = np.stack([np.full(n_pairs, env & 0xffffffff, dtype=np.uint64), ((env >> 32) & 0xffff) | (p << np.uint64(16)),
+                    np.full(n_pairs, t & 0xffffffff, dtype=np.uint64), np.full(n_pairs, call & 0xffffffff, dtype=np.uint64)], axis=-1)
+    x = philox4x32_10(ctr, (seed & 0xffffffff, ((seed >> 32) ^ (call >> 32)) & 0xffffffff)).astype(np.float64)
+    x = x.astype(np.uint64)
+    u1 = ((x[:, 0] >> np.uint64(5)).astype(np.float64) * 67108864.0 + (x[:, 1] >> np.uint64(6)).astype(np.float64) + 1.0) / 9007199254740992.0
+    u2 = ((x[:, 2] >> np.uint64(5)).astype(np.float64) * 67108864.0 + (x[:, 3] >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
+    r = np.sqrt(-2.0 * np.log(u1))
+    return np.stack([r * np.cos(2 * np.pi * u2), r * np.sin(2 * np.pi * u2)], axis=-1).reshape(-1)
+
+
+def engine_noisy_row(clean, p, order, sigma, increase, env, t, seed, call, series_len):
+    """Expected observation row after mg_forecast_noise.  clean: the oracle-forecast row; sigma: dict name -> per-column
+    normalised std (list); increase: dict name -> bool."""
+    from pymgrid_b200 import views
+    H = p.forecast_horizon
+    n_fc = H * (2 + 4 * p.has_grid)
+    z = engine_noise_normals(env, t, (n_fc + 1) // 2, seed, call)
+    n_real = min(max(series_len - (t + 1), 0), H)
+    out = np.array(clean, dtype=np.float64)
+    sl = views.obs_slices(p, order)
+    for f in range(n_fc):
+        if f < H:
+            name, k, col, off = "load", f, 0, sl["load"].start + 1 + f
+        elif f < 2 * H:
+            name, k, col, off = "pv", f - H, 0, sl["pv"].start + 1 + (f - H)
+        else:
+            q = f - 2 * H
+            name, k, col, off = "grid", q // 4, q % 4, sl["grid"].start + 4 + q
+        s = sigma[name][col]
+        if k >= n_real or s == 0:
+            continue
+        if increase[name]:
+            s = s * (1.0 + np.log(1.0 + k))
+        out[off] = min(max(out[off] + z[f] * s, 0.0), 1.0)
+    return out

@@ -205,3 +205,32 @@ def test_host_io_graph_replay_equals_eager():
         assert torch.equal(ha.reward, c.reward.cpu()) and torch.equal(ha.done, c.done.cpu())
     for ga, gc in zip(a.groups, c.groups):
         assert torch.equal(ga.obs, gc.obs) and torch.equal(ga.charge, gc.charge)
+
+
+def test_reward_shaping_func_drop_in(golden):
+    """Microgrid(reward_shaping_func=...) like the reference (microgrid.py:100-124): run returns the shaped reward, the
+    balance log keeps reward and shaped_reward, and the shaper's assert surfaces as AssertionError on the same step."""
+    from pymgrid_b200.microgrid import Microgrid
+    from tests.helpers import jump_to
+    z = golden["shaped"]
+
+    class PVCurtailmentShaper:      # stands in for the reference's class: matched by name
+        pass
+
+    key = "s1_pv_0"
+    m = Microgrid(jump_to(load_pymgrid25(1), int(z[key + "_t0"])), reward_shaping_func=PVCurtailmentShaper())
+    for k, a in enumerate(z[key + "_a"]):
+        assert m.run(control(m.params, a))[1] == z[key + "_r"][k]
+    log = m.get_log()
+    np.testing.assert_array_equal(log[("balance", 0, "reward")].to_numpy(), z[key + "_log_reward"])
+    np.testing.assert_array_equal(log[("balance", 0, "shaped_reward")].to_numpy(), z[key + "_log_shaped"])
+
+    key = next(f"s2_bat_{s}" for s in range(int(z["n_seg"])) if int(z[f"s2_bat_{s}_raised"]) > 0)
+    m = Microgrid(jump_to(load_pymgrid25(2), int(z[key + "_t0"])), reward_shaping_func="battery_discharge")
+    raised = int(z[key + "_raised"])
+    for k in range(raised):
+        assert m.run(control(m.params, z[key + "_a"][k]))[1] == z[key + "_r"][k]
+    with pytest.raises(AssertionError):
+        m.run(control(m.params, z[key + "_a"][raised]))
+    with pytest.raises(ValueError):
+        Microgrid(load_pymgrid25(0), reward_shaping_func=lambda info, cost: 0.0)

@@ -534,3 +534,54 @@ def test_float32_observation_output_is_the_rounded_f64_observation():
         ob, _, _, _ = as_lists(gf.step(acts))
         for x, y in zip(oa, ob):
             assert torch.equal(x.to(torch.float32), y)
+
+
+def test_reward_shapers_golden_and_oracle(golden):
+    """Microgrid(reward_shaping_func=...): the shaped reward replaces the step reward (utils/step.py:38-46).
+    (1) the reference's recorded BatteryDischargeShaper runs under priority-list dispatch, bit for bit;
+    (2) a mixed batch (no shaper / PVCurtailmentShaper / BatteryDischargeShaper side by side in one launch) against the
+        oracle, including the flag that stands for the shaper's assert."""
+    from oracle.oracle import OracleGrid
+    z = golden["shaped"]
+    scen = (0, 1, 2, 13)
+    configs = []
+    for n in scen:
+        p = jump_to(load_pymgrid25(n), int(z[f"s{n}_batd_t0"]))
+        p.reward_shaper = "battery_discharge"
+        configs.append(p)
+    bm = engine(configs, np.arange(len(scen)))
+    for k in range(150):
+        acts = group_actions(bm, [z[f"s{n}_batd_controls"][k] for n in scen])
+        _, reward, _, info = as_lists(bm.step(acts, normalized=False))
+        r, inf = gather(bm, reward), gather(bm, info)
+        for e, n in enumerate(scen):
+            assert r[e] == z[f"s{n}_batd_r"][k], (n, k)
+            unshaped = 0.0
+            for col in (12, 13, 14, 15):
+                unshaped += inf[e][col]
+            assert unshaped == z[f"s{n}_batd_log_reward"][k]
+    assert all(((g.flags & (1 << 7)) == 0).all() for g in bm.groups)
+
+    rng = np.random.default_rng(77)
+    configs = []
+    for n in scen:
+        for shaper in (None, "pv_curtailment", "battery_discharge"):
+            p = jump_to(load_pymgrid25(n), int(rng.integers(0, 8000)))
+            p.reward_shaper = shaper
+            configs.append(p)
+    B, n_steps = 96, 25
+    env_config = np.arange(B) % len(configs)
+    bm = engine(configs, env_config)
+    oracles = [OracleGrid(configs[c]) for c in env_config]
+    n_flagged = 0
+    for k in range(n_steps):
+        a = [rng.random(o.n_act) for o in oracles]
+        _, reward, _, _ = as_lists(bm.step(group_actions(bm, a)))
+        r = gather(bm, reward)
+        flags = gather(bm, [g.flags for g in bm.groups])
+        for e, o in enumerate(oracles):
+            _, ro, _, _, err = o.run(a[e])
+            assert (r[e] == ro) or (np.isnan(r[e]) and np.isnan(ro)), (e, k)
+            assert (int(flags[e]) & 0xffff) == (err & 0xffff), (e, k)
+            n_flagged += bool(err & (1 << 7))
+    assert n_flagged > 20

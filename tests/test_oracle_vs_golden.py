@@ -159,3 +159,61 @@ def test_container_order_is_a_permutation_of_sorted_order():
     rows = 1 + p.forecast_horizon
     bat, gen, grid, load, pv = np.split(oa, np.cumsum([2, 4, 4 * rows, rows]))
     np.testing.assert_array_equal(ob, np.concatenate([load, pv, gen, bat, grid]))
+
+
+SHAPER_FLAG = 1 << 7
+
+
+def shaped_segments(z):
+    for n in (0, 1, 2, 13):
+        for tag, name in (("pv", "pv_curtailment"), ("bat", "battery_discharge")):
+            for seg in range(int(z["n_seg"])):
+                yield n, name, f"s{n}_{tag}_{seg}"
+
+
+def shaped_params(n, name, t0):
+    p = jump_to(load_pymgrid25(n), int(t0))
+    p.reward_shaper = name
+    return p
+
+
+def sequential_module_reward(info):
+    """the unshaped step reward the balance log keeps: module rewards added in dispatch order (utils/step.py:18)"""
+    r = 0.0
+    for col in (12, 13, 14, 15):
+        r += info[col]
+    return r
+
+
+def test_reward_shapers(golden):
+    """Microgrid(reward_shaping_func=PVCurtailmentShaper / BatteryDischargeShaper): shaped reward bit for bit, the
+    unshaped sum still available, and the shaper's assert (mid-step or final) reported as a flag on the same step."""
+    z = golden["shaped"]
+    n_rows = n_raised = 0
+    for n, name, key in shaped_segments(z):
+        o = OracleGrid(shaped_params(n, name, z[key + "_t0"]))
+        a, r, s, raised = z[key + "_a"], z[key + "_r"], z[key + "_s"], int(z[key + "_raised"])
+        for k in range(len(r)):
+            _, rew, _, info, err = o.run(a[k])
+            assert rew == r[k] and not err & SHAPER_FLAG, (key, k)
+            assert rew == z[key + "_log_shaped"][k] and sequential_module_reward(info) == z[key + "_log_reward"][k]
+            np.testing.assert_array_equal(state_from_oracle(o), s[k])
+        n_rows += len(r)
+        if raised >= 0:
+            assert raised == len(r)
+            assert o.run(a[raised])[4] & SHAPER_FLAG, (key, raised)
+            n_raised += 1
+    assert n_rows > 1000 and n_raised >= 10
+
+
+@pytest.mark.parametrize("n", (0, 1, 2, 13))
+def test_battery_discharge_shaper_under_priority_lists(golden, n):
+    z = golden["shaped"]
+    key = f"s{n}_batd"
+    o = OracleGrid(shaped_params(n, "battery_discharge", z[key + "_t0"]))
+    assert int(z[key + "_raised"]) == -1
+    for k, ctrl in enumerate(z[key + "_controls"]):
+        _, rew, _, info, err = o.run(ctrl, normalized=False)
+        assert rew == z[key + "_r"][k] and not err & SHAPER_FLAG, k
+        assert sequential_module_reward(info) == z[key + "_log_reward"][k]
+        np.testing.assert_array_equal(state_from_oracle(o), z[key + "_s"][k])
