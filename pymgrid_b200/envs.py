@@ -79,6 +79,34 @@ class _BaseEnv:
         """reference: BaseMicrogridEnv.from_scenario (envs/base/base.py:292-299)."""
         return cls(load_pymgrid25(microgrid_number), batch=batch, **kw)
 
+    @classmethod
+    def from_microgrid(cls, microgrid, batch=None, **kw):
+        """reference: BaseMicrogridEnv.from_microgrid (envs/base/base.py:270-290): an env over a copy of a (possibly
+        running) microgrid, state included.  Accepts a pymgrid_b200.Microgrid or a MicrogridParams."""
+        params = microgrid.export_params() if hasattr(microgrid, "export_params") else microgrid
+        return cls(params, batch=batch, **kw)
+
+    @property
+    def modules(self):
+        """module views of the (first) microgrid, as notebooks read them (`env.modules`)"""
+        from .microgrid import ModuleContainerView, ModuleView
+        names = ["load", "pv", "unbalanced_energy"] + (["genset"] if self.params.has_genset else []) + ["battery"] + \
+                (["grid"] if self.params.has_grid else [])
+        return ModuleContainerView((n, [ModuleView(self, n)]) for n in names)
+
+    def _state(self):     # live state of env 0, for the module views
+        g = self.group
+        gen = tuple(int(x) for x in self.engine.genset_status(0)[0].tolist()) if g.genset is not None else (0, 0, 0, 0)
+        return dict(t=int(g.step[0].item()), charge=float(g.charge[0].item()), genset=gen)
+
+    @property
+    def initial_step(self):
+        return self.params.initial_step
+
+    @property
+    def final_step(self):
+        return self.params.final_step
+
     @property
     def current_step(self):
         return self.group.step if not self.single else int(self.group.step[0].item())

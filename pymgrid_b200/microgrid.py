@@ -101,14 +101,177 @@ class ModuleView:
         self._require("genset")
         return self._m._state()["genset"][1]
 
+    # -- typing (module_container.py:355-413 sorts modules by these) --
+    @property
+    def module_type(self):
+        """(class tag, dispatch type) like the reference's class attribute, e.g. ('load', 'fixed')"""
+        tag = {"pv": "renewable", "unbalanced_energy": "balancing"}.get(self.name[0], self.name[0])
+        return (tag, {"load": "fixed", "pv": "flex", "unbalanced_energy": "flex"}.get(self.name[0], "controllable"))
+
+    @property
+    def is_source(self):
+        return self.name[0] != "load"
+
+    @property
+    def is_sink(self):
+        return self.name[0] in ("load", "battery", "grid", "unbalanced_energy")
+
+    @property
+    def action_space(self):
+        """only `.shape` is read by the reference's callers (priority_list.py:27-33)"""
+        from types import SimpleNamespace
+        n = {"genset": 2, "battery": 1, "grid": 1, "pv": 1, "unbalanced_energy": 1}.get(self.name[0], 0)
+        return SimpleNamespace(shape=(n,))
+
+    # -- costs (base_module.py:651-670 and the per-module overrides) --
+    @property
+    def production_marginal_cost(self):
+        n, p = self.name[0], self._p
+        if n == "battery":
+            return p.battery.battery_cost_cycle                           # battery_module.py:340-342
+        if n == "genset":                                                 # genset_module.py:519-521: get_cost(1.0)
+            return p.genset.genset_cost * 1.0 + p.genset.cost_per_unit_co2 * (p.genset.co2_per_unit * 1.0)
+        if n == "grid":
+            return self.import_price[0]                                   # grid_module.py:322-324
+        if n == "unbalanced_energy":
+            return p.loss_load_cost                                       # unbalanced_energy_module.py:111-113
+        return 0.0
+
+    @property
+    def absorption_marginal_cost(self):
+        n, p = self.name[0], self._p
+        if n == "battery":
+            return p.battery.battery_cost_cycle
+        if n == "grid":
+            return self.export_price[0]
+        if n == "unbalanced_energy":
+            return p.overgeneration_cost
+        return 0.0
+
+    @property
+    def marginal_cost(self):
+        return self.production_marginal_cost
+
+    # -- genset look-ahead (genset_module.py:360-424) --
+    def next_status(self, goal_status):
+        self._require("genset")
+        cs, _, up, dn = self._m._state()["genset"]
+        if goal_status:
+            return 1 if (cs or up == 0) else 0
+        return 0 if (not cs or dn == 0) else 1
+
+    def next_max_production(self, goal_status):
+        return self.next_status(goal_status) * self._p.genset.running_max_production
+
+    def next_min_production(self, goal_status):
+        return self.next_status(goal_status) * self._p.genset.running_min_production
+
+    # -- state vectors (BaseMicrogridModule.state / state_dict, base_module.py:535-560) --
+    def state_dict(self, normalized=False):
+        st = self._m._state()
+        d = views.state_dict(self._p, st["t"], st["charge"], st["genset"])[self.name[0]]
+        if normalized:
+            return OrderedDict(zip(d.keys(), self.to_normalized(np.array(list(d.values()), dtype=np.float64), obs=True)))
+        return d
+
+    @property
+    def state(self):
+        return np.array(list(self.state_dict().values()), dtype=np.float64)
+
+    @property
+    def min_obs(self):
+        return self._bounds("obs")[0]
+
+    @property
+    def max_obs(self):
+        return self._bounds("obs")[1]
+
+    @property
+    def min_act(self):
+        return self._bounds("act")[0]
+
+    @property
+    def max_act(self):
+        return self._bounds("act")[1]
+
+    def _bounds(self, which):
+        n, p, rows = self.name[0], self._p, 1 + self._p.forecast_horizon
+        if n == "battery":      # battery_module.py:323-338
+            b = p.battery
+            return ((np.array([b.min_soc, b.min_capacity]), np.array([1.0, b.max_capacity])) if which == "obs"
+                    else (b.min_act, b.max_act))
+        if n == "genset":       # genset_module.py:503-517
+            g = p.genset
+            return ((np.zeros(4), np.array([1.0, 1.0, g.start_up_time, g.wind_down_time])) if which == "obs"
+                    else (np.array([0.0, 0.0]), np.array([1.0, g.running_max_production])))
+        if n == "grid":         # grid_module.py:125-132
+            ts = p.grid.effective_time_series()
+            return ((np.tile(ts.min(axis=0), rows), np.tile(ts.max(axis=0), rows)) if which == "obs"
+                    else (-1 * p.grid.max_export, p.grid.max_import))
+        if n in ("load", "pv"):  # base_timeseries_module.py:81-88
+            ts = (p.load_ts * p.load_scale) if n == "load" else (p.pv_ts * p.pv_scale)
+            lo, hi = views.series_bounds(ts, True)
+            return (np.full(rows, lo), np.full(rows, hi)) if which == "obs" else ((lo, hi) if n == "pv" else (np.array([]), np.array([])))
+        return (np.array([]), np.array([])) if which == "obs" else (-np.inf, np.inf)
+
+    def to_normalized(self, value, act=False, obs=False):
+        """reference: BaseMicrogridModule.to_normalized -> ModuleSpace.normalize (utils/space.py:207-218)"""
+        assert act + obs == 1, "One of act or obs must be True but not both."
+        low, high = self._bounds("act" if act else "obs")
+        spread = np.asarray(high, dtype=np.float64) - np.asarray(low, dtype=np.float64)
+        spread = np.where(spread == 0, 1.0, spread)
+        return (np.asarray(value, dtype=np.float64) - low) / spread
+
+    def from_normalized(self, value, act=False, obs=False):
+        """reference: ModuleSpace.denormalize (utils/space.py:220-231)"""
+        assert act + obs == 1, "One of act or obs must be True but not both."
+        low, high = self._bounds("act" if act else "obs")
+        spread = np.asarray(high, dtype=np.float64) - np.asarray(low, dtype=np.float64)
+        spread = np.where(spread == 0, 1.0, spread)
+        return low + spread * np.asarray(value, dtype=np.float64)
+
+    # -- grid columns of the current state (grid_module.py:248-299: state[k::4], current + forecast) --
+    def _grid_column(self, k):
+        self._require("grid")
+        return self.state[k::4]
+
+    @property
+    def import_price(self):
+        return self._grid_column(0)
+
+    @property
+    def export_price(self):
+        return self._grid_column(1)
+
+    @property
+    def co2_per_kwh(self):
+        return self._grid_column(2)
+
+    @property
+    def grid_status(self):
+        return self._grid_column(3)
+
+    @property
+    def min_soc(self):
+        self._require("battery")
+        return self._p.battery.min_soc
+
+    @property
+    def max_soc(self):
+        self._require("battery")
+        return 1.0
+
     def __getattr__(self, item):   # constructor parameters, e.g. battery.max_capacity, genset.genset_cost, grid.max_import
         src = {"battery": self._p.battery, "genset": self._p.genset, "grid": self._p.grid}.get(self.name[0])
-        if src is not None and hasattr(src, item):
+        if src is not None and hasattr(src, item) and not item.startswith("_"):
             return getattr(src, item)
         if item == "time_series":
-            return {"load": self._p.load_ts.reshape(-1, 1), "pv": self._p.pv_ts.reshape(-1, 1)}[self.name[0]]
+            return {"load": self._p.load_ts.reshape(-1, 1) * self._p.load_scale,
+                    "pv": self._p.pv_ts.reshape(-1, 1) * self._p.pv_scale}[self.name[0]]
         if item == "forecast_horizon" and self.name[0] in ("load", "pv", "grid"):
             return self._p.forecast_horizon
+        if item in ("initial_step", "final_step"):
+            return getattr(self._m, item)
         if item in ("loss_load_cost", "overgeneration_cost") and self.name[0] == "unbalanced_energy":
             return getattr(self._p, item)
         raise AttributeError(item)
@@ -128,6 +291,24 @@ class ModuleContainerView(OrderedDict):
 
     def iterlist(self):
         return [m for lst in self.values() for m in lst]
+
+    to_list = iterlist
+
+    def _filtered(self, keep):
+        return ModuleContainerView((n, lst) for n, lst in self.items() if keep(lst[0]))
+
+    # the reference's second container level (module_container.py:405-411): sources / sinks / source_and_sinks
+    @property
+    def sources(self):
+        return self._filtered(lambda m: m.is_source and not m.is_sink)
+
+    @property
+    def sinks(self):
+        return self._filtered(lambda m: m.is_sink and not m.is_source)
+
+    @property
+    def source_and_sinks(self):
+        return self._filtered(lambda m: m.is_source and m.is_sink)
 
     def to_dict(self):
         return dict(self)
@@ -273,6 +454,30 @@ class Microgrid:
                     hi = (m.max_production - act_lo) / spread
                 out[name] = [np.random.rand() * (hi - lo) + lo]
         return out
+
+    def export_params(self):
+        """A copy of the parameter record carrying the LIVE state (step, battery charge, genset tuple): what the
+        reference's deep copies of a running microgrid hold (e.g. BaseMicrogridEnv.from_microgrid, envs/base/base.py:270-290)."""
+        import copy
+        st = self._state()
+        p = copy.deepcopy(self.params)
+        p.current_step, p.initial_step, p.final_step = st["t"], self._initial_step, self._final_step
+        p.battery.current_charge = st["charge"]
+        if p.genset is not None:
+            g = p.genset
+            g.current_status, g.goal_status, g.steps_until_up, g.steps_until_down = st["genset"]
+        return p
+
+    def get_forecast_horizon(self):
+        """reference: Microgrid.get_forecast_horizon (microgrid.py:364-388)"""
+        return self.params.forecast_horizon
+
+    def to_normalized(self, data_dict, act=False, obs=False):
+        """reference: Microgrid.to_normalized (microgrid.py:390-410): {name: [values]} through each module's space"""
+        return {name: [self._modules[name][0].to_normalized(v, act=act, obs=obs) for v in vals] for name, vals in data_dict.items()}
+
+    def from_normalized(self, data_dict, act=False, obs=False):
+        return {name: [self._modules[name][0].from_normalized(v, act=act, obs=obs) for v in vals] for name, vals in data_dict.items()}
 
     def get_empty_action(self, sample_flex_modules=False):
         return {name: [None] for name in views.control_names(self.params)}

@@ -485,6 +485,58 @@ def make_shaped():
     np.savez_compressed(os.path.join(HERE, "shaped.npz"), **out)
 
 
+VIEW_SCALARS = ("marginal_cost", "production_marginal_cost", "absorption_marginal_cost", "max_production",
+                "max_consumption", "min_production", "is_source", "is_sink")
+VIEW_VECTORS = ("state", "min_obs", "max_obs", "min_act", "max_act")
+
+
+def make_views():
+    """Module attributes the reference's own callers read (RBC / priority lists / MPC / notebooks), after a few
+    random steps: costs, limits, state vectors, spaces, the genset look-ahead, grid price columns, container sorting."""
+    out = {}
+    for n in (0, 1, 2):
+        m = Microgrid.from_scenario(n)
+        rng = np.random.default_rng(9000 + n)
+        for row in rng.random((7, n_act(m))):
+            m.run(control_from_flat(m, row))
+        out[f"s{n}_state"] = state_vec(m)
+        out[f"s{n}_actions"] = np.random.default_rng(9000 + n).random((7, n_act(m)))
+        for name, lst in m.modules.iterdict():
+            mod = lst[0]
+            for a in VIEW_SCALARS:
+                try:
+                    out[f"s{n}_{name}_{a}"] = np.array(float(getattr(mod, a)))
+                except (AttributeError, NotImplementedError, TypeError):
+                    pass
+            for a in VIEW_VECTORS:
+                out[f"s{n}_{name}_{a}"] = np.atleast_1d(np.asarray(getattr(mod, a), dtype=np.float64)).ravel()
+            out[f"s{n}_{name}_type"] = np.array(",".join(mod.module_type))
+            out[f"s{n}_{name}_n_act"] = np.array(mod.action_space.shape[0])
+            st = mod.state
+            out[f"s{n}_{name}_norm_state"] = np.atleast_1d(np.asarray(mod.to_normalized(st, obs=True), dtype=np.float64)).ravel()
+        if hasattr(m.modules, "genset"):
+            g = m.modules.genset[0]
+            out[f"s{n}_genset_next"] = np.array([g.next_status(0), g.next_status(1), g.next_max_production(0), g.next_max_production(1),
+                                                 g.next_min_production(0), g.next_min_production(1)], dtype=np.float64)
+        if hasattr(m.modules, "grid"):
+            g = m.modules.grid[0]
+            out[f"s{n}_grid_columns"] = np.stack([g.import_price, g.export_price, g.co2_per_kwh])
+        b = m.modules.battery[0]
+        out[f"s{n}_battery_socs"] = np.array([b.soc, b.min_soc, b.max_soc])
+        for kind in ("fixed", "flex", "controllable"):
+            c = getattr(m, kind)
+            for sub in ("sources", "sinks", "source_and_sinks"):
+                names = list(getattr(c, sub).keys()) if hasattr(c, sub) else []
+                out[f"s{n}_{kind}_{sub}"] = np.array(",".join(names))
+        out[f"s{n}_horizon"] = np.array(m.get_forecast_horizon())
+        ctrl = control_from_flat(m, rng.random(n_act(m)))
+        dn = m.from_normalized(ctrl, act=True)
+        out[f"s{n}_denorm_in"] = np.concatenate([np.ravel(v[0]) for v in ctrl.values()])
+        out[f"s{n}_denorm_out"] = np.concatenate([np.ravel(v[0]) for v in dn.values()])
+        print("views", n, out[f"s{n}_state"], out[f"s{n}_controllable_source_and_sinks"], out[f"s{n}_denorm_out"])
+    np.savez_compressed(os.path.join(HERE, "views.npz"), **out)
+
+
 NOISE_CASES = (   # scenario, {module: (std, increase_uncertainty, relative_noise)}
     (0, dict(load=(40.0, False, False), pv=(0.15, True, True), grid=(0.05, True, False))),
     (2, dict(load=(0.1, True, True), pv=(25.0, False, False))),
@@ -518,11 +570,13 @@ def make_noisy_forecast():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["noisy", "steps", "year", "discrete", "genset", "custom", "log", "rbc", "generator", "shaped"]
+    which = sys.argv[1:] or ["views", "noisy", "steps", "year", "discrete", "genset", "custom", "log", "rbc", "generator", "shaped"]
     if "shaped" in which:
         make_shaped()
     if "noisy" in which:
         make_noisy_forecast()
+    if "views" in which:
+        make_views()
     if "generator" in which:
         make_generator()
     if "rbc" in which:

@@ -234,3 +234,23 @@ def test_reward_shaping_func_drop_in(golden):
         m.run(control(m.params, z[key + "_a"][raised]))
     with pytest.raises(ValueError):
         Microgrid(load_pymgrid25(0), reward_shaping_func=lambda info, cost: 0.0)
+
+
+@pytest.mark.parametrize("n", (0, 1, 2))
+def test_module_views_on_the_engine(golden, n):
+    """the attributes RBC / priority lists / MPC / notebooks read, backed by device state, against the reference"""
+    from pymgrid_b200.envs import DiscreteMicrogridEnv
+    from pymgrid_b200.microgrid import Microgrid
+    from tests.test_module_views import check_views
+    z = golden["views"]
+    m = Microgrid.from_scenario(n)
+    for a in z[f"s{n}_actions"]:
+        m.run(control(m.params, a))
+    np.testing.assert_array_equal(np.array([m.current_step, m.modules.battery[0].current_charge]), z[f"s{n}_state"][:2])
+    check_views(m, z, n)
+    # an env over a copy of the running microgrid carries its state (envs/base/base.py:270-290)
+    env = DiscreteMicrogridEnv.from_microgrid(m)
+    assert env.current_step == m.current_step and env.modules.battery[0].current_charge == m.modules.battery[0].current_charge
+    assert env.modules.battery[0].max_production == m.modules.battery[0].max_production
+    if m.params.has_genset:
+        assert env.modules.genset[0].current_status == m.modules.genset[0].current_status
