@@ -360,7 +360,8 @@ def main():
     value = world * B * K / (ms * 1e-3)
 
     # ---- end to end through the public API with host buffers -------------------------------------------------
-    # HostIO.step(): actions pinned-host -> device (one copy), fused kernel, reward + done device -> pinned-host (one copy)
+    # (1) HostIO.step(): one step per call -- actions pinned-host -> device (one copy), fused kernel, reward + done
+    #     device -> pinned-host (one copy), serialised on one stream: the figure a host-side control loop sees.
     Ke = min(K, 200)
     bm.load_state_dict(state0)
     hio = bm.host_io(normalized=True, obs=[r[0] for r in rings], discrete=discrete)
@@ -376,7 +377,64 @@ def main():
         ev1.record(stream)
         barrier()
     h2d, d2h = hio.h2d_bytes, hio.d2h_bytes
-    e2e_value = world * B * Ke / (max_over_ranks(ev0.elapsed_time(ev1)) * 1e-3)
+    e2e_step_value = world * B * Ke / (max_over_ranks(ev0.elapsed_time(ev1)) * 1e-3)
+    e2e = {"value": e2e_step_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+           "api": "BatchedMicrogrid.host_io().step()",
+           "note": "actions written into pinned host memory by the caller, one H2D copy, fused kernel, one D2H copy of "
+                   "reward+done, every step; observations stay on the device"}
+    # (2) HostRollout.run(): the workload's own call (a year rollout with pre-generated actions) with HOST buffers --
+    #     every step's actions cross the bus host -> device and every step's reward + done come back, in chunks of
+    #     `chunk` steps, the copies of neighbouring chunks overlapped with the persistent kernel on three streams.
+    #     Same bytes per step as (1); this is the headline e2e figure when it runs (any failure keeps (1) and says so).
+    # Collectives (barrier, max over ranks) stay outside the try blocks so that a failure on one rank cannot hang the others.
+    err, hr, ms_local = None, None, float("inf")
+    Kr, chunk = min(K, 1024), 64
+    try:
+        del hio
+        bm.load_state_dict(state0)
+        hr = bm.host_rollout(Kr, chunk=chunk, normalized=True, discrete=discrete, ring=R)
+        for a, g in zip(hr.actions, groups):
+            if discrete:
+                a.copy_(torch.randint(0, g.n_actions, tuple(a.shape), dtype=torch.int32))
+            else:
+                a.uniform_(0.0, 1.0)
+        with torch.cuda.stream(stream):
+            hr.run(min(Kr, 3 * chunk) if Kr % chunk == 0 else Kr)      # warm-up (untimed)
+            bm.load_state_dict(state0)
+    except Exception as ex:      # keep the per-step figure; never lose the bench line to this path
+        err = f"{type(ex).__name__}: {ex}"
+    barrier()
+    if err is None:
+        try:
+            with torch.cuda.stream(stream):
+                launch_e = bm.launch_count
+                ev0.record(stream)
+                hr.run()
+                ev1.record(stream)
+            torch.cuda.synchronize()
+            if not all(bool(torch.isfinite(r).all()) for r in hr.reward):
+                raise RuntimeError("non-finite reward came back from the host rollout")
+            ms_local = ev0.elapsed_time(ev1)
+        except Exception as ex:
+            err = f"{type(ex).__name__}: {ex}"
+            ms_local = float("inf")
+    barrier()
+    ms_e = max_over_ranks(ms_local)
+    if ms_e != float("inf"):
+        e2e = {"value": world * B * Kr / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": hr.h2d_bytes_per_step,
+               "d2h_bytes_per_step": hr.d2h_bytes_per_step, "steps": Kr, "chunk_steps": chunk,
+               "gpu_launches": bm.launch_count - launch_e, "us_per_step": 1e3 * ms_e / Kr,
+               "pcie_gbs": {"h2d": hr.h2d_bytes_per_step * Kr / (ms_e * 1e-3) / 1e9, "d2h": hr.d2h_bytes_per_step * Kr / (ms_e * 1e-3) / 1e9},
+               "api": "BatchedMicrogrid.host_rollout(n_steps).run()",
+               "note": "year-rollout call with HOST buffers: every step's actions go pinned-host -> device and every step's "
+                       "reward + done come back device -> pinned-host inside the timed region, in chunks of 64 steps; copy-in, "
+                       "persistent kernel and copy-out of neighbouring chunks overlap on three streams (PCIe-bound); "
+                       "observations go to the device ring",
+               "per_step_call": {"value": e2e_step_value, "api": "BatchedMicrogrid.host_io().step()", "steps": Ke,
+                                 "note": "one H2D + kernel + one D2H per step, serialised (a host-side control loop)"}}
+    else:
+        e2e["host_rollout_error"] = err or "failed on another rank"
+    hr = None
 
     if rank == 0:
         bytes_per_launch = sum(g.n_envs * algorithmic_bytes(*g.arch, discrete=discrete, obs_bytes=4 if args.obs_f32 else 8) for g in groups)
@@ -406,9 +464,7 @@ def main():
                        "parallelism": f"batch sharded over {world} GPU(s), no collective on the step path"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "note": "BatchedMicrogrid.host_io().step(): actions written into pinned host memory by the caller, one H2D copy, "
-                            "fused kernel, one D2H copy of reward+done, every step; observations stay on the device"},
+            "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "mg_step_kernel" if args.path != "rollout" else "mg_rollout_kernel",
                          "bytes_per_launch": bytes_per_launch, "bytes_per_step": bytes_per_step, "steps_per_launch": steps_per_launch,

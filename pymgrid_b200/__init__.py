@@ -7,7 +7,7 @@ from .scenario import load_pymgrid25  # noqa: E402,F401
 
 def __getattr__(name):
     # the engine-backed classes import torch and load the CUDA extension: resolve them lazily
-    if name in ("BatchedMicrogrid", "HostIO"):
+    if name in ("BatchedMicrogrid", "HostIO", "HostRollout"):
         from . import engine
         return getattr(engine, name)
     if name == "Microgrid":

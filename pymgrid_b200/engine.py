@@ -218,6 +218,98 @@ class HostIO:
         return [g.obs.cpu() for g in self.bm.groups]
 
 
+class HostRollout:
+    """A rollout whose actions and results live in HOST memory (BASELINE configs[2]: a year of pre-generated actions),
+    pipelined over three CUDA streams so that PCIe, not the sum of copy + kernel + copy, sets the pace:
+
+        copy-in stream :  H2D chunk c+1 ........ H2D chunk c+2 ........
+        current stream :  mg_rollout(chunk c) .. mg_rollout(chunk c+1)      (persistent kernel, `chunk` steps per launch)
+        copy-out stream:  D2H reward/done c-1 .. D2H reward/done c ....
+
+    `actions[g]`: pinned float64 [n_steps, n_g, n_act] (int32 [n_steps, n_g] when discrete), filled by the caller;
+    `reward[g]` / `done[g]`: pinned [n_steps, n_g] float64 / uint8, valid after `sync()`.  Per step the same bytes cross
+    the bus as in `HostIO.step()` (all actions in, reward + done out); observations go to a device ring of `ring`
+    buffers (`obs_ring[g]`, step s of a chunk in slot s % ring), where a policy or a logger would read them.
+    Device staging is double-buffered (2 x chunk steps of actions and results), whatever n_steps is.
+
+    Every cross-stream wait refers to an event recorded earlier in the same host thread, so the schedule cannot deadlock.
+    """
+
+    def __init__(self, bm, n_steps, chunk=64, normalized=True, discrete=False, ring=4, keep_obs=True):
+        if n_steps < 1 or chunk < 1:
+            raise ValueError("n_steps and chunk must be positive")
+        self.bm, self.n_steps, self.chunk = bm, int(n_steps), int(min(chunk, n_steps))
+        self.discrete = discrete
+        dev, C = bm.device, self.chunk
+        adt = torch.int32 if discrete else torch.float64
+        ashape = (lambda g: (g.n_envs,)) if discrete else (lambda g: (g.n_envs, g.n_act))
+        self.actions = [torch.empty((self.n_steps,) + ashape(g), dtype=adt, pin_memory=True) for g in bm.groups]
+        self.reward = [torch.empty((self.n_steps, g.n_envs), dtype=torch.float64, pin_memory=True) for g in bm.groups]
+        self.done = [torch.empty((self.n_steps, g.n_envs), dtype=torch.uint8, pin_memory=True) for g in bm.groups]
+        self.obs_ring = [torch.empty((ring, g.n_envs, g.obs_dim), dtype=bm.obs_dtype, device=dev) if keep_obs else None
+                         for g in bm.groups]
+        self._d_act = [[torch.empty((C,) + ashape(g), dtype=adt, device=dev) for g in bm.groups] for _ in range(2)]
+        self._d_rew = [[torch.empty((C, g.n_envs), dtype=torch.float64, device=dev) for g in bm.groups] for _ in range(2)]
+        self._d_done = [[torch.empty((C, g.n_envs), dtype=torch.uint8, device=dev) for g in bm.groups] for _ in range(2)]
+        self._s_in, self._s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self._launch = {}
+        lengths = {C} | ({self.n_steps % C} - {0})
+        for slot in range(2):
+            for n in lengths:       # bind the argument blocks once: a chunk costs one C call
+                out = [dict(reward=self._d_rew[slot][gi][:n], done=self._d_done[slot][gi][:n], obs_ring=self.obs_ring[gi],
+                            reward_sum=None) for gi in range(len(bm.groups))]
+                acts = [a[:n] for a in self._d_act[slot]]
+                self._launch[slot, n] = bm.rollout(acts if len(acts) > 1 else acts[0], normalized=normalized,
+                                                   discrete=discrete, ring=ring, keep_obs=keep_obs, out=out, bind_only=True)
+        item = 4 if discrete else 8
+        self.h2d_bytes_per_step = sum(a[0].numel() * item for a in self.actions)
+        self.d2h_bytes_per_step = 9 * bm.n_envs
+        self.launches = 0
+
+    def run(self, n_steps=None):
+        """Enqueue the whole rollout (asynchronous w.r.t. the host); results are complete after `sync()` or after any
+        later work on the current stream, which is made to wait for the last copy-out."""
+        T = self.n_steps if n_steps is None else int(n_steps)
+        if not 1 <= T <= self.n_steps:
+            raise ValueError(f"n_steps must be in [1, {self.n_steps}]")
+        C, G = self.chunk, range(len(self.bm.groups))
+        if (0, T % C or C) not in self._launch:
+            raise ValueError(f"run({T}): a last chunk of {T % C} steps was not bound; use a multiple of chunk={C} or n_steps={self.n_steps}")
+        cur = torch.cuda.current_stream(self.bm.device)
+        s_in, s_out = self._s_in, self._s_out
+        s_in.wait_stream(cur)              # the caller's earlier work (state loads, a previous run) comes first
+        s_out.wait_stream(cur)
+        computed, drained = [None, None], [None, None]
+        for c, s0 in enumerate(range(0, T, C)):
+            slot, n = c & 1, min(C, T - s0)
+            with torch.cuda.stream(s_in):
+                if computed[slot] is not None:
+                    s_in.wait_event(computed[slot])        # the kernel that read this slot's actions is done
+                for gi in G:
+                    self._d_act[slot][gi][:n].copy_(self.actions[gi][s0:s0 + n], non_blocking=True)
+                uploaded = torch.cuda.Event()
+                uploaded.record(s_in)
+            cur.wait_event(uploaded)
+            if drained[slot] is not None:
+                cur.wait_event(drained[slot])              # this slot's previous results have left the device
+            self._launch[slot, n]()
+            self.launches += 1
+            computed[slot] = torch.cuda.Event()
+            computed[slot].record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(computed[slot])
+                for gi in G:
+                    self.reward[gi][s0:s0 + n].copy_(self._d_rew[slot][gi][:n], non_blocking=True)
+                    self.done[gi][s0:s0 + n].copy_(self._d_done[slot][gi][:n], non_blocking=True)
+                drained[slot] = torch.cuda.Event()
+                drained[slot].record(s_out)
+        cur.wait_stream(s_out)
+        cur.wait_stream(s_in)
+
+    def sync(self):
+        torch.cuda.current_stream(self.bm.device).synchronize()
+
+
 class LogRecorder:
     """Opt-in log for a SUBSET of a batch (reference: Microgrid.get_log, microgrid.py:434-475; the full log is 169-176 f64
     columns per env-step, ~800 GB per year at 65 536 envs, so it cannot be always-on -- SURVEY.md section 5).
@@ -731,6 +823,10 @@ class BatchedMicrogrid:
     def host_io(self, normalized=True, discrete=False, obs=True, use_graph=False):
         """Pinned host staging for a host-resident control loop (see HostIO)."""
         return HostIO(self, normalized=normalized, discrete=discrete, obs=obs, use_graph=use_graph)
+
+    def host_rollout(self, n_steps, chunk=64, **kw):
+        """Rollout with host-resident actions and results, copies overlapped with the kernel (see HostRollout)."""
+        return HostRollout(self, n_steps, chunk=chunk, **kw)
 
     # ------------------------------------------------------------------------------------------------------
     @property

@@ -207,6 +207,43 @@ def test_host_io_graph_replay_equals_eager():
         assert torch.equal(ga.obs, gc.obs) and torch.equal(ga.charge, gc.charge)
 
 
+@pytest.mark.parametrize("discrete", [False, True])
+def test_host_rollout_pipeline_equals_device_rollout(discrete):
+    """HostRollout.run(): actions in pinned host memory, chunks of 8 steps uploaded / computed / drained on three
+    streams (double-buffered staging, a shorter last chunk, two consecutive runs) == one mg_rollout over device-resident
+    actions, bit for bit: reward, done, final state and the last observation rows."""
+    from pymgrid_b200.engine import BatchedMicrogrid
+    scen = [n for n in range(25) if load_pymgrid25(n).grid is not None] if discrete else list(range(25))
+    configs = [load_pymgrid25(n) for n in scen]
+    env_config = np.arange(2500) % len(configs)
+    a = BatchedMicrogrid(configs, env_config, device="cuda:0")
+    b = BatchedMicrogrid(configs, env_config, device="cuda:0")
+    T, ring = 45, 4
+    hr = a.host_rollout(T, chunk=8, discrete=discrete, ring=ring)
+    assert hr.h2d_bytes_per_step == sum(g.n_envs * (4 if discrete else 8 * g.n_act) for g in a.groups)
+    gen = torch.Generator().manual_seed(11)
+    for rep in range(2):
+        for x, g in zip(hr.actions, a.groups):
+            if discrete:
+                x.copy_(torch.randint(0, g.n_actions, tuple(x.shape), dtype=torch.int32, generator=gen))
+            else:
+                x.copy_(torch.rand(tuple(x.shape), dtype=torch.float64, generator=gen))
+        hr.run()
+        hr.sync()
+        dev = [x.cuda() for x in hr.actions]
+        out = b.rollout(dev if len(dev) > 1 else dev[0], discrete=discrete, ring=ring)
+        out = [out] if isinstance(out, dict) else out
+        for gi, (ga, gb) in enumerate(zip(a.groups, b.groups)):
+            assert torch.equal(hr.reward[gi], out[gi]["reward"].cpu())
+            assert torch.equal(hr.done[gi], out[gi]["done"].cpu())
+            assert torch.equal(ga.step, gb.step) and torch.equal(ga.charge, gb.charge)
+            # the last chunk (steps 40..44) restarts the ring at slot 0: its last row sits in slot (T - 40 - 1) % ring
+            assert torch.equal(hr.obs_ring[gi][(T - 40 - 1) % ring], out[gi]["obs_ring"][(T - 1) % ring])
+    assert hr.launches == 2 * 6
+    with pytest.raises(ValueError):
+        hr.run(44)          # 44 = 5 x 8 + 4: a last chunk of 4 steps was never bound
+
+
 def test_reward_shaping_func_drop_in(golden):
     """Microgrid(reward_shaping_func=...) like the reference (microgrid.py:100-124): run returns the shaped reward, the
     balance log keeps reward and shaped_reward, and the shaper's assert surfaces as AssertionError on the same step."""
