@@ -387,54 +387,62 @@ def main():
     #     `chunk` steps, the copies of neighbouring chunks overlapped with the persistent kernel on three streams.
     #     Same bytes per step as (1); this is the headline e2e figure when it runs (any failure keeps (1) and says so).
     # Collectives (barrier, max over ranks) stay outside the try blocks so that a failure on one rank cannot hang the others.
-    err, hr, ms_local = None, None, float("inf")
     Kr, chunk = min(K, 1024), 64
-    try:
-        del hio
-        bm.load_state_dict(state0)
-        hr = bm.host_rollout(Kr, chunk=chunk, normalized=True, discrete=discrete, ring=R)
-        for a, g in zip(hr.actions, groups):
-            if discrete:
-                a.copy_(torch.randint(0, g.n_actions, tuple(a.shape), dtype=torch.int32))
-            else:
-                a.uniform_(0.0, 1.0)
-        with torch.cuda.stream(stream):
-            hr.run(min(Kr, 3 * chunk) if Kr % chunk == 0 else Kr)      # warm-up (untimed)
-            bm.load_state_dict(state0)
-    except Exception as ex:      # keep the per-step figure; never lose the bench line to this path
-        err = f"{type(ex).__name__}: {ex}"
-    barrier()
-    if err is None:
+    del hio
+    errors = {}
+    for pipeline in ("native", "torch"):       # mg_rollout_host (one C-ABI call); else the same schedule from torch streams
+        err, hr, ms_local, launch_e = None, None, float("inf"), 0
         try:
+            bm.load_state_dict(state0)
+            hr = bm.host_rollout(Kr, chunk=chunk, normalized=True, discrete=discrete, ring=R, pipeline=pipeline)
+            for a, g in zip(hr.actions, groups):
+                if discrete:
+                    a.copy_(torch.randint(0, g.n_actions, tuple(a.shape), dtype=torch.int32))
+                else:
+                    a.uniform_(0.0, 1.0)
             with torch.cuda.stream(stream):
-                launch_e = bm.launch_count
-                ev0.record(stream)
-                hr.run()
-                ev1.record(stream)
-            torch.cuda.synchronize()
-            if not all(bool(torch.isfinite(r).all()) for r in hr.reward):
-                raise RuntimeError("non-finite reward came back from the host rollout")
-            ms_local = ev0.elapsed_time(ev1)
-        except Exception as ex:
+                hr.run(min(Kr, 3 * chunk) if Kr % chunk == 0 else Kr)      # warm-up (untimed)
+                bm.load_state_dict(state0)
+        except Exception as ex:      # keep the per-step figure; never lose the bench line to this path
             err = f"{type(ex).__name__}: {ex}"
-            ms_local = float("inf")
-    barrier()
-    ms_e = max_over_ranks(ms_local)
-    if ms_e != float("inf"):
-        e2e = {"value": world * B * Kr / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": hr.h2d_bytes_per_step,
-               "d2h_bytes_per_step": hr.d2h_bytes_per_step, "steps": Kr, "chunk_steps": chunk,
-               "gpu_launches": bm.launch_count - launch_e, "us_per_step": 1e3 * ms_e / Kr,
-               "pcie_gbs": {"h2d": hr.h2d_bytes_per_step * Kr / (ms_e * 1e-3) / 1e9, "d2h": hr.d2h_bytes_per_step * Kr / (ms_e * 1e-3) / 1e9},
-               "api": "BatchedMicrogrid.host_rollout(n_steps).run()",
-               "note": "year-rollout call with HOST buffers: every step's actions go pinned-host -> device and every step's "
-                       "reward + done come back device -> pinned-host inside the timed region, in chunks of 64 steps; copy-in, "
-                       "persistent kernel and copy-out of neighbouring chunks overlap on three streams (PCIe-bound); "
-                       "observations go to the device ring",
-               "per_step_call": {"value": e2e_step_value, "api": "BatchedMicrogrid.host_io().step()", "steps": Ke,
-                                 "note": "one H2D + kernel + one D2H per step, serialised (a host-side control loop)"}}
-    else:
-        e2e["host_rollout_error"] = err or "failed on another rank"
-    hr = None
+        barrier()
+        if err is None:
+            try:
+                with torch.cuda.stream(stream):
+                    launch_e = bm.launch_count
+                    ev0.record(stream)
+                    hr.run()
+                    ev1.record(stream)
+                torch.cuda.synchronize()
+                launch_e = bm.launch_count - launch_e
+                if not all(bool(torch.isfinite(r).all()) for r in hr.reward):
+                    raise RuntimeError("non-finite reward came back from the host rollout")
+                ms_local = ev0.elapsed_time(ev1)
+            except Exception as ex:
+                err = f"{type(ex).__name__}: {ex}"
+                ms_local = float("inf")
+        barrier()
+        ms_e = max_over_ranks(ms_local)
+        if ms_e != float("inf"):
+            name = "mg_rollout_host" if pipeline == "native" else "mg_rollout + torch streams"
+            e2e = {"value": world * B * Kr / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": hr.h2d_bytes_per_step,
+                   "d2h_bytes_per_step": hr.d2h_bytes_per_step, "steps": Kr, "chunk_steps": chunk,
+                   "gpu_launches": launch_e, "us_per_step": 1e3 * ms_e / Kr,
+                   "pcie_gbs": {"h2d": hr.h2d_bytes_per_step * Kr / (ms_e * 1e-3) / 1e9, "d2h": hr.d2h_bytes_per_step * Kr / (ms_e * 1e-3) / 1e9},
+                   "api": f"BatchedMicrogrid.host_rollout(n_steps).run() -> {name}",
+                   "note": "year-rollout call with HOST buffers: every step's actions go pinned-host -> device and every step's "
+                           "reward + done come back device -> pinned-host inside the timed region, in chunks of 64 steps; copy-in, "
+                           "persistent kernel and copy-out of neighbouring chunks overlap on three streams (PCIe-bound); "
+                           "observations go to the device ring",
+                   "per_step_call": {"value": e2e_step_value, "api": "BatchedMicrogrid.host_io().step()", "steps": Ke,
+                                     "note": "one H2D + kernel + one D2H per step, serialised (a host-side control loop)"}}
+        else:
+            errors[pipeline] = err or "failed on another rank"
+        hr = None
+        if ms_e != float("inf"):
+            break
+    if errors:
+        e2e["host_rollout_errors"] = errors
 
     if rank == 0:
         bytes_per_launch = sum(g.n_envs * algorithmic_bytes(*g.arch, discrete=discrete, obs_bytes=4 if args.obs_f32 else 8) for g in groups)

@@ -215,7 +215,7 @@ typedef struct MgHandle MgHandle;
 /* library / build identification (also the symbol the loader probes first) */
 int mg_abi_version(void);
 /* sizeof of an ABI struct as compiled (0 MgConfig, 1 MgPriorityList, 2 MgGroup, 3 MgLayout, 4 MgStepIO,
- * 5 MgRolloutIO): lets a foreign-language binding verify its struct mirror before the first call */
+ * 5 MgRolloutIO, 6 MgForecastNoise, 7 MgHostRolloutIO): lets a foreign-language binding verify its struct mirror before the first call */
 int64_t mg_sizeof(int which);
 const char *mg_build_info(void);
 const char *mg_last_error(void);
@@ -259,6 +259,31 @@ int mg_observe(MgHandle *h, const MgStepIO *io, void *stream);
  */
 int mg_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, int normalized, void *stream);
 int mg_rollout_discrete(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, void *stream);
+
+/*
+ * mg_rollout_host -- the same loop for callers whose actions and results live in HOST memory, which is where every
+ * caller of the reference keeps them (the control dicts of Microgrid.run, microgrid.py:227-251; the numpy action arrays
+ * of algos/rbc/rbc.py:87-91 and of the RL notebooks).  The rollout is cut into chunks of `chunk` steps and pipelined on
+ * three streams: chunk c+1's actions go host -> device on a copy-in stream while the persistent kernel runs chunk c on
+ * `stream` and chunk c-1's reward / done go device -> host on a copy-out stream, so the bus, not the sum of the three,
+ * sets the pace.  The handle owns the double-buffered device staging (2 x chunk steps of actions, reward, done; allocated
+ * on first use on the current device, released by mg_destroy) -- the only device memory this library ever allocates.
+ * Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) for the copies to overlap;
+ * pageable memory gives the same results without the overlap.  The call returns once everything is enqueued; the results
+ * are complete when `stream` has drained (it is made to wait for the last copy-out).  Observations go to the caller's
+ * DEVICE ring (every chunk restarts at slot 0: step s of a chunk writes slot s % ring).
+ */
+typedef struct MgHostRolloutIO {
+    const double *actions;   /* HOST [n_steps, n, n_act] f64 (discrete == 0)                                  */
+    const int32_t *dactions; /* HOST [n_steps, n] int32 priority-list index (discrete != 0)                   */
+    double *reward;          /* HOST [n_steps, n]                                                             */
+    uint8_t *done;           /* HOST [n_steps, n]                                                             */
+    void *obs_ring;          /* DEVICE [ring, n, obs_dim] or NULL to skip observations                        */
+    uint32_t *flags;         /* DEVICE [n] OR over the rollout, or NULL                                       */
+} MgHostRolloutIO;
+
+int mg_rollout_host(MgHandle *h, const MgHostRolloutIO *io, int32_t n_steps, int32_t chunk, int32_t ring, int discrete,
+                    int normalized, void *stream);
 
 /*
  * mg_forecast_noise -- GaussianNoiseForecaster (forecast/forecaster.py:220-262) applied to observation rows that

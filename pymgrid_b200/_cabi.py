@@ -78,6 +78,10 @@ class MgRolloutIO(C.Structure):
                 ("reward_sum", _vp), ("flags", _vp), ("dactions_const", C.c_int64), ("reward_total", _vp)]
 
 
+class MgHostRolloutIO(C.Structure):
+    _fields_ = [("actions", _vp), ("dactions", _vp), ("reward", _vp), ("done", _vp), ("obs_ring", _vp), ("flags", _vp)]
+
+
 class MgForecastNoise(C.Structure):
     _fields_ = [("load_sigma", _d), ("pv_sigma", _d), ("grid_sigma", _d * 4),
                 ("load_increase", _i32), ("pv_increase", _i32), ("grid_increase", _i32), ("_pad", _i32)]
@@ -116,13 +120,15 @@ def lib():
     L.mg_observe.argtypes = [_vp, C.POINTER(MgStepIO), _vp]
     L.mg_rollout.argtypes = [_vp, C.POINTER(MgRolloutIO), _i32, _i32, C.c_int, _vp]
     L.mg_rollout_discrete.argtypes = [_vp, C.POINTER(MgRolloutIO), _i32, _i32, _vp]
+    L.mg_rollout_host.argtypes = [_vp, C.POINTER(MgHostRolloutIO), _i32, _i32, _i32, C.c_int, C.c_int, _vp]
     L.mg_set_option.argtypes = [_vp, C.c_int, C.c_int]
     L.mg_forecast_noise.argtypes = [_vp, _vp, C.POINTER(_vp), C.POINTER(C.c_int64), C.c_uint64, C.c_uint64, _vp]
     L.mg_launch_count.argtypes = [_vp]
     L.mg_launch_count.restype = C.c_int64
     if L.mg_abi_version() != MG_ABI_VERSION:
         raise EngineError(f"ABI mismatch: library {L.mg_abi_version()} vs binding {MG_ABI_VERSION}")
-    for which, struct in enumerate((MgConfig, MgPriorityList, MgGroup, MgLayout, MgStepIO, MgRolloutIO, MgForecastNoise)):
+    for which, struct in enumerate((MgConfig, MgPriorityList, MgGroup, MgLayout, MgStepIO, MgRolloutIO, MgForecastNoise,
+                                    MgHostRolloutIO)):
         if L.mg_sizeof(which) != C.sizeof(struct):
             raise EngineError(f"struct {struct.__name__}: library sizeof {L.mg_sizeof(which)} != binding {C.sizeof(struct)}")
     _lib = L
@@ -131,7 +137,7 @@ def lib():
 
 EXPORTED_SYMBOLS = ("mg_abi_version", "mg_sizeof", "mg_build_info", "mg_last_error", "mg_create", "mg_destroy",
                     "mg_step", "mg_step_discrete", "mg_reset", "mg_observe", "mg_rollout", "mg_rollout_discrete",
-                    "mg_launch_count", "mg_set_option", "mg_forecast_noise")
+                    "mg_rollout_host", "mg_launch_count", "mg_set_option", "mg_forecast_noise")
 
 
 def check(code, what):

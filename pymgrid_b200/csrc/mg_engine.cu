@@ -1223,7 +1223,34 @@ struct MgHandle {
     bool hetero;            // per-env series (profile * scale) or per-env grid status present: run the kHetero kernels
     bool obs_f32;           // observation buffers are float32 (MG_LAYOUT_OBS_F32)
     bool rollout_specialised;   // MG_OPT_ROLLOUT_SPECIALISED
+    struct HostStage *stage;    // mg_rollout_host: streams, events and device staging (lazy)
 };
+
+// Device staging of mg_rollout_host: two slots of `chunk` steps each (actions in, reward + done out) for every group,
+// two copy streams and the events that order them against the caller's stream.
+struct HostStage {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t uploaded[2] = {nullptr, nullptr}, computed[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+    cudaEvent_t fence = nullptr;            // start of a call on the caller's stream / end of the previous call
+    bool fence_recorded = false;
+    char *in[2] = {nullptr, nullptr}, *out[2] = {nullptr, nullptr};
+    size_t in_cap = 0, out_cap = 0;         // bytes per slot
+};
+
+static void stage_free(HostStage *st) {
+    if (!st) return;
+    for (int k = 0; k < 2; ++k) {
+        if (st->in[k]) cudaFree(st->in[k]);
+        if (st->out[k]) cudaFree(st->out[k]);
+        if (st->uploaded[k]) cudaEventDestroy(st->uploaded[k]);
+        if (st->computed[k]) cudaEventDestroy(st->computed[k]);
+        if (st->drained[k]) cudaEventDestroy(st->drained[k]);
+    }
+    if (st->fence) cudaEventDestroy(st->fence);
+    if (st->s_in) cudaStreamDestroy(st->s_in);
+    if (st->s_out) cudaStreamDestroy(st->s_out);
+    delete st;
+}
 
 static thread_local char g_err[512] = "";
 
@@ -1248,6 +1275,7 @@ extern "C" int64_t mg_sizeof(int which) {
         case 4: return sizeof(MgStepIO);
         case 5: return sizeof(MgRolloutIO);
         case 6: return sizeof(MgForecastNoise);
+        case 7: return sizeof(MgHostRolloutIO);
         default: return -1;
     }
 }
@@ -1312,6 +1340,7 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
     h->hetero = (L->flags & MG_LAYOUT_SCALED_SERIES) != 0;
     h->obs_f32 = (L->flags & MG_LAYOUT_OBS_F32) != 0;
     h->rollout_specialised = true;
+    h->stage = nullptr;
     h->last_stream = nullptr;
     for (int g = 0; g < MG_MAX_GROUPS; ++g) h->last_obs[g] = nullptr;
     LaunchParams &B = h->base;
@@ -1367,6 +1396,10 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
 }
 
 extern "C" int mg_destroy(MgHandle *h) {
+    if (h && h->stage) {
+        stage_free(h->stage);
+        cudaGetLastError();     // a context that is already gone at interpreter exit is not an error worth keeping
+    }
     delete h;
     return MG_OK;
 }
@@ -1528,4 +1561,121 @@ extern "C" int mg_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
 }
 extern "C" int mg_rollout_discrete(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int32_t ring, void *stream) {
     return launch_rollout(h, io, n_steps, ring, MODE_DISCRETE, 0, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// mg_rollout_host: host-resident actions / results, chunked and pipelined over three streams
+// ------------------------------------------------------------------------------------------------------------------
+#define MG_CUDA_TRY(call, what)                              \
+    do {                                                     \
+        cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) return cuda_fail(e_, what);   \
+    } while (0)
+
+static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+extern "C" int mg_rollout_host(MgHandle *h, const MgHostRolloutIO *io, int32_t n_steps, int32_t chunk, int32_t ring,
+                               int discrete, int normalized, void *stream) {
+    if (!h || !io) return fail(MG_E_INVALID, "mg_rollout_host: null argument");
+    if (n_steps < 1 || chunk < 1 || ring < 1) return fail(MG_E_INVALID, "mg_rollout_host: n_steps, chunk and ring must be >= 1");
+    if (chunk > n_steps) chunk = n_steps;
+    const int G = h->base.n_groups;
+    size_t in_off[MG_MAX_GROUPS], rew_off[MG_MAX_GROUPS], done_off[MG_MAX_GROUPS], act_row[MG_MAX_GROUPS];
+    size_t in_bytes = 0, out_bytes = 0;
+    for (int g = 0; g < G; ++g) {
+        const DevGroup &d = h->base.g[g];
+        if (discrete ? !io[g].dactions : !io[g].actions) return fail(MG_E_INVALID, "mg_rollout_host: null host actions");
+        if (!io[g].reward || !io[g].done) return fail(MG_E_INVALID, "mg_rollout_host: null host reward / done");
+        act_row[g] = discrete ? (size_t)d.n_envs * sizeof(int32_t) : (size_t)d.n_envs * d.n_act * sizeof(double);   // bytes per step
+        in_off[g] = in_bytes;
+        in_bytes += align256(act_row[g] * chunk);
+        rew_off[g] = out_bytes;
+        out_bytes += align256((size_t)d.n_envs * sizeof(double) * chunk);
+        done_off[g] = out_bytes;
+        out_bytes += align256((size_t)d.n_envs * chunk);
+    }
+    cudaStream_t cur = (cudaStream_t)stream;
+    if (!h->stage) {
+        HostStage *st = new (std::nothrow) HostStage();
+        if (!st) return fail(MG_E_INVALID, "mg_rollout_host: out of host memory");
+        h->stage = st;      // (released by mg_destroy, also when the set-up below stops half way)
+        MG_CUDA_TRY(cudaStreamCreateWithFlags(&st->s_in, cudaStreamNonBlocking), "mg_rollout_host: stream");
+        MG_CUDA_TRY(cudaStreamCreateWithFlags(&st->s_out, cudaStreamNonBlocking), "mg_rollout_host: stream");
+        for (int k = 0; k < 2; ++k) {
+            MG_CUDA_TRY(cudaEventCreateWithFlags(&st->uploaded[k], cudaEventDisableTiming), "mg_rollout_host: event");
+            MG_CUDA_TRY(cudaEventCreateWithFlags(&st->computed[k], cudaEventDisableTiming), "mg_rollout_host: event");
+            MG_CUDA_TRY(cudaEventCreateWithFlags(&st->drained[k], cudaEventDisableTiming), "mg_rollout_host: event");
+        }
+        MG_CUDA_TRY(cudaEventCreateWithFlags(&st->fence, cudaEventDisableTiming), "mg_rollout_host: event");
+    }
+    HostStage *st = h->stage;
+    if (in_bytes > st->in_cap || out_bytes > st->out_cap) {     // (re)allocate: nothing may still be using the old slots
+        MG_CUDA_TRY(cudaStreamSynchronize(st->s_in), "mg_rollout_host: sync");
+        MG_CUDA_TRY(cudaStreamSynchronize(st->s_out), "mg_rollout_host: sync");
+        if (st->fence_recorded) MG_CUDA_TRY(cudaEventSynchronize(st->fence), "mg_rollout_host: sync");
+        for (int k = 0; k < 2; ++k) {
+            if (st->in[k]) cudaFree(st->in[k]);
+            if (st->out[k]) cudaFree(st->out[k]);
+            st->in[k] = st->out[k] = nullptr;
+        }
+        st->in_cap = st->out_cap = 0;
+        for (int k = 0; k < 2; ++k) {
+            MG_CUDA_TRY(cudaMalloc((void **)&st->in[k], in_bytes), "mg_rollout_host: cudaMalloc (action staging)");
+            MG_CUDA_TRY(cudaMalloc((void **)&st->out[k], out_bytes), "mg_rollout_host: cudaMalloc (result staging)");
+        }
+        st->in_cap = in_bytes;
+        st->out_cap = out_bytes;
+    }
+    // Order this call after the previous one (whatever stream that ran on) and the copy streams after the caller's
+    // earlier work on `stream` (state loads, resets).
+    if (st->fence_recorded) MG_CUDA_TRY(cudaStreamWaitEvent(cur, st->fence, 0), "mg_rollout_host: wait");
+    MG_CUDA_TRY(cudaEventRecord(st->fence, cur), "mg_rollout_host: record");
+    MG_CUDA_TRY(cudaStreamWaitEvent(st->s_in, st->fence, 0), "mg_rollout_host: wait");
+    MG_CUDA_TRY(cudaStreamWaitEvent(st->s_out, st->fence, 0), "mg_rollout_host: wait");
+    const int mode = discrete ? MODE_DISCRETE : MODE_STEP;
+    MgRolloutIO rio[MG_MAX_GROUPS];
+    int c = 0;
+    for (int32_t s0 = 0; s0 < n_steps; s0 += chunk, ++c) {
+        const int slot = c & 1;
+        const int32_t n = n_steps - s0 < chunk ? n_steps - s0 : chunk;
+        // copy-in: this slot's previous reader (chunk c-2) must have finished
+        if (c >= 2) MG_CUDA_TRY(cudaStreamWaitEvent(st->s_in, st->computed[slot], 0), "mg_rollout_host: wait");
+        for (int g = 0; g < G; ++g) {
+            const char *src = discrete ? (const char *)io[g].dactions : (const char *)io[g].actions;
+            MG_CUDA_TRY(cudaMemcpyAsync(st->in[slot] + in_off[g], src + (size_t)s0 * act_row[g], (size_t)n * act_row[g],
+                                        cudaMemcpyHostToDevice, st->s_in), "mg_rollout_host: copy-in");
+        }
+        MG_CUDA_TRY(cudaEventRecord(st->uploaded[slot], st->s_in), "mg_rollout_host: record");
+        // compute: needs the actions, and the slot's previous results (chunk c-2) must have left the device
+        MG_CUDA_TRY(cudaStreamWaitEvent(cur, st->uploaded[slot], 0), "mg_rollout_host: wait");
+        if (c >= 2) MG_CUDA_TRY(cudaStreamWaitEvent(cur, st->drained[slot], 0), "mg_rollout_host: wait");
+        memset(rio, 0, sizeof rio);
+        for (int g = 0; g < G; ++g) {
+            if (discrete) rio[g].dactions = (const int32_t *)(st->in[slot] + in_off[g]);
+            else rio[g].actions = (const double *)(st->in[slot] + in_off[g]);
+            rio[g].obs_ring = (double *)io[g].obs_ring;
+            rio[g].reward = (double *)(st->out[slot] + rew_off[g]);
+            rio[g].done = (uint8_t *)(st->out[slot] + done_off[g]);
+            rio[g].flags = io[g].flags;
+        }
+        const int rc = launch_rollout(h, rio, n, ring, mode, normalized != 0, stream);
+        if (rc != MG_OK) return rc;
+        MG_CUDA_TRY(cudaEventRecord(st->computed[slot], cur), "mg_rollout_host: record");
+        // copy-out
+        MG_CUDA_TRY(cudaStreamWaitEvent(st->s_out, st->computed[slot], 0), "mg_rollout_host: wait");
+        for (int g = 0; g < G; ++g) {
+            const size_t n_envs = (size_t)h->base.g[g].n_envs;
+            MG_CUDA_TRY(cudaMemcpyAsync(io[g].reward + (size_t)s0 * n_envs, st->out[slot] + rew_off[g], (size_t)n * n_envs * sizeof(double),
+                                        cudaMemcpyDeviceToHost, st->s_out), "mg_rollout_host: copy-out");
+            MG_CUDA_TRY(cudaMemcpyAsync(io[g].done + (size_t)s0 * n_envs, st->out[slot] + done_off[g], (size_t)n * n_envs,
+                                        cudaMemcpyDeviceToHost, st->s_out), "mg_rollout_host: copy-out");
+        }
+        MG_CUDA_TRY(cudaEventRecord(st->drained[slot], st->s_out), "mg_rollout_host: record");
+    }
+    // the caller's stream completes only when the last results are in host memory
+    MG_CUDA_TRY(cudaStreamWaitEvent(cur, st->drained[(c - 1) & 1], 0), "mg_rollout_host: wait");
+    if (c >= 2) MG_CUDA_TRY(cudaStreamWaitEvent(cur, st->drained[c & 1], 0), "mg_rollout_host: wait");
+    MG_CUDA_TRY(cudaEventRecord(st->fence, cur), "mg_rollout_host: record");
+    st->fence_recorded = true;
+    return MG_OK;
 }

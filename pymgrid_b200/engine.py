@@ -18,7 +18,7 @@ import torch
 
 from . import _cabi
 from ._cabi import (MgForecastNoise, MG_ABI_VERSION, MG_MAX_GROUPS, MG_N_INFO, MG_OBS_CONTAINER, MG_OBS_GYM_SORTED, EngineError,
-                    MgConfig, MgLayout, MgPriorityList, MgRolloutIO, MgStepIO)
+                    MgConfig, MgHostRolloutIO, MgLayout, MgPriorityList, MgRolloutIO, MgStepIO)
 from .params import REWARD_SHAPERS, MicrogridParams
 from .priority_list import priority_lists
 
@@ -229,17 +229,24 @@ class HostRollout:
     `actions[g]`: pinned float64 [n_steps, n_g, n_act] (int32 [n_steps, n_g] when discrete), filled by the caller;
     `reward[g]` / `done[g]`: pinned [n_steps, n_g] float64 / uint8, valid after `sync()`.  Per step the same bytes cross
     the bus as in `HostIO.step()` (all actions in, reward + done out); observations go to a device ring of `ring`
-    buffers (`obs_ring[g]`, step s of a chunk in slot s % ring), where a policy or a logger would read them.
-    Device staging is double-buffered (2 x chunk steps of actions and results), whatever n_steps is.
+    buffers (`obs_ring[g]`; every chunk restarts at slot 0: step s of a chunk writes slot s % ring), where a policy or a
+    logger would read them.  Device staging is double-buffered (2 x chunk steps of actions and results), whatever
+    n_steps is.
 
-    Every cross-stream wait refers to an event recorded earlier in the same host thread, so the schedule cannot deadlock.
+    pipeline="native" (default): ONE C-ABI call, `mg_rollout_host`, which takes the host pointers and owns streams,
+    events and staging (include/pymgrid_b200.h) -- the entry point a binding without torch would use.
+    pipeline="torch": the same schedule built here from torch streams / events around `mg_rollout` (kept as the
+    cross-check of the native one; `run(n)` then needs n to end on a bound chunk length).
+    In both, every cross-stream wait refers to an event recorded earlier by the same host thread: no deadlock possible.
     """
 
-    def __init__(self, bm, n_steps, chunk=64, normalized=True, discrete=False, ring=4, keep_obs=True):
-        if n_steps < 1 or chunk < 1:
-            raise ValueError("n_steps and chunk must be positive")
-        self.bm, self.n_steps, self.chunk = bm, int(n_steps), int(min(chunk, n_steps))
-        self.discrete = discrete
+    def __init__(self, bm, n_steps, chunk=64, normalized=True, discrete=False, ring=4, keep_obs=True, pipeline="native"):
+        if n_steps < 1 or chunk < 1 or ring < 1:
+            raise ValueError("n_steps, chunk and ring must be positive")
+        if pipeline not in ("native", "torch"):
+            raise ValueError("pipeline must be 'native' or 'torch'")
+        self.bm, self.n_steps, self.chunk, self.ring = bm, int(n_steps), int(min(chunk, n_steps)), int(ring)
+        self.discrete, self.normalized, self.pipeline = bool(discrete), bool(normalized), pipeline
         dev, C = bm.device, self.chunk
         adt = torch.int32 if discrete else torch.float64
         ashape = (lambda g: (g.n_envs,)) if discrete else (lambda g: (g.n_envs, g.n_act))
@@ -248,6 +255,21 @@ class HostRollout:
         self.done = [torch.empty((self.n_steps, g.n_envs), dtype=torch.uint8, pin_memory=True) for g in bm.groups]
         self.obs_ring = [torch.empty((ring, g.n_envs, g.obs_dim), dtype=bm.obs_dtype, device=dev) if keep_obs else None
                          for g in bm.groups]
+        item = 4 if discrete else 8
+        self.h2d_bytes_per_step = sum(a[0].numel() * item for a in self.actions)
+        self.d2h_bytes_per_step = 9 * bm.n_envs
+        self._launch0 = bm.launch_count
+        if pipeline == "native":
+            self._io = (MgHostRolloutIO * len(bm.groups))()
+            for gi, g in enumerate(bm.groups):
+                io = self._io[gi]
+                if discrete:
+                    io.dactions = self.actions[gi].data_ptr()
+                else:
+                    io.actions = self.actions[gi].data_ptr()
+                io.reward, io.done = self.reward[gi].data_ptr(), self.done[gi].data_ptr()
+                io.obs_ring, io.flags = _ptr(self.obs_ring[gi]), _ptr(g.flags)
+            return
         self._d_act = [[torch.empty((C,) + ashape(g), dtype=adt, device=dev) for g in bm.groups] for _ in range(2)]
         self._d_rew = [[torch.empty((C, g.n_envs), dtype=torch.float64, device=dev) for g in bm.groups] for _ in range(2)]
         self._d_done = [[torch.empty((C, g.n_envs), dtype=torch.uint8, device=dev) for g in bm.groups] for _ in range(2)]
@@ -261,17 +283,24 @@ class HostRollout:
                 acts = [a[:n] for a in self._d_act[slot]]
                 self._launch[slot, n] = bm.rollout(acts if len(acts) > 1 else acts[0], normalized=normalized,
                                                    discrete=discrete, ring=ring, keep_obs=keep_obs, out=out, bind_only=True)
-        item = 4 if discrete else 8
-        self.h2d_bytes_per_step = sum(a[0].numel() * item for a in self.actions)
-        self.d2h_bytes_per_step = 9 * bm.n_envs
-        self.launches = 0
+
+    @property
+    def launches(self):
+        """kernel launches enqueued since this object was built (one per chunk)"""
+        return self.bm.launch_count - self._launch0
 
     def run(self, n_steps=None):
-        """Enqueue the whole rollout (asynchronous w.r.t. the host); results are complete after `sync()` or after any
-        later work on the current stream, which is made to wait for the last copy-out."""
+        """Enqueue the first n_steps (default: all) of the rollout, asynchronously w.r.t. the host; results are complete
+        after `sync()` or after any later work on the current stream, which is made to wait for the last copy-out."""
         T = self.n_steps if n_steps is None else int(n_steps)
         if not 1 <= T <= self.n_steps:
             raise ValueError(f"n_steps must be in [1, {self.n_steps}]")
+        if self.pipeline == "native":
+            bm = self.bm
+            rc = bm._lib.mg_rollout_host(bm._handle, self._io, T, self.chunk, self.ring, int(self.discrete),
+                                         int(self.normalized), bm._stream())
+            _cabi.check(rc, "mg_rollout_host")
+            return
         C, G = self.chunk, range(len(self.bm.groups))
         if (0, T % C or C) not in self._launch:
             raise ValueError(f"run({T}): a last chunk of {T % C} steps was not bound; use a multiple of chunk={C} or n_steps={self.n_steps}")
@@ -293,7 +322,6 @@ class HostRollout:
             if drained[slot] is not None:
                 cur.wait_event(drained[slot])              # this slot's previous results have left the device
             self._launch[slot, n]()
-            self.launches += 1
             computed[slot] = torch.cuda.Event()
             computed[slot].record(cur)
             with torch.cuda.stream(s_out):
@@ -308,6 +336,13 @@ class HostRollout:
 
     def sync(self):
         torch.cuda.current_stream(self.bm.device).synchronize()
+
+    def __del__(self):
+        # the native pipeline copies from / into the pinned buffers behind torch's back: drain before they are released
+        try:
+            torch.cuda.synchronize(self.bm.device)
+        except Exception:
+            pass
 
 
 class LogRecorder:

@@ -207,11 +207,13 @@ def test_host_io_graph_replay_equals_eager():
         assert torch.equal(ga.obs, gc.obs) and torch.equal(ga.charge, gc.charge)
 
 
+@pytest.mark.parametrize("pipeline", ["native", "torch"])
 @pytest.mark.parametrize("discrete", [False, True])
-def test_host_rollout_pipeline_equals_device_rollout(discrete):
-    """HostRollout.run(): actions in pinned host memory, chunks of 8 steps uploaded / computed / drained on three
-    streams (double-buffered staging, a shorter last chunk, two consecutive runs) == one mg_rollout over device-resident
-    actions, bit for bit: reward, done, final state and the last observation rows."""
+def test_host_rollout_pipeline_equals_device_rollout(discrete, pipeline):
+    """HostRollout.run() -- `mg_rollout_host` (native) or the same schedule built from torch streams: actions in pinned
+    host memory, chunks of 8 steps uploaded / computed / drained on three streams (double-buffered staging, a shorter
+    last chunk, two consecutive runs) == one mg_rollout over device-resident actions, bit for bit: reward, done, final
+    state and the last observation rows."""
     from pymgrid_b200.engine import BatchedMicrogrid
     scen = [n for n in range(25) if load_pymgrid25(n).grid is not None] if discrete else list(range(25))
     configs = [load_pymgrid25(n) for n in scen]
@@ -219,7 +221,7 @@ def test_host_rollout_pipeline_equals_device_rollout(discrete):
     a = BatchedMicrogrid(configs, env_config, device="cuda:0")
     b = BatchedMicrogrid(configs, env_config, device="cuda:0")
     T, ring = 45, 4
-    hr = a.host_rollout(T, chunk=8, discrete=discrete, ring=ring)
+    hr = a.host_rollout(T, chunk=8, discrete=discrete, ring=ring, pipeline=pipeline)
     assert hr.h2d_bytes_per_step == sum(g.n_envs * (4 if discrete else 8 * g.n_act) for g in a.groups)
     gen = torch.Generator().manual_seed(11)
     for rep in range(2):
@@ -240,8 +242,22 @@ def test_host_rollout_pipeline_equals_device_rollout(discrete):
             # the last chunk (steps 40..44) restarts the ring at slot 0: its last row sits in slot (T - 40 - 1) % ring
             assert torch.equal(hr.obs_ring[gi][(T - 40 - 1) % ring], out[gi]["obs_ring"][(T - 1) % ring])
     assert hr.launches == 2 * 6
-    with pytest.raises(ValueError):
-        hr.run(44)          # 44 = 5 x 8 + 4: a last chunk of 4 steps was never bound
+    if pipeline == "torch":
+        with pytest.raises(ValueError):
+            hr.run(44)          # 44 = 5 x 8 + 4: a last chunk of 4 steps was never bound
+    else:                       # the native entry takes any prefix: 3 more steps, compared with 3 single steps
+        hr.run(3)
+        hr.sync()
+        for k in range(3):
+            acts = [x[k].cuda() for x in hr.actions]
+            if discrete:
+                _, reward, done, _ = b.step_discrete(acts)
+            else:
+                _, reward, done, _ = b.step(acts)
+            for gi in range(len(a.groups)):
+                assert torch.equal(hr.reward[gi][k], reward[gi].cpu()) and torch.equal(hr.done[gi][k], done[gi].cpu())
+        for ga, gb in zip(a.groups, b.groups):
+            assert torch.equal(ga.charge, gb.charge) and torch.equal(ga.step, gb.step)
 
 
 def test_reward_shaping_func_drop_in(golden):
