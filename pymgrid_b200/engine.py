@@ -467,8 +467,14 @@ class BatchedMicrogrid:
         names = {p.renewable_name for p in self.configs}
         if len(names) != 1:
             raise ValueError("all configs must name the renewable module the same way")
-        if obs_order == "gym_sorted" and names == {"PV"}:
-            obs_order = "gym_sorted_pv_first"
+        if obs_order == "gym_sorted":
+            # gym.spaces.Dict sorts the module names: a renewable called 'PV' (MicrogridGenerator) comes before 'battery',
+            # one called 'pv' / 'renewable' after 'load'; other positions have no row layout in the kernel
+            name = next(iter(names))
+            if name < "battery":
+                obs_order = "gym_sorted_pv_first"
+            elif not name > "load":
+                raise NotImplementedError(f"renewable module name {name!r} sorts between 'battery' and 'load': use obs_order='container'")
         status = None
         if any(p.grid is not None and p.grid.status is not None for p in self.configs):
             status = [None if p.grid is None else (p.grid.status if p.grid.status is not None else p.grid.time_series[:, 3])

@@ -58,8 +58,24 @@ class Discrete:
 class _BaseEnv:
     """Shared plumbing: one architecture (all envs share obs / action layout), B replicas or B heterogeneous configs."""
 
-    def __init__(self, configs, env_config=None, batch=None, device=None, obs_order="gym_sorted", with_info=False):
-        configs = list(configs) if isinstance(configs, (list, tuple)) else [configs]
+    def __init__(self, configs, env_config=None, batch=None, device=None, obs_order="gym_sorted", with_info=False,
+                 add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2., reward_shaping_func=None,
+                 trajectory_func=None):
+        """`configs`: one MicrogridParams, a list of them, or -- the reference's call, BaseMicrogridEnv(modules,
+        add_unbalanced_module, loss_load_cost, overgeneration_cost, reward_shaping_func, trajectory_func)
+        (envs/base/base.py:84-110) -- a list of `pymgrid_b200.modules` objects / (name, module) tuples."""
+        from .params import MicrogridParams
+        if isinstance(configs, MicrogridParams):
+            configs = [configs]
+        else:
+            configs = list(configs)
+            if not all(isinstance(c, MicrogridParams) for c in configs):
+                from .modules import params_from_modules
+                configs = [params_from_modules(configs, add_unbalanced_module, loss_load_cost, overgeneration_cost)]
+        if reward_shaping_func is not None:
+            import dataclasses
+            name = reward_shaping_func if isinstance(reward_shaping_func, str) else type(reward_shaping_func).__name__
+            configs = [dataclasses.replace(c, reward_shaper=name) for c in configs]
         self.single = batch is None and env_config is None
         if env_config is None:
             env_config = np.arange(1 if batch is None else batch) % len(configs)
@@ -73,6 +89,9 @@ class _BaseEnv:
         self.n_envs = self.engine.n_envs
         self.observation_space = Box(0.0, 1.0, (self.group.obs_dim,))     # base.py:161-163
         self._obs_order = obs_order
+        if trajectory_func is not None and not callable(trajectory_func):
+            raise TypeError('trajectory_func must be callable.')             # microgrid.py:171-172
+        self.trajectory_func = trajectory_func
 
     @classmethod
     def from_scenario(cls, microgrid_number=0, batch=None, **kw):
@@ -92,7 +111,8 @@ class _BaseEnv:
         from .microgrid import ModuleContainerView, ModuleView
         names = ["load", "pv", "unbalanced_energy"] + (["genset"] if self.params.has_genset else []) + ["battery"] + \
                 (["grid"] if self.params.has_grid else [])
-        return ModuleContainerView((n, [ModuleView(self, n)]) for n in names)
+        ren = self.params.renewable_name
+        return ModuleContainerView((ren if n == "pv" else n, [ModuleView(self, n, ren if n == "pv" else n)]) for n in names)
 
     def _state(self):     # live state of env 0, for the module views
         g = self.group
@@ -113,8 +133,28 @@ class _BaseEnv:
 
     def reset(self, mask=None):
         """reference: BaseMicrogridEnv.reset (base.py:165-167): flat observation after Microgrid.reset."""
+        if self.trajectory_func is not None:      # microgrid.py:221-225: a new episode window per reset
+            self._draw_windows(mask)
         obs = self.engine.reset(mask=mask)
         return obs[0].cpu().numpy() if self.single else obs
+
+    def _draw_windows(self, mask):
+        """One (initial_step, final_step) pair per env that is being reset, from `trajectory_func(initial, final)`; the
+        vectorised trajectory classes of pymgrid_b200.trajectory draw all of them in one call (`n=`)."""
+        lo, hi, n = self.params.initial_step, self.params.final_step, self.n_envs
+        try:
+            initial, final = self.trajectory_func(lo, hi, n=n)
+        except TypeError:                          # a plain reference-style callable: one call per env
+            pairs = [self.trajectory_func(lo, hi) for _ in range(n)]
+            initial, final = np.array([p[0] for p in pairs]), np.array([p[1] for p in pairs])
+        initial, final = np.asarray(initial, dtype=np.int32).reshape(n), np.asarray(final, dtype=np.int32).reshape(n)
+        if (initial < lo).any() or (final > hi).any() or (initial >= final).any():
+            raise ValueError(f"trajectory_func returned a window outside [{lo}, {hi}] or an empty one")   # microgrid.py:184-197
+        if mask is not None and getattr(self, "_windows", None) is not None:     # envs that keep running keep their window
+            keep = ~np.asarray(mask.cpu() if hasattr(mask, "cpu") else mask, dtype=bool).reshape(n)
+            initial[keep], final[keep] = self._windows[0][keep], self._windows[1][keep]
+        self._windows = (initial, final)
+        self.engine.set_trajectories(initial, final)
 
     def _finish(self, res):
         obs, reward, done, info = res

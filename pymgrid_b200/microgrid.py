@@ -24,8 +24,10 @@ class ModuleView:
     """Read-only view of one module: constructor parameters + the live state the reference's callers read
     (max_production, max_consumption, soc, current_status, ...)."""
 
-    def __init__(self, microgrid, name):
-        self._m, self.name = microgrid, (name, 0)
+    def __init__(self, microgrid, kind, name=None):
+        # kind: the engine's module key (load, pv, unbalanced_energy, genset, battery, grid); name: what the caller
+        # called it -- only the renewable can be renamed (('pv', module) in pymgrid25, 'renewable' by default)
+        self._m, self._kind, self.name = microgrid, kind, (name or kind, 0)
 
     def __repr__(self):
         return f"ModuleView({self.name[0]})"
@@ -40,8 +42,8 @@ class ModuleView:
 
     # -- battery (battery_module.py:283-291) --
     def _require(self, kind):
-        if self.name[0] != kind:
-            raise AttributeError(f"{self.name[0]} module has no such attribute")
+        if self._kind != kind:
+            raise AttributeError(f"{self._kind} module has no such attribute")
 
     @property
     def current_charge(self):
@@ -54,7 +56,7 @@ class ModuleView:
 
     @property
     def max_production(self):
-        n, p, st = self.name[0], self._p, self._m._state()
+        n, p, st = self._kind, self._p, self._m._state()
         if n == "battery":
             b = p.battery
             return min(b.max_discharge, st["charge"] - b.min_capacity) * b.efficiency
@@ -70,7 +72,7 @@ class ModuleView:
 
     @property
     def max_consumption(self):
-        n, p, st = self.name[0], self._p, self._m._state()
+        n, p, st = self._kind, self._p, self._m._state()
         if n == "battery":
             b = p.battery
             return min(b.max_charge, b.max_capacity - st["charge"]) / b.efficiency
@@ -84,15 +86,15 @@ class ModuleView:
 
     @property
     def min_production(self):
-        if self.name[0] == "genset":
+        if self._kind == "genset":
             return self._m._state()["genset"][0] * self._p.genset.running_min_production
         return 0
 
     @property
     def current_status(self):
-        if self.name[0] == "genset":
+        if self._kind == "genset":
             return self._m._state()["genset"][0]
-        if self.name[0] == "grid":
+        if self._kind == "grid":
             return self._p.grid.time_series[self._m.current_step, 3]
         raise AttributeError("current_status")
 
@@ -105,28 +107,28 @@ class ModuleView:
     @property
     def module_type(self):
         """(class tag, dispatch type) like the reference's class attribute, e.g. ('load', 'fixed')"""
-        tag = {"pv": "renewable", "unbalanced_energy": "balancing"}.get(self.name[0], self.name[0])
-        return (tag, {"load": "fixed", "pv": "flex", "unbalanced_energy": "flex"}.get(self.name[0], "controllable"))
+        tag = {"pv": "renewable", "unbalanced_energy": "balancing"}.get(self._kind, self._kind)
+        return (tag, {"load": "fixed", "pv": "flex", "unbalanced_energy": "flex"}.get(self._kind, "controllable"))
 
     @property
     def is_source(self):
-        return self.name[0] != "load"
+        return self._kind != "load"
 
     @property
     def is_sink(self):
-        return self.name[0] in ("load", "battery", "grid", "unbalanced_energy")
+        return self._kind in ("load", "battery", "grid", "unbalanced_energy")
 
     @property
     def action_space(self):
         """only `.shape` is read by the reference's callers (priority_list.py:27-33)"""
         from types import SimpleNamespace
-        n = {"genset": 2, "battery": 1, "grid": 1, "pv": 1, "unbalanced_energy": 1}.get(self.name[0], 0)
+        n = {"genset": 2, "battery": 1, "grid": 1, "pv": 1, "unbalanced_energy": 1}.get(self._kind, 0)
         return SimpleNamespace(shape=(n,))
 
     # -- costs (base_module.py:651-670 and the per-module overrides) --
     @property
     def production_marginal_cost(self):
-        n, p = self.name[0], self._p
+        n, p = self._kind, self._p
         if n == "battery":
             return p.battery.battery_cost_cycle                           # battery_module.py:340-342
         if n == "genset":                                                 # genset_module.py:519-521: get_cost(1.0)
@@ -139,7 +141,7 @@ class ModuleView:
 
     @property
     def absorption_marginal_cost(self):
-        n, p = self.name[0], self._p
+        n, p = self._kind, self._p
         if n == "battery":
             return p.battery.battery_cost_cycle
         if n == "grid":
@@ -169,7 +171,7 @@ class ModuleView:
     # -- state vectors (BaseMicrogridModule.state / state_dict, base_module.py:535-560) --
     def state_dict(self, normalized=False):
         st = self._m._state()
-        d = views.state_dict(self._p, st["t"], st["charge"], st["genset"])[self.name[0]]
+        d = views.state_dict(self._p, st["t"], st["charge"], st["genset"])[self._kind]
         if normalized:
             return OrderedDict(zip(d.keys(), self.to_normalized(np.array(list(d.values()), dtype=np.float64), obs=True)))
         return d
@@ -195,7 +197,7 @@ class ModuleView:
         return self._bounds("act")[1]
 
     def _bounds(self, which):
-        n, p, rows = self.name[0], self._p, 1 + self._p.forecast_horizon
+        n, p, rows = self._kind, self._p, 1 + self._p.forecast_horizon
         if n == "battery":      # battery_module.py:323-338
             b = p.battery
             return ((np.array([b.min_soc, b.min_capacity]), np.array([1.0, b.max_capacity])) if which == "obs"
@@ -262,17 +264,17 @@ class ModuleView:
         return 1.0
 
     def __getattr__(self, item):   # constructor parameters, e.g. battery.max_capacity, genset.genset_cost, grid.max_import
-        src = {"battery": self._p.battery, "genset": self._p.genset, "grid": self._p.grid}.get(self.name[0])
+        src = {"battery": self._p.battery, "genset": self._p.genset, "grid": self._p.grid}.get(self._kind)
         if src is not None and hasattr(src, item) and not item.startswith("_"):
             return getattr(src, item)
         if item == "time_series":
             return {"load": self._p.load_ts.reshape(-1, 1) * self._p.load_scale,
-                    "pv": self._p.pv_ts.reshape(-1, 1) * self._p.pv_scale}[self.name[0]]
-        if item == "forecast_horizon" and self.name[0] in ("load", "pv", "grid"):
+                    "pv": self._p.pv_ts.reshape(-1, 1) * self._p.pv_scale}[self._kind]
+        if item == "forecast_horizon" and self._kind in ("load", "pv", "grid"):
             return self._p.forecast_horizon
         if item in ("initial_step", "final_step"):
             return getattr(self._m, item)
-        if item in ("loss_load_cost", "overgeneration_cost") and self.name[0] == "unbalanced_energy":
+        if item in ("loss_load_cost", "overgeneration_cost") and self._kind == "unbalanced_energy":
             return getattr(self._p, item)
         raise AttributeError(item)
 
@@ -315,12 +317,23 @@ class ModuleContainerView(OrderedDict):
 
 
 class Microgrid:
-    def __init__(self, params: MicrogridParams, device=None, obs_order="gym_sorted", reward_shaping_func=None):
-        """`reward_shaping_func` (reference: Microgrid.__init__, microgrid.py:100-106): None, "pv_curtailment" /
-        "battery_discharge", or an object of the reference's PVCurtailmentShaper / BatteryDischargeShaper classes (matched
-        by class name); arbitrary Python callables cannot run inside the kernel and are rejected."""
-        if not isinstance(params, MicrogridParams):
-            raise TypeError("pymgrid_b200.Microgrid is built from MicrogridParams (see scenario.load_pymgrid25 / params.py)")
+    def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2.,
+                 reward_shaping_func=None, trajectory_func=None, device=None, obs_order="gym_sorted"):
+        """The reference's constructor (microgrid/microgrid.py:100-128):
+
+        `modules`: list of `pymgrid_b200.modules` objects or `(name, module)` tuples, as in the reference -- or a ready
+        `MicrogridParams` record (scenario readers; then the three arguments after it are not used).
+        `reward_shaping_func`: None, "pv_curtailment" / "battery_discharge", or an object of the reference's
+        PVCurtailmentShaper / BatteryDischargeShaper classes (matched by class name); arbitrary Python callables cannot
+        run inside the kernel and are rejected.
+        `trajectory_func(initial_step, final_step) -> (initial, final)`: called on every `reset()` (microgrid.py:221-225),
+        validated like `_check_trajectory_func` (:167-199).
+        `device`, `obs_order`: engine options (not in the reference)."""
+        if isinstance(modules, MicrogridParams):
+            params = modules
+        else:
+            from .modules import params_from_modules
+            params = params_from_modules(modules, add_unbalanced_module, loss_load_cost, overgeneration_cost)
         if reward_shaping_func is not None:
             import dataclasses
             name = reward_shaping_func if isinstance(reward_shaping_func, str) else type(reward_shaping_func).__name__
@@ -333,10 +346,50 @@ class Microgrid:
         self._actions = torch.zeros((1, params.n_act), dtype=torch.float64, device=self._engine.device)
         self._log_rows = []
         self._initial_step, self._final_step = params.initial_step, params.final_step
-        self.raise_errors = False
+        self.raise_errors = bool(params.meta.get("raise_errors", False))
         names = ["load", "pv", "unbalanced_energy"] + (["genset"] if params.has_genset else []) + ["battery"] + \
                 (["grid"] if params.has_grid else [])
-        self._modules = ModuleContainerView((n, [ModuleView(self, n)]) for n in names)
+        self._modules = ModuleContainerView((self._ren if n == "pv" else n, [ModuleView(self, n, self._ren if n == "pv" else n)])
+                                            for n in names)
+        self.trajectory_func = self._check_trajectory_func(trajectory_func)
+
+    @property
+    def _ren(self):
+        """the caller's name of the renewable module ('pv' in pymgrid25, 'PV' in MicrogridGenerator grids, 'renewable' by default)"""
+        return self.params.renewable_name
+
+    def _check_trajectory_func(self, trajectory_func):
+        """reference: Microgrid._check_trajectory_func (microgrid.py:167-199), same errors."""
+        if trajectory_func is None:
+            return trajectory_func
+        if not callable(trajectory_func):
+            raise TypeError('trajectory_func must be callable.')
+        output = trajectory_func(self._initial_step, self._final_step)
+        try:
+            initial_step, final_step = output
+            if not (isinstance(initial_step, int) and isinstance(final_step, int)):
+                raise ValueError
+        except (TypeError, ValueError):
+            raise TypeError(f'trajectory func must return two integer values, not {output}')
+        if initial_step < self._initial_step:
+            raise ValueError(f'trajectory_func returned initial_step value ({initial_step}) less than env\'s initial '
+                             f'step: ({self._initial_step})')
+        if final_step > self._final_step:
+            raise ValueError(f'trajectory_func returned final_step value ({final_step}) greater than env\'s final step:'
+                             f' ({self._final_step})')
+        if initial_step >= final_step:
+            raise ValueError(f'trajectory_func returned values ({initial_step}, {final_step}) such that initial_step'
+                             f'was greater than or equal to final_step.')
+        return trajectory_func
+
+    def _named(self, d):
+        """engine key 'pv' -> the caller's name of the renewable module, for dicts keyed by module name or by
+        (module name, number, field)"""
+        if self._ren == "pv":
+            return d
+        ren = self._ren
+        return type(d)(((ren if k == "pv" else (ren,) + k[1:] if isinstance(k, tuple) and k[0] == "pv" else k), v)
+                       for k, v in d.items())
 
     # ---- construction ------------------------------------------------------------------------------------
     @classmethod
@@ -388,7 +441,7 @@ class Microgrid:
 
     @property
     def flex(self):
-        return self._typed(("pv", "unbalanced_energy"))
+        return self._typed((self._ren, "unbalanced_energy"))
 
     @property
     def controllable(self):
@@ -409,10 +462,10 @@ class Microgrid:
         obs_row, info_row = obs[0].cpu().numpy(), info[0].cpu().numpy()
         r = float(reward[0].item())
         post = self._state()
-        self._log_rows.append(views.log_row(p, views.state_dict(p, pre["t"], pre["charge"], pre["genset"]), info_row, r,
-                                            post["genset"]))
-        return (views.obs_row_to_dict(obs_row, p, self._obs_order), r, bool(done[0].item()),
-                views.info_row_to_dict(info_row, flags, p))
+        self._log_rows.append(self._named(views.log_row(p, views.state_dict(p, pre["t"], pre["charge"], pre["genset"]),
+                                                        info_row, r, post["genset"])))
+        return (self._named(views.obs_row_to_dict(obs_row, p, self._obs_order)), r, bool(done[0].item()),
+                self._named(views.info_row_to_dict(info_row, flags, p)))
 
     def _raise_for_flags(self, flags):
         err = flags & FLAG_ERROR_MASK
@@ -427,9 +480,12 @@ class Microgrid:
 
     def reset(self):
         """reference: Microgrid.reset (microgrid.py:205-225): step = initial_step, logs flushed, battery / genset kept."""
+        if self.trajectory_func is not None:      # microgrid.py:221-225: the modules' window, not the microgrid's own bounds
+            initial_step, final_step = self.trajectory_func(self._initial_step, self._final_step)
+            self._engine.set_trajectories(np.array([initial_step]), np.array([final_step]))
         obs = self._engine.reset()
         self._log_rows = []
-        out = views.obs_row_to_dict(obs[0].cpu().numpy(), self.params, self._obs_order)
+        out = self._named(views.obs_row_to_dict(obs[0].cpu().numpy(), self.params, self._obs_order))
         out["balance"], out["other"] = {}, {}
         return out
 
@@ -486,13 +542,13 @@ class Microgrid:
     def state_dict(self, normalized=False):
         st = self._state()
         sd = views.state_dict(self.params, st["t"], st["charge"], st["genset"])
-        return {name: [dict(d)] for name, d in sd.items()}
+        return {name: [dict(d)] for name, d in self._named(sd).items()}
 
     def state_series(self, normalized=False):
         import pandas as pd
         st = self._state()
         sd = views.state_dict(self.params, st["t"], st["charge"], st["genset"])
-        data = OrderedDict(((name, 0, k), v) for name, d in sd.items() for k, v in d.items())
+        data = OrderedDict(((name, 0, k), v) for name, d in self._named(sd).items() for k, v in d.items())
         return pd.Series(data)
 
     def get_log(self, as_frame=True, drop_singleton_key=False):

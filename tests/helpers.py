@@ -113,3 +113,31 @@ def engine_noisy_row(clean, p, order, sigma, increase, env, t, seed, call, serie
             s = s * (1.0 + np.log(1.0 + k))
         out[off] = min(max(out[off] + z[f] * s, 0.0), 1.0)
     return out
+
+
+def custom_modules(golden_custom, i, ns=None, renewable_name="pv"):
+    """Custom grid i of tests/golden/custom.npz as a list of reference-style MODULES, built with the very keyword arguments
+    make_golden.build_custom hands to the reference's constructors.  `ns`: the namespace providing the classes
+    (pymgrid_b200.modules by default; pymgrid.modules for a live cross-check)."""
+    if ns is None:
+        from pymgrid_b200 import modules as ns
+    z = golden_custom
+    U, D, abort, init, H, final_step, eff, weak, has_gen, has_grid = z[f"c{i}_spec"]
+    fc = "oracle" if H > 0 else None
+    Hc = int(H) if H > 0 else 23
+    pv = ns.RenewableModule(time_series=z["pv"], forecaster=fc, forecast_horizon=Hc, final_step=int(final_step))
+    mods = [ns.LoadModule(time_series=z["load"], forecaster=fc, forecast_horizon=Hc, final_step=int(final_step)),
+            (renewable_name, pv) if renewable_name else pv]
+    if has_gen:
+        mods.append(ns.GensetModule(running_min_production=10, running_max_production=50, genset_cost=0.5, co2_per_unit=1.5,
+                                    cost_per_unit_co2=0.2, start_up_time=int(U), wind_down_time=int(D),
+                                    allow_abortion=bool(abort), init_start_up=bool(init)))
+    mods.append(ns.BatteryModule(min_capacity=10, max_capacity=100, max_charge=40, max_discharge=45, efficiency=float(eff),
+                                 battery_cost_cycle=0.05, init_soc=0.6))
+    if has_grid:
+        ts = z["grid_ts"].copy()
+        if not weak:
+            ts[:, 3] = 1.0
+        mods.append(ns.GridModule(max_import=70, max_export=30, time_series=ts, forecaster=fc, forecast_horizon=Hc,
+                                  final_step=int(final_step), cost_per_unit_co2=0.15))
+    return mods

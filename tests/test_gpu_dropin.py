@@ -260,6 +260,92 @@ def test_host_rollout_pipeline_equals_device_rollout(discrete, pipeline):
             assert torch.equal(ga.charge, gb.charge) and torch.equal(ga.step, gb.step)
 
 
+@pytest.mark.parametrize("i", (0, 2, 4))
+def test_microgrid_from_reference_style_modules(golden, i):
+    """Microgrid([LoadModule(...), ("pv", RenewableModule(...)), ...], loss_load_cost=..., overgeneration_cost=...) -- the
+    reference's constructor call (microgrid/microgrid.py:100-128) with `pymgrid_b200.modules` classes -- reproduces what the
+    reference returned for the same constructor arguments (tests/golden/custom.npz), bit for bit."""
+    import warnings
+    from pymgrid_b200 import Microgrid
+    from tests.helpers import custom_modules
+    z = golden["custom"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = Microgrid(custom_modules(z, i), loss_load_cost=9.0, overgeneration_cost=1.5)
+    flat = lambda obs: np.concatenate([obs[name][0] for name in SORTED if name in obs])   # noqa: E731
+    np.testing.assert_array_equal(flat(m.reset()), z[f"c{i}_reset_obs"])
+    for k, a in enumerate(z[f"c{i}_a"]):
+        obs, reward, done, info = m.run(control(m.params, a))
+        np.testing.assert_array_equal(flat(obs), z[f"c{i}_o"][k])
+        assert reward == z[f"c{i}_r"][k] and done == bool(z[f"c{i}_d"][k])
+        assert info["pv"][0]["provided_energy"] == z[f"c{i}_i"][k][1] and info["pv"][0]["curtailment"] == z[f"c{i}_i"][k][2]
+    np.testing.assert_array_equal(flat(m.reset()), z[f"c{i}_after_reset_obs"])
+
+
+def test_default_module_names_and_trajectory_func(golden):
+    """An un-named RenewableModule is called 'renewable' in observations, info, log and `modules` (renewable_module.py:84);
+    trajectory_func is validated at construction and applied on every reset (microgrid.py:167-225)."""
+    from pymgrid_b200 import Microgrid
+    from tests.helpers import custom_modules
+    z = golden["custom"]
+    calls = []
+
+    def window(initial_step, final_step):
+        calls.append((initial_step, final_step))
+        return 10, 14
+
+    m = Microgrid(custom_modules(z, 4, renewable_name=None), loss_load_cost=9.0, overgeneration_cost=1.5, trajectory_func=window)
+    assert calls == [(0, 60)] and m.initial_step == 0 and m.final_step == 60
+    obs = m.reset()
+    assert m.current_step == 10 and "renewable" in obs and "pv" not in obs
+    assert list(m.modules) == ["load", "renewable", "unbalanced_energy", "battery", "grid"]
+    assert m.modules.renewable[0].name == ("renewable", 0) and list(m.flex) == ["renewable", "unbalanced_energy"]
+    dones = []
+    for k in range(4):
+        obs, _, done, info = m.run({"battery": [0.5], "grid": [0.5]})
+        dones.append(done)
+        assert "renewable" in obs and "renewable" in info and "pv" not in info
+    assert dones == [False, False, False, True] and m.current_step == 14       # episode length = final - initial
+    df = m.get_log()
+    assert "renewable" in df.columns.get_level_values(0) and "pv" not in df.columns.get_level_values(0)
+    assert ("renewable", 0, "renewable_used") in df.columns and len(df) == 4
+    assert ("renewable", 0, "renewable_current") in m.state_series().index
+    for bad, exc in ((lambda a, b: (0.5, 3), TypeError), (lambda a, b: (-1, 5), ValueError), (lambda a, b: (0, 61), ValueError),
+                     (lambda a, b: (7, 7), ValueError), ("not callable", TypeError)):
+        with pytest.raises(exc):
+            Microgrid(custom_modules(z, 4), trajectory_func=bad)
+
+
+def test_env_from_modules_with_trajectory_func(golden):
+    """DiscreteMicrogridEnv(modules, ..., trajectory_func=...) -- the reference's env constructor (envs/base/base.py:84-110):
+    every reset draws a new episode window per env (microgrid.py:221-225); episode length = final - initial."""
+    import warnings
+    from pymgrid_b200.envs import DiscreteMicrogridEnv
+    from pymgrid_b200.trajectory import FixedLengthStochasticTrajectory
+    from tests.helpers import custom_modules
+    z = golden["custom"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = DiscreteMicrogridEnv(custom_modules(z, 0), batch=64, loss_load_cost=9.0, overgeneration_cost=1.5,
+                                   trajectory_func=FixedLengthStochasticTrajectory(5))
+        single = DiscreteMicrogridEnv(custom_modules(z, 0), loss_load_cost=9.0, overgeneration_cost=1.5,
+                                      trajectory_func=lambda a, b: (7, 10))
+    assert env.params.loss_load_cost == 9.0 and env.action_space.n == single.action_space.n == 12
+    for episode in range(2):
+        env.reset()
+        start = env.current_step.cpu().numpy().copy()
+        assert ((start >= 0) & (start <= 55)).all() and len(set(start.tolist())) > 1
+        for k in range(5):
+            _, _, done, _ = env.step(env.sample_action())
+            assert bool(done.all()) == (k == 4) and (k == 4 or not bool(done.any()))
+        np.testing.assert_array_equal(env.current_step.cpu().numpy(), start + 5)
+    single.reset()
+    assert single.current_step == 7
+    assert [single.step(0)[2] for _ in range(3)] == [False, False, True]
+    with pytest.raises(ValueError):
+        DiscreteMicrogridEnv(custom_modules(z, 0), trajectory_func=lambda a, b: (0, 61)).reset()
+
+
 def test_reward_shaping_func_drop_in(golden):
     """Microgrid(reward_shaping_func=...) like the reference (microgrid.py:100-124): run returns the shaped reward, the
     balance log keeps reward and shaped_reward, and the shaper's assert surfaces as AssertionError on the same step."""
