@@ -467,6 +467,39 @@ class Microgrid:
         return (self._named(views.obs_row_to_dict(obs_row, p, self._obs_order)), r, bool(done[0].item()),
                 self._named(views.info_row_to_dict(info_row, flags, p)))
 
+    def run_priority_list(self, action_index, n_steps):
+        """`n_steps` consecutive DiscreteMicrogridEnv-style steps with the same priority list (index into
+        `engine.action_tables[0]`): what RuleBasedControl.run does every step (algos/rbc/rbc.py:87-91 ->
+        priority_list.py:69-116 -> Microgrid.run(normalized=False)), expanded on the device.  The log rows of the whole
+        episode are gathered on the device and brought back with ONE device->host copy, so a year costs seconds, not
+        minutes.  Returns the number of steps taken (stops after the step that reports done)."""
+        p, g = self.params, self._g
+        t0 = self.current_step
+        windows = (g.env_final_step is not None)
+        final = int(g.env_final_step[0].item()) if windows else self._final_step
+        n = max(0, min(int(n_steps), final - t0 if final - 1 >= t0 else 1, len(p) - t0))
+        if n == 0:
+            if n_steps > 0:
+                raise IndexError(f"index {t0} is out of bounds for axis 0 with size {len(p)}")   # load_module.py:111
+            return 0
+        act = torch.full((1,), int(action_index), dtype=torch.int32, device=self._engine.device)
+        pre_t, pre_charge, pre_gen, post_gen, infos, rewards, flags = [], [], [], [], [], [], []
+        zero = torch.zeros(1, dtype=torch.int32, device=self._engine.device)
+        gen = (lambda: g.genset.clone()) if g.genset is not None else (lambda: zero)
+        for _ in range(n):
+            pre_t.append(g.step.clone()); pre_charge.append(g.charge.clone()); pre_gen.append(gen())
+            _, reward, _, info = self._engine.step_discrete(act, obs=False)
+            infos.append(info.clone()); rewards.append(reward.clone()); post_gen.append(gen()); flags.append(g.flags.clone())
+        host = lambda xs: torch.cat(xs).cpu().numpy()      # noqa: E731  (one device->host copy per column)
+        pre_t, pre_charge, pre_gen, post_gen = host(pre_t), host(pre_charge), host(pre_gen), host(post_gen)
+        infos, rewards, flags = torch.stack(infos).cpu().numpy()[:, 0], host(rewards), host(flags)
+        unpack = lambda w: (int(w) & 0xff, (int(w) >> 8) & 0xff, (int(w) >> 16) & 0xff, (int(w) >> 24) & 0xff)   # noqa: E731
+        for k in range(n):
+            self._raise_for_flags(int(flags[k]) & 0xffffffff)
+            state = views.state_dict(p, int(pre_t[k]), float(pre_charge[k]), unpack(pre_gen[k]))
+            self._log_rows.append(self._named(views.log_row(p, state, infos[k], float(rewards[k]), unpack(post_gen[k]))))
+        return n
+
     def _raise_for_flags(self, flags):
         err = flags & FLAG_ERROR_MASK
         if err:

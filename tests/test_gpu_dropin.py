@@ -346,6 +346,46 @@ def test_env_from_modules_with_trajectory_func(golden):
         DiscreteMicrogridEnv(custom_modules(z, 0), trajectory_func=lambda a, b: (0, 61)).reset()
 
 
+@pytest.mark.parametrize("n", (0, 1, 2, 5))
+def test_rule_based_control_class(golden, n):
+    """pymgrid_b200.algos.RuleBasedControl(microgrid).run(max_steps) -- the reference's class (algos/rbc/rbc.py:7-140): the
+    automatically chosen priority list, the per-step balance reward of the returned log and the final state match what
+    the live reference produced (tests/golden/rbc.npz); the log has the reference's columns."""
+    from pymgrid_b200 import Microgrid
+    from pymgrid_b200.algos import PriorityListElement, RuleBasedControl
+    z = golden["rbc"]
+    m = Microgrid.from_scenario(n)
+    rbc = RuleBasedControl(m)
+    names = {"genset": 0, "battery": 1, "grid": 2}
+    assert [names[el.module[0]] for el in rbc.priority_list] == list(z[f"s{n}_list_mod"])
+    assert [el.action for el in rbc.priority_list] == list(z[f"s{n}_list_act"])
+    assert all(isinstance(el, PriorityListElement) and el.marginal_cost is not None for el in rbc.priority_list)
+    assert rbc.priority_list == sorted(rbc.get_priority_lists()[0])
+    df = rbc.run(max_steps=300)
+    assert len(df) == 300 and m.current_step == 0 and rbc.microgrid.current_step == 300      # works on a copy (rbc.py:30)
+    np.testing.assert_array_equal(df[("balance", 0, "reward")].values, z[f"s{n}_rewards"][:300])
+    if n != 0:      # (scenario 0 was recorded over the whole year)
+        st = rbc.microgrid._state()
+        np.testing.assert_array_equal(np.array([st["t"], st["charge"], *st["genset"]], dtype=np.float64), z[f"s{n}_final_state"])
+    assert ("load", 0, "load_met") in df.columns and ("battery", 0, "soc") in df.columns
+    again = rbc.run(max_steps=5)                   # run() resets first: the log restarts, battery / genset state carries on
+    assert len(again) == 5 and again.index[0] == 0
+    with pytest.raises(ValueError, match="Invalid priority list"):
+        RuleBasedControl(m, priority_list=[PriorityListElement(("battery", 0), 1, 0, 0.0)] * 2)
+    lists = rbc.get_priority_lists()
+    other = RuleBasedControl(m, priority_list=lists[-1])
+    assert other.priority_list == lists[-1] and len(other.run(max_steps=3)) == 3
+
+
+def test_rule_based_control_runs_until_done():
+    from pymgrid_b200 import Microgrid
+    from pymgrid_b200.algos import RuleBasedControl
+    from tests.helpers import jump_to
+    m = Microgrid(jump_to(load_pymgrid25(0), 8700))
+    df = RuleBasedControl(m).run()                 # max_steps=None: until the microgrid terminates (final_step 8759)
+    assert len(df) == 59 and df.index[0] == 8700 and df.index[-1] == 8758
+
+
 def test_reward_shaping_func_drop_in(golden):
     """Microgrid(reward_shaping_func=...) like the reference (microgrid.py:100-124): run returns the shaped reward, the
     balance log keeps reward and shaped_reward, and the shaper's assert surfaces as AssertionError on the same step."""
