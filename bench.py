@@ -216,6 +216,9 @@ def main():
                     help="NON-CANONICAL secondary mode: observations written as float32 (half the dominant bytes); reported with dtype f64+f32obs")
     ap.add_argument("--ragged", action="store_true",
                     help="start every env at its own random step (envs that reset independently): no two rows of a tile share a window")
+    ap.add_argument("--no-ring", action="store_true",
+                    help="per-env series batches (generator workload): use the persistent kernel that normalises whole windows per "
+                         "row instead of the one that keeps sliding windows in shared memory (A/B)")
     ap.add_argument("--preheat", type=float, default=0.2, help="seconds of untimed steps before the warm-up (0 under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -238,6 +241,8 @@ def main():
     discrete = args.workload == "discrete"
 
     bm = build_engine(B, dev, rank, world, args.workload, args.obs_f32)
+    if args.no_ring:
+        bm.set_rollout_ring(False)
     groups = bm.groups
 
     def rand_actions(steps, g):

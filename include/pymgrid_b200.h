@@ -316,7 +316,11 @@ int mg_forecast_noise(MgHandle *h, const MgForecastNoise *noise /* DEVICE [n_cfg
  * kernel when every group writes observations.  It wins when the envs of a tile advance in lock-step (11.5 vs 12.4
  * us/step at 65 536 envs) and loses when every env is at its own step (39.6 vs 29 us/step): hosts that install per-env
  * trajectory windows turn it off. */
-enum { MG_OPT_ROLLOUT_SPECIALISED = 1 };
+enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2 };
+/* MG_OPT_ROLLOUT_RING (default 1): batches with per-env series (MG_LAYOUT_SCALED_SERIES / grid_status_bits) run mg_rollout
+ * with every env's normalised load / pv windows held in shared memory (H + 2 slots per env and series; one new value per
+ * env, series and step instead of a whole window per row) when all horizons are <= 24.  0 selects the kernel that
+ * normalises whole windows per row (the one mg_step uses). */
 int mg_set_option(MgHandle *h, int option, int value);
 
 /* number of kernel launches this handle has enqueued since creation (bench.py's gpu_launches claim) */

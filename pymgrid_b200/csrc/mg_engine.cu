@@ -45,6 +45,9 @@
 #ifndef MG_TMA_MIN_RUN
 #define MG_TMA_MIN_RUN 2
 #endif
+// persistent kernel for per-env series: sliding load / pv windows live in shared memory, H + 2 slots per env and series
+#define MG_RING_MAX 26      // forecast horizons up to 24
+#define MG_MIN_CTAS_RING 5  // 40 KB of shared memory per CTA
 // runs of at least this many rows stage their grid window in shared memory with TMA
 
 enum { KIND_BAT = 0, KIND_GEN = 1, KIND_GRID = 2, KIND_LOAD = 3, KIND_PV = 4 };
@@ -502,6 +505,109 @@ __device__ __forceinline__ RowStarts row_starts(const DevGroup &G) {
     return st;
 }
 
+// ---- sliding windows of the persistent kernel for per-env series (kRing) --------------------------------------------
+// A MicrogridGenerator-style env has its own load / pv series (profile * scale), so no two rows share a window and the
+// step kernel normalises all 2 (1 + H) window values of a row on the fly (emit_row_hetero: two f64 divisions per lane
+// and row).  Inside a rollout the window of step s+1 is the window of step s shifted by one: the persistent kernel keeps
+// every env's normalised windows in shared memory -- ring of R = H + 2 slots per env and series, absolute series index
+// idx lives in slot idx mod R -- and the env's owner thread appends ONE new value per series and step.  R = H + 2, not
+// H + 1: the slot the owner overwrites for step s+1 then belongs to index t_s - 1, which the warps still streaming the
+// rows of step s ([t_s, t_s + H]) do not read.
+struct RingShared {
+    double win[2][MG_TILE][MG_RING_MAX];   // [0] load, [1] pv
+};
+template <bool kRing>
+struct RingStorage;
+template <>
+struct RingStorage<true> {
+    typedef RingShared type;
+    __device__ static __forceinline__ RingShared *get(type &s) { return &s; }
+};
+template <>
+struct RingStorage<false> {
+    typedef Empty type;
+    __device__ static __forceinline__ RingShared *get(type &) { return nullptr; }
+};
+
+__device__ __forceinline__ bool env_is_special(const MgConfig *__restrict__ c, const DevGroup &G) {
+    return c->series_scaled || (G.has_grid && G.status_bits);
+}
+
+// normalised load / pv observation value at absolute series index idx (idx <= T + H): the env's own series where it is
+// profile * scale -- (profile * scale - low) / spread, or the normalised forecaster fill past the end, exactly as
+// emit_row_hetero computes it -- else the pre-normalised, end-padded table
+__device__ __forceinline__ void series_obs_value(const LaunchParams &P, const MgConfig *__restrict__ c, int idx, double &ld, double &pv) {
+    if (c->series_scaled) {
+        const bool in = idx < P.T;
+        const double rp = in ? __ldg(P.pv_raw + (size_t)c->pv_series * P.T + idx) : 0.0;
+        const double rl = in ? __ldg(P.load_raw + (size_t)c->load_series * P.T + idx) : 0.0;
+        const double np_ = (rp * c->pv_scale - c->pv_low) / c->pv_spread;
+        const double nl = (rl * c->load_scale - c->load_low) / c->load_spread;
+        pv = in ? np_ : c->pv_fill_nrm;
+        ld = in ? nl : c->load_fill_nrm;
+    } else {
+        pv = __ldg(P.pv_nrm + (size_t)c->pv_series * P.Tp + idx);
+        ld = __ldg(P.load_nrm + (size_t)c->load_series * P.Tp + idx);
+    }
+}
+
+// the 32 grid-status bits of env e starting at step t_obs (bit k = status at t_obs + k)
+__device__ __forceinline__ uint32_t status_window(const DevGroup &G, int e, int t_obs) {
+    const uint32_t *bits = G.status_bits + (size_t)e * G.status_words;
+    const int i = t_obs >> 5;
+    const uint32_t lo = __ldg(bits + i);
+    const uint32_t hi = (i + 1 < G.status_words) ? __ldg(bits + i + 1) : 0u;
+    return __funnelshift_r(lo, hi, t_obs & 31);
+}
+
+// TileEnv of a ring row: off_grid = grid window offset (columns 0-2), special = t_obs, and -- the table offsets of the
+// load / pv windows being meaningless for it -- off_load = the status window word, off_pv = ring base | weak << 16
+__device__ __forceinline__ void publish_ring(TileEnv &te, const MgConfig *__restrict__ c, const DevGroup &G, int e, int base) {
+    const int t_obs = te.special;
+    te.off_load = (G.has_grid && G.status_bits) ? (int32_t)status_window(G, e, t_obs) : 0;
+    te.off_pv = base | (c->grid_status_weak ? (1 << 16) : 0);
+}
+
+// One observation row of a ring env, straight from the rings / the grid table / the status word into this lane's pairs
+// (no staging): ~10 instructions per element against a full normalisation in emit_row_hetero.
+template <int SLOTS, typename TO>
+__device__ __forceinline__ void emit_row_ring(const LaunchParams &P, const DevGroup &G, const TileEnv &te, const double *__restrict__ ring_load,
+                                              const double *__restrict__ ring_pv, const int (&code)[SLOTS][2], const bool (&act)[SLOTS],
+                                              const bool (&st_lane)[SLOTS], int sp0, TO *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int R = G.horizon + 2;
+    const int t_obs = te.special, base = te.off_pv & 0xffff;
+    const bool weak = (te.off_pv >> 16) != 0;
+    const uint32_t w = (uint32_t)te.off_load;
+    const bool own_status = G.status_bits != nullptr;
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+        if (st_lane[k]) {
+            const double2 sv = *reinterpret_cast<const double2 *>(te.state + 2 * (lane + 32 * k - sp0));
+            st_global_v2(out + 64 * k, sv.x, sv.y);
+        } else if (act[k]) {
+            double v[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kind = code[k][h] >> 16, off = code[k][h] & 0xffff;
+                if (kind == KIND_GRID) {
+                    if (own_status && (off & 3) == 3) {   // bounds of the status column: (0, 1) on a weak grid, else spread 1
+                        const int kk = off >> 2;
+                        v[h] = weak ? (t_obs + kk < P.T ? (double)((w >> kk) & 1u) : 0.5) : 0.0;
+                    } else {
+                        v[h] = __ldg(P.grid_nrm + te.off_grid + off);
+                    }
+                } else {
+                    int slot = base + off;
+                    if (slot >= R) slot -= R;
+                    v[h] = (kind == KIND_LOAD ? ring_load : ring_pv)[slot];
+                }
+            }
+            st_global_v2(out + 64 * k, v[0], v[1]);
+        }
+    }
+}
+
 // One observation row of an env with per-env series (MicrogridGenerator grids: load / pv = profile * scale normalised
 // on the fly, grid status from the env's own bit row).  Warp-cooperative, one block of the row at a time so that every
 // lane of a block runs the same code: lane l normalises window element l (+32) of the pv block, then of the load block
@@ -566,10 +672,10 @@ __device__ __forceinline__ void emit_row_hetero(const LaunchParams &P, const Dev
 // The 1-3 lanes that own the battery / genset pairs take them from the env's shared-memory record instead, so every
 // byte of a row -- and of the contiguous 19 KB chunk of 16 rows -- is written by one warp in consecutive instructions
 // (a separate writer for those 48 bytes costs ~20% of the store bandwidth: partial-sector merging in L2).
-template <int SLOTS, bool kHetero, typename TO>
+template <int SLOTS, bool kHetero, typename TO, bool kRing = false>
 __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const DevGroup &G, TileShared &S, const HeteroEnv *het,
                                                  int ebuf, TO *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase,
-                                                 int r_begin) {
+                                                 int r_begin, const RingShared *rings = nullptr) {
     // rows [r_begin, r_begin + MG_ROWS_PER_WARP) of the tile; staging slot and mbarrier are the calling warp's own
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r_end = min(r_begin + MG_ROWS_PER_WARP, n_rows);
@@ -620,7 +726,9 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
             }
         }
         if (kHetero && sig.special >= 0) {   // a row with per-env series: always a run of one
-            emit_row_hetero(P, G, env[r], het[r], rs, img, e_base + r, obs_tile + (size_t)r * D);
+            if (kRing) emit_row_ring<SLOTS, TO>(P, G, env[r], rings->win[0][r], rings->win[1][r], code, act, st_lane, sp0,
+                                                obs_tile + (size_t)r * D + 2 * lane);
+            else emit_row_hetero(P, G, env[r], het[r], rs, img, e_base + r, obs_tile + (size_t)r * D);
             r += 1;
             continue;
         }
@@ -668,13 +776,13 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
     }
 }
 
-template <bool kHetero, typename TO>
+template <bool kHetero, typename TO, bool kRing = false>
 __device__ __forceinline__ void warp_emit_rows(const LaunchParams &P, const DevGroup &G, TileShared &S, const HeteroEnv *het,
                                                int ebuf, TO *__restrict__ obs_tile, int n_rows, int e_base, uint32_t &phase,
-                                               int r_begin) {
+                                               int r_begin, const RingShared *rings = nullptr) {
     const int pairs = G.obs_dim >> 1;
-    if (pairs <= 32) warp_emit_rows_t<1, kHetero, TO>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase, r_begin);
-    else warp_emit_rows_t<3, kHetero, TO>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase, r_begin);
+    if (pairs <= 32) warp_emit_rows_t<1, kHetero, TO, kRing>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase, r_begin, rings);
+    else warp_emit_rows_t<3, kHetero, TO, kRing>(P, G, S, het, ebuf, obs_tile, n_rows, e_base, phase, r_begin, rings);
 }
 
 // rows longer than MG_MAX_IMG: element-wise path straight from the tables (no staging)
@@ -891,10 +999,13 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
 // ------------------------------------------------------------------------------------------------------------------
 // persistent multi-step kernel: every CTA owns its tile for all n_steps; env state stays in registers
 // ------------------------------------------------------------------------------------------------------------------
-template <bool kHetero, typename TO>
-__global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_MIN_CTAS) mg_rollout_kernel(const __grid_constant__ LaunchParams P) {
+template <bool kHetero, typename TO, bool kRing = false>
+__global__ void __launch_bounds__(MG_THREADS, kRing ? MG_MIN_CTAS_RING : kHetero ? MG_MIN_CTAS_HETERO : MG_MIN_CTAS) mg_rollout_kernel(const __grid_constant__ LaunchParams P) {
+    static_assert(!kRing || kHetero, "the ring path is a variant of the per-env series kernels");
     __shared__ TileShared S;
-    __shared__ typename HeteroStorage<kHetero>::type SH;
+    __shared__ typename HeteroStorage<kHetero && !kRing>::type SH;    // (the ring variant needs no per-env series records)
+    __shared__ typename RingStorage<kRing>::type SR;
+    RingShared *rings = RingStorage<kRing>::get(SR);
     const int gi = find_group(P, blockIdx.x);
     const DevGroup &G = P.g[gi];
     const int e0 = (blockIdx.x - G.tile_begin) * MG_TILE;
@@ -917,6 +1028,31 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
         if (G.has_genset) unpack_genset(G.genset[e], s);
         final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
     }
+    // ring variant: fill every special env's windows for its current step [t, t + H], one env per warp pass, lane k = window
+    // element k (the only place where a whole window is normalised); the owner then appends one value per step
+    const int ring_R = G.horizon + 2;
+    int ring_base = 0;
+    bool ring_env = false;
+    if (kRing && G.obs) {
+        const int lane = tid & 31, w0 = (tid >> 5) * MG_ROWS_PER_WARP;
+        for (int r = w0; r < min(w0 + MG_ROWS_PER_WARP, n_rows); ++r) {
+            const MgConfig *__restrict__ cr = P.cfg + __ldg(G.cfg_index + e0 + r);
+            if (!env_is_special(cr, G)) continue;
+            const int t_r = min(G.step[e0 + r], P.T);
+            for (int k = lane; k <= G.horizon; k += 32) {
+                double ld, pv;
+                series_obs_value(P, cr, t_r + k, ld, pv);
+                const int slot = (t_r + k) % ring_R;
+                rings->win[0][r][slot] = ld;
+                rings->win[1][r][slot] = pv;
+            }
+        }
+        if (owner) {
+            ring_env = env_is_special(c, G);
+            ring_base = min(s.t, P.T) % ring_R;
+        }
+        // (visibility: the first reader passes the __syncthreads of step 0 first)
+    }
     // (requesting step s+1's inputs before streaming step s's rows was measured SLOWER -- 13.6 vs 12.2 us/step: the
     //  prefetched registers spill under the 72-register budget that keeps all 1 024 tiles resident)
     for (int step = 0; step < P.n_steps; ++step) {
@@ -933,7 +1069,21 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
             rsum += reward;
             fsum |= flags;
             my_reward = reward;
-            if (G.obs) publish_env<kHetero>(S.env[ebuf][tid], kHetero ? HeteroStorage<kHetero>::rows(SH, ebuf) + tid : nullptr, c, G, s, P.T, P.Tp);
+            if (G.obs) {
+                publish_env<kHetero>(S.env[ebuf][tid], (kHetero && !kRing) ? HeteroStorage<kHetero && !kRing>::rows(SH, ebuf) + tid : nullptr, c, G, s, P.T, P.Tp);
+                if (kRing && ring_env) {
+                    if (in.valid) {   // the step counter moved from t to t + 1 <= T: the window gains index t + 1 + H
+                        ring_base = ring_base + 1 == ring_R ? 0 : ring_base + 1;
+                        double ld, pv;
+                        series_obs_value(P, c, s.t + G.horizon, ld, pv);
+                        int slot = ring_base + G.horizon;
+                        if (slot >= ring_R) slot -= ring_R;
+                        rings->win[0][tid][slot] = ld;
+                        rings->win[1][tid][slot] = pv;
+                    }
+                    publish_ring(S.env[ebuf][tid], c, G, e, ring_base);
+                }
+            }
         }
         if (G.reward_total && tid < MG_TILE) add_reward_total(G.reward_total + step, my_reward, owner);
         if (G.obs) {
@@ -941,7 +1091,7 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
             // step s+1 after it has finished reading env[s & 1], so the owners may overwrite it at step s+2
             __syncthreads();
             TO *obs_tile = reinterpret_cast<TO *>(G.obs) + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim;
-            if (!G.long_path) warp_emit_rows<kHetero, TO>(P, G, S, HeteroStorage<kHetero>::rows(SH, ebuf), ebuf, obs_tile, n_rows, e0, phase, (tid >> 5) * MG_ROWS_PER_WARP);
+            if (!G.long_path) warp_emit_rows<kHetero, TO, kRing>(P, G, S, HeteroStorage<kHetero && !kRing>::rows(SH, ebuf), ebuf, obs_tile, n_rows, e0, phase, (tid >> 5) * MG_ROWS_PER_WARP, rings);
             else warp_emit_rows_long<TO>(P, G, S, ebuf, obs_tile, n_rows);
         }
     }
@@ -1223,6 +1373,7 @@ struct MgHandle {
     bool hetero;            // per-env series (profile * scale) or per-env grid status present: run the kHetero kernels
     bool obs_f32;           // observation buffers are float32 (MG_LAYOUT_OBS_F32)
     bool rollout_specialised;   // MG_OPT_ROLLOUT_SPECIALISED
+    bool rollout_ring;          // MG_OPT_ROLLOUT_RING
     struct HostStage *stage;    // mg_rollout_host: streams, events and device staging (lazy)
 };
 
@@ -1340,6 +1491,7 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
     h->hetero = (L->flags & MG_LAYOUT_SCALED_SERIES) != 0;
     h->obs_f32 = (L->flags & MG_LAYOUT_OBS_F32) != 0;
     h->rollout_specialised = true;
+    h->rollout_ring = true;
     h->stage = nullptr;
     h->last_stream = nullptr;
     for (int g = 0; g < MG_MAX_GROUPS; ++g) h->last_obs[g] = nullptr;
@@ -1453,6 +1605,10 @@ extern "C" int mg_set_option(MgHandle *h, int option, int value) {
         h->rollout_specialised = value != 0;
         return MG_OK;
     }
+    if (option == MG_OPT_ROLLOUT_RING) {
+        h->rollout_ring = value != 0;
+        return MG_OK;
+    }
     return fail(MG_E_INVALID, "mg_set_option: unknown option");
 }
 
@@ -1539,9 +1695,16 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
     bool ws = MG_ROLLOUT_WS != 0 && !h->hetero && h->rollout_specialised;
     for (int g = 0; g < P.n_groups; ++g)
         if (!P.g[g].obs || P.g[g].long_path) ws = false;
+    // per-env series: keep the sliding windows in shared memory when every group's ring fits (H <= 24) and rows are staged
+    bool use_ring = h->hetero && h->rollout_ring;
+    for (int g = 0; g < P.n_groups; ++g)
+        if (!P.g[g].obs || P.g[g].long_path || P.g[g].horizon + 2 > MG_RING_MAX) use_ring = false;
     if (ws) {
         if (h->obs_f32) mg_rollout_ws_kernel<false, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
         else mg_rollout_ws_kernel<false, double><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+    } else if (use_ring) {
+        if (h->obs_f32) mg_rollout_kernel<true, float, true><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+        else mg_rollout_kernel<true, double, true><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
     } else if (h->obs_f32) {
         if (h->hetero) mg_rollout_kernel<true, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
         else mg_rollout_kernel<false, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);

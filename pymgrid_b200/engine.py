@@ -674,6 +674,11 @@ class BatchedMicrogrid:
         started at unrelated steps."""
         _cabi.check(self._lib.mg_set_option(self._handle, _cabi.MG_OPT_ROLLOUT_SPECIALISED, int(bool(on))), "mg_set_option")
 
+    def set_rollout_ring(self, on):
+        """Batches with per-env series (MicrogridGenerator grids): keep every env's normalised load / pv windows in shared
+        memory across the steps of `rollout` (default on; MG_OPT_ROLLOUT_RING).  Off = normalise whole windows per row."""
+        _cabi.check(self._lib.mg_set_option(self._handle, _cabi.MG_OPT_ROLLOUT_RING, int(bool(on))), "mg_set_option")
+
     def __del__(self):
         try:
             if getattr(self, "_handle", None) is not None:

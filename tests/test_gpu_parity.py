@@ -449,12 +449,47 @@ def test_generator_grids_scaled_series_and_weak_grid_bits(golden):
         np.testing.assert_array_equal(st[i], z[f"g{i}_s"][-1])
 
 
-def test_vectorised_generator_batch_vs_oracle():
+def test_generator_grids_rollout_keeps_sliding_windows(golden):
+    """The persistent kernel for per-env series keeps each env's normalised load / pv windows in shared memory and appends
+    one value per step (MG_OPT_ROLLOUT_RING): every step's observation row of the real MicrogridGenerator grids equals
+    the reference's recorded row, bit for bit -- also when the rollout is cut into launches (the windows are rebuilt at the
+    start of each) -- and equals what the window-per-row kernel writes."""
+    from tests.helpers import generator_params
+    z = golden["generator"]
+    n = int(z["n"])
+    configs = [generator_params(z, i) for i in range(n)]
+    env_config = np.arange(3 * n) % n            # 72 envs: more than one tile's worth of rows per warp pass
+    outs = {}
+    for ring_kernel in (True, False):
+        bm = engine(configs, env_config)
+        bm.set_rollout_ring(ring_kernel)
+        acts = [torch.from_numpy(np.ascontiguousarray(np.stack([z[f"g{env_config[e]}_a"][:60] for e in g.env_ids], axis=1))).cuda()
+                for g in bm.groups]
+        first = bm.rollout([a[:23].contiguous() for a in acts], ring=23)
+        rest = bm.rollout([a[23:].contiguous() for a in acts], ring=37)
+        first, rest = ([x] if isinstance(x, dict) else x for x in (first, rest))
+        outs[ring_kernel] = (first, rest)
+        for g, f, r in zip(bm.groups, first, rest):
+            rows = torch.cat([f["obs_ring"], r["obs_ring"]]).cpu().numpy()          # [60, n_g, D]
+            rew = torch.cat([f["reward"], r["reward"]]).cpu().numpy()
+            for slot, e in enumerate(g.env_ids):
+                i = env_config[e]
+                np.testing.assert_array_equal(rew[:, slot], z[f"g{i}_r"][:60])
+                np.testing.assert_array_equal(rows[:, slot], z[f"g{i}_o"][:60], err_msg=f"ring={ring_kernel} grid {i}")
+    for a, b in zip(outs[True], outs[False]):
+        for x, y in zip(a, b):
+            assert torch.equal(x["obs_ring"], y["obs_ring"]) and torch.equal(x["done"], y["done"])
+
+
+@pytest.mark.parametrize("ring_kernel", [True, False])
+def test_vectorised_generator_batch_vs_oracle(ring_kernel):
     """5 000 heterogeneous grids built in array form (one config record per env) == the oracle on each grid's explicit
-    form, over a rollout that crosses the end of the series for envs started late."""
+    form, over a rollout that crosses the end of the series for envs started late (both persistent kernels for per-env
+    series: sliding windows in shared memory, and whole windows per row)."""
     from pymgrid_b200 import generator
     gb = generator.sample(5000, seed=11)
     bm = generator.engine_from_batch(gb, device="cuda:0", action_order=CONTAINER)
+    bm.set_rollout_ring(ring_kernel)
     rng = np.random.default_rng(8)
     plist = [gb.to_params(i) for i in range(gb.n)]
     starts = rng.integers(0, 8700, gb.n)
