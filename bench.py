@@ -451,7 +451,9 @@ def main():
 
     if rank == 0:
         bytes_per_launch = sum(g.n_envs * algorithmic_bytes(*g.arch, discrete=discrete, obs_bytes=4 if args.obs_f32 else 8) for g in groups)
-        if args.workload == "generator":   # + the env's own parameter record and status word(s), re-read every step
+        if args.workload == "generator" and args.path != "rollout":
+            # + the env's own parameter record and status word(s), re-read by every single-step launch (+~176 B
+            # there, 336 B with this engine's record); inside the persistent kernel they stay cache-resident and are not counted
             bytes_per_launch += sum(g.n_envs * (336 + 8 * g.arch[1]) for g in groups)
         peak, peak_src = measured_peak()
         bytes_per_step = bytes_per_launch

@@ -568,42 +568,65 @@ __device__ __forceinline__ void publish_ring(TileEnv &te, const MgConfig *__rest
     te.off_pv = base | (c->grid_status_weak ? (1 << 16) : 0);
 }
 
-// One observation row of a ring env, straight from the rings / the grid table / the status word into this lane's pairs
-// (no staging): ~10 instructions per element against a full normalisation in emit_row_hetero.
-template <int SLOTS, typename TO>
-__device__ __forceinline__ void emit_row_ring(const LaunchParams &P, const DevGroup &G, const TileEnv &te, const double *__restrict__ ring_load,
-                                              const double *__restrict__ ring_pv, const int (&code)[SLOTS][2], const bool (&act)[SLOTS],
-                                              const bool (&st_lane)[SLOTS], int sp0, TO *__restrict__ out) {
+// One observation row of a ring env.  Warp-cooperative and block-wise like emit_row_hetero -- every lane of a block runs
+// the same code, so nothing diverges -- but with nothing left to compute: lane k copies window element k of the pv and the
+// load ring, lanes copy grid elements l, l + 32, ... from the table (a lane always sees the same grid column because 32
+// is a multiple of 4; the status column comes from the env's window word), lanes 0..5 the battery / genset values; the
+// row is assembled in the warp's shared-memory image and streamed out with 16-byte stores.
+// (A first version gathered each lane's six row elements straight into registers: 260 warp-instructions per row, almost
+//  all of them integer / branch work for the per-element kind dispatch -- profiles/r01_ncu_generator_ring_v1.txt.)
+// (row-invariant quantities are hoisted into RingRowCtx once per step; every loop has a compile-time trip count -- the ring
+//  path implies 1 + H <= 25 window elements, 4 (1 + H) <= 100 grid elements and at most MG_MAX_IMG / 2 pairs per row)
+struct RingRowCtx {
+    int pairs, rows, R, T, pv0, load0, grid0, state0, n_state;
+    bool has_grid, own_status;
+    const double *grid_nrm;
+};
+__device__ __forceinline__ RingRowCtx ring_row_ctx(const LaunchParams &P, const DevGroup &G, const RowStarts &rs) {
+    RingRowCtx x;
+    x.pairs = G.obs_dim >> 1; x.rows = 1 + G.horizon; x.R = G.horizon + 2; x.T = P.T;
+    x.pv0 = rs.pv; x.load0 = rs.load; x.grid0 = rs.grid; x.state0 = rs.state; x.n_state = 2 + 4 * G.has_genset;
+    x.has_grid = G.has_grid != 0; x.own_status = G.status_bits != nullptr;
+    x.grid_nrm = P.grid_nrm;
+    return x;
+}
+template <typename TO>
+__device__ __forceinline__ void emit_row_ring(const RingRowCtx &x, const TileEnv &te, const double *__restrict__ ring_load,
+                                              const double *__restrict__ ring_pv, double *__restrict__ img, TO *__restrict__ out) {
     const int lane = threadIdx.x & 31;
-    const int R = G.horizon + 2;
     const int t_obs = te.special, base = te.off_pv & 0xffff;
     const bool weak = (te.off_pv >> 16) != 0;
     const uint32_t w = (uint32_t)te.off_load;
-    const bool own_status = G.status_bits != nullptr;
+    __syncwarp();   // the previous row has been read out of the image
+    if (lane < x.rows) {
+        int slot = base + lane;
+        if (slot >= x.R) slot -= x.R;
+        img[x.pv0 + lane] = ring_pv[slot];
+        img[x.load0 + lane] = ring_load[slot];
+    }
+    if (x.has_grid) {
+        const bool status_lane = x.own_status && (lane & 3) == 3;
+        const double *__restrict__ gsrc = x.grid_nrm + te.off_grid;
 #pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
-        if (st_lane[k]) {
-            const double2 sv = *reinterpret_cast<const double2 *>(te.state + 2 * (lane + 32 * k - sp0));
-            st_global_v2(out + 64 * k, sv.x, sv.y);
-        } else if (act[k]) {
-            double v[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int kind = code[k][h] >> 16, off = code[k][h] & 0xffff;
-                if (kind == KIND_GRID) {
-                    if (own_status && (off & 3) == 3) {   // bounds of the status column: (0, 1) on a weak grid, else spread 1
-                        const int kk = off >> 2;
-                        v[h] = weak ? (t_obs + kk < P.T ? (double)((w >> kk) & 1u) : 0.5) : 0.0;
-                    } else {
-                        v[h] = __ldg(P.grid_nrm + te.off_grid + off);
-                    }
-                } else {
-                    int slot = base + off;
-                    if (slot >= R) slot -= R;
-                    v[h] = (kind == KIND_LOAD ? ring_load : ring_pv)[slot];
-                }
+        for (int j = 0; j < 4; ++j) {
+            const int g = lane + 32 * j;
+            if (g < 4 * x.rows) {
+                const int kk = g >> 2;
+                // bounds of the status column: (0, 1) on a weak grid, (1, 1) -> spread 1 otherwise (utils/space.py:204-205)
+                const double own = weak ? (t_obs + kk < x.T ? (((w >> kk) & 1u) ? 1.0 : 0.0) : 0.5) : 0.0;
+                const double tab = __ldg(gsrc + g);
+                img[x.grid0 + g] = status_lane ? own : tab;
             }
-            st_global_v2(out + 64 * k, v[0], v[1]);
+        }
+    }
+    if (lane < x.n_state) img[x.state0 + lane] = te.state[lane];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < MG_MAX_IMG / 64; ++j) {
+        const int p = lane + 32 * j;
+        if (p < x.pairs) {
+            const double2 v2 = *reinterpret_cast<const double2 *>(img + 2 * p);
+            st_global_v2(out + 2 * p, v2.x, v2.y);
         }
     }
 }
@@ -699,6 +722,8 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
         }
     }
     const RowStarts rs = row_starts(G);   // used by rows with per-env series (kHetero kernels only)
+    RingRowCtx rx;
+    if (kRing) rx = ring_row_ctx(P, G, rs);
     const bool tma_grid = G.has_grid && G.tma_ok;
     const uint32_t grid_bytes = (uint32_t)(4 * (1 + G.horizon) * sizeof(double));
     // run boundaries of this warp's rows in one vote: bit l set <=> row l starts a new run
@@ -726,8 +751,7 @@ __device__ __forceinline__ void warp_emit_rows_t(const LaunchParams &P, const De
             }
         }
         if (kHetero && sig.special >= 0) {   // a row with per-env series: always a run of one
-            if (kRing) emit_row_ring<SLOTS, TO>(P, G, env[r], rings->win[0][r], rings->win[1][r], code, act, st_lane, sp0,
-                                                obs_tile + (size_t)r * D + 2 * lane);
+            if (kRing) emit_row_ring<TO>(rx, env[r], rings->win[0][r], rings->win[1][r], img, obs_tile + (size_t)r * D);
             else emit_row_hetero(P, G, env[r], het[r], rs, img, e_base + r, obs_tile + (size_t)r * D);
             r += 1;
             continue;
