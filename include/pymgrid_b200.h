@@ -65,7 +65,7 @@ enum {
     MG_FLAG_GENSET_AS_SINK = 1u << 1,    /* AssertionError genset_module.py:208                         */
     MG_FLAG_BALANCE = 1u << 2,           /* RuntimeError   microgrid.py:321-323                         */
     MG_FLAG_BATTERY_MIN_CAP = 1u << 3,   /* AssertionError battery_module.py:128                        */
-    MG_FLAG_NEGATIVE_ABSORB = 1u << 4,   /* AssertionError base_module.py:272                           */
+    MG_FLAG_NEGATIVE_ABSORB = 1u << 4,   /* AssertionError base_module.py:272; priority_list.py:124     */
     MG_FLAG_STEP_PAST_END = 1u << 5,     /* IndexError     load_module.py:111 (t >= len(series))        */
     MG_FLAG_BAD_ACTION = 1u << 6,        /* ValueError     envs/discrete/discrete.py:84 (action not in space) */
     MG_FLAG_SHAPER_RANGE = 1u << 7,      /* AssertionError reward_shaping/battery_discharge_shaper.py:33 (value outside [-1, 1]) */
@@ -322,6 +322,19 @@ enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2 };
  * env, series and step instead of a whole window per row) when all horizons are <= 24.  0 selects the kernel that
  * normalises whole windows per row (the one mg_step uses). */
 int mg_set_option(MgHandle *h, int option, int value);
+
+/*
+ * mg_set_reported_soc -- BatteryModule._soc before the first update (battery_module.py:89, 96-106).  The reference keeps
+ * the soc a battery was CONSTRUCTED with (init_soc) and only recomputes it as current_charge / max_capacity in
+ * _update_state (:125-130); init_soc * max_capacity / max_capacity is not always init_soc in the last bit, so the
+ * observation Microgrid.reset() returns before any step can differ from charge / max_capacity by one ulp.
+ * `soc`: HOST array of n_groups DEVICE pointers ([n] f64 each; an entry or the whole array may be NULL = derive from the
+ * charge).  mg_observe / mg_reset report these values as the battery's soc until the first mg_step* / mg_rollout* call
+ * on the handle, which drops them (every battery updates in every step).  The arrays stay owned by the caller and must
+ * outlive that first step.  Callers that overwrite the charge array themselves (BatteryModule.current_charge setter,
+ * :360-362) pass NULL to drop them.
+ */
+int mg_set_reported_soc(MgHandle *h, const double *const *soc);
 
 /* number of kernel launches this handle has enqueued since creation (bench.py's gpu_launches claim) */
 int64_t mg_launch_count(const MgHandle *h);

@@ -110,8 +110,7 @@ static void genset_obs(const OrcGrid *g, double out[4]) {
 }
 static void battery_obs(const OrcGrid *g, double out[2]) {
     double min_soc = g->min_capacity / g->max_capacity; /* battery_module.py:88 */
-    double soc = g->charge / g->max_capacity;           /* battery_module.py:130 */
-    out[0] = space_normalize(soc, min_soc, 1.0);
+    out[0] = space_normalize(g->soc, min_soc, 1.0);     /* _soc as stored, battery_module.py:89, 130 */
     out[1] = space_normalize(g->charge, g->min_capacity, g->max_capacity);
 }
 
@@ -275,6 +274,7 @@ void orc_run(OrcGrid *g, const double *control, int normalized, int order, doubl
             if (!np_isclose(g->charge, g->min_capacity, 1e-5, 1e-8)) err |= ORC_ERR_BATTERY_MIN_CAP;
             g->charge = g->min_capacity;
         }
+        g->soc = g->charge / g->max_capacity; /* :130 */
         inf[ORC_INFO_REWARD_BATTERY] = -1.0 * (fabs(internal) * g->battery_cost_cycle); /* :121, get_cost :147 */
         reward += inf[ORC_INFO_REWARD_BATTERY];
     }
@@ -364,8 +364,9 @@ void orc_run(OrcGrid *g, const double *control, int normalized, int order, doubl
 /* ------------------------------------------------------------------------------------------------
  * PriorityListAlgo._populate_action  algos/priority_list/priority_list.py:69-167
  * ---------------------------------------------------------------------------------------------- */
-void orc_priority_control(const OrcGrid *g, const int8_t *plist_module, const int8_t *plist_action, int n_el,
-                          double *control) {
+uint32_t orc_priority_control(const OrcGrid *g, const int8_t *plist_module, const int8_t *plist_action, int n_el,
+                              double *control) {
+    uint32_t err = 0;
     const int t = g->t;
     int gen_off = 0, bat_off = g->has_genset ? 2 : 0, grid_off = bat_off + 1;
     int genset_seen = 0;
@@ -407,6 +408,7 @@ void orc_priority_control(const OrcGrid *g, const int8_t *plist_module, const in
             else {
                 double mc = (mod == 1) ? fmin(g->max_charge, g->max_capacity - g->charge) / g->efficiency
                                        : g->max_export * g->grid_ts[4 * (size_t)t + 3];
+                if (!(mc >= 0)) err |= ORC_ERR_NEGATIVE_ABSORB; /* :124 assert module_max_consumption >= 0 */
                 if (-1 * remaining > mc) energy = -1.0 * mc;
                 else energy = remaining;
             }
@@ -416,6 +418,7 @@ void orc_priority_control(const OrcGrid *g, const int8_t *plist_module, const in
         else control[grid_off] = energy;
         remaining -= energy; /* :108 */
     }
+    return err;
 }
 
 /* ------------------------------------------------------------------------------------------------

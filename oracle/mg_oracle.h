@@ -46,7 +46,7 @@ enum {
     ORC_ERR_GENSET_AS_SINK    = 1u << 1,   /* genset_module.py:208 assert as_source                      */
     ORC_ERR_BALANCE           = 1u << 2,   /* microgrid.py:321 RuntimeError                              */
     ORC_ERR_BATTERY_MIN_CAP   = 1u << 3,   /* battery_module.py:128 assert isclose                       */
-    ORC_ERR_NEGATIVE_ABSORB   = 1u << 4,   /* base_module.py:272 assert absorbed_energy >= 0             */
+    ORC_ERR_NEGATIVE_ABSORB   = 1u << 4,   /* base_module.py:272 assert absorbed_energy >= 0; priority_list.py:124 */
     ORC_ERR_STEP_PAST_END     = 1u << 5,   /* IndexError on ts[t] when t >= len                          */
     ORC_ERR_SHAPER_RANGE      = 1u << 7,   /* reward_shaping/battery_discharge_shaper.py:33 assert       */
     ORC_CLIP_GENSET           = 1u << 8,   /* raise_errors=True would raise ValueError here              */
@@ -83,7 +83,9 @@ typedef struct OrcGrid {
     int32_t t;
     int32_t cs, gs, up, dn;      /* genset: current_status, goal_status, steps_until_up, steps_until_down */
     int32_t _pad1;
-    double charge;               /* battery _current_charge (soc derived) */
+    double charge;               /* battery _current_charge */
+    double soc;                  /* battery _soc: what the constructor was given (init_soc, or init_charge / max_capacity,
+                                    battery_module.py:96-106) until the first _update_state recomputes it (:125-130) */
     /* observation bounds, computed once by orc_prepare like the reference does at module construction
        (base_timeseries_module.py:81-88 for load/pv, grid_module.py:125-132 per grid column)            */
     int32_t prepared, _pad2;
@@ -114,9 +116,11 @@ int orc_genset_next_status(const OrcGrid *g, int goal_status);
 
 /* PriorityListAlgo._populate_action (algos/priority_list/priority_list.py:69-116).
  * plist: n_el elements, each (module, action) with module 0=genset 1=battery 2=grid.
- * Writes the UNNORMALISED control in container order (same layout as orc_run's control). */
-void orc_priority_control(const OrcGrid *g, const int8_t *plist_module, const int8_t *plist_action,
-                          int n_el, double *control);
+ * Writes the UNNORMALISED control in container order (same layout as orc_run's control).
+ * Returns ORC_ERR_NEGATIVE_ABSORB where the reference's `assert module_max_consumption >= 0` (:124) fires (a battery whose
+ * charge sits an ulp above max_capacity is asked to absorb), else 0. */
+uint32_t orc_priority_control(const OrcGrid *g, const int8_t *plist_module, const int8_t *plist_action,
+                              int n_el, double *control);
 
 /* Batched drivers used only for CPU-baseline timing (bench.py) and bulk parity tests.
  * grids[n]; actions [n_steps][n][max_act] row-major with stride max_act; rewards/dones [n_steps][n];

@@ -32,7 +32,7 @@ class OrcGrid(C.Structure):
         ("loss_load_cost", C.c_double), ("overgeneration_cost", C.c_double),
         ("load_ts", C.POINTER(C.c_double)), ("pv_ts", C.POINTER(C.c_double)), ("grid_ts", C.POINTER(C.c_double)),
         ("t", C.c_int32), ("cs", C.c_int32), ("gs", C.c_int32), ("up", C.c_int32), ("dn", C.c_int32), ("_pad1", C.c_int32),
-        ("charge", C.c_double),
+        ("charge", C.c_double), ("soc", C.c_double),
         ("prepared", C.c_int32), ("_pad2", C.c_int32),
         ("load_low", C.c_double), ("load_high", C.c_double), ("pv_low", C.c_double), ("pv_high", C.c_double),
         ("grid_low", C.c_double * 4), ("grid_high", C.c_double * 4),
@@ -74,8 +74,9 @@ def lib():
         L.orc_rollout_discrete.argtypes = [P(OrcGrid), C.c_int64, P(C.c_int32), C.c_int32, P(C.c_int8), P(C.c_int8),
                                            P(C.c_int32), C.c_int32, C.c_int, P(C.c_double), P(C.c_uint8),
                                            P(C.c_double), C.c_int32, C.c_int32]
+        L.orc_priority_control.restype = C.c_uint32
         for f in (L.orc_prepare, L.orc_run, L.orc_observe, L.orc_reset, L.orc_genset_update_status,
-                  L.orc_priority_control, L.orc_rollout, L.orc_rollout_discrete):
+                  L.orc_rollout, L.orc_rollout_discrete):
             f.restype = None
         _lib = L
     return _lib
@@ -99,6 +100,8 @@ def fill_struct(g, p, keep):
     g.min_capacity, g.max_capacity, g.max_charge = b.min_capacity, b.max_capacity, b.max_charge
     g.max_discharge, g.efficiency, g.battery_cost_cycle = b.max_discharge, b.efficiency, b.battery_cost_cycle
     g.charge = b.current_charge
+    soc = getattr(b, "soc", None)      # _soc as constructed (init_soc); derived when the record does not carry one
+    g.soc = b.current_charge / b.max_capacity if soc is None else soc
     if p.genset is not None:
         s = p.genset
         g.running_min_production, g.running_max_production = s.running_min_production, s.running_max_production
@@ -154,8 +157,8 @@ class OracleGrid:
         mods = np.array([m for m, _ in plist], dtype=np.int8)
         acts = np.array([a for _, a in plist], dtype=np.int8)
         out = np.empty(self.n_act)
-        lib().orc_priority_control(C.byref(self.g), mods.ctypes.data_as(C.POINTER(C.c_int8)),
-                                   acts.ctypes.data_as(C.POINTER(C.c_int8)), len(plist), _dp(out))
+        self.list_flags = lib().orc_priority_control(C.byref(self.g), mods.ctypes.data_as(C.POINTER(C.c_int8)),
+                                                     acts.ctypes.data_as(C.POINTER(C.c_int8)), len(plist), _dp(out))
         return out
 
     @property

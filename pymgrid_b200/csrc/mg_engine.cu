@@ -76,6 +76,7 @@ struct DevGroup {
     uint32_t *flags;
     const uint8_t *mask;
     double *reward_total;               // optional aggregate of the step's rewards over the group (logging)
+    const double *soc_reported;         // mg_observe / mg_reset before the first step: the soc each battery was constructed with
     // rollout io
     double *reward_sum;
     int64_t act_step_stride, out_step_stride, obs_slot_stride, dact_step_stride;
@@ -188,8 +189,9 @@ struct RawRow {       // ts[t] of the env's series (reference: *_module.update r
 };
 
 // PriorityListAlgo._populate_action, algos/priority_list/priority_list.py:69-167.
-// Writes the unnormalised control: gen_goal, gen_energy, bat, grid.
-__device__ __forceinline__ void priority_control(const MgPriorityList pl, const MgConfig *__restrict__ c, const DevGroup &G,
+// Writes the unnormalised control: gen_goal, gen_energy, bat, grid.  Returns MG_FLAG_NEGATIVE_ABSORB where the reference's
+// `assert module_max_consumption >= 0` (:124) fires: a battery whose charge sits an ulp above max_capacity asked to absorb.
+__device__ __forceinline__ uint32_t priority_control(const MgPriorityList pl, const MgConfig *__restrict__ c, const DevGroup &G,
                                                  const EnvRegs &s, const RawRow &raw, double &gen_goal,
                                                  double &gen_energy, double &bat, double &grid) {
     gen_goal = 0.0; gen_energy = 0.0; bat = 0.0; grid = 0.0;
@@ -198,6 +200,7 @@ __device__ __forceinline__ void priority_control(const MgPriorityList pl, const 
     const double renewable = 0.0 + raw.pv;
     double remaining = total_load - renewable;
     bool genset_seen = false;
+    uint32_t flags = 0;
 #pragma unroll
     for (int i = 0; i < MG_PLIST_WIDTH; ++i) {
         const int mod = pl.module[i];
@@ -233,6 +236,7 @@ __device__ __forceinline__ void priority_control(const MgPriorityList pl, const 
                 const double mc = (mod == MG_MOD_BATTERY)
                                       ? fmin(c->bat_max_charge, c->bat_max_capacity - s.charge) / c->bat_efficiency
                                       : c->grid_max_export * raw.status;
+                if (!(mc >= 0)) flags |= MG_FLAG_NEGATIVE_ABSORB;
                 if (-1 * remaining > mc) energy = -1.0 * mc;
                 else energy = remaining;
             }
@@ -242,6 +246,7 @@ __device__ __forceinline__ void priority_control(const MgPriorityList pl, const 
         else grid = energy;
         remaining -= energy;
     }
+    return flags;
 }
 
 // One Microgrid.run for one env (microgrid.py:227-325; modules as cited inline).  Dispatch order
@@ -944,11 +949,13 @@ __device__ __forceinline__ void owner_step(const LaunchParams &P, const DevGroup
     }
     ActionRegs a = in.act;
     bool normalized = P.normalized != 0;
+    uint32_t list_flags = 0;
     if (P.mode == MODE_DISCRETE) {
         normalized = false;
-        priority_control(P.plist[c->plist_offset + in.dact], c, G, s, in.raw, a.goal, a.gen, a.bat, a.grid);
+        list_flags = priority_control(P.plist[c->plist_offset + in.dact], c, G, s, in.raw, a.goal, a.gen, a.bat, a.grid);
     }
     env_step(c, G, s, in.raw, a.goal, a.gen, a.bat, a.grid, normalized, final_step, reward, done, flags, info);
+    flags |= list_flags;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1004,7 +1011,15 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
                 G.step[e] = s.t;
             }
         }
-        if (G.obs) publish_env<kHetero>(S.env[0][tid], het0 ? het0 + tid : nullptr, c, G, s, P.T, P.Tp);
+        if (G.obs) {
+            publish_env<kHetero>(S.env[0][tid], het0 ? het0 + tid : nullptr, c, G, s, P.T, P.Tp);
+            if (P.mode >= MODE_OBSERVE && G.soc_reported) {
+                // BatteryModule keeps the soc it was constructed with until its first _update_state (battery_module.py:89,
+                // 125-130); init_soc * max_capacity / max_capacity is not always init_soc
+                const double soc = __ldg(G.soc_reported + e);
+                S.env[0][tid].state[(G.has_genset && G.state_genset_first) ? 4 : 0] = (soc - c->bat_soc_low) / c->bat_soc_spread;
+            }
+        }
     }
     if (G.reward_total && tid < MG_TILE) add_reward_total(G.reward_total, my_reward, stepped);   // warps 0..1, uniformly
     // Every write a following step depends on (state, reward, done, flags, info) is issued: let the next launch's CTAs
@@ -1399,6 +1414,7 @@ struct MgHandle {
     bool rollout_specialised;   // MG_OPT_ROLLOUT_SPECIALISED
     bool rollout_ring;          // MG_OPT_ROLLOUT_RING
     struct HostStage *stage;    // mg_rollout_host: streams, events and device staging (lazy)
+    const double *soc_reported[MG_MAX_GROUPS];   // mg_set_reported_soc; dropped by the first step / rollout
 };
 
 // Device staging of mg_rollout_host: two slots of `chunk` steps each (actions in, reward + done out) for every group,
@@ -1582,6 +1598,12 @@ extern "C" int mg_destroy(MgHandle *h) {
 
 extern "C" int64_t mg_launch_count(const MgHandle *h) { return h ? h->launches : 0; }
 
+extern "C" int mg_set_reported_soc(MgHandle *h, const double *const *soc) {
+    if (!h) return fail(MG_E_INVALID, "mg_set_reported_soc: null handle");
+    for (int g = 0; g < MG_MAX_GROUPS; ++g) h->soc_reported[g] = (soc && g < h->base.n_groups) ? soc[g] : nullptr;
+    return MG_OK;
+}
+
 extern "C" int mg_forecast_noise(MgHandle *h, const MgForecastNoise *noise, void *const *obs, const int64_t *env_base,
                                  uint64_t seed, uint64_t call, void *stream) {
     if (!h || !noise || !obs) return fail(MG_E_INVALID, "mg_forecast_noise: null argument");
@@ -1646,6 +1668,7 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
         d.actions = io[g].actions; d.dactions = io[g].dactions; d.obs = io[g].obs; d.reward = io[g].reward;
         d.done = io[g].done; d.info = io[g].info; d.flags = io[g].flags; d.mask = io[g].mask;
         d.reward_total = io[g].reward_total;
+        d.soc_reported = (mode == MODE_OBSERVE || mode == MODE_RESET) ? h->soc_reported[g] : nullptr;
         if (mode == MODE_STEP && !d.actions) return fail(MG_E_INVALID, "mg_step: null actions");
         if (mode == MODE_DISCRETE && (!d.dactions || !P.plist)) return fail(MG_E_INVALID, "mg_step_discrete: null actions or priority lists");
         if ((mode == MODE_STEP || mode == MODE_DISCRETE) && (!d.reward || !d.done)) return fail(MG_E_INVALID, "step: null reward / done");
@@ -1674,6 +1697,7 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
     if (h->obs_f32) e = h->hetero ? cudaLaunchKernelEx(&cfg, mg_step_kernel<true, float>, P) : cudaLaunchKernelEx(&cfg, mg_step_kernel<false, float>, P);
     else e = h->hetero ? cudaLaunchKernelEx(&cfg, mg_step_kernel<true, double>, P) : cudaLaunchKernelEx(&cfg, mg_step_kernel<false, double>, P);
     if (e != cudaSuccess) return cuda_fail(e, "step kernel launch");
+    if (mode == MODE_STEP || mode == MODE_DISCRETE) memset(h->soc_reported, 0, sizeof h->soc_reported);   // every battery updates
     h->launches += 1;
     h->last_was_step = true;
     h->last_stream = stream;
@@ -1738,6 +1762,7 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "rollout kernel launch");
+    memset(h->soc_reported, 0, sizeof h->soc_reported);
     h->launches += 1;
     h->last_was_step = false;
     return MG_OK;

@@ -139,6 +139,7 @@ class Group:
     step: torch.Tensor = None      # int32 [n]
     charge: torch.Tensor = None    # f64 [n]
     genset: torch.Tensor = None    # int32 [n] (packed cs | gs<<8 | up<<16 | dn<<24) or None
+    soc_reported: Optional[torch.Tensor] = None   # f64 [n]: the soc the batteries were constructed with (mg_set_reported_soc)
     cfg_index: torch.Tensor = None
     env_initial_step: Optional[torch.Tensor] = None
     env_final_step: Optional[torch.Tensor] = None
@@ -297,6 +298,7 @@ class HostRollout:
             raise ValueError(f"n_steps must be in [1, {self.n_steps}]")
         if self.pipeline == "native":
             bm = self.bm
+            bm._mark_stepped()
             rc = bm._lib.mg_rollout_host(bm._handle, self._io, T, self.chunk, self.ring, int(self.discrete),
                                          int(self.normalized), bm._stream())
             _cabi.check(rc, "mg_rollout_host")
@@ -381,6 +383,7 @@ class LogRecorder:
     def step(self, actions, normalized=True, discrete=False, obs=True):
         from . import views
         pre = self._snapshot()
+        pristine = self.bm._soc_pristine       # first update of every battery: the logged soc is the constructed-with one
         res = self.bm.step_discrete(actions, obs=obs) if discrete else self.bm.step(actions, normalized=normalized, obs=obs)
         post = self._snapshot()
         for gi, ((envs, slots), g) in enumerate(zip(self._sel, self.bm.groups)):
@@ -394,7 +397,7 @@ class LogRecorder:
                 gen_post = unpack(post[gi][2][k]) if post[gi][2] is not None else (0, 0, 0, 0)
                 t = int(pre[gi][0][k])
                 self.first_step.setdefault(e, t)
-                state = views.state_dict(p, t, float(pre[gi][1][k]), gen_pre)
+                state = views.state_dict(p, t, float(pre[gi][1][k]), gen_pre, p.battery.soc if pristine else None)
                 self.rows[e].append(views.log_row(p, state, info[k], float(reward[k]), gen_post))
         return res
 
@@ -483,6 +486,7 @@ class BatchedMicrogrid:
                     cfg_arch=np.array([p.arch for p in self.configs], dtype=np.int64),
                     cfg_step=np.array([p.current_step for p in self.configs], dtype=np.int32),
                     cfg_charge=np.array([p.battery.current_charge for p in self.configs], dtype=np.float64),
+                    cfg_soc=np.array([np.nan if p.battery.soc is None else p.battery.soc for p in self.configs], dtype=np.float64),
                     cfg_genset=np.array([0 if p.genset is None else (p.genset.current_status | (p.genset.goal_status << 8)
                                          | (p.genset.steps_until_up << 16) | (p.genset.steps_until_down << 24))
                                          for p in self.configs], dtype=np.int64).astype(np.int32),
@@ -493,10 +497,11 @@ class BatchedMicrogrid:
 
     def _setup(self, cfg_np, plist_np, action_tables, env_config, cfg_arch, cfg_step, cfg_charge, cfg_genset, load_np,
                pv_np, grid_np, cfg_status, device, obs_order, with_info, with_flags, action_order,
-               obs_dtype=torch.float64):
+               obs_dtype=torch.float64, cfg_soc=None):
         """Common construction from array-form inputs (also used by the vectorised generator front end):
         cfg_np structured MgConfig records; cfg_arch [n_cfg, 3]; cfg_* initial state per config; series tables;
-        cfg_status: None or per-config 0/1 status rows ([n_cfg, T] array or list with None for grid-less configs)."""
+        cfg_status: None or per-config 0/1 status rows ([n_cfg, T] array or list with None for grid-less configs);
+        cfg_soc: None or the soc each config's battery was constructed with (nan = derive from the charge)."""
         if not torch.cuda.is_available():
             raise EngineError("BatchedMicrogrid needs a CUDA device: there is no CPU path")
         self._lib = _cabi.lib()
@@ -572,6 +577,13 @@ class BatchedMicrogrid:
             g.cfg_index = torch.from_numpy(cfg_ids.astype(np.int32)).to(dev)
             g.step = torch.from_numpy(cfg_step[cfg_ids].astype(np.int32)).to(dev)
             g.charge = torch.from_numpy(cfg_charge[cfg_ids].astype(np.float64)).to(dev)
+            if cfg_soc is not None:
+                # BatteryModule reports the soc it was constructed with until its first update (battery_module.py:89, 125-130);
+                # only batches where that differs from charge / max_capacity (by an ulp) carry the extra array
+                derived = cfg_charge[cfg_ids].astype(np.float64) / cfg_np["bat_max_capacity"][cfg_ids]
+                soc = np.where(np.isnan(cfg_soc[cfg_ids]), derived, cfg_soc[cfg_ids])
+                if (soc != derived).any():
+                    g.soc_reported = torch.from_numpy(np.ascontiguousarray(soc, dtype=np.float64)).to(dev)
             if has_genset:
                 g.genset = torch.from_numpy(cfg_genset[cfg_ids].astype(np.int32)).to(dev)
             if has_grid and cfg_status is not None:
@@ -595,6 +607,7 @@ class BatchedMicrogrid:
             self.groups.append(g)
             start += len(ids)
         self._handle = None
+        self._soc_pristine = True      # no battery has updated yet (see _mark_stepped)
         self._create()
 
     # ------------------------------------------------------------------------------------------------------
@@ -633,9 +646,17 @@ class BatchedMicrogrid:
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.mg_create(C.byref(L), self._stream(), C.byref(h)), "mg_create")
         self._handle = h
+        if self._soc_pristine and any(g.soc_reported is not None for g in self.groups):
+            socs = (C.c_void_p * len(self.groups))(*[_ptr(g.soc_reported) or None for g in self.groups])
+            _cabi.check(self._lib.mg_set_reported_soc(h, socs), "mg_set_reported_soc")
         # envs with their own episode windows do not advance in lock-step: the plain persistent kernel is faster there
         ragged = any(g.env_initial_step is not None for g in self.groups)
         self.set_rollout_specialised(not ragged)
+
+    def _mark_stepped(self):
+        """Called by everything that steps (or binds a stepping launcher): the handle drops the constructed-with soc values at
+        its first step; this flag keeps a later re-creation of the handle (set_trajectories) from installing them again."""
+        self._soc_pristine = False
 
     def set_forecast_noise(self, seed=0, env_offset=0, records=None):
         """Turn on the Gaussian-noise forecasters of the configs (`MicrogridParams.forecasters`; reference:
@@ -746,6 +767,7 @@ class BatchedMicrogrid:
         """Bind the argument block of a step ONCE for fixed buffers and return a zero-argument launcher: the per-call
         host cost drops to one ctypes call (used by HostIO and by loops that step the same buffers repeatedly)."""
         io, obs_bufs = self._io(dactions=actions, obs=obs) if discrete else self._io(actions=actions, obs=obs)
+        self._mark_stepped()
         lib, handle, norm = self._lib, self._handle, int(bool(normalized))
         stream_of, dev = torch.cuda.current_stream, self.device
         noise = self._apply_noise if self._noise is not None else None   # (a captured graph replays one call number)
@@ -771,6 +793,7 @@ class BatchedMicrogrid:
         columns per `Group.act_cols`.  Returns (obs, reward, done, info) as device tensors (lists for > 1 group).
         reward_total: optional f64 [1] device tensor that the kernel adds the batch's summed reward to (logging)."""
         io, obs_bufs = self._io(actions=actions, obs=obs, reward_total=reward_total)
+        self._mark_stepped()
         _cabi.check(self._lib.mg_step(self._handle, io, int(bool(normalized)), self._stream()), "mg_step")
         self._apply_noise(obs_bufs)
         return self._result(obs_bufs)
@@ -778,6 +801,7 @@ class BatchedMicrogrid:
     def step_discrete(self, actions, obs=True):
         """DiscreteMicrogridEnv.step for every env (reference envs/discrete/discrete.py:109-143)."""
         io, obs_bufs = self._io(dactions=actions, obs=obs)
+        self._mark_stepped()
         _cabi.check(self._lib.mg_step_discrete(self._handle, io, self._stream()), "mg_step_discrete")
         self._apply_noise(obs_bufs)
         return self._result(obs_bufs)
@@ -847,6 +871,7 @@ class BatchedMicrogrid:
             io[gi].reward_sum, io[gi].flags = _ptr(r["reward_sum"]), _ptr(g.flags)
             io[gi].reward_total = _ptr(reward_total)
         lib, handle, norm, dev = self._lib, self._handle, int(bool(normalized)), self.device
+        self._mark_stepped()
 
         def launch():
             st = torch.cuda.current_stream(dev).cuda_stream
@@ -885,6 +910,9 @@ class BatchedMicrogrid:
                 for g in self.groups]
 
     def load_state_dict(self, state):
+        # BatteryModule.current_charge setter (battery_module.py:360-362): the soc follows the restored charge
+        self._mark_stepped()
+        _cabi.check(self._lib.mg_set_reported_soc(self._handle, None), "mg_set_reported_soc")
         for g, s in zip(self.groups, state):
             g.step.copy_(s["step"])
             g.charge.copy_(s["charge"])

@@ -117,7 +117,9 @@ class _BaseEnv:
     def _state(self):     # live state of env 0, for the module views
         g = self.group
         gen = tuple(int(x) for x in self.engine.genset_status(0)[0].tolist()) if g.genset is not None else (0, 0, 0, 0)
-        return dict(t=int(g.step[0].item()), charge=float(g.charge[0].item()), genset=gen)
+        charge, b = float(g.charge[0].item()), self.params.battery
+        soc = b.soc if (self.engine._soc_pristine and b.soc is not None) else charge / b.max_capacity   # battery_module.py:89, 130
+        return dict(t=int(g.step[0].item()), charge=charge, genset=gen, soc=soc)
 
     @property
     def initial_step(self):

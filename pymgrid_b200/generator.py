@@ -81,7 +81,7 @@ class GeneratorBatch:
         cap = float(self.bat_capacity[i])
         battery = BatteryParams(min_capacity=cap * 0.2, max_capacity=cap, max_charge=float(self.bat_power[i]),
                                 max_discharge=float(self.bat_power[i]), efficiency=0.9, battery_cost_cycle=0.02,
-                                current_charge=float(self.bat_soc0[i]) * cap)
+                                current_charge=float(self.bat_soc0[i]) * cap, soc=float(self.bat_soc0[i]))
         genset = grid = None
         if self.has_genset[i]:
             r = float(self.gen_rated[i])
@@ -158,7 +158,7 @@ def engine_from_batch(gb, device=None, obs_order="gym_sorted", with_info=False, 
     bm.generator_batch = gb
     bm._setup(cfg_np=cfg, plist_np=np.concatenate(plist_rows).view(np.uint8), action_tables=tables,
               env_config=np.arange(n), cfg_arch=np.stack([hg.astype(np.int64), hr.astype(np.int64), np.full(n, HORIZON)], axis=1),
-              cfg_step=np.zeros(n, dtype=np.int32), cfg_charge=gb.bat_soc0[sel] * cap,
+              cfg_step=np.zeros(n, dtype=np.int32), cfg_charge=gb.bat_soc0[sel] * cap, cfg_soc=gb.bat_soc0[sel],
               cfg_genset=np.where(hg, 0x0101, 0).astype(np.int32), load_np=load_tab, pv_np=pv_tab, grid_np=grid_np,
               cfg_status=status, device=device, obs_order="gym_sorted_pv_first" if obs_order == "gym_sorted" else obs_order,
               with_info=with_info, with_flags=with_flags, action_order=action_order,

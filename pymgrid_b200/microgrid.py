@@ -52,7 +52,8 @@ class ModuleView:
 
     @property
     def soc(self):
-        return self.current_charge / self._p.battery.max_capacity
+        self._require("battery")
+        return self._m._state()["soc"]
 
     @property
     def max_production(self):
@@ -171,7 +172,7 @@ class ModuleView:
     # -- state vectors (BaseMicrogridModule.state / state_dict, base_module.py:535-560) --
     def state_dict(self, normalized=False):
         st = self._m._state()
-        d = views.state_dict(self._p, st["t"], st["charge"], st["genset"])[self._kind]
+        d = views.state_dict(self._p, st["t"], st["charge"], st["genset"], st["soc"])[self._kind]
         if normalized:
             return OrderedDict(zip(d.keys(), self.to_normalized(np.array(list(d.values()), dtype=np.float64), obs=True)))
         return d
@@ -345,6 +346,7 @@ class Microgrid:
         self._g = self._engine.groups[0]
         self._actions = torch.zeros((1, params.n_act), dtype=torch.float64, device=self._engine.device)
         self._log_rows = []
+        self._soc0 = params.battery.soc     # the soc the battery was constructed with, reported until its first update
         self._initial_step, self._final_step = params.initial_step, params.final_step
         self.raise_errors = bool(params.meta.get("raise_errors", False))
         names = ["load", "pv", "unbalanced_energy"] + (["genset"] if params.has_genset else []) + ["battery"] + \
@@ -401,7 +403,9 @@ class Microgrid:
     def _state(self):
         g = self._g
         gen = tuple(int(x) for x in self._engine.genset_status(0)[0].tolist()) if g.genset is not None else (0, 0, 0, 0)
-        return dict(t=int(g.step[0].item()), charge=float(g.charge[0].item()), genset=gen)
+        charge = float(g.charge[0].item())
+        soc = charge / self.params.battery.max_capacity if self._soc0 is None else self._soc0     # battery_module.py:89, 130
+        return dict(t=int(g.step[0].item()), charge=charge, genset=gen, soc=soc)
 
     @property
     def current_step(self):
@@ -457,12 +461,13 @@ class Microgrid:
             raise IndexError(f"index {pre['t']} is out of bounds for axis 0 with size {len(p)}")   # load_module.py:111
         self._actions.copy_(torch.from_numpy(row).reshape(1, -1))
         obs, reward, done, info = self._engine.step(self._actions, normalized=normalized)
+        self._soc0 = None
         flags = int(self._g.flags[0].item()) & 0xffffffff
         self._raise_for_flags(flags)
         obs_row, info_row = obs[0].cpu().numpy(), info[0].cpu().numpy()
         r = float(reward[0].item())
         post = self._state()
-        self._log_rows.append(self._named(views.log_row(p, views.state_dict(p, pre["t"], pre["charge"], pre["genset"]),
+        self._log_rows.append(self._named(views.log_row(p, views.state_dict(p, pre["t"], pre["charge"], pre["genset"], pre["soc"]),
                                                         info_row, r, post["genset"])))
         return (self._named(views.obs_row_to_dict(obs_row, p, self._obs_order)), r, bool(done[0].item()),
                 self._named(views.info_row_to_dict(info_row, flags, p)))
@@ -483,6 +488,7 @@ class Microgrid:
                 raise IndexError(f"index {t0} is out of bounds for axis 0 with size {len(p)}")   # load_module.py:111
             return 0
         act = torch.full((1,), int(action_index), dtype=torch.int32, device=self._engine.device)
+        soc0, self._soc0 = self._soc0, None
         pre_t, pre_charge, pre_gen, post_gen, infos, rewards, flags = [], [], [], [], [], [], []
         zero = torch.zeros(1, dtype=torch.int32, device=self._engine.device)
         gen = (lambda: g.genset.clone()) if g.genset is not None else (lambda: zero)
@@ -496,7 +502,7 @@ class Microgrid:
         unpack = lambda w: (int(w) & 0xff, (int(w) >> 8) & 0xff, (int(w) >> 16) & 0xff, (int(w) >> 24) & 0xff)   # noqa: E731
         for k in range(n):
             self._raise_for_flags(int(flags[k]) & 0xffffffff)
-            state = views.state_dict(p, int(pre_t[k]), float(pre_charge[k]), unpack(pre_gen[k]))
+            state = views.state_dict(p, int(pre_t[k]), float(pre_charge[k]), unpack(pre_gen[k]), soc0 if k == 0 else None)
             self._log_rows.append(self._named(views.log_row(p, state, infos[k], float(rewards[k]), unpack(post_gen[k]))))
         return n
 
@@ -551,7 +557,7 @@ class Microgrid:
         st = self._state()
         p = copy.deepcopy(self.params)
         p.current_step, p.initial_step, p.final_step = st["t"], self._initial_step, self._final_step
-        p.battery.current_charge = st["charge"]
+        p.battery.current_charge, p.battery.soc = st["charge"], self._soc0
         if p.genset is not None:
             g = p.genset
             g.current_status, g.goal_status, g.steps_until_up, g.steps_until_down = st["genset"]
@@ -574,13 +580,13 @@ class Microgrid:
     # ---- introspection -----------------------------------------------------------------------------------
     def state_dict(self, normalized=False):
         st = self._state()
-        sd = views.state_dict(self.params, st["t"], st["charge"], st["genset"])
+        sd = views.state_dict(self.params, st["t"], st["charge"], st["genset"], st["soc"])
         return {name: [dict(d)] for name, d in self._named(sd).items()}
 
     def state_series(self, normalized=False):
         import pandas as pd
         st = self._state()
-        sd = views.state_dict(self.params, st["t"], st["charge"], st["genset"])
+        sd = views.state_dict(self.params, st["t"], st["charge"], st["genset"], st["soc"])
         data = OrderedDict(((name, 0, k), v) for name, d in self._named(sd).items() for k, v in d.items())
         return pd.Series(data)
 

@@ -64,7 +64,8 @@ class BatteryModule(_Module):
     def _params(self):
         return BatteryParams(min_capacity=self.min_capacity, max_capacity=self.max_capacity, max_charge=self.max_charge,
                              max_discharge=self.max_discharge, efficiency=self.efficiency,
-                             battery_cost_cycle=self.battery_cost_cycle, current_charge=self.init_charge)
+                             battery_cost_cycle=self.battery_cost_cycle, current_charge=self.init_charge,
+                             soc=self.init_soc)
 
 
 class GensetModule(_Module):

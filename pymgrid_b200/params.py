@@ -24,6 +24,14 @@ class BatteryParams:
     efficiency: float
     battery_cost_cycle: float = 0.0
     current_charge: float = 0.0     # state: _current_charge
+    # state: _soc.  The reference keeps the soc it was CONSTRUCTED with (init_soc, battery_module.py:96-106) until the
+    # first update recomputes it as current_charge / max_capacity (:125-130); init_soc * max_capacity / max_capacity can
+    # differ from init_soc in the last bit, so a record built from init_soc carries it.  None = current_charge / max_capacity.
+    soc: Optional[float] = None
+
+    @property
+    def reported_soc(self):
+        return self.current_charge / self.max_capacity if self.soc is None else self.soc
 
     @property
     def min_soc(self):

@@ -95,7 +95,8 @@ def read_reference_scenario(yaml_path):
     elif bp.get("init_charge") is not None:
         battery.current_charge = float(bp["init_charge"])
     else:
-        battery.current_charge = float(bp["init_soc"]) * battery.max_capacity
+        battery.soc = float(bp["init_soc"])
+        battery.current_charge = battery.soc * battery.max_capacity
     genset = None
     if gen is not None:
         gp, gs = gen[1], gen[2]

@@ -116,8 +116,9 @@ def series_state(ts, t, horizon, low, high):
     return np.array(rows, dtype=np.float64).reshape(-1)
 
 
-def state_dict(p, t, charge, genset):
-    """Unnormalised state of every module at step t, keyed like the reference's `state_dict()`s."""
+def state_dict(p, t, charge, genset, soc=None):
+    """Unnormalised state of every module at step t, keyed like the reference's `state_dict()`s.  `soc`: the battery's
+    stored `_soc` when it is not charge / max_capacity (before its first update, battery_module.py:89, 125-130)."""
     H = p.forecast_horizon
     out = OrderedDict()
 
@@ -138,7 +139,7 @@ def state_dict(p, t, charge, genset):
     if p.has_genset:
         cs, gs, up, dn = genset
         out["genset"] = OrderedDict(current_status=int(cs), goal_status=int(gs), steps_until_up=int(up), steps_until_down=int(dn))
-    out["battery"] = OrderedDict(soc=charge / p.battery.max_capacity, current_charge=charge)
+    out["battery"] = OrderedDict(soc=charge / p.battery.max_capacity if soc is None else soc, current_charge=charge)
     if p.has_grid:
         ts_entries("grid", ["import_price", "export_price", "co2_per_kwh", "grid_status"], p.grid.time_series, False)
     return out

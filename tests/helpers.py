@@ -24,10 +24,68 @@ def custom_params(golden_custom, i):
             ts[:, 3] = 1.0
         grid = GridParams(max_import=70, max_export=30, time_series=ts, cost_per_unit_co2=0.15)
     battery = BatteryParams(min_capacity=10, max_capacity=100, max_charge=40, max_discharge=45, efficiency=float(eff),
-                            battery_cost_cycle=0.05, current_charge=0.6 * 100)
+                            battery_cost_cycle=0.05, current_charge=0.6 * 100, soc=0.6)
     return MicrogridParams(battery=battery, genset=genset, grid=grid, load_ts=z["load"], pv_ts=z["pv"],
                            loss_load_cost=9.0, overgeneration_cost=1.5, forecast_horizon=int(H),
                            final_step=int(final_step))
+
+
+def fuzz_spec(z, i):
+    return dict(zip([str(c) for c in z["spec_cols"]], z[f"f{i}_spec"]))
+
+
+def fuzz_params(z, i):
+    """Rebuild randomised grid i of tests/golden/fuzz.npz (see tests/golden/make_fuzz.py: draw_spec / build)."""
+    s = fuzz_spec(z, i)
+    genset = grid = None
+    if s["has_gen"]:
+        genset = GensetParams.with_init(init_start_up=bool(s["g_init"]), running_min_production=s["g_min"],
+                                        running_max_production=s["g_max"], genset_cost=s["g_cost"], co2_per_unit=s["g_co2"],
+                                        cost_per_unit_co2=s["g_cco2"], start_up_time=int(s["g_U"]),
+                                        wind_down_time=int(s["g_D"]), allow_abortion=bool(s["g_abort"]))
+    if s["has_grid"]:
+        grid = GridParams(max_import=s["r_imp"], max_export=s["r_exp"], time_series=z[f"f{i}_grid_ts"],
+                          cost_per_unit_co2=s["r_cco2"])
+    battery = BatteryParams(min_capacity=s["b_min"], max_capacity=s["b_max"], max_charge=s["b_charge"],
+                            max_discharge=s["b_discharge"], efficiency=s["b_eff"], battery_cost_cycle=s["b_cost"],
+                            current_charge=s["b_init_soc"] * s["b_max"], soc=s["b_init_soc"])
+    return MicrogridParams(battery=battery, genset=genset, grid=grid, load_ts=z[f"f{i}_load"], pv_ts=z[f"f{i}_pv"],
+                           loss_load_cost=s["llc"], overgeneration_cost=s["ogc"], forecast_horizon=int(s["H"]),
+                           initial_step=int(s["initial_step"]), current_step=int(s["initial_step"]),
+                           final_step=int(s["final_step"]))
+
+
+def fuzz_modules(z, i, ns=None):
+    """Grid i of tests/golden/fuzz.npz as a list of reference-style MODULES, with the keyword arguments make_fuzz.build hands
+    to the reference's constructors (initial_step is applied afterwards through `Microgrid.initial_step`, as there)."""
+    if ns is None:
+        from pymgrid_b200 import modules as ns
+    s = fuzz_spec(z, i)
+    ts_kw = dict(forecaster="oracle" if s["H"] > 0 else None, forecast_horizon=int(s["H"]) if s["H"] > 0 else 23,
+                 final_step=int(s["final_step"]))
+    mods = [ns.LoadModule(time_series=z[f"f{i}_load"], **ts_kw), ("pv", ns.RenewableModule(time_series=z[f"f{i}_pv"], **ts_kw))]
+    if s["has_gen"]:
+        mods.append(ns.GensetModule(running_min_production=s["g_min"], running_max_production=s["g_max"],
+                                    genset_cost=s["g_cost"], co2_per_unit=s["g_co2"], cost_per_unit_co2=s["g_cco2"],
+                                    start_up_time=int(s["g_U"]), wind_down_time=int(s["g_D"]),
+                                    allow_abortion=bool(s["g_abort"]), init_start_up=bool(s["g_init"])))
+    mods.append(ns.BatteryModule(min_capacity=s["b_min"], max_capacity=s["b_max"], max_charge=s["b_charge"],
+                                 max_discharge=s["b_discharge"], efficiency=s["b_eff"], battery_cost_cycle=s["b_cost"],
+                                 init_soc=s["b_init_soc"]))
+    if s["has_grid"]:
+        mods.append(ns.GridModule(max_import=s["r_imp"], max_export=s["r_exp"], time_series=z[f"f{i}_grid_ts"],
+                                  cost_per_unit_co2=s["r_cco2"], **ts_kw))
+    return mods
+
+
+def overfull_params(z):
+    """tests/golden/fuzz.npz `over_*`: a battery whose charge sits one ulp above max_capacity (make_fuzz.overfull_battery)."""
+    mn, mx, ch, dis, eff, cc, imp, exp = z["over_spec"]
+    battery = BatteryParams(min_capacity=mn, max_capacity=mx, max_charge=ch, max_discharge=dis, efficiency=eff,
+                            battery_cost_cycle=cc, current_charge=float(z["over_charge"]))
+    grid = GridParams(max_import=imp, max_export=exp, time_series=z["over_grid_ts"])
+    return MicrogridParams(battery=battery, grid=grid, load_ts=z["over_load"], pv_ts=z["over_pv"], loss_load_cost=10.0,
+                           overgeneration_cost=1.0, forecast_horizon=3)
 
 
 def jump_to(params, step):

@@ -282,6 +282,38 @@ def test_microgrid_from_reference_style_modules(golden, i):
     np.testing.assert_array_equal(flat(m.reset()), z[f"c{i}_after_reset_obs"])
 
 
+@pytest.mark.parametrize("i", (1, 8, 16, 22))
+def test_battery_soc_before_the_first_update(golden, i):
+    """The reference's BatteryModule reports the soc it was CONSTRUCTED with until its first update recomputes it from the
+    charge (battery_module.py:89, 125-130); for these grids init_soc * max_capacity / max_capacity != init_soc in the last
+    bit.  reset observation, module view, state_dict and the first logged row carry the constructed value; everything after
+    the first step the derived one (tests/golden/fuzz.npz, recorded from the live reference)."""
+    import warnings
+    from pymgrid_b200 import Microgrid
+    from tests.helpers import fuzz_modules, fuzz_spec
+    z = golden["fuzz"]
+    s = fuzz_spec(z, i)
+    assert s["b_init_soc"] * s["b_max"] / s["b_max"] != s["b_init_soc"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = Microgrid(fuzz_modules(z, i), loss_load_cost=s["llc"], overgeneration_cost=s["ogc"])
+    if s["initial_step"]:
+        m.initial_step = int(s["initial_step"])
+    flat = lambda obs: np.concatenate([obs[name][0] for name in SORTED if name in obs])   # noqa: E731
+    np.testing.assert_array_equal(flat(m.reset()), z[f"f{i}_reset_obs"])
+    before = z[f"f{i}_soc_before"]
+    assert m.modules.battery[0].soc == before[0] == s["b_init_soc"] and m.state_dict()["battery"][0]["soc"] == before[1]
+    for k, a in enumerate(z[f"f{i}_n_a"]):
+        obs, reward, done, _ = m.run(control(m.params, a))
+        np.testing.assert_array_equal(flat(obs), z[f"f{i}_n_o"][k])
+        assert reward == z[f"f{i}_n_r"][k]
+    log = m.get_log()
+    np.testing.assert_array_equal(log[("battery", 0, "soc")].values.astype(float), z[f"f{i}_log_soc"])
+    np.testing.assert_array_equal(log[("battery", 0, "current_charge")].values.astype(float), z[f"f{i}_log_charge"])
+    assert m.modules.battery[0].soc == float(z[f"f{i}_soc_after"])
+    assert m.modules.battery[0].soc == m.modules.battery[0].current_charge / s["b_max"]
+
+
 def test_default_module_names_and_trajectory_func(golden):
     """An un-named RenewableModule is called 'renewable' in observations, info, log and `modules` (renewable_module.py:84);
     trajectory_func is validated at construction and applied on every reset (microgrid.py:167-225)."""

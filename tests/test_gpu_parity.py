@@ -10,7 +10,7 @@ import torch
 
 from oracle.oracle import OracleBatch
 from pymgrid_b200.scenario import load_pymgrid25
-from tests.helpers import custom_params, jump_to
+from tests.helpers import custom_params, fuzz_params, jump_to, overfull_params
 
 pytestmark = pytest.mark.gpu
 CONTAINER = ("genset", "battery", "grid")
@@ -124,6 +124,82 @@ def test_custom_grids_golden(golden, i):
     ro = bm.reset()
     np.testing.assert_array_equal(ro[0].cpu().numpy(), z[f"c{i}_after_reset_obs"])
     assert torch.equal(charge, bm.groups[0].charge) and (bm.groups[0].step == 0).all()
+
+
+@pytest.mark.parametrize("i", range(40))
+def test_fuzz_grids_golden(golden, i):
+    """Randomised constructor arguments recorded from the live reference (tests/golden/make_fuzz.py): every architecture
+    (with and without genset / grid), horizons 0 .. 40, initial_step > 0, final_step inside the series, min_capacity 0,
+    running_min_production 0 or == max, max_export 0, init_soc that does not survive * max_capacity / max_capacity.
+    Continuous steps (normalised, then unnormalised beyond every limit), the discrete env with slow gensets, and
+    rule-based control as one persistent rollout -- all bit for bit."""
+    z = golden["fuzz"]
+    g = lambda k: z[f"f{i}_{k}"]  # noqa: E731
+    p = fuzz_params(z, i)
+    bm = engine([p], np.zeros(2, dtype=np.int64), with_flags=True)       # two replicas fed the same actions
+    ro = bm.reset()
+    for e in range(2):
+        np.testing.assert_array_equal(ro[e].cpu().numpy(), g("reset_obs"))
+    np.testing.assert_array_equal(bm.observe()[1].cpu().numpy(), g("reset_obs"))
+    for seg, normalized in (("n", True), ("u", False)):
+        n = len(g(f"{seg}_r"))
+        seq = [dict(a=g(f"{seg}_a")[:n], r=g(f"{seg}_r"), d=g(f"{seg}_d"), o=g(f"{seg}_o"), i=g(f"{seg}_i"), s=g(f"{seg}_s"))] * 2
+        check_against_golden(bm, seq, normalized=normalized)
+        err = int(g(f"{seg}_err"))
+        if err >= 0:     # the reference raised AssertionError (base_module.py:272) on this action
+            assert err == n
+            bm.step(group_actions(bm, [g(f"{seg}_a")[err]] * 2), normalized=normalized)
+            assert ((bm.groups[0].flags.cpu().numpy() & (1 << 4)) != 0).all()
+            break
+    # DiscreteMicrogridEnv: host-side action table == the reference's, expansion + step on the device
+    bm = engine([fuzz_params(z, i)], np.zeros(2, dtype=np.int64))
+    np.testing.assert_array_equal(bm.reset()[0].cpu().numpy(), g("d_reset_obs"))
+    mod, act = g("d_table_mod"), g("d_table_act")
+    table = bm.action_tables[0]
+    assert len(table) == len(mod)
+    for row, pl in enumerate(table):
+        assert [tuple(x) for x in pl] == [(int(m), int(a)) for m, a in zip(mod[row], act[row]) if m >= 0]
+    for k, a in enumerate(g("d_actions")):
+        obs, reward, done, _ = bm.step_discrete(torch.full((2,), int(a), dtype=torch.int32, device="cuda"))
+        assert reward[1].item() == g("d_rewards")[k] and bool(done[1].item()) == bool(g("d_dones")[k]), k
+        np.testing.assert_array_equal(obs[1].cpu().numpy(), g("d_obs")[k], err_msg=f"discrete step {k}")
+    np.testing.assert_array_equal(state_rows(bm)[1], g("d_state"))
+    # RuleBasedControl: the sorted list chosen on the host, the whole run in one persistent kernel
+    bm = engine([fuzz_params(z, i)], np.zeros(2, dtype=np.int64))
+    want = [(int(m), int(a)) for m, a in zip(g("rbc_list_mod"), g("rbc_list_act"))]
+    assert [tuple(x) for x in bm.action_tables[0][int(bm.rbc_actions()[0][0].item())]] == want
+    out = bm.rollout_rbc(len(g("rbc_rewards")), keep_obs=False)
+    np.testing.assert_array_equal(out["reward"][:, 1].cpu().numpy(), g("rbc_rewards"))
+    assert out["done"][-1].all() and not out["done"][:-1].any()
+    np.testing.assert_array_equal(state_rows(bm)[0], g("rbc_final_state"))
+
+
+def test_overfull_battery_is_flagged_where_the_reference_asserts(golden):
+    """charge one ulp above max_capacity: MG_FLAG_NEGATIVE_ABSORB where the reference raises AssertionError
+    (base_module.py:272 on a continuous charge request, priority_list.py:124 on a list that makes the battery absorb);
+    discharging and the list that lets the grid take the surplus first run normally, bit for bit."""
+    z = golden["fuzz"]
+    act = lambda a, b: torch.tensor([[a, b]] * 3, dtype=torch.float64, device="cuda")   # noqa: E731  container order: battery, grid
+    bm = engine([overfull_params(z)], np.zeros(3, dtype=np.int64), with_flags=True)
+    bm.step(act(-10.0, 0.0), normalized=False)
+    assert ((bm.groups[0].flags & (1 << 4)) != 0).all()
+    bm = engine([overfull_params(z)], np.zeros(3, dtype=np.int64), with_flags=True)
+    obs, reward, _, _ = bm.step(act(5.0, -9.0), normalized=False)
+    assert ((bm.groups[0].flags & 0x7f) == 0).all() and reward[2].item() == float(z["over_discharge_reward"])
+    np.testing.assert_array_equal(obs[2].cpu().numpy(), z["over_discharge_obs"])
+    np.testing.assert_array_equal(state_rows(bm)[2], z["over_discharge_state"])
+    for a, raised in enumerate(z["over_discrete_raised"]):
+        bm = engine([overfull_params(z)], np.zeros(3, dtype=np.int64), with_flags=True)
+        _, reward, _, _ = bm.step_discrete(torch.full((3,), a, dtype=torch.int32, device="cuda"))
+        flagged = (bm.groups[0].flags & (1 << 4)) != 0
+        if str(raised):
+            assert flagged.all()
+        else:
+            assert not flagged.any() and reward[1].item() == z["over_discrete_reward"][a]
+    # the same through the persistent kernel: flags are OR-ed over the rollout
+    bm = engine([overfull_params(z)], np.zeros(3, dtype=np.int64), with_flags=True)
+    bm.rollout(torch.zeros((2, 3), dtype=torch.int32, device="cuda"), discrete=True, keep_obs=False)
+    assert ((bm.groups[0].flags & (1 << 4)) != 0).all()
 
 
 def _discrete_cases(z):

@@ -18,7 +18,9 @@ class HostBackedMicrogrid(Microgrid):
 
     def __init__(self, params, state):
         self.params = params
-        self._st = dict(t=int(state[0]), charge=float(state[1]), genset=tuple(int(x) for x in state[2:6]))
+        self._st = dict(t=int(state[0]), charge=float(state[1]), genset=tuple(int(x) for x in state[2:6]),
+                        soc=params.battery.reported_soc if float(state[1]) == params.battery.current_charge
+                        else float(state[1]) / params.battery.max_capacity)
         self._initial_step, self._final_step = params.initial_step, params.final_step
         names = ["load", "pv", "unbalanced_energy"] + (["genset"] if params.has_genset else []) + ["battery"] + \
                 (["grid"] if params.has_grid else [])

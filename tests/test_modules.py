@@ -11,7 +11,7 @@ import pytest
 from oracle.oracle import OracleGrid
 from pymgrid_b200 import modules as M
 from pymgrid_b200.modules import params_from_modules
-from tests.helpers import custom_modules, custom_params, state_from_oracle
+from tests.helpers import custom_modules, custom_params, fuzz_modules, fuzz_params, fuzz_spec, jump_to, state_from_oracle
 
 
 def assert_same_params(a, b):
@@ -44,6 +44,23 @@ def test_modules_fold_into_the_same_record_and_reproduce_the_reference(golden, i
         np.testing.assert_array_equal(ob, z[f"c{i}_o"][k])
         np.testing.assert_array_equal(info, z[f"c{i}_i"][k])
         np.testing.assert_array_equal(state_from_oracle(o), z[f"c{i}_s"][k])
+
+
+@pytest.mark.parametrize("i", range(0, 40, 3))
+def test_randomised_modules_fold_into_the_same_record(golden, i):
+    """Randomised constructor arguments (tests/golden/fuzz.npz): the module classes fold into the record the parity tests
+    build by hand -- including the soc the battery was constructed with, which the reference reports until the battery's
+    first update (battery_module.py:89, 125-130) -- and the oracle run on it returns the reference's reset observation."""
+    z = golden["fuzz"]
+    s = fuzz_spec(z, i)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        p = params_from_modules(fuzz_modules(z, i), loss_load_cost=s["llc"], overgeneration_cost=s["ogc"])
+    assert p.battery.soc == s["b_init_soc"] and p.battery.reported_soc == z[f"f{i}_soc_before"][0] == z[f"f{i}_soc_before"][1]
+    if s["initial_step"]:
+        p = jump_to(p, int(s["initial_step"]))
+    assert_same_params(p, fuzz_params(z, i))
+    np.testing.assert_array_equal(OracleGrid(p).reset(), z[f"f{i}_reset_obs"])
 
 
 def test_default_names_and_unbalanced_module_defaults(golden):

@@ -5,7 +5,7 @@ import pytest
 
 from oracle.oracle import MOD_BATTERY, MOD_GENSET, MOD_GRID, OracleBatch, OracleGrid  # noqa: F401
 from pymgrid_b200.scenario import load_pymgrid25
-from tests.helpers import custom_params, jump_to, state_from_oracle
+from tests.helpers import custom_params, fuzz_params, jump_to, overfull_params, state_from_oracle
 
 
 def run_and_compare(o, actions, rewards, dones, obs, infos, states, normalized=True):
@@ -125,6 +125,83 @@ def test_custom_grids(golden, i):
     charge = o.state["charge"]
     np.testing.assert_array_equal(o.reset(), z[f"c{i}_after_reset_obs"])
     assert o.state["charge"] == charge and o.state["t"] == 0
+
+
+@pytest.mark.parametrize("i", range(40))
+def test_fuzz_grids(golden, i):
+    """Randomised constructor arguments (tests/golden/make_fuzz.py): continuous steps (normalised, then unnormalised
+    beyond every limit), the discrete env's priority-list expansion with slow gensets, and RuleBasedControl's sorted list."""
+    from pymgrid_b200 import priority_list as PL
+    z = golden["fuzz"]
+    g = lambda k: z[f"f{i}_{k}"]  # noqa: E731
+    p = fuzz_params(z, i)
+    o = OracleGrid(p)
+    np.testing.assert_array_equal(o.reset(), g("reset_obs"))
+    for seg, normalized in (("n", True), ("u", False)):
+        n = len(g(f"{seg}_r"))
+        run_and_compare(o, g(f"{seg}_a")[:n], g(f"{seg}_r"), g(f"{seg}_d"), g(f"{seg}_o"), g(f"{seg}_i"), g(f"{seg}_s"),
+                        normalized=normalized)
+        err = int(g(f"{seg}_err"))
+        if err >= 0:     # the reference raised AssertionError (base_module.py:272) on this action
+            assert err == n
+            _, _, _, _, flags = o.run(g(f"{seg}_a")[err], normalized=normalized)
+            assert flags & (1 << 4), flags
+            break
+    # discrete env: table built on the host, expansion by the oracle
+    o = OracleGrid(fuzz_params(z, i))
+    np.testing.assert_array_equal(o.reset(), g("d_reset_obs"))
+    table = PL.priority_lists(p.has_genset, p.has_grid, p.genset.running_min_production if p.has_genset else None)
+    mod, act = g("d_table_mod"), g("d_table_act")
+    assert len(table) == len(mod)
+    for row, pl in enumerate(table):
+        assert [(int(m), int(a)) for m, a in zip(mod[row], act[row]) if m >= 0] == list(pl)
+    for k, a in enumerate(g("d_actions")):
+        ctrl = o.priority_control(table[a])
+        np.testing.assert_array_equal(ctrl, g("d_controls")[k], err_msg=f"control {k}")
+        ob, r, d, _, _ = o.run(ctrl, normalized=False)
+        assert r == g("d_rewards")[k] and d == bool(g("d_dones")[k])
+        np.testing.assert_array_equal(ob, g("d_obs")[k])
+    np.testing.assert_array_equal(state_from_oracle(o), g("d_state"))
+    # rule based control: the automatically sorted list, then its whole run
+    o = OracleGrid(fuzz_params(z, i))
+    o.reset()
+    pl = PL.rbc_priority_list(p)
+    assert [m for m, _ in pl] == list(g("rbc_list_mod")) and [a for _, a in pl] == list(g("rbc_list_act"))
+    rewards = []
+    for _ in range(len(g("rbc_rewards"))):
+        _, r, _, _, _ = o.run(o.priority_control(pl), normalized=False)
+        rewards.append(r)
+    np.testing.assert_array_equal(np.array(rewards), g("rbc_rewards"))
+    np.testing.assert_array_equal(state_from_oracle(o), g("rbc_final_state"))
+
+
+def test_overfull_battery_is_flagged_where_the_reference_asserts(golden):
+    """charge one ulp above max_capacity (reachable by rounding): the reference refuses a continuous charge request
+    (AssertionError base_module.py:272) and any priority list that reaches the battery while there is surplus energy
+    (AssertionError priority_list.py:124); both set the NEGATIVE_ABSORB flag here.  Discharging and lists that never make
+    the battery absorb run normally (tests/golden/fuzz.npz over_*, make_fuzz.overfull_battery)."""
+    from pymgrid_b200 import priority_list as PL
+    z = golden["fuzz"]
+    assert str(z["over_continuous_charge_raised"]) == "base_module.py:272"
+    o = OracleGrid(overfull_params(z))
+    _, _, _, _, flags = o.run(np.array([-10.0, 0.0]), normalized=False)
+    assert flags & (1 << 4)
+    o = OracleGrid(overfull_params(z))
+    ob, r, _, _, flags = o.run(np.array([5.0, -9.0]), normalized=False)
+    assert flags & 0x7f == 0 and r == float(z["over_discharge_reward"])
+    np.testing.assert_array_equal(ob, z["over_discharge_obs"])
+    np.testing.assert_array_equal(state_from_oracle(o), z["over_discharge_state"])
+    table = PL.priority_lists(False, True)
+    assert [list(pl) for pl in table] == [[(int(m), int(a)) for m, a in zip(mr, ar) if m >= 0]
+                                          for mr, ar in zip(z["over_table_mod"], z["over_table_act"])]
+    for a, pl in enumerate(table):
+        o = OracleGrid(overfull_params(z))
+        ctrl = o.priority_control(pl)
+        raised = str(z["over_discrete_raised"][a])
+        assert bool(o.list_flags & (1 << 4)) == (raised == "priority_list.py:124"), (a, raised)
+        if not raised:
+            _, r, _, _, flags = o.run(ctrl, normalized=False)
+            assert flags & 0x7f == 0 and r == z["over_discrete_reward"][a]
 
 
 def _discrete_cases(z):
