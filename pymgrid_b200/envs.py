@@ -111,8 +111,8 @@ class _BaseEnv:
         from .microgrid import ModuleContainerView, ModuleView
         names = ["load", "pv", "unbalanced_energy"] + (["genset"] if self.params.has_genset else []) + ["battery"] + \
                 (["grid"] if self.params.has_grid else [])
-        ren = self.params.renewable_name
-        return ModuleContainerView((ren if n == "pv" else n, [ModuleView(self, n, ren if n == "pv" else n)]) for n in names)
+        nm = lambda n: {"pv": self.params.renewable_name, "unbalanced_energy": self.params.unbalanced_name}.get(n, n)   # noqa: E731
+        return ModuleContainerView((nm(n), [ModuleView(self, n, nm(n))]) for n in names)
 
     def _state(self):     # live state of env 0, for the module views
         g = self.group

@@ -26,7 +26,8 @@ class ModuleView:
 
     def __init__(self, microgrid, kind, name=None):
         # kind: the engine's module key (load, pv, unbalanced_energy, genset, battery, grid); name: what the caller
-        # called it -- only the renewable can be renamed (('pv', module) in pymgrid25, 'renewable' by default)
+        # called it -- the renewable (('pv', module) in pymgrid25, 'renewable' by default) and the slack module
+        # ('unbalanced_energy' in pymgrid25, 'balancing' by default) carry names of their own
         self._m, self._kind, self.name = microgrid, kind, (name or kind, 0)
 
     def __repr__(self):
@@ -351,8 +352,7 @@ class Microgrid:
         self.raise_errors = bool(params.meta.get("raise_errors", False))
         names = ["load", "pv", "unbalanced_energy"] + (["genset"] if params.has_genset else []) + ["battery"] + \
                 (["grid"] if params.has_grid else [])
-        self._modules = ModuleContainerView((self._ren if n == "pv" else n, [ModuleView(self, n, self._ren if n == "pv" else n)])
-                                            for n in names)
+        self._modules = ModuleContainerView((self._caller_name(n), [ModuleView(self, n, self._caller_name(n))]) for n in names)
         self.trajectory_func = self._check_trajectory_func(trajectory_func)
 
     @property
@@ -384,14 +384,18 @@ class Microgrid:
                              f'was greater than or equal to final_step.')
         return trajectory_func
 
+    def _caller_name(self, kind):
+        """engine key -> the caller's name of that module: only the renewable ('pv' in pymgrid25, 'renewable' by default,
+        'PV' in MicrogridGenerator grids) and the slack module ('unbalanced_energy' in pymgrid25, 'balancing' when
+        Microgrid(modules) appends it) carry names of their own"""
+        return {"pv": self.params.renewable_name, "unbalanced_energy": self.params.unbalanced_name}.get(kind, kind)
+
     def _named(self, d):
-        """engine key 'pv' -> the caller's name of the renewable module, for dicts keyed by module name or by
-        (module name, number, field)"""
-        if self._ren == "pv":
+        """engine keys -> caller names, for dicts keyed by module name or by (module name, number, field)"""
+        if self._ren == "pv" and self.params.unbalanced_name == "unbalanced_energy":
             return d
-        ren = self._ren
-        return type(d)(((ren if k == "pv" else (ren,) + k[1:] if isinstance(k, tuple) and k[0] == "pv" else k), v)
-                       for k, v in d.items())
+        nm = self._caller_name
+        return type(d)(((nm(k) if not isinstance(k, tuple) else (nm(k[0]),) + k[1:]), v) for k, v in d.items())
 
     # ---- construction ------------------------------------------------------------------------------------
     @classmethod
@@ -445,7 +449,7 @@ class Microgrid:
 
     @property
     def flex(self):
-        return self._typed((self._ren, "unbalanced_energy"))
+        return self._typed((self._ren, self.params.unbalanced_name))
 
     @property
     def controllable(self):
@@ -524,7 +528,10 @@ class Microgrid:
             self._engine.set_trajectories(np.array([initial_step]), np.array([final_step]))
         obs = self._engine.reset()
         self._log_rows = []
-        out = self._named(views.obs_row_to_dict(obs[0].cpu().numpy(), self.params, self._obs_order))
+        by_name = self._named(views.obs_row_to_dict(obs[0].cpu().numpy(), self.params, self._obs_order))
+        # reset() lists the modules in CONTAINER order (fixed, flex, controllable -- `modules.to_dict()`, microgrid.py:217-219),
+        # run() in dispatch order
+        out = type(by_name)((name, by_name[name]) for name in self._modules)
         out["balance"], out["other"] = {}, {}
         return out
 

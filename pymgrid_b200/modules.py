@@ -202,7 +202,7 @@ class GridModule(_TimeSeriesModule):
 class UnbalancedEnergyModule(_Module):
     """reference: modules/unbalanced_energy_module.py:13-26."""
     module_type = ("balancing", "flex")
-    _default_name = "unbalanced_energy"
+    _default_name = "balancing"
 
     def __init__(self, raise_errors, initial_step=0, loss_load_cost=10, overgeneration_cost=2.0):
         self.loss_load_cost, self.overgeneration_cost = loss_load_cost, overgeneration_cost
@@ -234,8 +234,9 @@ def params_from_modules(modules, add_unbalanced_module=True, loss_load_cost=10.0
         raise TypeError("modules must be list-like of modules.")
     named = _named(list(modules))
     if add_unbalanced_module:
-        named.append(("unbalanced_energy", UnbalancedEnergyModule(raise_errors=False, loss_load_cost=loss_load_cost,
-                                                                 overgeneration_cost=overgeneration_cost)))
+        # appended un-named, so the container calls it 'balancing' (module_type[0]; microgrid.py:170-171)
+        named.append(("balancing", UnbalancedEnergyModule(raise_errors=False, loss_load_cost=loss_load_cost,
+                                                         overgeneration_cost=overgeneration_cost)))
     by_kind = {}
     for name, m in named:
         by_kind.setdefault(m.module_type[0], []).append((name, m))
@@ -246,13 +247,15 @@ def params_from_modules(modules, add_unbalanced_module=True, loss_load_cost=10.0
             raise NotImplementedError(
                 "the fused B200 step covers microgrids with exactly one load, one renewable, one battery and one "
                 f"unbalanced-energy module and at most one genset and one grid; got {counts}")
-    canonical = {"battery": "battery", "genset": "genset", "grid": "grid", "load": "load", "balancing": "unbalanced_energy"}
+    canonical = {"battery": "battery", "genset": "genset", "grid": "grid", "load": "load"}
     for kind, want in canonical.items():
         for name, _ in by_kind.get(kind, []):
             if name != want:
-                raise NotImplementedError(f"module name {name!r}: only the renewable module can be renamed (the {kind} "
+                raise NotImplementedError(f"module name {name!r}: only the renewable and the slack module can be renamed (the {kind} "
                                           f"module is addressed as {want!r} in controls, observations and logs)")
-    (ren_name, ren), (_, load), (_, bat), (_, unb) = (by_kind[k][0] for k in ("renewable", "load", "battery", "balancing"))
+    if len({name for name, _ in named}) != len(named):      # module_container.py:391-396
+        raise NameError("two modules share a name: " + repr(sorted(name for name, _ in named)))
+    (ren_name, ren), (_, load), (_, bat), (unb_name, unb) = (by_kind[k][0] for k in ("renewable", "load", "battery", "balancing"))
     genset = by_kind["genset"][0][1] if "genset" in by_kind else None
     grid = by_kind["grid"][0][1] if "grid" in by_kind else None
     if "battery" <= ren_name <= "load":
@@ -281,5 +284,5 @@ def params_from_modules(modules, add_unbalanced_module=True, loss_load_cost=10.0
                            pv_ts=ren.time_series[:, 0], loss_load_cost=unb.loss_load_cost,
                            overgeneration_cost=unb.overgeneration_cost, forecast_horizon=int(horizons.pop()),
                            initial_step=initial_step, current_step=initial_step, final_step=int(final.pop()),
-                           renewable_name=ren_name, forecasters=forecasters,
+                           renewable_name=ren_name, unbalanced_name=unb_name, forecasters=forecasters,
                            meta={"raise_errors": any(m.raise_errors for m in every)})

@@ -128,6 +128,9 @@ class MicrogridParams:
     load_scale: float = 1.0
     pv_scale: float = 1.0
     renewable_name: str = "pv"      # 'PV' for MicrogridGenerator grids: decides the gym-sorted observation order
+    # name of the slack module in dicts, logs and `modules`: 'unbalanced_energy' in the pymgrid25 YAMLs; 'balancing' (the
+    # class's module_type[0], module_container.py:366-374) when Microgrid(modules) appends it itself (microgrid.py:170-171)
+    unbalanced_name: str = "unbalanced_energy"
     # Microgrid(reward_shaping_func=...): None, "pv_curtailment" (PVCurtailmentShaper) or "battery_discharge"
     # (BatteryDischargeShaper), microgrid/reward_shaping/*.py; the shaped value replaces the step reward (utils/step.py:38-46)
     reward_shaper: Optional[str] = None

@@ -27,7 +27,7 @@ def custom_params(golden_custom, i):
                             battery_cost_cycle=0.05, current_charge=0.6 * 100, soc=0.6)
     return MicrogridParams(battery=battery, genset=genset, grid=grid, load_ts=z["load"], pv_ts=z["pv"],
                            loss_load_cost=9.0, overgeneration_cost=1.5, forecast_horizon=int(H),
-                           final_step=int(final_step))
+                           final_step=int(final_step), unbalanced_name="balancing")
 
 
 def fuzz_spec(z, i):
@@ -52,7 +52,7 @@ def fuzz_params(z, i):
     return MicrogridParams(battery=battery, genset=genset, grid=grid, load_ts=z[f"f{i}_load"], pv_ts=z[f"f{i}_pv"],
                            loss_load_cost=s["llc"], overgeneration_cost=s["ogc"], forecast_horizon=int(s["H"]),
                            initial_step=int(s["initial_step"]), current_step=int(s["initial_step"]),
-                           final_step=int(s["final_step"]))
+                           final_step=int(s["final_step"]), unbalanced_name="balancing")
 
 
 def fuzz_modules(z, i, ns=None):

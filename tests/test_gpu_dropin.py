@@ -109,9 +109,9 @@ def test_discrete_env_single_and_batched(golden):
         benv = DiscreteMicrogridEnv.from_scenario(n, batch=257)
         benv.reset()
         for k, a in enumerate(z[f"{tag}_actions"][:15]):
-            obs, r, d, _ = benv.step(torch.full((257,), int(a), dtype=torch.int32, device="cuda"))
+            obs, r, d, _ = benv.step(torch.full((257,), int(a), dtype=torch.int32, device=benv.engine.device))
             assert obs.shape == (257, env.observation_space.shape[0])
-            assert (r == z[f"{tag}_rewards"][k]).all() and (obs == torch.from_numpy(z[f"{tag}_obs"][k]).cuda()).all()
+            assert (r == z[f"{tag}_rewards"][k]).all() and (obs == torch.from_numpy(z[f"{tag}_obs"][k]).to(obs.device)).all()
 
 
 def test_continuous_env_config2_shape(golden):
@@ -123,9 +123,9 @@ def test_continuous_env_config2_shape(golden):
     assert env.action_layout == {"battery": 0, "grid": 1}
     env.reset()
     for k, a in enumerate(z["s0_a0"][:25]):
-        act = torch.from_numpy(np.tile(a, (4096, 1))).cuda()
+        act = torch.from_numpy(np.tile(a, (4096, 1))).to(env.engine.device)
         obs, r, d, _ = env.step(act)
-        assert (r == z["s0_r0"][k]).all() and (obs == torch.from_numpy(z["s0_o0"][k]).cuda()).all()
+        assert (r == z["s0_r0"][k]).all() and (obs == torch.from_numpy(z["s0_o0"][k]).to(obs.device)).all()
     single = ContinuousMicrogridEnv.from_scenario(1)          # gym-sorted action layout: battery, genset(2), grid
     assert single.action_layout == {"battery": 0, "genset": 1, "grid": 3}
     a = z["s1_a0"][0]                                          # golden actions are in container order: genset, battery, grid
@@ -314,6 +314,58 @@ def test_battery_soc_before_the_first_update(golden, i):
     assert m.modules.battery[0].soc == m.modules.battery[0].current_charge / s["b_max"]
 
 
+@pytest.mark.parametrize("i", (0, 5, 11, 12, 17, 24, 30, 38))
+def test_randomised_grids_through_the_drop_in_classes(golden, i):
+    """tests/golden/fuzz.npz through the reference-shaped classes, all built from the module list the reference was given:
+    Microgrid.run (dict keys, values, the AssertionError where the reference raised one), DiscreteMicrogridEnv (action
+    table, flat observations, rewards with slow gensets), RuleBasedControl (sorted list, run length, rewards, log)."""
+    import warnings
+    from pymgrid_b200 import Microgrid
+    from pymgrid_b200.algos import RuleBasedControl
+    from pymgrid_b200.envs import DiscreteMicrogridEnv
+    from tests.helpers import fuzz_modules, fuzz_spec
+    z = golden["fuzz"]
+    s = fuzz_spec(z, i)
+    g = lambda k: z[f"f{i}_{k}"]  # noqa: E731
+    warnings.simplefilter("ignore")
+
+    def build():
+        m = Microgrid(fuzz_modules(z, i), loss_load_cost=s["llc"], overgeneration_cost=s["ogc"])
+        if s["initial_step"]:
+            m.initial_step = int(s["initial_step"])
+            m.reset()
+        return m
+    flat = lambda obs: np.concatenate([obs[name][0] for name in SORTED if name in obs])   # noqa: E731
+    m = build()
+    names = ["load"] + (["genset"] if s["has_gen"] else []) + ["battery"] + (["grid"] if s["has_grid"] else []) + ["pv", "balancing"]
+    np.testing.assert_array_equal(flat(m.reset()), g("reset_obs"))
+    for seg, normalized in (("n", True), ("u", False)):
+        for k in range(len(g(f"{seg}_r"))):
+            obs, reward, done, info = m.run(control(m.params, g(f"{seg}_a")[k]), normalized=normalized)
+            assert list(obs) == list(info) == names
+            np.testing.assert_array_equal(flat(obs), g(f"{seg}_o")[k])
+            assert reward == g(f"{seg}_r")[k] and done == bool(g(f"{seg}_d")[k])
+        err = int(g(f"{seg}_err"))
+        if err >= 0:
+            with pytest.raises(AssertionError):
+                m.run(control(m.params, g(f"{seg}_a")[err]), normalized=normalized)
+            break
+    env = DiscreteMicrogridEnv.from_microgrid(build())
+    assert env.action_space.n == len(g("d_table_mod")) and env.observation_space.shape == g("d_reset_obs").shape
+    np.testing.assert_array_equal(env.reset(), g("d_reset_obs"))
+    for k, a in enumerate(g("d_actions")):
+        obs, r, d, _ = env.step(int(a))
+        assert r == g("d_rewards")[k] and d == bool(g("d_dones")[k])
+        np.testing.assert_array_equal(obs, g("d_obs")[k])
+    rbc = RuleBasedControl(build())
+    assert [{"genset": 0, "battery": 1, "grid": 2}[el.module[0]] for el in rbc.priority_list] == list(g("rbc_list_mod"))
+    assert [el.action for el in rbc.priority_list] == list(g("rbc_list_act"))
+    df = rbc.run()
+    assert len(df) == len(g("rbc_rewards")) and df.index[0] == int(s["initial_step"])
+    assert ("balancing", 0, "reward") in df.columns and ("unbalanced_energy", 0, "reward") not in df.columns
+    np.testing.assert_array_equal(df[("balance", 0, "reward")].values.astype(float), g("rbc_rewards"))
+
+
 def test_default_module_names_and_trajectory_func(golden):
     """An un-named RenewableModule is called 'renewable' in observations, info, log and `modules` (renewable_module.py:84);
     trajectory_func is validated at construction and applied on every reset (microgrid.py:167-225)."""
@@ -330,13 +382,17 @@ def test_default_module_names_and_trajectory_func(golden):
     assert calls == [(0, 60)] and m.initial_step == 0 and m.final_step == 60
     obs = m.reset()
     assert m.current_step == 10 and "renewable" in obs and "pv" not in obs
-    assert list(m.modules) == ["load", "renewable", "unbalanced_energy", "battery", "grid"]
-    assert m.modules.renewable[0].name == ("renewable", 0) and list(m.flex) == ["renewable", "unbalanced_energy"]
+    # the slack module Microgrid(modules) appends is called 'balancing' (its class's module_type[0]), not 'unbalanced_energy'
+    # as in the pymgrid25 YAMLs -- checked against the live reference for this very module list
+    assert list(m.modules) == ["load", "renewable", "balancing", "battery", "grid"]
+    assert m.modules.renewable[0].name == ("renewable", 0) and list(m.flex) == ["renewable", "balancing"]
+    assert m.modules.balancing[0].name == ("balancing", 0) and list(obs) == ["load", "renewable", "balancing", "battery", "grid", "balance", "other"]
     dones = []
     for k in range(4):
         obs, _, done, info = m.run({"battery": [0.5], "grid": [0.5]})
         dones.append(done)
         assert "renewable" in obs and "renewable" in info and "pv" not in info
+        assert list(obs) == list(info) == ["load", "battery", "grid", "renewable", "balancing"]
     assert dones == [False, False, False, True] and m.current_step == 14       # episode length = final - initial
     df = m.get_log()
     assert "renewable" in df.columns.get_level_values(0) and "pv" not in df.columns.get_level_values(0)

@@ -69,9 +69,12 @@ def test_default_names_and_unbalanced_module_defaults(golden):
     z = golden["custom"]
     p = params_from_modules(custom_modules(z, 4, renewable_name=None))
     assert (p.loss_load_cost, p.overgeneration_cost, p.renewable_name) == (10.0, 2.0, "renewable")
+    assert p.unbalanced_name == "balancing"     # module_type[0] of the appended module (module_container.py:366-374)
     mods = custom_modules(z, 4) + [M.UnbalancedEnergyModule(raise_errors=False, loss_load_cost=3.0, overgeneration_cost=0.5)]
     p = params_from_modules(mods, add_unbalanced_module=False)
-    assert (p.loss_load_cost, p.overgeneration_cost, p.renewable_name) == (3.0, 0.5, "pv")
+    assert (p.loss_load_cost, p.overgeneration_cost, p.renewable_name, p.unbalanced_name) == (3.0, 0.5, "pv", "balancing")
+    named = custom_modules(z, 4) + [("unbalanced_energy", M.UnbalancedEnergyModule(raise_errors=False))]
+    assert params_from_modules(named, add_unbalanced_module=False).unbalanced_name == "unbalanced_energy"
     with pytest.raises(NotImplementedError):
         params_from_modules(custom_modules(z, 4), add_unbalanced_module=False)       # no slack module at all
     with pytest.raises(NotImplementedError):
@@ -140,7 +143,7 @@ def test_module_sets_outside_the_fused_step_fail_loudly(golden):
             params_from_modules(bad)
     with pytest.raises(NotImplementedError, match="renewable module name"):
         params_from_modules(custom_modules(z, 0, renewable_name="d_pv"))
-    with pytest.raises(NotImplementedError, match="only the renewable module can be renamed"):
+    with pytest.raises(NotImplementedError, match="only the renewable and the slack module can be renamed"):
         params_from_modules([("storage", m) if isinstance(m, M.BatteryModule) else m for m in mods])
     with pytest.raises(TypeError):
         params_from_modules("battery")
