@@ -5,8 +5,12 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-SRC = os.path.join(_PKG, "csrc", "mg_engine.cu")
+SRC = os.path.join(_PKG, "csrc", "mg_engine.cu")                    # the pymgrid25 / MicrogridGenerator module set
+SRC_COMPOSE = os.path.join(_PKG, "csrc", "mg_compose.cu")           # any module list (include/pymgrid_b200_compose.h)
+SOURCES = [SRC, SRC_COMPOSE]
 HEADER = os.path.join(_ROOT, "include", "pymgrid_b200.h")
+DEPENDS = SOURCES + [HEADER, os.path.join(_ROOT, "include", "pymgrid_b200_compose.h"),
+                     os.path.join(_PKG, "csrc", "mg_compose_step.h")]
 LIB_DIR = os.path.join(_PKG, "_lib")
 LIB = os.path.join(LIB_DIR, "libpymgrid_b200.so")
 
@@ -25,7 +29,7 @@ def nvcc_path():
 def is_stale():
     if not os.path.exists(LIB):
         return True
-    return os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HEADER))
+    return os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in DEPENDS if os.path.exists(f))
 
 
 def build(force=False, verbose=False, extra=()):
@@ -33,7 +37,7 @@ def build(force=False, verbose=False, extra=()):
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     extra = list(extra) + os.environ.get("PYMGRID_B200_NVCC_EXTRA", "").split()
-    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-I", os.path.join(_ROOT, "include"), "-o", LIB, SRC]
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-I", os.path.join(_ROOT, "include"), "-o", LIB, *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -1,0 +1,814 @@
+"""Composed microgrids: `Microgrid.run` for ANY module list, on the GPU (C-ABI: include/pymgrid_b200_compose.h).
+
+The fused engine (`engine.BatchedMicrogrid`) covers the module set of every pymgrid25 / MicrogridGenerator grid.  The
+reference's `Microgrid` (src/pymgrid/microgrid/microgrid.py:100-325) takes any list of modules -- several loads and
+renewables (its own balance tests, tests/microgrid/test_microgrid.py:188-455), several batteries / gensets / grids, no
+battery, no slack module, one forecast horizon per time-series module.  This module is the host side of that general
+path:
+
+  Composition        the static structure of a module list: the container's listing and dispatch orders
+                     (module_container.py:355-413), action columns, observation blocks, parameter packing
+  ComposedBatch      B microgrids sharing one composition (own parameters, series, state): device tensors + mgc_* calls
+  ComposedMicrogrid  the reference's single-microgrid surface (run / reset / get_log / state_dict / sample_action / modules)
+                     on a batch of one; `pymgrid_b200.Microgrid(modules)` returns it when the list is outside the fused scope
+
+No CPU fallback: without the CUDA extension or a CUDA device, construction raises.  (`_library` is the test suite's hook
+for the host build of the same C source, tests/hostsim/.)
+"""
+import ctypes as C
+import warnings
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _cabi, views
+from .modules import (BatteryModule, GensetModule, GridModule, LoadModule, RenewableModule, UnbalancedEnergyModule, _Module,
+                      _named)
+
+MGC_ABI_VERSION = 1
+MGC_MAX_MODULES = 64
+MGC_INFO_SLOTS = 5
+MGC_BALANCE_SLOTS = 6
+MGC_CFG_HEADER = 2
+KIND = {"load": 0, "renewable": 1, "battery": 2, "genset": 3, "grid": 4, "balancing": 5}
+PARAM_COUNT = {"load": 3, "renewable": 3, "battery": 6, "genset": 8, "grid": 12, "balancing": 2}
+FLAG_GENSET_GOAL_RANGE, FLAG_NOT_A_SINK, FLAG_BALANCE, FLAG_BATTERY_MIN_CAP = 1 << 0, 1 << 1, 1 << 2, 1 << 3
+FLAG_NEGATIVE_ABSORB, FLAG_STEP_PAST_END, FLAG_CLIP, FLAG_CLIP_RAISES, FLAG_EXCESS = 1 << 4, 1 << 5, 1 << 8, 1 << 11, 1 << 14
+
+_i32, _vp = C.c_int32, C.c_void_p
+
+
+class MgcModule(C.Structure):
+    _fields_ = [(n, _i32) for n in ("kind", "horizon", "act_col", "obs_off", "param_off", "fstate_off", "istate_off",
+                                    "listing", "raise_errors")]
+
+
+class MgcLayout(C.Structure):
+    _fields_ = [("abi_version", _i32), ("n_modules", _i32), ("modules", MgcModule * MGC_MAX_MODULES),
+                ("n_act", _i32), ("obs_dim", _i32), ("n_fstate", _i32), ("n_istate", _i32), ("cfg_stride", _i32),
+                ("n_cfg", _i32), ("series_len", _i32), ("n_series", _i32), ("n_envs", C.c_int64),
+                ("cfg", _vp), ("series", _vp), ("series_off", _vp), ("step", _vp), ("fstate", _vp), ("istate", _vp),
+                ("cfg_index", _vp)]
+
+
+class MgcIO(C.Structure):
+    _fields_ = [("actions", _vp), ("obs", _vp), ("reward", _vp), ("done", _vp), ("info", _vp), ("flags", _vp), ("mask", _vp)]
+
+
+EXPORTED_SYMBOLS = ("mgc_abi_version", "mgc_sizeof", "mgc_param_count", "mgc_create", "mgc_destroy", "mgc_run", "mgc_reset",
+                    "mgc_observe", "mgc_launch_count")
+
+
+def bind(L):
+    """argtypes + ABI checks on a loaded library (libpymgrid_b200.so; the test suite passes its host build)"""
+    if getattr(L, "_mgc_bound", False):
+        return L
+    L.mgc_abi_version.restype = C.c_int
+    L.mgc_sizeof.restype, L.mgc_sizeof.argtypes = C.c_int64, [C.c_int]
+    L.mgc_param_count.restype, L.mgc_param_count.argtypes = _i32, [C.c_int]
+    L.mgc_create.argtypes = [C.POINTER(MgcLayout), C.POINTER(_vp)]
+    L.mgc_destroy.argtypes = [_vp]
+    L.mgc_run.argtypes = [_vp, C.POINTER(MgcIO), _i32, _i32, C.c_int, _vp]
+    L.mgc_reset.argtypes = [_vp, C.POINTER(MgcIO), _vp]
+    L.mgc_observe.argtypes = [_vp, C.POINTER(MgcIO), _vp]
+    L.mgc_launch_count.restype, L.mgc_launch_count.argtypes = C.c_int64, [_vp]
+    L.mg_last_error.restype = C.c_char_p
+    if L.mgc_abi_version() != MGC_ABI_VERSION:
+        raise _cabi.EngineError(f"composed-step ABI mismatch: library {L.mgc_abi_version()} vs binding {MGC_ABI_VERSION}")
+    for which, struct in enumerate((MgcModule, MgcLayout, MgcIO)):
+        if L.mgc_sizeof(which) != C.sizeof(struct):
+            raise _cabi.EngineError(f"struct {struct.__name__}: library sizeof {L.mgc_sizeof(which)} != binding {C.sizeof(struct)}")
+    for name, kind in KIND.items():
+        if L.mgc_param_count(kind) != PARAM_COUNT[name]:
+            raise _cabi.EngineError(f"parameter block of {name}: library {L.mgc_param_count(kind)} != binding {PARAM_COUNT[name]}")
+    L._mgc_bound = True
+    return L
+
+
+# ---- the static structure of a module list ------------------------------------------------------------------------------
+class _Slot:
+    """one module of a composition"""
+    __slots__ = ("name", "index", "kind", "dispatch", "horizon", "raise_errors", "listing", "act_col", "n_act", "obs_off",
+                 "obs_len", "param_off", "fstate_off", "istate_off", "is_source", "is_sink")
+
+
+def _obs_len(kind, horizon):
+    return {"load": 1 + horizon, "renewable": 1 + horizon, "grid": 4 * (1 + horizon), "battery": 2, "genset": 4}.get(kind, 0)
+
+
+class Composition:
+    def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10.0, overgeneration_cost=2.0, obs_order="gym_sorted"):
+        """`modules`: list of pymgrid_b200.modules objects or (name, module) tuples, as Microgrid takes them
+        (microgrid.py:100-165).  Returns the structure AND keeps the (name, module) records in listing order."""
+        if isinstance(modules, (str, bytes)) or not hasattr(modules, "__iter__"):
+            raise TypeError("modules must be list-like of modules.")
+        named = _named(list(modules))
+        if add_unbalanced_module:       # appended un-named -> 'balancing' (microgrid.py:170-171)
+            named.append(("balancing", UnbalancedEnergyModule(raise_errors=False, loss_load_cost=loss_load_cost,
+                                                             overgeneration_cost=overgeneration_cost)))
+        if len(named) > MGC_MAX_MODULES:
+            raise NotImplementedError(f"at most {MGC_MAX_MODULES} modules per microgrid")
+        # module_container.py:355-413: cells (fixed, flex, controllable) x (sources, sinks, source_and_sinks); names in
+        # insertion order inside a cell; the modules of one name in insertion order
+        cells = OrderedDict(((d, s), OrderedDict()) for d in ("fixed", "flex", "controllable")
+                            for s in ("sources", "sinks", "source_and_sinks"))
+        types = {}
+        for name, m in named:
+            kind, dispatch = m.module_type
+            src, snk = kind != "load", kind in ("load", "battery", "grid", "balancing")
+            cell = (dispatch, "source_and_sinks" if src and snk else "sources" if src else "sinks")
+            if types.setdefault(name, cell) != cell:
+                raise NameError(f"Attempted to add module {name} of type {cell}, but there is an identically named "
+                                f"module of type {types[name]}.")
+            cells[cell].setdefault(name, []).append(m)
+        self.by_name = OrderedDict()            # name -> [module records], LISTING order (Container.to_dict)
+        for cell in cells.values():
+            self.by_name.update(cell)
+        self.slots = []
+        for name, lst in self.by_name.items():
+            for j, m in enumerate(lst):
+                s = _Slot()
+                s.name, s.index, (s.kind, s.dispatch) = name, j, m.module_type
+                s.horizon = int(getattr(m, "forecast_horizon", 0))
+                s.raise_errors, s.listing = bool(m.raise_errors), len(self.slots)
+                s.is_source, s.is_sink = s.kind != "load", s.kind in ("load", "battery", "grid", "balancing")
+                s.n_act = {"genset": 2, "battery": 1, "grid": 1}.get(s.kind, 0)
+                s.obs_len = _obs_len(s.kind, s.horizon)
+                self.slots.append(s)
+        self.records = [m for lst in self.by_name.values() for m in lst]       # listing order, parallel to self.slots
+        # dispatch order of Microgrid.run: fixed, controllable, flex (microgrid.py:255-314)
+        self.dispatch = [s for d in ("fixed", "controllable", "flex") for s in self.slots if s.dispatch == d]
+        col = 0
+        for s in self.dispatch:
+            s.act_col = col if s.n_act else -1
+            col += s.n_act
+        self.n_act = col
+        self.obs_order = obs_order
+        if obs_order == "gym_sorted":       # gym.spaces.Dict sorts its keys (envs/base/base.py:128-163, 211-223)
+            order = [s for name in sorted(self.by_name) for s in self.slots if s.name == name]
+        elif obs_order == "container":
+            order = list(self.slots)
+        else:
+            raise ValueError("obs_order must be 'gym_sorted' or 'container'")
+        off = 0
+        for s in order:
+            s.obs_off = off
+            off += s.obs_len
+        self.obs_dim = off
+        p, f, i = MGC_CFG_HEADER, 0, 0
+        for s in self.slots:
+            s.param_off = p
+            p += PARAM_COUNT[s.kind]
+            s.fstate_off, s.istate_off = (f if s.kind == "battery" else -1), (i if s.kind == "genset" else -1)
+            f += 2 * (s.kind == "battery")
+            i += 4 * (s.kind == "genset")
+        self.cfg_stride, self.n_fstate, self.n_istate = p, f, i
+        ts = [m for m in self.records if hasattr(m, "time_series")]
+        if len({len(m) for m in ts}) > 1:
+            raise ValueError("all time series must have the same length")
+        self.series_len = len(ts[0]) if ts else 0
+        initial = {m.initial_step for m in self.records}
+        final = {(m.final_step if m.final_step > 0 else len(m)) for m in ts}      # base_timeseries_module.py:317-330
+        if len(initial) > 1 or len(final) > 1:      # microgrid.py:640-675 reads a unique value
+            raise ValueError("Attribute(s) ['initial_step' / 'final_step'] have non-unique values, cannot return single unique value.")
+        self.initial_step = initial.pop() if initial else 0
+        self.final_step = final.pop() if final else 0
+        for m in ts:
+            if m._forecaster_params() is not None:
+                raise NotImplementedError("composed microgrids run the oracle forecaster (or none); Gaussian-noise forecasts "
+                                          "are built for the fused module set only")
+
+    @property
+    def signature(self):
+        """what B microgrids must share to be stepped as one batch"""
+        return tuple((s.name, s.kind, s.horizon, s.raise_errors) for s in self.slots) + (self.obs_order, self.series_len)
+
+    def controllable(self):
+        """[(name, [slots])] in Microgrid.controllable's iteration order"""
+        out = OrderedDict()
+        for s in self.dispatch:
+            if s.dispatch == "controllable":
+                out.setdefault(s.name, []).append(s)
+        return list(out.items())
+
+    # ---- packing ----
+    def config_record(self, series_index):
+        """the f64 parameter record of this microgrid (include/pymgrid_b200_compose.h: enum MGC_* lists the blocks).
+        `series_index(array) -> int` registers a series in the pool."""
+        rec = np.zeros(self.cfg_stride)
+        rec[0], rec[1] = self.initial_step, self.final_step
+        for s, m in zip(self.slots, self.records):
+            o = s.param_off
+            if s.kind in ("load", "renewable"):     # bounds: base_timeseries_module.py:81-88
+                lo, hi = views.series_bounds(m.time_series[:, 0], True)
+                rec[o:o + 3] = series_index(m.time_series), lo, hi
+            elif s.kind == "grid":                  # per-column bounds: grid_module.py:125-132
+                ts = m.time_series
+                rec[o:o + 4] = series_index(ts), m.max_import, m.max_export, m.cost_per_unit_co2
+                rec[o + 4:o + 8], rec[o + 8:o + 12] = ts.min(axis=0), ts.max(axis=0)
+            elif s.kind == "battery":
+                rec[o:o + 6] = (m.min_capacity, m.max_capacity, m.max_charge, m.max_discharge, m.efficiency, m.battery_cost_cycle)
+            elif s.kind == "genset":
+                rec[o:o + 8] = (m.running_min_production, m.running_max_production, m.genset_cost, m.co2_per_unit,
+                                m.cost_per_unit_co2, int(m.start_up_time), int(m.wind_down_time), int(bool(m.allow_abortion)))
+            else:
+                rec[o:o + 2] = m.loss_load_cost, m.overgeneration_cost
+        return rec
+
+    def initial_state(self):
+        """(fstate row, istate row) of a freshly constructed microgrid: battery_module.py:89-106, genset_module.py:91-92"""
+        f, i = np.zeros(self.n_fstate), np.zeros(self.n_istate, dtype=np.int32)
+        for s, m in zip(self.slots, self.records):
+            if s.kind == "battery":
+                f[s.fstate_off:s.fstate_off + 2] = m.init_charge, m.init_soc
+            elif s.kind == "genset":
+                on = int(bool(m.init_start_up))
+                i[s.istate_off:s.istate_off + 4] = (on, on, 0, int(m.wind_down_time)) if on else (0, 0, int(m.start_up_time), 0)
+        return f, i
+
+    def module_table(self):
+        arr = (MgcModule * MGC_MAX_MODULES)()
+        for k, s in enumerate(self.dispatch):
+            arr[k] = MgcModule(KIND[s.kind], s.horizon, s.act_col, s.obs_off if s.obs_len else 0, s.param_off, s.fstate_off,
+                               s.istate_off, s.listing, int(s.raise_errors))
+        return arr
+
+
+# ---- the batch ----------------------------------------------------------------------------------------------------------
+class ComposedBatch:
+    def __init__(self, microgrids, env_config=None, device=None, obs_order="gym_sorted", with_info=False,
+                 microgrid_kwargs=None, _library=None):
+        """`microgrids`: list of module lists (one per parameter set; all with the same composition) or ready
+        `Composition`s; `env_config[e]`: which one env e is (default: one env per entry)."""
+        kw = dict(microgrid_kwargs or {})
+        self.compositions = [m if isinstance(m, Composition) else Composition(m, obs_order=obs_order, **kw) for m in microgrids]
+        if not self.compositions:
+            raise ValueError("at least one microgrid is needed")
+        self.comp = comp = self.compositions[0]
+        for c in self.compositions[1:]:
+            if c.signature != comp.signature:
+                raise ValueError("the microgrids of one ComposedBatch must share one composition (module names, kinds, "
+                                 "forecast horizons, series length); build one batch per composition")
+        if _library is None:
+            self._L = bind(_cabi.lib())       # raises EngineError when the CUDA extension is missing
+            if not torch.cuda.is_available():
+                raise _cabi.EngineError("ComposedBatch needs a CUDA device: there is no CPU fallback")
+            self.device = torch.device(device if device is not None else "cuda")
+            if self.device.type != "cuda":
+                raise _cabi.EngineError("ComposedBatch runs on CUDA devices only")
+        else:                                 # tests/hostsim: the same C source built for the host
+            self._L = bind(_library)
+            self.device = torch.device("cpu")
+        env_config = np.arange(len(self.compositions)) if env_config is None else np.asarray(env_config, dtype=np.int64)
+        if env_config.ndim != 1 or len(env_config) < 1 or env_config.min() < 0 or env_config.max() >= len(self.compositions):
+            raise ValueError("env_config must index the microgrid list")
+        self.env_config = env_config
+        self.n_envs = n = len(env_config)
+        # series pool, deduplicated by content
+        pool, offsets, seen, total = [], [], {}, 0
+
+        def series_index(ts):
+            nonlocal total
+            arr = np.ascontiguousarray(ts, dtype=np.float64)
+            key = (arr.shape, arr.tobytes())
+            if key not in seen:
+                seen[key] = len(offsets)
+                offsets.append(total)
+                pool.append(arr.reshape(-1))
+                total += arr.size
+            return seen[key]
+        cfg = np.stack([c.config_record(series_index) for c in self.compositions])
+        states = [c.initial_state() for c in self.compositions]
+        dev = self.device
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dtype=dt).to(dev)      # noqa: E731
+        self.cfg = t(cfg, torch.float64)
+        self.series = t(np.concatenate(pool) if pool else np.zeros(1), torch.float64)
+        self.series_off = t(np.array(offsets if offsets else [0], dtype=np.int64), torch.int64)
+        self.cfg_index = t(env_config, torch.int32)
+        self.step_counter = t(np.array([self.compositions[c].initial_step for c in env_config]), torch.int32)
+        self.fstate = t(np.stack([states[c][0] for c in env_config]).reshape(n, comp.n_fstate), torch.float64)
+        self.istate = t(np.stack([states[c][1] for c in env_config]).reshape(n, comp.n_istate), torch.int32)
+        self.obs = torch.zeros((n, comp.obs_dim), dtype=torch.float64, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.flags = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.n_info = len(comp.slots) * MGC_INFO_SLOTS + MGC_BALANCE_SLOTS
+        self.info = torch.zeros((n, self.n_info), dtype=torch.float64, device=dev) if with_info else None
+        L = MgcLayout()
+        L.abi_version, L.n_modules, L.modules = MGC_ABI_VERSION, len(comp.slots), comp.module_table()
+        L.n_act, L.obs_dim, L.n_fstate, L.n_istate = comp.n_act, comp.obs_dim, comp.n_fstate, comp.n_istate
+        L.cfg_stride, L.n_cfg, L.series_len, L.n_series, L.n_envs = comp.cfg_stride, len(cfg), comp.series_len, len(offsets), n
+        L.cfg, L.series, L.series_off = self.cfg.data_ptr(), self.series.data_ptr(), self.series_off.data_ptr()
+        L.step, L.cfg_index = self.step_counter.data_ptr(), self.cfg_index.data_ptr()
+        L.fstate = self.fstate.data_ptr() if comp.n_fstate else None
+        L.istate = self.istate.data_ptr() if comp.n_istate else None
+        self._handle = _vp()
+        self._check(self._L.mgc_create(C.byref(L), C.byref(self._handle)), "mgc_create")
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            try:
+                self._L.mgc_destroy(h)
+            except Exception:       # interpreter shutdown
+                pass
+
+    def _check(self, code, what):
+        if code != 0:
+            raise _cabi.EngineError(f"{what} failed ({code}): {self._L.mg_last_error().decode()}")
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
+
+    @property
+    def launch_count(self):
+        return int(self._L.mgc_launch_count(self._handle))
+
+    def _actions(self, actions, lead):
+        comp = self.comp
+        if comp.n_act == 0:
+            return None
+        a = torch.as_tensor(actions, dtype=torch.float64, device=self.device).contiguous()
+        if tuple(a.shape) != lead + (self.n_envs, comp.n_act):
+            raise ValueError(f"actions must have shape {lead + (self.n_envs, comp.n_act)}, got {tuple(a.shape)}")
+        return a
+
+    def step(self, actions=None, normalized=True, obs=True):
+        """Microgrid.run for every env (microgrid.py:227-325): `actions` [B, n_act] in the composition's control order
+        (`Composition.controllable()`; genset: goal, energy).  Returns (obs [B, D] | None, reward [B], done [B], info | None);
+        the tensors are the batch's own buffers, overwritten by the next call."""
+        a = self._actions(actions, ())
+        io = MgcIO(a.data_ptr() if a is not None else None, self.obs.data_ptr() if obs else None, self.reward.data_ptr(),
+                   self.done.data_ptr(), self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None)
+        self._check(self._L.mgc_run(self._handle, C.byref(io), 1, 1, int(bool(normalized)), self._stream()), "mgc_run")
+        return (self.obs if obs else None), self.reward, self.done, self.info
+
+    def rollout(self, actions=None, n_steps=None, normalized=True, ring=1, obs=True):
+        """`n_steps` consecutive steps in ONE launch; `actions` [T, B, n_act].  Returns dict(reward [T, B], done [T, B],
+        obs_ring [ring, B, D] | None, flags [B] OR-ed over the steps)."""
+        comp = self.comp
+        if comp.n_act:
+            T = int(torch.as_tensor(actions).shape[0]) if n_steps is None else int(n_steps)
+            a = self._actions(actions, (T,))
+        else:
+            if n_steps is None:
+                raise ValueError("n_steps is required when the composition has no controllable module")
+            T, a = int(n_steps), None
+        reward = torch.empty((T, self.n_envs), dtype=torch.float64, device=self.device)
+        done = torch.empty((T, self.n_envs), dtype=torch.uint8, device=self.device)
+        ring_buf = torch.zeros((ring, self.n_envs, comp.obs_dim), dtype=torch.float64, device=self.device) if obs else None
+        io = MgcIO(a.data_ptr() if a is not None else None, ring_buf.data_ptr() if obs else None, reward.data_ptr(),
+                   done.data_ptr(), self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None)
+        self._check(self._L.mgc_run(self._handle, C.byref(io), T, int(ring), int(bool(normalized)), self._stream()), "mgc_run")
+        return dict(reward=reward, done=done, obs_ring=ring_buf, flags=self.flags)
+
+    def reset(self, mask=None):
+        """Microgrid.reset (microgrid.py:205-225) for the masked envs (default all); returns every env's observation"""
+        m = None if mask is None else torch.as_tensor(mask, dtype=torch.uint8, device=self.device).contiguous()
+        io = MgcIO(None, self.obs.data_ptr(), None, None, None, None, m.data_ptr() if m is not None else None)
+        self._check(self._L.mgc_reset(self._handle, C.byref(io), self._stream()), "mgc_reset")
+        return self.obs
+
+    def observe(self):
+        io = MgcIO(None, self.obs.data_ptr(), None, None, None, None, None)
+        self._check(self._L.mgc_observe(self._handle, C.byref(io), self._stream()), "mgc_observe")
+        return self.obs
+
+
+# ---- B = 1: the reference's Microgrid surface ---------------------------------------------------------------------------
+class ModuleList(list):
+    """microgrid.modules.<name>: list of module views (module_container.py ModuleList)"""
+
+    def item(self):
+        if len(self) != 1:
+            raise ValueError("Can only convert a ModuleList of length one to a scalar")
+        return self[0]
+
+    def to_list(self):
+        return self
+
+
+class ComposedModuleView:
+    """Read-only view of one module of a ComposedMicrogrid: constructor parameters + the live values the reference's
+    callers read."""
+    _STATE_NAMES = {"load": ["load"], "renewable": ["renewable"],
+                    "grid": ["import_price", "export_price", "co2_per_kwh", "grid_status"]}
+    _ENERGY_NAMES = {"load": (None, "load_met"), "renewable": ("renewable_used", None),
+                     "battery": ("discharge_amount", "charge_amount"), "genset": ("genset_production", None),
+                     "grid": ("grid_import", "grid_export"), "balancing": ("loss_load", "overgeneration")}
+
+    def __init__(self, microgrid, slot, record):
+        self._m, self._s, self._r = microgrid, slot, record
+        self.name = (slot.name, slot.index)
+
+    def __repr__(self):
+        return f"{type(self._r).__name__}View{self.name}"
+
+    def __getattr__(self, item):        # constructor parameters: battery.max_capacity, genset.genset_cost, load.time_series ...
+        if item.startswith("_"):
+            raise AttributeError(item)
+        return getattr(self._r, item)
+
+    module_type = property(lambda self: self._r.module_type)
+    is_source = property(lambda self: self._s.is_source)
+    is_sink = property(lambda self: self._s.is_sink)
+    current_step = property(lambda self: self._m.current_step)
+    initial_step = property(lambda self: self._m.initial_step)
+    final_step = property(lambda self: self._m.final_step)
+    provided_energy_name = property(lambda self: self._ENERGY_NAMES[self._s.kind][0])
+    absorbed_energy_name = property(lambda self: self._ENERGY_NAMES[self._s.kind][1])
+
+    @property
+    def action_space(self):
+        from types import SimpleNamespace
+        n = self._s.n_act if self._s.dispatch == "controllable" else (1 if self._s.dispatch == "flex" else 0)
+        return SimpleNamespace(shape=(n,))
+
+    def _state(self):
+        t, f, i = self._m._state()
+        s = self._s
+        return t, (f[s.fstate_off:s.fstate_off + 2] if s.kind == "battery" else None), \
+            (i[s.istate_off:s.istate_off + 4] if s.kind == "genset" else None)
+
+    def _row(self):
+        return self._r.time_series[self._m.current_step]
+
+    # live values
+    current_load = property(lambda self: -1 * self._row().item())                  # load_module.py:100-111
+    current_renewable = property(lambda self: self._row().item())                  # renewable_module.py:99-110
+    current_charge = property(lambda self: float(self._state()[1][0]))
+    soc = property(lambda self: float(self._state()[1][1]))
+    current_status = property(lambda self: int(self._state()[2][0]) if self._s.kind == "genset" else self._row()[3])
+    goal_status = property(lambda self: int(self._state()[2][1]))
+
+    @property
+    def max_production(self):
+        k, r = self._s.kind, self._r
+        if k == "battery":
+            return min(r.max_discharge, self.current_charge - r.min_capacity) * r.efficiency
+        if k == "genset":
+            return self.current_status * r.running_max_production
+        if k == "grid":
+            return r.max_import * self._row()[3]
+        if k == "renewable":
+            return self.current_renewable
+        if k == "balancing":
+            return np.inf
+        return 0.0
+
+    @property
+    def min_production(self):
+        return self.current_status * self._r.running_min_production if self._s.kind == "genset" else 0
+
+    @property
+    def max_consumption(self):
+        k, r = self._s.kind, self._r
+        if k == "battery":
+            return min(r.max_charge, r.max_capacity - self.current_charge) / r.efficiency
+        if k == "grid":
+            return r.max_export * self._row()[3]
+        if k == "load":
+            return self.current_load
+        if k == "balancing":
+            return np.inf
+        return 0.0
+
+    @property
+    def production_marginal_cost(self):
+        k, r = self._s.kind, self._r
+        return {"battery": lambda: r.battery_cost_cycle,
+                "genset": lambda: r.genset_cost * 1.0 + r.cost_per_unit_co2 * (r.co2_per_unit * 1.0),
+                "grid": lambda: self._row()[0], "balancing": lambda: r.loss_load_cost}.get(k, lambda: 0.0)()
+
+    @property
+    def absorption_marginal_cost(self):
+        k, r = self._s.kind, self._r
+        return {"battery": lambda: r.battery_cost_cycle, "grid": lambda: self._row()[1],
+                "balancing": lambda: r.overgeneration_cost}.get(k, lambda: 0.0)()
+
+    marginal_cost = production_marginal_cost
+
+    def _series_bounds(self):
+        ts = self._r.time_series
+        if self._s.kind == "grid":
+            return ts.min(axis=0), ts.max(axis=0)
+        lo, hi = views.series_bounds(ts[:, 0], True)
+        return np.array([lo]), np.array([hi])
+
+    def state_dict(self, normalized=False):
+        """base_module.py:473-490 / the modules' _state_dict"""
+        s, r = self._s, self._r
+        t, f, i = self._state()
+        d = OrderedDict()
+        if s.kind in self._STATE_NAMES:
+            lo, hi = self._series_bounds()
+            vals = views.series_state(r.time_series, t, s.horizon, lo, hi)
+            comps = self._STATE_NAMES[s.kind]
+            keys = [f"{c}_current" for c in comps] + [f"{c}_forecast_{j}" for j in range(s.horizon) for c in comps]
+            d.update(zip(keys, (float(v) for v in vals)))
+        elif s.kind == "battery":
+            d.update(soc=float(f[1]), current_charge=float(f[0]))
+        elif s.kind == "genset":
+            d.update(current_status=int(i[0]), goal_status=int(i[1]), steps_until_up=int(i[2]), steps_until_down=int(i[3]))
+        if normalized and d:
+            lo, hi = self.min_obs, self.max_obs
+            spread = np.where(hi - lo == 0, 1.0, hi - lo)
+            d = OrderedDict(zip(d.keys(), (np.array(list(d.values()), dtype=np.float64) - lo) / spread))
+        return d
+
+    @property
+    def state(self):
+        return np.array(list(self.state_dict().values()), dtype=np.float64)
+
+    def _obs_bounds(self):
+        s, r = self._s, self._r
+        if s.kind in self._STATE_NAMES:
+            lo, hi = self._series_bounds()
+            return np.tile(lo, 1 + s.horizon), np.tile(hi, 1 + s.horizon)
+        if s.kind == "battery":
+            return np.array([r.min_capacity / r.max_capacity, r.min_capacity]), np.array([1.0, r.max_capacity])
+        if s.kind == "genset":
+            return np.zeros(4), np.array([1.0, 1.0, r.start_up_time, r.wind_down_time], dtype=np.float64)
+        return np.array([]), np.array([])
+
+    min_obs = property(lambda self: self._obs_bounds()[0])
+    max_obs = property(lambda self: self._obs_bounds()[1])
+
+    def _act_bounds(self):
+        k, r = self._s.kind, self._r
+        if k == "battery":
+            return -r.max_discharge / r.efficiency, r.max_charge * r.efficiency
+        if k == "genset":
+            return np.array([0.0, 0.0]), np.array([1.0, r.running_max_production])
+        if k == "grid":
+            return -1 * r.max_export, r.max_import
+        if k == "renewable":
+            lo, hi = self._series_bounds()
+            return lo[0], hi[0]
+        if k == "balancing":
+            return -np.inf, np.inf
+        return np.array([]), np.array([])
+
+    min_act = property(lambda self: self._act_bounds()[0])
+    max_act = property(lambda self: self._act_bounds()[1])
+
+    def sample_action(self, strict_bound=False):
+        """base_module.py:326-356 (genset: genset_module.py:348-349)"""
+        if self._s.kind == "genset":
+            return np.array([np.random.rand(), np.random.rand()])
+        lo_b, hi_b = 0, 1
+        if strict_bound:
+            lo, hi = self._act_bounds()
+            spread = (hi - lo) or 1.0
+            if self.is_sink:
+                lo_b = (-1 * self.max_consumption - lo) / spread
+                lo_b = 0 if np.isnan(lo_b) else lo_b
+            if self.is_source:
+                hi_b = (self.max_production - lo) / spread
+                hi_b = 0 if np.isnan(hi_b) else hi_b
+        return np.random.rand() * (hi_b - lo_b) + lo_b
+
+
+class ComposedContainer(OrderedDict):
+    """`microgrid.modules` and its sub-containers: name -> ModuleList, attribute access, the reference's helpers"""
+
+    def __getattr__(self, item):
+        try:
+            return self[item]
+        except KeyError:
+            raise AttributeError(item)
+
+    def iterdict(self):
+        return self.items()
+
+    def to_dict(self):
+        return OrderedDict(self)
+
+    def iterlist(self):
+        return [m for lst in self.values() for m in lst]
+
+    to_list = iterlist
+
+    def names(self):
+        return list(self.keys())
+
+    def to_tuples(self):
+        return [(name, m) for name, lst in self.items() for m in lst]
+
+    def __len__(self):      # counts modules, like the reference's container
+        return sum(len(v) for v in self.values())
+
+    def _filtered(self, keep):
+        return ComposedContainer((n, lst) for n, lst in self.items() if keep(lst[0]))
+
+    fixed = property(lambda self: self._filtered(lambda m: m.module_type[1] == "fixed"))
+    flex = property(lambda self: self._filtered(lambda m: m.module_type[1] == "flex"))
+    controllable = property(lambda self: self._filtered(lambda m: m.module_type[1] == "controllable"))
+    sources = property(lambda self: self._filtered(lambda m: m.is_source and not m.is_sink))
+    sinks = property(lambda self: self._filtered(lambda m: m.is_sink and not m.is_source))
+    source_and_sinks = property(lambda self: self._filtered(lambda m: m.is_source and m.is_sink))
+
+
+class ComposedMicrogrid:
+    """pymgrid.Microgrid's surface for any module list (see the module docstring).  What the reference raises mid-step
+    (AssertionError, ValueError under raise_errors=True) is raised here AFTER the step has been applied with the
+    reference's clip semantics -- the engine reports events, it does not unwind."""
+
+    def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2.,
+                 reward_shaping_func=None, trajectory_func=None, device=None, obs_order="gym_sorted", _library=None):
+        if reward_shaping_func is not None or trajectory_func is not None:
+            raise NotImplementedError("reward_shaping_func / trajectory_func are built for the fused module set (one load, one "
+                                      "renewable, one battery, at most one genset and one grid)")
+        comp = Composition(modules, add_unbalanced_module, loss_load_cost, overgeneration_cost, obs_order=obs_order)
+        self.composition = comp
+        self._batch = ComposedBatch([comp], device=device, obs_order=obs_order, with_info=True, _library=_library)
+        self._modules = ComposedContainer()
+        for s, r in zip(comp.slots, comp.records):
+            self._modules.setdefault(s.name, ModuleList()).append(ComposedModuleView(self, s, r))
+        self._views = [v for lst in self._modules.values() for v in lst]        # listing order
+        self._log_rows = []
+        self._log_start = comp.initial_step
+        self._actions = np.zeros((1, comp.n_act))
+
+    # ---- state ----
+    def _state(self):
+        b = self._batch
+        return int(b.step_counter[0].item()), b.fstate[0].cpu().numpy(), b.istate[0].cpu().numpy()
+
+    current_step = property(lambda self: int(self._batch.step_counter[0].item()))
+    initial_step = property(lambda self: self.composition.initial_step)
+    final_step = property(lambda self: self.composition.final_step)
+    modules = property(lambda self: self._modules)
+    fixed = property(lambda self: self._modules.fixed)
+    flex = property(lambda self: self._modules.flex)
+    controllable = property(lambda self: self._modules.controllable)
+
+    def __len__(self):
+        return self.composition.series_len
+
+    def __repr__(self):
+        return "Microgrid([" + ", ".join(f"{n} x {len(lst)}" for n, lst in self._modules.items()) + "])"
+
+    # ---- conversions ----
+    def _obs_dict(self, row, order):
+        out = OrderedDict()
+        for s in order:
+            out.setdefault(s.name, []).append(np.array(row[s.obs_off:s.obs_off + s.obs_len], dtype=np.float64))
+        return out
+
+    def _info_dict(self, info):
+        out = OrderedDict()
+        for s in self.composition.dispatch:
+            r = info[s.listing * MGC_INFO_SLOTS:(s.listing + 1) * MGC_INFO_SLOTS]
+            d = OrderedDict()
+            d["absorbed_energy" if r[4] else "provided_energy"] = float(r[1] if r[4] else r[0])
+            if s.kind in ("genset", "grid"):
+                d["co2_production"] = float(r[2])
+            elif s.kind == "renewable":
+                d["curtailment"] = float(r[2])
+            out.setdefault(s.name, []).append(d)
+        return out
+
+    def _control_row(self, control):
+        """microgrid.py:262-284: missing modules raise ValueError, extra keys warn, a bare scalar stands for [scalar]"""
+        row = self._actions
+        row[:] = 0.0
+        control = dict(control)
+        for name, slots in self.composition.controllable():
+            try:
+                vals = control.pop(name)
+            except KeyError:
+                raise ValueError(f'Control for module "{name}" not found. Available controls:\n\t{control.keys()}')
+            try:
+                pairs = list(zip(slots, vals))
+            except TypeError:
+                pairs = list(zip(slots, [vals]))
+            for s, v in pairs:
+                arr = np.asarray(v, dtype=np.float64).reshape(-1)
+                if arr.size != s.n_act:
+                    raise ValueError(f"Bad action {v}")
+                row[0, s.act_col:s.act_col + s.n_act] = arr
+        if control:
+            warnings.warn(f'\nIgnoring the following keys in passed control:\n {list(control.keys())}')
+        return row
+
+    # ---- the hot path ----
+    def run(self, control, normalized=True):
+        """reference: Microgrid.run (microgrid.py:227-325).  Same arguments, return types and errors."""
+        comp, b = self.composition, self._batch
+        row = self._control_row(control)
+        pre = [v.state_dict() for v in self._views]
+        b.step(row if comp.n_act else None, normalized=normalized)
+        flags = int(b.flags[0].item()) & 0xffffffff
+        if flags & FLAG_STEP_PAST_END:
+            t = self.current_step
+            raise IndexError(f"index {t} is out of bounds for axis 0 with size {len(self)}")     # e.g. load_module.py:111
+        info = b.info[0].cpu().numpy()
+        reward = float(b.reward[0].item())
+        self._log_rows.append(self._log_row(pre, info, reward))
+        if flags & (FLAG_GENSET_GOAL_RANGE | FLAG_NOT_A_SINK | FLAG_BATTERY_MIN_CAP | FLAG_NEGATIVE_ABSORB):
+            raise AssertionError(f"step rejected (flags {flags:#x})")
+        if flags & FLAG_CLIP_RAISES:
+            raise ValueError("requested value outside the module's limits")                        # base_module.py:79-93
+        if flags & FLAG_BALANCE:
+            raise RuntimeError("Microgrid modules unable to balance energy production with consumption.\n")
+        return (self._obs_dict(b.obs[0].cpu().numpy(), comp.dispatch), reward, bool(b.done[0].item()), self._info_dict(info))
+
+    def _log_row(self, pre, info, reward):
+        """one row of get_log(): base_module.py:276-290 per module, microgrid.py:259-260, 281, 317-319 for the balance"""
+        row = OrderedDict()
+        for v, state in zip(self._views, pre):
+            s = v._s
+            r = info[s.listing * MGC_INFO_SLOTS:(s.listing + 1) * MGC_INFO_SLOTS]
+            key = (s.name, s.index)
+            row[key + ("reward",)] = float(r[3])
+            if s.kind in ("genset", "grid"):
+                row[key + ("co2_production",)] = float(r[2])
+            elif s.kind == "renewable":
+                row[key + ("curtailment",)] = float(r[2])
+            p_name, a_name = v._ENERGY_NAMES[s.kind]
+            if p_name is not None:
+                row[key + (p_name,)] = float(r[0])
+            if a_name is not None:
+                row[key + (a_name,)] = float(r[1])
+            if s.kind == "genset":      # the genset logs its state AFTER the status update (genset_module.py:148-149)
+                state = v.state_dict()
+            for k, val in state.items():
+                row[key + (k,)] = val
+        bal = info[len(self._views) * MGC_INFO_SLOTS:]
+        for k, val in (("reward", reward), ("shaped_reward", reward), ("overall_provided_to_microgrid", bal[4]),
+                       ("overall_absorbed_from_microgrid", bal[5]), ("controllable_provided_to_microgrid", bal[2]),
+                       ("controllable_absorbed_from_microgrid", bal[3]), ("fixed_provided_to_microgrid", bal[0]),
+                       ("fixed_absorbed_from_microgrid", bal[1])):
+            row[("balance", 0, k)] = float(val)
+        return row
+
+    def reset(self):
+        """reference: Microgrid.reset (microgrid.py:205-225): modules in LISTING order, then 'balance' and 'other'"""
+        obs = self._batch.reset()[0].cpu().numpy()
+        self._log_rows = []
+        out = self._obs_dict(obs, self.composition.slots)
+        out["balance"], out["other"] = {}, {}
+        return out
+
+    # ---- actions ----
+    def sample_action(self, strict_bound=False, sample_flex_modules=False):
+        """reference: Microgrid.sample_action (microgrid.py:337-362)"""
+        it = self._modules if sample_flex_modules else self._modules.controllable
+        return {name: [m.sample_action(strict_bound=strict_bound) for m in lst] for name, lst in it.items()
+                if lst[0].action_space.shape[0]}
+
+    def get_empty_action(self, sample_flex_modules=False):
+        it = self._modules if sample_flex_modules else self._modules.controllable
+        return {name: [None] * len(lst) for name, lst in it.items() if lst[0].action_space.shape[0]}
+
+    # ---- introspection ----
+    def state_dict(self, normalized=False):
+        return {name: [m.state_dict(normalized=normalized) for m in lst] for name, lst in self._modules.items()}
+
+    def state_series(self, normalized=False):
+        import pandas as pd
+        data = OrderedDict(((name, j, k), v) for name, lst in self._modules.items() for j, m in enumerate(lst)
+                           for k, v in m.state_dict(normalized=normalized).items())
+        return pd.Series(data, dtype=np.float64)
+
+    def get_log(self, as_frame=True, drop_singleton_key=False):
+        """reference: Microgrid.get_log (microgrid.py:434-475): one row per step since the last reset"""
+        import pandas as pd
+        start = self.current_step - len(self._log_rows)
+        cols = list(self._log_rows[0].keys()) if self._log_rows else []
+        df = pd.DataFrame([list(r.values()) for r in self._log_rows], columns=pd.MultiIndex.from_tuples(
+            cols, names=["module_name", "module_number", "field"]) if cols else None,
+            index=pd.RangeIndex(start=start, stop=self.current_step))
+        if drop_singleton_key and cols:
+            df.columns = df.columns.remove_unused_levels()
+        return df if as_frame else df.to_dict()
+
+    log = property(lambda self: self.get_log())
+
+
+def in_fused_scope(modules, add_unbalanced_module=True):
+    """True when the module list is one the fused kernels cover: exactly one load, renewable, battery and slack module, at
+    most one genset and one grid, canonical names, one forecast horizon (modules.params_from_modules' conditions)."""
+    try:
+        named = _named(list(modules))
+    except TypeError:
+        return True        # let the fused constructor raise its own error
+    counts, names, horizons = {}, {}, set()
+    for name, m in named:
+        k = m.module_type[0]
+        counts[k] = counts.get(k, 0) + 1
+        names[k] = name
+        if hasattr(m, "forecast_horizon"):
+            horizons.add(m.forecast_horizon)
+    if add_unbalanced_module:
+        counts["balancing"] = counts.get("balancing", 0) + 1
+    need = {"load": (1, 1), "renewable": (1, 1), "battery": (1, 1), "balancing": (1, 1), "genset": (0, 1), "grid": (0, 1)}
+    if any(not lo <= counts.get(k, 0) <= hi for k, (lo, hi) in need.items()):
+        return False
+    if any(names.get(k, k) != k for k in ("battery", "genset", "grid", "load")):
+        return False
+    if "battery" <= names["renewable"] <= "load" or len(horizons) != 1:
+        return False
+    return True

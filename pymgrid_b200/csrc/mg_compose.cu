@@ -1,0 +1,283 @@
+// mg_compose.cu -- composed-microgrid step (any module list) for a batch: kernels + the C-ABI of
+// include/pymgrid_b200_compose.h.  Linked into libpymgrid_b200.so beside mg_engine.cu.
+//
+// One CTA = a tile of MGC_TILE envs, one launch = n_steps steps.  Per step:
+//   1. thread e <-> env: the whole Microgrid.run dispatch (mg_compose_step.h: mgc_env_step) over the module table, state
+//      rows read and written in place, reward / done / info / flags written back;
+//   2. the CTA emits the tile's observation rows cooperatively, module block by module block: consecutive threads write
+//      consecutive elements of a block (the forecast windows are contiguous slices of the series pool, which stays in
+//      L2), so stores are coalesced within every block of every row.
+// This is the general path; the pymgrid25 / MicrogridGenerator module set has kernels of its own (mg_engine.cu), which is
+// where the throughput work lives.  HBM-bound like them: per env-step algorithmic bytes = 8 n_act + state r/w + 9 +
+// 8 obs_dim.
+//
+// The same file compiles for the HOST with -DMGC_HOSTSIM (g++ -x c++, tests/hostsim/): launches become loops over tiles
+// and threads, pointers are host pointers.  That build is test infrastructure -- it lets the CPU suite drive this ABI,
+// the layout validation and the per-env arithmetic against the reference's recorded outputs; it is never loaded by the
+// package (pymgrid_b200/_cabi.py loads libpymgrid_b200.so only and fails loudly without it).
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#ifndef MGC_HOSTSIM
+#include <cuda_runtime.h>
+#endif
+
+#include "mg_compose_step.h"
+
+#define MGC_TILE 128
+
+struct MgcLaunch {
+    MgcModule mod[MGC_MAX_MODULES];
+    int32_t n_mod, n_act, obs_dim, n_fstate, n_istate, cfg_stride, T, n_envs;
+    const double *cfg;
+    const double *series;
+    const int64_t *series_off;
+    int32_t *step;
+    double *fstate;
+    int32_t *istate;
+    const int32_t *cfg_index;
+    // per call
+    MgcIO io;
+    int32_t mode, n_steps, ring, normalized;
+};
+
+enum { MGC_MODE_RUN = 0, MGC_MODE_RESET = 1, MGC_MODE_OBSERVE = 2 };
+
+#ifdef MGC_HOSTSIM
+#define MGC_DEV static inline
+#else
+#define MGC_DEV __device__ __forceinline__
+#endif
+
+MGC_DEV MgcView mgc_view(const MgcLaunch &P, int e) {
+    MgcView V;
+    V.mod = P.mod;
+    V.n_mod = P.n_mod;
+    V.cfg = P.cfg + (int64_t)P.cfg_index[e] * P.cfg_stride;
+    V.series = P.series;
+    V.series_off = P.series_off;
+    V.T = P.T;
+    return V;
+}
+
+// phase 1 of a step for env e (one thread)
+MGC_DEV void mgc_owner(const MgcLaunch &P, int e, int s) {
+    MgcView V = mgc_view(P, e);
+    if (P.mode == MGC_MODE_RUN) {
+        int32_t t = P.step[e];
+        uint32_t flags = 0;
+        double reward;
+        uint8_t done;
+        const int64_t slot = (int64_t)s * P.n_envs + e;
+        const double *action = P.io.actions ? P.io.actions + slot * P.n_act : nullptr;
+        double *info = P.io.info ? P.io.info + (int64_t)e * (P.n_mod * MGC_INFO_SLOTS + MGC_BALANCE_SLOTS) : nullptr;
+        mgc_env_step(V, t, P.fstate + (int64_t)e * P.n_fstate, P.istate + (int64_t)e * P.n_istate, action, P.normalized, &reward,
+                     &done, info, &flags);
+        P.step[e] = t;
+        P.io.reward[slot] = reward;
+        P.io.done[slot] = done;
+        if (P.io.flags) P.io.flags[e] = (s == 0 ? 0u : P.io.flags[e]) | flags;
+    } else if (P.mode == MGC_MODE_RESET) {
+        if (!P.io.mask || P.io.mask[e]) P.step[e] = (int32_t)V.cfg[0];      // microgrid.py:205-225: only the step moves
+    }
+}
+
+// phase 2: element `idx` of module m's block over the tile [e0, e0 + n_tile)
+MGC_DEV void mgc_emit(const MgcLaunch &P, double *obs, int e0, int m, int len, int idx) {
+    const int r = idx / len, k = idx - r * len;
+    const int e = e0 + r;
+    MgcView V = mgc_view(P, e);
+    const double v = mgc_obs_element(V, m, k, P.step[e], P.fstate + (int64_t)e * P.n_fstate, P.istate + (int64_t)e * P.n_istate);
+    obs[(int64_t)e * P.obs_dim + P.mod[m].obs_off + k] = v;
+}
+
+#ifndef MGC_HOSTSIM
+__global__ void __launch_bounds__(MGC_TILE) mgc_kernel(const __grid_constant__ MgcLaunch P) {
+    const int e0 = blockIdx.x * MGC_TILE;
+    const int n_tile = min(MGC_TILE, P.n_envs - e0);
+    const int e = e0 + threadIdx.x;
+    const int n_steps = (P.mode == MGC_MODE_RUN) ? P.n_steps : 1;
+    for (int s = 0; s < n_steps; ++s) {
+        if (threadIdx.x < n_tile) mgc_owner(P, e, s);
+        __syncthreads();      // the tile's state rows (global memory, written by their owners) are read by every thread below
+        if (P.io.obs) {
+            double *obs = P.io.obs + (int64_t)(s % P.ring) * P.n_envs * P.obs_dim;
+            for (int m = 0; m < P.n_mod; ++m) {
+                const int len = mgc_obs_len(P.mod[m]);
+                const int total = len * n_tile;
+                for (int idx = threadIdx.x; idx < total; idx += MGC_TILE) mgc_emit(P, obs, e0, m, len, idx);
+            }
+        }
+        __syncthreads();      // the next step's owners overwrite the state this step's emitters have just read
+    }
+}
+#else
+static void mgc_kernel_host(const MgcLaunch &P) {
+    const int tiles = (P.n_envs + MGC_TILE - 1) / MGC_TILE;
+    const int n_steps = (P.mode == MGC_MODE_RUN) ? P.n_steps : 1;
+    for (int b = 0; b < tiles; ++b) {
+        const int e0 = b * MGC_TILE;
+        const int n_tile = (P.n_envs - e0 < MGC_TILE) ? P.n_envs - e0 : MGC_TILE;
+        for (int s = 0; s < n_steps; ++s) {
+            for (int th = 0; th < n_tile; ++th) mgc_owner(P, e0 + th, s);
+            if (P.io.obs) {
+                double *obs = P.io.obs + (int64_t)(s % P.ring) * P.n_envs * P.obs_dim;
+                for (int m = 0; m < P.n_mod; ++m) {
+                    const int len = mgc_obs_len(P.mod[m]);
+                    const int total = len * n_tile;
+                    for (int th = 0; th < MGC_TILE; ++th)
+                        for (int idx = th; idx < total; idx += MGC_TILE) mgc_emit(P, obs, e0, m, len, idx);
+                }
+            }
+        }
+    }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------------------------------
+struct MgcHandle {
+    MgcLaunch base;
+    int64_t launches;
+};
+
+#ifdef MGC_HOSTSIM
+static thread_local char g_mgc_err[512] = "";
+extern "C" const char *mg_last_error(void) { return g_mgc_err; }
+static int mgc_fail(int code, const char *msg) {
+    snprintf(g_mgc_err, sizeof g_mgc_err, "%s", msg);
+    return code;
+}
+#else
+int mg_set_error(int code, const char *msg);      // mg_engine.cu: the text mg_last_error() returns
+static int mgc_fail(int code, const char *msg) { return mg_set_error(code, msg); }
+#endif
+
+extern "C" int mgc_abi_version(void) { return MGC_ABI_VERSION; }
+
+extern "C" int64_t mgc_sizeof(int which) {
+    switch (which) {
+    case 0: return (int64_t)sizeof(MgcModule);
+    case 1: return (int64_t)sizeof(MgcLayout);
+    case 2: return (int64_t)sizeof(MgcIO);
+    default: return -1;
+    }
+}
+
+extern "C" int32_t mgc_param_count(int kind) {
+    switch (kind) {
+    case MGC_LOAD:
+    case MGC_RENEWABLE: return 3;
+    case MGC_BATTERY: return 6;
+    case MGC_GENSET: return 8;
+    case MGC_GRID: return 12;
+    case MGC_UNBALANCED: return 2;
+    default: return -1;
+    }
+}
+
+extern "C" int mgc_create(const MgcLayout *L, MgcHandle **out) {
+    if (!L || !out) return mgc_fail(MG_E_INVALID, "mgc_create: null argument");
+    if (L->abi_version != MGC_ABI_VERSION) return mgc_fail(MG_E_INVALID, "mgc_create: abi_version mismatch");
+    if (L->n_modules < 1 || L->n_modules > MGC_MAX_MODULES) return mgc_fail(MG_E_INVALID, "mgc_create: n_modules out of range");
+    if (L->n_envs < 1 || L->n_envs >= (1ll << 31) - MGC_TILE) return mgc_fail(MG_E_INVALID, "mgc_create: n_envs out of range");
+    if (L->n_cfg < 1 || L->cfg_stride < MGC_CFG_HEADER || !L->cfg || !L->step || !L->cfg_index)
+        return mgc_fail(MG_E_INVALID, "mgc_create: missing config / state arrays");
+    // the module table: dispatch classes in order (fixed, controllable, flex), blocks inside the rows, listing a permutation
+    int cls = 0, obs = 0, act = 0, nf = 0, ni = 0, n_ts = 0;
+    bool seen[MGC_MAX_MODULES] = {false};
+    for (int m = 0; m < L->n_modules; ++m) {
+        const MgcModule &M = L->modules[m];
+        const int pc = mgc_param_count(M.kind);
+        if (pc < 0) return mgc_fail(MG_E_INVALID, "mgc_create: unknown module kind");
+        const int c = mgc_dispatch_class(M.kind);
+        if (c < cls) return mgc_fail(MG_E_INVALID, "mgc_create: modules must be in dispatch order (fixed, controllable, flex)");
+        cls = c;
+        if (M.param_off < MGC_CFG_HEADER || M.param_off + pc > L->cfg_stride)
+            return mgc_fail(MG_E_INVALID, "mgc_create: module parameters outside the config record");
+        if (M.horizon < 0 || (!mgc_is_timeseries(M.kind) && M.horizon != 0)) return mgc_fail(MG_E_INVALID, "mgc_create: bad horizon");
+        const int len = mgc_obs_len(M);
+        if (len > 0 && (M.obs_off < 0 || M.obs_off + len > L->obs_dim)) return mgc_fail(MG_E_INVALID, "mgc_create: observation block outside the row");
+        obs += len;
+        if (c == 1) {
+            const int w = (M.kind == MGC_GENSET) ? 2 : 1;
+            if (M.act_col < 0 || M.act_col + w > L->n_act) return mgc_fail(MG_E_INVALID, "mgc_create: action columns outside the row");
+            act += w;
+        }
+        if (M.kind == MGC_BATTERY) {
+            if (M.fstate_off < 0 || M.fstate_off + 2 > L->n_fstate) return mgc_fail(MG_E_INVALID, "mgc_create: battery state outside the row");
+            nf += 2;
+        }
+        if (M.kind == MGC_GENSET) {
+            if (M.istate_off < 0 || M.istate_off + 4 > L->n_istate) return mgc_fail(MG_E_INVALID, "mgc_create: genset state outside the row");
+            ni += 4;
+        }
+        if (mgc_is_timeseries(M.kind)) ++n_ts;
+        if (M.listing < 0 || M.listing >= L->n_modules || seen[M.listing]) return mgc_fail(MG_E_INVALID, "mgc_create: listing is not a permutation");
+        seen[M.listing] = true;
+    }
+    if (obs != L->obs_dim || act != L->n_act || nf != L->n_fstate || ni != L->n_istate)
+        return mgc_fail(MG_E_INVALID, "mgc_create: row widths do not match the module table");
+    if ((nf > 0 && !L->fstate) || (ni > 0 && !L->istate)) return mgc_fail(MG_E_INVALID, "mgc_create: null state pointer");
+    if (n_ts > 0 && (L->series_len < 1 || L->n_series < 1 || !L->series || !L->series_off))
+        return mgc_fail(MG_E_INVALID, "mgc_create: time-series modules without a series pool");
+    MgcHandle *h = new (std::nothrow) MgcHandle();
+    if (!h) return mgc_fail(MG_E_INVALID, "mgc_create: out of host memory");
+    MgcLaunch &B = h->base;
+    memset(&B, 0, sizeof B);
+    memcpy(B.mod, L->modules, sizeof(MgcModule) * (size_t)L->n_modules);
+    B.n_mod = L->n_modules; B.n_act = L->n_act; B.obs_dim = L->obs_dim; B.n_fstate = L->n_fstate; B.n_istate = L->n_istate;
+    B.cfg_stride = L->cfg_stride; B.T = L->series_len; B.n_envs = (int32_t)L->n_envs;
+    B.cfg = L->cfg; B.series = L->series; B.series_off = L->series_off;
+    B.step = L->step; B.fstate = L->fstate; B.istate = L->istate; B.cfg_index = L->cfg_index;
+    h->launches = 0;
+    *out = h;
+    return MG_OK;
+}
+
+extern "C" int mgc_destroy(MgcHandle *h) {
+    delete h;
+    return MG_OK;
+}
+
+extern "C" int64_t mgc_launch_count(const MgcHandle *h) { return h ? h->launches : 0; }
+
+static int mgc_launch(MgcHandle *h, const MgcIO *io, int mode, int32_t n_steps, int32_t ring, int normalized, void *stream) {
+    if (!h || !io) return mgc_fail(MG_E_INVALID, "mgc: null argument");
+    MgcLaunch P = h->base;
+    P.io = *io;
+    P.mode = mode; P.n_steps = n_steps; P.ring = ring; P.normalized = normalized;
+    if (mode == MGC_MODE_RUN) {
+        if (n_steps < 1 || ring < 1) return mgc_fail(MG_E_INVALID, "mgc_run: n_steps and ring must be >= 1");
+        if (!io->reward || !io->done) return mgc_fail(MG_E_INVALID, "mgc_run: reward and done are required");
+        if (P.n_act > 0 && !io->actions) return mgc_fail(MG_E_INVALID, "mgc_run: actions are required (n_act > 0)");
+    } else {
+        P.n_steps = 1; P.ring = 1;
+        if (mode == MGC_MODE_OBSERVE && !io->obs) return mgc_fail(MG_E_INVALID, "mgc_observe: obs is required");
+    }
+#ifdef MGC_HOSTSIM
+    (void)stream;
+    mgc_kernel_host(P);
+#else
+    const int tiles = (P.n_envs + MGC_TILE - 1) / MGC_TILE;
+    mgc_kernel<<<tiles, MGC_TILE, 0, (cudaStream_t)stream>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        char msg[256];
+        snprintf(msg, sizeof msg, "mgc kernel launch: %s", cudaGetErrorString(e));
+        return mgc_fail(MG_E_CUDA, msg);
+    }
+#endif
+    h->launches += 1;
+    return MG_OK;
+}
+
+extern "C" int mgc_run(MgcHandle *h, const MgcIO *io, int32_t n_steps, int32_t ring, int normalized, void *stream) {
+    return mgc_launch(h, io, MGC_MODE_RUN, n_steps, ring, normalized, stream);
+}
+extern "C" int mgc_reset(MgcHandle *h, const MgcIO *io, void *stream) { return mgc_launch(h, io, MGC_MODE_RESET, 1, 1, 0, stream); }
+extern "C" int mgc_observe(MgcHandle *h, const MgcIO *io, void *stream) { return mgc_launch(h, io, MGC_MODE_OBSERVE, 1, 1, 0, stream); }

@@ -1450,6 +1450,12 @@ static int fail(int code, const char *fmt, const char *detail = "") {
     return code;
 }
 
+// the other translation units of this library (mg_compose.cu) report through the same text
+int mg_set_error(int code, const char *msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return code;
+}
+
 static int cuda_fail(cudaError_t e, const char *what) {
     snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
     return MG_E_CUDA;

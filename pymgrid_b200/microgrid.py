@@ -319,6 +319,17 @@ class ModuleContainerView(OrderedDict):
 
 
 class Microgrid:
+    def __new__(cls, modules=None, *args, **kw):
+        """Module lists outside the fused kernels' scope (several loads / renewables / batteries / gensets / grids, no
+        battery, per-module horizons, renamed modules ...) are served by the composed path: same surface, general
+        dispatch kernel (compose.py, include/pymgrid_b200_compose.h)."""
+        if cls is Microgrid and isinstance(modules, (list, tuple)):
+            from .compose import ComposedMicrogrid, in_fused_scope
+            add_unbalanced = args[0] if args else kw.get("add_unbalanced_module", True)
+            if not in_fused_scope(modules, add_unbalanced):
+                return ComposedMicrogrid(modules, *args, **kw)
+        return super().__new__(cls)
+
     def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2.,
                  reward_shaping_func=None, trajectory_func=None, device=None, obs_order="gym_sorted"):
         """The reference's constructor (microgrid/microgrid.py:100-128):

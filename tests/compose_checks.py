@@ -1,0 +1,125 @@
+"""Shared bodies of the composed-microgrid parity tests: run once on the CPU against the host build of the C source
+(tests/test_compose_host.py) and once on the GPU against the CUDA build (tests/test_zz_gpu_compose.py).  `lib` is the
+host-build library handle, or None for the product path (CUDA)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.compose import ComposedOracle
+from pymgrid_b200.compose import ComposedBatch, ComposedMicrogrid
+from tests.compose_cases import BALANCE_COLS, load_cases
+
+CASES = load_cases()
+
+
+def widths(mg):
+    return [(name, [s.n_act for s in slots]) for name, slots in mg.composition.controllable()]
+
+
+def listing_flat(obs, mg):
+    return np.concatenate([np.asarray(obs[s.name][s.index]).ravel() for s in mg.composition.slots] + [np.zeros(0)])
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def check_microgrid_reproduces_reference(case, order, lib):
+    mg = ComposedMicrogrid(case.modules(), obs_order=order, _library=lib, **case.microgrid_kwargs)
+    assert [(s.name, s.index) for s in mg.composition.slots] == [(n, j) for n, j, _ in case.names]
+    assert {k: len(v) for k, v in mg.get_empty_action().items()} == case.json("empty_action")
+    reset = mg.reset()
+    assert list(reset.keys()) == case.json("reset_keys")
+    assert np.array_equal(listing_flat(reset, mg), case["obs_reset"])
+    n = len(case["rewards"])
+    for k in range(n):
+        obs, reward, done, info = mg.run(case.control(k, widths(mg)), normalized=bool(case["normalized"][k]))
+        assert list(obs.keys()) == case.json("run_keys")
+        assert reward == case["rewards"][k] and done == bool(case["dones"][k]), k
+        assert np.array_equal(listing_flat(obs, mg), case["obs"][k]), k
+        for i, s in enumerate(mg.composition.slots):
+            inf, want = info[s.name][s.index], case["info"][k, i]
+            assert inf.get("provided_energy", 0.0) == want[0] and inf.get("absorbed_energy", 0.0) == want[1], (k, s.name)
+            assert inf.get("co2_production", inf.get("curtailment", 0.0)) == want[2]
+            assert ("absorbed_energy" in inf) == bool(want[4])
+        t, f, i_ = mg._state()
+        state = []
+        for s in mg.composition.slots:
+            if s.kind == "battery":
+                state += list(f[s.fstate_off:s.fstate_off + 2])
+            elif s.kind == "genset":
+                state += list(i_[s.istate_off:s.istate_off + 4])
+        assert np.array_equal(np.array(state, dtype=np.float64), case["states"][k]), k
+    if int(case["raised_at"]) >= 0:
+        ctrl = {name: [np.array([0.5, 0.5]) if w == 2 else 0.5 for w in ws] for name, ws in widths(mg)}
+        exc = {"RuntimeError": RuntimeError, "IndexError": IndexError}[str(case["raised_type"])]
+        with pytest.raises(exc):
+            mg.run(ctrl)
+    log = mg.get_log()
+    assert [list(c) for c in log.columns] == case.json("log_columns")
+    assert np.array_equal(log.to_numpy(dtype=np.float64), case["log_values"], equal_nan=True)
+    assert np.array_equal(np.array(log.index), case["log_index"])
+    assert mg.current_step == int(case["current_step"])
+    ss = mg.state_series()          # recorded at the end of the run
+    assert [[str(x) for x in i] for i in ss.index] == case.json("state_series_index")
+    assert np.array_equal(ss.to_numpy(), case["state_series_values"])
+    if n:
+        assert np.array_equal(log["balance"][0][list(BALANCE_COLS)].to_numpy()[:n], case["balance"][:n])
+
+
+def _batch_case(lib, label, n_envs, seed):
+    """a batch whose envs are re-parameterised copies of one golden composition, and the oracle twin of every env"""
+    case = next(c for c in CASES if c.label == label)
+    rng = np.random.default_rng(seed)
+    configs = []
+    for _ in range(3):
+        mods = case.modules()
+        for m in mods:
+            m = m[1] if isinstance(m, tuple) else m
+            if hasattr(m, "time_series") and m.module_type[0] != "grid":
+                m.time_series = m.time_series * rng.uniform(0.5, 1.5)
+            if m.module_type[0] == "battery":
+                m.init_charge = m.min_capacity + rng.random() * (m.max_capacity - m.min_capacity)
+                m.init_soc = m.init_charge / m.max_capacity
+        configs.append(mods)
+    env_config = rng.integers(0, 3, n_envs)
+    batch = ComposedBatch(configs, env_config, obs_order="container", with_info=True, microgrid_kwargs=case.microgrid_kwargs,
+                          _library=lib)
+    oracles = [ComposedOracle(configs[c], **case.microgrid_kwargs) for c in env_config]
+    return case, batch, oracles
+
+
+def check_batch_matches_oracle_and_rollout_matches_steps(label, lib, n_envs=131, T=9):
+    case, batch, oracles = _batch_case(lib, label, n_envs, 7)
+    comp = batch.comp
+    rng = np.random.default_rng(3)
+    actions = rng.random((T, n_envs, comp.n_act))
+    ctl = comp.controllable()
+    want_r, want_obs = np.zeros((T, n_envs)), None
+    for e, orc in enumerate(oracles):
+        for k in range(T):
+            control = {name: [actions[k, e, s.act_col:s.act_col + s.n_act] if s.n_act == 2 else actions[k, e, s.act_col]
+                              for s in slots] for name, slots in ctl}
+            obs, r, d, info = orc.run(control, normalized=True)
+            want_r[k, e] = r
+        if want_obs is None:
+            want_obs = np.zeros((n_envs, comp.obs_dim))
+        want_obs[e] = np.concatenate([np.asarray(obs[m.name][m.index]).ravel() for m in orc.listing])
+    # one launch for the whole rollout ...
+    out = batch.rollout(torch.from_numpy(actions).to(batch.device), ring=2)
+    assert np.array_equal(out["reward"].cpu().numpy(), want_r)
+    assert np.array_equal(out["obs_ring"][(T - 1) % 2].cpu().numpy(), want_obs)
+    assert batch.launch_count == 1
+    # ... equals T single steps on a fresh batch
+    _, batch2, _ = _batch_case(lib, label, n_envs, 7)
+    for k in range(T):
+        obs, r, d, info = batch2.step(torch.from_numpy(actions[k]).to(batch2.device))
+        assert np.array_equal(r.cpu().numpy(), want_r[k])
+    assert np.array_equal(obs.cpu().numpy(), want_obs)
+    assert np.array_equal(batch2.fstate.cpu().numpy(), batch.fstate.cpu().numpy()) and np.array_equal(batch2.istate.cpu().numpy(), batch.istate.cpu().numpy())
+    # masked reset: only the step counter of the masked envs moves (microgrid.py:205-225)
+    mask = (np.arange(n_envs) % 3 == 0).astype(np.uint8)
+    before = batch.fstate.clone()
+    batch.reset(mask)
+    assert np.array_equal(batch.step_counter.cpu().numpy(), np.where(mask, comp.initial_step, T + comp.initial_step))
+    assert torch.equal(before, batch.fstate)

@@ -34,6 +34,26 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert L.mg_sizeof(99) == -1
 
 
+def test_compose_header_symbols_are_exported_and_bound():
+    """include/pymgrid_b200_compose.h: every declared entry point is exported by the CUDA library, the ctypes mirrors
+    have the compiled sizes, invalid layouts are refused on the host (no compute calls)."""
+    from pymgrid_b200 import _cabi, compose
+    text = open(os.path.join(ROOT, "include", "pymgrid_b200_compose.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(mgc_[a-z_0-9]+)\s*\(", text)))
+    assert set(declared) == set(compose.EXPORTED_SYMBOLS)
+    L = compose.bind(_cabi.lib())         # ABI version, struct sizes and parameter-block widths, raises otherwise
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    h = C.c_void_p()
+    assert L.mgc_create(None, C.byref(h)) == -1 and b"null" in L.mg_last_error()
+    layout = compose.MgcLayout()
+    layout.abi_version = 99
+    assert L.mgc_create(C.byref(layout), C.byref(h)) == -1 and b"abi_version" in L.mg_last_error()
+    assert L.mgc_run(None, None, 1, 1, 1, None) == -1
+    assert L.mgc_sizeof(99) == -1 and L.mgc_param_count(99) == -1
+
+
 def test_invalid_arguments_are_rejected_without_touching_the_gpu():
     from pymgrid_b200 import _cabi
     L = _cabi.lib()

@@ -1,0 +1,79 @@
+"""The composed-microgrid path on the CPU: the C source of the CUDA path (pymgrid_b200/csrc/mg_compose.cu +
+mg_compose_step.h) built for the host (tests/hostsim) under the package's own Python host layer
+(pymgrid_b200/compose.py), against what the live reference returned (tests/golden/compose.npz) -- bit for bit, down to
+the get_log() frame -- and against the Python oracle on batches.  The GPU twin is tests/test_zz_gpu_compose.py."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from pymgrid_b200 import _cabi
+from pymgrid_b200.compose import (MGC_INFO_SLOTS, ComposedBatch, ComposedMicrogrid, Composition, in_fused_scope)
+from tests import hostsim
+from tests import compose_checks as K
+from tests.compose_checks import CASES
+
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return ctypes.CDLL(hostsim.build())
+
+
+@pytest.mark.parametrize("order", ["container", "gym_sorted"])
+@pytest.mark.parametrize("case", CASES, ids=[c.label for c in CASES])
+def test_composed_microgrid_reproduces_reference(case, order, lib):
+    K.check_microgrid_reproduces_reference(case, order, lib)
+
+
+def test_gym_sorted_order_is_a_permutation_by_name(lib):
+    case = next(c for c in CASES if c.label == "custom_names")
+    a = ComposedMicrogrid(case.modules(), obs_order="container", _library=lib, **case.microgrid_kwargs)
+    b = ComposedMicrogrid(case.modules(), obs_order="gym_sorted", _library=lib, **case.microgrid_kwargs)
+    # capital letters sort first: 'Abat', 'PV', then 'unbalanced_energy' (empty), 'wind', 'zload'
+    assert [s.name for s in sorted(b.composition.slots, key=lambda s: s.obs_off) if s.obs_len] == ["Abat", "PV", "wind", "zload"]
+    ra, rb = a._batch.observe()[0].numpy(), b._batch.observe()[0].numpy()
+    for sa, sb in zip(a.composition.slots, b.composition.slots):
+        assert np.array_equal(ra[sa.obs_off:sa.obs_off + sa.obs_len], rb[sb.obs_off:sb.obs_off + sb.obs_len])
+
+
+@pytest.mark.parametrize("label", ["several_of_each", "pairwise_sums", "load_pv_genset"])
+def test_batch_matches_oracle_and_rollout_matches_steps(label, lib):
+    K.check_batch_matches_oracle_and_rollout_matches_steps(label, lib, n_envs=131, T=9)     # two tiles, ragged last tile
+
+
+def test_layout_validation_and_scope(lib):
+    case = next(c for c in CASES if c.label == "per_module_horizons")
+    assert not in_fused_scope(case.modules())
+    fused = next(c for c in CASES if c.label == "past_the_end")
+    assert in_fused_scope(fused.modules(), add_unbalanced_module=False)
+    with pytest.raises(ValueError):     # different compositions in one batch
+        ComposedBatch([case.modules(), next(c for c in CASES if c.label == "load_only").modules()], _library=lib)
+    comp = Composition(case.modules(), obs_order="container")
+    assert comp.n_act == 4 and comp.obs_dim == 4 + 1 + 2 + 4 + 4 * 6
+    assert [s.kind for s in comp.dispatch] == ["load", "genset", "battery", "grid", "renewable", "balancing"]
+    b = ComposedBatch([comp], _library=lib)
+    with pytest.raises(ValueError):
+        b.step(np.zeros((1, 3)))
+    # a module table the library must refuse: dispatch order broken
+    from pymgrid_b200.compose import MgcLayout
+    tab = comp.module_table()
+    tab[0], tab[1] = tab[1], tab[0]
+    L = MgcLayout()
+    L.abi_version, L.n_modules, L.modules = 1, len(comp.slots), tab
+    h = ctypes.c_void_p()
+    assert b._L.mgc_create(ctypes.byref(L), ctypes.byref(h)) != 0
+    assert b"mgc_create" in b._L.mg_last_error()
+
+
+def test_product_path_needs_cuda():
+    """no _library, no GPU in this container: constructing the product path must fail loudly, never fall back"""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    case = next(c for c in CASES if c.label == "load_pv")
+    with pytest.raises(_cabi.EngineError):
+        ComposedMicrogrid(case.modules())
+    import pymgrid_b200
+    with pytest.raises(_cabi.EngineError):
+        pymgrid_b200.Microgrid(case.modules())        # routed to the composed path (two-module list), which needs CUDA

@@ -1,0 +1,77 @@
+"""GPU parity of the composed-microgrid path (mgc_* in libpymgrid_b200.so): the checks tests/test_compose_host.py runs
+against the host build of the same C source, here through the CUDA build on cuda:0 -- the reference's recorded outputs
+(tests/golden/compose.npz) bit for bit, batches against the Python oracle, one-launch rollouts against single steps.
+(The file name sorts last on purpose: the fused path's GPU suites run first.)"""
+import numpy as np
+import pytest
+import torch
+
+from tests import compose_checks as K
+from tests.compose_checks import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("order", ["container", "gym_sorted"])
+@pytest.mark.parametrize("case", CASES, ids=[c.label for c in CASES])
+def test_composed_microgrid_reproduces_reference_on_gpu(case, order):
+    K.check_microgrid_reproduces_reference(case, order, None)
+
+
+@pytest.mark.parametrize("label", ["several_of_each", "pairwise_sums", "load_pv_genset"])
+def test_batch_matches_oracle_and_rollout_matches_steps_on_gpu(label):
+    K.check_batch_matches_oracle_and_rollout_matches_steps(label, None, n_envs=389, T=7)    # four tiles, ragged last tile
+
+
+def test_microgrid_constructor_routes_module_lists_outside_the_fused_scope():
+    """pymgrid_b200.Microgrid(modules): the reference's own balance-test grid (a load and a renewable, nothing else;
+    tests/microgrid/test_microgrid.py:188-319) runs on the composed path with the reference's known answers"""
+    import pymgrid_b200
+    from pymgrid_b200.compose import ComposedMicrogrid
+    from pymgrid_b200.modules import LoadModule, RenewableModule
+    rng = np.random.default_rng(0)
+    load_ts = 10 * rng.random(100)
+    pv_ts = load_ts + 5 * rng.random(100) * (rng.random(100) > 0.5) - 3 * rng.random(100)
+    pv_ts = np.abs(pv_ts)
+    mg = pymgrid_b200.Microgrid([LoadModule(time_series=load_ts, raise_errors=True),
+                                 RenewableModule(time_series=pv_ts, raise_errors=True)])
+    assert isinstance(mg, ComposedMicrogrid)
+    for step in range(100):
+        obs, reward, done, info = mg.run(mg.get_empty_action())
+        loss_load = max(load_ts[step] - pv_ts[step], 0)
+        assert -1 * reward == mg.modules.balancing[0].loss_load_cost * loss_load
+    log = mg.log
+    assert len(log) == 100
+    assert np.array_equal(log[("load", 0, "load_met")].to_numpy(), load_ts)
+    assert np.array_equal(log[("renewable", 0, "renewable_used")].to_numpy(), np.minimum(load_ts, pv_ts))
+    assert np.array_equal(log[("renewable", 0, "curtailment")].to_numpy(), pv_ts - np.minimum(load_ts, pv_ts))
+
+
+def test_large_batch_energy_balance_and_replica_consistency():
+    """65 536 replicas of one composition: identical actions give identical rows, every env balances, and env 0 equals
+    the oracle"""
+    from oracle.compose import ComposedOracle
+    from pymgrid_b200.compose import FLAG_BALANCE, ComposedBatch
+    case = next(c for c in CASES if c.label == "several_of_each")
+    n, T = 65536, 5
+    batch = ComposedBatch([case.modules()], np.zeros(n, dtype=np.int64), obs_order="container", with_info=True,
+                          microgrid_kwargs=case.microgrid_kwargs)
+    comp = batch.comp
+    rng = np.random.default_rng(11)
+    a = rng.random((T, 1, comp.n_act))
+    actions = torch.from_numpy(np.broadcast_to(a, (T, n, comp.n_act)).copy()).cuda()
+    out = batch.rollout(actions, ring=1)
+    torch.cuda.synchronize()
+    reward = out["reward"].cpu().numpy()
+    assert (reward == reward[:, :1]).all()
+    obs = out["obs_ring"][0]
+    assert bool((obs == obs[:1]).all())
+    assert not bool((out["flags"] & FLAG_BALANCE).any())
+    orc = ComposedOracle(case.modules(), **case.microgrid_kwargs)
+    for k in range(T):
+        control = {name: [a[k, 0, s.act_col:s.act_col + s.n_act] if s.n_act == 2 else a[k, 0, s.act_col] for s in slots]
+                   for name, slots in comp.controllable()}
+        o, r, d, info = orc.run(control, normalized=True)
+        assert r == reward[k, 0]
+    want = np.concatenate([np.asarray(o[m.name][m.index]).ravel() for m in orc.listing])
+    assert np.array_equal(obs[0].cpu().numpy(), want)
