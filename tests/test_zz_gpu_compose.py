@@ -75,3 +75,11 @@ def test_large_batch_energy_balance_and_replica_consistency():
         assert r == reward[k, 0]
     want = np.concatenate([np.asarray(o[m.name][m.index]).ravel() for m in orc.listing])
     assert np.array_equal(obs[0].cpu().numpy(), want)
+
+
+# the reference's TestMicrogridLoadPV family (tests/microgrid/test_microgrid.py:188-421) through the CUDA path
+from tests.reference_suite_compose import make_suite  # noqa: E402
+
+for _cls in make_suite(None):
+    globals()[_cls.__name__ + "OnGpu"] = type(_cls.__name__ + "OnGpu", (_cls,), {})
+del _cls
