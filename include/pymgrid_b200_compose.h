@@ -85,6 +85,11 @@ typedef struct MgcLayout {
     double *fstate;                  /* [n][n_fstate]                                                                   */
     int32_t *istate;                 /* [n][n_istate]                                                                   */
     const int32_t *cfg_index;        /* [n] row of `cfg`                                                                */
+    /* discrete actions (mgc_run_discrete): the priority lists of the composition (algos/priority_list/priority_list.py:15-67),
+       [n_plist][plist_width][2] int16 = (index of a controllable module in `modules`, action number: the goal of a genset,
+       0 otherwise); a negative module pads.  NULL / 0 when mgc_run_discrete is not used. */
+    const int16_t *plist;
+    int32_t n_plist, plist_width;
 } MgcLayout;
 
 typedef struct MgcIO {
@@ -95,6 +100,8 @@ typedef struct MgcIO {
     double *info;           /* [n, n_modules * MGC_INFO_SLOTS + MGC_BALANCE_SLOTS] of the LAST step, or NULL             */
     uint32_t *flags;        /* [n] OR over the steps, or NULL                                                            */
     const uint8_t *mask;    /* mgc_reset only: envs to reset (NULL = all)                                                */
+    const int32_t *dactions; /* mgc_run_discrete: [n_steps, n] priority-list index; [n] when dactions_const != 0           */
+    int64_t dactions_const;  /* != 0: the same list every step -- rule-based control (algos/rbc/rbc.py:64-93)             */
 } MgcIO;
 
 typedef struct MgcHandle MgcHandle;
@@ -114,6 +121,13 @@ int mgc_destroy(MgcHandle *h);
  * observation of every module (base_module.py:157).  n_steps = 1 is one Microgrid.run.
  */
 int mgc_run(MgcHandle *h, const MgcIO *io, int32_t n_steps, int32_t ring, int normalized, void *stream);
+/*
+ * mgc_run_discrete -- DiscreteMicrogridEnv.step(action) (envs/discrete/discrete.py:109-143) / RuleBasedControl.run
+ * (algos/rbc/rbc.py:64-93): io->dactions picks a priority list per env and step, its expansion into controls
+ * (priority_list.py:69-116) is fused in front of the step.  An index outside the table sets MG_FLAG_BAD_ACTION and leaves
+ * the env untouched (reward NaN).
+ */
+int mgc_run_discrete(MgcHandle *h, const MgcIO *io, int32_t n_steps, int32_t ring, void *stream);
 /* mgc_reset -- Microgrid.reset (microgrid.py:205-225): step = initial_step for the masked envs; battery and genset
  * state stay; writes every env's observation when io->obs is not NULL. */
 int mgc_reset(MgcHandle *h, const MgcIO *io, void *stream);

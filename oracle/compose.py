@@ -450,3 +450,87 @@ class ComposedOracle:
         if not isclose(p, a):
             raise Raised("RuntimeError", "Microgrid modules unable to balance energy production with consumption.")
         return obs, reward_sum, done_any, info_out
+
+
+# ---- priority lists: algos/priority_list/priority_list.py:15-167, priority_list_element.py:6-80 ------------------------
+def _marginal_cost(m):
+    k, r = m.kind, m.rec
+    if k == "battery":
+        return r.battery_cost_cycle                                            # battery_module.py:340-346
+    if k == "genset":
+        return r.genset_cost * 1.0 + r.cost_per_unit_co2 * (r.co2_per_unit * 1.0)   # genset_module.py:519-521
+    return float(m.ts[m.t, 0])                                                 # grid_module.py:322-324
+
+
+def oracle_priority_lists(orc, remove_redundant_gensets=False):
+    """every deployment order of the controllable modules as tuples of (name, index, module_actions, action)"""
+    from itertools import permutations
+    ctl = [m for _, lst in orc._of(CONTROLLABLE) for m in lst]
+    ordered = [m for m in ctl if not m.is_sink] + [m for m in ctl if m.is_sink]      # sources, then source_and_sinks
+    elements = []
+    for m in ordered:
+        n = 2 if m.kind == "genset" else 1
+        elements += [(m.name, m.index, n, a) for a in range(n)]
+    out, seen = [], set()
+    for perm in permutations(elements):
+        listed, pl = set(), []
+        for el in perm:
+            if el[:2] not in listed:
+                listed.add(el[:2])
+                pl.append(el)
+        pl = tuple(pl)
+        if pl not in seen:
+            seen.add(pl)
+            out.append(pl)
+    if remove_redundant_gensets:
+        redundant = [(m.name, m.index, 2, 0) for m in orc.listing if m.kind == "genset" and m.rec.running_min_production == 0]
+        out = [pl for pl in out if not any(r in pl for r in redundant)]
+    return out
+
+
+def oracle_rbc_list(orc, remove_redundant_gensets=True):
+    """RuleBasedControl's automatic list (algos/rbc/rbc.py:31-44): the first priority list sorted by marginal cost, ties
+    towards the higher action number"""
+    first = oracle_priority_lists(orc, remove_redundant_gensets)[0]
+    cost = {(m.name, m.index): _marginal_cost(m) for m in orc.listing if m.dispatch == CONTROLLABLE}
+    return sorted(first, key=lambda el: (cost[el[:2]], -el[3]))
+
+
+def oracle_priority_control(orc, pl):
+    """_populate_action (:69-116): priority list -> {name: [unnormalised action per module]}"""
+    action = {name: [None] * len(lst) for name, lst in orc._of(CONTROLLABLE)}
+    total_load = 0.0
+    for m in orc.listing:
+        if m.kind == "load":
+            total_load += -1 * float(m.ts[m.t, 0])
+    renewable = np_sum([float(m.ts[m.t, 0]) for m in orc.listing if m.kind == "renewable"])
+    remaining = total_load - renewable
+    for name, index, n_actions, act in pl:
+        m = orc.by_name[name][index]
+        if n_actions > 1:
+            if action[name][index] is not None:
+                continue
+            action[name][index] = [act]
+        if isclose(remaining, 0.0, atol=1e-4):
+            energy = 0.0
+        elif remaining > 0:
+            if m.kind == "genset":
+                nxt = (1 if (m.cs or m.up == 0) else 0) if act else (0 if (not m.cs or m.dn == 0) else 1)
+                mx, mn = nxt * m.rec.running_max_production, nxt * m.rec.running_min_production
+            else:
+                mx, mn = m.max_production(), m.min_production()
+            energy = remaining if mn <= remaining <= mx else (mn if remaining < mn else mx)
+        else:
+            if m.is_sink:
+                mc = m.max_consumption()
+                if not mc >= 0:
+                    raise Raised("AssertionError", "module_max_consumption >= 0")
+                energy = -1.0 * mc if -1 * remaining > mc else remaining
+            else:
+                energy = 0.0
+        if n_actions > 1:
+            action[name][index] = np.array(action[name][index] + [energy])
+        else:
+            action[name][index] = energy
+        remaining -= energy
+    return action

@@ -60,6 +60,12 @@ def _engine_form(elements):
 
 
 class RuleBasedControl:
+    def __new__(cls, microgrid=None, *args, **kw):
+        from .compose import ComposedMicrogrid, ComposedRuleBasedControl
+        if cls is RuleBasedControl and isinstance(microgrid, ComposedMicrogrid):      # any module list: the composed path
+            return ComposedRuleBasedControl(microgrid, *args, **kw)
+        return super().__new__(cls)
+
     def __init__(self, microgrid, priority_list=None, remove_redundant_gensets=True):
         """`microgrid`: a pymgrid_b200.Microgrid; like the reference (rbc.py:28-30) the controller works on a COPY that
         carries the microgrid's current state.  `priority_list`: None (ordered by marginal cost, rbc.py:31-44) or one of

@@ -23,8 +23,7 @@ import numpy as np
 import torch
 
 from . import _cabi, views
-from .modules import (BatteryModule, GensetModule, GridModule, LoadModule, RenewableModule, UnbalancedEnergyModule, _Module,
-                      _named)
+from .modules import UnbalancedEnergyModule, _named
 
 MGC_ABI_VERSION = 1
 MGC_MAX_MODULES = 64
@@ -49,15 +48,18 @@ class MgcLayout(C.Structure):
                 ("n_act", _i32), ("obs_dim", _i32), ("n_fstate", _i32), ("n_istate", _i32), ("cfg_stride", _i32),
                 ("n_cfg", _i32), ("series_len", _i32), ("n_series", _i32), ("n_envs", C.c_int64),
                 ("cfg", _vp), ("series", _vp), ("series_off", _vp), ("step", _vp), ("fstate", _vp), ("istate", _vp),
-                ("cfg_index", _vp)]
+                ("cfg_index", _vp), ("plist", _vp), ("n_plist", _i32), ("plist_width", _i32)]
 
 
 class MgcIO(C.Structure):
-    _fields_ = [("actions", _vp), ("obs", _vp), ("reward", _vp), ("done", _vp), ("info", _vp), ("flags", _vp), ("mask", _vp)]
+    _fields_ = [("actions", _vp), ("obs", _vp), ("reward", _vp), ("done", _vp), ("info", _vp), ("flags", _vp), ("mask", _vp),
+                ("dactions", _vp), ("dactions_const", C.c_int64)]
 
 
-EXPORTED_SYMBOLS = ("mgc_abi_version", "mgc_sizeof", "mgc_param_count", "mgc_create", "mgc_destroy", "mgc_run", "mgc_reset",
-                    "mgc_observe", "mgc_launch_count")
+EXPORTED_SYMBOLS = ("mgc_abi_version", "mgc_sizeof", "mgc_param_count", "mgc_create", "mgc_destroy", "mgc_run",
+                    "mgc_run_discrete", "mgc_reset", "mgc_observe", "mgc_launch_count")
+MAX_PRIORITY_ELEMENTS = 8       # (elements)! permutations are enumerated like the reference does (priority_list.py:15-38)
+FLAG_BAD_ACTION = 1 << 6
 
 
 def bind(L):
@@ -70,6 +72,7 @@ def bind(L):
     L.mgc_create.argtypes = [C.POINTER(MgcLayout), C.POINTER(_vp)]
     L.mgc_destroy.argtypes = [_vp]
     L.mgc_run.argtypes = [_vp, C.POINTER(MgcIO), _i32, _i32, C.c_int, _vp]
+    L.mgc_run_discrete.argtypes = [_vp, C.POINTER(MgcIO), _i32, _i32, _vp]
     L.mgc_reset.argtypes = [_vp, C.POINTER(MgcIO), _vp]
     L.mgc_observe.argtypes = [_vp, C.POINTER(MgcIO), _vp]
     L.mgc_launch_count.restype, L.mgc_launch_count.argtypes = C.c_int64, [_vp]
@@ -192,6 +195,51 @@ class Composition:
                 out.setdefault(s.name, []).append(s)
         return list(out.items())
 
+    # ---- priority lists (algos/priority_list/priority_list.py:15-67) ----
+    def priority_elements(self):
+        """one element per action-space dimension of every controllable source (a genset: goal 0, goal 1), then one per
+        controllable source-and-sink (battery, grid), in the container's order: [(slot, action)]"""
+        ctl = [s for s in self.slots if s.dispatch == "controllable"]
+        ordered = [s for s in ctl if not s.is_sink] + [s for s in ctl if s.is_sink]
+        return [(s, a) for s in ordered for a in range(2 if s.kind == "genset" else 1)]
+
+    def priority_lists(self, remove_redundant_gensets=False):
+        """All deployment orders: every permutation of the elements, later elements of an already listed module dropped,
+        duplicates removed in first-seen order; optionally without the lists that switch off a genset whose
+        running_min_production is 0 (:53-67).  Tuples of (slot, action)."""
+        from itertools import permutations
+        elements = self.priority_elements()
+        if len(elements) > MAX_PRIORITY_ELEMENTS:
+            raise NotImplementedError(f"{len(elements)} priority-list elements: the action table is enumerated from "
+                                      f"{len(elements)}! permutations like the reference's; at most {MAX_PRIORITY_ELEMENTS} are supported")
+        seen, out = set(), []
+        for perm in permutations(range(len(elements))):
+            listed, pl = set(), []
+            for i in perm:
+                s = elements[i][0]
+                if s.listing not in listed:
+                    listed.add(s.listing)
+                    pl.append(i)
+            pl = tuple(pl)
+            if pl not in seen:
+                seen.add(pl)
+                out.append(pl)
+        if remove_redundant_gensets:
+            redundant = {i for i, (s, a) in enumerate(elements)
+                         if s.kind == "genset" and a == 0 and self.records[s.listing].running_min_production == 0}
+            out = [pl for pl in out if not redundant.intersection(pl)]
+        return [tuple(elements[i] for i in pl) for pl in out]
+
+    def priority_table(self, lists):
+        """int16 [n, width, 2] = (index in the DISPATCH-ordered module table, action); -1 pads"""
+        width = max((len(pl) for pl in lists), default=1) or 1
+        tab = np.full((max(len(lists), 1), width, 2), -1, dtype=np.int16)
+        index = {id(s): k for k, s in enumerate(self.dispatch)}
+        for r, pl in enumerate(lists):
+            for c, (s, a) in enumerate(pl):
+                tab[r, c] = index[id(s)], a
+        return tab
+
     # ---- packing ----
     def config_record(self, series_index):
         """the f64 parameter record of this microgrid (include/pymgrid_b200_compose.h: enum MGC_* lists the blocks).
@@ -303,6 +351,13 @@ class ComposedBatch:
         L.step, L.cfg_index = self.step_counter.data_ptr(), self.cfg_index.data_ptr()
         L.fstate = self.fstate.data_ptr() if comp.n_fstate else None
         L.istate = self.istate.data_ptr() if comp.n_istate else None
+        # the discrete action table: every priority list of the composition (redundant genset lists included; callers
+        # that drop them map their own indices, see ComposedDiscreteEnv)
+        self.action_lists = None
+        if comp.n_act and len(comp.priority_elements()) <= MAX_PRIORITY_ELEMENTS:
+            self.action_lists = comp.priority_lists(False)
+            self.plist = t(comp.priority_table(self.action_lists), torch.int16)
+            L.plist, L.n_plist, L.plist_width = self.plist.data_ptr(), len(self.action_lists), self.plist.shape[1]
         self._handle = _vp()
         self._check(self._L.mgc_create(C.byref(L), C.byref(self._handle)), "mgc_create")
 
@@ -343,6 +398,38 @@ class ComposedBatch:
                    self.done.data_ptr(), self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None)
         self._check(self._L.mgc_run(self._handle, C.byref(io), 1, 1, int(bool(normalized)), self._stream()), "mgc_run")
         return (self.obs if obs else None), self.reward, self.done, self.info
+
+    def _dactions(self, actions, lead):
+        if self.action_lists is None:
+            raise NotImplementedError("this composition has no discrete action table (no controllable module, or more than "
+                                      f"{MAX_PRIORITY_ELEMENTS} priority-list elements)")
+        a = torch.as_tensor(actions, dtype=torch.int32, device=self.device).contiguous()
+        if tuple(a.shape) != lead + (self.n_envs,):
+            raise ValueError(f"discrete actions must have shape {lead + (self.n_envs,)}, got {tuple(a.shape)}")
+        return a
+
+    def step_discrete(self, actions, obs=True):
+        """DiscreteMicrogridEnv.step for every env (envs/discrete/discrete.py:109-143): `actions` int32 [B], indices into
+        `action_lists`; the expansion into controls (priority_list.py:69-116) runs on the device in front of the step."""
+        a = self._dactions(actions, ())
+        io = MgcIO(None, self.obs.data_ptr() if obs else None, self.reward.data_ptr(), self.done.data_ptr(),
+                   self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None, a.data_ptr(), 0)
+        self._check(self._L.mgc_run_discrete(self._handle, C.byref(io), 1, 1, self._stream()), "mgc_run_discrete")
+        return (self.obs if obs else None), self.reward, self.done, self.info
+
+    def rollout_discrete(self, actions, n_steps=None, ring=1, obs=True):
+        """`actions` int32 [T, B]: T discrete steps in one launch; or int32 [B] with `n_steps`: the same priority list
+        every step -- rule-based control (algos/rbc/rbc.py:64-93)."""
+        const = n_steps is not None
+        T = int(n_steps) if const else int(torch.as_tensor(actions).shape[0])
+        a = self._dactions(actions, () if const else (T,))
+        reward = torch.empty((T, self.n_envs), dtype=torch.float64, device=self.device)
+        done = torch.empty((T, self.n_envs), dtype=torch.uint8, device=self.device)
+        ring_buf = torch.zeros((ring, self.n_envs, self.comp.obs_dim), dtype=torch.float64, device=self.device) if obs else None
+        io = MgcIO(None, ring_buf.data_ptr() if obs else None, reward.data_ptr(), done.data_ptr(),
+                   self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None, a.data_ptr(), int(const))
+        self._check(self._L.mgc_run_discrete(self._handle, C.byref(io), T, int(ring), self._stream()), "mgc_run_discrete")
+        return dict(reward=reward, done=done, obs_ring=ring_buf, flags=self.flags)
 
     def rollout(self, actions=None, n_steps=None, normalized=True, ring=1, obs=True):
         """`n_steps` consecutive steps in ONE launch; `actions` [T, B, n_act].  Returns dict(reward [T, B], done [T, B],
@@ -622,6 +709,7 @@ class ComposedMicrogrid:
                                       "renewable, one battery, at most one genset and one grid)")
         comp = Composition(modules, add_unbalanced_module, loss_load_cost, overgeneration_cost, obs_order=obs_order)
         self.composition = comp
+        self._library = _library
         self._batch = ComposedBatch([comp], device=device, obs_order=obs_order, with_info=True, _library=_library)
         self._modules = ComposedContainer()
         for s, r in zip(comp.slots, comp.records):
@@ -700,7 +788,14 @@ class ComposedMicrogrid:
         row = self._control_row(control)
         pre = [v.state_dict() for v in self._views]
         b.step(row if comp.n_act else None, normalized=normalized)
+        return self._finish_step(pre)
+
+    def _finish_step(self, pre):
+        """log row, the reference's exceptions from the event flags, and the reference's return types"""
+        comp, b = self.composition, self._batch
         flags = int(b.flags[0].item()) & 0xffffffff
+        if flags & FLAG_BAD_ACTION:
+            raise ValueError("Action not in action space")                                          # envs/discrete/discrete.py:84
         if flags & FLAG_STEP_PAST_END:
             t = self.current_step
             raise IndexError(f"index {t} is out of bounds for axis 0 with size {len(self)}")     # e.g. load_module.py:111
@@ -714,6 +809,51 @@ class ComposedMicrogrid:
         if flags & FLAG_BALANCE:
             raise RuntimeError("Microgrid modules unable to balance energy production with consumption.\n")
         return (self._obs_dict(b.obs[0].cpu().numpy(), comp.dispatch), reward, bool(b.done[0].item()), self._info_dict(info))
+
+    def run_priority_list(self, priority_list, n_steps=1):
+        """`n_steps` DiscreteMicrogridEnv-style steps with one priority list -- an index into `action_lists`, or a list of
+        PriorityListElement-like objects (`.module`, `.action`): what RuleBasedControl.run does every step
+        (algos/rbc/rbc.py:87-91 -> priority_list.py:69-116 -> Microgrid.run(normalized=False)), expanded on the device.
+        Stops after the step that reports done; returns the last step's (obs, reward, done, info)."""
+        index = priority_list if isinstance(priority_list, (int, np.integer)) else self.priority_list_index(priority_list)
+        out = None
+        act = np.array([int(index)], dtype=np.int32)
+        for _ in range(int(n_steps)):
+            pre = [v.state_dict() for v in self._views]
+            self._batch.step_discrete(act)
+            out = self._finish_step(pre)
+            if out[2]:
+                break
+        return out
+
+    @property
+    def action_lists(self):
+        """every priority list of the microgrid as PriorityListElement tuples, in the reference's order
+        (PriorityListAlgo.get_priority_lists(remove_redundant_gensets=False))"""
+        return [self._elements(pl) for pl in (self._batch.action_lists or [])]
+
+    def _elements(self, pl):
+        from .algos import PriorityListElement
+        return tuple(PriorityListElement(module=(s.name, s.index), module_actions=2 if s.kind == "genset" else 1, action=a,
+                                         marginal_cost=self._views[s.listing].marginal_cost) for s, a in pl)
+
+    def priority_list_index(self, priority_list):
+        want = tuple((tuple(el.module), int(el.action)) for el in priority_list)
+        for k, pl in enumerate(self._batch.action_lists or []):
+            if tuple(((s.name, s.index), a) for s, a in pl) == want:
+                return k
+        raise ValueError('Invalid priority list. Use RuleBasedControl.get_priority_lists to view all valid priority lists.')
+
+    def copy(self):
+        """a second microgrid over the same module records carrying this one's live state (the deep copies the reference
+        takes in RuleBasedControl.__init__ / BaseMicrogridEnv.from_microgrid)"""
+        comp = self.composition
+        named = [(s.name, r) for s, r in zip(comp.slots, comp.records)]
+        other = ComposedMicrogrid(named, add_unbalanced_module=False, device=self._batch.device if self._batch.device.type == "cuda" else None,
+                                  obs_order=comp.obs_order, _library=self._library)
+        for a in ("step_counter", "fstate", "istate"):
+            getattr(other._batch, a).copy_(getattr(self._batch, a))
+        return other
 
     def _log_row(self, pre, info, reward):
         """one row of get_log(): base_module.py:276-290 per module, microgrid.py:259-260, 281, 317-319 for the balance"""
@@ -812,3 +952,170 @@ def in_fused_scope(modules, add_unbalanced_module=True):
     if "battery" <= names["renewable"] <= "load" or len(horizons) != 1:
         return False
     return True
+
+
+# ---- Gym-style envs and rule-based control on composed microgrids -------------------------------------------------------
+class _ComposedEnv:
+    """The reference's BaseMicrogridEnv surface (envs/base/base.py:84-223) for any module list: `batch=None` is one
+    microgrid with the reference's host types, `batch=B` steps B replicas with device tensors."""
+
+    def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2., reward_shaping_func=None,
+                 trajectory_func=None, batch=None, device=None, obs_order="gym_sorted", _library=None):
+        from .envs import Box
+        if reward_shaping_func is not None or trajectory_func is not None:
+            raise NotImplementedError("reward_shaping_func / trajectory_func are built for the fused module set only")
+        self.single = batch is None
+        self._mg = ComposedMicrogrid(modules, add_unbalanced_module, loss_load_cost, overgeneration_cost, device=device,
+                                     obs_order=obs_order, _library=_library) if not isinstance(modules, ComposedMicrogrid) else modules
+        comp = self.composition = self._mg.composition
+        if self.single:
+            self.batch = self._mg._batch
+        else:
+            self.batch = ComposedBatch([comp], np.zeros(int(batch), dtype=np.int64), device=device, obs_order=comp.obs_order,
+                                       _library=self._mg._library)
+            for a in ("step_counter", "fstate", "istate"):      # replicas start from the microgrid's live state
+                getattr(self.batch, a).copy_(getattr(self._mg._batch, a).expand_as(getattr(self.batch, a)))
+        self.n_envs = self.batch.n_envs
+        self.observation_space = Box(0.0, 1.0, (comp.obs_dim,))                 # base.py:161-163
+
+    @classmethod
+    def from_microgrid(cls, microgrid, **kw):
+        """reference: BaseMicrogridEnv.from_microgrid (envs/base/base.py:270-290): an env over a copy of a (possibly
+        running) microgrid, state included"""
+        if not isinstance(microgrid, ComposedMicrogrid):
+            raise TypeError("from_microgrid needs a composed pymgrid_b200.Microgrid")
+        return cls(microgrid.copy(), **kw)
+
+    modules = property(lambda self: self._mg.modules)
+    fixed = property(lambda self: self._mg.fixed)
+    flex = property(lambda self: self._mg.flex)
+    controllable = property(lambda self: self._mg.controllable)
+    initial_step = property(lambda self: self.composition.initial_step)
+    final_step = property(lambda self: self.composition.final_step)
+    log = property(lambda self: self._mg.log)
+
+    @property
+    def current_step(self):
+        return self._mg.current_step if self.single else self.batch.step_counter
+
+    def __len__(self):
+        return len(self._mg)
+
+    def get_log(self, *a, **kw):
+        return self._mg.get_log(*a, **kw)
+
+    def reset(self, mask=None):
+        """reference: BaseMicrogridEnv.reset (base.py:165-167): the flat observation after Microgrid.reset"""
+        if self.single:
+            self._mg.reset()
+            return self.batch.obs[0].cpu().numpy().copy()
+        return self.batch.reset(mask)
+
+    def _single_result(self, out):
+        obs, reward, done, info = out
+        return self.batch.obs[0].cpu().numpy().copy(), reward, done, info
+
+
+class ComposedDiscreteEnv(_ComposedEnv):
+    """Action = index of a priority list (reference: envs/discrete/discrete.py:60-143)"""
+
+    def __init__(self, modules, *args, remove_redundant_gensets=True, **kw):
+        from .envs import Discrete
+        super().__init__(modules, *args, **kw)
+        full = self.batch.action_lists
+        if full is None:
+            raise NotImplementedError("no discrete action table for this composition")
+        kept = self.composition.priority_lists(remove_redundant_gensets)
+        key = lambda pl: tuple((s.listing, a) for s, a in pl)      # noqa: E731
+        where = {key(pl): k for k, pl in enumerate(full)}
+        self._index = np.array([where[key(pl)] for pl in kept], dtype=np.int32)     # env action -> row of the device table
+        self.actions_list = [self._mg._elements(pl) for pl in kept]
+        self.action_space = Discrete(len(kept))
+        self._index_dev = torch.from_numpy(self._index).to(self.batch.device)
+
+    def step(self, action):
+        if self.single:
+            if action not in self.action_space:
+                raise ValueError(f" Action {action} not in action space {self.action_space}")       # discrete.py:84
+            return self._single_result(self._mg.run_priority_list(int(self._index[int(action)]), 1))
+        a = torch.as_tensor(action, device=self.batch.device).to(torch.int64)
+        bad = (a < 0) | (a >= len(self._index))
+        mapped = torch.where(bad, torch.full_like(a, -1), self._index_dev.to(torch.int64)[a.clamp(0, len(self._index) - 1)])
+        obs, reward, done, _ = self.batch.step_discrete(mapped.to(torch.int32))
+        return obs, reward, done, {"flags": self.batch.flags}
+
+    def sample_action(self, strict_bound=False, sample_flex_modules=False):
+        if self.single:
+            return self.action_space.sample()
+        return torch.randint(0, self.action_space.n, (self.n_envs,), dtype=torch.int32, device=self.batch.device)
+
+
+class ComposedContinuousEnv(_ComposedEnv):
+    """Action = flat vector in [0,1]^n_act: the controllable modules' normalised actions in Microgrid.controllable's order
+    (`action_layout`: (name, index) -> first column); the intended semantics of the reference's ContinuousMicrogridEnv
+    """
+
+    def __init__(self, modules, *args, **kw):
+        from .envs import Box
+        super().__init__(modules, *args, **kw)
+        self.action_space = Box(0.0, 1.0, (self.composition.n_act,))
+        self.action_layout = {(s.name, s.index): s.act_col for s in self.composition.dispatch if s.n_act}
+
+    def step(self, action, normalized=True):
+        if self.single:
+            row = np.asarray(action, dtype=np.float64).reshape(-1)
+            control = {name: [row[s.act_col:s.act_col + s.n_act] if s.n_act > 1 else row[s.act_col] for s in slots]
+                       for name, slots in self.composition.controllable()}
+            return self._single_result(self._mg.run(control, normalized=normalized))
+        obs, reward, done, _ = self.batch.step(action, normalized=normalized)
+        return obs, reward, done, {"flags": self.batch.flags}
+
+    def sample_action(self, strict_bound=False, sample_flex_modules=False):
+        if self.single:
+            return self.action_space.sample()
+        return torch.rand((self.n_envs, self.composition.n_act), dtype=torch.float64, device=self.batch.device)
+
+
+class ComposedRuleBasedControl:
+    """pymgrid.algos.RuleBasedControl (algos/rbc/rbc.py:7-140) on a composed microgrid: a fixed priority list -- by default
+    the first one sorted by marginal cost, ties towards the higher action number (rbc.py:31-44,
+    priority_list_element.py:73-80) -- deployed every step on the device."""
+
+    def __init__(self, microgrid, priority_list=None, remove_redundant_gensets=True):
+        if not isinstance(microgrid, ComposedMicrogrid):
+            raise TypeError("ComposedRuleBasedControl needs a composed pymgrid_b200.Microgrid")
+        self._microgrid = microgrid.copy()          # rbc.py:28-30: the controller works on a copy
+        self._remove_redundant_gensets = remove_redundant_gensets
+        lists = self.get_priority_lists(remove_redundant_gensets)
+        if priority_list is None:
+            priority_list = sorted(lists[0])
+        elif tuple(priority_list) not in [tuple(pl) for pl in lists]:
+            raise ValueError('Invalid priority list. Use RuleBasedControl.get_priority_lists to view all '
+                             'valid priority lists.')
+        self._priority_list = list(priority_list)
+        self._index = self._microgrid.priority_list_index(self._priority_list)
+
+    def get_priority_lists(self, remove_redundant_gensets=None):
+        if remove_redundant_gensets is None:
+            remove_redundant_gensets = self._remove_redundant_gensets
+        return [self._microgrid._elements(pl) for pl in self._microgrid.composition.priority_lists(remove_redundant_gensets)]
+
+    def reset(self):
+        return self._microgrid.reset()
+
+    def run(self, max_steps=None, verbose=False):
+        """reference: RuleBasedControl.run (rbc.py:64-93)"""
+        if max_steps is None:
+            max_steps = len(self._microgrid)
+        self.reset()
+        self._microgrid.run_priority_list(self._index, max_steps)
+        return self._microgrid.get_log(as_frame=True)
+
+    def get_empty_action(self):
+        return self._microgrid.get_empty_action()
+
+    microgrid = property(lambda self: self._microgrid)
+    fixed = property(lambda self: self._microgrid.fixed)
+    flex = property(lambda self: self._microgrid.flex)
+    modules = property(lambda self: self._microgrid.modules)
+    priority_list = property(lambda self: self._priority_list)

@@ -39,12 +39,14 @@ struct MgcLaunch {
     double *fstate;
     int32_t *istate;
     const int32_t *cfg_index;
+    const int16_t *plist;
+    int32_t n_plist, plist_width;
     // per call
     MgcIO io;
     int32_t mode, n_steps, ring, normalized;
 };
 
-enum { MGC_MODE_RUN = 0, MGC_MODE_RESET = 1, MGC_MODE_OBSERVE = 2 };
+enum { MGC_MODE_RUN = 0, MGC_MODE_RESET = 1, MGC_MODE_OBSERVE = 2, MGC_MODE_RUN_DISCRETE = 3 };
 
 #ifdef MGC_HOSTSIM
 #define MGC_DEV static inline
@@ -66,7 +68,7 @@ MGC_DEV MgcView mgc_view(const MgcLaunch &P, int e) {
 // phase 1 of a step for env e (one thread)
 MGC_DEV void mgc_owner(const MgcLaunch &P, int e, int s) {
     MgcView V = mgc_view(P, e);
-    if (P.mode == MGC_MODE_RUN) {
+    if (P.mode == MGC_MODE_RUN || P.mode == MGC_MODE_RUN_DISCRETE) {
         int32_t t = P.step[e];
         uint32_t flags = 0;
         double reward;
@@ -74,8 +76,26 @@ MGC_DEV void mgc_owner(const MgcLaunch &P, int e, int s) {
         const int64_t slot = (int64_t)s * P.n_envs + e;
         const double *action = P.io.actions ? P.io.actions + slot * P.n_act : nullptr;
         double *info = P.io.info ? P.io.info + (int64_t)e * (P.n_mod * MGC_INFO_SLOTS + MGC_BALANCE_SLOTS) : nullptr;
-        mgc_env_step(V, t, P.fstate + (int64_t)e * P.n_fstate, P.istate + (int64_t)e * P.n_istate, action, P.normalized, &reward,
-                     &done, info, &flags);
+        double *fstate = P.fstate + (int64_t)e * P.n_fstate;
+        int32_t *istate = P.istate + (int64_t)e * P.n_istate;
+        int normalized = P.normalized;
+        double ctl[2 * MGC_MAX_MODULES];
+        bool skip = false;
+        if (P.mode == MGC_MODE_RUN_DISCRETE) {
+            const int32_t a = P.io.dactions[P.io.dactions_const ? e : slot];
+            if (a < 0 || a >= P.n_plist) {              // ValueError, envs/discrete/discrete.py:84
+                flags |= MG_FLAG_BAD_ACTION;
+                reward = NAN;
+                done = 0;
+                skip = true;
+            } else if (P.T == 0 || t < P.T) {           // past the end of the series the step itself reports IndexError
+                mgc_priority_control(V, t, fstate, istate, P.plist + (int64_t)a * P.plist_width * 2, P.plist_width, P.n_act,
+                                     ctl, &flags);
+            }
+            action = ctl;
+            normalized = 0;
+        }
+        if (!skip) mgc_env_step(V, t, fstate, istate, action, normalized, &reward, &done, info, &flags);
         P.step[e] = t;
         P.io.reward[slot] = reward;
         P.io.done[slot] = done;
@@ -99,7 +119,7 @@ __global__ void __launch_bounds__(MGC_TILE) mgc_kernel(const __grid_constant__ M
     const int e0 = blockIdx.x * MGC_TILE;
     const int n_tile = min(MGC_TILE, P.n_envs - e0);
     const int e = e0 + threadIdx.x;
-    const int n_steps = (P.mode == MGC_MODE_RUN) ? P.n_steps : 1;
+    const int n_steps = (P.mode == MGC_MODE_RUN || P.mode == MGC_MODE_RUN_DISCRETE) ? P.n_steps : 1;
     for (int s = 0; s < n_steps; ++s) {
         if (threadIdx.x < n_tile) mgc_owner(P, e, s);
         __syncthreads();      // the tile's state rows (global memory, written by their owners) are read by every thread below
@@ -117,7 +137,7 @@ __global__ void __launch_bounds__(MGC_TILE) mgc_kernel(const __grid_constant__ M
 #else
 static void mgc_kernel_host(const MgcLaunch &P) {
     const int tiles = (P.n_envs + MGC_TILE - 1) / MGC_TILE;
-    const int n_steps = (P.mode == MGC_MODE_RUN) ? P.n_steps : 1;
+    const int n_steps = (P.mode == MGC_MODE_RUN || P.mode == MGC_MODE_RUN_DISCRETE) ? P.n_steps : 1;
     for (int b = 0; b < tiles; ++b) {
         const int e0 = b * MGC_TILE;
         const int n_tile = (P.n_envs - e0 < MGC_TILE) ? P.n_envs - e0 : MGC_TILE;
@@ -225,6 +245,8 @@ extern "C" int mgc_create(const MgcLayout *L, MgcHandle **out) {
     if ((nf > 0 && !L->fstate) || (ni > 0 && !L->istate)) return mgc_fail(MG_E_INVALID, "mgc_create: null state pointer");
     if (n_ts > 0 && (L->series_len < 1 || L->n_series < 1 || !L->series || !L->series_off))
         return mgc_fail(MG_E_INVALID, "mgc_create: time-series modules without a series pool");
+    if (L->plist && (L->n_plist < 1 || L->plist_width < 1 || L->plist_width > 2 * MGC_MAX_MODULES))
+        return mgc_fail(MG_E_INVALID, "mgc_create: bad priority-list table");
     MgcHandle *h = new (std::nothrow) MgcHandle();
     if (!h) return mgc_fail(MG_E_INVALID, "mgc_create: out of host memory");
     MgcLaunch &B = h->base;
@@ -234,6 +256,7 @@ extern "C" int mgc_create(const MgcLayout *L, MgcHandle **out) {
     B.cfg_stride = L->cfg_stride; B.T = L->series_len; B.n_envs = (int32_t)L->n_envs;
     B.cfg = L->cfg; B.series = L->series; B.series_off = L->series_off;
     B.step = L->step; B.fstate = L->fstate; B.istate = L->istate; B.cfg_index = L->cfg_index;
+    B.plist = L->plist; B.n_plist = L->plist ? L->n_plist : 0; B.plist_width = L->plist_width;
     h->launches = 0;
     *out = h;
     return MG_OK;
@@ -255,6 +278,10 @@ static int mgc_launch(MgcHandle *h, const MgcIO *io, int mode, int32_t n_steps, 
         if (n_steps < 1 || ring < 1) return mgc_fail(MG_E_INVALID, "mgc_run: n_steps and ring must be >= 1");
         if (!io->reward || !io->done) return mgc_fail(MG_E_INVALID, "mgc_run: reward and done are required");
         if (P.n_act > 0 && !io->actions) return mgc_fail(MG_E_INVALID, "mgc_run: actions are required (n_act > 0)");
+    } else if (mode == MGC_MODE_RUN_DISCRETE) {
+        if (n_steps < 1 || ring < 1) return mgc_fail(MG_E_INVALID, "mgc_run_discrete: n_steps and ring must be >= 1");
+        if (!io->reward || !io->done || !io->dactions) return mgc_fail(MG_E_INVALID, "mgc_run_discrete: reward, done and dactions are required");
+        if (!P.plist) return mgc_fail(MG_E_INVALID, "mgc_run_discrete: the layout has no priority-list table");
     } else {
         P.n_steps = 1; P.ring = 1;
         if (mode == MGC_MODE_OBSERVE && !io->obs) return mgc_fail(MG_E_INVALID, "mgc_observe: obs is required");
@@ -278,6 +305,9 @@ static int mgc_launch(MgcHandle *h, const MgcIO *io, int mode, int32_t n_steps, 
 
 extern "C" int mgc_run(MgcHandle *h, const MgcIO *io, int32_t n_steps, int32_t ring, int normalized, void *stream) {
     return mgc_launch(h, io, MGC_MODE_RUN, n_steps, ring, normalized, stream);
+}
+extern "C" int mgc_run_discrete(MgcHandle *h, const MgcIO *io, int32_t n_steps, int32_t ring, void *stream) {
+    return mgc_launch(h, io, MGC_MODE_RUN_DISCRETE, n_steps, ring, 0, stream);
 }
 extern "C" int mgc_reset(MgcHandle *h, const MgcIO *io, void *stream) { return mgc_launch(h, io, MGC_MODE_RESET, 1, 1, 0, stream); }
 extern "C" int mgc_observe(MgcHandle *h, const MgcIO *io, void *stream) { return mgc_launch(h, io, MGC_MODE_OBSERVE, 1, 1, 0, stream); }

@@ -414,4 +414,68 @@ MGC_HD void mgc_env_step(const MgcView &V, int32_t &t, double *fstate, int32_t *
     *flags |= A.flags;
 }
 
+/*
+ * PriorityListAlgo._populate_action (algos/priority_list/priority_list.py:69-167) for one env: expand one priority list --
+ * `width` elements (dispatch index of a controllable module, action number), negative module = padding -- into the
+ * UNNORMALISED action row `ctl` (n_act doubles) that Microgrid.run(normalized=False) then takes.
+ *   remaining = sum of the loads - np.sum of the renewables' production (:71-75, 157-167), then per element:
+ *   |remaining| <= 1e-4 -> 0 (:92); remaining > 0 -> clip into the module's [min, max] production, a genset's taken
+ *   from the status its goal leads to NEXT step (:138-155, genset_module.py:360-424); remaining < 0 -> absorb what a sink
+ *   can, sources 0 (:118-136); remaining -= energy.  A genset appears once per goal in a list; only its first
+ *   element counts (:84-87).
+ */
+MGC_HD void mgc_priority_control(const MgcView &V, int t, const double *fstate, const int32_t *istate, const int16_t *pl,
+                                 int width, int n_act, double *ctl, uint32_t *flags) {
+    double total_load = 0.0;
+    double ren[MGC_MAX_MODULES];
+    int n_ren = 0;
+    for (int m = 0; m < V.n_mod; ++m) {
+        const MgcModule &M = V.mod[m];
+        const double *p = V.cfg + M.param_off;
+        if (M.kind == MGC_LOAD) total_load += -1 * mgc_series_of(V, p)[t];          /* load_module.py:96-111 */
+        else if (M.kind == MGC_RENEWABLE) ren[n_ren++] = mgc_series_of(V, p)[t];
+    }
+    double remaining = total_load - mgc_np_sum(ren, n_ren);
+    for (int i = 0; i < n_act; ++i) ctl[i] = 0.0;
+    uint64_t seen = 0;          /* gensets already given their goal by an earlier element */
+    for (int i = 0; i < width; ++i) {
+        const int m = pl[2 * i], act = pl[2 * i + 1];
+        if (m < 0) continue;
+        const MgcModule &M = V.mod[m];
+        const double *p = V.cfg + M.param_off;
+        if (M.kind == MGC_GENSET) {
+            if (seen & (1ull << m)) continue;
+            seen |= 1ull << m;
+            ctl[M.act_col] = (double)act;
+        }
+        double energy;
+        if (fabs(remaining - 0.0) <= 1e-4 + 1e-5 * fabs(0.0)) {       /* np.isclose(remaining, 0.0, atol=1e-4) */
+            energy = 0.0;
+        } else if (remaining > 0) {
+            double mx, mn;
+            if (M.kind == MGC_GENSET) {
+                const int32_t *s = istate + M.istate_off;
+                const int next = act ? ((s[0] || s[2] == 0) ? 1 : 0) : ((!s[0] || s[3] == 0) ? 0 : 1);
+                mx = next * p[1];
+                mn = next * p[0];
+            } else {
+                mx = mgc_max_production(V, M, p, t, fstate, istate);
+                mn = 0.0;
+            }
+            if (mn <= remaining && remaining <= mx) energy = remaining;
+            else if (remaining < mn) energy = mn;
+            else energy = mx;
+        } else {
+            if (!mgc_is_sink(M.kind)) energy = 0.0;
+            else {
+                const double mc = mgc_max_consumption(V, M, p, t, fstate);
+                if (!(mc >= 0)) *flags |= MG_FLAG_NEGATIVE_ABSORB;     /* :124 assert module_max_consumption >= 0 */
+                energy = (-1 * remaining > mc) ? -1.0 * mc : remaining;
+            }
+        }
+        ctl[M.act_col + (M.kind == MGC_GENSET ? 1 : 0)] = energy;
+        remaining -= energy;
+    }
+}
+
 #endif /* MG_COMPOSE_STEP_H */

@@ -55,8 +55,23 @@ class Discrete:
         return f"Discrete({self.n})"
 
 
+def _composed_route(cls, configs, kw):
+    """module lists outside the fused kernels' scope go to the composed path (compose.py), same surface"""
+    if isinstance(configs, (list, tuple)) and configs and not any(hasattr(c, "arch") for c in configs):
+        from .compose import ComposedContinuousEnv, ComposedDiscreteEnv, in_fused_scope
+        if not in_fused_scope(configs, kw.get("add_unbalanced_module", True)):
+            return ComposedDiscreteEnv if cls is DiscreteMicrogridEnv else ComposedContinuousEnv
+    return None
+
+
 class _BaseEnv:
     """Shared plumbing: one architecture (all envs share obs / action layout), B replicas or B heterogeneous configs."""
+
+    def __new__(cls, configs=None, env_config=None, batch=None, **kw):
+        target = _composed_route(cls, configs, kw) if cls in (DiscreteMicrogridEnv, ContinuousMicrogridEnv) and env_config is None else None
+        if target is not None:
+            return target(configs, batch=batch, **kw)
+        return super().__new__(cls)
 
     def __init__(self, configs, env_config=None, batch=None, device=None, obs_order="gym_sorted", with_info=False,
                  add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2., reward_shaping_func=None,
@@ -102,6 +117,10 @@ class _BaseEnv:
     def from_microgrid(cls, microgrid, batch=None, **kw):
         """reference: BaseMicrogridEnv.from_microgrid (envs/base/base.py:270-290): an env over a copy of a (possibly
         running) microgrid, state included.  Accepts a pymgrid_b200.Microgrid or a MicrogridParams."""
+        from .compose import ComposedContinuousEnv, ComposedDiscreteEnv, ComposedMicrogrid
+        if isinstance(microgrid, ComposedMicrogrid):       # any module list: the composed path
+            target = ComposedDiscreteEnv if issubclass(cls, DiscreteMicrogridEnv) else ComposedContinuousEnv
+            return target.from_microgrid(microgrid, batch=batch, **kw)
         params = microgrid.export_params() if hasattr(microgrid, "export_params") else microgrid
         return cls(params, batch=batch, **kw)
 

@@ -7,7 +7,7 @@ import numpy as np
 
 from pymgrid_b200 import modules as M
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "compose.npz")
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 INFO_SLOTS = 5
 BALANCE_COLS = ("reward", "shaped_reward", "overall_provided_to_microgrid", "overall_absorbed_from_microgrid",
                 "controllable_provided_to_microgrid", "controllable_absorbed_from_microgrid",
@@ -54,6 +54,6 @@ class ComposeCase:
         return out
 
 
-def load_cases():
-    data = np.load(GOLDEN)
+def load_cases(file="compose.npz"):
+    data = np.load(os.path.join(GOLDEN_DIR, file))
     return [ComposeCase(data, i) for i in range(int(data["n_cases"]))]

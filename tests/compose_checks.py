@@ -123,3 +123,62 @@ def check_batch_matches_oracle_and_rollout_matches_steps(label, lib, n_envs=131,
     batch.reset(mask)
     assert np.array_equal(batch.step_counter.cpu().numpy(), np.where(mask, comp.initial_step, T + comp.initial_step))
     assert torch.equal(before, batch.fstate)
+
+
+# ---- priority lists: DiscreteMicrogridEnv / RuleBasedControl on composed microgrids ------------------------------------
+DISCRETE_CASES = load_cases("compose_discrete.npz")
+
+
+def check_discrete_env_and_rbc(case, lib):
+    from pymgrid_b200.compose import ComposedDiscreteEnv, ComposedRuleBasedControl
+    kw = {} if lib is None else {"_library": lib}
+    rows = lambda pls: [[[el.module[0], el.module[1], el.module_actions, el.action] for el in pl] for pl in pls]     # noqa: E731
+    # the action tables, with and without the redundant genset lists
+    for flag in (0, 1):
+        env = ComposedDiscreteEnv(case.modules(), obs_order="container", remove_redundant_gensets=bool(flag), **kw, **case.microgrid_kwargs)
+        assert rows(env.actions_list) == case.json(f"table_{flag}")
+        assert env.action_space.n == len(case.json(f"table_{flag}"))
+    env = ComposedDiscreteEnv(case.modules(), obs_order="container", remove_redundant_gensets=False, **kw, **case.microgrid_kwargs)
+    assert env.observation_space.shape == (case["obs"].shape[1],)
+    env.reset()
+    mg = env._mg
+    for k, a in enumerate(case["actions"]):
+        obs, reward, done, info = env.step(int(a))
+        assert reward == case["rewards"][k] and done == bool(case["dones"][k]), k
+        assert np.array_equal(obs, case["obs"][k]), k          # container order = the recorded listing order
+        t, f, i_ = mg._state()
+        state = []
+        for s in mg.composition.slots:
+            if s.kind == "battery":
+                state += list(f[s.fstate_off:s.fstate_off + 2])
+            elif s.kind == "genset":
+                state += list(i_[s.istate_off:s.istate_off + 4])
+        assert np.array_equal(np.array(state, dtype=np.float64), case["states"][k]), k
+    with pytest.raises(ValueError):
+        env.step(env.action_space.n)
+    # the same action sequence for a batch of replicas, one launch
+    benv = ComposedDiscreteEnv(case.modules(), obs_order="container", remove_redundant_gensets=False, batch=130, **kw,
+                               **case.microgrid_kwargs)
+    benv.reset()
+    acts = torch.from_numpy(np.repeat(case["actions"][:, None], 130, axis=1).astype(np.int32)).to(benv.batch.device)
+    out = benv.batch.rollout_discrete(acts, ring=1)
+    assert np.array_equal(host(out["reward"]), np.repeat(case["rewards"][:, None], 130, axis=1))
+    assert np.array_equal(host(out["obs_ring"][0]), np.repeat(case["obs"][-1][None], 130, axis=0))
+    obs, reward, done, _ = benv.step(torch.full((130,), -1, dtype=torch.int32))       # not in the action space
+    assert bool(torch.isnan(reward).all()) and bool((benv.batch.flags & 64).all())
+    # rule-based control
+    import pymgrid_b200
+    mg = ComposedMicrogrid(case.modules(), obs_order="container", **kw, **case.microgrid_kwargs)
+    rbc = pymgrid_b200.algos.RuleBasedControl(mg)
+    assert isinstance(rbc, ComposedRuleBasedControl)
+    assert rows([rbc.priority_list])[0] == case.json("rbc_list")
+    log = rbc.run(max_steps=len(case["rbc_rewards"]))
+    assert [list(c) for c in log.columns] == case.json("rbc_log_columns")
+    assert np.array_equal(log.to_numpy(dtype=np.float64), case["rbc_log_values"], equal_nan=True)
+    assert np.array_equal(log[("balance", 0, "reward")].to_numpy(), case["rbc_rewards"])
+    assert mg.current_step == mg.initial_step           # the controller ran on a copy (rbc.py:28-30)
+    # one launch for the whole run, B replicas
+    batch = ComposedBatch([case.modules()], np.zeros(5, dtype=np.int64), microgrid_kwargs=case.microgrid_kwargs, **kw)
+    T = len(case["rbc_rewards"])
+    out = batch.rollout_discrete(np.full(5, rbc._index, dtype=np.int32), n_steps=T, obs=False)
+    assert np.array_equal(host(out["reward"]), np.repeat(case["rbc_rewards"][:, None], 5, axis=1))

@@ -77,3 +77,40 @@ def test_product_path_needs_cuda():
     import pymgrid_b200
     with pytest.raises(_cabi.EngineError):
         pymgrid_b200.Microgrid(case.modules())        # routed to the composed path (two-module list), which needs CUDA
+
+
+@pytest.mark.parametrize("case", K.DISCRETE_CASES, ids=[c.label for c in K.DISCRETE_CASES])
+def test_discrete_env_and_rule_based_control_reproduce_reference(case, lib):
+    K.check_discrete_env_and_rbc(case, lib)
+
+
+def test_env_and_controller_constructors_route_to_the_composed_path(lib):
+    """pymgrid_b200.envs.DiscreteMicrogridEnv / ContinuousMicrogridEnv / algos.RuleBasedControl / Microgrid take module lists
+    outside the fused scope and hand them to the composed classes (same surface)"""
+    import pymgrid_b200
+    from pymgrid_b200.compose import ComposedContinuousEnv, ComposedDiscreteEnv, ComposedRuleBasedControl
+    from pymgrid_b200.envs import ContinuousMicrogridEnv, DiscreteMicrogridEnv
+    case = next(c for c in K.DISCRETE_CASES if c.label == "two_batteries_grid")
+    env = DiscreteMicrogridEnv(case.modules(), _library=lib)
+    assert isinstance(env, ComposedDiscreteEnv) and env.action_space.n == 6
+    obs = env.reset()
+    assert obs.shape == env.observation_space.shape and ((0 <= obs) & (obs <= 1)).all()
+    obs, reward, done, info = env.step(env.sample_action())
+    assert isinstance(reward, float) and isinstance(done, bool) and set(info) == {"load", "renewable", "battery", "grid", "balancing"}
+    cenv = ContinuousMicrogridEnv(case.modules(), batch=7, _library=lib)
+    assert isinstance(cenv, ComposedContinuousEnv) and cenv.action_space.shape == (3,)
+    assert cenv.action_layout == {("battery", 0): 0, ("battery", 1): 1, ("grid", 0): 2}
+    obs, reward, done, _ = cenv.step(cenv.sample_action())
+    assert obs.shape == (7, cenv.observation_space.shape[0]) and reward.shape == (7,)
+    single = ContinuousMicrogridEnv(case.modules(), _library=lib)
+    mg = pymgrid_b200.Microgrid(case.modules(), _library=lib)
+    a = np.array([0.3, 0.8, 0.55])
+    o1, r1, d1, _ = single.step(a)
+    _, r2, d2, _ = mg.run({"battery": [0.3, 0.8], "grid": [0.55]})
+    assert r1 == r2 and d1 == d2
+    env3 = DiscreteMicrogridEnv.from_microgrid(mg)
+    assert isinstance(env3, ComposedDiscreteEnv)
+    assert env3.current_step == mg.current_step == 1          # the copy carries the live state
+    env3.step(0)
+    assert env3.current_step == 2 and mg.current_step == 1
+    assert isinstance(pymgrid_b200.algos.RuleBasedControl(mg), ComposedRuleBasedControl)

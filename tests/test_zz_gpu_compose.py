@@ -83,3 +83,8 @@ from tests.reference_suite_compose import make_suite  # noqa: E402
 for _cls in make_suite(None):
     globals()[_cls.__name__ + "OnGpu"] = type(_cls.__name__ + "OnGpu", (_cls,), {})
 del _cls
+
+
+@pytest.mark.parametrize("case", K.DISCRETE_CASES, ids=[c.label for c in K.DISCRETE_CASES])
+def test_discrete_env_and_rule_based_control_reproduce_reference_on_gpu(case):
+    K.check_discrete_env_and_rbc(case, None)
