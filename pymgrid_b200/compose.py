@@ -431,9 +431,10 @@ class ComposedBatch:
         self._check(self._L.mgc_run_discrete(self._handle, C.byref(io), T, int(ring), self._stream()), "mgc_run_discrete")
         return dict(reward=reward, done=done, obs_ring=ring_buf, flags=self.flags)
 
-    def rollout(self, actions=None, n_steps=None, normalized=True, ring=1, obs=True):
+    def rollout(self, actions=None, n_steps=None, normalized=True, ring=1, obs=True, out=None):
         """`n_steps` consecutive steps in ONE launch; `actions` [T, B, n_act].  Returns dict(reward [T, B], done [T, B],
-        obs_ring [ring, B, D] | None, flags [B] OR-ed over the steps)."""
+        obs_ring [ring, B, D] | None, flags [B] OR-ed over the steps); `out`: a dict returned by an earlier call of the same
+        shape, to write into instead of allocating."""
         comp = self.comp
         if comp.n_act:
             T = int(torch.as_tensor(actions).shape[0]) if n_steps is None else int(n_steps)
@@ -442,9 +443,13 @@ class ComposedBatch:
             if n_steps is None:
                 raise ValueError("n_steps is required when the composition has no controllable module")
             T, a = int(n_steps), None
-        reward = torch.empty((T, self.n_envs), dtype=torch.float64, device=self.device)
-        done = torch.empty((T, self.n_envs), dtype=torch.uint8, device=self.device)
-        ring_buf = torch.zeros((ring, self.n_envs, comp.obs_dim), dtype=torch.float64, device=self.device) if obs else None
+        if out is not None and tuple(out["reward"].shape) == (T, self.n_envs) and \
+                (not obs or (out["obs_ring"] is not None and out["obs_ring"].shape[0] == ring)):
+            reward, done, ring_buf = out["reward"], out["done"], (out["obs_ring"] if obs else None)
+        else:
+            reward = torch.empty((T, self.n_envs), dtype=torch.float64, device=self.device)
+            done = torch.empty((T, self.n_envs), dtype=torch.uint8, device=self.device)
+            ring_buf = torch.zeros((ring, self.n_envs, comp.obs_dim), dtype=torch.float64, device=self.device) if obs else None
         io = MgcIO(a.data_ptr() if a is not None else None, ring_buf.data_ptr() if obs else None, reward.data_ptr(),
                    done.data_ptr(), self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None)
         self._check(self._L.mgc_run(self._handle, C.byref(io), T, int(ring), int(bool(normalized)), self._stream()), "mgc_run")
