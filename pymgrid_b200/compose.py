@@ -897,6 +897,20 @@ class ComposedMicrogrid:
         out["balance"], out["other"] = {}, {}
         return out
 
+    def __getattr__(self, item):
+        """`microgrid.<module name>` (reference: Microgrid.__getattr__, microgrid.py:1023-1030)"""
+        if item.startswith("_"):
+            raise AttributeError(item)
+        mods = self.__dict__.get("_modules")
+        if mods is not None and item in mods:
+            return mods[item]
+        raise AttributeError(item)
+
+    def get_cost_info(self):
+        """reference: Microgrid.get_cost_info (microgrid.py:334-335)"""
+        return {name: [dict(production_marginal_cost=m.production_marginal_cost, absorption_marginal_cost=m.absorption_marginal_cost)
+                       for m in lst] for name, lst in self._modules.items()}
+
     # ---- actions ----
     def sample_action(self, strict_bound=False, sample_flex_modules=False):
         """reference: Microgrid.sample_action (microgrid.py:337-362)"""

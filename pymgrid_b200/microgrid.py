@@ -581,6 +581,20 @@ class Microgrid:
             g.current_status, g.goal_status, g.steps_until_up, g.steps_until_down = st["genset"]
         return p
 
+    def __getattr__(self, item):
+        """`microgrid.<module name>` (reference: Microgrid.__getattr__, microgrid.py:1023-1030)"""
+        if item.startswith("_"):
+            raise AttributeError(item)
+        mods = self.__dict__.get("_modules")
+        if mods is not None and item in mods:
+            return mods[item]
+        raise AttributeError(item)
+
+    def get_cost_info(self):
+        """reference: Microgrid.get_cost_info (microgrid.py:334-335)"""
+        return {name: [dict(production_marginal_cost=m.production_marginal_cost, absorption_marginal_cost=m.absorption_marginal_cost)
+                       for m in lst] for name, lst in self._modules.items()}
+
     def get_forecast_horizon(self):
         """reference: Microgrid.get_forecast_horizon (microgrid.py:364-388)"""
         return self.params.forecast_horizon

@@ -182,3 +182,30 @@ def check_discrete_env_and_rbc(case, lib):
     T = len(case["rbc_rewards"])
     out = batch.rollout_discrete(np.full(5, rbc._index, dtype=np.int32), n_steps=T, obs=False)
     assert np.array_equal(host(out["reward"]), np.repeat(case["rbc_rewards"][:, None], 5, axis=1))
+
+
+# ---- the reference's quick-start notebook, cell by cell ----------------------------------------------------------------
+def check_quickstart_notebook(lib):
+    """notebooks/quick-start.ipynb against pymgrid_b200: same cells (tests/golden/make_quickstart.py: notebook()), same
+    displays, same log -- including the ten `sample_action(strict_bound=True)` steps under np.random.seed(0)"""
+    import importlib.util
+    import json
+    import os
+    import pymgrid_b200
+    from pymgrid_b200.modules import BatteryModule, GridModule, LoadModule, RenewableModule
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = open(os.path.join(here, "golden", "make_quickstart.py")).read()
+    start, end = src.index("def notebook("), src.index("def main():")
+    ns = {"np": np}
+    exec(compile(src[start:end], "quickstart_notebook", "exec"), ns)      # the notebook cells only, not the reference loader
+    kw = {} if lib is None else {"_library": lib}
+    got = ns["notebook"](pymgrid_b200.Microgrid, BatteryModule, LoadModule, RenewableModule, GridModule, obs_order="container", **kw)
+    want = np.load(os.path.join(here, "golden", "quickstart.npz"))
+    for key, value in got.items():
+        ref = want[key]
+        if isinstance(value, np.ndarray):
+            assert np.array_equal(value, ref, equal_nan=True), key
+        elif isinstance(value, float):
+            assert value == float(json.loads(str(ref))), key
+        else:
+            assert json.loads(json.dumps(value)) == json.loads(str(ref)), key

@@ -114,3 +114,7 @@ def test_env_and_controller_constructors_route_to_the_composed_path(lib):
     env3.step(0)
     assert env3.current_step == 2 and mg.current_step == 1
     assert isinstance(pymgrid_b200.algos.RuleBasedControl(mg), ComposedRuleBasedControl)
+
+
+def test_quickstart_notebook_replays_value_for_value(lib):
+    K.check_quickstart_notebook(lib)

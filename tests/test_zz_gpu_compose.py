@@ -88,3 +88,7 @@ del _cls
 @pytest.mark.parametrize("case", K.DISCRETE_CASES, ids=[c.label for c in K.DISCRETE_CASES])
 def test_discrete_env_and_rule_based_control_reproduce_reference_on_gpu(case):
     K.check_discrete_env_and_rbc(case, None)
+
+
+def test_quickstart_notebook_replays_value_for_value_on_gpu():
+    K.check_quickstart_notebook(None)
