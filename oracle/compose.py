@@ -212,8 +212,10 @@ class Raised(Exception):
 
 
 class ComposedOracle:
-    def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10.0, overgeneration_cost=2.0):
+    def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10.0, overgeneration_cost=2.0,
+                 reward_shaping_func=None, trajectory_func=None):
         """modules: list of pymgrid_b200.modules records or (name, record) tuples -- microgrid.py:100-165"""
+        self.reward_shaping_func, self.trajectory_func = reward_shaping_func, trajectory_func
         from pymgrid_b200.modules import UnbalancedEnergyModule
         named = []
         for m in modules:
@@ -248,8 +250,15 @@ class ComposedOracle:
 
     def reset(self):
         """microgrid.py:205-225 + base_module.py:65-77: only the step counter moves"""
+        initial = self.initial_step
+        if self.trajectory_func is not None:      # microgrid.py:221-225, 652-684: the modules' window moves, the microgrid's stays
+            ts = [m for m in self.listing if m.kind in ("load", "renewable", "grid")]
+            final0 = ts[0].rec.final_step if ts[0].rec.final_step > 0 else ts[0].T
+            initial, final = self.trajectory_func(self.initial_step, final0)
+            for m in ts:
+                m.final_step = final
         for m in self.listing:
-            m.t = m.rec.initial_step
+            m.t = initial
         self.log_rows = []
         return OrderedDict((name, [m.obs() for m in lst]) for name, lst in self.by_name.items())
 
@@ -377,6 +386,9 @@ class ComposedOracle:
     def run(self, control, normalized=True):
         """microgrid.py:227-325 -> (obs dict, reward, done, info dict); the log row is appended to self.log_rows"""
         obs, info_out = OrderedDict(), OrderedDict()
+        cost_info = self.cost_info()              # microgrid.py:253, before any module steps
+        shaped = lambda: (self.reward_shaping_func(OrderedDict(info_out), cost_info)      # noqa: E731  step.py:41-46
+                          if self.reward_shaping_func is not None else reward_sum)
         reward_sum, done_any = 0.0, False
         provided, absorbed = [], []
         logs = {}
@@ -398,6 +410,7 @@ class ComposedOracle:
             for m in lst:
                 append(name, m, self._module_step(m, 0.0, False))
         fixed_p, fixed_a = np_sum(provided), np_sum(absorbed)
+        shaped()                                  # balance() evaluates the shaper every time it is called (step.py:33-36)
         control = dict(control)
         for name, lst in self._of(CONTROLLABLE):
             if name not in control:
@@ -410,6 +423,7 @@ class ComposedOracle:
             for m, a in pairs:
                 append(name, m, self._module_step(m, a, normalized))
         p, a = np_sum(provided), np_sum(absorbed)
+        shaped()
         difference = p - a
         ctrl_p, ctrl_a = p - fixed_p, a - fixed_a
         if difference > 0:
@@ -437,11 +451,12 @@ class ComposedOracle:
                     append(name, m, self._module_step(m, amt, False))
                     needed -= amt
         p, a = np_sum(provided), np_sum(absorbed)
+        shaped_reward = shaped()
         row = OrderedDict()
         for m in self.listing:
             for key, v in logs[(m.name, m.index)].items():
                 row[(m.name, m.index, key)] = v
-        for key, v in (("reward", reward_sum), ("shaped_reward", reward_sum), ("overall_provided_to_microgrid", p),
+        for key, v in (("reward", reward_sum), ("shaped_reward", shaped_reward), ("overall_provided_to_microgrid", p),
                        ("overall_absorbed_from_microgrid", a), ("controllable_provided_to_microgrid", ctrl_p),
                        ("controllable_absorbed_from_microgrid", ctrl_a), ("fixed_provided_to_microgrid", fixed_p),
                        ("fixed_absorbed_from_microgrid", fixed_a)):
@@ -449,7 +464,28 @@ class ComposedOracle:
         self.log_rows.append(row)
         if not isclose(p, a):
             raise Raised("RuntimeError", "Microgrid modules unable to balance energy production with consumption.")
-        return obs, reward_sum, done_any, info_out
+        return obs, shaped(), done_any, info_out
+
+    def cost_info(self):
+        """Microgrid.get_cost_info (microgrid.py:334-335): each module's marginal costs at the CURRENT step"""
+        out = OrderedDict()
+        for name, lst in self.by_name.items():
+            out[name] = []
+            for m in lst:
+                k, r = m.kind, m.rec
+                if k == "battery":
+                    pc = ac = r.battery_cost_cycle                                          # battery_module.py:340-346
+                elif k == "genset":
+                    pc, ac = r.genset_cost * 1.0 + r.cost_per_unit_co2 * (r.co2_per_unit * 1.0), 0.0      # genset_module.py:519-521
+                elif k == "grid":
+                    row = m.series_state()                                                  # grid_module.py:322-328: state[0], state[1]
+                    pc, ac = row[0], row[1]
+                elif k == "balancing":
+                    pc, ac = r.loss_load_cost, r.overgeneration_cost
+                else:
+                    pc = ac = 0.0
+                out[name].append(dict(production_marginal_cost=pc, absorption_marginal_cost=ac))
+        return out
 
 
 # ---- priority lists: algos/priority_list/priority_list.py:15-167, priority_list_element.py:6-80 ------------------------

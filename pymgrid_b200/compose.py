@@ -502,6 +502,7 @@ class ComposedModuleView:
             raise AttributeError(item)
         return getattr(self._r, item)
 
+    _module_record = property(lambda self: self._r)      # what `Microgrid(microgrid.modules.to_tuples())` rebuilds from
     module_type = property(lambda self: self._r.module_type)
     is_source = property(lambda self: self._s.is_source)
     is_sink = property(lambda self: self._s.is_sink)
@@ -571,12 +572,12 @@ class ComposedModuleView:
         k, r = self._s.kind, self._r
         return {"battery": lambda: r.battery_cost_cycle,
                 "genset": lambda: r.genset_cost * 1.0 + r.cost_per_unit_co2 * (r.co2_per_unit * 1.0),
-                "grid": lambda: self._row()[0], "balancing": lambda: r.loss_load_cost}.get(k, lambda: 0.0)()
+                "grid": lambda: float(self.state[0]), "balancing": lambda: r.loss_load_cost}.get(k, lambda: 0.0)()   # grid_module.py:322-324
 
     @property
     def absorption_marginal_cost(self):
         k, r = self._s.kind, self._r
-        return {"battery": lambda: r.battery_cost_cycle, "grid": lambda: self._row()[1],
+        return {"battery": lambda: r.battery_cost_cycle, "grid": lambda: float(self.state[1]),
                 "balancing": lambda: r.overgeneration_cost}.get(k, lambda: 0.0)()
 
     marginal_cost = production_marginal_cost
@@ -709,9 +710,11 @@ class ComposedMicrogrid:
 
     def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2.,
                  reward_shaping_func=None, trajectory_func=None, device=None, obs_order="gym_sorted", _library=None):
-        if reward_shaping_func is not None or trajectory_func is not None:
-            raise NotImplementedError("reward_shaping_func / trajectory_func are built for the fused module set (one load, one "
-                                      "renewable, one battery, at most one genset and one grid)")
+        if reward_shaping_func is not None and not callable(reward_shaping_func):
+            raise TypeError("reward_shaping_func must be callable: f(energy_info, cost_info) -> float (microgrid/utils/step.py:41-46)")
+        # B = 1: the shaper is the caller's Python function of the step's info dict, evaluated on the host exactly where
+        # the reference evaluates it (every MicrogridStep.balance() and the output, microgrid.py:259, 277, 316, 325)
+        self.reward_shaping_func = reward_shaping_func
         comp = Composition(modules, add_unbalanced_module, loss_load_cost, overgeneration_cost, obs_order=obs_order)
         self.composition = comp
         self._library = _library
@@ -721,8 +724,37 @@ class ComposedMicrogrid:
             self._modules.setdefault(s.name, ModuleList()).append(ComposedModuleView(self, s, r))
         self._views = [v for lst in self._modules.values() for v in lst]        # listing order
         self._log_rows = []
-        self._log_start = comp.initial_step
         self._actions = np.zeros((1, comp.n_act))
+        self._initial_step, self._final_step = comp.initial_step, comp.final_step
+        self.trajectory_func = self._check_trajectory_func(trajectory_func)
+
+    def _check_trajectory_func(self, trajectory_func):
+        """reference: Microgrid._check_trajectory_func (microgrid.py:167-199), same errors"""
+        if trajectory_func is None:
+            return trajectory_func
+        if not callable(trajectory_func):
+            raise TypeError('trajectory_func must be callable.')
+        output = trajectory_func(self._initial_step, self._final_step)
+        try:
+            initial_step, final_step = output
+            if not (isinstance(initial_step, int) and isinstance(final_step, int)):
+                raise ValueError
+        except (TypeError, ValueError):
+            raise TypeError(f'trajectory func must return two integer values, not {output}')
+        if initial_step < self._initial_step:
+            raise ValueError(f'trajectory_func returned initial_step value ({initial_step}) less than env\'s initial '
+                             f'step: ({self._initial_step})')
+        if final_step > self._final_step:
+            raise ValueError(f'trajectory_func returned final_step value ({final_step}) greater than env\'s final step:'
+                             f' ({self._final_step})')
+        if initial_step >= final_step:
+            raise ValueError(f'trajectory_func returned values ({initial_step}, {final_step}) such that initial_step'
+                             f'was greater than or equal to final_step.')
+        return trajectory_func
+
+    def _set_window(self, initial_step, final_step):
+        """the modules' episode window (microgrid.py:221-225, 652-684): the two header words of the config record"""
+        self._batch.cfg[0, 0], self._batch.cfg[0, 1] = float(initial_step), float(final_step)
 
     # ---- state ----
     def _state(self):
@@ -730,8 +762,6 @@ class ComposedMicrogrid:
         return int(b.step_counter[0].item()), b.fstate[0].cpu().numpy(), b.istate[0].cpu().numpy()
 
     current_step = property(lambda self: int(self._batch.step_counter[0].item()))
-    initial_step = property(lambda self: self.composition.initial_step)
-    final_step = property(lambda self: self.composition.final_step)
     modules = property(lambda self: self._modules)
     fixed = property(lambda self: self._modules.fixed)
     flex = property(lambda self: self._modules.flex)
@@ -742,6 +772,24 @@ class ComposedMicrogrid:
 
     def __repr__(self):
         return "Microgrid([" + ", ".join(f"{n} x {len(lst)}" for n, lst in self._modules.items()) + "])"
+
+    @property
+    def initial_step(self):
+        return self._initial_step
+
+    @initial_step.setter
+    def initial_step(self, value):
+        self._initial_step = int(value)
+        self._set_window(self._initial_step, self._final_step)
+
+    @property
+    def final_step(self):
+        return self._final_step
+
+    @final_step.setter
+    def final_step(self, value):
+        self._final_step = int(value)
+        self._set_window(self._initial_step, self._final_step)
 
     # ---- conversions ----
     def _obs_dict(self, row, order):
@@ -791,9 +839,15 @@ class ComposedMicrogrid:
         """reference: Microgrid.run (microgrid.py:227-325).  Same arguments, return types and errors."""
         comp, b = self.composition, self._batch
         row = self._control_row(control)
-        pre = [v.state_dict() for v in self._views]
+        pre = self._pre_step()
         b.step(row if comp.n_act else None, normalized=normalized)
         return self._finish_step(pre)
+
+    def _pre_step(self):
+        """what the reference snapshots before stepping: every module's state for the log (base_module.py:152) and the cost
+        info the reward shaper gets (microgrid.py:253)"""
+        self._cost_info = self.get_cost_info() if self.reward_shaping_func is not None else None
+        return [v.state_dict() for v in self._views]
 
     def _finish_step(self, pre):
         """log row, the reference's exceptions from the event flags, and the reference's return types"""
@@ -805,15 +859,28 @@ class ComposedMicrogrid:
             t = self.current_step
             raise IndexError(f"index {t} is out of bounds for axis 0 with size {len(self)}")     # e.g. load_module.py:111
         info = b.info[0].cpu().numpy()
-        reward = float(b.reward[0].item())
-        self._log_rows.append(self._log_row(pre, info, reward))
+        reward = shaped = float(b.reward[0].item())
+        if self.reward_shaping_func is not None:
+            shaped = self._shaped_reward(info)
+        self._log_rows.append(self._log_row(pre, info, reward, shaped))
         if flags & (FLAG_GENSET_GOAL_RANGE | FLAG_NOT_A_SINK | FLAG_BATTERY_MIN_CAP | FLAG_NEGATIVE_ABSORB):
             raise AssertionError(f"step rejected (flags {flags:#x})")
         if flags & FLAG_CLIP_RAISES:
             raise ValueError("requested value outside the module's limits")                        # base_module.py:79-93
         if flags & FLAG_BALANCE:
             raise RuntimeError("Microgrid modules unable to balance energy production with consumption.\n")
-        return (self._obs_dict(b.obs[0].cpu().numpy(), comp.dispatch), reward, bool(b.done[0].item()), self._info_dict(info))
+        return (self._obs_dict(b.obs[0].cpu().numpy(), comp.dispatch), shaped, bool(b.done[0].item()), self._info_dict(info))
+
+    def _shaped_reward(self, info):
+        """MicrogridStep.shaped_reward (microgrid/utils/step.py:41-46): the caller's function of (energy info, cost info),
+        called where the reference calls it -- after the fixed modules, after the controllable ones, after the flex ones
+        (the three balance() calls of Microgrid.run) and once more for the output; the last value is the step's reward."""
+        cost_info, full = self._cost_info, self._info_dict(info)
+        value = None
+        for classes in (("fixed",), ("fixed", "controllable"), ("fixed", "controllable", "flex"), ("fixed", "controllable", "flex")):
+            names = {s.name for s in self.composition.dispatch if s.dispatch in classes}
+            value = self.reward_shaping_func(OrderedDict((k, v) for k, v in full.items() if k in names), cost_info)
+        return value
 
     def run_priority_list(self, priority_list, n_steps=1):
         """`n_steps` DiscreteMicrogridEnv-style steps with one priority list -- an index into `action_lists`, or a list of
@@ -824,7 +891,7 @@ class ComposedMicrogrid:
         out = None
         act = np.array([int(index)], dtype=np.int32)
         for _ in range(int(n_steps)):
-            pre = [v.state_dict() for v in self._views]
+            pre = self._pre_step()
             self._batch.step_discrete(act)
             out = self._finish_step(pre)
             if out[2]:
@@ -856,11 +923,13 @@ class ComposedMicrogrid:
         named = [(s.name, r) for s, r in zip(comp.slots, comp.records)]
         other = ComposedMicrogrid(named, add_unbalanced_module=False, device=self._batch.device if self._batch.device.type == "cuda" else None,
                                   obs_order=comp.obs_order, _library=self._library)
-        for a in ("step_counter", "fstate", "istate"):
+        for a in ("step_counter", "fstate", "istate", "cfg"):
             getattr(other._batch, a).copy_(getattr(self._batch, a))
+        other.reward_shaping_func, other.trajectory_func = self.reward_shaping_func, self.trajectory_func
+        other._initial_step, other._final_step = self._initial_step, self._final_step
         return other
 
-    def _log_row(self, pre, info, reward):
+    def _log_row(self, pre, info, reward, shaped=None):
         """one row of get_log(): base_module.py:276-290 per module, microgrid.py:259-260, 281, 317-319 for the balance"""
         row = OrderedDict()
         for v, state in zip(self._views, pre):
@@ -882,7 +951,7 @@ class ComposedMicrogrid:
             for k, val in state.items():
                 row[key + (k,)] = val
         bal = info[len(self._views) * MGC_INFO_SLOTS:]
-        for k, val in (("reward", reward), ("shaped_reward", reward), ("overall_provided_to_microgrid", bal[4]),
+        for k, val in (("reward", reward), ("shaped_reward", reward if shaped is None else shaped), ("overall_provided_to_microgrid", bal[4]),
                        ("overall_absorbed_from_microgrid", bal[5]), ("controllable_provided_to_microgrid", bal[2]),
                        ("controllable_absorbed_from_microgrid", bal[3]), ("fixed_provided_to_microgrid", bal[0]),
                        ("fixed_absorbed_from_microgrid", bal[1])):
@@ -891,6 +960,8 @@ class ComposedMicrogrid:
 
     def reset(self):
         """reference: Microgrid.reset (microgrid.py:205-225): modules in LISTING order, then 'balance' and 'other'"""
+        if self.trajectory_func is not None:      # microgrid.py:221-225: a new episode window per reset
+            self._set_window(*self.trajectory_func(self._initial_step, self._final_step))
         obs = self._batch.reset()[0].cpu().numpy()
         self._log_rows = []
         out = self._obs_dict(obs, self.composition.slots)
@@ -981,11 +1052,13 @@ class _ComposedEnv:
     def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2., reward_shaping_func=None,
                  trajectory_func=None, batch=None, device=None, obs_order="gym_sorted", _library=None):
         from .envs import Box
-        if reward_shaping_func is not None or trajectory_func is not None:
-            raise NotImplementedError("reward_shaping_func / trajectory_func are built for the fused module set only")
         self.single = batch is None
-        self._mg = ComposedMicrogrid(modules, add_unbalanced_module, loss_load_cost, overgeneration_cost, device=device,
-                                     obs_order=obs_order, _library=_library) if not isinstance(modules, ComposedMicrogrid) else modules
+        if not self.single and (reward_shaping_func is not None or trajectory_func is not None):
+            raise NotImplementedError("batched composed envs: reward_shaping_func / trajectory_func are Python callables and "
+                                      "run for single microgrids only (the fused module set has on-device shapers and windows)")
+        self._mg = ComposedMicrogrid(modules, add_unbalanced_module, loss_load_cost, overgeneration_cost, reward_shaping_func,
+                                     trajectory_func, device=device, obs_order=obs_order, _library=_library) \
+            if not isinstance(modules, ComposedMicrogrid) else modules
         comp = self.composition = self._mg.composition
         if self.single:
             self.batch = self._mg._batch
@@ -1009,8 +1082,8 @@ class _ComposedEnv:
     fixed = property(lambda self: self._mg.fixed)
     flex = property(lambda self: self._mg.flex)
     controllable = property(lambda self: self._mg.controllable)
-    initial_step = property(lambda self: self.composition.initial_step)
-    final_step = property(lambda self: self.composition.final_step)
+    initial_step = property(lambda self: self._mg.initial_step)
+    final_step = property(lambda self: self._mg.final_step)
     log = property(lambda self: self._mg.log)
 
     @property

@@ -220,6 +220,7 @@ def _named(modules):
         name = None
         if isinstance(m, tuple):
             name, m = m
+        m = getattr(m, "_module_record", m)       # a module view of a built microgrid (`microgrid.modules.to_tuples()`)
         if not isinstance(m, _Module):
             raise TypeError(f"Module {m!r} is not one of pymgrid_b200.modules' classes")
         out.append((name if name is not None else m._default_name, m))

@@ -14,6 +14,38 @@ BALANCE_COLS = ("reward", "shaped_reward", "overall_provided_to_microgrid", "ove
                 "fixed_provided_to_microgrid", "fixed_absorbed_from_microgrid")
 
 
+def marginal_cost_total(energy_info, cost_info):
+    """the reward shaper of the reference's TestMicrogridRewardShaping (tests/microgrid/test_microgrid.py:436-455), with the
+    module index taken from the list position: energy x marginal cost over all modules"""
+    total = 0
+    for module_name, info_list in energy_info.items():
+        for module_n, module_info in enumerate(info_list):
+            for energy_type, energy_amount in module_info.items():
+                if energy_type == 'absorbed_energy':
+                    marginal_cost = cost_info[module_name][module_n]['absorption_marginal_cost']
+                elif energy_type == 'provided_energy':
+                    marginal_cost = cost_info[module_name][module_n]['production_marginal_cost']
+                else:
+                    continue
+                total += energy_amount * marginal_cost
+    return total
+
+
+def window_trajectory(lo_offset, hi_offset):
+    """a deterministic trajectory_func (microgrid/trajectory/deterministic.py): the window [initial + lo, final + hi]"""
+    return lambda initial_step, final_step: (initial_step + lo_offset, final_step + hi_offset)
+
+
+def callable_kwargs(spec):
+    """the Python callables a case's Microgrid takes, rebuilt from their names in the JSON spec"""
+    kw = {}
+    if spec.get("shaper") == "marginal_cost_total":
+        kw["reward_shaping_func"] = marginal_cost_total
+    if spec.get("trajectory"):
+        kw["trajectory_func"] = window_trajectory(*spec["trajectory"])
+    return kw
+
+
 class ComposeCase:
     def __init__(self, data, i):
         self.i = i
@@ -41,6 +73,10 @@ class ComposeCase:
     @property
     def microgrid_kwargs(self):
         return dict(self.spec["microgrid_kwargs"])
+
+    @property
+    def callable_kwargs(self):
+        return callable_kwargs(self.spec)
 
     def control(self, k, controllable):
         """the recorded action row of step k -> {name: [action per module]}; `controllable`: [(name, [n_act per module])]"""

@@ -25,15 +25,20 @@ def host(t):
 
 
 def check_microgrid_reproduces_reference(case, order, lib):
-    mg = ComposedMicrogrid(case.modules(), obs_order=order, _library=lib, **case.microgrid_kwargs)
+    mg = ComposedMicrogrid(case.modules(), obs_order=order, _library=lib, **case.microgrid_kwargs, **case.callable_kwargs)
     assert [(s.name, s.index) for s in mg.composition.slots] == [(n, j) for n, j, _ in case.names]
     assert {k: len(v) for k, v in mg.get_empty_action().items()} == case.json("empty_action")
     reset = mg.reset()
     assert list(reset.keys()) == case.json("reset_keys")
     assert np.array_equal(listing_flat(reset, mg), case["obs_reset"])
     n = len(case["rewards"])
+    reset_at, n_resets = list(case.spec.get("reset_at", [])), 0
     for k in range(n):
+        if k in reset_at:
+            assert np.array_equal(listing_flat(mg.reset(), mg), case["reset_obs_rows"][n_resets]), k
+            n_resets += 1
         obs, reward, done, info = mg.run(case.control(k, widths(mg)), normalized=bool(case["normalized"][k]))
+        assert mg.current_step == int(case["steps_after"][k]), k
         assert list(obs.keys()) == case.json("run_keys")
         assert reward == case["rewards"][k] and done == bool(case["dones"][k]), k
         assert np.array_equal(listing_flat(obs, mg), case["obs"][k]), k
@@ -55,6 +60,12 @@ def check_microgrid_reproduces_reference(case, order, lib):
         exc = {"RuntimeError": RuntimeError, "IndexError": IndexError}[str(case["raised_type"])]
         with pytest.raises(exc):
             mg.run(ctrl)
+    assert mg.current_step == int(case["current_step"])
+    if str(case["log_raises"]):
+        # the reference's own get_log() fails under a trajectory_func (tests/golden/make_compose.py); ours indexes the rows
+        # since the last reset
+        assert len(mg.get_log()) == n - max(reset_at)
+        return
     log = mg.get_log()
     assert [list(c) for c in log.columns] == case.json("log_columns")
     assert np.array_equal(log.to_numpy(dtype=np.float64), case["log_values"], equal_nan=True)

@@ -3,8 +3,9 @@
 `Microgrid`: same set-up, same assertions, same names.  `make_suite(library)` returns the classes bound to a backend --
 the host build of the C source (CPU suite) or None = the CUDA path (GPU suite).
 
-Not restated: test_to_nonmodular (conversion to the deprecated stack is out of scope) and TestMicrogridRewardShaping (a
-Python callable as reward_shaping_func cannot run inside the kernel; the constructor refuses it, checked below).
+TestMicrogridRewardShaping (:424-455, a Python callable as reward_shaping_func) is included: for a single microgrid the
+shaper runs on the host on the step's info dict, where the reference calls it.  Not restated: test_to_nonmodular
+(conversion to the deprecated stack is out of scope).
 """
 import unittest
 
@@ -139,11 +140,6 @@ def make_suite(library):
                 with self.subTest(step=step):
                     microgrid = self.check_step(microgrid=microgrid, step_number=step)
 
-        def test_python_reward_shaper_is_refused(self):
-            with self.assertRaises(NotImplementedError):
-                Microgrid([LoadModule(time_series=self.load_ts), RenewableModule(time_series=self.pv_ts)],
-                          reward_shaping_func=lambda energy_info, cost_info: 0.0)
-
     class TestMicrogridLoadExcessPV(TestMicrogridLoadPV):
         def set_ts(self):
             load_ts = 10 * np.random.rand(100)
@@ -218,6 +214,28 @@ def make_suite(library):
             load_ts = pv_ts + 5 * np.random.rand(100)
             return load_ts, pv_ts
 
-    return [TestMicrogridLoadPV, TestMicrogridLoadExcessPV, TestMicrogridPVExcessLoad, TestMicrogridTwoLoads,
+    class TestMicrogridRewardShaping(TestMicrogridLoadPV):
+        def set_microgrid(self):
+            original_microgrid, n_loads, n_pvs = super().set_microgrid()
+            new_microgrid = Microgrid(original_microgrid.modules.to_tuples(), add_unbalanced_module=False,
+                                      reward_shaping_func=self.reward_shaping_func)
+            return new_microgrid, n_loads, n_pvs
+
+        @staticmethod
+        def reward_shaping_func(energy_info, cost_info):
+            total = 0
+            for module_name, info_list in energy_info.items():
+                for module_info in info_list:
+                    for j, (energy_type, energy_amount) in enumerate(module_info.items()):
+                        if energy_type == 'absorbed_energy':
+                            marginal_cost = cost_info[module_name][j]['absorption_marginal_cost']
+                        elif energy_type == 'provided_energy':
+                            marginal_cost = cost_info[module_name][j]['production_marginal_cost']
+                        else:
+                            continue
+                        total += energy_amount * marginal_cost
+            return total
+
+    return [TestMicrogridRewardShaping, TestMicrogridLoadPV, TestMicrogridLoadExcessPV, TestMicrogridPVExcessLoad, TestMicrogridTwoLoads,
             TestMicrogridTwoPV, TestMicrogridTwoEach, TestMicrogridManyEach, TestMicrogridManyEachExcessPV,
             TestMicrogridManyEachExcessLoad]
