@@ -90,6 +90,11 @@ typedef struct MgcLayout {
        0 otherwise); a negative module pads.  NULL / 0 when mgc_run_discrete is not used. */
     const int16_t *plist;
     int32_t n_plist, plist_width;
+    /* optional per-env episode windows (microgrid/trajectory/: trajectory_func on reset, microgrid.py:221-225):
+       [n] each, read at every step / reset, so the caller may rewrite them between calls; NULL -> the config record's
+       initial_step / final_step */
+    const int32_t *env_initial_step;
+    const int32_t *env_final_step;
 } MgcLayout;
 
 typedef struct MgcIO {

@@ -48,7 +48,8 @@ class MgcLayout(C.Structure):
                 ("n_act", _i32), ("obs_dim", _i32), ("n_fstate", _i32), ("n_istate", _i32), ("cfg_stride", _i32),
                 ("n_cfg", _i32), ("series_len", _i32), ("n_series", _i32), ("n_envs", C.c_int64),
                 ("cfg", _vp), ("series", _vp), ("series_off", _vp), ("step", _vp), ("fstate", _vp), ("istate", _vp),
-                ("cfg_index", _vp), ("plist", _vp), ("n_plist", _i32), ("plist_width", _i32)]
+                ("cfg_index", _vp), ("plist", _vp), ("n_plist", _i32), ("plist_width", _i32),
+                ("env_initial_step", _vp), ("env_final_step", _vp)]
 
 
 class MgcIO(C.Structure):
@@ -335,6 +336,9 @@ class ComposedBatch:
         self.series_off = t(np.array(offsets if offsets else [0], dtype=np.int64), torch.int64)
         self.cfg_index = t(env_config, torch.int32)
         self.step_counter = t(np.array([self.compositions[c].initial_step for c in env_config]), torch.int32)
+        # per-env episode windows (trajectory functions rewrite them; the kernel reads them at every step / reset)
+        self.env_initial_step = self.step_counter.clone()
+        self.env_final_step = t(np.array([self.compositions[c].final_step for c in env_config]), torch.int32)
         self.fstate = t(np.stack([states[c][0] for c in env_config]).reshape(n, comp.n_fstate), torch.float64)
         self.istate = t(np.stack([states[c][1] for c in env_config]).reshape(n, comp.n_istate), torch.int32)
         self.obs = torch.zeros((n, comp.obs_dim), dtype=torch.float64, device=dev)
@@ -358,8 +362,21 @@ class ComposedBatch:
             self.action_lists = comp.priority_lists(False)
             self.plist = t(comp.priority_table(self.action_lists), torch.int16)
             L.plist, L.n_plist, L.plist_width = self.plist.data_ptr(), len(self.action_lists), self.plist.shape[1]
+        L.env_initial_step, L.env_final_step = self.env_initial_step.data_ptr(), self.env_final_step.data_ptr()
         self._handle = _vp()
         self._check(self._L.mgc_create(C.byref(L), C.byref(self._handle)), "mgc_create")
+
+    def set_trajectories(self, initial_step, final_step):
+        """per-env episode windows [B] (microgrid/trajectory/*.py through `trajectory_func`, microgrid.py:221-225): `reset`
+        puts an env at its initial step, `done` is reported at its final_step - 1.  Must stay inside the configured window."""
+        ini = torch.as_tensor(np.asarray(initial_step), dtype=torch.int32, device=self.device).reshape(self.n_envs)
+        fin = torch.as_tensor(np.asarray(final_step), dtype=torch.int32, device=self.device).reshape(self.n_envs)
+        lo = torch.as_tensor(np.array([self.compositions[c].initial_step for c in self.env_config]), dtype=torch.int32, device=self.device)
+        hi = torch.as_tensor(np.array([self.compositions[c].final_step for c in self.env_config]), dtype=torch.int32, device=self.device)
+        if bool((ini < lo).any()) or bool((fin > hi).any()) or bool((ini >= fin).any()):
+            raise ValueError("trajectory windows must lie inside [initial_step, final_step] and be non-empty")     # microgrid.py:184-197
+        self.env_initial_step.copy_(ini)
+        self.env_final_step.copy_(fin)
 
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
@@ -753,8 +770,8 @@ class ComposedMicrogrid:
         return trajectory_func
 
     def _set_window(self, initial_step, final_step):
-        """the modules' episode window (microgrid.py:221-225, 652-684): the two header words of the config record"""
-        self._batch.cfg[0, 0], self._batch.cfg[0, 1] = float(initial_step), float(final_step)
+        """the modules' episode window (microgrid.py:221-225, 652-684): the env's entry of the batch's per-env window arrays"""
+        self._batch.env_initial_step[0], self._batch.env_final_step[0] = int(initial_step), int(final_step)
 
     # ---- state ----
     def _state(self):
@@ -923,7 +940,7 @@ class ComposedMicrogrid:
         named = [(s.name, r) for s, r in zip(comp.slots, comp.records)]
         other = ComposedMicrogrid(named, add_unbalanced_module=False, device=self._batch.device if self._batch.device.type == "cuda" else None,
                                   obs_order=comp.obs_order, _library=self._library)
-        for a in ("step_counter", "fstate", "istate", "cfg"):
+        for a in ("step_counter", "fstate", "istate", "env_initial_step", "env_final_step"):
             getattr(other._batch, a).copy_(getattr(self._batch, a))
         other.reward_shaping_func, other.trajectory_func = self.reward_shaping_func, self.trajectory_func
         other._initial_step, other._final_step = self._initial_step, self._final_step
@@ -1053,12 +1070,13 @@ class _ComposedEnv:
                  trajectory_func=None, batch=None, device=None, obs_order="gym_sorted", _library=None):
         from .envs import Box
         self.single = batch is None
-        if not self.single and (reward_shaping_func is not None or trajectory_func is not None):
-            raise NotImplementedError("batched composed envs: reward_shaping_func / trajectory_func are Python callables and "
-                                      "run for single microgrids only (the fused module set has on-device shapers and windows)")
+        if not self.single and reward_shaping_func is not None:
+            raise NotImplementedError("batched composed envs: a reward_shaping_func is a Python callable and runs for single "
+                                      "microgrids only (the fused module set has on-device shapers)")
         self._mg = ComposedMicrogrid(modules, add_unbalanced_module, loss_load_cost, overgeneration_cost, reward_shaping_func,
                                      trajectory_func, device=device, obs_order=obs_order, _library=_library) \
             if not isinstance(modules, ComposedMicrogrid) else modules
+        self.trajectory_func = self._mg.trajectory_func
         comp = self.composition = self._mg.composition
         if self.single:
             self.batch = self._mg._batch
@@ -1101,7 +1119,25 @@ class _ComposedEnv:
         if self.single:
             self._mg.reset()
             return self.batch.obs[0].cpu().numpy().copy()
+        if self.trajectory_func is not None:      # microgrid.py:221-225: a new episode window per reset, per env
+            self._draw_windows(mask)
         return self.batch.reset(mask)
+
+    def _draw_windows(self, mask):
+        """one (initial_step, final_step) pair per env being reset; the vectorised classes of pymgrid_b200.trajectory draw all
+        of them in one call (`n=`), a plain reference-style callable is called once per env"""
+        lo, hi, n = self._mg.initial_step, self._mg.final_step, self.n_envs
+        try:
+            initial, final = self.trajectory_func(lo, hi, n=n)
+        except TypeError:
+            pairs = [self.trajectory_func(lo, hi) for _ in range(n)]
+            initial, final = np.array([p[0] for p in pairs]), np.array([p[1] for p in pairs])
+        initial, final = np.asarray(initial, dtype=np.int32).reshape(n).copy(), np.asarray(final, dtype=np.int32).reshape(n).copy()
+        if mask is not None:                      # envs that keep running keep their window
+            keep = ~np.asarray(mask.cpu() if hasattr(mask, "cpu") else mask, dtype=bool).reshape(n)
+            initial[keep] = self.batch.env_initial_step.cpu().numpy()[keep]
+            final[keep] = self.batch.env_final_step.cpu().numpy()[keep]
+        self.batch.set_trajectories(initial, final)
 
     def _single_result(self, out):
         obs, reward, done, info = out

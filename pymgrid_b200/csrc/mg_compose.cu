@@ -41,6 +41,7 @@ struct MgcLaunch {
     const int32_t *cfg_index;
     const int16_t *plist;
     int32_t n_plist, plist_width;
+    const int32_t *env_initial, *env_final;
     // per call
     MgcIO io;
     int32_t mode, n_steps, ring, normalized;
@@ -95,13 +96,15 @@ MGC_DEV void mgc_owner(const MgcLaunch &P, int e, int s) {
             action = ctl;
             normalized = 0;
         }
-        if (!skip) mgc_env_step(V, t, fstate, istate, action, normalized, &reward, &done, info, &flags);
+        const int final_step = P.env_final ? P.env_final[e] : (int)V.cfg[1];
+        if (!skip) mgc_env_step(V, t, fstate, istate, action, normalized, final_step, &reward, &done, info, &flags);
         P.step[e] = t;
         P.io.reward[slot] = reward;
         P.io.done[slot] = done;
         if (P.io.flags) P.io.flags[e] = (s == 0 ? 0u : P.io.flags[e]) | flags;
     } else if (P.mode == MGC_MODE_RESET) {
-        if (!P.io.mask || P.io.mask[e]) P.step[e] = (int32_t)V.cfg[0];      // microgrid.py:205-225: only the step moves
+        // microgrid.py:205-225: only the step moves
+        if (!P.io.mask || P.io.mask[e]) P.step[e] = P.env_initial ? P.env_initial[e] : (int32_t)V.cfg[0];
     }
 }
 
@@ -257,6 +260,7 @@ extern "C" int mgc_create(const MgcLayout *L, MgcHandle **out) {
     B.cfg = L->cfg; B.series = L->series; B.series_off = L->series_off;
     B.step = L->step; B.fstate = L->fstate; B.istate = L->istate; B.cfg_index = L->cfg_index;
     B.plist = L->plist; B.n_plist = L->plist ? L->n_plist : 0; B.plist_width = L->plist_width;
+    B.env_initial = L->env_initial_step; B.env_final = L->env_final_step;
     h->launches = 0;
     *out = h;
     return MG_OK;

@@ -309,11 +309,11 @@ MGC_HD void mgc_module_step(const MgcView &V, int m, double a, int t, double *fs
 
 /*
  * Microgrid.run for one env.  `t` is the env's current step (advanced on success), `fstate` / `istate` its state rows,
- * `action` its action row.  Writes reward / done, ORs event bits into *flags, fills `info` (n_mod * MGC_INFO_SLOTS +
+ * `action` its action row, `final_step` the end of its episode window.  Writes reward / done, ORs event bits into *flags, fills `info` (n_mod * MGC_INFO_SLOTS +
  * MGC_BALANCE_SLOTS doubles) when not NULL.
  */
 MGC_HD void mgc_env_step(const MgcView &V, int32_t &t, double *fstate, int32_t *istate, const double *action, int normalized,
-                         double *reward_out, uint8_t *done_out, double *info, uint32_t *flags) {
+                         int final_step, double *reward_out, uint8_t *done_out, double *info, uint32_t *flags) {
     MgcStepAcc A;
     A.n_provided = A.n_absorbed = 0;
     A.reward = 0.0;
@@ -332,7 +332,6 @@ MGC_HD void mgc_env_step(const MgcView &V, int32_t &t, double *fstate, int32_t *
     if (info)
         for (int i = 0; i < n * MGC_INFO_SLOTS + MGC_BALANCE_SLOTS; ++i) info[i] = 0.0;
     /* BaseTimeSeriesMicrogridModule._done, base_timeseries_module.py:124-125, evaluated before t += 1 */
-    const int final_step = (int)V.cfg[1];
     const int ts_done = (t0 >= final_step - 1);
     int m = 0;
     /* ---- fixed modules: step(0.0, normalized=False), microgrid.py:255-257 ---- */

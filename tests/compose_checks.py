@@ -220,3 +220,44 @@ def check_quickstart_notebook(lib):
             assert value == float(json.loads(str(ref))), key
         else:
             assert json.loads(json.dumps(value)) == json.loads(str(ref)), key
+
+
+def check_batch_trajectory_windows(lib):
+    """per-env episode windows on a composed batch: reset puts every env at its own initial step, done fires at its own
+    final_step - 1 (base_timeseries_module.py:124-125), and every env equals the oracle run with that window"""
+    from pymgrid_b200.compose import ComposedContinuousEnv
+    case = next(c for c in CASES if c.label == "trajectory_window")
+    kw = {} if lib is None else {"_library": lib}
+    n, T = 9, 12
+    rng = np.random.default_rng(21)
+    windows = [(int(a), int(a + b)) for a, b in zip(rng.integers(0, 20, n), rng.integers(3, 30, n))]
+    it = iter([windows[0]] + windows)          # the constructor validates the function with one call (microgrid.py:167-199)
+    env = ComposedContinuousEnv(case.modules(), obs_order="container", batch=n, trajectory_func=lambda lo, hi: next(it), **kw,
+                                **case.microgrid_kwargs)
+    obs0 = host(env.reset()).copy()
+    assert np.array_equal(host(env.current_step), np.array([w[0] for w in windows]))
+    actions = rng.random((T, n, env.composition.n_act))
+    out = env.batch.rollout(torch.from_numpy(actions).to(env.batch.device), ring=1)
+    done = host(out["done"])
+    for e, (lo, hi) in enumerate(windows):
+        orc = ComposedOracle(case.modules(), trajectory_func=lambda a, b, w=(lo, hi): w, **case.microgrid_kwargs)
+        flat = lambda obs: np.concatenate([np.asarray(obs[m.name][m.index]).ravel() for m in orc.listing])      # noqa: E731
+        assert np.array_equal(flat(orc.reset()), obs0[e])
+        for k in range(T):
+            control = {name: [actions[k, e, s.act_col] for s in slots] for name, slots in env.composition.controllable()}
+            o, r, d, _ = orc.run(control)
+            assert r == host(out["reward"])[k, e] and d == bool(done[k, e]), (e, k)
+            assert d == (lo + k >= hi - 1)
+        assert np.array_equal(flat(o), host(out["obs_ring"][0])[e])
+    # masked reset: the envs that finished get a new window, the others keep theirs and their step
+    finished = done[-1].astype(bool)
+    new = [(1, 9)] * int(finished.sum())
+    it2 = iter(new + [(0, 5)] * n)
+    env.trajectory_func = lambda lo, hi: next(it2)
+    before = host(env.current_step).copy()
+    env.reset(mask=torch.from_numpy(finished.astype(np.uint8)).to(env.batch.device))
+    after = host(env.current_step)
+    assert np.array_equal(after[~finished], before[~finished])
+    assert np.array_equal(host(env.batch.env_final_step)[~finished], np.array([w[1] for w in windows])[~finished])
+    with pytest.raises(ValueError):
+        env.batch.set_trajectories(np.zeros(n), np.full(n, 10 ** 6))

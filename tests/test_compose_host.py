@@ -118,3 +118,7 @@ def test_env_and_controller_constructors_route_to_the_composed_path(lib):
 
 def test_quickstart_notebook_replays_value_for_value(lib):
     K.check_quickstart_notebook(lib)
+
+
+def test_batch_trajectory_windows(lib):
+    K.check_batch_trajectory_windows(lib)

@@ -68,3 +68,53 @@ def test_two_rank_aggregate_matches_single_process():
     actions = np.random.default_rng(5).random((n_steps, global_batch, 4))
     rewards, _, _ = OracleBatch([configs[c] for c in pymgrid25_env_config(global_batch)]).rollout(actions)
     np.testing.assert_allclose(per_step, rewards.sum(axis=1), rtol=1e-12)
+
+
+# ---- the composed path (any module list): same sharding, per-rank compute = the host build of its C source ------------
+def _composed_worker(rank, world, port, global_batch, n_steps, out_q):
+    import ctypes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pymgrid_b200.compose import ComposedBatch
+    from pymgrid_b200.sharding import aggregate_sum
+    from tests import hostsim
+    from tests.compose_cases import load_cases
+    case = next(c for c in load_cases() if c.label == "several_of_each")
+    configs = [case.modules(), case.modules()]
+    env_config, ids = shard_env_config(np.arange(global_batch) % 2, rank, world)
+    batch = ComposedBatch(configs, env_config, microgrid_kwargs=case.microgrid_kwargs, _library=ctypes.CDLL(hostsim.build()))
+    actions = np.random.default_rng(5).random((n_steps, global_batch, batch.comp.n_act))[:, ids]
+    out = batch.rollout(torch.from_numpy(np.ascontiguousarray(actions)), obs=False)
+    per_step = out["reward"].sum(dim=1)
+    aggregate_sum(per_step)                                      # the only collective: the logging aggregate
+    if rank == 0:
+        out_q.put((per_step.numpy(), out["reward"].numpy(), ids))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_composed_batch_matches_single_process():
+    import ctypes
+    from pymgrid_b200.compose import ComposedBatch
+    from tests import hostsim
+    from tests.compose_cases import load_cases
+    global_batch, n_steps, world = 37, 5, 2
+    hostsim.build()                                              # once, before the ranks race to build it
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_composed_worker, args=(r, world, port, global_batch, n_steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    per_step, rank0_rewards, rank0_ids = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    case = next(c for c in load_cases() if c.label == "several_of_each")
+    batch = ComposedBatch([case.modules(), case.modules()], np.arange(global_batch) % 2, microgrid_kwargs=case.microgrid_kwargs,
+                          _library=ctypes.CDLL(hostsim.build()))
+    actions = np.random.default_rng(5).random((n_steps, global_batch, batch.comp.n_act))
+    want = batch.rollout(torch.from_numpy(actions), obs=False)["reward"].numpy()
+    assert np.array_equal(rank0_rewards, want[:, rank0_ids])     # a shard computes exactly its slice of the global batch
+    np.testing.assert_allclose(per_step, want.sum(axis=1), rtol=1e-12)

@@ -92,3 +92,7 @@ def test_discrete_env_and_rule_based_control_reproduce_reference_on_gpu(case):
 
 def test_quickstart_notebook_replays_value_for_value_on_gpu():
     K.check_quickstart_notebook(None)
+
+
+def test_batch_trajectory_windows_on_gpu():
+    K.check_batch_trajectory_windows(None)
