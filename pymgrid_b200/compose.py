@@ -107,7 +107,8 @@ class Composition:
         (microgrid.py:100-165).  Returns the structure AND keeps the (name, module) records in listing order."""
         if isinstance(modules, (str, bytes)) or not hasattr(modules, "__iter__"):
             raise TypeError("modules must be list-like of modules.")
-        named = _named(list(modules))
+        import copy
+        named = [(name, copy.copy(m)) for name, m in _named(list(modules))]      # microgrid.py:165 works on copies too
         if add_unbalanced_module:       # appended un-named -> 'balancing' (microgrid.py:170-171)
             named.append(("balancing", UnbalancedEnergyModule(raise_errors=False, loss_load_cost=loss_load_cost,
                                                              overgeneration_cost=overgeneration_cost)))
@@ -879,7 +880,9 @@ class ComposedMicrogrid:
         reward = shaped = float(b.reward[0].item())
         if self.reward_shaping_func is not None:
             shaped = self._shaped_reward(info)
-        self._log_rows.append(self._log_row(pre, info, reward, shaped))
+        row = self._log_row(pre, info, reward, shaped)
+        stale = self.__dict__.pop("_stale_forecast", None)
+        self._log_rows.append(row if stale is None else views.drop_stale_forecasts(row, stale))
         if flags & (FLAG_GENSET_GOAL_RANGE | FLAG_NOT_A_SINK | FLAG_BATTERY_MIN_CAP | FLAG_NEGATIVE_ABSORB):
             raise AssertionError(f"step rejected (flags {flags:#x})")
         if flags & FLAG_CLIP_RAISES:
@@ -999,6 +1002,56 @@ class ComposedMicrogrid:
         return {name: [dict(production_marginal_cost=m.production_marginal_cost, absorption_marginal_cost=m.absorption_marginal_cost)
                        for m in lst] for name, lst in self._modules.items()}
 
+    def set_forecaster(self, forecaster, forecast_horizon=None, forecaster_increase_uncertainty=False,
+                       forecaster_relative_noise=False):
+        """reference: Microgrid.set_forecaster (microgrid.py:477-546): one setting for every time-series module.  None = no
+        forecast (horizon 0), "oracle" = perfect forecast.  The batch is rebuilt around the live state; the log is kept."""
+        from .params import DEFAULT_HORIZON
+        if forecast_horizon is None:
+            forecast_horizon = DEFAULT_HORIZON
+        comp = self.composition
+        if isinstance(forecaster, dict):
+            # the reference's dict branch (microgrid.py:520-533) calls set_forecaster on the module LIST of each name and
+            # swallows the AttributeError that raises: names are checked, nothing else happens.  Mirrored.
+            for name in forecaster:
+                if name not in self._modules:
+                    raise NameError(f'Unrecognized module {name}.')
+            return
+        chosen = {s.name: forecaster for s in comp.slots}
+        stale = {(s.name, s.index): s.horizon for s in comp.slots if s.obs_len and s.kind in ("load", "renewable", "grid")}
+        for s, r in zip(comp.slots, comp.records):
+            if s.name in chosen and hasattr(r, "time_series"):
+                f = chosen[s.name]
+                r.forecaster, r.forecast_horizon = f, forecast_horizon * (f is not None)       # base_timeseries_module.py:237
+                r.forecaster_increase_uncertainty, r.forecaster_relative_noise = forecaster_increase_uncertainty, forecaster_relative_noise
+        self._rebuild()
+        self._stale_forecast = stale       # the next step still logs the forecast computed before the change
+
+    def set_module_attr(self, attr_name, value):
+        """reference: Microgrid.set_module_attr (microgrid.py:584-612): set a constructor attribute on every module that
+        has it (e.g. 'forecast_horizon'); AttributeError when none does"""
+        hit = False
+        for r in self.composition.records:
+            if hasattr(r, attr_name):
+                setattr(r, attr_name, value)
+                hit = True
+        if not hit:
+            raise AttributeError(f"No module has attribute '{attr_name}'.")
+        self._rebuild()
+
+    def _rebuild(self):
+        """a new composition / batch from the (modified) module records, carrying over state, windows and the log"""
+        old = self._batch
+        comp = self.composition
+        named = [(s.name, r) for s, r in zip(comp.slots, comp.records)]
+        state = {a: getattr(old, a).clone() for a in ("step_counter", "fstate", "istate", "env_initial_step", "env_final_step")}
+        keep = (self._log_rows, self.reward_shaping_func, self.trajectory_func, self._initial_step, self._final_step)
+        ComposedMicrogrid.__init__(self, named, add_unbalanced_module=False, device=old.device if old.device.type == "cuda" else None,
+                                   obs_order=comp.obs_order, _library=self._library)
+        self._log_rows, self.reward_shaping_func, self.trajectory_func, self._initial_step, self._final_step = keep
+        for a, v in state.items():
+            getattr(self._batch, a).copy_(v)
+
     # ---- actions ----
     def sample_action(self, strict_bound=False, sample_flex_modules=False):
         """reference: Microgrid.sample_action (microgrid.py:337-362)"""
@@ -1022,14 +1075,7 @@ class ComposedMicrogrid:
 
     def get_log(self, as_frame=True, drop_singleton_key=False):
         """reference: Microgrid.get_log (microgrid.py:434-475): one row per step since the last reset"""
-        import pandas as pd
-        start = self.current_step - len(self._log_rows)
-        cols = list(self._log_rows[0].keys()) if self._log_rows else []
-        df = pd.DataFrame([list(r.values()) for r in self._log_rows], columns=pd.MultiIndex.from_tuples(
-            cols, names=["module_name", "module_number", "field"]) if cols else None,
-            index=pd.RangeIndex(start=start, stop=self.current_step))
-        if drop_singleton_key and cols:
-            df.columns = df.columns.remove_unused_levels()
+        df = views.log_frame(self._log_rows, self.current_step, drop_singleton_key)
         return df if as_frame else df.to_dict()
 
     log = property(lambda self: self.get_log())

@@ -482,8 +482,10 @@ class Microgrid:
         obs_row, info_row = obs[0].cpu().numpy(), info[0].cpu().numpy()
         r = float(reward[0].item())
         post = self._state()
-        self._log_rows.append(self._named(views.log_row(p, views.state_dict(p, pre["t"], pre["charge"], pre["genset"], pre["soc"]),
-                                                        info_row, r, post["genset"])))
+        row = self._named(views.log_row(p, views.state_dict(p, pre["t"], pre["charge"], pre["genset"], pre["soc"]),
+                                        info_row, r, post["genset"]))
+        stale = self.__dict__.pop("_stale_forecast", None)
+        self._log_rows.append(row if stale is None else views.drop_stale_forecasts(row, stale))
         return (self._named(views.obs_row_to_dict(obs_row, p, self._obs_order)), r, bool(done[0].item()),
                 self._named(views.info_row_to_dict(info_row, flags, p)))
 
@@ -595,6 +597,72 @@ class Microgrid:
         return {name: [dict(production_marginal_cost=m.production_marginal_cost, absorption_marginal_cost=m.absorption_marginal_cost)
                        for m in lst] for name, lst in self._modules.items()}
 
+    def set_forecaster(self, forecaster, forecast_horizon=None, forecaster_increase_uncertainty=False,
+                       forecaster_relative_noise=False):
+        """reference: Microgrid.set_forecaster (microgrid.py:477-546): None (no forecast, horizon 0), "oracle", or a noise
+        standard deviation, for every time-series module (BASELINE config 4 is `set_forecaster('oracle',
+        forecast_horizon=24)`).  The engine is rebuilt around the live state; the log is kept."""
+        import dataclasses
+        from .params import DEFAULT_HORIZON, ForecasterParams
+        if forecast_horizon is None:
+            forecast_horizon = DEFAULT_HORIZON
+        ts_names = {"load": "load", self._ren: "pv"}
+        if self.params.has_grid:
+            ts_names["grid"] = "grid"
+        if isinstance(forecaster, dict):
+            # the reference's dict branch (microgrid.py:520-533) calls set_forecaster on the module LIST of each name and
+            # swallows the AttributeError that raises: names are checked, nothing else happens.  Mirrored.
+            for name in forecaster:
+                if name not in self._modules:
+                    raise NameError(f'Unrecognized module {name}.')
+            return
+        settings = {key: forecaster for key in ts_names.values()}
+        horizons = {forecast_horizon * (f is not None) for f in settings.values()}       # base_timeseries_module.py:237
+        if len(horizons) != 1:
+            raise NotImplementedError("one forecast horizon for all time-series modules on the fused path")
+        noise = {}
+        for key, f in settings.items():
+            if f is None or (isinstance(f, str) and f == "oracle"):
+                continue
+            if isinstance(f, (int, float, np.integer, np.floating)) and not isinstance(f, bool):
+                if f < 0:
+                    raise ValueError("noise_std must be non-negative")
+                if f != 0:
+                    noise[key] = ForecasterParams(float(f), bool(forecaster_increase_uncertainty), bool(forecaster_relative_noise))
+                continue
+            raise NotImplementedError(f"forecaster={f!r}: only None, 'oracle' and a noise standard deviation are built in "
+                                      f"(user-defined forecasters are Python callables)")
+        old_horizon = self.params.forecast_horizon
+        params = dataclasses.replace(self.export_params(), forecast_horizon=int(horizons.pop()), forecasters=noise)
+        keep = (self._log_rows, self.trajectory_func, self.raise_errors, self._soc0, self._initial_step, self._final_step)
+        Microgrid.__init__(self, params, device=self._engine.device, obs_order=self._obs_order)
+        self._log_rows, self.trajectory_func, self.raise_errors, self._soc0, self._initial_step, self._final_step = keep
+        # the next step still logs the forecast computed before the change (views.drop_stale_forecasts)
+        self._stale_forecast = {(name, 0): old_horizon for name in ts_names}
+
+    def set_module_attr(self, attr_name, value):
+        """reference: Microgrid.set_module_attr (microgrid.py:584-612): set a constructor attribute on every module that
+        has it -- 'forecast_horizon' on the time-series modules, a parameter of the battery / genset / grid records
+        (`max_capacity`, `genset_cost`, `max_import` ...); AttributeError when no module has it.  The engine is rebuilt
+        around the live state; the log is kept."""
+        import dataclasses
+        params = self.export_params()
+        hit = False
+        if attr_name == "forecast_horizon":
+            params, hit = dataclasses.replace(params, forecast_horizon=int(value)), True
+        for part in ("battery", "genset", "grid"):
+            rec = getattr(params, part)
+            if rec is not None and attr_name in {f.name for f in dataclasses.fields(rec)} and attr_name != "time_series":
+                setattr(rec, attr_name, value)
+                hit = True
+        if attr_name in ("loss_load_cost", "overgeneration_cost"):
+            params, hit = dataclasses.replace(params, **{attr_name: value}), True
+        if not hit:
+            raise AttributeError(f"No module has attribute '{attr_name}'.")
+        keep = (self._log_rows, self.trajectory_func, self.raise_errors, self._soc0, self._initial_step, self._final_step)
+        Microgrid.__init__(self, params, device=self._engine.device, obs_order=self._obs_order)
+        self._log_rows, self.trajectory_func, self.raise_errors, self._soc0, self._initial_step, self._final_step = keep
+
     def get_forecast_horizon(self):
         """reference: Microgrid.get_forecast_horizon (microgrid.py:364-388)"""
         return self.params.forecast_horizon
@@ -624,14 +692,7 @@ class Microgrid:
 
     def get_log(self, as_frame=True, drop_singleton_key=False):
         """reference: Microgrid.get_log (microgrid.py:434-475): one row per step since the last reset."""
-        import pandas as pd
-        start = self.current_step - len(self._log_rows)
-        cols = list(self._log_rows[0].keys()) if self._log_rows else []
-        df = pd.DataFrame([list(r.values()) for r in self._log_rows], columns=pd.MultiIndex.from_tuples(
-            cols, names=["module_name", "module_number", "field"]) if cols else None,
-            index=pd.RangeIndex(start=start, stop=self.current_step))
-        if drop_singleton_key and cols:
-            df.columns = df.columns.remove_unused_levels()
+        df = views.log_frame(self._log_rows, self.current_step, drop_singleton_key)
         return df if as_frame else df.to_dict()
 
     @property

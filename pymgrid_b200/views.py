@@ -199,3 +199,36 @@ def log_row(p, pre_state, info, reward, genset_after=None):
     row[("balance", 0, "fixed_provided_to_microgrid")] = 0.0
     row[("balance", 0, "fixed_absorbed_from_microgrid")] = fixed_absorbed
     return row
+
+
+def log_frame(rows, stop, drop_singleton_key=False):
+    """`Microgrid.get_log()` (microgrid.py:434-475) from per-step row dicts {(module, number, field): value}.  Columns keep
+    the reference's order: modules in the order of the first row, each module's fields in first-logged order -- a field
+    that appears later (a longer forecast after set_forecaster) is appended to ITS module's block and is NaN before
+    (ModularLogger.log, utils/logger.py:18-28).  A field that stops being logged is NaN afterwards (the reference's
+    get_log() raises a length mismatch in that situation)."""
+    import pandas as pd
+    blocks = OrderedDict()
+    for r in rows:
+        for col in r:
+            blocks.setdefault(col[:2], OrderedDict()).setdefault(col, None)
+    cols = [c for b in blocks.values() for c in b]
+    uniform = all(len(r) == len(cols) for r in rows)
+    data = [list(r.values()) if uniform else [r.get(c, np.nan) for c in cols] for r in rows]
+    df = pd.DataFrame(data, columns=pd.MultiIndex.from_tuples(cols, names=["module_name", "module_number", "field"]) if cols else None,
+                      index=pd.RangeIndex(start=stop - len(rows), stop=stop))
+    if drop_singleton_key and cols:
+        df.columns = df.columns.remove_unused_levels()
+    return df
+
+
+def drop_stale_forecasts(row, stale):
+    """The first step after `set_forecaster` logs the forecast the module computed BEFORE the change: the reference's
+    `_state_dict` zips the new keys with the stale `_current_forecast` (base_timeseries_module.py:332-338, :99-101), so
+    that row carries only the first min(old, new) forecast rows.  `stale`: {(module, number): old horizon}."""
+    def keep(col):
+        old = stale.get(col[:2])
+        if old is None or "_forecast_" not in col[2]:
+            return True
+        return int(col[2].rsplit("_", 1)[1]) < old
+    return OrderedDict((c, v) for c, v in row.items() if keep(c))

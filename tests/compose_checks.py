@@ -261,3 +261,24 @@ def check_batch_trajectory_windows(lib):
     assert np.array_equal(host(env.batch.env_final_step)[~finished], np.array([w[1] for w in windows])[~finished])
     with pytest.raises(ValueError):
         env.batch.set_trajectories(np.zeros(n), np.full(n, 10 ** 6))
+
+
+def check_set_forecaster(lib, golden_dir=None):
+    """Microgrid.set_forecaster on the quick-start notebook's two-battery grid (tests/golden/make_set_forecaster.py)"""
+    import os
+    import pymgrid_b200
+    from pymgrid_b200 import modules as M
+    from tests.test_gpu_dropin import _set_forecaster_flow
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "set_forecaster.npz"))
+    rng = np.random.default_rng(0)
+    load, pv = 100 + 100 * rng.random(200), 200 * rng.random(200)
+    mods = [M.BatteryModule(10, 100, 50, 50, 0.9, init_soc=0.2), M.BatteryModule(10, 1000, 10, 10, 0.7, init_soc=0.2),
+            ("pv", M.RenewableModule(time_series=pv)), M.LoadModule(time_series=load),
+            M.GridModule(100, 100, [0.2, 0.1, 0.5] * np.ones((200, 3)))]
+    kw = {} if lib is None else {"_library": lib}
+    mg = pymgrid_b200.Microgrid(mods, **kw)
+    _set_forecaster_flow(mg, z, "quick", ["load"])
+    with pytest.raises(AttributeError):
+        mg.set_module_attr("blah", "blah")                  # tests/microgrid/test_microgrid.py:144-147
+    mg.set_module_attr("forecast_horizon", 50)              # :135-142
+    assert {m.forecast_horizon for m in mg.modules.iterlist() if hasattr(m, "forecast_horizon")} == {50}

@@ -122,3 +122,7 @@ def test_quickstart_notebook_replays_value_for_value(lib):
 
 def test_batch_trajectory_windows(lib):
     K.check_batch_trajectory_windows(lib)
+
+
+def test_set_forecaster_and_set_module_attr(lib):
+    K.check_set_forecaster(lib)

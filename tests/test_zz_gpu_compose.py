@@ -96,3 +96,7 @@ def test_quickstart_notebook_replays_value_for_value_on_gpu():
 
 def test_batch_trajectory_windows_on_gpu():
     K.check_batch_trajectory_windows(None)
+
+
+def test_set_forecaster_and_set_module_attr_on_gpu():
+    K.check_set_forecaster(None)
