@@ -268,7 +268,6 @@ def check_set_forecaster(lib, golden_dir=None):
     import os
     import pymgrid_b200
     from pymgrid_b200 import modules as M
-    from tests.test_gpu_dropin import _set_forecaster_flow
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "set_forecaster.npz"))
     rng = np.random.default_rng(0)
     load, pv = 100 + 100 * rng.random(200), 200 * rng.random(200)
@@ -282,3 +281,39 @@ def check_set_forecaster(lib, golden_dir=None):
         mg.set_module_attr("blah", "blah")                  # tests/microgrid/test_microgrid.py:144-147
     mg.set_module_attr("forecast_horizon", 50)              # :135-142
     assert {m.forecast_horizon for m in mg.modules.iterlist() if hasattr(m, "forecast_horizon")} == {50}
+
+PHASES = (("keep", 4), ("oracle24", 4), ("dict", 2), ("none", 3))
+
+
+def _set_forecaster_flow(m, z, prefix, names):
+    """the recorded flow of tests/golden/make_set_forecaster.py against microgrid `m`"""
+    import json
+    for phase, n in PHASES:
+        if phase == "oracle24":
+            m.set_forecaster("oracle", forecast_horizon=24)             # BASELINE config 4's call
+        elif phase == "dict":
+            m.set_forecaster({names[0]: None}, forecast_horizon=7)      # a silent no-op in the reference, mirrored
+            with pytest.raises(NameError):
+                m.set_forecaster({"no_such_module": None})
+        elif phase == "none":
+            m.set_forecaster(None)
+        for k in range(n):
+            flat, col, control = z[f"{prefix}_{phase}_actions"][k], 0, {}
+            for name, mods in m.controllable.items():
+                vals = []
+                for _ in mods:
+                    w = 2 if name == "genset" else 1
+                    vals.append(np.array(flat[col:col + w]) if w == 2 else float(flat[col]))
+                    col += w
+                control[name] = vals
+            obs, reward, done, info = m.run(control)
+            assert reward == z[f"{prefix}_{phase}_rewards"][k], (phase, k)
+            row = np.concatenate([np.asarray(x).ravel() for name in sorted(obs) for x in obs[name]])
+            np.testing.assert_array_equal(row, z[f"{prefix}_{phase}_obs"][k])
+        if phase == "dict":
+            log = m.get_log()
+            assert [list(c) for c in log.columns] == json.loads(str(z[f"{prefix}_log_columns"]))
+            assert np.array_equal(log.to_numpy(dtype=np.float64), z[f"{prefix}_log_values"], equal_nan=True)
+    # a shorter horizon: the reference's own get_log() raises a length mismatch here; ours keeps every column, NaN-padded
+    assert str(z[f"{prefix}_final_log_raises"]) == "ValueError"
+    assert len(m.get_log()) == sum(n for _, n in PHASES)

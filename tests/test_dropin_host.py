@@ -30,5 +30,8 @@ test_rule_based_control_class = G.test_rule_based_control_class
 test_rule_based_control_runs_until_done = G.test_rule_based_control_runs_until_done
 test_reward_shaping_func_drop_in = G.test_reward_shaping_func_drop_in
 test_module_views_on_the_engine = G.test_module_views_on_the_engine
-test_set_forecaster_matches_reference = G.test_set_forecaster_matches_reference
-test_set_module_attr_like_the_reference_tests = G.test_set_module_attr_like_the_reference_tests
+
+import tests.test_zz_gpu_dropin_more as G2  # noqa: E402
+
+test_set_forecaster_matches_reference = G2.test_set_forecaster_matches_reference
+test_set_module_attr_like_the_reference_tests = G2.test_set_module_attr_like_the_reference_tests

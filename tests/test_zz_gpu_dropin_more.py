@@ -1,0 +1,39 @@
+"""More drop-in surface checks on the GPU for the fused module set (Microgrid.set_forecaster, set_module_attr, get_cost_info,
+module attribute access), written after round 1's GPU budget was spent: the file name sorts after the suites that have
+already run on a B200, so that a surprise here cannot hide them behind `pytest -x`.  tests/test_dropin_host.py runs the
+same functions on the CPU against the oracle-backed engine stand-in."""
+import numpy as np
+import pytest
+
+from tests.compose_checks import _set_forecaster_flow
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", (0, 1, 2))
+def test_set_forecaster_matches_reference(golden, n):
+    """Microgrid.set_forecaster (microgrid.py:477-546) on the fused module set: longer horizon, no-op dict, no forecast"""
+    from pymgrid_b200.microgrid import Microgrid
+    m = Microgrid.from_scenario(n)
+    _set_forecaster_flow(m, golden["set_forecaster"], f"s{n}", ["load"])
+    assert m.get_forecast_horizon() == 0
+
+
+def test_set_module_attr_like_the_reference_tests():
+    """tests/microgrid/test_microgrid.py:135-147 (set_module_attr) and :149-166 (get_cost_info), on the fused module set"""
+    from pymgrid_b200.microgrid import Microgrid
+    m = Microgrid.from_scenario(1)
+    m.run(m.sample_action())
+    charge = m.modules.battery[0].current_charge
+    m.set_module_attr("forecast_horizon", 50)
+    fh = [mod.forecast_horizon for mod in m.modules.iterlist() if hasattr(mod, "forecast_horizon")]
+    assert min(fh) == max(fh) == 50 and m.get_forecast_horizon() == 50
+    assert m.current_step == 1 and m.modules.battery[0].current_charge == charge and len(m.get_log()) == 1
+    with pytest.raises(AttributeError):
+        m.set_module_attr("blah", "blah")
+    m.set_module_attr("genset_cost", 0.9)
+    assert m.modules.genset[0].genset_cost == 0.9
+    cost_info = m.get_cost_info()
+    for name in ("genset", "battery", "pv", "load", "grid", "unbalanced_energy"):
+        assert len(cost_info[name]) == 1 and set(cost_info[name][0]) == {"production_marginal_cost", "absorption_marginal_cost"}
+    assert hasattr(m, "load") and hasattr(m, "pv") and hasattr(m, "battery") and m.grid is m.modules["grid"]
