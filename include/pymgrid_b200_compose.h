@@ -80,6 +80,11 @@ typedef struct MgcLayout {
     const double *series;            /* pool; series i starts at series_off[i], row-major [T][C], C = 4 (grid) or 1;
                                         load series are stored NEGATIVE like the reference (base_timeseries_module.py:68-79) */
     const int64_t *series_off;       /* [n_series] element offsets into `series`                                        */
+    const double *series_nrm;        /* the same pool NORMALISED per column, (ts - low) / spread with the bounds of the module
+                                        kind that owns the series (base_timeseries_module.py:81-88, grid_module.py:125-132,
+                                        utils/space.py:207-218), computed once by the host in f64: observation rows are then
+                                        pure gathers (series values lie inside their own bounds, so the forecaster's clip,
+                                        forecast/forecaster.py:139-149, never moves them).  NULL -> normalise on the fly. */
     /* per-env state, read AND written */
     int32_t *step;                   /* [n] _current_step (all modules of a microgrid share it)                         */
     double *fstate;                  /* [n][n_fstate]                                                                   */

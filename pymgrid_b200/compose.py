@@ -47,7 +47,7 @@ class MgcLayout(C.Structure):
     _fields_ = [("abi_version", _i32), ("n_modules", _i32), ("modules", MgcModule * MGC_MAX_MODULES),
                 ("n_act", _i32), ("obs_dim", _i32), ("n_fstate", _i32), ("n_istate", _i32), ("cfg_stride", _i32),
                 ("n_cfg", _i32), ("series_len", _i32), ("n_series", _i32), ("n_envs", C.c_int64),
-                ("cfg", _vp), ("series", _vp), ("series_off", _vp), ("step", _vp), ("fstate", _vp), ("istate", _vp),
+                ("cfg", _vp), ("series", _vp), ("series_off", _vp), ("series_nrm", _vp), ("step", _vp), ("fstate", _vp), ("istate", _vp),
                 ("cfg_index", _vp), ("plist", _vp), ("n_plist", _i32), ("plist_width", _i32),
                 ("env_initial_step", _vp), ("env_final_step", _vp)]
 
@@ -245,17 +245,17 @@ class Composition:
     # ---- packing ----
     def config_record(self, series_index):
         """the f64 parameter record of this microgrid (include/pymgrid_b200_compose.h: enum MGC_* lists the blocks).
-        `series_index(array) -> int` registers a series in the pool."""
+        `series_index(array, pull_zero) -> int` registers a series in the pool."""
         rec = np.zeros(self.cfg_stride)
         rec[0], rec[1] = self.initial_step, self.final_step
         for s, m in zip(self.slots, self.records):
             o = s.param_off
             if s.kind in ("load", "renewable"):     # bounds: base_timeseries_module.py:81-88
                 lo, hi = views.series_bounds(m.time_series[:, 0], True)
-                rec[o:o + 3] = series_index(m.time_series), lo, hi
+                rec[o:o + 3] = series_index(m.time_series, True), lo, hi
             elif s.kind == "grid":                  # per-column bounds: grid_module.py:125-132
                 ts = m.time_series
-                rec[o:o + 4] = series_index(ts), m.max_import, m.max_export, m.cost_per_unit_co2
+                rec[o:o + 4] = series_index(ts, False), m.max_import, m.max_export, m.cost_per_unit_co2
                 rec[o + 4:o + 8], rec[o + 8:o + 12] = ts.min(axis=0), ts.max(axis=0)
             elif s.kind == "battery":
                 rec[o:o + 6] = (m.min_capacity, m.max_capacity, m.max_charge, m.max_discharge, m.efficiency, m.battery_cost_cycle)
@@ -288,7 +288,7 @@ class Composition:
 # ---- the batch ----------------------------------------------------------------------------------------------------------
 class ComposedBatch:
     def __init__(self, microgrids, env_config=None, device=None, obs_order="gym_sorted", with_info=False,
-                 microgrid_kwargs=None, _library=None):
+                 microgrid_kwargs=None, prenormalised=True, _library=None):
         """`microgrids`: list of module lists (one per parameter set; all with the same composition) or ready
         `Composition`s; `env_config[e]`: which one env e is (default: one env per entry)."""
         kw = dict(microgrid_kwargs or {})
@@ -316,16 +316,27 @@ class ComposedBatch:
         self.env_config = env_config
         self.n_envs = n = len(env_config)
         # series pool, deduplicated by content
-        pool, offsets, seen, total = [], [], {}, 0
+        pool, pool_nrm, offsets, seen, total = [], [], [], {}, 0
 
-        def series_index(ts):
+        def series_index(ts, pull_zero):
+            """registers a series (deduplicated by content and bounds rule) and its normalised twin: (ts - low) / spread per
+            column with the owning module kind's bounds, spread 0 -> 1 (utils/space.py:204-218) -- the same f64 operations
+            the reference applies per step, done once"""
             nonlocal total
             arr = np.ascontiguousarray(ts, dtype=np.float64)
-            key = (arr.shape, arr.tobytes())
+            key = (arr.shape, bool(pull_zero), arr.tobytes())
             if key not in seen:
                 seen[key] = len(offsets)
                 offsets.append(total)
                 pool.append(arr.reshape(-1))
+                if pull_zero:
+                    lo, hi = views.series_bounds(arr[:, 0], True)
+                    lo, hi = np.array([lo]), np.array([hi])
+                else:
+                    lo, hi = arr.min(axis=0), arr.max(axis=0)
+                spread = hi - lo
+                spread = np.where(spread == 0, 1.0, spread)
+                pool_nrm.append(((arr - lo) / spread).reshape(-1))
                 total += arr.size
             return seen[key]
         cfg = np.stack([c.config_record(series_index) for c in self.compositions])
@@ -334,6 +345,7 @@ class ComposedBatch:
         t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dtype=dt).to(dev)      # noqa: E731
         self.cfg = t(cfg, torch.float64)
         self.series = t(np.concatenate(pool) if pool else np.zeros(1), torch.float64)
+        self.series_nrm = t(np.concatenate(pool_nrm) if pool_nrm else np.zeros(1), torch.float64)
         self.series_off = t(np.array(offsets if offsets else [0], dtype=np.int64), torch.int64)
         self.cfg_index = t(env_config, torch.int32)
         self.step_counter = t(np.array([self.compositions[c].initial_step for c in env_config]), torch.int32)
@@ -353,6 +365,7 @@ class ComposedBatch:
         L.n_act, L.obs_dim, L.n_fstate, L.n_istate = comp.n_act, comp.obs_dim, comp.n_fstate, comp.n_istate
         L.cfg_stride, L.n_cfg, L.series_len, L.n_series, L.n_envs = comp.cfg_stride, len(cfg), comp.series_len, len(offsets), n
         L.cfg, L.series, L.series_off = self.cfg.data_ptr(), self.series.data_ptr(), self.series_off.data_ptr()
+        L.series_nrm = self.series_nrm.data_ptr() if prenormalised else None      # None: the kernel normalises every element itself
         L.step, L.cfg_index = self.step_counter.data_ptr(), self.cfg_index.data_ptr()
         L.fstate = self.fstate.data_ptr() if comp.n_fstate else None
         L.istate = self.istate.data_ptr() if comp.n_istate else None

@@ -35,6 +35,7 @@ struct MgcLaunch {
     const double *cfg;
     const double *series;
     const int64_t *series_off;
+    const double *series_nrm;
     int32_t *step;
     double *fstate;
     int32_t *istate;
@@ -62,6 +63,7 @@ MGC_DEV MgcView mgc_view(const MgcLaunch &P, int e) {
     V.cfg = P.cfg + (int64_t)P.cfg_index[e] * P.cfg_stride;
     V.series = P.series;
     V.series_off = P.series_off;
+    V.series_nrm = P.series_nrm;
     V.T = P.T;
     return V;
 }
@@ -257,7 +259,7 @@ extern "C" int mgc_create(const MgcLayout *L, MgcHandle **out) {
     memcpy(B.mod, L->modules, sizeof(MgcModule) * (size_t)L->n_modules);
     B.n_mod = L->n_modules; B.n_act = L->n_act; B.obs_dim = L->obs_dim; B.n_fstate = L->n_fstate; B.n_istate = L->n_istate;
     B.cfg_stride = L->cfg_stride; B.T = L->series_len; B.n_envs = (int32_t)L->n_envs;
-    B.cfg = L->cfg; B.series = L->series; B.series_off = L->series_off;
+    B.cfg = L->cfg; B.series = L->series; B.series_off = L->series_off; B.series_nrm = L->series_nrm;
     B.step = L->step; B.fstate = L->fstate; B.istate = L->istate; B.cfg_index = L->cfg_index;
     B.plist = L->plist; B.n_plist = L->plist ? L->n_plist : 0; B.plist_width = L->plist_width;
     B.env_initial = L->env_initial_step; B.env_final = L->env_final_step;

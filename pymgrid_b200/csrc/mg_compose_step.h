@@ -32,6 +32,7 @@ struct MgcView {
     const double *cfg;            /* this env's config record */
     const double *series;
     const int64_t *series_off;
+    const double *series_nrm;     /* may be NULL */
     int32_t T;
 };
 
@@ -118,6 +119,7 @@ MGC_HD double mgc_obs_element(const MgcView &V, int m, int k, int t, const doubl
         const int idx = t + row;
         double v;
         if (idx < V.T && t < V.T) {
+            if (V.series_nrm) return V.series_nrm[V.series_off[(int)p[0]] + (int64_t)idx * C + c];     /* pre-normalised gather */
             v = mgc_series_of(V, p)[(int64_t)idx * C + c];
             if (row > 0) {
                 if (v < low) v = low;

@@ -128,6 +128,13 @@ def check_batch_matches_oracle_and_rollout_matches_steps(label, lib, n_envs=131,
         assert np.array_equal(r.cpu().numpy(), want_r[k])
     assert np.array_equal(obs.cpu().numpy(), want_obs)
     assert np.array_equal(batch2.fstate.cpu().numpy(), batch.fstate.cpu().numpy()) and np.array_equal(batch2.istate.cpu().numpy(), batch.istate.cpu().numpy())
+    # the same rows when the kernel normalises the series itself instead of gathering from the pre-normalised pool
+    batch3 = ComposedBatch([c for c in batch.compositions], batch.env_config, obs_order="container", prenormalised=False,
+                           **({} if lib is None else {"_library": lib}))
+    for a in ("fstate", "istate"):
+        getattr(batch3, a).copy_(getattr(_batch_case(lib, label, n_envs, 7)[1], a))
+    out3 = batch3.rollout(torch.from_numpy(actions).to(batch3.device), ring=2)
+    assert np.array_equal(out3["reward"].cpu().numpy(), want_r) and np.array_equal(out3["obs_ring"][(T - 1) % 2].cpu().numpy(), want_obs)
     # masked reset: only the step counter of the masked envs moves (microgrid.py:205-225)
     mask = (np.arange(n_envs) % 3 == 0).astype(np.uint8)
     before = batch.fstate.clone()
