@@ -120,7 +120,10 @@ int mgc_abi_version(void);
 int64_t mgc_sizeof(int which);     /* 0 MgcModule, 1 MgcLayout, 2 MgcIO */
 int32_t mgc_param_count(int kind); /* doubles a module of this kind takes in a config record */
 
-/* mgc_create -- replaces Microgrid.__init__ for a batch (microgrid.py:100-165): validates the composition. */
+/* mgc_create -- replaces Microgrid.__init__ for a batch (microgrid.py:100-165): validates the composition (dispatch order,
+ * blocks inside their rows and not overlapping, listing a permutation) and uploads one small table to the CURRENT device
+ * (obs_dim int32: observation element -> module, offset) -- the only device memory a handle owns, released by mgc_destroy.
+ * Every other array stays owned by the caller. */
 int mgc_create(const MgcLayout *layout, MgcHandle **out);
 int mgc_destroy(MgcHandle *h);
 

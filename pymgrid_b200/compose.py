@@ -378,7 +378,8 @@ class ComposedBatch:
             L.plist, L.n_plist, L.plist_width = self.plist.data_ptr(), len(self.action_lists), self.plist.shape[1]
         L.env_initial_step, L.env_final_step = self.env_initial_step.data_ptr(), self.env_final_step.data_ptr()
         self._handle = _vp()
-        self._check(self._L.mgc_create(C.byref(L), C.byref(self._handle)), "mgc_create")
+        with self._on_device():         # mgc_create uploads its element table to the CURRENT device
+            self._check(self._L.mgc_create(C.byref(L), C.byref(self._handle)), "mgc_create")
 
     def set_trajectories(self, initial_step, final_step):
         """per-env episode windows [B] (microgrid/trajectory/*.py through `trajectory_func`, microgrid.py:221-225): `reset`
@@ -404,6 +405,10 @@ class ComposedBatch:
         if code != 0:
             raise _cabi.EngineError(f"{what} failed ({code}): {self._L.mg_last_error().decode()}")
 
+    def _on_device(self):
+        import contextlib
+        return torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()
+
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
 
@@ -427,7 +432,8 @@ class ComposedBatch:
         a = self._actions(actions, ())
         io = MgcIO(a.data_ptr() if a is not None else None, self.obs.data_ptr() if obs else None, self.reward.data_ptr(),
                    self.done.data_ptr(), self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None)
-        self._check(self._L.mgc_run(self._handle, C.byref(io), 1, 1, int(bool(normalized)), self._stream()), "mgc_run")
+        with self._on_device():
+            self._check(self._L.mgc_run(self._handle, C.byref(io), 1, 1, int(bool(normalized)), self._stream()), "mgc_run")
         return (self.obs if obs else None), self.reward, self.done, self.info
 
     def _dactions(self, actions, lead):
@@ -445,7 +451,8 @@ class ComposedBatch:
         a = self._dactions(actions, ())
         io = MgcIO(None, self.obs.data_ptr() if obs else None, self.reward.data_ptr(), self.done.data_ptr(),
                    self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None, a.data_ptr(), 0)
-        self._check(self._L.mgc_run_discrete(self._handle, C.byref(io), 1, 1, self._stream()), "mgc_run_discrete")
+        with self._on_device():
+            self._check(self._L.mgc_run_discrete(self._handle, C.byref(io), 1, 1, self._stream()), "mgc_run_discrete")
         return (self.obs if obs else None), self.reward, self.done, self.info
 
     def rollout_discrete(self, actions, n_steps=None, ring=1, obs=True):
@@ -459,7 +466,8 @@ class ComposedBatch:
         ring_buf = torch.zeros((ring, self.n_envs, self.comp.obs_dim), dtype=torch.float64, device=self.device) if obs else None
         io = MgcIO(None, ring_buf.data_ptr() if obs else None, reward.data_ptr(), done.data_ptr(),
                    self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None, a.data_ptr(), int(const))
-        self._check(self._L.mgc_run_discrete(self._handle, C.byref(io), T, int(ring), self._stream()), "mgc_run_discrete")
+        with self._on_device():
+            self._check(self._L.mgc_run_discrete(self._handle, C.byref(io), T, int(ring), self._stream()), "mgc_run_discrete")
         return dict(reward=reward, done=done, obs_ring=ring_buf, flags=self.flags)
 
     def rollout(self, actions=None, n_steps=None, normalized=True, ring=1, obs=True, out=None):
@@ -483,19 +491,22 @@ class ComposedBatch:
             ring_buf = torch.zeros((ring, self.n_envs, comp.obs_dim), dtype=torch.float64, device=self.device) if obs else None
         io = MgcIO(a.data_ptr() if a is not None else None, ring_buf.data_ptr() if obs else None, reward.data_ptr(),
                    done.data_ptr(), self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None)
-        self._check(self._L.mgc_run(self._handle, C.byref(io), T, int(ring), int(bool(normalized)), self._stream()), "mgc_run")
+        with self._on_device():
+            self._check(self._L.mgc_run(self._handle, C.byref(io), T, int(ring), int(bool(normalized)), self._stream()), "mgc_run")
         return dict(reward=reward, done=done, obs_ring=ring_buf, flags=self.flags)
 
     def reset(self, mask=None):
         """Microgrid.reset (microgrid.py:205-225) for the masked envs (default all); returns every env's observation"""
         m = None if mask is None else torch.as_tensor(mask, dtype=torch.uint8, device=self.device).contiguous()
         io = MgcIO(None, self.obs.data_ptr(), None, None, None, None, m.data_ptr() if m is not None else None)
-        self._check(self._L.mgc_reset(self._handle, C.byref(io), self._stream()), "mgc_reset")
+        with self._on_device():
+            self._check(self._L.mgc_reset(self._handle, C.byref(io), self._stream()), "mgc_reset")
         return self.obs
 
     def observe(self):
         io = MgcIO(None, self.obs.data_ptr(), None, None, None, None, None)
-        self._check(self._L.mgc_observe(self._handle, C.byref(io), self._stream()), "mgc_observe")
+        with self._on_device():
+            self._check(self._L.mgc_observe(self._handle, C.byref(io), self._stream()), "mgc_observe")
         return self.obs
 
 
