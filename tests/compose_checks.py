@@ -206,7 +206,6 @@ def check_discrete_env_and_rbc(case, lib):
 def check_quickstart_notebook(lib):
     """notebooks/quick-start.ipynb against pymgrid_b200: same cells (tests/golden/make_quickstart.py: notebook()), same
     displays, same log -- including the ten `sample_action(strict_bound=True)` steps under np.random.seed(0)"""
-    import importlib.util
     import json
     import os
     import pymgrid_b200

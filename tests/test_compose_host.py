@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from pymgrid_b200 import _cabi
-from pymgrid_b200.compose import (MGC_INFO_SLOTS, ComposedBatch, ComposedMicrogrid, Composition, in_fused_scope)
+from pymgrid_b200.compose import ComposedBatch, ComposedMicrogrid, Composition, in_fused_scope
 from tests import hostsim
 from tests import compose_checks as K
 from tests.compose_checks import CASES
