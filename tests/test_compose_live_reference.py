@@ -8,6 +8,7 @@ import ctypes
 import warnings
 
 import numpy as np
+import pymgrid_b200  # noqa: F401
 import pytest
 
 from tests import hostsim
@@ -140,3 +141,76 @@ def test_random_compositions_against_the_live_reference():
             checked_steps += 1
     print(f"{built} of {N_GRIDS} compositions built, {checked_steps} steps compared, {logs} full logs compared, {raised} runs ended where the reference raised: {sorted(kinds)}")
     assert built > N_GRIDS // 2 and checked_steps > 15 * built and raised > 0 and logs > built // 2
+
+
+def test_random_compositions_priority_lists_against_the_live_reference():
+    """DiscreteMicrogridEnv action tables (with / without the redundant genset lists), the controls random actions expand
+    to, rewards and observations, and RuleBasedControl's sorted list and run, on random compositions"""
+    from oracle.ref_loader import load_reference
+    load_reference()
+    import pymgrid
+    import pymgrid.modules as R
+    from pymgrid.algos import RuleBasedControl
+    from pymgrid.envs import DiscreteMicrogridEnv
+    import pymgrid_b200
+    from pymgrid_b200 import modules as M
+    from pymgrid_b200.compose import MAX_PRIORITY_ELEMENTS, ComposedDiscreteEnv, ComposedMicrogrid
+    lib = ctypes.CDLL(hostsim.build())
+    rows = lambda pls: [[(el.module[0], el.module[1], el.module_actions, el.action) for el in pl] for pl in pls]      # noqa: E731
+    compared = steps = 0
+    for g in range(40):
+        T = 30
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref_mods = draw(np.random.default_rng(7000 + g), R, T)
+            n_el = sum(2 if type(m[1] if isinstance(m, tuple) else m).__name__ == "GensetModule" else 1
+                       for m in ref_mods if type(m[1] if isinstance(m, tuple) else m).__name__ in ("GensetModule", "BatteryModule", "GridModule"))
+            if not 1 <= n_el <= 6 or not any(type(m[1] if isinstance(m, tuple) else m).__name__ == "LoadModule" for m in ref_mods):
+                continue
+            try:
+                ref_env = {f: DiscreteMicrogridEnv(draw(np.random.default_rng(7000 + g), R, T), add_unbalanced_module=False,
+                                                   remove_redundant_gensets=f) for f in (False, True)}
+            except Exception:      # noqa: BLE001
+                continue
+            ours_env = {f: ComposedDiscreteEnv(draw(np.random.default_rng(7000 + g), M, T), add_unbalanced_module=False,
+                                               remove_redundant_gensets=f, obs_order="container", _library=lib) for f in (False, True)}
+        assert n_el <= MAX_PRIORITY_ELEMENTS
+        for f in (False, True):
+            assert rows(ours_env[f].actions_list) == rows(ref_env[f].actions_list), (g, f)
+        ref, ours = ref_env[False], ours_env[False]
+        order = [(name, j) for name, lst in ref.modules.iterdict() for j in range(len(lst))]
+        ref.reset(), ours.reset()
+        rng = np.random.default_rng(300 + g)
+        for k in range(20):
+            a = int(rng.integers(0, ref.action_space.n))
+            try:
+                control = ref._get_action(a)
+                o0, r0, d0, _ = pymgrid.Microgrid.run(ref, control, normalized=False)
+            except Exception as exc:      # noqa: BLE001
+                with pytest.raises(type(exc)):
+                    ours.step(a)
+                break
+            o2, r2, d2, _ = ours.step(a)
+            assert r0 == r2 and d0 == d2, (g, k, a, r0, r2)
+            flat = np.concatenate([np.asarray(o0[n][j], dtype=np.float64).ravel() for n, j in order] + [np.zeros(0)])
+            assert np.array_equal(flat, o2), (g, k)
+            steps += 1
+        # rule-based control on fresh copies
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref_rbc = RuleBasedControl(pymgrid.Microgrid(draw(np.random.default_rng(7000 + g), R, T), add_unbalanced_module=False))
+            ours_rbc = pymgrid_b200.algos.RuleBasedControl(ComposedMicrogrid(draw(np.random.default_rng(7000 + g), M, T),
+                                                                            add_unbalanced_module=False, _library=lib))
+        assert rows([ours_rbc.priority_list]) == rows([ref_rbc.priority_list]), g
+        try:
+            want = ref_rbc.run(max_steps=12)
+        except Exception as exc:      # noqa: BLE001
+            with pytest.raises(type(exc)):
+                ours_rbc.run(max_steps=12)
+        else:
+            got = ours_rbc.run(max_steps=12)
+            assert [tuple(c) for c in got.columns] == [tuple(c) for c in want.columns], g
+            assert np.array_equal(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), equal_nan=True), g
+        compared += 1
+    print(f"{compared} compositions, {steps} discrete steps compared")
+    assert compared >= 10 and steps > 100
