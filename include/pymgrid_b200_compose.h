@@ -100,6 +100,11 @@ typedef struct MgcLayout {
        initial_step / final_step */
     const int32_t *env_initial_step;
     const int32_t *env_final_step;
+    /* optional observation selection (BaseMicrogridEnv(observation_keys=...), envs/base/base.py:109-163, 211-223): HOST array
+       [obs_dim], entry j = (index of the module in `modules`) << 16 | element of that module's observation block.  The row
+       then holds exactly these elements in this order and the modules' obs_off are ignored.  NULL -> every module block at
+       its obs_off. */
+    const int32_t *obs_select;
 } MgcLayout;
 
 typedef struct MgcIO {

@@ -49,7 +49,7 @@ class MgcLayout(C.Structure):
                 ("n_cfg", _i32), ("series_len", _i32), ("n_series", _i32), ("n_envs", C.c_int64),
                 ("cfg", _vp), ("series", _vp), ("series_off", _vp), ("series_nrm", _vp), ("step", _vp), ("fstate", _vp), ("istate", _vp),
                 ("cfg_index", _vp), ("plist", _vp), ("n_plist", _i32), ("plist_width", _i32),
-                ("env_initial_step", _vp), ("env_final_step", _vp)]
+                ("env_initial_step", _vp), ("env_final_step", _vp), ("obs_select", _vp)]
 
 
 class MgcIO(C.Structure):
@@ -277,6 +277,28 @@ class Composition:
                 i[s.istate_off:s.istate_off + 4] = (on, on, 0, int(m.wind_down_time)) if on else (0, 0, int(m.start_up_time), 0)
         return f, i
 
+    _FIELDS = {"load": ["load"], "renewable": ["renewable"], "grid": ["import_price", "export_price", "co2_per_kwh", "grid_status"]}
+
+    def field_names(self, s):
+        """names of the elements of slot s's observation block = the keys of the module's state_dict()"""
+        if s.kind in self._FIELDS:
+            comps = self._FIELDS[s.kind]
+            return [f"{c}_current" for c in comps] + [f"{c}_forecast_{j}" for j in range(s.horizon) for c in comps]
+        return {"battery": ["soc", "current_charge"],
+                "genset": ["current_status", "goal_status", "steps_until_up", "steps_until_down"]}.get(s.kind, [])
+
+    def select_observation(self, keys):
+        """BaseMicrogridEnv(observation_keys=...) (envs/base/base.py:109-123, 211-218): the observation is
+        `state_series(normalized=True).loc[:, :, keys]` -- for every key in the order given, the modules that have such a
+        field in listing order.  Returns [(slot, element)]; NameError for keys no module has."""
+        if isinstance(keys, str):
+            keys = [keys]
+        names = {id(s): self.field_names(s) for s in self.slots}
+        bad = [k for k in keys if not any(k in n for n in names.values())]
+        if bad:
+            raise NameError(f'Keys {bad} not found in state.')
+        return [(s, names[id(s)].index(k)) for k in keys for s in self.slots if k in names[id(s)]]
+
     def module_table(self):
         arr = (MgcModule * MGC_MAX_MODULES)()
         for k, s in enumerate(self.dispatch):
@@ -288,7 +310,7 @@ class Composition:
 # ---- the batch ----------------------------------------------------------------------------------------------------------
 class ComposedBatch:
     def __init__(self, microgrids, env_config=None, device=None, obs_order="gym_sorted", with_info=False,
-                 microgrid_kwargs=None, prenormalised=True, _library=None):
+                 microgrid_kwargs=None, prenormalised=True, observation_keys=(), _library=None):
         """`microgrids`: list of module lists (one per parameter set; all with the same composition) or ready
         `Composition`s; `env_config[e]`: which one env e is (default: one env per entry)."""
         kw = dict(microgrid_kwargs or {})
@@ -354,7 +376,10 @@ class ComposedBatch:
         self.env_final_step = t(np.array([self.compositions[c].final_step for c in env_config]), torch.int32)
         self.fstate = t(np.stack([states[c][0] for c in env_config]).reshape(n, comp.n_fstate), torch.float64)
         self.istate = t(np.stack([states[c][1] for c in env_config]).reshape(n, comp.n_istate), torch.int32)
-        self.obs = torch.zeros((n, comp.obs_dim), dtype=torch.float64, device=dev)
+        # observation_keys: the kernel writes only the selected elements, in the order the reference's envs return them
+        self.selection = comp.select_observation(observation_keys) if observation_keys else None
+        self.obs_dim = len(self.selection) if self.selection is not None else comp.obs_dim
+        self.obs = torch.zeros((n, self.obs_dim), dtype=torch.float64, device=dev)
         self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
         self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.flags = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -362,7 +387,11 @@ class ComposedBatch:
         self.info = torch.zeros((n, self.n_info), dtype=torch.float64, device=dev) if with_info else None
         L = MgcLayout()
         L.abi_version, L.n_modules, L.modules = MGC_ABI_VERSION, len(comp.slots), comp.module_table()
-        L.n_act, L.obs_dim, L.n_fstate, L.n_istate = comp.n_act, comp.obs_dim, comp.n_fstate, comp.n_istate
+        L.n_act, L.obs_dim, L.n_fstate, L.n_istate = comp.n_act, self.obs_dim, comp.n_fstate, comp.n_istate
+        if self.selection is not None:
+            index = {id(s): k for k, s in enumerate(comp.dispatch)}
+            select = (C.c_int32 * max(self.obs_dim, 1))(*[(index[id(s)] << 16) | k for s, k in self.selection])
+            L.obs_select = C.cast(select, _vp)
         L.cfg_stride, L.n_cfg, L.series_len, L.n_series, L.n_envs = comp.cfg_stride, len(cfg), comp.series_len, len(offsets), n
         L.cfg, L.series, L.series_off = self.cfg.data_ptr(), self.series.data_ptr(), self.series_off.data_ptr()
         L.series_nrm = self.series_nrm.data_ptr() if prenormalised else None      # None: the kernel normalises every element itself
@@ -463,7 +492,7 @@ class ComposedBatch:
         a = self._dactions(actions, () if const else (T,))
         reward = torch.empty((T, self.n_envs), dtype=torch.float64, device=self.device)
         done = torch.empty((T, self.n_envs), dtype=torch.uint8, device=self.device)
-        ring_buf = torch.zeros((ring, self.n_envs, self.comp.obs_dim), dtype=torch.float64, device=self.device) if obs else None
+        ring_buf = torch.zeros((ring, self.n_envs, self.obs_dim), dtype=torch.float64, device=self.device) if obs else None
         io = MgcIO(None, ring_buf.data_ptr() if obs else None, reward.data_ptr(), done.data_ptr(),
                    self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None, a.data_ptr(), int(const))
         with self._on_device():
@@ -488,7 +517,7 @@ class ComposedBatch:
         else:
             reward = torch.empty((T, self.n_envs), dtype=torch.float64, device=self.device)
             done = torch.empty((T, self.n_envs), dtype=torch.uint8, device=self.device)
-            ring_buf = torch.zeros((ring, self.n_envs, comp.obs_dim), dtype=torch.float64, device=self.device) if obs else None
+            ring_buf = torch.zeros((ring, self.n_envs, self.obs_dim), dtype=torch.float64, device=self.device) if obs else None
         io = MgcIO(a.data_ptr() if a is not None else None, ring_buf.data_ptr() if obs else None, reward.data_ptr(),
                    done.data_ptr(), self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None)
         with self._on_device():
@@ -1137,8 +1166,11 @@ class _ComposedEnv:
     microgrid with the reference's host types, `batch=B` steps B replicas with device tensors."""
 
     def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2., reward_shaping_func=None,
-                 trajectory_func=None, batch=None, device=None, obs_order="gym_sorted", _library=None):
+                 trajectory_func=None, flat_spaces=True, observation_keys=(), batch=None, device=None, obs_order="gym_sorted",
+                 _library=None):
         from .envs import Box
+        if not flat_spaces:
+            raise NotImplementedError("flat_spaces=False (nested gym spaces) is not part of the batched surface")
         self.single = batch is None
         if not self.single and reward_shaping_func is not None:
             raise NotImplementedError("batched composed envs: a reward_shaping_func is a Python callable and runs for single "
@@ -1152,11 +1184,17 @@ class _ComposedEnv:
             self.batch = self._mg._batch
         else:
             self.batch = ComposedBatch([comp], np.zeros(int(batch), dtype=np.int64), device=device, obs_order=comp.obs_order,
-                                       _library=self._mg._library)
+                                       observation_keys=observation_keys, _library=self._mg._library)
             for a in ("step_counter", "fstate", "istate"):      # replicas start from the microgrid's live state
                 getattr(self.batch, a).copy_(getattr(self._mg._batch, a).expand_as(getattr(self.batch, a)))
         self.n_envs = self.batch.n_envs
-        self.observation_space = Box(0.0, 1.0, (comp.obs_dim,))                 # base.py:161-163
+        # observation_keys (base.py:109-163, 211-218): a batch writes only the selected elements (ComposedBatch); a single
+        # microgrid keeps its full row for Microgrid.run's dicts and the env picks the selected elements out of it
+        self.observation_keys = [observation_keys] if isinstance(observation_keys, str) else list(observation_keys)
+        self._take = None
+        if self.observation_keys:
+            self._take = np.array([s.obs_off + k for s, k in comp.select_observation(self.observation_keys)], dtype=np.int64)
+        self.observation_space = Box(0.0, 1.0, (len(self._take) if self._take is not None else comp.obs_dim,))     # base.py:161-163
 
     @classmethod
     def from_microgrid(cls, microgrid, **kw):
@@ -1188,7 +1226,7 @@ class _ComposedEnv:
         """reference: BaseMicrogridEnv.reset (base.py:165-167): the flat observation after Microgrid.reset"""
         if self.single:
             self._mg.reset()
-            return self.batch.obs[0].cpu().numpy().copy()
+            return self._single_obs()
         if self.trajectory_func is not None:      # microgrid.py:221-225: a new episode window per reset, per env
             self._draw_windows(mask)
         return self.batch.reset(mask)
@@ -1209,9 +1247,13 @@ class _ComposedEnv:
             final[keep] = self.batch.env_final_step.cpu().numpy()[keep]
         self.batch.set_trajectories(initial, final)
 
+    def _single_obs(self):
+        row = self.batch.obs[0].cpu().numpy()
+        return row[self._take] if self._take is not None else row.copy()
+
     def _single_result(self, out):
         obs, reward, done, info = out
-        return self.batch.obs[0].cpu().numpy().copy(), reward, done, info
+        return self._single_obs(), reward, done, info
 
 
 class ComposedDiscreteEnv(_ComposedEnv):

@@ -254,7 +254,8 @@ extern "C" int mgc_create(const MgcLayout *L, MgcHandle **out) {
             return mgc_fail(MG_E_INVALID, "mgc_create: module parameters outside the config record");
         if (M.horizon < 0 || (!mgc_is_timeseries(M.kind) && M.horizon != 0)) return mgc_fail(MG_E_INVALID, "mgc_create: bad horizon");
         const int len = mgc_obs_len(M);
-        if (len > 0 && (M.obs_off < 0 || M.obs_off + len > L->obs_dim)) return mgc_fail(MG_E_INVALID, "mgc_create: observation block outside the row");
+        if (!L->obs_select && len > 0 && (M.obs_off < 0 || M.obs_off + len > L->obs_dim))
+            return mgc_fail(MG_E_INVALID, "mgc_create: observation block outside the row");
         obs += len;
         if (c == 1) {
             const int w = (M.kind == MGC_GENSET) ? 2 : 1;
@@ -273,7 +274,8 @@ extern "C" int mgc_create(const MgcLayout *L, MgcHandle **out) {
         if (M.listing < 0 || M.listing >= L->n_modules || seen[M.listing]) return mgc_fail(MG_E_INVALID, "mgc_create: listing is not a permutation");
         seen[M.listing] = true;
     }
-    if (obs != L->obs_dim || act != L->n_act || nf != L->n_fstate || ni != L->n_istate)
+    if (L->obs_select) obs = L->obs_dim;      // the row holds the selected elements only (checked below)
+    if (L->obs_dim < 0 || obs != L->obs_dim || act != L->n_act || nf != L->n_fstate || ni != L->n_istate)
         return mgc_fail(MG_E_INVALID, "mgc_create: row widths do not match the module table");
     if ((nf > 0 && !L->fstate) || (ni > 0 && !L->istate)) return mgc_fail(MG_E_INVALID, "mgc_create: null state pointer");
     if (n_ts > 0 && (L->series_len < 1 || L->n_series < 1 || !L->series || !L->series_off))
@@ -284,7 +286,18 @@ extern "C" int mgc_create(const MgcLayout *L, MgcHandle **out) {
     int32_t *tab = new (std::nothrow) int32_t[L->obs_dim > 0 ? L->obs_dim : 1];
     if (!tab) return mgc_fail(MG_E_INVALID, "mgc_create: out of host memory");
     for (int j = 0; j < L->obs_dim; ++j) tab[j] = -1;
-    for (int m = 0; m < L->n_modules; ++m) {
+    if (L->obs_select) {
+        for (int j = 0; j < L->obs_dim; ++j) {
+            const int32_t d = L->obs_select[j];
+            const int m = d >> 16, k = d & 0xffff;
+            if (d < 0 || m >= L->n_modules || k >= mgc_obs_len(L->modules[m])) {
+                delete[] tab;
+                return mgc_fail(MG_E_INVALID, "mgc_create: obs_select entry outside the module's observation block");
+            }
+            tab[j] = d;
+        }
+    }
+    for (int m = 0; m < L->n_modules && !L->obs_select; ++m) {
         const int len = mgc_obs_len(L->modules[m]);
         if (len > 0xffff) { delete[] tab; return mgc_fail(MG_E_UNSUPPORTED, "mgc_create: a module's observation block exceeds 65535 elements"); }
         for (int k = 0; k < len; ++k) {

@@ -75,7 +75,7 @@ class _BaseEnv:
 
     def __init__(self, configs, env_config=None, batch=None, device=None, obs_order="gym_sorted", with_info=False,
                  add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2., reward_shaping_func=None,
-                 trajectory_func=None):
+                 trajectory_func=None, flat_spaces=True, observation_keys=()):
         """`configs`: one MicrogridParams, a list of them, or -- the reference's call, BaseMicrogridEnv(modules,
         add_unbalanced_module, loss_load_cost, overgeneration_cost, reward_shaping_func, trajectory_func)
         (envs/base/base.py:84-110) -- a list of `pymgrid_b200.modules` objects / (name, module) tuples."""
@@ -102,8 +102,26 @@ class _BaseEnv:
         self.group = self.engine.groups[0]
         self.params = configs[0]
         self.n_envs = self.engine.n_envs
-        self.observation_space = Box(0.0, 1.0, (self.group.obs_dim,))     # base.py:161-163
         self._obs_order = obs_order
+        if not flat_spaces:
+            raise NotImplementedError("flat_spaces=False (nested gym spaces) is not part of the batched surface")
+        # observation_keys (base.py:109-163, 211-218): the observation is state_series(normalized=True).loc[:, :, keys] -- for
+        # every key in the order given, the modules that have such a field in listing order.  The fused kernels write full
+        # rows; the env gathers the selected columns (composed batches write only the selected elements, compose.py)
+        self.observation_keys = [observation_keys] if isinstance(observation_keys, str) else list(observation_keys)
+        self._take = self._take_dev = None
+        if self.observation_keys:
+            sl = views.obs_slices(self.params, obs_order)
+            sd = views.state_dict(self.params, self.params.current_step, 0.0, (0, 0, 0, 0))
+            fields = {name: list(sd[name].keys()) for name in sl}
+            bad = [k for k in self.observation_keys if not any(k in f for f in fields.values())]
+            if bad:
+                raise NameError(f'Keys {bad} not found in state.')
+            listing = [n for n in ("load", "pv", "genset", "battery", "grid") if n in sl]
+            self._take = np.array([sl[n].start + fields[n].index(k) for k in self.observation_keys for n in listing if k in fields[n]],
+                                  dtype=np.int64)
+            self._take_dev = torch.from_numpy(self._take).to(self.engine.device)
+        self.observation_space = Box(0.0, 1.0, (len(self._take) if self._take is not None else self.group.obs_dim,))     # base.py:161-163
         if trajectory_func is not None and not callable(trajectory_func):
             raise TypeError('trajectory_func must be callable.')             # microgrid.py:171-172
         self.trajectory_func = trajectory_func
@@ -157,7 +175,12 @@ class _BaseEnv:
         if self.trajectory_func is not None:      # microgrid.py:221-225: a new episode window per reset
             self._draw_windows(mask)
         obs = self.engine.reset(mask=mask)
-        return obs[0].cpu().numpy() if self.single else obs
+        return self._select(obs[0].cpu().numpy() if self.single else obs)
+
+    def _select(self, obs):
+        if self._take is None:
+            return obs
+        return obs[self._take] if self.single else obs.index_select(1, self._take_dev)
 
     def _draw_windows(self, mask):
         """One (initial_step, final_step) pair per env that is being reset, from `trajectory_func(initial, final)`; the
@@ -180,9 +203,9 @@ class _BaseEnv:
     def _finish(self, res):
         obs, reward, done, info = res
         if not self.single:
-            return obs, reward, done, ({} if info is None else {"info_block": info, "flags": self.group.flags})
+            return self._select(obs), reward, done, ({} if info is None else {"info_block": info, "flags": self.group.flags})
         flags = int(self.group.flags[0].item()) & 0xffffffff
-        return (obs[0].cpu().numpy(), float(reward[0].item()), bool(done[0].item()),
+        return (self._select(obs[0].cpu().numpy()), float(reward[0].item()), bool(done[0].item()),
                 views.info_row_to_dict(info[0].cpu().numpy(), flags, self.params))
 
     def __len__(self):

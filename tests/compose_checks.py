@@ -323,3 +323,31 @@ def _set_forecaster_flow(m, z, prefix, names):
     # a shorter horizon: the reference's own get_log() raises a length mismatch here; ours keeps every column, NaN-padded
     assert str(z[f"{prefix}_final_log_raises"]) == "ValueError"
     assert len(m.get_log()) == sum(n for _, n in PHASES)
+
+
+def check_observation_keys(lib):
+    """observation_keys on a composed env: a single microgrid picks the selected elements out of its row, a batch has the
+    kernel write only those (MgcLayout.obs_select); both equal the live reference's recorded observations"""
+    import importlib.util
+    import os
+    from pymgrid_b200 import modules as M
+    from pymgrid_b200.envs import DiscreteMicrogridEnv
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_observation_keys", os.path.join(here, "golden", "make_observation_keys.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    z = np.load(os.path.join(here, "golden", "observation_keys.npz"))
+    kw = {} if lib is None else {"_library": lib}
+    env = DiscreteMicrogridEnv(mk.composed_modules(M), observation_keys=mk.COMPOSED_KEYS, **kw)
+    assert env.observation_space.shape == (z["composed_obs"].shape[1],)
+    rows, rewards = mk.flow(env, mk.COMPOSED_ACTIONS)
+    assert np.array_equal(rows, z["composed_obs"]) and np.array_equal(rewards, z["composed_rewards"])
+    benv = DiscreteMicrogridEnv(mk.composed_modules(M), observation_keys=mk.COMPOSED_KEYS, batch=130, **kw)
+    assert benv.batch.obs.shape == (130, z["composed_obs"].shape[1])
+    assert np.array_equal(host(benv.reset()), np.repeat(z["composed_obs"][:1], 130, axis=0))
+    for k, a in enumerate(mk.COMPOSED_ACTIONS):
+        obs, reward, _, _ = benv.step(torch.full((130,), a, dtype=torch.int32))
+        assert np.array_equal(host(obs), np.repeat(z["composed_obs"][k + 1][None], 130, axis=0)), k
+        assert np.array_equal(host(reward), np.full(130, z["composed_rewards"][k]))
+    with pytest.raises(NameError):
+        DiscreteMicrogridEnv(mk.composed_modules(M), observation_keys=["no_such_field"], **kw)

@@ -126,3 +126,7 @@ def test_batch_trajectory_windows(lib):
 
 def test_set_forecaster_and_set_module_attr(lib):
     K.check_set_forecaster(lib)
+
+
+def test_env_observation_keys(lib):
+    K.check_observation_keys(lib)

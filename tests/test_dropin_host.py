@@ -35,3 +35,4 @@ import tests.test_zz_gpu_dropin_more as G2  # noqa: E402
 
 test_set_forecaster_matches_reference = G2.test_set_forecaster_matches_reference
 test_set_module_attr_like_the_reference_tests = G2.test_set_module_attr_like_the_reference_tests
+test_env_observation_keys_match_reference = G2.test_env_observation_keys_match_reference

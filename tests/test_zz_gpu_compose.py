@@ -100,3 +100,7 @@ def test_batch_trajectory_windows_on_gpu():
 
 def test_set_forecaster_and_set_module_attr_on_gpu():
     K.check_set_forecaster(None)
+
+
+def test_env_observation_keys_on_gpu():
+    K.check_observation_keys(None)

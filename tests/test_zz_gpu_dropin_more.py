@@ -37,3 +37,30 @@ def test_set_module_attr_like_the_reference_tests():
     for name in ("genset", "battery", "pv", "load", "grid", "unbalanced_energy"):
         assert len(cost_info[name]) == 1 and set(cost_info[name][0]) == {"production_marginal_cost", "absorption_marginal_cost"}
     assert hasattr(m, "load") and hasattr(m, "pv") and hasattr(m, "battery") and m.grid is m.modules["grid"]
+
+
+def test_env_observation_keys_match_reference(golden):
+    """DiscreteMicrogridEnv.from_scenario(1, observation_keys=[...]) (envs/base/base.py:109-163, 211-218; the reference's
+    tests/envs/test_discrete.py:82-95): selected state components, in key order"""
+    import importlib.util
+    import os
+    from pymgrid_b200.envs import DiscreteMicrogridEnv
+    spec = importlib.util.spec_from_file_location("make_observation_keys", os.path.join(os.path.dirname(__file__), "golden", "make_observation_keys.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    z = golden["observation_keys"]
+    env = DiscreteMicrogridEnv.from_scenario(1, observation_keys=mk.FUSED_KEYS)
+    assert env.observation_space.shape == (len(mk.FUSED_KEYS),)
+    rows, rewards = mk.flow(env, mk.FUSED_ACTIONS)
+    assert np.array_equal(rows, z["fused_obs"]) and np.array_equal(rewards, z["fused_rewards"])
+    # a batch gathers the same columns
+    benv = DiscreteMicrogridEnv.from_scenario(1, batch=3, observation_keys=mk.FUSED_KEYS)
+    obs = benv.reset()
+    assert tuple(obs.shape) == (3, len(mk.FUSED_KEYS)) and np.array_equal(obs[0].cpu().numpy(), z["fused_obs"][0])
+    with pytest.raises(NameError):
+        DiscreteMicrogridEnv.from_scenario(1, observation_keys=["no_such_field"])
+    # the reference's own check (tests/envs/test_discrete.py:82-95)
+    env = DiscreteMicrogridEnv.from_scenario(0, observation_keys=["load_current", "renewable_current"])
+    obs, _, _, _ = env.step(env.action_space.sample())
+    expected = [env.modules["load"][0].state_dict(normalized=True)["load_current"], env.modules["pv"][0].state_dict(normalized=True)["renewable_current"]]
+    assert obs.tolist() == expected
