@@ -1277,7 +1277,9 @@ class ComposedDiscreteEnv(_ComposedEnv):
         if self.single:
             if action not in self.action_space:
                 raise ValueError(f" Action {action} not in action space {self.action_space}")       # discrete.py:84
-            return self._single_result(self._mg.run_priority_list(int(self._index[int(action)]), 1))
+            out = self._mg.run_priority_list(int(self._index[int(action)]), 1)
+            self._mg._log_rows[-1][("action", 0, "")] = int(action)      # discrete.py:141 logs the action it was given
+            return self._single_result(out)
         a = torch.as_tensor(action, device=self.batch.device).to(torch.int64)
         bad = (a < 0) | (a >= len(self._index))
         mapped = torch.where(bad, torch.full_like(a, -1), self._index_dev.to(torch.int64)[a.clamp(0, len(self._index) - 1)])

@@ -122,6 +122,7 @@ class _BaseEnv:
                                   dtype=np.int64)
             self._take_dev = torch.from_numpy(self._take).to(self.engine.device)
         self.observation_space = Box(0.0, 1.0, (len(self._take) if self._take is not None else self.group.obs_dim,))     # base.py:161-163
+        self._log_rows = []         # single microgrid: the per-step log the reference's env keeps (it IS a Microgrid)
         if trajectory_func is not None and not callable(trajectory_func):
             raise TypeError('trajectory_func must be callable.')             # microgrid.py:171-172
         self.trajectory_func = trajectory_func
@@ -175,7 +176,29 @@ class _BaseEnv:
         if self.trajectory_func is not None:      # microgrid.py:221-225: a new episode window per reset
             self._draw_windows(mask)
         obs = self.engine.reset(mask=mask)
+        self._log_rows = []
         return self._select(obs[0].cpu().numpy() if self.single else obs)
+
+    # ---- the log of a single microgrid (reference: the env inherits Microgrid.get_log / .log, microgrid.py:434-475) ----
+    def _log_step(self, pre, info_row, reward, action=None):
+        p = self.params
+        row = views.log_row(p, views.state_dict(p, pre["t"], pre["charge"], pre["genset"], pre["soc"]), info_row, reward,
+                            self._state()["genset"])
+        row = views.caller_names(row, p)
+        if action is not None:
+            row[("action", 0, "")] = action      # DiscreteMicrogridEnv logs the action it was given (discrete.py:141)
+        self._log_rows.append(row)
+
+    def get_log(self, as_frame=True, drop_singleton_key=False):
+        if not self.single:
+            raise NotImplementedError("batched envs keep no per-step log (808 GB per year at 65 536 envs); use "
+                                      "BatchedMicrogrid.recorder(env_ids) for selected envs")
+        df = views.log_frame(self._log_rows, int(self.group.step[0].item()), drop_singleton_key)
+        return df if as_frame else df.to_dict()
+
+    @property
+    def log(self):
+        return self.get_log()
 
     def _select(self, obs):
         if self._take is None:
@@ -200,13 +223,15 @@ class _BaseEnv:
         self._windows = (initial, final)
         self.engine.set_trajectories(initial, final)
 
-    def _finish(self, res):
+    def _finish(self, res, pre=None, action=None):
         obs, reward, done, info = res
         if not self.single:
             return self._select(obs), reward, done, ({} if info is None else {"info_block": info, "flags": self.group.flags})
         flags = int(self.group.flags[0].item()) & 0xffffffff
-        return (self._select(obs[0].cpu().numpy()), float(reward[0].item()), bool(done[0].item()),
-                views.info_row_to_dict(info[0].cpu().numpy(), flags, self.params))
+        info_row, r = info[0].cpu().numpy(), float(reward[0].item())
+        if pre is not None and not flags & (1 << 5):        # a step past the end logs nothing (the reference raises there)
+            self._log_step(pre, info_row, r, action)
+        return (self._select(obs[0].cpu().numpy()), r, bool(done[0].item()), views.info_row_to_dict(info_row, flags, self.params))
 
     def __len__(self):
         return len(self.params)
@@ -226,7 +251,8 @@ class DiscreteMicrogridEnv(_BaseEnv):
             if action not in self.action_space:
                 raise ValueError(f" Action {action} not in action space {self.action_space}")   # discrete.py:84
             self._a[0] = int(action)
-            action = self._a
+            pre = self._state()
+            return self._finish(self.engine.step_discrete(self._a), pre, int(action))
         return self._finish(self.engine.step_discrete(action))
 
     def sample_action(self):
@@ -248,7 +274,8 @@ class ContinuousMicrogridEnv(_BaseEnv):
     def step(self, action, normalized=True):
         if self.single:
             self._a.copy_(torch.as_tensor(np.asarray(action, dtype=np.float64)).reshape(1, -1))
-            action = self._a
+            pre = self._state()
+            return self._finish(self.engine.step(self._a, normalized=normalized), pre)
         return self._finish(self.engine.step(action, normalized=normalized))
 
     def sample_action(self):

@@ -317,6 +317,25 @@ class ModuleContainerView(OrderedDict):
     def to_dict(self):
         return dict(self)
 
+    # the reference's first container level (module_container.py:405-411): fixed / flex / controllable
+    @property
+    def fixed(self):
+        return self._filtered(lambda m: m.module_type[1] == "fixed")
+
+    @property
+    def flex(self):
+        return self._filtered(lambda m: m.module_type[1] == "flex")
+
+    @property
+    def controllable(self):
+        return self._filtered(lambda m: m.module_type[1] == "controllable")
+
+    def names(self):
+        return list(self.keys())
+
+    def to_tuples(self):
+        return [(name, m) for name, lst in self.items() for m in lst]
+
 
 class Microgrid:
     def __new__(cls, modules=None, *args, **kw):

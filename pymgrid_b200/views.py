@@ -232,3 +232,12 @@ def drop_stale_forecasts(row, stale):
             return True
         return int(col[2].rsplit("_", 1)[1]) < old
     return OrderedDict((c, v) for c, v in row.items() if keep(c))
+
+
+def caller_names(d, p):
+    """engine keys ('pv', 'unbalanced_energy') -> the caller's module names (`p.renewable_name`, `p.unbalanced_name`), for
+    dicts keyed by module name or by (module name, number, field)"""
+    if p.renewable_name == "pv" and p.unbalanced_name == "unbalanced_energy":
+        return d
+    nm = lambda k: {"pv": p.renewable_name, "unbalanced_energy": p.unbalanced_name}.get(k, k)      # noqa: E731
+    return type(d)(((nm(k) if not isinstance(k, tuple) else (nm(k[0]),) + k[1:]), v) for k, v in d.items())

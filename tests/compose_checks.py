@@ -351,3 +351,11 @@ def check_observation_keys(lib):
         assert np.array_equal(host(reward), np.full(130, z["composed_rewards"][k]))
     with pytest.raises(NameError):
         DiscreteMicrogridEnv(mk.composed_modules(M), observation_keys=["no_such_field"], **kw)
+    # the log a single env keeps: the microgrid's columns + the action it was given (envs/discrete/discrete.py:141)
+    import json
+    env = DiscreteMicrogridEnv(mk.composed_modules(M), **kw)
+    for a in z["envlog_composed_actions"]:
+        env.step(int(a))
+    log = env.log
+    assert [list(c) for c in log.columns] == json.loads(str(z["envlog_composed_columns"]))
+    assert np.array_equal(log.to_numpy(dtype=np.float64), z["envlog_composed_values"], equal_nan=True)

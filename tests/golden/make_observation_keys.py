@@ -47,6 +47,19 @@ def main():
     data["fused_obs"], data["fused_rewards"] = flow(DiscreteMicrogridEnv.from_scenario(1, observation_keys=FUSED_KEYS), FUSED_ACTIONS)
     data["composed_obs"], data["composed_rewards"] = flow(DiscreteMicrogridEnv(composed_modules(R), observation_keys=COMPOSED_KEYS),
                                                           COMPOSED_ACTIONS)
+    # the log a (single) env keeps: the microgrid's columns + the action it was given (envs/discrete/discrete.py:141)
+    import json
+    for label, make in (("s0", lambda: DiscreteMicrogridEnv.from_scenario(0)), ("s1", lambda: DiscreteMicrogridEnv.from_scenario(1)),
+                        ("s2", lambda: DiscreteMicrogridEnv.from_scenario(2)), ("composed", lambda: DiscreteMicrogridEnv(composed_modules(R)))):
+        env = make()
+        rng = np.random.default_rng(5)
+        acts = [int(rng.integers(0, env.action_space.n)) for _ in range(8)]
+        for a in acts:
+            env.step(a)
+        log = env.log
+        data[f"envlog_{label}_actions"] = np.array(acts)
+        data[f"envlog_{label}_columns"] = np.array(json.dumps([list(c) for c in log.columns]))
+        data[f"envlog_{label}_values"] = log.to_numpy(dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, "observation_keys.npz"), **data)
     print({k: v.shape for k, v in data.items()})
 

@@ -64,3 +64,38 @@ def test_env_observation_keys_match_reference(golden):
     obs, _, _, _ = env.step(env.action_space.sample())
     expected = [env.modules["load"][0].state_dict(normalized=True)["load_current"], env.modules["pv"][0].state_dict(normalized=True)["renewable_current"]]
     assert obs.tolist() == expected
+
+
+@pytest.mark.parametrize("n", range(25))
+def test_discrete_env_scenarios_like_the_reference_suite(n):
+    """tests/envs/test_discrete.py:33-80 (TestDiscreteEnvScenario, one subclass per pymgrid25 scenario): the log grows by
+    one row per step, reset flushes it, and the action space has n_modules! * 2^n_gensets priority lists"""
+    from math import factorial
+    from pymgrid_b200.envs import DiscreteMicrogridEnv
+    env = DiscreteMicrogridEnv.from_scenario(microgrid_number=n)
+    assert len(env.log) == 0
+    for j in range(4):
+        env.step(env.sample_action())
+        assert len(env.log) == j + 1
+    env.reset()
+    assert len(env.log) == 0
+    for j in range(3):
+        env.step(env.sample_action())
+        assert len(env.log) == j + 1
+    n_action_modules = len(env.modules.controllable.sources) + len(env.modules.controllable.source_and_sinks)
+    genset_modules = len(env.modules.genset) if hasattr(env.modules, "genset") else 0
+    assert env.action_space.n == factorial(n_action_modules) * (2 ** genset_modules)
+
+
+@pytest.mark.parametrize("n", (0, 1, 2))
+def test_env_log_matches_reference(golden, n):
+    """env.log of a single DiscreteMicrogridEnv == the reference's frame, action column included (discrete.py:141)"""
+    import json
+    from pymgrid_b200.envs import DiscreteMicrogridEnv
+    z = golden["observation_keys"]
+    env = DiscreteMicrogridEnv.from_scenario(n)
+    for a in z[f"envlog_s{n}_actions"]:
+        env.step(int(a))
+    log = env.log
+    assert [list(c) for c in log.columns] == json.loads(str(z[f"envlog_s{n}_columns"]))
+    assert np.array_equal(log.to_numpy(dtype=np.float64), z[f"envlog_s{n}_values"], equal_nan=True)
