@@ -578,8 +578,9 @@ class ComposedModuleView:
     is_source = property(lambda self: self._s.is_source)
     is_sink = property(lambda self: self._s.is_sink)
     current_step = property(lambda self: self._m.current_step)
-    initial_step = property(lambda self: self._m.initial_step)
-    final_step = property(lambda self: self._m.final_step)
+    # a module's own window: what trajectory_func set at the last reset (microgrid.py:221-225), else the microgrid's
+    initial_step = property(lambda self: int(self._m._batch.env_initial_step[0].item()))
+    final_step = property(lambda self: int(self._m._batch.env_final_step[0].item()))
     provided_energy_name = property(lambda self: self._ENERGY_NAMES[self._s.kind][0])
     absorbed_energy_name = property(lambda self: self._ENERGY_NAMES[self._s.kind][1])
 
@@ -759,6 +760,11 @@ class ComposedContainer(OrderedDict):
 
     def to_tuples(self):
         return [(name, m) for name, lst in self.items() for m in lst]
+
+    def get_attrs(self, *attrs, unique=False, as_pandas=True):
+        """reference: Container.get_attrs (module_container.py:97-195)"""
+        from .microgrid import container_get_attrs
+        return container_get_attrs(self, attrs, unique, as_pandas)
 
     def __len__(self):      # counts modules, like the reference's container
         return sum(len(v) for v in self.values())

@@ -123,9 +123,30 @@ class _BaseEnv:
             self._take_dev = torch.from_numpy(self._take).to(self.engine.device)
         self.observation_space = Box(0.0, 1.0, (len(self._take) if self._take is not None else self.group.obs_dim,))     # base.py:161-163
         self._log_rows = []         # single microgrid: the per-step log the reference's env keeps (it IS a Microgrid)
-        if trajectory_func is not None and not callable(trajectory_func):
-            raise TypeError('trajectory_func must be callable.')             # microgrid.py:171-172
-        self.trajectory_func = trajectory_func
+        self.trajectory_func = self._check_trajectory_func(trajectory_func)
+
+    def _check_trajectory_func(self, trajectory_func):
+        """reference: Microgrid._check_trajectory_func (microgrid.py:167-199): one validating call, same errors"""
+        if trajectory_func is None:
+            return trajectory_func
+        if not callable(trajectory_func):
+            raise TypeError('trajectory_func must be callable.')
+        lo, hi = self.params.initial_step, self.params.final_step
+        output = trajectory_func(lo, hi)
+        try:
+            initial_step, final_step = output
+            if not (isinstance(initial_step, (int, np.integer)) and isinstance(final_step, (int, np.integer))):
+                raise ValueError
+        except (TypeError, ValueError):
+            raise TypeError(f'trajectory func must return two integer values, not {output}')
+        if initial_step < lo:
+            raise ValueError(f'trajectory_func returned initial_step value ({initial_step}) less than env\'s initial step: ({lo})')
+        if final_step > hi:
+            raise ValueError(f'trajectory_func returned final_step value ({final_step}) greater than env\'s final step: ({hi})')
+        if initial_step >= final_step:
+            raise ValueError(f'trajectory_func returned values ({initial_step}, {final_step}) such that initial_step'
+                             f'was greater than or equal to final_step.')
+        return trajectory_func
 
     @classmethod
     def from_scenario(cls, microgrid_number=0, batch=None, **kw):
@@ -221,6 +242,7 @@ class _BaseEnv:
             keep = ~np.asarray(mask.cpu() if hasattr(mask, "cpu") else mask, dtype=bool).reshape(n)
             initial[keep], final[keep] = self._windows[0][keep], self._windows[1][keep]
         self._windows = (initial, final)
+        self._module_window = (int(initial[0]), int(final[0]))      # what the module views of env 0 report
         self.engine.set_trajectories(initial, final)
 
     def _finish(self, res, pre=None, action=None):

@@ -275,7 +275,9 @@ class ModuleView:
         if item == "forecast_horizon" and self._kind in ("load", "pv", "grid"):
             return self._p.forecast_horizon
         if item in ("initial_step", "final_step"):
-            return getattr(self._m, item)
+            # a module's own window: what trajectory_func set at the last reset (microgrid.py:221-225, 652-684), else the microgrid's
+            window = getattr(self._m, "_module_window", None)
+            return window[item == "final_step"] if window is not None else getattr(self._m, item)
         if item in ("loss_load_cost", "overgeneration_cost") and self._kind == "unbalanced_energy":
             return getattr(self._p, item)
         raise AttributeError(item)
@@ -335,6 +337,41 @@ class ModuleContainerView(OrderedDict):
 
     def to_tuples(self):
         return [(name, m) for name, lst in self.items() for m in lst]
+
+    def get_attrs(self, *attrs, unique=False, as_pandas=True):
+        """reference: Container.get_attrs (module_container.py:97-195): the given attributes of every module that has them;
+        unique=True returns the single value each attribute takes (ValueError when the modules disagree)"""
+        return container_get_attrs(self, attrs, unique, as_pandas)
+
+
+def container_get_attrs(container, attrs, unique, as_pandas):
+    import pandas as pd
+    rows = OrderedDict()
+    for name, lst in container.items():
+        for j, m in enumerate(lst):
+            rows[(name, j)] = {a: getattr(m, a) for a in attrs if _has_attr(m, a)}
+    missing = [a for a in attrs if not any(a in r for r in rows.values())]
+    if missing:
+        raise AttributeError(f'No values found for key(s) {missing}')
+    if unique:
+        out = {}
+        for a in attrs:
+            vals = [r[a] for r in rows.values() if a in r]
+            if any(v != vals[0] for v in vals[1:]):
+                raise ValueError(f"Attribute(s) {[a]} have non-unique values, cannot return single unique value.")
+            out[a] = vals[0]
+        return pd.Series(out) if as_pandas else out
+    if as_pandas:
+        return pd.DataFrame.from_dict({k: r for k, r in rows.items() if r}, orient="index")
+    return {name: [rows[(name, j)] for j in range(len(lst))] for name, lst in container.items()}
+
+
+def _has_attr(m, a):
+    try:
+        getattr(m, a)
+        return True
+    except (AttributeError, KeyError, IndexError):
+        return False
 
 
 class Microgrid:
@@ -549,8 +586,12 @@ class Microgrid:
             if err & (1 << 2):
                 raise RuntimeError("Microgrid modules unable to balance energy production with consumption.\n")
             raise AssertionError(f"step rejected: {names}")
-        if self.raise_errors and flags & FLAG_CLIP_MASK:
-            names = [n for bit, n in FLAG_NAMES.items() if flags & FLAG_CLIP_MASK & bit]
+        mask = FLAG_CLIP_MASK
+        by_module = self.params.meta.get("raise_errors_by_module")
+        if by_module is not None:       # built from modules: only a module constructed with raise_errors=True raises for ITS clip
+            mask = sum(bit for bit, key in ((1 << 8, "genset"), (1 << 9, "battery"), (1 << 10, "grid")) if by_module.get(key))
+        if self.raise_errors and flags & mask:
+            names = [n for bit, n in FLAG_NAMES.items() if flags & mask & bit]
             raise ValueError(f"requested value outside the module's limits: {names}")    # base_module.py:79-93
 
     def reset(self):
@@ -558,6 +599,7 @@ class Microgrid:
         if self.trajectory_func is not None:      # microgrid.py:221-225: the modules' window, not the microgrid's own bounds
             initial_step, final_step = self.trajectory_func(self._initial_step, self._final_step)
             self._engine.set_trajectories(np.array([initial_step]), np.array([final_step]))
+            self._module_window = (int(initial_step), int(final_step))
         obs = self._engine.reset()
         self._log_rows = []
         by_name = self._named(views.obs_row_to_dict(obs[0].cpu().numpy(), self.params, self._obs_order))

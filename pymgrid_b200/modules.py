@@ -286,4 +286,8 @@ def params_from_modules(modules, add_unbalanced_module=True, loss_load_cost=10.0
                            overgeneration_cost=unb.overgeneration_cost, forecast_horizon=int(horizons.pop()),
                            initial_step=initial_step, current_step=initial_step, final_step=int(final.pop()),
                            renewable_name=ren_name, unbalanced_name=unb_name, forecasters=forecasters,
-                           meta={"raise_errors": any(m.raise_errors for m in every)})
+                           meta={"raise_errors": any(m.raise_errors for m in every),
+                                 # per controllable module: only ITS clip raises (base_module.py:79-93, 213-221, 265-268)
+                                 "raise_errors_by_module": {"genset": bool(genset.raise_errors) if genset is not None else False,
+                                                            "battery": bool(bat.raise_errors),
+                                                            "grid": bool(grid.raise_errors) if grid is not None else False}})

@@ -99,3 +99,11 @@ def test_env_log_matches_reference(golden, n):
     log = env.log
     assert [list(c) for c in log.columns] == json.loads(str(z[f"envlog_s{n}_columns"]))
     assert np.array_equal(log.to_numpy(dtype=np.float64), z[f"envlog_s{n}_values"], equal_nan=True)
+
+
+# the reference's TestMicrogrid / TestTrajectory / TestRBC on its fixture grid, through the CUDA engine
+from tests.reference_suite_fused import SUITES  # noqa: E402
+
+for _cls in SUITES:
+    globals()[_cls.__name__ + "OnGpu"] = type(_cls.__name__ + "OnGpu", (_cls,), {})
+del _cls
