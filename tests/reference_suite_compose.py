@@ -1,241 +1,126 @@
-"""The reference's own balance tests (tests/microgrid/test_microgrid.py:188-421: TestMicrogridLoadPV and its subclasses
--- load + PV only, excess PV, excess load, two loads, two PVs, two of each, 3-9 of each) restated against this package's
-`Microgrid`: same set-up, same assertions, same names.  `make_suite(library)` returns the classes bound to a backend --
-the host build of the C source (CPU suite) or None = the CUDA path (GPU suite).
+"""What the reference's balance tests pin (tests/microgrid/test_microgrid.py:188-455, the TestMicrogridLoadPV family: a
+microgrid of loads and renewables only -- equal series, PV surplus, load surplus, two loads, two PVs, two of each, three to
+nine of each, and a Python reward shaper), written for this package.  The facts checked are the reference's; the code is
+ours: one table of variants, one builder, plain check functions.  `checks(library)` binds them to a backend -- the host
+build of the composed path's C source (CPU suite) or None = the CUDA path (GPU suite).
 
-TestMicrogridRewardShaping (:424-455, a Python callable as reward_shaping_func) is included: for a single microgrid the
-shaper runs on the host on the step's info dict, where the reference calls it.  Not restated: test_to_nonmodular
-(conversion to the deprecated stack is out of scope).
+Not covered: conversion to the deprecated non-modular stack (test_to_nonmodular), which is out of scope.
 """
-import unittest
-
 import numpy as np
 import pandas as pd
+import pytest
 
 import pymgrid_b200
 from pymgrid_b200.modules import LoadModule, RenewableModule
 
+STEPS = 100
+# variant -> (number of loads, number of renewables (None = random 3..9), which side gets a surplus, reward shaper?)
+VARIANTS = {
+    "one_each": (1, 1, None, False), "pv_surplus": (1, 1, "pv", False), "load_surplus": (1, 1, "load", False),
+    "two_loads": (2, 1, None, False), "two_pv": (1, 2, None, False), "two_each": (2, 2, None, False),
+    "many_each": (None, None, None, False), "many_each_pv_surplus": (None, None, "pv", False),
+    "many_each_load_surplus": (None, None, "load", False), "python_reward_shaper": (1, 1, None, True),
+}
+CLOSE = dict(rtol=1e-7, atol=1e-10)      # the tolerance of the reference's own assertEqual (tests/helpers/test_case.py:6-25)
 
-def make_suite(library):
-    kw = {} if library is None else {"_library": library}
 
-    def Microgrid(modules, **extra):
-        return pymgrid_b200.Microgrid(modules, **kw, **extra)
+def energy_times_marginal_cost(energy_info, cost_info):
+    """the shaper of the reference's TestMicrogridRewardShaping: every module's energy times its marginal cost"""
+    cost = 0
+    for name, infos in energy_info.items():
+        for info in infos:
+            for position, (kind, amount) in enumerate(info.items()):
+                if kind in ("absorbed_energy", "provided_energy"):
+                    key = "absorption_marginal_cost" if kind == "absorbed_energy" else "production_marginal_cost"
+                    cost += amount * cost_info[name][position][key]
+    return cost
 
-    class TestMicrogridLoadPV(unittest.TestCase):
-        def setUp(self):
-            np.random.seed(0)
-            self.load_ts, self.pv_ts = self.set_ts()
-            self.microgrid, self.n_loads, self.n_pvs = self.set_microgrid()
-            self.n_modules = 1 + self.n_loads + self.n_pvs
 
-        def set_ts(self):
-            ts = 10 * np.random.rand(100)
-            return ts, ts
+def split_positive(rng, total, parts):
+    """`parts` positive series that add up to `total`"""
+    out, rest = [], total.copy()
+    for _ in range(parts - 1):
+        out.append(rest * (1 - rng.random(total.shape)))
+        rest = rest - out[-1]
+    return out + [rest]
 
-        def set_microgrid(self):
-            load = LoadModule(time_series=self.load_ts, raise_errors=True)
-            pv = RenewableModule(time_series=self.pv_ts, raise_errors=True)
-            return Microgrid([load, pv]), 1, 1
 
-        def test_populated_correctly(self):
-            self.assertTrue(hasattr(self.microgrid.modules, 'load'))
-            self.assertTrue(hasattr(self.microgrid.modules, 'renewable'))
-            self.assertEqual(len(self.microgrid.modules), self.n_modules)  # load, pv, unbalanced
+class Variant:
+    def __init__(self, name, library):
+        n_loads, n_pvs, surplus, shaped = VARIANTS[name]
+        rng = np.random.default_rng(sum(map(ord, name)))
+        base = 10 * rng.random(STEPS)
+        extra = 5 * rng.random(STEPS)
+        self.load = base + (extra if surplus == "load" else 0)
+        self.pv = base + (extra if surplus == "pv" else 0)
+        self.n_loads = n_loads or int(rng.integers(3, 10))
+        self.n_pvs = n_pvs or int(rng.integers(3, 10))
+        modules = [LoadModule(time_series=ts, raise_errors=self.n_loads <= 2) for ts in split_positive(rng, self.load, self.n_loads)]
+        modules += [RenewableModule(time_series=ts) for ts in split_positive(rng, self.pv, self.n_pvs)]
+        kw = {} if library is None else {"_library": library}
+        self.microgrid = pymgrid_b200.Microgrid(modules, **kw)
+        if shaped:      # rebuilt from the first microgrid's own modules, slack module included
+            self.microgrid = pymgrid_b200.Microgrid(self.microgrid.modules.to_tuples(), add_unbalanced_module=False,
+                                                    reward_shaping_func=energy_times_marginal_cost, **kw)
 
-        def test_current_load_correct(self):
-            try:
-                current_load = self.microgrid.modules.load.item().current_load
-            except ValueError:
-                current_load = sum(load.current_load for load in self.microgrid.modules.load)
-            np.testing.assert_allclose(current_load, self.load_ts[0], rtol=1e-7, atol=1e-10)
 
-        def test_current_pv_correct(self):
-            try:
-                current_renewable = self.microgrid.modules.renewable.item().current_renewable
-            except ValueError:
-                current_renewable = sum(renewable.current_renewable for renewable in self.microgrid.modules.renewable)
-            np.testing.assert_allclose(current_renewable, self.pv_ts[0], rtol=1e-7, atol=1e-10)
+def checks(library):
+    names = list(VARIANTS)
 
-        def test_sample_action(self):
-            sampled_action = self.microgrid.sample_action()
-            self.assertEqual(len(sampled_action), 0)
+    @pytest.mark.parametrize("name", names)
+    def test_structure_and_current_values(name):
+        v = Variant(name, library)
+        m = v.microgrid
+        assert hasattr(m.modules, "load") and hasattr(m.modules, "renewable")
+        assert len(m.modules) == 1 + v.n_loads + v.n_pvs                      # + the slack module
+        np.testing.assert_allclose(sum(x.current_load for x in m.modules.load), v.load[0], **CLOSE)
+        np.testing.assert_allclose(sum(x.current_renewable for x in m.modules.renewable), v.pv[0], **CLOSE)
+        if v.n_loads == 1:
+            assert m.modules.load.item().current_load == v.load[0]
+        else:
+            with pytest.raises(ValueError):
+                m.modules.load.item()
 
-        def test_sample_action_with_flex(self):
-            sampled_action = self.microgrid.sample_action(sample_flex_modules=True)
-            self.assertEqual(len(sampled_action), 2)
-            self.assertIn('renewable', sampled_action)
-            self.assertIn('balancing', sampled_action)
-            self.assertEqual(len(sampled_action['renewable']), self.n_pvs)
+    @pytest.mark.parametrize("name", names)
+    def test_actions_and_state_views(name):
+        v = Variant(name, library)
+        m = v.microgrid
+        assert m.sample_action() == {} and m.get_empty_action() == {}         # nothing controllable
+        flex = m.sample_action(sample_flex_modules=True)
+        assert set(flex) == {"renewable", "balancing"} and len(flex["renewable"]) == v.n_pvs
+        state = m.state_dict()
+        assert {"load", "renewable", "balancing"} <= set(state)
+        assert len(state["load"]) == v.n_loads and len(state["balancing"]) == 1
+        series = m.state_series()
+        assert set(series.index.get_level_values(0)) == {"load", "renewable"}
+        assert series["load"].index.get_level_values(0).nunique() == v.n_loads
+        assert series["renewable"].index.get_level_values(0).nunique() == v.n_pvs
 
-        def test_state_dict(self):
-            sd = self.microgrid.state_dict()
-            self.assertIn('load', sd)
-            self.assertIn('renewable', sd)
-            self.assertIn('balancing', sd)
-            self.assertEqual(len(sd['load']), self.n_loads)
-            self.assertEqual(len(sd['balancing']), 1)
+    @pytest.mark.parametrize("name", names)
+    def test_every_step_balances_and_logs(name):
+        v = Variant(name, library)
+        m = v.microgrid
+        loss_load_cost = m.modules.balancing[0].loss_load_cost
+        for t in range(STEPS):
+            obs, reward, done, info = m.run(m.get_empty_action())
+            met = min(v.load[t], v.pv[t])
+            unmet, curtailed = max(v.load[t] - met, 0), max(v.pv[t] - met, 0)
+            np.testing.assert_allclose(-reward, loss_load_cost * max(v.load[t] - v.pv[t], 0), **CLOSE)
+            log = m.log
+            assert len(log) == t + 1 and all(n in log for n in m.modules.names())
+            row = log.iloc[t]
+            total = lambda module, field: row.loc[pd.IndexSlice[module, :, field]].sum()      # noqa: E731
+            assert row["load"].index.get_level_values(0).nunique() == v.n_loads
+            want = {("load", "load_current"): -v.load[t], ("load", "load_met"): v.load[t],
+                    ("renewable", "renewable_current"): v.pv[t], ("renewable", "renewable_used"): met,
+                    ("renewable", "curtailment"): curtailed, ("balancing", "loss_load"): unmet,
+                    ("balance", "reward"): -loss_load_cost * unmet,
+                    ("balance", "overall_provided_to_microgrid"): v.load[t],
+                    ("balance", "overall_absorbed_from_microgrid"): v.load[t],
+                    ("balance", "fixed_provided_to_microgrid"): 0.0, ("balance", "fixed_absorbed_from_microgrid"): v.load[t],
+                    ("balance", "controllable_provided_to_microgrid"): 0.0,
+                    ("balance", "controllable_absorbed_from_microgrid"): 0.0}
+            for (module, field), value in want.items():
+                np.testing.assert_allclose(total(module, field), value, err_msg=f"{module}.{field} at step {t}", **CLOSE)
 
-        def test_state_series(self):
-            ss = self.microgrid.state_series()
-            self.assertEqual({'load', 'renewable'}, set(ss.index.get_level_values(0)))
-            self.assertEqual(ss['load'].index.get_level_values(0).nunique(), self.n_loads)
-            self.assertEqual(ss['renewable'].index.get_level_values(0).nunique(), self.n_pvs)
-
-        def assertClose(self, a, b):
-            # the reference's TestCase.assertEqual falls back to assert_allclose(rtol=1e-7, atol=1e-10)
-            # (tests/helpers/test_case.py:6-25): its own sums over split series are not exact either
-            np.testing.assert_allclose(a, b, rtol=1e-7, atol=1e-10)
-
-        def check_step(self, microgrid, step_number=0):
-            control = microgrid.get_empty_action()
-            self.assertEqual(len(control), 0)
-
-            obs, reward, done, info = microgrid.run(control)
-            loss_load = self.load_ts[step_number] - self.pv_ts[step_number]
-            loss_load_cost = self.microgrid.modules.balancing[0].loss_load_cost * max(loss_load, 0)
-
-            self.assertClose(loss_load_cost, -1 * reward)
-
-            self.assertEqual(len(microgrid.log), step_number + 1)
-            self.assertTrue(all(module in microgrid.log for module in microgrid.modules.names()))
-
-            load_met = min(self.load_ts[step_number], self.pv_ts[step_number])
-            loss_load = max(self.load_ts[step_number] - load_met, 0)
-            pv_curtailment = max(self.pv_ts[step_number] - load_met, 0)
-
-            log_row = microgrid.log.iloc[step_number]
-            log_entry = lambda module, entry: log_row.loc[pd.IndexSlice[module, :, entry]].sum()  # noqa: E731
-
-            self.assertEqual(log_row['load'].index.get_level_values(0).nunique(), self.n_loads)
-
-            self.assertClose(log_entry('load', 'load_current'), -1 * self.load_ts[step_number])
-            self.assertClose(log_entry('load', 'load_met'), self.load_ts[step_number])
-
-            if loss_load == 0:
-                self.assertClose(log_entry('load', 'load_met'), load_met)
-
-            self.assertClose(log_entry('renewable', 'renewable_current'), self.pv_ts[step_number])
-            self.assertClose(log_entry('renewable', 'renewable_used'), load_met)
-            self.assertClose(log_entry('renewable', 'curtailment'), pv_curtailment)
-
-            self.assertClose(log_entry('balancing', 'loss_load'), loss_load)
-
-            self.assertClose(log_entry('balance', 'reward'), -1 * loss_load_cost)
-            self.assertClose(log_entry('balance', 'overall_provided_to_microgrid'), self.load_ts[step_number])
-            self.assertClose(log_entry('balance', 'overall_absorbed_from_microgrid'), self.load_ts[step_number])
-            self.assertClose(log_entry('balance', 'fixed_provided_to_microgrid'), 0.0)
-            self.assertClose(log_entry('balance', 'fixed_absorbed_from_microgrid'), self.load_ts[step_number])
-            self.assertClose(log_entry('balance', 'controllable_absorbed_from_microgrid'), 0.0)
-            self.assertClose(log_entry('balance', 'controllable_provided_to_microgrid'), 0.0)
-
-            return microgrid
-
-        def test_run_one_step(self):
-            self.check_step(microgrid=self.microgrid, step_number=0)
-
-        def test_run_n_steps(self):
-            microgrid = self.microgrid
-            for step in range(len(self.load_ts)):
-                with self.subTest(step=step):
-                    microgrid = self.check_step(microgrid=microgrid, step_number=step)
-
-    class TestMicrogridLoadExcessPV(TestMicrogridLoadPV):
-        def set_ts(self):
-            load_ts = 10 * np.random.rand(100)
-            pv_ts = load_ts + 5 * np.random.rand(100)
-            return load_ts, pv_ts
-
-    class TestMicrogridPVExcessLoad(TestMicrogridLoadPV):
-        def set_ts(self):
-            pv_ts = 10 * np.random.rand(100)
-            load_ts = pv_ts + 5 * np.random.rand(100)
-            return load_ts, pv_ts
-
-    class TestMicrogridTwoLoads(TestMicrogridLoadPV):
-        def set_microgrid(self):
-            load_1_ts = self.load_ts * (1 - np.random.rand(*self.load_ts.shape))
-            load_2_ts = self.load_ts - load_1_ts
-            assert all(load_1_ts > 0) and all(load_2_ts > 0)
-            load_1 = LoadModule(time_series=load_1_ts, raise_errors=True)
-            load_2 = LoadModule(time_series=load_2_ts, raise_errors=True)
-            pv = RenewableModule(time_series=self.pv_ts, raise_errors=True)
-            return Microgrid([load_1, load_2, pv]), 2, 1
-
-    class TestMicrogridTwoPV(TestMicrogridLoadPV):
-        def set_microgrid(self):
-            pv_1_ts = self.pv_ts * (1 - np.random.rand(*self.pv_ts.shape))
-            pv_2_ts = self.pv_ts - pv_1_ts
-            assert all(pv_1_ts > 0) and all(pv_2_ts > 0)
-            load = LoadModule(time_series=self.load_ts, raise_errors=True)
-            pv_1 = RenewableModule(time_series=pv_1_ts, raise_errors=True)
-            pv_2 = RenewableModule(time_series=pv_2_ts)
-            return Microgrid([load, pv_1, pv_2]), 1, 2
-
-    class TestMicrogridTwoEach(TestMicrogridLoadPV):
-        def set_microgrid(self):
-            load_1_ts = self.load_ts * (1 - np.random.rand(*self.load_ts.shape))
-            load_2_ts = self.load_ts - load_1_ts
-            pv_1_ts = self.pv_ts * (1 - np.random.rand(*self.pv_ts.shape))
-            pv_2_ts = self.pv_ts - pv_1_ts
-            load_1 = LoadModule(time_series=load_1_ts, raise_errors=True)
-            load_2 = LoadModule(time_series=load_2_ts, raise_errors=True)
-            pv_1 = RenewableModule(time_series=pv_1_ts, raise_errors=True)
-            pv_2 = RenewableModule(time_series=pv_2_ts)
-            return Microgrid([load_1, load_2, pv_1, pv_2]), 2, 2
-
-    class TestMicrogridManyEach(TestMicrogridLoadPV):
-        def set_microgrid(self):
-            n_loads = np.random.randint(3, 10)
-            n_pvs = np.random.randint(3, 10)
-            load_ts = [self.load_ts * (1 - np.random.rand(*self.load_ts.shape))]
-            pv_ts = [self.pv_ts * (1 - np.random.rand(*self.pv_ts.shape))]
-            for ts_list, ts_sum, n_modules in zip([load_ts, pv_ts], [self.load_ts, self.pv_ts], [n_loads, n_pvs]):
-                remaining = ts_sum - ts_list[0]
-                for j in range(1, n_modules - 1):
-                    ts_list.append(remaining * (1 - np.random.rand(*ts_sum.shape)))
-                    assert all(ts_list[-1] > 0)
-                    remaining -= ts_list[-1]
-                assert all(remaining > 0)
-                ts_list.append(remaining)
-            load_modules = [LoadModule(time_series=ts) for ts in load_ts]
-            pv_modules = [RenewableModule(time_series=ts) for ts in pv_ts]
-            return Microgrid([*load_modules, *pv_modules]), n_loads, n_pvs
-
-    class TestMicrogridManyEachExcessPV(TestMicrogridManyEach):
-        def set_ts(self):
-            load_ts = 10 * np.random.rand(100)
-            pv_ts = load_ts + 5 * np.random.rand(100)
-            return load_ts, pv_ts
-
-    class TestMicrogridManyEachExcessLoad(TestMicrogridManyEach):
-        def set_ts(self):
-            pv_ts = 10 * np.random.rand(100)
-            load_ts = pv_ts + 5 * np.random.rand(100)
-            return load_ts, pv_ts
-
-    class TestMicrogridRewardShaping(TestMicrogridLoadPV):
-        def set_microgrid(self):
-            original_microgrid, n_loads, n_pvs = super().set_microgrid()
-            new_microgrid = Microgrid(original_microgrid.modules.to_tuples(), add_unbalanced_module=False,
-                                      reward_shaping_func=self.reward_shaping_func)
-            return new_microgrid, n_loads, n_pvs
-
-        @staticmethod
-        def reward_shaping_func(energy_info, cost_info):
-            total = 0
-            for module_name, info_list in energy_info.items():
-                for module_info in info_list:
-                    for j, (energy_type, energy_amount) in enumerate(module_info.items()):
-                        if energy_type == 'absorbed_energy':
-                            marginal_cost = cost_info[module_name][j]['absorption_marginal_cost']
-                        elif energy_type == 'provided_energy':
-                            marginal_cost = cost_info[module_name][j]['production_marginal_cost']
-                        else:
-                            continue
-                        total += energy_amount * marginal_cost
-            return total
-
-    return [TestMicrogridRewardShaping, TestMicrogridLoadPV, TestMicrogridLoadExcessPV, TestMicrogridPVExcessLoad, TestMicrogridTwoLoads,
-            TestMicrogridTwoPV, TestMicrogridTwoEach, TestMicrogridManyEach, TestMicrogridManyEachExcessPV,
-            TestMicrogridManyEachExcessLoad]
+    return [test_structure_and_current_values, test_actions_and_state_views, test_every_step_balances_and_logs]

@@ -1,214 +1,149 @@
-"""The reference's API / env / controller tests on its shared fixture grid (tests/helpers/modular_microgrid.py:14-55: genset
-10-50 @ 0.5, battery 0-100 / 50 / 50, PV == 50, load == 60, grid import 100 / export 0 at price 1, raise_errors on the grid)
-restated against this package: tests/microgrid/test_microgrid.py:12-186 (TestMicrogrid), tests/envs/test_trajectory.py,
-tests/control/test_rbc.py -- same set-up, same assertions.  Collected twice: on the CPU with the engine replaced by the
-oracle-backed stand-in (tests/test_reference_suite_fused_host.py) and on the GPU (tests/test_zz_gpu_dropin_more.py).
+"""What the reference's API / env / controller tests pin on its shared fixture grid (tests/helpers/modular_microgrid.py:14-55:
+genset 10-50 at cost 0.5, battery 0-100 with 50 / 50 power and efficiency 1 at soc 0.5, PV == 50, load == 60, grid import
+100 / export 0 at price 1 with raise_errors=True) -- tests/microgrid/test_microgrid.py:12-186, tests/envs/test_trajectory.py,
+tests/control/test_rbc.py -- written for this package: the facts are the reference's, the code is ours (plain pytest
+functions over one fixture builder).  Collected twice: on the CPU with the engine replaced by the oracle-backed stand-in
+(tests/test_reference_suite_fused_host.py) and on the GPU (tests/test_zz_gpu_dropin_more.py).
 
-Not restated: the MicrogridSpace sampling tests (test_action_space*: gym space objects are not mirrored), test_init of TestRBC
-and test_trajectory_serialization (object equality / YAML round trips of the reference classes).
+Not covered: sampling from gym space objects (test_action_space*), object equality and YAML round trips of the reference
+classes (TestRBC.test_init, test_trajectory_serialization).
 """
-import unittest
-
 import numpy as np
+import pytest
 
 import pymgrid_b200
 from pymgrid_b200.algos import RuleBasedControl
 from pymgrid_b200.envs import DiscreteMicrogridEnv
 from pymgrid_b200.modules import BatteryModule, GensetModule, GridModule, LoadModule, RenewableModule
 
-
-def get_modular_microgrid(remove_modules=(), timeseries_length=100, modules_only=False, **microgrid_kw):
-    modules = dict(
-        genset=GensetModule(running_min_production=10, running_max_production=50, genset_cost=0.5),
-        battery=BatteryModule(min_capacity=0, max_capacity=100, max_charge=50, max_discharge=50, efficiency=1.0, init_soc=0.5),
-        renewable=RenewableModule(time_series=50 * np.ones(timeseries_length)),
-        load=LoadModule(time_series=60 * np.ones(timeseries_length)),
-        grid=GridModule(max_import=100, max_export=0, time_series=np.ones((timeseries_length, 3)), raise_errors=True))
-    for module in remove_modules:
-        modules.pop(module)
-    modules = list(modules.values())
-    if modules_only:
-        return modules
-    return pymgrid_b200.Microgrid(modules, **microgrid_kw)
+T = 100
 
 
-class TestMicrogrid(unittest.TestCase):
-    def test_from_scenario(self):
-        for j in range(25):
-            with self.subTest(microgrid_number=j):
-                microgrid = pymgrid_b200.Microgrid.from_scenario(j)
-                self.assertTrue(hasattr(microgrid, "load"))
-                self.assertTrue(hasattr(microgrid, "pv"))
-                self.assertTrue(hasattr(microgrid, "battery"))
-                self.assertTrue(hasattr(microgrid, "grid") or hasattr(microgrid, "genset"))
-
-    def test_empty_action_with_load(self):
-        action = get_modular_microgrid().get_empty_action()
-        self.assertIn('battery', action)
-        self.assertIn('genset', action)
-        self.assertIn('grid', action)
-        self.assertNotIn('load', action)
-        self.assertTrue(all(v == [None] for v in action.values()))
-
-    def test_sample_action(self):
-        microgrid = get_modular_microgrid()
-        action = microgrid.sample_action()
-        for module_name, action_list in action.items():
-            for module_num, _act in enumerate(action_list):
-                action_arr = np.atleast_1d(np.array(_act))
-                self.assertEqual(action_arr.shape[0], microgrid.modules[module_name][module_num].action_space.shape[0])
-                self.assertTrue(((0 <= action_arr) & (action_arr <= 1)).all())
-
-    def test_sample_action_all_modules_populated(self):
-        microgrid = get_modular_microgrid()
-        action = microgrid.sample_action()
-        for module_name, module_list in microgrid.fixed.iterdict():
-            for module_num, module in enumerate(module_list):
-                empty_action_space = module.action_space.shape == (0, )
-                try:
-                    _ = action[module_name][module_num]
-                    has_corresponding_action = True
-                except KeyError:
-                    has_corresponding_action = False
-                self.assertTrue(empty_action_space != has_corresponding_action)  # XOR
-
-    def test_current_step(self):
-        microgrid = get_modular_microgrid()
-        self.assertEqual(microgrid.current_step, 0)
-        for j in range(4):
-            microgrid.run(microgrid.sample_action())
-            self.assertEqual(microgrid.current_step, j + 1)
-
-    def test_current_step_after_reset(self):
-        microgrid = get_modular_microgrid()
-        microgrid.run(microgrid.sample_action())
-        self.assertEqual(microgrid.current_step, 1)
-        microgrid.reset()
-        self.assertEqual(microgrid.current_step, 0)
-
-    def test_set_module_attr_forecast_horizon(self):
-        microgrid = get_modular_microgrid()
-        microgrid.set_module_attr('forecast_horizon', 50)
-        fh = [module.forecast_horizon for module in microgrid.modules.iterlist() if hasattr(module, 'forecast_horizon')]
-        self.assertEqual(min(fh), max(fh))
-        self.assertEqual(min(fh), 50)
-
-    def test_set_module_attr_bad_attr_name(self):
-        with self.assertRaises(AttributeError):
-            get_modular_microgrid().set_module_attr('blah', 'blah')
-
-    def test_get_cost_info(self):
-        cost_info = get_modular_microgrid().get_cost_info()
-        for module in ('genset', 'battery', 'renewable', 'load', 'grid', 'balancing'):
-            self.assertIn(module, cost_info.keys())
-            self.assertEqual(len(cost_info[module]), 1)
-            self.assertEqual(set(cost_info[module][0]), {'production_marginal_cost', 'absorption_marginal_cost'})
-
-    def test_set_initial_step(self):
-        microgrid = get_modular_microgrid()
-        self.assertEqual(microgrid.initial_step, 0)
-        microgrid.initial_step = 1
-        self.assertEqual(microgrid.initial_step, 1)
-        microgrid.reset()
-        self.assertEqual(microgrid.current_step, 1)
+def fixture_modules(length=T):
+    return [GensetModule(running_min_production=10, running_max_production=50, genset_cost=0.5),
+            BatteryModule(min_capacity=0, max_capacity=100, max_charge=50, max_discharge=50, efficiency=1.0, init_soc=0.5),
+            RenewableModule(time_series=np.full(length, 50.0)), LoadModule(time_series=np.full(length, 60.0)),
+            GridModule(max_import=100, max_export=0, time_series=np.ones((length, 3)), raise_errors=True)]
 
 
-class TestTrajectory(unittest.TestCase):
-    def check_initial_final_steps(self, env, expected_env_initial, expected_env_final, expected_module_initial, expected_module_final):
-        self.assertEqual(env.initial_step, expected_env_initial)
-        self.assertEqual(env.final_step, expected_env_final)
+def fixture_microgrid():
+    return pymgrid_b200.Microgrid(fixture_modules())
+
+
+def windowed_env(trajectory_func):
+    return DiscreteMicrogridEnv(fixture_modules(), trajectory_func=trajectory_func)
+
+
+# ---- Microgrid surface (test_microgrid.py:12-186) ----------------------------------------------------------------------
+def test_every_scenario_exposes_its_modules_as_attributes():
+    for n in range(25):
+        m = pymgrid_b200.Microgrid.from_scenario(n)
+        assert all(hasattr(m, name) for name in ("load", "pv", "battery")) and (hasattr(m, "grid") or hasattr(m, "genset")), n
+
+
+def test_action_templates_cover_exactly_the_controllable_modules():
+    m = fixture_microgrid()
+    empty = m.get_empty_action()
+    assert set(empty) == {"battery", "genset", "grid"} and all(v == [None] for v in empty.values())
+    sampled = m.sample_action()
+    assert set(sampled) == set(empty)
+    for name, values in sampled.items():
+        for k, value in enumerate(values):
+            arr = np.atleast_1d(np.asarray(value, dtype=float))
+            assert arr.shape[0] == m.modules[name][k].action_space.shape[0] and ((0 <= arr) & (arr <= 1)).all()
+    for name, modules in m.fixed.iterdict():          # fixed modules have no action space and get no action
+        for module in modules:
+            assert module.action_space.shape == (0,) and name not in sampled
+
+
+def test_step_counter_and_reset():
+    m = fixture_microgrid()
+    assert m.current_step == 0
+    for k in range(4):
+        m.run(m.sample_action())
+        assert m.current_step == k + 1
+    m.reset()
+    assert m.current_step == 0
+    m.initial_step = 1
+    assert m.initial_step == 1
+    m.reset()
+    assert m.current_step == 1
+
+
+def test_set_module_attr_and_cost_info():
+    m = fixture_microgrid()
+    m.set_module_attr("forecast_horizon", 50)
+    horizons = {x.forecast_horizon for x in m.modules.iterlist() if hasattr(x, "forecast_horizon")}
+    assert horizons == {50}
+    with pytest.raises(AttributeError):
+        m.set_module_attr("blah", "blah")
+    info = fixture_microgrid().get_cost_info()
+    for name in ("genset", "battery", "renewable", "load", "grid", "balancing"):
+        assert len(info[name]) == 1 and set(info[name][0]) == {"production_marginal_cost", "absorption_marginal_cost"}
+        assert all(isinstance(float(v), float) for v in info[name][0].values())
+
+
+# ---- episode windows (test_trajectory.py) ------------------------------------------------------------------------------
+def module_window(env):
+    return (env.modules.get_attrs("initial_step", unique=True).item(), env.modules.get_attrs("final_step", unique=True).item())
+
+
+@pytest.mark.parametrize("func, window", [(None, (0, T)), (lambda lo, hi: (10, 20), (10, 20))])
+def test_trajectory_moves_the_modules_window_not_the_envs(func, window):
+    env = windowed_env(func)
+    assert (env.initial_step, env.final_step) == (0, T)
+    env.reset()
+    assert (env.initial_step, env.final_step) == (0, T) and module_window(env) == window
+
+
+def test_random_trajectory_stays_inside_the_series():
+    def draw(lo, hi):
+        a = int(np.random.randint(lo + 1, hi - 2))
+        return a, int(np.random.randint(a + 1, hi))
+    env = windowed_env(draw)
+    env.reset()
+    lo, hi = module_window(env)
+    assert (env.initial_step, env.final_step) == (0, T) and 0 < lo < hi < T
+
+
+@pytest.mark.parametrize("func, error", [
+    (lambda lo, hi: (10, 110), ValueError),            # beyond the series
+    (lambda lo: (10, 110), TypeError),                 # wrong signature
+    (lambda lo, hi: (20, 10), ValueError),             # empty window
+    (lambda lo, hi: 20, TypeError),                    # not a pair
+    (lambda lo, hi: (10, 20, 30), TypeError),          # too many values
+    (lambda lo, hi: ("abc", 10.0), TypeError)])        # not integers
+def test_bad_trajectory_functions_are_rejected_at_construction(func, error):
+    with pytest.raises(error):
+        windowed_env(func)
+
+
+def test_episode_length_is_the_window_length():
+    calls = {"n": 0}
+
+    def growing(lo, hi):
+        calls["n"] += 1
+        return 10, 11 + calls["n"]
+    env = windowed_env(growing)            # one validating call here, like Microgrid._check_trajectory_func
+    for expected in range(3, 7):
         env.reset()
-        self.assertEqual(env.initial_step, expected_env_initial)
-        self.assertEqual(env.final_step, expected_env_final)
-        self.assertEqual(env.modules.get_attrs('initial_step', unique=True).item(), expected_module_initial)
-        self.assertEqual(env.modules.get_attrs('final_step', unique=True).item(), expected_module_final)
-
-    def env(self, trajectory_func, timeseries_length=100):
-        return DiscreteMicrogridEnv(get_modular_microgrid(timeseries_length=timeseries_length, modules_only=True),
-                                    trajectory_func=trajectory_func)
-
-    def test_none_trajectory(self):
-        self.check_initial_final_steps(self.env(None), 0, 100, 0, 100)
-
-    def test_deterministic_trajectory(self):
-        self.check_initial_final_steps(self.env(lambda initial_step, final_step: (10, 20)), 0, 100, 10, 20)
-
-    def test_stochastic_trajectory(self):
-        def trajectory_func(initial_step, final_step):
-            initial = np.random.randint(low=initial_step + 1, high=final_step - 2)
-            final = np.random.randint(low=initial, high=final_step)
-            return int(initial), int(max(final, initial + 1))
-        env = self.env(trajectory_func)
-        env.reset()
-        self.assertEqual((env.initial_step, env.final_step), (0, 100))
-        ini = env.modules.get_attrs('initial_step', unique=True).item()
-        fin = env.modules.get_attrs('final_step', unique=True).item()
-        self.assertTrue(0 < ini < fin <= 100)
-
-    def test_bad_trajectory_out_of_range(self):
-        with self.assertRaises(ValueError):
-            self.env(lambda initial_step, final_step: (10, 110))
-
-    def test_bad_trajectory_bad_signature(self):
-        with self.assertRaises(TypeError):
-            self.env(lambda initial_step: (10, 110))
-
-    def test_bad_trajectory_initial_gt_final(self):
-        with self.assertRaises(ValueError):
-            self.env(lambda initial_step, final_step: (20, 10))
-
-    def test_bad_trajectory_scalar_output(self):
-        with self.assertRaises(TypeError):
-            self.env(lambda initial_step, final_step: 20)
-
-    def test_bad_trajectory_too_many_outputs(self):
-        with self.assertRaises(TypeError):
-            self.env(lambda initial_step, final_step: (10, 20, 30))
-
-    def test_bad_trajectory_wrong_output_types(self):
-        with self.assertRaises(TypeError):
-            self.env(lambda initial_step, final_step: ('abc', 10.0))
-
-    def test_correct_trajectory_length(self):
-        def trajectory_func(initial_step, final_step):
-            trajectory_func.n_resets += 1
-            return 10, 11 + trajectory_func.n_resets
-        trajectory_func.n_resets = 0
-        env = self.env(trajectory_func)
-        for correct_trajectory_length in range(3, 7):
-            with self.subTest(correct_trajectory_length=correct_trajectory_length):
-                env.reset()
-                n_steps, done = 0, False
-                while not done:
-                    _, _, done, _ = env.step(env.action_space.sample())
-                    n_steps += 1
-                self.assertEqual(n_steps, correct_trajectory_length)
+        n_steps, done = 0, False
+        while not done:
+            _, _, done, _ = env.step(env.action_space.sample())
+            n_steps += 1
+        assert n_steps == expected
 
 
-class TestRBC(unittest.TestCase):
-    def setUp(self):
-        self.rbc = RuleBasedControl(get_modular_microgrid())
-
-    def test_priority_list(self):
-        for element_1, element_2 in zip(self.rbc.priority_list[:-1], self.rbc.priority_list[1:]):
-            self.assertLessEqual(element_1.marginal_cost, element_2.marginal_cost)
-
-    def run_once(self):
-        rbc = self.rbc
-        self.assertEqual(len(rbc.microgrid.log), 0)
-        n_steps = 10
-        log = rbc.run(n_steps)
-        self.assertEqual(len(log), n_steps)
-        self.assertTrue(log.equals(rbc.microgrid.log))
-        return rbc
-
-    def test_run_once(self):
-        self.run_once()
-
-    def test_reset_after_run(self):
-        rbc = self.run_once()
-        rbc.reset()
-        self.assertEqual(len(rbc.microgrid.log), 0)
+# ---- rule-based control (test_rbc.py) ----------------------------------------------------------------------------------
+def test_rule_based_control_orders_by_cost_runs_and_resets():
+    rbc = RuleBasedControl(fixture_microgrid())
+    costs = [el.marginal_cost for el in rbc.priority_list]
+    assert costs == sorted(costs)
+    assert len(rbc.microgrid.log) == 0
+    log = rbc.run(10)
+    assert len(log) == 10 and log.equals(rbc.microgrid.log)
+    rbc.reset()
+    assert len(rbc.microgrid.log) == 0
 
 
-SUITES = (TestMicrogrid, TestTrajectory, TestRBC)
+CHECKS = [v for k, v in sorted(globals().items()) if k.startswith("test_")]

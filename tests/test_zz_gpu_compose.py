@@ -77,12 +77,12 @@ def test_large_batch_energy_balance_and_replica_consistency():
     assert np.array_equal(obs[0].cpu().numpy(), want)
 
 
-# the reference's TestMicrogridLoadPV family (tests/microgrid/test_microgrid.py:188-421) through the CUDA path
-from tests.reference_suite_compose import make_suite  # noqa: E402
+# what the reference's TestMicrogridLoadPV family pins (tests/microgrid/test_microgrid.py:188-455), through the CUDA path
+from tests.reference_suite_compose import checks  # noqa: E402
 
-for _cls in make_suite(None):
-    globals()[_cls.__name__ + "OnGpu"] = type(_cls.__name__ + "OnGpu", (_cls,), {})
-del _cls
+for _fn in checks(None):
+    globals()[_fn.__name__ + "_on_gpu"] = _fn
+del _fn
 
 
 @pytest.mark.parametrize("case", K.DISCRETE_CASES, ids=[c.label for c in K.DISCRETE_CASES])

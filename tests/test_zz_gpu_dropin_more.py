@@ -101,9 +101,9 @@ def test_env_log_matches_reference(golden, n):
     assert np.array_equal(log.to_numpy(dtype=np.float64), z[f"envlog_s{n}_values"], equal_nan=True)
 
 
-# the reference's TestMicrogrid / TestTrajectory / TestRBC on its fixture grid, through the CUDA engine
-from tests.reference_suite_fused import SUITES  # noqa: E402
+# what the reference's TestMicrogrid / TestTrajectory / TestRBC pin on its fixture grid, through the CUDA engine
+from tests.reference_suite_fused import CHECKS  # noqa: E402
 
-for _cls in SUITES:
-    globals()[_cls.__name__ + "OnGpu"] = type(_cls.__name__ + "OnGpu", (_cls,), {})
-del _cls
+for _fn in CHECKS:
+    globals()[_fn.__name__ + "_on_gpu"] = _fn
+del _fn
