@@ -2,7 +2,8 @@
 microgrid of loads and renewables only -- equal series, PV surplus, load surplus, two loads, two PVs, two of each, three to
 nine of each, and a Python reward shaper), written for this package.  The facts checked are the reference's; the code is
 ours: one table of variants, one builder, plain check functions.  `checks(library)` binds them to a backend -- the host
-build of the composed path's C source (CPU suite) or None = the CUDA path (GPU suite).
+build of the composed path's C source (CPU suite; a callable, so that nothing is compiled at collection time) or None = the
+CUDA path (GPU suite).
 
 Not covered: conversion to the deprecated non-modular stack (test_to_nonmodular), which is out of scope.
 """
@@ -57,6 +58,8 @@ class Variant:
         self.n_pvs = n_pvs or int(rng.integers(3, 10))
         modules = [LoadModule(time_series=ts, raise_errors=self.n_loads <= 2) for ts in split_positive(rng, self.load, self.n_loads)]
         modules += [RenewableModule(time_series=ts) for ts in split_positive(rng, self.pv, self.n_pvs)]
+        if callable(library):          # resolved when a test runs, not when the module is collected
+            library = library()
         kw = {} if library is None else {"_library": library}
         self.microgrid = pymgrid_b200.Microgrid(modules, **kw)
         if shaped:      # rebuilt from the first microgrid's own modules, slack module included
