@@ -62,7 +62,7 @@ enum {
 /* per-env event flags: where the reference raises (or, with raise_errors=False, silently clips) */
 enum {
     MG_FLAG_GENSET_GOAL_RANGE = 1u << 0, /* AssertionError genset_module.py:147                         */
-    MG_FLAG_GENSET_AS_SINK = 1u << 1,    /* AssertionError genset_module.py:208                         */
+    MG_FLAG_GENSET_AS_SINK = 1u << 1,    /* TypeError base_module.py:265 (max_consumption is NotImplemented) */
     MG_FLAG_BALANCE = 1u << 2,           /* RuntimeError   microgrid.py:321-323                         */
     MG_FLAG_BATTERY_MIN_CAP = 1u << 3,   /* AssertionError battery_module.py:128                        */
     MG_FLAG_NEGATIVE_ABSORB = 1u << 4,   /* AssertionError base_module.py:272; priority_list.py:124     */

@@ -45,7 +45,7 @@ enum {
 /* additional per-env flag bits (beside MG_FLAG_*) */
 #define MGC_FLAG_CLIP 0x100u            /* some module clipped the request to its limits (base_module.py:213-224, 265-270)   */
 #define MGC_FLAG_CLIP_RAISES 0x800u     /* ... and that module was built with raise_errors=True: ValueError, :79-93          */
-#define MGC_FLAG_NOT_A_SINK 0x2u        /* a source-only module was asked to absorb: AssertionError (= MG_FLAG_GENSET_AS_SINK) */
+#define MGC_FLAG_NOT_A_SINK 0x2u        /* a source-only module was asked to absorb: TypeError, base_module.py:265 (= MG_FLAG_GENSET_AS_SINK) */
 
 /*
  * One module of the composition.  The array is in DISPATCH order -- fixed modules, then controllable, then flex, each in
@@ -146,6 +146,14 @@ int mgc_run(MgcHandle *h, const MgcIO *io, int32_t n_steps, int32_t ring, int no
  * the env untouched (reward NaN).
  */
 int mgc_run_discrete(MgcHandle *h, const MgcIO *io, int32_t n_steps, int32_t ring, void *stream);
+/*
+ * mgc_modules_step -- BaseMicrogridModule.step(action, normalized) (modules/base/base_module.py:95-159) for every module of
+ * the composition on its own: the reference's operator API without a Microgrid around it.  io->actions: [n, W] with one
+ * column per module in dispatch order (load: none; renewable, battery, grid, unbalanced: one; genset: goal, energy).  No
+ * energy balance: the flex modules act on THEIR action like everyone else.  reward = sum of the modules' rewards, `info` the
+ * per-module slots; one step per call.
+ */
+int mgc_modules_step(MgcHandle *h, const MgcIO *io, int normalized, void *stream);
 /* mgc_reset -- Microgrid.reset (microgrid.py:205-225): step = initial_step for the masked envs; battery and genset
  * state stay; writes every env's observation when io->obs is not NULL. */
 int mgc_reset(MgcHandle *h, const MgcIO *io, void *stream);

@@ -58,7 +58,7 @@ class MgcIO(C.Structure):
 
 
 EXPORTED_SYMBOLS = ("mgc_abi_version", "mgc_sizeof", "mgc_param_count", "mgc_create", "mgc_destroy", "mgc_run",
-                    "mgc_run_discrete", "mgc_reset", "mgc_observe", "mgc_launch_count")
+                    "mgc_run_discrete", "mgc_modules_step", "mgc_reset", "mgc_observe", "mgc_launch_count")
 MAX_PRIORITY_ELEMENTS = 8       # (elements)! permutations are enumerated like the reference does (priority_list.py:15-38)
 FLAG_BAD_ACTION = 1 << 6
 
@@ -74,6 +74,7 @@ def bind(L):
     L.mgc_destroy.argtypes = [_vp]
     L.mgc_run.argtypes = [_vp, C.POINTER(MgcIO), _i32, _i32, C.c_int, _vp]
     L.mgc_run_discrete.argtypes = [_vp, C.POINTER(MgcIO), _i32, _i32, _vp]
+    L.mgc_modules_step.argtypes = [_vp, C.POINTER(MgcIO), C.c_int, _vp]
     L.mgc_reset.argtypes = [_vp, C.POINTER(MgcIO), _vp]
     L.mgc_observe.argtypes = [_vp, C.POINTER(MgcIO), _vp]
     L.mgc_launch_count.restype, L.mgc_launch_count.argtypes = C.c_int64, [_vp]
@@ -109,6 +110,8 @@ class Composition:
             raise TypeError("modules must be list-like of modules.")
         import copy
         named = [(name, copy.copy(m)) for name, m in _named(list(modules))]      # microgrid.py:165 works on copies too
+        for _, m in named:
+            m.__dict__.pop("_runner", None)       # a standalone runner (module.step()) belongs to the caller's object only
         if add_unbalanced_module:       # appended un-named -> 'balancing' (microgrid.py:170-171)
             named.append(("balancing", UnbalancedEnergyModule(raise_errors=False, loss_load_cost=loss_load_cost,
                                                              overgeneration_cost=overgeneration_cost)))
@@ -465,6 +468,21 @@ class ComposedBatch:
             self._check(self._L.mgc_run(self._handle, C.byref(io), 1, 1, int(bool(normalized)), self._stream()), "mgc_run")
         return (self.obs if obs else None), self.reward, self.done, self.info
 
+    def modules_step(self, actions=None, normalized=True, obs=True):
+        """BaseMicrogridModule.step for every module on its own (mgc_modules_step): `actions` [B, W], one column per module in
+        dispatch order (load: none; renewable, battery, grid, slack: one; genset: goal, energy).  No energy balance."""
+        W = sum(2 if s.kind == "genset" else 0 if s.kind == "load" else 1 for s in self.comp.slots)
+        a = None
+        if W:
+            a = torch.as_tensor(actions, dtype=torch.float64, device=self.device).contiguous()
+            if tuple(a.shape) != (self.n_envs, W):
+                raise ValueError(f"actions must have shape {(self.n_envs, W)}, got {tuple(a.shape)}")
+        io = MgcIO(a.data_ptr() if a is not None else None, self.obs.data_ptr() if obs else None, self.reward.data_ptr(),
+                   self.done.data_ptr(), self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None)
+        with self._on_device():
+            self._check(self._L.mgc_modules_step(self._handle, C.byref(io), int(bool(normalized)), self._stream()), "mgc_modules_step")
+        return (self.obs if obs else None), self.reward, self.done, self.info
+
     def _dactions(self, actions, lead):
         if self.action_lists is None:
             raise NotImplementedError("this composition has no discrete action table (no controllable module, or more than "
@@ -537,6 +555,17 @@ class ComposedBatch:
         with self._on_device():
             self._check(self._L.mgc_observe(self._handle, C.byref(io), self._stream()), "mgc_observe")
         return self.obs
+
+
+def _raise_for(flags):
+    """the reference's exceptions for the event bits of one env (raised after the step has been applied)"""
+    if flags & FLAG_NOT_A_SINK:     # a source-only module asked to absorb: as_sink compares with max_consumption, which such a
+        # module does not implement (base_module.py:265, :604-619)
+        raise TypeError("'>' not supported between instances of 'float' and 'NotImplementedType'")
+    if flags & (FLAG_GENSET_GOAL_RANGE | FLAG_BATTERY_MIN_CAP | FLAG_NEGATIVE_ABSORB):
+        raise AssertionError(f"step rejected (flags {flags:#x})")
+    if flags & FLAG_CLIP_RAISES:
+        raise ValueError("requested value outside the module's limits")                            # base_module.py:79-93
 
 
 # ---- B = 1: the reference's Microgrid surface ---------------------------------------------------------------------------
@@ -942,10 +971,7 @@ class ComposedMicrogrid:
         row = self._log_row(pre, info, reward, shaped)
         stale = self.__dict__.pop("_stale_forecast", None)
         self._log_rows.append(row if stale is None else views.drop_stale_forecasts(row, stale))
-        if flags & (FLAG_GENSET_GOAL_RANGE | FLAG_NOT_A_SINK | FLAG_BATTERY_MIN_CAP | FLAG_NEGATIVE_ABSORB):
-            raise AssertionError(f"step rejected (flags {flags:#x})")
-        if flags & FLAG_CLIP_RAISES:
-            raise ValueError("requested value outside the module's limits")                        # base_module.py:79-93
+        _raise_for(flags)
         if flags & FLAG_BALANCE:
             raise RuntimeError("Microgrid modules unable to balance energy production with consumption.\n")
         return (self._obs_dict(b.obs[0].cpu().numpy(), comp.dispatch), shaped, bool(b.done[0].item()), self._info_dict(info))
@@ -1367,3 +1393,51 @@ class ComposedRuleBasedControl:
     flex = property(lambda self: self._microgrid.flex)
     modules = property(lambda self: self._microgrid.modules)
     priority_list = property(lambda self: self._priority_list)
+
+
+# ---- a module on its own: the reference's operator API (BaseMicrogridModule.step / reset / state) ------------------------
+_STANDALONE_LIBRARY = None      # test hook: the host build of the C source (tests/hostsim); None = the CUDA library
+
+
+class StandaloneModule:
+    """`module.step(action, normalized)` without a Microgrid around it (modules/base/base_module.py:95-159; the reference's
+    module-level tests use its modules this way): a batch of one holding just this module, stepped by mgc_modules_step.
+    Built lazily by pymgrid_b200.modules' classes on the first `step()` / `reset()` / live-attribute access."""
+
+    def __init__(self, record, device=None):
+        name = record.module_type[0]
+        self.mg = ComposedMicrogrid([(name, record)], add_unbalanced_module=False, obs_order="container", device=device,
+                                    _library=_STANDALONE_LIBRARY)
+        self.view = self.mg.modules[name][0]
+        self.kind = record.module_type[0]
+        self.width = 2 if self.kind == "genset" else 0 if self.kind == "load" else 1
+        self.log_rows = []
+
+    def step(self, action, normalized=True):
+        b = self.mg._batch
+        row = None
+        if self.width:
+            try:
+                arr = np.asarray(action, dtype=np.float64).reshape(-1)
+            except (TypeError, ValueError):
+                raise ValueError(f'Bad action {action}')
+            if arr.size != self.width:
+                raise ValueError(f'Bad action {action}')
+            row = arr.reshape(1, -1)
+        pre = self.view.state_dict()
+        b.modules_step(row, normalized=normalized)
+        flags = int(b.flags[0].item()) & 0xffffffff
+        if flags & FLAG_STEP_PAST_END:
+            raise IndexError(f"index {self.mg.current_step} is out of bounds for axis 0 with size {len(self.mg)}")
+        _raise_for(flags)
+        info = b.info[0].cpu().numpy()
+        reward = float(b.reward[0].item())
+        full = self.mg._log_row([pre], info, reward)
+        self.log_rows.append(OrderedDict((k[2], v) for k, v in full.items() if k[0] != "balance"))
+        return (b.obs[0].cpu().numpy().copy(), reward, bool(b.done[0].item()), self.mg._info_dict(info)[self.view.name[0]][0])
+
+    def reset(self):
+        """BaseMicrogridModule.reset (base_module.py:65-77): step = initial_step, log flushed, normalised state returned"""
+        obs = self.mg._batch.reset()[0].cpu().numpy().copy()
+        self.log_rows = []
+        return obs

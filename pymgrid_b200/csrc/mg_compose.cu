@@ -35,6 +35,7 @@
 struct MgcLaunch {
     MgcModule mod[MGC_MAX_MODULES];
     int32_t n_mod, n_act, obs_dim, n_fstate, n_istate, cfg_stride, T, n_envs;
+    int32_t n_act_modules;      // action columns of mgc_modules_step: one per non-fixed module, two per genset
     const double *cfg;
     const double *series;
     const int64_t *series_off;
@@ -52,7 +53,7 @@ struct MgcLaunch {
     int32_t mode, n_steps, ring, normalized;
 };
 
-enum { MGC_MODE_RUN = 0, MGC_MODE_RESET = 1, MGC_MODE_OBSERVE = 2, MGC_MODE_RUN_DISCRETE = 3 };
+enum { MGC_MODE_RUN = 0, MGC_MODE_RESET = 1, MGC_MODE_OBSERVE = 2, MGC_MODE_RUN_DISCRETE = 3, MGC_MODE_MODULES = 4 };
 
 #ifdef MGC_HOSTSIM
 #define MGC_DEV static inline
@@ -75,13 +76,14 @@ MGC_DEV MgcView mgc_view(const MgcLaunch &P, int e) {
 // phase 1 of a step for env e (one thread)
 MGC_DEV void mgc_owner(const MgcLaunch &P, int e, int s) {
     MgcView V = mgc_view(P, e);
-    if (P.mode == MGC_MODE_RUN || P.mode == MGC_MODE_RUN_DISCRETE) {
+    if (P.mode == MGC_MODE_RUN || P.mode == MGC_MODE_RUN_DISCRETE || P.mode == MGC_MODE_MODULES) {
         int32_t t = P.step[e];
         uint32_t flags = 0;
         double reward;
         uint8_t done;
         const int64_t slot = (int64_t)s * P.n_envs + e;
-        const double *action = P.io.actions ? P.io.actions + slot * P.n_act : nullptr;
+        const int act_width = (P.mode == MGC_MODE_MODULES) ? P.n_act_modules : P.n_act;
+        const double *action = P.io.actions ? P.io.actions + slot * act_width : nullptr;
         double *info = P.io.info ? P.io.info + (int64_t)e * (P.n_mod * MGC_INFO_SLOTS + MGC_BALANCE_SLOTS) : nullptr;
         double *fstate = P.fstate + (int64_t)e * P.n_fstate;
         int32_t *istate = P.istate + (int64_t)e * P.n_istate;
@@ -103,7 +105,8 @@ MGC_DEV void mgc_owner(const MgcLaunch &P, int e, int s) {
             normalized = 0;
         }
         const int final_step = P.env_final ? P.env_final[e] : (int)V.cfg[1];
-        if (!skip) mgc_env_step(V, t, fstate, istate, action, normalized, final_step, &reward, &done, info, &flags);
+        if (P.mode == MGC_MODE_MODULES) mgc_modules_step(V, t, fstate, istate, action, normalized, final_step, &reward, &done, info, &flags);
+        else if (!skip) mgc_env_step(V, t, fstate, istate, action, normalized, final_step, &reward, &done, info, &flags);
         P.step[e] = t;
         P.io.reward[slot] = reward;
         P.io.done[slot] = done;
@@ -314,6 +317,8 @@ extern "C" int mgc_create(const MgcLayout *L, MgcHandle **out) {
     MgcLaunch &B = h->base;
     memset(&B, 0, sizeof B);
     B.elem = h->elem;
+    for (int m = 0; m < L->n_modules; ++m)
+        B.n_act_modules += (L->modules[m].kind == MGC_GENSET) ? 2 : (L->modules[m].kind == MGC_LOAD) ? 0 : 1;
     memcpy(B.mod, L->modules, sizeof(MgcModule) * (size_t)L->n_modules);
     B.n_mod = L->n_modules; B.n_act = L->n_act; B.obs_dim = L->obs_dim; B.n_fstate = L->n_fstate; B.n_istate = L->n_istate;
     B.cfg_stride = L->cfg_stride; B.T = L->series_len; B.n_envs = (int32_t)L->n_envs;
@@ -343,6 +348,9 @@ static int mgc_launch(MgcHandle *h, const MgcIO *io, int mode, int32_t n_steps, 
         if (n_steps < 1 || ring < 1) return mgc_fail(MG_E_INVALID, "mgc_run: n_steps and ring must be >= 1");
         if (!io->reward || !io->done) return mgc_fail(MG_E_INVALID, "mgc_run: reward and done are required");
         if (P.n_act > 0 && !io->actions) return mgc_fail(MG_E_INVALID, "mgc_run: actions are required (n_act > 0)");
+    } else if (mode == MGC_MODE_MODULES) {
+        if (!io->reward || !io->done) return mgc_fail(MG_E_INVALID, "mgc_modules_step: reward and done are required");
+        if (P.n_act_modules > 0 && !io->actions) return mgc_fail(MG_E_INVALID, "mgc_modules_step: actions are required");
     } else if (mode == MGC_MODE_RUN_DISCRETE) {
         if (n_steps < 1 || ring < 1) return mgc_fail(MG_E_INVALID, "mgc_run_discrete: n_steps and ring must be >= 1");
         if (!io->reward || !io->done || !io->dactions) return mgc_fail(MG_E_INVALID, "mgc_run_discrete: reward, done and dactions are required");
@@ -373,6 +381,9 @@ extern "C" int mgc_run(MgcHandle *h, const MgcIO *io, int32_t n_steps, int32_t r
 }
 extern "C" int mgc_run_discrete(MgcHandle *h, const MgcIO *io, int32_t n_steps, int32_t ring, void *stream) {
     return mgc_launch(h, io, MGC_MODE_RUN_DISCRETE, n_steps, ring, 0, stream);
+}
+extern "C" int mgc_modules_step(MgcHandle *h, const MgcIO *io, int normalized, void *stream) {
+    return mgc_launch(h, io, MGC_MODE_MODULES, 1, 1, normalized, stream);
 }
 extern "C" int mgc_reset(MgcHandle *h, const MgcIO *io, void *stream) { return mgc_launch(h, io, MGC_MODE_RESET, 1, 1, 0, stream); }
 extern "C" int mgc_observe(MgcHandle *h, const MgcIO *io, void *stream) { return mgc_launch(h, io, MGC_MODE_OBSERVE, 1, 1, 0, stream); }

@@ -416,6 +416,68 @@ MGC_HD void mgc_env_step(const MgcView &V, int32_t &t, double *fstate, int32_t *
 }
 
 /*
+ * BaseMicrogridModule.step(action, normalized) (base_module.py:95-159; GensetModule.step, genset_module.py:100-149) for
+ * every module of the composition ON ITS OWN -- the reference's operator API used without a Microgrid around it (its
+ * module-level tests do): each module takes its own action columns (load: none; renewable, battery, grid, unbalanced: one;
+ * genset: goal, energy), normalised actions are mapped through the module's action bounds (utils/space.py:220-231;
+ * renewable: its series bounds, base_timeseries_module.py:81-88; unbalanced: (-inf, inf)), then as_source / as_sink /
+ * update run as in mgc_module_step.  No energy balance, no flex split.  Columns are assigned in dispatch order.
+ */
+MGC_HD void mgc_modules_step(const MgcView &V, int32_t &t, double *fstate, int32_t *istate, const double *action, int normalized,
+                             int final_step, double *reward_out, uint8_t *done_out, double *info, uint32_t *flags) {
+    MgcStepAcc A;
+    A.n_provided = A.n_absorbed = 0;
+    A.reward = 0.0;
+    A.done = 0;
+    A.flags = 0;
+    const int t0 = t, n = V.n_mod;
+    bool any_series = false;
+    for (int m = 0; m < n; ++m) any_series |= mgc_is_timeseries(V.mod[m].kind);
+    if (any_series && t0 >= V.T) {
+        *reward_out = NAN;
+        *done_out = 1;
+        *flags |= MG_FLAG_STEP_PAST_END;
+        return;
+    }
+    if (info)
+        for (int i = 0; i < n * MGC_INFO_SLOTS + MGC_BALANCE_SLOTS; ++i) info[i] = 0.0;
+    const int ts_done = (t0 >= final_step - 1);
+    int col = 0;
+    for (int m = 0; m < n; ++m) {
+        const MgcModule &M = V.mod[m];
+        const double *p = V.cfg + M.param_off;
+        const double *c = action + col;
+        double a = 0.0;
+        switch (M.kind) {
+        case MGC_GENSET: {
+            const double goal = c[0];
+            int32_t *s = istate + M.istate_off;
+            if (!(0 <= goal && goal <= 1)) A.flags |= MG_FLAG_GENSET_GOAL_RANGE;
+            else {
+                int cs = s[0], gs = s[1], up = s[2], dn = s[3];
+                mgc_genset_update_status(cs, gs, up, dn, goal, (int)p[5], (int)p[6], p[7] != 0.0);
+                s[0] = cs; s[1] = gs; s[2] = up; s[3] = dn;
+            }
+            a = normalized ? mgc_denormalize(c[1], 0.0, p[1]) : c[1];
+            col += 2;
+            break;
+        }
+        case MGC_BATTERY: a = normalized ? mgc_denormalize(c[0], -p[3] / p[4], p[2] * p[4]) : c[0]; col += 1; break;
+        case MGC_GRID: a = normalized ? mgc_denormalize(c[0], -1 * p[2], p[1]) : c[0]; col += 1; break;
+        case MGC_RENEWABLE: a = normalized ? mgc_denormalize(c[0], p[1], p[2]) : c[0]; col += 1; break;
+        case MGC_UNBALANCED: a = normalized ? mgc_denormalize(c[0], -mgc_inf(), mgc_inf()) : c[0]; col += 1; break;
+        default: break;      /* load: fixed, takes no action */
+        }
+        mgc_module_step(V, m, a, t0, fstate, istate, A, info);
+        if (mgc_is_timeseries(M.kind)) A.done |= ts_done;
+    }
+    t = t0 + 1;
+    *reward_out = A.reward;
+    *done_out = (uint8_t)(A.done != 0);
+    *flags |= A.flags;
+}
+
+/*
  * PriorityListAlgo._populate_action (algos/priority_list/priority_list.py:69-167) for one env: expand one priority list --
  * `width` elements (dispatch index of a controllable module, action number), negative module = padding -- into the
  * UNNORMALISED action row `ctl` (n_act doubles) that Microgrid.run(normalized=False) then takes.

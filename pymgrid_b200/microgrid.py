@@ -583,6 +583,9 @@ class Microgrid:
         err = flags & FLAG_ERROR_MASK
         if err:
             names = [n for bit, n in FLAG_NAMES.items() if err & bit]
+            if err & (1 << 1):      # a genset asked to absorb: as_sink compares with max_consumption, which a source-only
+                # module does not implement (base_module.py:265, :604-619)
+                raise TypeError("'>' not supported between instances of 'float' and 'NotImplementedType'")
             if err & (1 << 2):
                 raise RuntimeError("Microgrid modules unable to balance energy production with consumption.\n")
             raise AssertionError(f"step rejected: {names}")

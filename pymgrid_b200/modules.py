@@ -34,6 +34,42 @@ class _Module:
         keys = [k for k in vars(self) if not k.startswith("_") and k not in ("name", "time_series")]
         return f"{type(self).__name__}(" + ", ".join(f"{k}={getattr(self, k)!r}" for k in keys) + ")"
 
+    # ---- the module on its own: the reference's operator API (modules/base/base_module.py:65-159) -----------------------
+    # Inside a Microgrid a module is a parameter record (the kernels step all modules of a microgrid together).  Used
+    # without one -- module.step(action), module.reset(), module.state, as the reference's module-level tests do -- it gets
+    # a one-module device batch of its own (compose.StandaloneModule) on first use and is stepped by mgc_modules_step.
+    _LIVE = ("state", "current_step", "current_charge", "soc", "current_status", "goal_status", "max_production",
+             "min_production", "max_consumption", "current_load", "current_renewable", "min_obs", "max_obs", "min_act", "max_act",
+             "production_marginal_cost", "absorption_marginal_cost", "marginal_cost", "import_price", "export_price",
+             "co2_per_kwh", "grid_status", "action_space", "is_source", "is_sink")
+
+    def _standalone(self):
+        runner = self.__dict__.get("_runner")
+        if runner is None:
+            from .compose import StandaloneModule
+            runner = self.__dict__["_runner"] = StandaloneModule(self)
+        return runner
+
+    def step(self, action, normalized=True):
+        """reference: BaseMicrogridModule.step (base_module.py:95-159) -> (normalised state after the step, reward, done, info)"""
+        return self._standalone().step(action, normalized=normalized)
+
+    def reset(self):
+        return self._standalone().reset()
+
+    def state_dict(self, normalized=False):
+        return self._standalone().view.state_dict(normalized=normalized)
+
+    def log_dict(self):
+        """reference: BaseMicrogridModule.log_dict: {field: [value per step]} since the last reset"""
+        rows = self._standalone().log_rows
+        return {k: [r[k] for r in rows] for k in (rows[0] if rows else {})}
+
+    def __getattr__(self, item):
+        if item in type(self)._LIVE:
+            return getattr(self._standalone().view, item)
+        raise AttributeError(item)
+
 
 class BatteryModule(_Module):
     """reference: modules/battery_module.py:66-106 (constructor, `_init_battery`)."""

@@ -359,3 +359,41 @@ def check_observation_keys(lib):
     log = env.log
     assert [list(c) for c in log.columns] == json.loads(str(z["envlog_composed_columns"]))
     assert np.array_equal(log.to_numpy(dtype=np.float64), z["envlog_composed_values"], equal_nan=True)
+
+
+# ---- modules on their own: BaseMicrogridModule.step / reset / state (the reference's operator API) ----------------------
+def check_standalone_module_steps(lib):
+    """module.step(action, normalized) on pymgrid_b200.modules' objects without a Microgrid, against the live reference's
+    recorded outputs (tests/golden/make_module_steps.py): observation, reward, done, info, state, exception type"""
+    import importlib.util
+    import os
+    import pymgrid_b200.compose as cp
+    from pymgrid_b200 import modules as M
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_module_steps", os.path.join(here, "golden", "make_module_steps.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    z = np.load(os.path.join(here, "golden", "module_steps.npz"))
+    saved, cp._STANDALONE_LIBRARY = cp._STANDALONE_LIBRARY, lib
+    try:
+        rng = np.random.default_rng(5)
+        for label, cls, kwargs in mk.specs():
+            acts = mk.actions_for(label, cls, kwargs, rng)
+            got = mk.run(getattr(M, cls)(**kwargs), cls, acts)
+            for key, value in got.items():
+                want = z[f"{label}_{key}"]
+                if value.dtype.kind in "US":
+                    assert str(value) == str(want), (label, key)
+                else:
+                    assert np.array_equal(value, want, equal_nan=True), (label, key)
+        # the reference's genset known answers (tests/microgrid/modules/module_tests/test_genset_module.py:64-163)
+        genset = M.GensetModule(running_min_production=10, running_max_production=50, genset_cost=0.5)
+        obs, reward, done, info = genset.step(np.array([1.0, 20.0]), normalized=False)
+        assert reward == -10.0 and not done and info["provided_energy"] == 20.0 and list(obs) == [1, 1, 0, 0]
+        obs, reward, done, info = genset.step(np.array([1.0, 5.0]), normalized=False)         # below running_min: clamped up
+        assert info["provided_energy"] == 10.0 and reward == -5.0
+        obs, reward, done, info = genset.step(np.array([0.0, 30.0]), normalized=False)        # switched off: nothing produced
+        assert info["provided_energy"] == 0.0 and reward == 0.0 and genset.current_status == 0
+        assert genset.log_dict()["genset_production"] == [20.0, 10.0, 0.0]
+    finally:
+        cp._STANDALONE_LIBRARY = saved

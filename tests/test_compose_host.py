@@ -130,3 +130,7 @@ def test_set_forecaster_and_set_module_attr(lib):
 
 def test_env_observation_keys(lib):
     K.check_observation_keys(lib)
+
+
+def test_standalone_module_steps(lib):
+    K.check_standalone_module_steps(lib)

@@ -214,3 +214,54 @@ def test_random_compositions_priority_lists_against_the_live_reference():
         compared += 1
     print(f"{compared} compositions, {steps} discrete steps compared")
     assert compared >= 10 and steps > 100
+
+
+def test_random_modules_on_their_own_against_the_live_reference():
+    """BaseMicrogridModule.step on randomly parameterised modules of every kind, used without a Microgrid: observation,
+    reward, done, info and the exception types, side by side with the live reference"""
+    from oracle.ref_loader import load_reference
+    load_reference()
+    import pymgrid.modules as R
+    import pymgrid_b200.compose as cp
+    from pymgrid_b200 import modules as M
+    saved, cp._STANDALONE_LIBRARY = cp._STANDALONE_LIBRARY, ctypes.CDLL(hostsim.build())
+    compared = raised = 0
+    try:
+        for g in range(25):
+            T = 30
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref_mods, our_mods = draw(np.random.default_rng(5000 + g), R, T), draw(np.random.default_rng(5000 + g), M, T)
+            rng = np.random.default_rng(g)
+            for a, b in zip(ref_mods, our_mods):
+                a, b = (a[1] if isinstance(a, tuple) else a), (b[1] if isinstance(b, tuple) else b)
+                kind = type(a).__name__
+                for k in range(T + 1):
+                    normalized = bool(rng.integers(0, 2)) and kind != "UnbalancedEnergyModule"
+                    if kind == "LoadModule":
+                        act = np.array([])
+                    elif kind == "GensetModule":
+                        act = np.array([rng.random(), rng.random() if normalized else rng.uniform(0, 1.5 * a.running_max_production)])
+                    else:
+                        lo, hi = (0.0, 1.0) if normalized else ((-60.0, 60.0) if kind != "RenewableModule" else (0.0, 250.0))
+                        act = float(rng.uniform(lo - 0.1 * (hi - lo) * (not normalized), hi))
+                    outs = []
+                    for mod in (a, b):
+                        try:
+                            with warnings.catch_warnings():
+                                warnings.simplefilter("ignore")
+                                outs.append(mod.step(act, normalized=normalized))
+                        except Exception as exc:      # noqa: BLE001
+                            outs.append(type(exc).__name__)
+                    if isinstance(outs[0], str) or isinstance(outs[1], str):
+                        assert outs[0] == outs[1], (g, kind, k, outs)
+                        raised += 1
+                        break
+                    (o0, r0, d0, i0), (o1, r1, d1, i1) = outs
+                    assert r0 == r1 and d0 == d1 and dict(i0) == dict(i1), (g, kind, k, r0, r1, i0, i1)
+                    assert np.array_equal(np.asarray(o0, dtype=np.float64).ravel(), o1), (g, kind, k)
+                    compared += 1
+    finally:
+        cp._STANDALONE_LIBRARY = saved
+    print(f"{compared} module steps compared, {raised} runs ended where the reference raised")
+    assert compared > 2000 and raised > 20

@@ -104,3 +104,7 @@ def test_set_forecaster_and_set_module_attr_on_gpu():
 
 def test_env_observation_keys_on_gpu():
     K.check_observation_keys(None)
+
+
+def test_standalone_module_steps_on_gpu():
+    K.check_standalone_module_steps(None)
