@@ -16,4 +16,13 @@ def __getattr__(name):
     if name in ("DiscreteMicrogridEnv", "ContinuousMicrogridEnv"):
         from . import envs
         return getattr(envs, name)
+    if name in ("ComposedBatch", "ComposedMicrogrid", "Composition"):      # any module list (include/pymgrid_b200_compose.h)
+        from . import compose
+        return getattr(compose, name)
+    if name == "RuleBasedControl":
+        from .algos import RuleBasedControl
+        return RuleBasedControl
+    if name in ("algos", "compose", "engine", "envs", "generator", "microgrid", "modules", "trajectory", "views"):
+        import importlib
+        return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)
