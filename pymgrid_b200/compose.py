@@ -668,6 +668,19 @@ class ComposedModuleView:
             return np.inf
         return 0.0
 
+    # genset look-ahead (genset_module.py:360-424): the status / limits one step after asking for `goal_status`
+    def next_status(self, goal_status):
+        cs, _, up, dn = (int(x) for x in self._state()[2])
+        if goal_status:
+            return 1 if (cs or up == 0) else 0
+        return 0 if (not cs or dn == 0) else 1
+
+    def next_max_production(self, goal_status):
+        return self.next_status(goal_status) * self._r.running_max_production
+
+    def next_min_production(self, goal_status):
+        return self.next_status(goal_status) * self._r.running_min_production
+
     @property
     def production_marginal_cost(self):
         k, r = self._s.kind, self._r

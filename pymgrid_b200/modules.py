@@ -41,7 +41,8 @@ class _Module:
     _LIVE = ("state", "current_step", "current_charge", "soc", "current_status", "goal_status", "max_production",
              "min_production", "max_consumption", "current_load", "current_renewable", "min_obs", "max_obs", "min_act", "max_act",
              "production_marginal_cost", "absorption_marginal_cost", "marginal_cost", "import_price", "export_price",
-             "co2_per_kwh", "grid_status", "action_space", "is_source", "is_sink")
+             "co2_per_kwh", "grid_status", "action_space", "is_source", "is_sink", "next_status", "next_max_production",
+             "next_min_production")
 
     def _standalone(self):
         runner = self.__dict__.get("_runner")

@@ -395,5 +395,17 @@ def check_standalone_module_steps(lib):
         obs, reward, done, info = genset.step(np.array([0.0, 30.0]), normalized=False)        # switched off: nothing produced
         assert info["provided_energy"] == 0.0 and reward == 0.0 and genset.current_status == 0
         assert genset.log_dict()["genset_production"] == [20.0, 10.0, 0.0]
+        # the reference's exhaustive look-ahead check (test_genset_long_status_changes.py:217-262): the status next_status()
+        # predicts for a goal is the status after stepping with that goal, for every start-up / wind-down time, both initial
+        # states and every goal sequence
+        import itertools
+        for U, D, init in itertools.product(range(3), range(3), (True, False)):
+            for goals in itertools.product((0, 1), repeat=4):
+                g = M.GensetModule(10, 50, 0.5, start_up_time=U, wind_down_time=D, init_start_up=init)
+                for goal in goals:
+                    predicted = g.next_status(goal)
+                    assert g.next_max_production(goal) == predicted * 50 and g.next_min_production(goal) == predicted * 10
+                    g.step(np.array([goal, 0.0]), normalized=False)
+                    assert g.current_status == predicted, (U, D, init, goals)
     finally:
         cp._STANDALONE_LIBRARY = saved
