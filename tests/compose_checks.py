@@ -395,6 +395,28 @@ def check_standalone_module_steps(lib):
         obs, reward, done, info = genset.step(np.array([0.0, 30.0]), normalized=False)        # switched off: nothing produced
         assert info["provided_energy"] == 0.0 and reward == 0.0 and genset.current_status == 0
         assert genset.log_dict()["genset_production"] == [20.0, 10.0, 0.0]
+        # what the reference's time-series module tests pin (module_tests/timeseries_modules.py:10-100, test_load_module.py,
+        # test_renewable_module.py): on the series 2 - cos(pi t / 2), with and without a 24-step forecast, the state is the
+        # window of the series, observations stay in [0, 1] until done, bounds are (min(0, ts), max(0, ts))
+        wave = 2 - np.cos(np.pi * np.arange(100) / 2)
+        for horizon in (0, 24):
+            kw = dict(forecaster="oracle", forecast_horizon=horizon) if horizon else {}
+            for cls, sign, given in ((M.LoadModule, -1, wave), (M.LoadModule, -1, -wave), (M.RenewableModule, 1, wave), (M.RenewableModule, 1, -wave)):
+                module = cls(time_series=given, **kw)
+                assert np.array_equal(module.state, sign * wave[:1 + horizon]) and len(module.state_dict()) == 1 + horizon
+                assert module.min_obs.tolist() == [min(0, (sign * wave).min())] * (1 + horizon)
+                assert module.max_obs.tolist() == [max(0, (sign * wave).max())] * (1 + horizon)
+                done, steps = False, 0
+                while not done:
+                    act = np.array([]) if cls is M.LoadModule else float(np.random.default_rng(steps).uniform(0, 3))
+                    obs, reward, done, info = module.step(act, normalized=False)
+                    assert ((0 <= obs) & (obs <= 1)).all() and reward == 0.0 and obs.shape == (1 + horizon,)
+                    if cls is M.LoadModule:
+                        assert info == {"absorbed_energy": wave[steps]}
+                    else:
+                        assert info["provided_energy"] == min(act, wave[steps]) and info["curtailment"] == wave[steps] - info["provided_energy"]
+                    steps += 1
+                assert steps == 100 == module.current_step      # done is reported by the step taken AT final_step - 1 (base_timeseries_module.py:124-125)
         # the reference's exhaustive look-ahead check (test_genset_long_status_changes.py:217-262): the status next_status()
         # predicts for a goal is the status after stepping with that goal, for every start-up / wind-down time, both initial
         # states and every goal sequence
