@@ -187,6 +187,10 @@ class Composition:
                 raise NotImplementedError("composed microgrids run the oracle forecaster (or none); Gaussian-noise forecasts "
                                           "are built for the fused module set only")
 
+    def records_named(self):
+        """[(name, record)] in listing order: what rebuilds the same microgrid (add_unbalanced_module=False)"""
+        return [(s.name, r) for s, r in zip(self.slots, self.records)]
+
     @property
     def signature(self):
         """what B microgrids must share to be stepped as one batch"""
@@ -483,6 +487,10 @@ class ComposedBatch:
             self._check(self._L.mgc_modules_step(self._handle, C.byref(io), int(bool(normalized)), self._stream()), "mgc_modules_step")
         return (self.obs if obs else None), self.reward, self.done, self.info
 
+    def recorder(self, env_ids):
+        """opt-in reference-format log for a subset of the envs (see ComposedLogRecorder)"""
+        return ComposedLogRecorder(self, env_ids)
+
     def _dactions(self, actions, lead):
         if self.action_lists is None:
             raise NotImplementedError("this composition has no discrete action table (no controllable module, or more than "
@@ -581,14 +589,123 @@ class ModuleList(list):
         return self
 
 
+_STATE_NAMES = {"load": ["load"], "renewable": ["renewable"], "grid": ["import_price", "export_price", "co2_per_kwh", "grid_status"]}
+_ENERGY_NAMES = {"load": (None, "load_met"), "renewable": ("renewable_used", None), "battery": ("discharge_amount", "charge_amount"),
+                 "genset": ("genset_production", None), "grid": ("grid_import", "grid_export"), "balancing": ("loss_load", "overgeneration")}
+
+
+def slot_state_dict(s, r, t, f, i):
+    """unnormalised state of module slot `s` (record `r`) at step t: `f` = its two battery doubles, `i` = its four genset
+    integers (None for other kinds) -- the modules' _state_dict of the reference"""
+    d = OrderedDict()
+    if s.kind in _STATE_NAMES:
+        ts = r.time_series
+        if s.kind == "grid":
+            lo, hi = ts.min(axis=0), ts.max(axis=0)
+        else:
+            lo, hi = views.series_bounds(ts[:, 0], True)
+            lo, hi = np.array([lo]), np.array([hi])
+        vals = views.series_state(ts, t, s.horizon, lo, hi)
+        comps = _STATE_NAMES[s.kind]
+        keys = [f"{c}_current" for c in comps] + [f"{c}_forecast_{j}" for j in range(s.horizon) for c in comps]
+        d.update(zip(keys, (float(v) for v in vals)))
+    elif s.kind == "battery":
+        d.update(soc=float(f[1]), current_charge=float(f[0]))
+    elif s.kind == "genset":
+        d.update(current_status=int(i[0]), goal_status=int(i[1]), steps_until_up=int(i[2]), steps_until_down=int(i[3]))
+    return d
+
+
+def log_row_from(comp, records, t, fstate, istate_pre, istate_post, info, reward, shaped=None):
+    """One row of Microgrid.get_log() (base_module.py:276-290 per module, microgrid.py:259-260, 281, 317-319 for the
+    balance) from an env's raw state rows BEFORE the step, its genset integers AFTER it (the genset logs its state after the
+    status update, genset_module.py:148-149) and its info row."""
+    row = OrderedDict()
+    for s, r in zip(comp.slots, records):
+        f = fstate[s.fstate_off:s.fstate_off + 2] if s.kind == "battery" else None
+        i = istate_post[s.istate_off:s.istate_off + 4] if s.kind == "genset" else None
+        x = info[s.listing * MGC_INFO_SLOTS:(s.listing + 1) * MGC_INFO_SLOTS]
+        key = (s.name, s.index)
+        row[key + ("reward",)] = float(x[3])
+        if s.kind in ("genset", "grid"):
+            row[key + ("co2_production",)] = float(x[2])
+        elif s.kind == "renewable":
+            row[key + ("curtailment",)] = float(x[2])
+        p_name, a_name = _ENERGY_NAMES[s.kind]
+        if p_name is not None:
+            row[key + (p_name,)] = float(x[0])
+        if a_name is not None:
+            row[key + (a_name,)] = float(x[1])
+        for k, val in slot_state_dict(s, r, t, f, i).items():
+            row[key + (k,)] = val
+    bal = info[len(comp.slots) * MGC_INFO_SLOTS:]
+    for k, val in (("reward", reward), ("shaped_reward", reward if shaped is None else shaped), ("overall_provided_to_microgrid", bal[4]),
+                   ("overall_absorbed_from_microgrid", bal[5]), ("controllable_provided_to_microgrid", bal[2]),
+                   ("controllable_absorbed_from_microgrid", bal[3]), ("fixed_provided_to_microgrid", bal[0]),
+                   ("fixed_absorbed_from_microgrid", bal[1])):
+        row[("balance", 0, k)] = float(val)
+    return row
+
+
+class ComposedLogRecorder:
+    """Opt-in reference-format log for a SUBSET of a composed batch (the full log of 65 536 envs would be hundreds of GB per
+    year): step the batch through the recorder and read `get_log(env)` -- the DataFrame Microgrid.get_log() returns
+    (microgrid.py:434-475) for each recorded env.  Host-side, from the info block and small state reads of the recorded envs."""
+
+    def __init__(self, batch, env_ids):
+        if batch.info is None:
+            raise ValueError("the recorder needs ComposedBatch(with_info=True)")
+        self.batch, self.env_ids = batch, [int(e) for e in env_ids]
+        self._idx = torch.as_tensor(self.env_ids, dtype=torch.int64, device=batch.device)
+        self.rows = {e: [] for e in self.env_ids}
+
+    def _snap(self):
+        b = self.batch
+        return (b.step_counter.index_select(0, self._idx).cpu().numpy(), b.fstate.index_select(0, self._idx).cpu().numpy(),
+                b.istate.index_select(0, self._idx).cpu().numpy())
+
+    def _record(self, pre):
+        b = self.batch
+        t, f, _ = pre
+        _, _, i_post = self._snap()
+        info = b.info.index_select(0, self._idx).cpu().numpy()
+        reward = b.reward.index_select(0, self._idx).cpu().numpy()
+        flags = b.flags.index_select(0, self._idx).cpu().numpy()
+        for k, e in enumerate(self.env_ids):
+            if int(flags[k]) & (FLAG_STEP_PAST_END | FLAG_BAD_ACTION):
+                continue            # the reference raises there and logs nothing
+            comp = b.compositions[int(b.env_config[e])]
+            self.rows[e].append(log_row_from(comp, comp.records, int(t[k]), f[k], None, i_post[k], info[k], float(reward[k])))
+
+    def step(self, actions=None, normalized=True, obs=True):
+        pre = self._snap()
+        out = self.batch.step(actions, normalized=normalized, obs=obs)
+        self._record(pre)
+        return out
+
+    def step_discrete(self, actions, obs=True):
+        pre = self._snap()
+        out = self.batch.step_discrete(actions, obs=obs)
+        self._record(pre)
+        return out
+
+    def reset(self, mask=None):
+        out = self.batch.reset(mask)
+        m = None if mask is None else np.asarray(mask.cpu() if hasattr(mask, "cpu") else mask, dtype=bool)
+        for e in self.env_ids:
+            if m is None or m[e]:
+                self.rows[e] = []
+        return out
+
+    def get_log(self, env, drop_singleton_key=False):
+        stop = int(self.batch.step_counter[int(env)].item())
+        return views.log_frame(self.rows[int(env)], stop, drop_singleton_key)
+
+
 class ComposedModuleView:
     """Read-only view of one module of a ComposedMicrogrid: constructor parameters + the live values the reference's
     callers read."""
-    _STATE_NAMES = {"load": ["load"], "renewable": ["renewable"],
-                    "grid": ["import_price", "export_price", "co2_per_kwh", "grid_status"]}
-    _ENERGY_NAMES = {"load": (None, "load_met"), "renewable": ("renewable_used", None),
-                     "battery": ("discharge_amount", "charge_amount"), "genset": ("genset_production", None),
-                     "grid": ("grid_import", "grid_export"), "balancing": ("loss_load", "overgeneration")}
+    _STATE_NAMES, _ENERGY_NAMES = _STATE_NAMES, _ENERGY_NAMES
 
     def __init__(self, microgrid, slot, record):
         self._m, self._s, self._r = microgrid, slot, record
@@ -705,19 +822,8 @@ class ComposedModuleView:
 
     def state_dict(self, normalized=False):
         """base_module.py:473-490 / the modules' _state_dict"""
-        s, r = self._s, self._r
         t, f, i = self._state()
-        d = OrderedDict()
-        if s.kind in self._STATE_NAMES:
-            lo, hi = self._series_bounds()
-            vals = views.series_state(r.time_series, t, s.horizon, lo, hi)
-            comps = self._STATE_NAMES[s.kind]
-            keys = [f"{c}_current" for c in comps] + [f"{c}_forecast_{j}" for j in range(s.horizon) for c in comps]
-            d.update(zip(keys, (float(v) for v in vals)))
-        elif s.kind == "battery":
-            d.update(soc=float(f[1]), current_charge=float(f[0]))
-        elif s.kind == "genset":
-            d.update(current_status=int(i[0]), goal_status=int(i[1]), steps_until_up=int(i[2]), steps_until_down=int(i[3]))
+        d = slot_state_dict(self._s, self._r, t, f, i)
         if normalized and d:
             lo, hi = self.min_obs, self.max_obs
             spread = np.where(hi - lo == 0, 1.0, hi - lo)
@@ -878,7 +984,8 @@ class ComposedMicrogrid:
     # ---- state ----
     def _state(self):
         b = self._batch
-        return int(b.step_counter[0].item()), b.fstate[0].cpu().numpy(), b.istate[0].cpu().numpy()
+        # copies: on a CPU tensor .numpy() is a view that the next step would change under the caller
+        return int(b.step_counter[0].item()), b.fstate[0].cpu().numpy().copy(), b.istate[0].cpu().numpy().copy()
 
     current_step = property(lambda self: int(self._batch.step_counter[0].item()))
     modules = property(lambda self: self._modules)
@@ -966,7 +1073,7 @@ class ComposedMicrogrid:
         """what the reference snapshots before stepping: every module's state for the log (base_module.py:152) and the cost
         info the reward shaper gets (microgrid.py:253)"""
         self._cost_info = self.get_cost_info() if self.reward_shaping_func is not None else None
-        return [v.state_dict() for v in self._views]
+        return self._state()
 
     def _finish_step(self, pre):
         """log row, the reference's exceptions from the event flags, and the reference's return types"""
@@ -1048,33 +1155,10 @@ class ComposedMicrogrid:
         return other
 
     def _log_row(self, pre, info, reward, shaped=None):
-        """one row of get_log(): base_module.py:276-290 per module, microgrid.py:259-260, 281, 317-319 for the balance"""
-        row = OrderedDict()
-        for v, state in zip(self._views, pre):
-            s = v._s
-            r = info[s.listing * MGC_INFO_SLOTS:(s.listing + 1) * MGC_INFO_SLOTS]
-            key = (s.name, s.index)
-            row[key + ("reward",)] = float(r[3])
-            if s.kind in ("genset", "grid"):
-                row[key + ("co2_production",)] = float(r[2])
-            elif s.kind == "renewable":
-                row[key + ("curtailment",)] = float(r[2])
-            p_name, a_name = v._ENERGY_NAMES[s.kind]
-            if p_name is not None:
-                row[key + (p_name,)] = float(r[0])
-            if a_name is not None:
-                row[key + (a_name,)] = float(r[1])
-            if s.kind == "genset":      # the genset logs its state AFTER the status update (genset_module.py:148-149)
-                state = v.state_dict()
-            for k, val in state.items():
-                row[key + (k,)] = val
-        bal = info[len(self._views) * MGC_INFO_SLOTS:]
-        for k, val in (("reward", reward), ("shaped_reward", reward if shaped is None else shaped), ("overall_provided_to_microgrid", bal[4]),
-                       ("overall_absorbed_from_microgrid", bal[5]), ("controllable_provided_to_microgrid", bal[2]),
-                       ("controllable_absorbed_from_microgrid", bal[3]), ("fixed_provided_to_microgrid", bal[0]),
-                       ("fixed_absorbed_from_microgrid", bal[1])):
-            row[("balance", 0, k)] = float(val)
-        return row
+        """one row of get_log() (log_row_from): `pre` = (t, fstate row, istate row) before the step"""
+        t, f, _ = pre
+        return log_row_from(self.composition, self.composition.records, t, f, None, self._batch.istate[0].cpu().numpy(), info,
+                            reward, shaped)
 
     def reset(self):
         """reference: Microgrid.reset (microgrid.py:205-225): modules in LISTING order, then 'balance' and 'other'"""
@@ -1437,7 +1521,7 @@ class StandaloneModule:
             if arr.size != self.width:
                 raise ValueError(f'Bad action {action}')
             row = arr.reshape(1, -1)
-        pre = self.view.state_dict()
+        pre = self.mg._state()
         b.modules_step(row, normalized=normalized)
         flags = int(b.flags[0].item()) & 0xffffffff
         if flags & FLAG_STEP_PAST_END:
@@ -1445,7 +1529,7 @@ class StandaloneModule:
         _raise_for(flags)
         info = b.info[0].cpu().numpy()
         reward = float(b.reward[0].item())
-        full = self.mg._log_row([pre], info, reward)
+        full = self.mg._log_row(pre, info, reward)
         self.log_rows.append(OrderedDict((k[2], v) for k, v in full.items() if k[0] != "balance"))
         return (b.obs[0].cpu().numpy().copy(), reward, bool(b.done[0].item()), self.mg._info_dict(info)[self.view.name[0]][0])
 

@@ -431,3 +431,41 @@ def check_standalone_module_steps(lib):
                     assert g.current_status == predicted, (U, D, init, goals)
     finally:
         cp._STANDALONE_LIBRARY = saved
+
+
+def check_batch_log_recorder(lib):
+    """ComposedBatch.recorder(env_ids): the reference-format log of selected envs of a batch == the get_log() of a single
+    microgrid stepped with the same actions (continuous and discrete steps, a masked reset in between)"""
+    kw = {} if lib is None else {"_library": lib}
+    case, batch, _ = _batch_case(lib, "several_of_each", 9, 13)
+    rec = batch.recorder([0, 4, 8])
+    singles = {e: ComposedMicrogrid(batch.compositions[int(batch.env_config[e])].records_named(), add_unbalanced_module=False,
+                                    obs_order="container", **kw) for e in (0, 4, 8)}
+    for e, mg in singles.items():        # same live state as the batch env
+        for a in ("fstate", "istate"):
+            getattr(mg._batch, a)[0].copy_(getattr(batch, a)[e])
+    rng = np.random.default_rng(2)
+    comp = batch.comp
+    n_lists = len(batch.action_lists)
+    for k in range(9):
+        if k == 5:
+            mask = np.zeros(9, dtype=np.uint8)
+            mask[4] = 1
+            rec.reset(torch.from_numpy(mask).to(batch.device))
+            singles[4].reset()
+        if k % 3 == 2:
+            d = rng.integers(0, n_lists, 9).astype(np.int32)
+            rec.step_discrete(torch.from_numpy(d).to(batch.device))
+            for e, mg in singles.items():
+                mg.run_priority_list(int(d[e]), 1)
+        else:
+            a = rng.random((9, comp.n_act))
+            rec.step(torch.from_numpy(a).to(batch.device))
+            for e, mg in singles.items():
+                mg.run({name: [a[e, s.act_col:s.act_col + s.n_act] if s.n_act == 2 else a[e, s.act_col] for s in slots]
+                        for name, slots in comp.controllable()})
+    for e, mg in singles.items():
+        got, want = rec.get_log(e), mg.get_log()
+        assert list(got.columns) == list(want.columns) and list(got.index) == list(want.index), e
+        assert np.array_equal(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), equal_nan=True), e
+    assert len(rec.get_log(4)) == 4 and len(rec.get_log(0)) == 9

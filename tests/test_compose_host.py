@@ -134,3 +134,7 @@ def test_env_observation_keys(lib):
 
 def test_standalone_module_steps(lib):
     K.check_standalone_module_steps(lib)
+
+
+def test_batch_log_recorder(lib):
+    K.check_batch_log_recorder(lib)

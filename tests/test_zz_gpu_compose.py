@@ -108,3 +108,7 @@ def test_env_observation_keys_on_gpu():
 
 def test_standalone_module_steps_on_gpu():
     K.check_standalone_module_steps(None)
+
+
+def test_batch_log_recorder_on_gpu():
+    K.check_batch_log_recorder(None)
