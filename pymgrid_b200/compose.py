@@ -866,6 +866,29 @@ class ComposedModuleView:
     min_act = property(lambda self: self._act_bounds()[0])
     max_act = property(lambda self: self._act_bounds()[1])
 
+    def _affine(self, act, obs):
+        assert act + obs == 1, "One of act or obs must be True but not both."
+        low, high = (self._act_bounds() if act else self._obs_bounds())
+        low, high = np.asarray(low, dtype=np.float64), np.asarray(high, dtype=np.float64)
+        spread = high - low
+        return low, np.where(spread == 0, 1.0, spread)
+
+    def to_normalized(self, value, act=False, obs=False):
+        """reference: BaseMicrogridModule.to_normalized -> ModuleSpace.normalize (utils/space.py:207-218)"""
+        low, spread = self._affine(act, obs)
+        return (np.asarray(value, dtype=np.float64) - low) / spread
+
+    def from_normalized(self, value, act=False, obs=False):
+        """reference: ModuleSpace.denormalize (utils/space.py:220-231)"""
+        low, spread = self._affine(act, obs)
+        return low + spread * np.asarray(value, dtype=np.float64)
+
+    # grid columns of the current state, current value first then the forecast (grid_module.py:248-299: state[k::4])
+    import_price = property(lambda self: self.state[0::4])
+    export_price = property(lambda self: self.state[1::4])
+    co2_per_kwh = property(lambda self: self.state[2::4])
+    grid_status = property(lambda self: self.state[3::4])
+
     def sample_action(self, strict_bound=False):
         """base_module.py:326-356 (genset: genset_module.py:348-349)"""
         if self._s.kind == "genset":
@@ -1208,6 +1231,29 @@ class ComposedMicrogrid:
                 r.forecaster_increase_uncertainty, r.forecaster_relative_noise = forecaster_increase_uncertainty, forecaster_relative_noise
         self._rebuild()
         self._stale_forecast = stale       # the next step still logs the forecast computed before the change
+
+    def get_forecast_horizon(self):
+        """reference: Microgrid.get_forecast_horizon (microgrid.py:548-582): the horizon the time-series modules share;
+        ValueError when they differ, the default (with a warning) when there is none"""
+        from .params import DEFAULT_HORIZON
+        horizons = [s.horizon for s in self.composition.slots if s.kind in ("load", "renewable", "grid")]
+        if not horizons:
+            warnings.warn(f"No forecast horizon found in microgrid.modules. Using default horizon {DEFAULT_HORIZON}")
+            return DEFAULT_HORIZON
+        if min(horizons) != max(horizons):
+            raise ValueError(f"Modules have inconsistent forecast horizons: {sorted(set(horizons))}")
+        return horizons[0]
+
+    def to_normalized(self, data_dict, act=False, obs=False):
+        """reference: Microgrid.to_normalized (microgrid.py:390-409): {name: [value per module]} through each module's space"""
+        assert act + obs == 1, 'One of act or obs must be True but not both.'
+        return {name: [m.to_normalized(v, act=act, obs=obs) for m, v in zip(lst, data_dict[name])]
+                for name, lst in self._modules.items() if name in data_dict}
+
+    def from_normalized(self, data_dict, act=False, obs=False):
+        assert act + obs == 1, 'One of act or obs must be True but not both.'
+        return {name: [m.from_normalized(v, act=act, obs=obs) for m, v in zip(lst, data_dict[name])]
+                for name, lst in self._modules.items() if name in data_dict}
 
     def set_module_attr(self, attr_name, value):
         """reference: Microgrid.set_module_attr (microgrid.py:584-612): set a constructor attribute on every module that

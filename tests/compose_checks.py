@@ -433,6 +433,35 @@ def check_standalone_module_steps(lib):
         cp._STANDALONE_LIBRARY = saved
 
 
+def check_microgrid_helpers(lib):
+    """get_forecast_horizon, to_normalized / from_normalized (round trip, module spaces), the grid's price / status columns"""
+    from pymgrid_b200 import modules as M
+    kw = {} if lib is None else {"_library": lib}
+    rng = np.random.default_rng(3)
+    load, pv = 100 + 100 * rng.random(60), 200 * rng.random(60)
+    g = np.stack([rng.uniform(0.05, 0.9, 60), rng.uniform(0, 0.4, 60), rng.uniform(0, 0.6, 60)], axis=1)
+    ts = dict(forecaster="oracle", forecast_horizon=4)
+    mg = ComposedMicrogrid([M.BatteryModule(10, 100, 50, 50, 0.9, init_soc=0.2), M.BatteryModule(10, 1000, 10, 10, 0.7, init_soc=0.3),
+                            M.GensetModule(5, 40, 0.3), ("pv", M.RenewableModule(time_series=pv, **ts)),
+                            M.LoadModule(time_series=load, **ts), M.GridModule(100, 100, g, **ts)], **kw)
+    assert mg.get_forecast_horizon() == 4
+    act = {"battery": [12.0, -3.0], "genset": [np.array([1.0, 22.0])], "grid": [40.0]}
+    nrm = mg.to_normalized(act, act=True)
+    assert nrm["battery"][0] == (12.0 - (-50 / 0.9)) / (50 * 0.9 + 50 / 0.9) and nrm["grid"][0] == 140.0 / 200.0     # battery_module.py:332-338
+    assert np.array_equal(nrm["genset"][0], [1.0, 22.0 / 40.0])
+    back = mg.from_normalized(nrm, act=True)
+    assert np.allclose(back["battery"], act["battery"], rtol=0, atol=1e-12) and np.allclose(back["genset"][0], act["genset"][0], rtol=0, atol=1e-12)
+    grid = mg.modules.grid[0]
+    assert np.array_equal(grid.import_price, g[:5, 0]) and np.array_equal(grid.export_price, g[:5, 1])
+    assert np.array_equal(grid.co2_per_kwh, g[:5, 2]) and np.array_equal(grid.grid_status, np.ones(5))
+    obs = mg.reset()
+    state = mg.from_normalized({k: v for k, v in obs.items() if k not in ("balance", "other")}, obs=True)
+    assert np.allclose(state["load"][0], -load[:5], rtol=0, atol=1e-9) and np.allclose(state["pv"][0], pv[:5], rtol=0, atol=1e-9)
+    mixed = ComposedMicrogrid([M.LoadModule(time_series=load), M.RenewableModule(time_series=pv, **ts)], **kw)
+    with pytest.raises(ValueError):
+        mixed.get_forecast_horizon()
+
+
 def check_batch_log_recorder(lib):
     """ComposedBatch.recorder(env_ids): the reference-format log of selected envs of a batch == the get_log() of a single
     microgrid stepped with the same actions (continuous and discrete steps, a masked reset in between)"""

@@ -138,3 +138,7 @@ def test_standalone_module_steps(lib):
 
 def test_batch_log_recorder(lib):
     K.check_batch_log_recorder(lib)
+
+
+def test_microgrid_helpers(lib):
+    K.check_microgrid_helpers(lib)

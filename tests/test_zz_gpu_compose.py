@@ -112,3 +112,7 @@ def test_standalone_module_steps_on_gpu():
 
 def test_batch_log_recorder_on_gpu():
     K.check_batch_log_recorder(None)
+
+
+def test_microgrid_helpers_on_gpu():
+    K.check_microgrid_helpers(None)
