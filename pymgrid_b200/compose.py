@@ -487,6 +487,15 @@ class ComposedBatch:
             self._check(self._L.mgc_modules_step(self._handle, C.byref(io), int(bool(normalized)), self._stream()), "mgc_modules_step")
         return (self.obs if obs else None), self.reward, self.done, self.info
 
+    def state_dict(self):
+        """the reference's serialisable state (base_module.py:852-868, genset_module.py:426-427) of every env: step, battery
+        charge + soc, genset integers, episode windows -- a checkpoint is these five tensors"""
+        return {a: getattr(self, a).clone() for a in ("step_counter", "fstate", "istate", "env_initial_step", "env_final_step")}
+
+    def load_state_dict(self, state):
+        for a, v in state.items():
+            getattr(self, a).copy_(v)
+
     def recorder(self, env_ids):
         """opt-in reference-format log for a subset of the envs (see ComposedLogRecorder)"""
         return ComposedLogRecorder(self, env_ids)

@@ -135,6 +135,15 @@ def check_batch_matches_oracle_and_rollout_matches_steps(label, lib, n_envs=131,
         getattr(batch3, a).copy_(getattr(_batch_case(lib, label, n_envs, 7)[1], a))
     out3 = batch3.rollout(torch.from_numpy(actions).to(batch3.device), ring=2)
     assert np.array_equal(out3["reward"].cpu().numpy(), want_r) and np.array_equal(out3["obs_ring"][(T - 1) % 2].cpu().numpy(), want_obs)
+    # checkpoint / resume: restoring the state tensors and replaying the tail gives the same tail
+    _, batch4, _ = _batch_case(lib, label, n_envs, 7)
+    head = batch4.rollout(torch.from_numpy(actions[:4]).to(batch4.device), obs=False)
+    saved = batch4.state_dict()
+    tail1 = batch4.rollout(torch.from_numpy(actions[4:]).to(batch4.device), ring=1)
+    batch4.load_state_dict(saved)
+    tail2 = batch4.rollout(torch.from_numpy(actions[4:]).to(batch4.device), ring=1)
+    assert np.array_equal(head["reward"].cpu().numpy(), want_r[:4]) and np.array_equal(tail1["reward"].cpu().numpy(), want_r[4:])
+    assert torch.equal(tail1["reward"], tail2["reward"]) and torch.equal(tail1["obs_ring"], tail2["obs_ring"])
     # masked reset: only the step counter of the masked envs moves (microgrid.py:205-225)
     mask = (np.arange(n_envs) % 3 == 0).astype(np.uint8)
     before = batch.fstate.clone()
