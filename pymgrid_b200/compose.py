@@ -1457,6 +1457,16 @@ class ComposedDiscreteEnv(_ComposedEnv):
         self.action_space = Discrete(len(kept))
         self._index_dev = torch.from_numpy(self._index).to(self.batch.device)
 
+    def remove_action(self, action_number):
+        """reference: DiscreteMicrogridEnv.remove_action (envs/discrete/discrete.py:90-105)"""
+        from .envs import Discrete
+        if action_number not in self.action_space:
+            raise ValueError('Cannot remove action that is not in the action space!')
+        self.actions_list.pop(action_number)
+        self._index = np.delete(self._index, action_number)
+        self.action_space = Discrete(self.action_space.n - 1)
+        self._index_dev = torch.from_numpy(self._index).to(self.batch.device)
+
     def step(self, action):
         if self.single:
             if action not in self.action_space:

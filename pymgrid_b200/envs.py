@@ -264,17 +264,34 @@ class DiscreteMicrogridEnv(_BaseEnv):
 
     def __init__(self, configs, env_config=None, batch=None, remove_redundant_gensets=True, **kw):
         super().__init__(configs, env_config, batch, **kw)
-        self.actions_list = self.engine.action_tables[0]
+        self.actions_list = list(self.engine.action_tables[0])
         self.action_space = Discrete(len(self.actions_list))
         self._a = torch.zeros(self.n_envs, dtype=torch.int32, device=self.engine.device)
+        self._index = None          # env action -> row of the engine's table, once remove_action() has been used
+
+    def remove_action(self, action_number):
+        """reference: DiscreteMicrogridEnv.remove_action (envs/discrete/discrete.py:90-105): drop one priority list from the
+        action space; the remaining actions are renumbered"""
+        if action_number not in self.action_space:
+            raise ValueError('Cannot remove action that is not in the action space!')
+        if self._index is None:
+            self._index = list(range(len(self.actions_list)))
+        self.actions_list.pop(action_number)
+        self._index.pop(action_number)
+        self.action_space = Discrete(self.action_space.n - 1)
+        self._index_dev = torch.tensor(self._index, dtype=torch.int64, device=self.engine.device)
 
     def step(self, action):
         if self.single:
             if action not in self.action_space:
                 raise ValueError(f" Action {action} not in action space {self.action_space}")   # discrete.py:84
-            self._a[0] = int(action)
+            self._a[0] = int(action) if self._index is None else self._index[int(action)]
             pre = self._state()
             return self._finish(self.engine.step_discrete(self._a), pre, int(action))
+        if self._index is not None:     # renumbered action space: map to the engine's rows, out-of-space actions stay invalid
+            a = torch.as_tensor(action, device=self.engine.device).to(torch.int64)
+            bad = (a < 0) | (a >= len(self._index))
+            action = torch.where(bad, torch.full_like(a, -1), self._index_dev[a.clamp(0, len(self._index) - 1)]).to(torch.int32)
         return self._finish(self.engine.step_discrete(action))
 
     def sample_action(self):

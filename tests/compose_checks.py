@@ -183,6 +183,15 @@ def check_discrete_env_and_rbc(case, lib):
         assert np.array_equal(np.array(state, dtype=np.float64), case["states"][k]), k
     with pytest.raises(ValueError):
         env.step(env.action_space.n)
+    # remove_action (envs/discrete/discrete.py:90-105): the remaining actions are renumbered and keep their own lists
+    if env.action_space.n > 2:
+        e1 = ComposedDiscreteEnv(case.modules(), obs_order="container", remove_redundant_gensets=False, **kw, **case.microgrid_kwargs)
+        e2 = ComposedDiscreteEnv(case.modules(), obs_order="container", remove_redundant_gensets=False, **kw, **case.microgrid_kwargs)
+        e2.remove_action(1)
+        assert e2.action_space.n == e1.action_space.n - 1 and e2.actions_list[1] == e1.actions_list[2]
+        for old, new in ((0, 0), (2, 1), (e1.action_space.n - 1, e2.action_space.n - 1)):
+            (o1, r1, d1, _), (o2, r2, d2, _) = e1.step(old), e2.step(new)
+            assert r1 == r2 and np.array_equal(o1, o2)
     # the same action sequence for a batch of replicas, one launch
     benv = ComposedDiscreteEnv(case.modules(), obs_order="container", remove_redundant_gensets=False, batch=130, **kw,
                                **case.microgrid_kwargs)

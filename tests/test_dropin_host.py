@@ -38,3 +38,4 @@ test_set_module_attr_like_the_reference_tests = G2.test_set_module_attr_like_the
 test_env_observation_keys_match_reference = G2.test_env_observation_keys_match_reference
 test_discrete_env_scenarios_like_the_reference_suite = G2.test_discrete_env_scenarios_like_the_reference_suite
 test_env_log_matches_reference = G2.test_env_log_matches_reference
+test_discrete_env_remove_action = G2.test_discrete_env_remove_action

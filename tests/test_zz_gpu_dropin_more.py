@@ -107,3 +107,28 @@ from tests.reference_suite_fused import CHECKS  # noqa: E402
 for _fn in CHECKS:
     globals()[_fn.__name__ + "_on_gpu"] = _fn
 del _fn
+
+
+def test_discrete_env_remove_action():
+    """DiscreteMicrogridEnv.remove_action (envs/discrete/discrete.py:90-105): the remaining actions are renumbered and still
+    expand to their own priority lists (single env and batch)"""
+    from pymgrid_b200.envs import DiscreteMicrogridEnv
+    a, b = DiscreteMicrogridEnv.from_scenario(1), DiscreteMicrogridEnv.from_scenario(1)
+    n = a.action_space.n
+    b.remove_action(2)
+    assert b.action_space.n == n - 1 and len(b.actions_list) == n - 1 and b.actions_list[2] == a.actions_list[3]
+    with pytest.raises(ValueError):
+        b.remove_action(n - 1)
+    for old, new in ((0, 0), (1, 1), (3, 2), (n - 1, n - 2)):
+        o1, r1, d1, _ = a.step(old)
+        o2, r2, d2, _ = b.step(new)
+        assert r1 == r2 and d1 == d2 and np.array_equal(o1, o2)
+    with pytest.raises(ValueError):
+        b.step(n - 1)
+    batch = DiscreteMicrogridEnv.from_scenario(1, batch=4)
+    full = DiscreteMicrogridEnv.from_scenario(1, batch=4)
+    batch.remove_action(2)
+    import torch
+    o1, r1, _, _ = full.step(torch.tensor([0, 3, 5, n - 1], dtype=torch.int32, device=full.engine.device))
+    o2, r2, _, _ = batch.step(torch.tensor([0, 2, 4, n - 2], dtype=torch.int32, device=batch.engine.device))
+    assert torch.equal(r1, r2) and torch.equal(o1, o2)
