@@ -213,6 +213,19 @@ int mg_set_error(int code, const char *msg);      // mg_engine.cu: the text mg_l
 static int mgc_fail(int code, const char *msg) { return mg_set_error(code, msg); }
 #endif
 
+#ifdef MGC_HOSTSIM
+// host build only: lets the CPU suite compare the streaming sum with numpy.sum directly, at every length of a growing list
+extern "C" void mgc_test_growing_sums(const double *values, int n, double *sums) {
+    MgcSum S;
+    mgc_sum_init(S);
+    sums[0] = mgc_sum_value(S);
+    for (int i = 0; i < n; ++i) {
+        mgc_sum_append(S, values[i]);
+        sums[i + 1] = mgc_sum_value(S);
+    }
+}
+#endif
+
 extern "C" int mgc_abi_version(void) { return MGC_ABI_VERSION; }
 
 extern "C" int64_t mgc_sizeof(int which) {

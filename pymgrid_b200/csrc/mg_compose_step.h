@@ -8,7 +8,7 @@
  * from the live reference without a GPU; on the GPU the same source runs one thread per env.
  *
  * IEEE f64 throughout, operations in the reference's order: sums start from 0.0 in dispatch order, np.sum's pairwise
- * order is restated for the energy lists, no fused multiply-add.
+ * order is restated for the energy lists (MgcSum), no fused multiply-add.
  */
 #ifndef MG_COMPOSE_STEP_H
 #define MG_COMPOSE_STEP_H
@@ -49,22 +49,36 @@ MGC_HD double mgc_denormalize(double x, double low, double high) { return low + 
 /* numpy.isclose(a, b) with the default rtol=1e-5, atol=1e-8 */
 MGC_HD bool mgc_isclose(double a, double b) { return fabs(a - b) <= (1e-8 + 1e-5 * fabs(b)); }
 
-/* numpy.sum of a list of f64 (pairwise_sum, numpy/_core/src/umath/loops_utils.h.src): sequential from 0.0 for n < 8,
- * eight running sums combined pairwise for n <= 128.  microgrid/utils/step.py:33-36 sums the energy lists with it. */
-MGC_HD double mgc_np_sum(const double *v, int n) {
-    if (n < 8) {
-        double res = 0.0;
-        for (int i = 0; i < n; ++i) res += v[i];
-        return res;
+/*
+ * numpy.sum of a GROWING list of f64, in numpy's order (pairwise_sum, numpy/_core/src/umath/loops_utils.h.src): sequential
+ * from 0.0 below 8 addends; from 8 on, eight running sums over the full blocks of eight, combined pairwise, then the
+ * remaining n % 8 values added one by one (valid up to 128 addends, where numpy starts to recurse; a microgrid has at most
+ * MGC_MAX_MODULES = 64).  microgrid/utils/step.py:33-36 sums the provided / absorbed energy lists with it after the fixed,
+ * after the controllable and after the flex modules, so the sum is needed at three lengths of the same list: the eight
+ * running sums and the pending block are kept instead of the list (16 doubles instead of 64).
+ */
+struct MgcSum {
+    double r[8];      /* running sums over the completed blocks of eight */
+    double pend[8];   /* the current, incomplete block (the whole list while it is shorter than 8) */
+    int n;
+};
+MGC_HD void mgc_sum_init(MgcSum &S) { S.n = 0; }
+MGC_HD void mgc_sum_append(MgcSum &S, double v) {
+    S.pend[S.n & 7] = v;
+    S.n += 1;
+    if ((S.n & 7) == 0) {
+        if (S.n == 8) {
+            for (int j = 0; j < 8; ++j) S.r[j] = S.pend[j];
+        } else {
+            for (int j = 0; j < 8; ++j) S.r[j] += S.pend[j];
+        }
     }
-    double r0 = v[0], r1 = v[1], r2 = v[2], r3 = v[3], r4 = v[4], r5 = v[5], r6 = v[6], r7 = v[7];
-    int i = 8;
-    for (; i < n - (n % 8); i += 8) {
-        r0 += v[i + 0]; r1 += v[i + 1]; r2 += v[i + 2]; r3 += v[i + 3];
-        r4 += v[i + 4]; r5 += v[i + 5]; r6 += v[i + 6]; r7 += v[i + 7];
-    }
-    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
-    for (; i < n; ++i) res += v[i];
+}
+MGC_HD double mgc_sum_value(const MgcSum &S) {
+    const int tail = S.n & 7;
+    double res = 0.0;
+    if (S.n >= 8) res = ((S.r[0] + S.r[1]) + (S.r[2] + S.r[3])) + ((S.r[4] + S.r[5]) + (S.r[6] + S.r[7]));
+    for (int i = 0; i < tail; ++i) res += S.pend[i];
     return res;
 }
 
@@ -170,9 +184,7 @@ MGC_HD bool mgc_is_sink(int kind) { return kind == MGC_LOAD || kind == MGC_BATTE
 
 /* accumulators of one Microgrid.run: microgrid/utils/step.py MicrogridStep */
 struct MgcStepAcc {
-    double provided[MGC_MAX_MODULES];
-    double absorbed[MGC_MAX_MODULES];
-    int n_provided, n_absorbed;
+    MgcSum provided, absorbed;
     double reward;
     int done;
     uint32_t flags;
@@ -297,8 +309,8 @@ MGC_HD void mgc_module_step(const MgcView &V, int m, double a, int t, double *fs
     }
     /* MicrogridStep.append, microgrid/utils/step.py:13-31 */
     A.reward += reward;
-    if (sink) A.absorbed[A.n_absorbed++] = absorbed;
-    else A.provided[A.n_provided++] = provided;
+    if (sink) mgc_sum_append(A.absorbed, absorbed);
+    else mgc_sum_append(A.provided, provided);
     if (info) {
         double *r = info + (int64_t)M.listing * MGC_INFO_SLOTS;
         r[0] = sink ? 0.0 : provided;
@@ -317,7 +329,8 @@ MGC_HD void mgc_module_step(const MgcView &V, int m, double a, int t, double *fs
 MGC_HD void mgc_env_step(const MgcView &V, int32_t &t, double *fstate, int32_t *istate, const double *action, int normalized,
                          int final_step, double *reward_out, uint8_t *done_out, double *info, uint32_t *flags) {
     MgcStepAcc A;
-    A.n_provided = A.n_absorbed = 0;
+    mgc_sum_init(A.provided);
+    mgc_sum_init(A.absorbed);
     A.reward = 0.0;
     A.done = 0;
     A.flags = 0;
@@ -341,7 +354,7 @@ MGC_HD void mgc_env_step(const MgcView &V, int32_t &t, double *fstate, int32_t *
         mgc_module_step(V, m, 0.0, t0, fstate, istate, A, info);
         A.done |= ts_done;
     }
-    const double fixed_p = mgc_np_sum(A.provided, A.n_provided), fixed_a = mgc_np_sum(A.absorbed, A.n_absorbed);
+    const double fixed_p = mgc_sum_value(A.provided), fixed_a = mgc_sum_value(A.absorbed);
     /* ---- controllable modules with the caller's control, microgrid.py:262-275 ---- */
     for (; m < n && mgc_dispatch_class(V.mod[m].kind) == 1; ++m) {
         const MgcModule &M = V.mod[m];
@@ -366,7 +379,7 @@ MGC_HD void mgc_env_step(const MgcView &V, int32_t &t, double *fstate, int32_t *
         mgc_module_step(V, m, a, t0, fstate, istate, A, info);
         if (M.kind == MGC_GRID) A.done |= ts_done;
     }
-    const double ctl_p = mgc_np_sum(A.provided, A.n_provided), ctl_a = mgc_np_sum(A.absorbed, A.n_absorbed);
+    const double ctl_p = mgc_sum_value(A.provided), ctl_a = mgc_sum_value(A.absorbed);
     const double difference = ctl_p - ctl_a;             /* microgrid.py:277-278 */
     /* ---- flex modules, microgrid.py:286-314 ---- */
     if (difference > 0) {
@@ -401,7 +414,7 @@ MGC_HD void mgc_env_step(const MgcView &V, int32_t &t, double *fstate, int32_t *
             needed -= amt;
         }
     }
-    const double all_p = mgc_np_sum(A.provided, A.n_provided), all_a = mgc_np_sum(A.absorbed, A.n_absorbed);
+    const double all_p = mgc_sum_value(A.provided), all_a = mgc_sum_value(A.absorbed);
     if (!mgc_isclose(all_p, all_a)) A.flags |= MG_FLAG_BALANCE;      /* microgrid.py:321-323 */
     if (info) {                                                        /* the balance log, microgrid.py:259-260, 281, 317-319 */
         double *b = info + (int64_t)n * MGC_INFO_SLOTS;
@@ -426,7 +439,8 @@ MGC_HD void mgc_env_step(const MgcView &V, int32_t &t, double *fstate, int32_t *
 MGC_HD void mgc_modules_step(const MgcView &V, int32_t &t, double *fstate, int32_t *istate, const double *action, int normalized,
                              int final_step, double *reward_out, uint8_t *done_out, double *info, uint32_t *flags) {
     MgcStepAcc A;
-    A.n_provided = A.n_absorbed = 0;
+    mgc_sum_init(A.provided);
+    mgc_sum_init(A.absorbed);
     A.reward = 0.0;
     A.done = 0;
     A.flags = 0;
@@ -490,15 +504,15 @@ MGC_HD void mgc_modules_step(const MgcView &V, int32_t &t, double *fstate, int32
 MGC_HD void mgc_priority_control(const MgcView &V, int t, const double *fstate, const int32_t *istate, const int16_t *pl,
                                  int width, int n_act, double *ctl, uint32_t *flags) {
     double total_load = 0.0;
-    double ren[MGC_MAX_MODULES];
-    int n_ren = 0;
+    MgcSum ren;
+    mgc_sum_init(ren);
     for (int m = 0; m < V.n_mod; ++m) {
         const MgcModule &M = V.mod[m];
         const double *p = V.cfg + M.param_off;
         if (M.kind == MGC_LOAD) total_load += -1 * mgc_series_of(V, p)[t];          /* load_module.py:96-111 */
-        else if (M.kind == MGC_RENEWABLE) ren[n_ren++] = mgc_series_of(V, p)[t];
+        else if (M.kind == MGC_RENEWABLE) mgc_sum_append(ren, mgc_series_of(V, p)[t]);
     }
-    double remaining = total_load - mgc_np_sum(ren, n_ren);
+    double remaining = total_load - mgc_sum_value(ren);
     for (int i = 0; i < n_act; ++i) ctl[i] = 0.0;
     uint64_t seen = 0;          /* gensets already given their goal by an earlier element */
     for (int i = 0; i < width; ++i) {

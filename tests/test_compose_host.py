@@ -142,3 +142,14 @@ def test_batch_log_recorder(lib):
 
 def test_microgrid_helpers(lib):
     K.check_microgrid_helpers(lib)
+
+
+def test_streaming_sum_equals_numpy_sum_at_every_length(lib):
+    """MgcSum (mg_compose_step.h): the sum of a growing list in numpy's pairwise order, queried at every length up to 128"""
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n = int(rng.integers(0, 129))
+        v = (10 * rng.random(n) - 3) * 10.0 ** rng.integers(-3, 4, n)
+        out = np.zeros(n + 1)
+        lib.mgc_test_growing_sums(v.ctypes.data_as(ctypes.c_void_p), n, out.ctypes.data_as(ctypes.c_void_p))
+        assert all(out[k] == (float(np.sum(list(v[:k]))) if k else 0.0) for k in range(n + 1))
