@@ -159,6 +159,16 @@ int mgc_modules_step(MgcHandle *h, const MgcIO *io, int normalized, void *stream
 int mgc_reset(MgcHandle *h, const MgcIO *io, void *stream);
 /* mgc_observe -- the current normalised observation without stepping. */
 int mgc_observe(MgcHandle *h, const MgcIO *io, void *stream);
+/*
+ * mgc_forecast_noise -- GaussianNoiseForecaster (forecast/forecaster.py:220-262) applied to observation rows that mgc_run /
+ * mgc_run_discrete (the last step's slot) / mgc_reset / mgc_observe have just written on the same stream: Gaussian noise on
+ * every real forecast row of the time-series modules, clipped to the bounds; current values, battery / genset entries and
+ * the physics are untouched.  `noise`: DEVICE [n_cfg][2 * obs_dim] -- per config, per row element, the normalised standard
+ * deviation (std, times |mean(series)| under relative_noise, divided by the column's spread; 0 = no noise) followed by the
+ * increase_uncertainty flags (0 / 1).  The draw is a pure function of (seed, call, env_base + env, the env's step, element):
+ * reproducible and independent of the launch shape -- parity with the reference's global numpy generator is distributional.
+ */
+int mgc_forecast_noise(MgcHandle *h, const double *noise, double *obs, int64_t env_base, uint64_t seed, uint64_t call, void *stream);
 int64_t mgc_launch_count(const MgcHandle *h);
 
 #ifdef __cplusplus

@@ -58,7 +58,7 @@ class MgcIO(C.Structure):
 
 
 EXPORTED_SYMBOLS = ("mgc_abi_version", "mgc_sizeof", "mgc_param_count", "mgc_create", "mgc_destroy", "mgc_run",
-                    "mgc_run_discrete", "mgc_modules_step", "mgc_reset", "mgc_observe", "mgc_launch_count")
+                    "mgc_run_discrete", "mgc_modules_step", "mgc_reset", "mgc_observe", "mgc_forecast_noise", "mgc_launch_count")
 MAX_PRIORITY_ELEMENTS = 8       # (elements)! permutations are enumerated like the reference does (priority_list.py:15-38)
 FLAG_BAD_ACTION = 1 << 6
 
@@ -77,6 +77,7 @@ def bind(L):
     L.mgc_modules_step.argtypes = [_vp, C.POINTER(MgcIO), C.c_int, _vp]
     L.mgc_reset.argtypes = [_vp, C.POINTER(MgcIO), _vp]
     L.mgc_observe.argtypes = [_vp, C.POINTER(MgcIO), _vp]
+    L.mgc_forecast_noise.argtypes = [_vp, _vp, _vp, C.c_int64, C.c_uint64, C.c_uint64, _vp]
     L.mgc_launch_count.restype, L.mgc_launch_count.argtypes = C.c_int64, [_vp]
     L.mg_last_error.restype = C.c_char_p
     if L.mgc_abi_version() != MGC_ABI_VERSION:
@@ -183,9 +184,7 @@ class Composition:
         self.initial_step = initial.pop() if initial else 0
         self.final_step = final.pop() if final else 0
         for m in ts:
-            if m._forecaster_params() is not None:
-                raise NotImplementedError("composed microgrids run the oracle forecaster (or none); Gaussian-noise forecasts "
-                                          "are built for the fused module set only")
+            m._forecaster_params()          # None / 'oracle' / a noise standard deviation; Python callables are refused here
 
     def records_named(self):
         """[(name, record)] in listing order: what rebuilds the same microgrid (add_unbalanced_module=False)"""
@@ -306,6 +305,44 @@ class Composition:
             raise NameError(f'Keys {bad} not found in state.')
         return [(s, names[id(s)].index(k)) for k in keys for s in self.slots if k in names[id(s)]]
 
+    def noise_rows(self, elements):
+        """GaussianNoiseForecaster parameters per element of the observation row (mgc_forecast_noise): the normalised standard
+        deviation -- the module's noise_std, times |mean(time_series[initial_step:final_step])| under relative_noise
+        (forecast/forecaster.py:237-250, base_timeseries_module.py:233-240), divided by the column's observation spread, 0 for
+        constant columns (the forecaster's clip pins them), for the current value and for modules without noise -- and the
+        increase_uncertainty flags.  `elements`: [(slot, element of its block)] in row order.  Returns None without noise."""
+        per_slot = {}
+        for s, r in zip(self.slots, self.records):
+            f = r._forecaster_params() if hasattr(r, "time_series") else None
+            if f is None or f.noise_std == 0:
+                continue
+            ts = r.time_series
+            std = float(f.noise_std)
+            if f.relative_noise:
+                std *= float(np.abs(ts[self.initial_step:self.final_step].mean()))
+            cols = []
+            for c in range(ts.shape[1]):
+                low, high = float(ts[:, c].min()), float(ts[:, c].max())
+                if s.kind != "grid":
+                    low, high = min(low, 0.0), max(high, 0.0)
+                cols.append(std / (high - low) if high > low else 0.0)
+            per_slot[id(s)] = (cols, float(bool(f.increase_uncertainty)))
+        if not per_slot:
+            return None
+        sigma, inc = np.zeros(len(elements)), np.zeros(len(elements))
+        for j, (s, k) in enumerate(elements):
+            if id(s) in per_slot:
+                cols, flag = per_slot[id(s)]
+                C_ = len(cols)
+                if k // C_ > 0:
+                    sigma[j], inc[j] = cols[k % C_], flag
+        return np.concatenate([sigma, inc])
+
+    def row_elements(self):
+        """[(slot, element)] of the full observation row, in row order"""
+        order = sorted((s for s in self.slots if s.obs_len), key=lambda s: s.obs_off)
+        return [(s, k) for s in order for k in range(s.obs_len)]
+
     def module_table(self):
         arr = (MgcModule * MGC_MAX_MODULES)()
         for k, s in enumerate(self.dispatch):
@@ -413,6 +450,15 @@ class ComposedBatch:
             self.plist = t(comp.priority_table(self.action_lists), torch.int16)
             L.plist, L.n_plist, L.plist_width = self.plist.data_ptr(), len(self.action_lists), self.plist.shape[1]
         L.env_initial_step, L.env_final_step = self.env_initial_step.data_ptr(), self.env_final_step.data_ptr()
+        # Gaussian-noise forecasters of the modules (forecast/forecaster.py:220-262): on by default when any module asks for one
+        elements = self.selection if self.selection is not None else comp.row_elements()
+        rows = [c.noise_rows([(c.slots[s.listing], k) for s, k in elements]) for c in self.compositions]
+        self._noise = None
+        self._noise_calls = 0
+        if any(r is not None for r in rows):
+            rows = [r if r is not None else np.zeros(2 * self.obs_dim) for r in rows]
+            self._noise_rows = t(np.stack(rows), torch.float64)
+            self.set_forecast_noise(seed=0)
         self._handle = _vp()
         with self._on_device():         # mgc_create uploads its element table to the CURRENT device
             self._check(self._L.mgc_create(C.byref(L), C.byref(self._handle)), "mgc_create")
@@ -440,6 +486,27 @@ class ComposedBatch:
     def _check(self, code, what):
         if code != 0:
             raise _cabi.EngineError(f"{what} failed ({code}): {self._L.mg_last_error().decode()}")
+
+    def set_forecast_noise(self, seed=0, env_offset=0):
+        """(Re)seed the Gaussian-noise forecasts: after every step / reset / observe the forecast entries of the freshly written
+        rows get N(0, std_k) added and are clipped to their bounds (mgc_forecast_noise).  The draw is a pure function of
+        (seed, call number, env_offset + env, the env's step, element); shards of one batch pass their own env_offset.
+        `rollout` keeps the oracle forecast inside its launch."""
+        if getattr(self, "_noise_rows", None) is None:
+            raise ValueError("no module of this batch has a Gaussian-noise forecaster")
+        self._noise = (int(seed) & (2 ** 64 - 1), int(env_offset))
+
+    def clear_forecast_noise(self):
+        self._noise = None
+
+    def _apply_noise(self, obs):
+        if self._noise is None or obs is None:
+            return
+        seed, base = self._noise
+        self._noise_calls += 1
+        with self._on_device():
+            self._check(self._L.mgc_forecast_noise(self._handle, self._noise_rows.data_ptr(), obs.data_ptr(), base, seed,
+                                                   self._noise_calls, self._stream()), "mgc_forecast_noise")
 
     def _on_device(self):
         import contextlib
@@ -470,6 +537,7 @@ class ComposedBatch:
                    self.done.data_ptr(), self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None)
         with self._on_device():
             self._check(self._L.mgc_run(self._handle, C.byref(io), 1, 1, int(bool(normalized)), self._stream()), "mgc_run")
+        self._apply_noise(self.obs if obs else None)
         return (self.obs if obs else None), self.reward, self.done, self.info
 
     def modules_step(self, actions=None, normalized=True, obs=True):
@@ -485,6 +553,7 @@ class ComposedBatch:
                    self.done.data_ptr(), self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None)
         with self._on_device():
             self._check(self._L.mgc_modules_step(self._handle, C.byref(io), int(bool(normalized)), self._stream()), "mgc_modules_step")
+        self._apply_noise(self.obs if obs else None)
         return (self.obs if obs else None), self.reward, self.done, self.info
 
     def state_dict(self):
@@ -517,6 +586,7 @@ class ComposedBatch:
                    self.info.data_ptr() if self.info is not None else None, self.flags.data_ptr(), None, a.data_ptr(), 0)
         with self._on_device():
             self._check(self._L.mgc_run_discrete(self._handle, C.byref(io), 1, 1, self._stream()), "mgc_run_discrete")
+        self._apply_noise(self.obs if obs else None)
         return (self.obs if obs else None), self.reward, self.done, self.info
 
     def rollout_discrete(self, actions, n_steps=None, ring=1, obs=True):
@@ -565,12 +635,14 @@ class ComposedBatch:
         io = MgcIO(None, self.obs.data_ptr(), None, None, None, None, m.data_ptr() if m is not None else None)
         with self._on_device():
             self._check(self._L.mgc_reset(self._handle, C.byref(io), self._stream()), "mgc_reset")
+        self._apply_noise(self.obs)
         return self.obs
 
     def observe(self):
         io = MgcIO(None, self.obs.data_ptr(), None, None, None, None, None)
         with self._on_device():
             self._check(self._L.mgc_observe(self._handle, C.byref(io), self._stream()), "mgc_observe")
+        self._apply_noise(self.obs)
         return self.obs
 
 

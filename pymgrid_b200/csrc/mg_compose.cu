@@ -165,6 +165,28 @@ static void mgc_kernel_host(const MgcLaunch &P) {
 }
 #endif
 
+// forecast noise: a post-pass over rows that have just been written, one warp per row
+struct MgcNoiseLaunch {
+    const double *noise;
+    double *obs;
+    int64_t env_base;
+    uint32_t k0, k1, c3, _pad;
+};
+
+MGC_DEV void mgc_noise_env(const MgcLaunch &P, const MgcNoiseLaunch &N, int e, int lane) {
+    MgcView V = mgc_view(P, e);
+    const double *sig = N.noise + (int64_t)P.cfg_index[e] * 2 * P.obs_dim;
+    mgc_noise_row(V, P.elem, P.obs_dim, N.obs + (int64_t)e * P.obs_dim, sig, sig + P.obs_dim, P.step[e],
+                  (uint64_t)(N.env_base + e), N.k0, N.k1, N.c3, lane);
+}
+
+#ifndef MGC_HOSTSIM
+__global__ void __launch_bounds__(128) mgc_noise_kernel(const __grid_constant__ MgcLaunch P, const MgcNoiseLaunch N) {
+    const int e = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (e < P.n_envs) mgc_noise_env(P, N, e, threadIdx.x & 31);
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------------------------------------------------
@@ -397,6 +419,32 @@ extern "C" int mgc_run_discrete(MgcHandle *h, const MgcIO *io, int32_t n_steps, 
 }
 extern "C" int mgc_modules_step(MgcHandle *h, const MgcIO *io, int normalized, void *stream) {
     return mgc_launch(h, io, MGC_MODE_MODULES, 1, 1, normalized, stream);
+}
+extern "C" int mgc_forecast_noise(MgcHandle *h, const double *noise, double *obs, int64_t env_base, uint64_t seed, uint64_t call,
+                                  void *stream) {
+    if (!h || !noise || !obs) return mgc_fail(MG_E_INVALID, "mgc_forecast_noise: null argument");
+    if (h->base.obs_dim > 2 * 65535) return mgc_fail(MG_E_UNSUPPORTED, "mgc_forecast_noise: observation row too long");
+    MgcNoiseLaunch N;
+    N.noise = noise; N.obs = obs; N.env_base = env_base;
+    N.k0 = (uint32_t)seed;
+    N.k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(call >> 32);
+    N.c3 = (uint32_t)call;
+    N._pad = 0;
+#ifdef MGC_HOSTSIM
+    (void)stream;
+    for (int e = 0; e < h->base.n_envs; ++e)
+        for (int lane = 0; lane < 32; ++lane) mgc_noise_env(h->base, N, e, lane);
+#else
+    mgc_noise_kernel<<<(h->base.n_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(h->base, N);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        char msg[256];
+        snprintf(msg, sizeof msg, "mgc_forecast_noise launch: %s", cudaGetErrorString(e));
+        return mgc_fail(MG_E_CUDA, msg);
+    }
+#endif
+    h->launches += 1;
+    return MG_OK;
 }
 extern "C" int mgc_reset(MgcHandle *h, const MgcIO *io, void *stream) { return mgc_launch(h, io, MGC_MODE_RESET, 1, 1, 0, stream); }
 extern "C" int mgc_observe(MgcHandle *h, const MgcIO *io, void *stream) { return mgc_launch(h, io, MGC_MODE_OBSERVE, 1, 1, 0, stream); }

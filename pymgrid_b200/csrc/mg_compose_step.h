@@ -555,4 +555,66 @@ MGC_HD void mgc_priority_control(const MgcView &V, int t, const double *fstate, 
     }
 }
 
+/*
+ * GaussianNoiseForecaster (forecast/forecaster.py:220-262) on a freshly written observation row: N(0, std_k) on every REAL
+ * forecast row k of a time-series module (rows past the end of the series are padding and carry none, :120-132), clipped to
+ * the column's bounds (:139-149) -- in normalised units  obs <- min(max(obs + z * sigma * scale_k, 0), 1)  with
+ * scale_k = 1 + log(1 + k) under increase_uncertainty (:244-248).  `sigma` / `increase` are per ELEMENT of the row (the host
+ * folds std, relative_noise and the column spread into sigma; 0 = leave the element alone).  z: Box-Muller over
+ * Philox4x32-10 (Salmon et al., SC'11), a pure function of (seed, call, global env id, the env's step, element pair) -- the
+ * same counter layout as mg_forecast_noise of the fused path.  Lane `lane` of a warp takes pairs lane, lane + 32, ...
+ */
+MGC_HD void mgc_philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t m0 = (uint64_t)0xD2511F53u * c[0], m1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t hi0 = (uint32_t)(m0 >> 32), lo0 = (uint32_t)m0, hi1 = (uint32_t)(m1 >> 32), lo1 = (uint32_t)m1;
+        c[0] = hi1 ^ c[1] ^ k0;
+        c[1] = lo1;
+        c[2] = hi0 ^ c[3] ^ k1;
+        c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+MGC_HD void mgc_noise_row(const MgcView &V, const int32_t *elem, int obs_dim, double *row, const double *sigma,
+                          const double *increase, int t, uint64_t env, uint32_t k0, uint32_t k1, uint32_t c3, int lane) {
+    for (int p = lane; 2 * p < obs_dim; p += 32) {
+        double z[2];
+        bool drawn = false;
+        for (int h = 0; h < 2; ++h) {
+            const int j = 2 * p + h;
+            if (j >= obs_dim || sigma[j] == 0.0) continue;
+            const int32_t d = elem[j];
+            const MgcModule &M = V.mod[d >> 16];
+            if (!mgc_is_timeseries(M.kind)) continue;
+            const int C = (M.kind == MGC_GRID) ? 4 : 1;
+            const int r = (d & 0xffff) / C;
+            if (r == 0) continue;                       /* the current value is not a forecast */
+            const int k = r - 1;
+            if (t + 1 + k >= V.T) continue;             /* padding past the end of the series */
+            if (!drawn) {
+                uint32_t c[4] = {(uint32_t)env, ((uint32_t)(env >> 32) & 0xffffu) | ((uint32_t)p << 16), (uint32_t)t, c3};
+                mgc_philox4x32_10(c, k0, k1);
+                /* two 53-bit uniforms, u1 in (0, 1], u2 in [0, 1) */
+                const double u1 = ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6) + 1.0) * (1.0 / 9007199254740992.0);
+                const double u2 = ((double)(c[2] >> 5) * 67108864.0 + (double)(c[3] >> 6)) * (1.0 / 9007199254740992.0);
+                const double radius = sqrt(-2.0 * log(u1));
+#if defined(__CUDA_ARCH__)
+                double sn, cs;
+                sincospi(2.0 * u2, &sn, &cs);
+#else
+                const double sn = sin(6.283185307179586476925286766559 * u2), cs = cos(6.283185307179586476925286766559 * u2);
+#endif
+                z[0] = radius * cs;
+                z[1] = radius * sn;
+                drawn = true;
+            }
+            double s = sigma[j];
+            if (increase[j] != 0.0) s = s * (1.0 + log(1.0 + (double)k));
+            row[j] = fmin(fmax(row[j] + z[h] * s, 0.0), 1.0);
+        }
+    }
+}
+
 #endif /* MG_COMPOSE_STEP_H */

@@ -516,3 +516,81 @@ def check_batch_log_recorder(lib):
         assert list(got.columns) == list(want.columns) and list(got.index) == list(want.index), e
         assert np.array_equal(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), equal_nan=True), e
     assert len(rec.get_log(4)) == 4 and len(rec.get_log(0)) == 9
+
+
+def check_forecast_noise(lib):
+    """Gaussian-noise forecasters on a composed batch (mgc_forecast_noise): the per-element standard deviations equal the
+    reference-pinned restatement of GaussianNoiseForecaster (oracle/forecast_noise.py), and every noisy observation equals
+    clip(clean + z * sigma * scale) with z from the numpy restatement of the kernel's Philox / Box-Muller stream."""
+    from oracle.forecast_noise import NoisyModule
+    from pymgrid_b200 import modules as M
+    from tests.helpers import engine_noise_normals
+    kw = {} if lib is None else {"_library": lib}
+    rng = np.random.default_rng(8)
+    T = 40
+    load, pv = 100 + 100 * rng.random(T), 200 * rng.random(T)
+    g = np.stack([rng.uniform(0.05, 0.9, T), np.zeros(T), rng.uniform(0, 0.6, T), (rng.random(T) > 0.3).astype(float)], axis=1)
+
+    def mods(noisy):
+        f = (lambda std: std) if noisy else (lambda std: "oracle")
+        return [M.LoadModule(time_series=load, forecaster=f(12.5), forecast_horizon=6, forecaster_relative_noise=False),
+                M.LoadModule(time_series=0.5 * load, forecaster="oracle", forecast_horizon=6),
+                M.RenewableModule(time_series=pv, forecaster=f(0.3), forecast_horizon=9, forecaster_increase_uncertainty=True,
+                                  forecaster_relative_noise=True),
+                M.BatteryModule(10, 100, 50, 50, 0.9, init_soc=0.5),
+                M.GridModule(100, 100, g, forecaster=f(0.02), forecast_horizon=4, forecaster_relative_noise=True)]
+    n = 7
+    noisy = ComposedBatch([mods(True)], np.zeros(n, dtype=np.int64), obs_order="container", **kw)
+    clean = ComposedBatch([mods(False)], np.zeros(n, dtype=np.int64), obs_order="container", **kw)
+    comp = noisy.comp
+    # sigma table against the reference-pinned restatement
+    rows = host(noisy._noise_rows)[0]
+    sigma, inc = rows[:comp.obs_dim], rows[comp.obs_dim:]
+    want = {("load", 0): NoisyModule(-load, 6, True, 12.5, False, False, 0, T), ("renewable", 0): NoisyModule(pv, 9, True, 0.3, True, True, 0, T),
+            ("grid", 0): NoisyModule(g, 4, False, 0.02, False, True, 0, T)}
+    for s in comp.slots:
+        block = sigma[s.obs_off:s.obs_off + s.obs_len]
+        if (s.name, s.index) in want:
+            tab = want[(s.name, s.index)].sigma_normalised()          # [H, C], incl. the 1 + log(1 + k) growth
+            C_ = tab.shape[1]
+            assert np.array_equal(block[:C_], np.zeros(C_))            # the current value carries no noise
+            base = block[C_:].reshape(-1, C_)
+            grow = (1 + np.log(1 + np.arange(len(base))))[:, None] if inc[s.obs_off + C_] else 1.0
+            np.testing.assert_allclose(base * grow, tab, rtol=1e-15, atol=0)
+        else:
+            assert not block.any()
+    assert sigma[comp.slots[-1].obs_off + 4 + 1] == 0.0                # export price is constant: the clip pins it
+    # every element against the generator restatement, across the end of the series (padding rows carry no noise)
+    noisy.set_forecast_noise(seed=77, env_offset=1000)
+    for b in (noisy, clean):
+        b.step_counter.fill_(T - 7)
+    acts = rng.random((6, n, comp.n_act))
+    call = 0
+    for k in range(6):
+        o_noisy = host(noisy.step(torch.from_numpy(acts[k]).to(noisy.device))[0]).copy()
+        o_clean = host(clean.step(torch.from_numpy(acts[k]).to(clean.device))[0]).copy()
+        call += 1
+        t = T - 7 + k + 1
+        for e in range(n):
+            z = engine_noise_normals(1000 + e, t, (comp.obs_dim + 1) // 2, 77, call)
+            expect = o_clean[e].copy()
+            for s in comp.slots:
+                if s.kind not in ("load", "renewable", "grid"):
+                    continue
+                C_ = 4 if s.kind == "grid" else 1
+                for kk in range(C_, s.obs_len):
+                    j, row = s.obs_off + kk, kk // C_ - 1
+                    if sigma[j] == 0 or t + 1 + row >= T:
+                        continue
+                    scale = 1 + np.log(1 + row) if inc[j] else 1.0
+                    expect[j] = min(max(o_clean[e, j] + z[j] * sigma[j] * scale, 0.0), 1.0)
+            np.testing.assert_allclose(o_noisy[e], expect, rtol=0, atol=1e-12)
+        assert not np.array_equal(o_noisy, o_clean) or t + 1 >= T
+    assert np.array_equal(host(noisy.reward), host(clean.reward))      # noise never touches the physics
+    # reproducible per seed, different per env and per call; rollouts keep the oracle forecast
+    a1 = host(noisy.observe()).copy()
+    noisy.set_forecast_noise(seed=77, env_offset=1000)
+    noisy._noise_calls = call
+    assert np.array_equal(host(noisy.observe()), a1)
+    noisy.clear_forecast_noise()
+    assert np.array_equal(host(noisy.observe()), host(clean.observe()))

@@ -153,3 +153,7 @@ def test_streaming_sum_equals_numpy_sum_at_every_length(lib):
         out = np.zeros(n + 1)
         lib.mgc_test_growing_sums(v.ctypes.data_as(ctypes.c_void_p), n, out.ctypes.data_as(ctypes.c_void_p))
         assert all(out[k] == (float(np.sum(list(v[:k]))) if k else 0.0) for k in range(n + 1))
+
+
+def test_forecast_noise(lib):
+    K.check_forecast_noise(lib)

@@ -116,3 +116,7 @@ def test_batch_log_recorder_on_gpu():
 
 def test_microgrid_helpers_on_gpu():
     K.check_microgrid_helpers(None)
+
+
+def test_forecast_noise_on_gpu():
+    K.check_forecast_noise(None)
