@@ -264,7 +264,9 @@ class DiscreteMicrogridEnv(_BaseEnv):
 
     def __init__(self, configs, env_config=None, batch=None, remove_redundant_gensets=True, **kw):
         super().__init__(configs, env_config, batch, **kw)
-        self.actions_list = list(self.engine.action_tables[0])
+        from .algos import _elements
+        # the reference's form (envs/discrete/discrete.py:60-80): one tuple of PriorityListElement per action
+        self.actions_list = [tuple(_elements(self.params, pl)) for pl in self.engine.action_tables[0]]
         self.action_space = Discrete(len(self.actions_list))
         self._a = torch.zeros(self.n_envs, dtype=torch.int32, device=self.engine.device)
         self._index = None          # env action -> row of the engine's table, once remove_action() has been used

@@ -82,6 +82,8 @@ def test_discrete_env_scenarios_like_the_reference_suite(n):
     for j in range(3):
         env.step(env.sample_action())
         assert len(env.log) == j + 1
+    first = env.actions_list[0]          # the reference's form: tuples of PriorityListElement
+    assert all(hasattr(el, "module") and hasattr(el, "marginal_cost") and el.module_actions in (1, 2) for el in first)
     n_action_modules = len(env.modules.controllable.sources) + len(env.modules.controllable.source_and_sinks)
     genset_modules = len(env.modules.genset) if hasattr(env.modules, "genset") else 0
     assert env.action_space.n == factorial(n_action_modules) * (2 ** genset_modules)
