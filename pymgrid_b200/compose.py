@@ -9,8 +9,13 @@ path:
   Composition        the static structure of a module list: the container's listing and dispatch orders
                      (module_container.py:355-413), action columns, observation blocks, parameter packing
   ComposedBatch      B microgrids sharing one composition (own parameters, series, state): device tensors + mgc_* calls
-  ComposedMicrogrid  the reference's single-microgrid surface (run / reset / get_log / state_dict / sample_action / modules)
-                     on a batch of one; `pymgrid_b200.Microgrid(modules)` returns it when the list is outside the fused scope
+  ComposedMicrogrid  the reference's single-microgrid surface (run / reset / get_log / state_dict / sample_action / modules,
+                     set_forecaster, Python reward shapers / trajectory functions) on a batch of one;
+                     `pymgrid_b200.Microgrid(modules)` returns it when the list is outside the fused scope
+  ComposedDiscreteEnv / ComposedContinuousEnv / ComposedRuleBasedControl
+                     the env and controller surfaces (priority lists expanded on the device: mgc_run_discrete)
+  ComposedLogRecorder  reference-format log for a subset of a batch
+  StandaloneModule   a module stepped on its own (mgc_modules_step): what `module.step(action)` of pymgrid_b200.modules runs on
 
 No CPU fallback: without the CUDA extension or a CUDA device, construction raises.  (`_library` is the test suite's hook
 for the host build of the same C source, tests/hostsim/.)
