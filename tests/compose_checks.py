@@ -594,3 +594,33 @@ def check_forecast_noise(lib):
     assert np.array_equal(host(noisy.observe()), a1)
     noisy.clear_forecast_noise()
     assert np.array_equal(host(noisy.observe()), host(clean.observe()))
+
+
+def check_modules_step_batch(lib):
+    """mgc_modules_step on a batch spanning several tiles: every env equals a batch of one stepped with the same actions"""
+    case = next(c for c in CASES if c.label == "several_of_each")
+    kw = {} if lib is None else {"_library": lib}
+    make = lambda k: ComposedBatch([case.modules()], np.zeros(k, dtype=np.int64), obs_order="container", with_info=True,      # noqa: E731
+                                   microgrid_kwargs=case.microgrid_kwargs, **kw)
+    n = 300
+    batch = make(n)
+    W = sum(2 if s.kind == "genset" else 0 if s.kind == "load" else 1 for s in batch.comp.slots)
+    rng = np.random.default_rng(0)
+    a1, a2 = rng.random((n, W)), rng.random((n, W)) * 10
+    a2[:, 0] = rng.random(n)            # the genset goals stay in [0, 1]
+    goal_cols = []
+    col = 0
+    for s in batch.comp.dispatch:
+        if s.kind == "genset":
+            goal_cols.append(col)
+        col += 2 if s.kind == "genset" else 0 if s.kind == "load" else 1
+    a2[:, goal_cols] = rng.random((n, len(goal_cols)))
+    batch.modules_step(torch.from_numpy(a1).to(batch.device), normalized=True)
+    obs, reward, _, info = batch.modules_step(torch.from_numpy(a2).to(batch.device), normalized=False)
+    obs, reward, info = host(obs).copy(), host(reward).copy(), host(info).copy()
+    for e in (0, 127, 128, 299):
+        one = make(1)
+        one.modules_step(torch.from_numpy(a1[e:e + 1]).to(one.device), normalized=True)
+        o, r, _, i = one.modules_step(torch.from_numpy(a2[e:e + 1]).to(one.device), normalized=False)
+        assert np.array_equal(host(o)[0], obs[e], equal_nan=True) and np.array_equal(host(r)[0], reward[e], equal_nan=True)
+        assert np.array_equal(host(i)[0], info[e], equal_nan=True)

@@ -157,3 +157,7 @@ def test_streaming_sum_equals_numpy_sum_at_every_length(lib):
 
 def test_forecast_noise(lib):
     K.check_forecast_noise(lib)
+
+
+def test_modules_step_batch(lib):
+    K.check_modules_step_batch(lib)

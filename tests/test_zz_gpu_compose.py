@@ -120,3 +120,7 @@ def test_microgrid_helpers_on_gpu():
 
 def test_forecast_noise_on_gpu():
     K.check_forecast_noise(None)
+
+
+def test_modules_step_batch_on_gpu():
+    K.check_modules_step_batch(None)
