@@ -618,20 +618,29 @@ class Microgrid:
         first (goal, energy).  `strict_bound` is only defined for grids without a genset, like in the reference."""
         if strict_bound and self.params.has_genset:
             raise TypeError("Unable to normalize scalar value, expected array-like of shape 2")   # utils/space.py:146-147
+        # microgrid.py:358-362: every module with an action space, in the container's listing order (flex modules first
+        # when they are asked for), one np.random.rand() each (genset: goal, energy) -- base_module.py:326-356
+        names = list(self._modules) if sample_flex_modules else [self._caller_name(n) for n in views.control_names(self.params)]
         out = {}
-        for name in views.control_names(self.params):
-            if name == "genset":
+        for name in names:
+            m = self._modules[name][0]
+            if not m.action_space.shape[0]:
+                continue
+            if m._kind == "genset":
                 out[name] = [np.array([np.random.rand(), np.random.rand()])]
-            else:
-                lo, hi = 0.0, 1.0
-                if strict_bound:
-                    m = self._modules[name][0]
-                    act_lo = {"battery": self.params.battery.min_act, "grid": -1 * self.params.grid.max_export if self.params.grid else 0}[name]
-                    act_hi = {"battery": self.params.battery.max_act, "grid": self.params.grid.max_import if self.params.grid else 0}[name]
+                continue
+            lo, hi = 0.0, 1.0
+            if strict_bound:
+                with np.errstate(invalid="ignore"):
+                    act_lo, act_hi = (float(x) for x in m._bounds("act"))
                     spread = (act_hi - act_lo) or 1.0
-                    lo = (-1 * m.max_consumption - act_lo) / spread
-                    hi = (m.max_production - act_lo) / spread
-                out[name] = [np.random.rand() * (hi - lo) + lo]
+                    if m.is_sink:
+                        lo = (-1 * m.max_consumption - act_lo) / spread
+                        lo = 0 if np.isnan(lo) else lo
+                    if m.is_source:
+                        hi = (m.max_production - act_lo) / spread
+                        hi = 0 if np.isnan(hi) else hi
+            out[name] = [np.random.rand() * (hi - lo) + lo]
         return out
 
     def export_params(self):
@@ -739,7 +748,8 @@ class Microgrid:
         return {name: [self._modules[name][0].from_normalized(v, act=act, obs=obs) for v in vals] for name, vals in data_dict.items()}
 
     def get_empty_action(self, sample_flex_modules=False):
-        return {name: [None] for name in views.control_names(self.params)}
+        names = list(self._modules) if sample_flex_modules else [self._caller_name(n) for n in views.control_names(self.params)]
+        return {name: [None] for name in names if self._modules[name][0].action_space.shape[0]}
 
     # ---- introspection -----------------------------------------------------------------------------------
     def state_dict(self, normalized=False):

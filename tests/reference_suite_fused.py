@@ -56,6 +56,18 @@ def test_action_templates_cover_exactly_the_controllable_modules():
             assert module.action_space.shape == (0,) and name not in sampled
 
 
+def test_flex_modules_are_sampled_on_request():
+    m = fixture_microgrid()
+    with_flex = m.sample_action(sample_flex_modules=True)          # test_microgrid.py:230-235 on its load + PV grids
+    assert list(with_flex) == ["renewable", "balancing", "genset", "battery", "grid"]
+    assert set(m.get_empty_action(sample_flex_modules=True)) == set(with_flex) and "load" not in with_flex
+    np.random.seed(11)
+    a = m.sample_action()
+    np.random.seed(11)
+    b = m.sample_action()
+    assert all(np.array_equal(np.asarray(a[k], dtype=float), np.asarray(b[k], dtype=float)) for k in a)      # numpy's global generator
+
+
 def test_step_counter_and_reset():
     m = fixture_microgrid()
     assert m.current_step == 0
