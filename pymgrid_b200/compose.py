@@ -1666,6 +1666,8 @@ class StandaloneModule:
         pre = self.mg._state()
         b.modules_step(row, normalized=normalized)
         flags = int(b.flags[0].item()) & 0xffffffff
+        if flags & FLAG_NOT_A_SINK:         # raised before the module reads its series, so also ahead of the IndexError
+            _raise_for(flags)
         if flags & FLAG_STEP_PAST_END:
             raise IndexError(f"index {self.mg.current_step} is out of bounds for axis 0 with size {len(self.mg)}")
         _raise_for(flags)

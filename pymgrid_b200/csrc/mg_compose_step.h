@@ -448,6 +448,18 @@ MGC_HD void mgc_modules_step(const MgcView &V, int32_t &t, double *fstate, int32
     bool any_series = false;
     for (int m = 0; m < n; ++m) any_series |= mgc_is_timeseries(V.mod[m].kind);
     if (any_series && t0 >= V.T) {
+        /* a renewable asked to ABSORB fails before it reads its series (as_sink compares with max_consumption first,
+           base_module.py:265): report that too, the wrapper raises it ahead of the IndexError */
+        int c0 = 0;
+        for (int m = 0; m < n; ++m) {
+            const MgcModule &M = V.mod[m];
+            if (M.kind == MGC_RENEWABLE) {
+                const double *p = V.cfg + M.param_off;
+                const double a = normalized ? mgc_denormalize(action[c0], p[1], p[2]) : action[c0];
+                if (a < 0) *flags |= MGC_FLAG_NOT_A_SINK;
+            }
+            c0 += (M.kind == MGC_GENSET) ? 2 : (M.kind == MGC_LOAD) ? 0 : 1;
+        }
         *reward_out = NAN;
         *done_out = 1;
         *flags |= MG_FLAG_STEP_PAST_END;
