@@ -1130,7 +1130,7 @@ class ComposedMicrogrid:
     def _obs_dict(self, row, order):
         out = OrderedDict()
         for s in order:
-            out.setdefault(s.name, []).append(np.array(row[s.obs_off:s.obs_off + s.obs_len], dtype=np.float64))
+            out.setdefault(s.name, []).append(views.module_obs(row[s.obs_off:s.obs_off + s.obs_len]))
         return out
 
     def _info_dict(self, info):
@@ -1274,9 +1274,9 @@ class ComposedMicrogrid:
         if self.trajectory_func is not None:      # microgrid.py:221-225: a new episode window per reset
             self._set_window(*self.trajectory_func(self._initial_step, self._final_step))
         obs = self._batch.reset()[0].cpu().numpy()
-        self._log_rows = []
+        flushed, self._log_rows = views.flushed_balance_log(self._log_rows), []
         out = self._obs_dict(obs, self.composition.slots)
-        out["balance"], out["other"] = {}, {}
+        out["balance"], out["other"] = flushed, {}
         return out
 
     def __getattr__(self, item):
@@ -1417,6 +1417,14 @@ def in_fused_scope(modules, add_unbalanced_module=True):
     if any(names.get(k, k) != k for k in ("battery", "genset", "grid", "load")):
         return False
     if "battery" <= names["renewable"] <= "load" or len(horizons) != 1:
+        return False
+    # the container keeps INSERTION order inside a cell (module_container.py:355-413), and that order is the dispatch order
+    # and the summation order of Microgrid.run: the fused kernels step battery before grid and the renewable before the slack
+    # module, so lists given the other way round take the general path
+    position = {m.module_type[0]: i for i, (_, m) in enumerate(named)}
+    if "grid" in position and position["grid"] < position["battery"]:
+        return False
+    if "balancing" in position and position["balancing"] < position["renewable"]:
         return False
     return True
 

@@ -604,12 +604,12 @@ class Microgrid:
             self._engine.set_trajectories(np.array([initial_step]), np.array([final_step]))
             self._module_window = (int(initial_step), int(final_step))
         obs = self._engine.reset()
-        self._log_rows = []
+        flushed, self._log_rows = views.flushed_balance_log(self._log_rows), []
         by_name = self._named(views.obs_row_to_dict(obs[0].cpu().numpy(), self.params, self._obs_order))
         # reset() lists the modules in CONTAINER order (fixed, flex, controllable -- `modules.to_dict()`, microgrid.py:217-219),
         # run() in dispatch order
         out = type(by_name)((name, by_name[name]) for name in self._modules)
-        out["balance"], out["other"] = {}, {}
+        out["balance"], out["other"] = flushed, {}
         return out
 
     # ---- actions -----------------------------------------------------------------------------------------

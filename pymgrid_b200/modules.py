@@ -291,6 +291,12 @@ def params_from_modules(modules, add_unbalanced_module=True, loss_load_cost=10.0
             if name != want:
                 raise NotImplementedError(f"module name {name!r}: only the renewable and the slack module can be renamed (the {kind} "
                                           f"module is addressed as {want!r} in controls, observations and logs)")
+    # the container keeps insertion order inside a cell (module_container.py:355-413) and Microgrid.run dispatches and sums in
+    # that order; the fused kernels' order is battery before grid, renewable before the slack module
+    position = {m.module_type[0]: i for i, (_, m) in enumerate(named)}
+    if ("grid" in position and position["grid"] < position["battery"]) or position["balancing"] < position["renewable"]:
+        raise NotImplementedError("the fused B200 step dispatches battery before grid and the renewable before the slack module; "
+                                  "module lists in another order run on the composed path (pymgrid_b200.Microgrid routes them)")
     if len({name for name, _ in named}) != len(named):      # module_container.py:391-396
         raise NameError("two modules share a name: " + repr(sorted(name for name, _ in named)))
     (ren_name, ren), (_, load), (_, bat), (unb_name, unb) = (by_kind[k][0] for k in ("renewable", "load", "battery", "balancing"))

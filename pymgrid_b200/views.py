@@ -46,8 +46,15 @@ def obs_row_to_dict(row, p, order="gym_sorted"):
         if name == "unbalanced_energy":
             out[name] = [np.array([])]
         elif name in sl:
-            out[name] = [np.array(row[sl[name]], dtype=np.float64)]
+            out[name] = [module_obs(row[sl[name]])]
     return out
+
+
+def module_obs(values):
+    """one module's normalised state as the reference returns it: an ndarray, or a Python float when the state has a single
+    element (a time-series module without a forecast) -- ModuleSpace.normalize hands back `.item()` for those"""
+    arr = np.array(values, dtype=np.float64)
+    return float(arr[0]) if arr.shape == (1,) else arr
 
 
 def info_row_to_dict(info, flags, p):
@@ -241,3 +248,14 @@ def caller_names(d, p):
         return d
     nm = lambda k: {"pv": p.renewable_name, "unbalanced_energy": p.unbalanced_name}.get(k, k)      # noqa: E731
     return type(d)(((nm(k) if not isinstance(k, tuple) else (nm(k[0]),) + k[1:]), v) for k, v in d.items())
+
+
+def flushed_balance_log(rows):
+    """what Microgrid.reset() returns under 'balance': the balance log it has just flushed, {field: [value per step]}
+    (microgrid.py:205-219: `self._balance_logger.flush()`)"""
+    out = OrderedDict()
+    for r in rows:
+        for (name, _, field), v in r.items():
+            if name == "balance":
+                out.setdefault(field, []).append(v)
+    return dict(out)

@@ -71,6 +71,7 @@ def test_microgrid_surface_against_the_live_reference(n):
     same_nested({k: v for k, v in r1.items() if k not in ("balance", "other")}, {k: v for k, v in r2.items() if k not in ("balance", "other")},
                 (n, "reset"))
     assert list(r1.keys()) == list(r2.keys()) and len(ours.get_log()) == 0
+    assert {k: [float(x) for x in v] for k, v in r1["balance"].items()} == r2["balance"] and r1["other"] == r2["other"] == {}
 
 
 @pytest.mark.parametrize("n", range(25))
@@ -94,3 +95,80 @@ def test_discrete_env_against_the_live_reference(n):
         assert r1 == r2 and d1 == d2 and np.array_equal(o1, o2), (n, k)
         same_nested(i1, i2, (n, k, "info"))
     same_frame(ref.log, ours.log, (n, "env log"))
+
+
+def draw_fused(rng, ns, T):
+    """a random microgrid INSIDE the fused kernels' scope (one load, renewable, battery; genset / grid optional; one horizon)"""
+    H = int(rng.choice([0, 1, 4, 23]))
+    ts = dict(forecaster="oracle", forecast_horizon=H) if H else {}
+    mx = float(rng.uniform(20, 400))
+    mods = [ns.LoadModule(time_series=rng.uniform(5, 200) * rng.random(T), **ts),
+            (str(rng.choice(["pv", "renewable", "PV"])), ns.RenewableModule(time_series=rng.uniform(5, 200) * np.clip(rng.random(T) - 0.3, 0, None), **ts)),
+            ns.BatteryModule(min_capacity=float(rng.choice([0.0, 0.2 * mx])), max_capacity=mx, max_charge=float(rng.uniform(0.05, 1.2) * mx),
+                             max_discharge=float(rng.uniform(0.05, 1.2) * mx), efficiency=float(rng.choice([1.0, rng.uniform(0.5, 0.99)])),
+                             battery_cost_cycle=float(rng.uniform(0, 0.5)), init_soc=float(rng.uniform(0.3, 1.0)))]
+    arch = int(rng.integers(0, 4))
+    if arch in (0, 1):
+        gmax = float(rng.uniform(20, 200))
+        mods.append(ns.GensetModule(running_min_production=float(rng.choice([0.0, 0.3 * gmax])), running_max_production=gmax,
+                                    genset_cost=float(rng.uniform(0, 1)), co2_per_unit=float(rng.uniform(0, 3)),
+                                    cost_per_unit_co2=float(rng.uniform(0, 0.5)), start_up_time=int(rng.integers(0, 3)),
+                                    wind_down_time=int(rng.integers(0, 3)), init_start_up=bool(rng.integers(0, 2))))
+    if arch in (0, 2):
+        g = np.stack([rng.uniform(0.05, 0.9, T), rng.uniform(0, 0.4, T), rng.uniform(0, 0.6, T), (rng.random(T) > 0.2).astype(float)], axis=1)
+        mods.append(ns.GridModule(max_import=float(rng.uniform(10, 300)), max_export=float(rng.choice([0.0, rng.uniform(10, 300)])),
+                                  time_series=g[:, :int(rng.choice([3, 4]))], cost_per_unit_co2=float(rng.uniform(0, 0.5)), **ts))
+    order = rng.permutation(len(mods))
+    return [mods[i] for i in order], dict(loss_load_cost=float(rng.uniform(1, 20)), overgeneration_cost=float(rng.uniform(0, 5)))
+
+
+@pytest.mark.parametrize("g", range(30))
+def test_random_fused_microgrids_built_from_modules_against_the_live_reference(g):
+    from oracle.ref_loader import load_reference
+    load_reference()
+    import pymgrid
+    import pymgrid.modules as R
+    from pymgrid.algos import RuleBasedControl as RefRBC
+    import pymgrid_b200
+    from pymgrid_b200 import modules as M
+    from pymgrid_b200.algos import RuleBasedControl
+    import ctypes
+    from pymgrid_b200.compose import in_fused_scope
+    from tests import hostsim
+    T = 40
+    extra = lambda mods: {} if in_fused_scope(mods) else {"_library": ctypes.CDLL(hostsim.build())}      # noqa: E731
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m1, kw = draw_fused(np.random.default_rng(600 + g), R, T)
+        m2, _ = draw_fused(np.random.default_rng(600 + g), M, T)
+        ref, ours = pymgrid.Microgrid(m1, **kw), pymgrid_b200.Microgrid(m2, obs_order="container", **extra(m2), **kw)
+    # a list that names the grid before the battery is dispatched in that order by the reference: it takes the composed path
+    assert type(ours).__name__ in ("Microgrid", "ComposedMicrogrid") and repr(ref) == repr(ours)
+    rng = np.random.default_rng(g)
+    for k in range(25):
+        normalized = k % 3 != 2
+        a = {}
+        for name, lst in ref.controllable.iterdict():
+            mod = lst[0]
+            n = mod.action_space.shape[0]
+            if normalized:
+                v = rng.random(n)
+            else:
+                lo, hi = np.atleast_1d(mod.min_act).astype(float), np.atleast_1d(mod.max_act).astype(float)
+                v = lo - 0.3 * (hi - lo) + 1.6 * (hi - lo) * rng.random(n)
+                if n == 2:
+                    v[0], v[1] = rng.random(), max(v[1], 0.0)
+            a[name] = [v if n > 1 else float(v[0])]
+        o1, r1, d1, i1 = ref.run(a, normalized=normalized)
+        o2, r2, d2, i2 = ours.run(a, normalized=normalized)
+        assert r1 == r2 and d1 == d2, (g, k)
+        same_nested(o1, o2, (g, k, "obs"))
+        same_nested(i1, i2, (g, k, "info"))
+    same_frame(ref.get_log(), ours.get_log(), (g, "log"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rbc1 = RefRBC(pymgrid.Microgrid(draw_fused(np.random.default_rng(600 + g), R, T)[0], **kw))
+        rbc2 = RuleBasedControl(pymgrid_b200.Microgrid(m2, obs_order="container", **extra(m2), **kw))
+    rows = lambda pl: [(el.module, el.module_actions, el.action, el.marginal_cost) for el in pl]      # noqa: E731
+    assert rows(rbc1.priority_list) == rows(rbc2.priority_list), g
+    same_frame(rbc1.run(max_steps=15), rbc2.run(max_steps=15), (g, "rbc log"))

@@ -33,7 +33,7 @@ def test_microgrid_run_returns_reference_types_and_values(golden, n):
         assert isinstance(reward, float) and isinstance(done, bool) and isinstance(obs, dict) and isinstance(info, dict)
         assert list(obs.keys()) == [x for x in ("load", "genset", "battery", "grid", "pv", "unbalanced_energy")
                                     if x in ("load", "battery", "pv", "unbalanced_energy") or hasattr(m.modules, x)]
-        flat = np.concatenate([obs[name][0] for name in SORTED if name in obs])
+        flat = np.concatenate([np.atleast_1d(obs[name][0]) for name in SORTED if name in obs])
         np.testing.assert_array_equal(flat, z[f"s{n}_o0"][k])
         assert reward == z[f"s{n}_r0"][k] and done == bool(z[f"s{n}_d0"][k])
         assert info["load"][0]["absorbed_energy"] == z[f"s{n}_i0"][k][0]
@@ -272,7 +272,7 @@ def test_microgrid_from_reference_style_modules(golden, i):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         m = Microgrid(custom_modules(z, i), loss_load_cost=9.0, overgeneration_cost=1.5)
-    flat = lambda obs: np.concatenate([obs[name][0] for name in SORTED if name in obs])   # noqa: E731
+    flat = lambda obs: np.concatenate([np.atleast_1d(obs[name][0]) for name in SORTED if name in obs])   # noqa: E731
     np.testing.assert_array_equal(flat(m.reset()), z[f"c{i}_reset_obs"])
     for k, a in enumerate(z[f"c{i}_a"]):
         obs, reward, done, info = m.run(control(m.params, a))
@@ -299,7 +299,7 @@ def test_battery_soc_before_the_first_update(golden, i):
         m = Microgrid(fuzz_modules(z, i), loss_load_cost=s["llc"], overgeneration_cost=s["ogc"])
     if s["initial_step"]:
         m.initial_step = int(s["initial_step"])
-    flat = lambda obs: np.concatenate([obs[name][0] for name in SORTED if name in obs])   # noqa: E731
+    flat = lambda obs: np.concatenate([np.atleast_1d(obs[name][0]) for name in SORTED if name in obs])   # noqa: E731
     np.testing.assert_array_equal(flat(m.reset()), z[f"f{i}_reset_obs"])
     before = z[f"f{i}_soc_before"]
     assert m.modules.battery[0].soc == before[0] == s["b_init_soc"] and m.state_dict()["battery"][0]["soc"] == before[1]
@@ -335,7 +335,7 @@ def test_randomised_grids_through_the_drop_in_classes(golden, i):
             m.initial_step = int(s["initial_step"])
             m.reset()
         return m
-    flat = lambda obs: np.concatenate([obs[name][0] for name in SORTED if name in obs])   # noqa: E731
+    flat = lambda obs: np.concatenate([np.atleast_1d(obs[name][0]) for name in SORTED if name in obs])   # noqa: E731
     m = build()
     names = ["load"] + (["genset"] if s["has_gen"] else []) + ["battery"] + (["grid"] if s["has_grid"] else []) + ["pv", "balancing"]
     np.testing.assert_array_equal(flat(m.reset()), g("reset_obs"))
