@@ -253,7 +253,8 @@ class _BaseEnv:
         info_row, r = info[0].cpu().numpy(), float(reward[0].item())
         if pre is not None and not flags & (1 << 5):        # a step past the end logs nothing (the reference raises there)
             self._log_step(pre, info_row, r, action)
-        return (self._select(obs[0].cpu().numpy()), r, bool(done[0].item()), views.info_row_to_dict(info_row, flags, self.params))
+        return (self._select(obs[0].cpu().numpy()), r, bool(done[0].item()),
+                views.caller_names(views.info_row_to_dict(info_row, flags, self.params), self.params))
 
     def __len__(self):
         return len(self.params)
