@@ -265,3 +265,59 @@ def test_random_modules_on_their_own_against_the_live_reference():
         cp._STANDALONE_LIBRARY = saved
     print(f"{compared} module steps compared, {raised} runs ended where the reference raised")
     assert compared > 2000 and raised > 20
+
+
+def test_composed_module_views_against_the_live_reference():
+    """every attribute the reference's in-repo callers read from a module on random compositions, after a few
+    steps; state dicts, cost info, normalisation helpers"""
+    from oracle.ref_loader import load_reference
+    load_reference()
+    import pymgrid
+    import pymgrid.modules as R
+    from pymgrid_b200 import modules as M
+    from pymgrid_b200.compose import ComposedMicrogrid
+    attrs = ("max_production", "max_consumption", "min_production", "production_marginal_cost", "absorption_marginal_cost",
+             "marginal_cost", "state", "min_obs", "max_obs", "min_act", "max_act", "is_source", "is_sink", "current_step",
+             "initial_step", "final_step", "soc", "current_charge", "current_status", "goal_status", "import_price", "export_price",
+             "co2_per_kwh", "grid_status", "forecast_horizon", "max_capacity", "efficiency", "running_max_production", "max_import",
+             "loss_load_cost", "current_load", "current_renewable")
+    lib = ctypes.CDLL(hostsim.build())
+    compared = 0
+    for g in range(30):
+        T = 30
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                ref = pymgrid.Microgrid(draw(np.random.default_rng(3000 + g), R, T), add_unbalanced_module=False)
+            except Exception:      # noqa: BLE001
+                continue
+            ours = ComposedMicrogrid(draw(np.random.default_rng(3000 + g), M, T), add_unbalanced_module=False, _library=lib)
+        rng = np.random.default_rng(g)
+        for k in range(3):
+            a = {name: [rng.random(m.action_space.shape[0]) if m.action_space.shape[0] > 1 else rng.random() for m in lst]
+                 for name, lst in ref.controllable.iterdict()}
+            try:
+                ref.run(a)
+            except Exception:      # noqa: BLE001
+                break
+            ours.run(a)
+            for name, lst in ref.modules.iterdict():
+                for j, theirs in enumerate(lst):
+                    mine = ours.modules[name][j]
+                    for attr in attrs:
+                        try:
+                            want = getattr(theirs, attr)
+                        except Exception:      # noqa: BLE001
+                            continue
+                        if want is NotImplemented:
+                            continue
+                        got = getattr(mine, attr)
+                        same = np.array_equal(np.asarray(want, dtype=np.float64), np.asarray(got, dtype=np.float64), equal_nan=True)
+                        assert same, (g, k, name, j, attr, want, got)
+                        compared += 1
+                    sd1, sd2 = theirs.state_dict(), mine.state_dict()
+                    assert list(sd1) == list(sd2), (g, name, j)
+                    assert np.array_equal(np.array(list(sd1.values()), dtype=float), np.array(list(sd2.values()), dtype=float))
+            c1, c2 = ref.get_cost_info(), ours.get_cost_info()
+            assert {k_: [dict(d) for d in v] for k_, v in c1.items()} == {k_: [dict(d) for d in v] for k_, v in c2.items()}
+    assert compared > 3000

@@ -223,3 +223,52 @@ def test_random_fused_discrete_envs_against_the_live_reference(g):
         assert r1 == r2 and d1 == d2 and np.array_equal(o1, o2), (g, k)
         same_nested(i1, i2, (g, k, "info"))
     same_frame(ref.log, ours.log, (g, "env log"))
+
+
+ATTRS = ("max_production", "max_consumption", "min_production", "production_marginal_cost", "absorption_marginal_cost", "marginal_cost",
+         "state", "min_obs", "max_obs", "min_act", "max_act", "is_source", "is_sink", "current_step", "initial_step", "final_step",
+         "soc", "current_charge", "min_soc", "max_soc", "current_status", "goal_status", "import_price", "export_price", "co2_per_kwh",
+         "grid_status", "forecast_horizon", "max_capacity", "efficiency", "running_max_production", "max_import", "loss_load_cost")
+
+
+@pytest.mark.parametrize("n", range(25))
+def test_module_views_and_normalisation_against_the_live_reference(n):
+    """every attribute the reference's in-repo callers read from a module, after a few steps, and
+    Microgrid.to_normalized / from_normalized, on all 25 scenarios"""
+    from oracle.ref_loader import load_reference
+    load_reference()
+    import pymgrid
+    from pymgrid_b200.microgrid import Microgrid
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref, ours = pymgrid.Microgrid.from_scenario(n), Microgrid.from_scenario(n)
+    rng = np.random.default_rng(n)
+    for k in range(4):
+        a = {name: [rng.random(2) if name == "genset" else rng.random()] for name in ref.get_empty_action()}
+        ref.run(a), ours.run(a)
+        for name, lst in ref.modules.iterdict():
+            mine = ours.modules[name][0]
+            for attr in ATTRS:
+                try:
+                    want = getattr(lst[0], attr)
+                except Exception:      # noqa: BLE001 -- the reference module has no such attribute
+                    continue
+                if want is NotImplemented:
+                    continue
+                got = getattr(mine, attr)
+                assert np.array_equal(np.asarray(want, dtype=np.float64), np.asarray(got, dtype=np.float64)), (n, k, name, attr, want, got)
+            if name == "genset":
+                for goal in (0, 1):
+                    assert lst[0].next_status(goal) == mine.next_status(goal)
+                    assert lst[0].next_max_production(goal) == mine.next_max_production(goal)
+            assert lst[0].module_type == mine.module_type and tuple(lst[0].name) == tuple(mine.name)
+            sd1, sd2 = lst[0].state_dict(), mine.state_dict()
+            assert list(sd1) == list(sd2) and np.array_equal(np.array(list(sd1.values()), dtype=float), np.array(list(sd2.values()), dtype=float))
+    act = {name: [rng.random(2) if name == "genset" else rng.random()] for name in ref.get_empty_action()}
+    d1, d2 = ref.from_normalized(act, act=True), ours.from_normalized(act, act=True)
+    same_nested(d1, d2, (n, "from_normalized"))
+    same_nested(ref.to_normalized(d1, act=True), ours.to_normalized(d2, act=True), (n, "to_normalized"))
+    obs = ref.reset()
+    obs = {k: v for k, v in obs.items() if k not in ("balance", "other")}
+    same_nested(ref.from_normalized(obs, obs=True), ours.from_normalized(obs, obs=True), (n, "obs denormalised"))
+    assert ref.get_forecast_horizon() == ours.get_forecast_horizon()
