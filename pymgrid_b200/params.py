@@ -152,6 +152,12 @@ class MicrogridParams:
         if self.reward_shaper == "pv_curtailment" and self.renewable_name != "pv":
             # sum_module_val(info, 'pv', ...) finds no such module and returns 0.0 (reward_shaping/base.py:11-16)
             raise ValueError("PVCurtailmentShaper reads the module named 'pv'; this grid names it " + repr(self.renewable_name))
+        if self.reward_shaper == "battery_discharge" and self.unbalanced_name != "unbalanced_energy":
+            # the shaper sums the loss load of the module NAMED 'unbalanced_energy' (battery_discharge_shaper.py:25); under
+            # another name (e.g. the 'balancing' module Microgrid(modules) appends) the reference silently counts none
+            raise ValueError("BatteryDischargeShaper reads the loss load of the module named 'unbalanced_energy'; this grid names "
+                             "its slack module " + repr(self.unbalanced_name) + " (pass ('unbalanced_energy', UnbalancedEnergyModule(...)) "
+                             "with add_unbalanced_module=False)")
         self.load_ts = -np.abs(np.ascontiguousarray(self.load_ts, dtype=np.float64).reshape(-1))
         self.pv_ts = np.abs(np.ascontiguousarray(self.pv_ts, dtype=np.float64).reshape(-1))
         if self.grid is not None:
