@@ -624,3 +624,28 @@ def check_modules_step_batch(lib):
         o, r, _, i = one.modules_step(torch.from_numpy(a2[e:e + 1]).to(one.device), normalized=False)
         assert np.array_equal(host(o)[0], obs[e], equal_nan=True) and np.array_equal(host(r)[0], reward[e], equal_nan=True)
         assert np.array_equal(host(i)[0], info[e], equal_nan=True)
+
+
+def check_control_dict_conventions(lib):
+    """Microgrid.run's control conventions (microgrid.py:262-284): a bare scalar stands for [scalar], unknown keys warn,
+    a missing controllable module raises ValueError"""
+    import warnings
+    from pymgrid_b200 import modules as M
+    kw = {} if lib is None else {"_library": lib}
+    rng = np.random.default_rng(1)
+
+    def build():
+        r = np.random.default_rng(1)
+        return ComposedMicrogrid([M.LoadModule(time_series=50 + 50 * r.random(20)), M.LoadModule(time_series=20 * r.random(20)),
+                                  M.RenewableModule(time_series=80 * r.random(20)), M.BatteryModule(10, 100, 50, 50, 0.9, init_soc=0.5),
+                                  M.GridModule(100, 50, np.ones((20, 3)) * [0.2, 0.1, 0.3])], **kw)
+    a, b = build(), build()
+    for _ in range(3):
+        x, y = float(rng.random()), float(rng.random())
+        assert a.run({"battery": x, "grid": y})[1] == b.run({"battery": [x], "grid": [y]})[1]
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        a.run({"battery": [0.3], "grid": [0.2], "extra": [1.0]})
+    assert any("Ignoring the following keys" in str(w.message) for w in caught)
+    with pytest.raises(ValueError, match='Control for module "grid" not found'):
+        a.run({"battery": [0.3]})

@@ -161,3 +161,7 @@ def test_forecast_noise(lib):
 
 def test_modules_step_batch(lib):
     K.check_modules_step_batch(lib)
+
+
+def test_control_dict_conventions(lib):
+    K.check_control_dict_conventions(lib)

@@ -124,3 +124,7 @@ def test_forecast_noise_on_gpu():
 
 def test_modules_step_batch_on_gpu():
     K.check_modules_step_batch(None)
+
+
+def test_control_dict_conventions_on_gpu():
+    K.check_control_dict_conventions(None)
