@@ -349,6 +349,10 @@ def main():
     ap.add_argument("--no-ring", action="store_true",
                     help="per-env series batches (generator workload): use the persistent kernel that normalises whole windows per "
                          "row instead of the one that keeps sliding windows in shared memory (A/B)")
+    ap.add_argument("--emit", default="image", choices=("image", "lsu"),
+                    help="row emitter: shared-memory images + TMA bulk stores (default) or the per-lane 16-byte store emitters (A/B)")
+    ap.add_argument("--image-shape", type=int, default=None, help="MG_OPT_IMAGE_SHAPE index (tuning)")
+    ap.add_argument("--no-specialised", action="store_true", help="persistent kernel without the owner / emitter warp split (A/B)")
     ap.add_argument("--preheat", type=float, default=0.2, help="seconds of untimed steps before the warm-up (0 under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -375,6 +379,12 @@ def main():
     bm = build_engine(B, dev, rank, world, args.workload, args.obs_f32)
     if args.no_ring:
         bm.set_rollout_ring(False)
+    if args.emit == "lsu":
+        bm.set_emit_image(False)
+    if args.image_shape is not None:
+        bm.set_image_shape(args.image_shape)
+    if args.no_specialised or (args.emit == "lsu" and args.ragged):
+        bm.set_rollout_specialised(False)      # (LSU emitters, envs at unrelated steps: the plain persistent kernel is the faster one)
     groups = bm.groups
 
     def rand_actions(steps, g):
@@ -392,7 +402,6 @@ def main():
     if args.ragged:
         for g in groups:
             g.step.copy_(torch.randint(0, 8760 - 2 * (W + K) - 64 if 2 * (W + K) < 4000 else 100, (g.n_envs,), dtype=torch.int32, device=dev, generator=gen))
-        bm.set_rollout_specialised(False)      # envs at unrelated steps: the plain persistent kernel is the faster one
     state0 = bm.state_dict()
     launchers = {}   # one pre-bound launcher per (action slot, obs slot)
 
@@ -606,7 +615,7 @@ def main():
             "dtype": "f64" if not args.obs_f32 else "f64 arithmetic, f32 observation output (non-canonical)",
             "data": "pymgrid25 scenario parameters + series (bundled), synthetic U[0,1) actions",
             "config": {"workload": WORKLOADS[args.workload],
-                       "batch_per_gpu": B, "global_batch": world * B, "forecast_horizon": 23, "path": args.path, "ragged_steps": bool(args.ragged),
+                       "batch_per_gpu": B, "global_batch": world * B, "forecast_horizon": 23, "path": args.path, "ragged_steps": bool(args.ragged), "emit": args.emit, "image_shape": args.image_shape, "specialised": not args.no_specialised,
                        "l2": f"inputs larger than L2: obs ring of {R} buffers = {ring_bytes / 1e6:.0f} MB and action ring = {act_bytes / 1e6:.0f} MB per GPU (L2 126 MB)",
                        "parallelism": f"batch sharded over {world} GPU(s), no collective on the step path"},
             "gpu_launches": launches,

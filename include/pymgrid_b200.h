@@ -316,11 +316,17 @@ int mg_forecast_noise(MgHandle *h, const MgForecastNoise *noise /* DEVICE [n_cfg
  * kernel when every group writes observations.  It wins when the envs of a tile advance in lock-step (11.5 vs 12.4
  * us/step at 65 536 envs) and loses when every env is at its own step (39.6 vs 29 us/step): hosts that install per-env
  * trajectory windows turn it off. */
-enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2 };
+enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2, MG_OPT_EMIT_IMAGE = 3, MG_OPT_IMAGE_SHAPE = 4 };
 /* MG_OPT_ROLLOUT_RING (default 1): batches with per-env series (MG_LAYOUT_SCALED_SERIES / grid_status_bits) run mg_rollout
  * with every env's normalised load / pv windows held in shared memory (H + 2 slots per env and series; one new value per
  * env, series and step instead of a whole window per row) when all horizons are <= 24.  0 selects the kernel that
  * normalises whole windows per row (the one mg_step uses). */
+/* MG_OPT_EMIT_IMAGE (default 1): observation rows are assembled in shared-memory images and leave the SM as TMA bulk stores
+ * (cp.async.bulk shared -> global, several rows per store) instead of per-lane 16-byte stores; applies when rows are f64,
+ * 1 + H <= 32 and the grid block starts at an even element, else the LSU emitters run.  0 selects the LSU emitters.
+ * MG_OPT_IMAGE_SHAPE (default 0): which instantiated (rows per bulk store, image buffers per emitting warp, rows gathered
+ * together) shape the image kernels use -- 0: (4, 2, 2), 1: (2, 2, 2), 2: (4, 2, 4), 3: (8, 2, 2); a tuning knob, results
+ * do not depend on it. */
 int mg_set_option(MgHandle *h, int option, int value);
 
 /*

@@ -16,6 +16,8 @@ MG_OBS_GYM_SORTED, MG_OBS_CONTAINER, MG_OBS_GYM_SORTED_PV_FIRST = 0, 1, 2
 MG_MOD_NONE, MG_MOD_GENSET, MG_MOD_BATTERY, MG_MOD_GRID = -1, 0, 1, 2
 MG_OPT_ROLLOUT_SPECIALISED = 1
 MG_OPT_ROLLOUT_RING = 2
+MG_OPT_EMIT_IMAGE = 3
+MG_OPT_IMAGE_SHAPE = 4
 
 FLAG_NAMES = {
     1 << 0: "GENSET_GOAL_RANGE", 1 << 1: "GENSET_AS_SINK", 1 << 2: "BALANCE", 1 << 3: "BATTERY_MIN_CAP",

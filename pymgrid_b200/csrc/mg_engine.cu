@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 
 #include "pymgrid_b200.h"
@@ -48,6 +49,7 @@
 // persistent kernel for per-env series: sliding load / pv windows live in shared memory, H + 2 slots per env and series
 #define MG_RING_MAX 26      // forecast horizons up to 24
 #define MG_MIN_CTAS_RING 5  // 40 KB of shared memory per CTA
+#define MG_N_IMAGE_SHAPES 4 // (rows per bulk store, buffers) shapes of the image-emitter kernels, see img_kernel_for
 // runs of at least this many rows stage their grid window in shared memory with TMA
 
 enum { KIND_BAT = 0, KIND_GEN = 1, KIND_GRID = 2, KIND_LOAD = 3, KIND_PV = 4 };
@@ -62,6 +64,7 @@ struct DevGroup {
     int32_t tma_ok;                     // the grid window can be staged with cp.async.bulk (16-byte aligned image slot)
     int32_t state_start, state_genset_first;   // the battery + genset run: first element and order
     int32_t long_path;                         // rows too long for the staged path, or a state run at an odd element
+    int32_t img_ok;                            // rows can be assembled by the image emitter (even grid offset, 1 + H <= 32)
     int32_t *step;
     double *charge;
     uint32_t *genset;
@@ -126,6 +129,20 @@ __device__ __forceinline__ void tma_load(void *sdst, const void *gsrc, uint32_t 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// shared -> global bulk copy (SASS UBLKCP.G.S) in the issuing thread's bulk async-group; both addresses and the size are
+// multiples of 16.  The source must stay untouched until bulk_wait_read says the copy has read it.
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups may still be reading their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// all of this thread's bulk groups have completed (their global writes included)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// order this thread's shared-memory writes (generic proxy) before later bulk copies (async proxy) that read them
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Aggregate reward of the tile's envs for logging: butterfly reduction with warp shuffles, one atomicAdd per warp.
 // Called by whole warps (all 32 lanes); lanes without an env (or with a rejected step, reward NaN) contribute 0.
 __device__ __forceinline__ void add_reward_total(double *total, double reward, bool has) {
@@ -839,6 +856,173 @@ __device__ __forceinline__ void warp_emit_rows_long(const LaunchParams &P, const
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Image emitter: rows that share no window with their neighbours (per-env series, envs at unrelated steps).
+// A warp assembles RC consecutive rows in a shared-memory image -- grid window by 16-byte read-only loads from the
+// normalised table (L1 / L2 resident), load / pv window from the env's shared-memory ring, the tables or normalised on the
+// fly, battery / genset values from the tile record -- and hands the RC * obs_dim * 8 contiguous output bytes to the TMA
+// unit as ONE bulk store (cp.async.bulk shared -> global).  All loads of a chunk are issued before its first
+// shared-memory store, so their latencies overlap across rows; the bulk store drains in the background while the next
+// chunk is gathered into the other image buffer (NB buffers per warp, recycled through the bulk-group queue).  No lane
+// ever issues a global store: the LSU only sees the gathers.
+// Needs obs_dim even, 1 + H <= 32, an even grid offset (16-byte aligned pairs in the image) and f64 rows.
+// ------------------------------------------------------------------------------------------------------------------
+// shared-memory accesses by 32-bit address (the emitter's address arithmetic stays in 32 bits, one add per access)
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_v2f64(uint32_t a, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int4 lds_v4s32(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
+struct ImgCtx {     // per group and lane, hoisted out of every loop
+    int T, ringR, row_bytes;
+    int lk;                              // window element this lane copies (clamped to a valid one for lanes past the window)
+    const double *pv_src, *load_src;     // table pointers already offset by this lane's window element
+    const double2 *g0_src, *g1_src;      // grid table pointers already offset by this lane's two pairs (clamped)
+    uint32_t a_pv, a_load, a_state, a_g0, a_g1;   // byte offsets of this lane's destinations inside a row image
+    uint32_t s_state;                    // byte offset of this lane's state element inside a TileEnv record
+    int k0, k1;                          // forecast row of this lane's two grid pairs (status column patch)
+    bool win_lane, state_lane, g0, g1, patch_lane, own_status, has_grid;
+};
+__device__ __forceinline__ ImgCtx img_ctx(const LaunchParams &P, const DevGroup &G) {
+    const RowStarts rs = row_starts(G);
+    const int lane = threadIdx.x & 31, rows = 1 + G.horizon, n_state = 2 + 4 * G.has_genset;
+    ImgCtx x;
+    x.T = P.T; x.ringR = G.horizon + 2; x.row_bytes = G.obs_dim * (int)sizeof(double);
+    x.has_grid = G.has_grid != 0;
+    x.win_lane = lane < rows; x.state_lane = lane < n_state;
+    x.lk = min(lane, rows - 1);
+    x.g0 = x.has_grid && lane < 2 * rows; x.g1 = x.has_grid && lane + 32 < 2 * rows;
+    x.pv_src = P.pv_nrm + x.lk; x.load_src = P.load_nrm + x.lk;
+    x.g0_src = reinterpret_cast<const double2 *>(P.grid_nrm) + (x.g0 ? lane : 0);
+    x.g1_src = reinterpret_cast<const double2 *>(P.grid_nrm) + (x.g1 ? lane + 32 : 0);
+    x.a_pv = 8u * (rs.pv + lane); x.a_load = 8u * (rs.load + lane); x.a_state = 8u * (rs.state + lane);
+    x.a_g0 = 8u * (rs.grid + 2 * lane); x.a_g1 = 8u * (rs.grid + 2 * (lane + 32));
+    x.s_state = (uint32_t)offsetof(TileEnv, state) + 8u * min(lane, n_state - 1);
+    x.k0 = lane >> 1; x.k1 = (lane + 32) >> 1;
+    x.own_status = G.status_bits != nullptr;
+    // odd grid pairs hold (co2, status); 32 is even, so both of a lane's pairs agree
+    x.patch_lane = x.own_status && (lane & 1) != 0;
+    return x;
+}
+
+struct ImgRow {     // what one lane holds of one row between the gather and the scatter
+    double2 g0, g1;
+    double pv, load, state;
+};
+
+// gather this lane's share of row r (tile record at shared address env_a + 64 r): every load is unconditional (clamped
+// addresses) and nothing diverges between lanes
+template <bool kHetero, bool kRing>
+__device__ __forceinline__ ImgRow img_gather(const LaunchParams &P, const DevGroup &G, const ImgCtx &x, uint32_t env_a,
+                                             const HeteroEnv *__restrict__ het, uint32_t ring_a, int r, int e_base) {
+    static_assert(sizeof(TileEnv) == 64, "the emitter addresses tile records by hand");
+    ImgRow v;
+    const uint32_t rec = env_a + 64u * (uint32_t)r;
+    const int4 hd = lds_v4s32(rec);      // off_grid, off_load, off_pv, special
+    const int off_grid = hd.x, off_load = hd.y, off_pv = hd.z, special = kHetero ? hd.w : -1;
+    if (x.has_grid) {   // group-uniform
+        v.g0 = __ldg(x.g0_src + (off_grid >> 1));
+        v.g1 = __ldg(x.g1_src + (off_grid >> 1));
+        if (kHetero && x.own_status && special >= 0) {   // warp-uniform
+            // bounds of the status column: (0, 1) on a weak grid, (1, 1) -> spread 1 otherwise (utils/space.py:204-205)
+            uint32_t w;
+            bool weak;
+            if (kRing) { w = (uint32_t)off_load; weak = (off_pv >> 16) != 0; }
+            else { w = status_window(G, e_base + r, special); weak = het[r].weak != 0; }
+            const double s0 = weak ? (special + x.k0 < x.T ? (double)((w >> x.k0) & 1u) : 0.5) : 0.0;
+            const double s1 = weak ? (special + x.k1 < x.T ? (double)((w >> (x.k1 & 31)) & 1u) : 0.5) : 0.0;
+            v.g0.y = x.patch_lane ? s0 : v.g0.y;
+            v.g1.y = x.patch_lane ? s1 : v.g1.y;
+        }
+    } else {
+        v.g0 = v.g1 = make_double2(0.0, 0.0);
+    }
+    if (kRing && special >= 0) {   // warp-uniform
+        int slot = (off_pv & 0xffff) + x.lk;
+        slot -= slot >= x.ringR ? x.ringR : 0;
+        const uint32_t a = ring_a + 8u * (uint32_t)(r * MG_RING_MAX + slot);
+        v.load = lds_f64(a);                                     // RingShared::win[0][r][slot]
+        v.pv = lds_f64(a + 8u * MG_TILE * MG_RING_MAX);          // RingShared::win[1][r][slot]
+    } else if (kHetero && !kRing && special >= 0 && het[r].scaled) {
+        // (profile * scale - low) / spread, or the normalised forecaster fill past the end (as emit_row_hetero)
+        const HeteroEnv &hv = het[r];
+        const int idx = special + x.lk;
+        const bool in = idx < x.T;
+        const double rp = in ? __ldg(P.pv_raw + hv.pv_base + idx) : 0.0;
+        const double rl = in ? __ldg(P.load_raw + hv.load_base + idx) : 0.0;
+        const double np_ = (rp * hv.pv_scale - hv.pv_low) / hv.pv_spread;
+        const double nl = (rl * hv.load_scale - hv.load_low) / hv.load_spread;
+        v.pv = in ? np_ : hv.pv_fill;
+        v.load = in ? nl : hv.load_fill;
+    } else {
+        v.pv = __ldg(x.pv_src + off_pv);
+        v.load = __ldg(x.load_src + off_load);
+    }
+    v.state = lds_f64(rec + x.s_state);
+    return v;
+}
+
+// write this lane's share of a row into the image at shared address row_a: five predicated stores
+__device__ __forceinline__ void img_scatter(const ImgCtx &x, uint32_t row_a, const ImgRow &v) {
+    if (x.g0) sts_v2f64(row_a + x.a_g0, v.g0);
+    if (x.g1) sts_v2f64(row_a + x.a_g1, v.g1);
+    if (x.win_lane) sts_f64(row_a + x.a_pv, v.pv);
+    if (x.win_lane) sts_f64(row_a + x.a_load, v.load);
+    if (x.state_lane) sts_f64(row_a + x.a_state, v.state);
+}
+
+// env_a / ring_a / img_a: shared-memory addresses of the tile records of this step, of the RingShared block and of the
+// calling warp's NB image buffers (warp-uniform values, so that the bulk store's operands stay in uniform registers)
+template <int RC, int NB, int GB, bool kHetero, bool kRing>
+__device__ __forceinline__ void warp_emit_rows_img(const LaunchParams &P, const DevGroup &G, const ImgCtx &x, uint32_t env_a,
+                                                   const HeteroEnv *__restrict__ het, uint32_t ring_a, uint32_t img_a, int &buf,
+                                                   double *__restrict__ obs_tile, int n_rows, int r_begin, int r_count, int e_base) {
+    const int lane = threadIdx.x & 31;
+    const int r_end = min(r_begin + r_count, n_rows);
+    const uint32_t buf_bytes = (uint32_t)(RC * x.row_bytes);
+#pragma unroll 1
+    for (int r = r_begin; r < r_end; r += RC) {
+        const uint32_t im = img_a + (uint32_t)buf * buf_bytes;
+        if (lane == 0) bulk_wait_read<NB - 1>();    // the bulk store that last read this buffer is done with it
+        __syncwarp();
+        int n = RC;
+        if (r + RC <= r_end) {                      // full chunk, GB rows at a time: their gathers are all in flight before the first image store
+            static_assert(RC % GB == 0, "gather batches tile the chunk");
+#pragma unroll
+            for (int b = 0; b < RC; b += GB) {
+                ImgRow v[GB];
+#pragma unroll
+                for (int q = 0; q < GB; ++q) v[q] = img_gather<kHetero, kRing>(P, G, x, env_a, het, ring_a, r + b + q, e_base);
+#pragma unroll
+                for (int q = 0; q < GB; ++q) img_scatter(x, im + (uint32_t)((b + q) * x.row_bytes), v[q]);
+            }
+        } else {                                    // the last rows of a partial tile, one by one
+            n = r_end - r;
+#pragma unroll 1
+            for (int q = 0; q < n; ++q)
+                img_scatter(x, im + (uint32_t)(q * x.row_bytes), img_gather<kHetero, kRing>(P, G, x, env_a, het, ring_a, r + q, e_base));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(obs_tile + (size_t)r * (x.row_bytes >> 3)), "r"(im),
+                         "r"((uint32_t)(n * x.row_bytes)) : "memory");
+            bulk_commit();
+        }
+        buf = buf + 1 == NB ? 0 : buf + 1;
+    }
+}
+
 template <bool kHetero>
 __device__ __forceinline__ RawRow gather_raw(const LaunchParams &P, const DevGroup &G, const MgConfig *__restrict__ c, int e, int t) {
     RawRow r;
@@ -1249,6 +1433,220 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// persistent kernel with the image emitter (warp_emit_rows_img): rows leave the SM as TMA bulk stores of RC rows.
+//   kWS = false  every warp: owners (threads < 64) run the physics, CTA barrier, each warp emits its 16 rows
+//   kWS = true   warps 0-1 own the envs and run one step ahead, warps 2-3 emit 32 rows each (named barriers as in
+//                mg_rollout_ws_kernel); only the two emitting warps have images
+// kRing keeps the sliding load / pv windows of envs with their own series in shared memory (see RingShared).
+// Dynamic shared memory: (kWS ? 2 : MG_WARPS) * NB * RC * obs_dim doubles (the images).
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef MG_IMG_MIN_CTAS
+#define MG_IMG_MIN_CTAS 3
+#endif
+extern __shared__ __align__(128) unsigned char mg_dyn_smem[];
+
+struct ImgTileShared {
+    TileEnv env[2][MG_TILE];   // double buffered across steps
+};
+
+// single-step kernel with the image emitter: mg_step_kernel's phases, rows leave as bulk stores of RC rows
+template <int RC, int NB, int GB, bool kHetero>
+__global__ void __launch_bounds__(MG_THREADS, 5) mg_step_img_kernel(const __grid_constant__ LaunchParams P) {
+    __shared__ TileEnv S_env[MG_TILE];
+    __shared__ typename HeteroStorage<kHetero>::type SH;
+    HeteroEnv *het0 = HeteroStorage<kHetero>::rows(SH, 0);
+    const int gi = find_group(P, blockIdx.x);
+    const DevGroup &G = P.g[gi];
+    const int e0 = (blockIdx.x - G.tile_begin) * MG_TILE;
+    const int n_rows = min(MG_TILE, G.n_envs - e0);
+    const int tid = threadIdx.x;
+    const int e = e0 + tid;
+    double my_reward = 0.0;
+    bool stepped = false;
+    if (tid < n_rows) {
+        const MgConfig *__restrict__ c = P.cfg + __ldg(G.cfg_index + e);
+        EnvRegs s;
+        s.t = G.step[e];
+        s.charge = G.charge[e];
+        s.cs = s.gs = s.up = s.dn = 0;
+        if (G.has_genset) unpack_genset(G.genset[e], s);
+        if (P.mode == MODE_STEP || P.mode == MODE_DISCRETE) {
+            const StepInputs in = fetch_inputs<kHetero>(P, G, c, e, 0, s.t);
+            const int final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
+            double reward;
+            int done;
+            uint32_t flags;
+            owner_step(P, G, c, s, in, final_step, G.info ? G.info + (size_t)e * MG_N_INFO : nullptr, reward, done, flags);
+            if (in.valid) {
+                G.step[e] = s.t;
+                G.charge[e] = s.charge;
+                if (G.has_genset) G.genset[e] = pack_genset(s);
+            }
+            G.reward[e] = reward;
+            G.done[e] = (uint8_t)done;
+            if (G.flags) G.flags[e] = flags;
+            my_reward = reward;
+            stepped = true;
+        } else if (P.mode == MODE_RESET) {
+            if (!G.mask || G.mask[e]) {   // Microgrid.reset: only the step counter moves (microgrid.py:205-225)
+                s.t = G.env_initial ? __ldg(G.env_initial + e) : c->initial_step;
+                G.step[e] = s.t;
+            }
+        }
+        if (G.obs) {
+            publish_env<kHetero>(S_env[tid], het0 ? het0 + tid : nullptr, c, G, s, P.T, P.Tp);
+            if (P.mode >= MODE_OBSERVE && G.soc_reported) {
+                // BatteryModule keeps the soc it was constructed with until its first _update_state (battery_module.py:89, 125-130)
+                const double soc = __ldg(G.soc_reported + e);
+                S_env[tid].state[(G.has_genset && G.state_genset_first) ? 4 : 0] = (soc - c->bat_soc_low) / c->bat_soc_spread;
+            }
+        }
+    }
+    if (G.reward_total && tid < MG_TILE) add_reward_total(G.reward_total, my_reward, stepped);   // warps 0..1, uniformly
+    if (G.obs) {   // CTA-uniform
+        __syncthreads();
+        const ImgCtx x = img_ctx(P, G);
+        int buf = 0;
+        const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (provably warp-uniform: bulk-store operands in uniform registers)
+        const uint32_t img_a = smem_u32(mg_dyn_smem) + (uint32_t)(warp * NB * RC * x.row_bytes);
+        warp_emit_rows_img<RC, NB, GB, kHetero, false>(P, G, x, smem_u32(S_env), het0, 0u, img_a, buf, G.obs + (size_t)e0 * G.obs_dim, n_rows,
+                                                   warp * MG_ROWS_PER_WARP, MG_ROWS_PER_WARP, e0);
+        if ((tid & 31) == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores' reads
+    }
+}
+
+template <int RC, int NB, int GB, bool kHetero, bool kRing, bool kWS>
+__global__ void __launch_bounds__(MG_THREADS, !kWS ? MG_IMG_MIN_CTAS : !kHetero ? MG_MIN_CTAS : kRing ? 4 : 5) mg_rollout_img_kernel(const __grid_constant__ LaunchParams P) {
+    static_assert(!kRing || kHetero, "the ring path is a variant of the per-env series kernels");
+    static_assert(MG_THREADS == 128 && MG_TILE == 64, "role split assumes 2 owner warps + 2 emitter warps");
+    __shared__ ImgTileShared S;
+    __shared__ typename HeteroStorage<kHetero && !kRing>::type SH;
+    __shared__ typename RingStorage<kRing>::type SR;
+    RingShared *rings = RingStorage<kRing>::get(SR);
+    const int gi = find_group(P, blockIdx.x);
+    const DevGroup &G = P.g[gi];
+    const int e0 = (blockIdx.x - G.tile_begin) * MG_TILE;
+    const int n_rows = min(MG_TILE, G.n_envs - e0);
+    // Role-relative thread id: owners are rtid < 64.  With the role split, odd CTAs give the owner role to warps 2-3: a warp's
+    // scheduler is its index mod 4, so without the flip every emitting warp of the SM would sit on the same two of the four
+    // schedulers (measured: those two saturate at ~85 issue slots per row while the other two idle).
+    const int tid = kWS ? (int)(threadIdx.x ^ ((blockIdx.x & 1u) << 6)) : (int)threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (provably warp-uniform: bulk-store operands in uniform registers)
+    const ImgCtx x = img_ctx(P, G);
+    const uint32_t ring_a = kRing ? smem_u32(rings) : 0u;
+    // ring variant: fill every special env's windows for its current step [t, t + H], one env per warp pass, lane k = window
+    // element k (the only place where a whole window is normalised); the owner then appends one value per step
+    const int ring_R = G.horizon + 2;
+    if (kRing) {
+        const int lane = tid & 31, w0 = warp * MG_ROWS_PER_WARP;
+        for (int r = w0; r < min(w0 + MG_ROWS_PER_WARP, n_rows); ++r) {
+            const MgConfig *__restrict__ cr = P.cfg + __ldg(G.cfg_index + e0 + r);
+            if (!env_is_special(cr, G)) continue;
+            const int t_r = min(G.step[e0 + r], P.T);
+            for (int k = lane; k <= G.horizon; k += 32) {
+                double ld, pv;
+                series_obs_value(P, cr, t_r + k, ld, pv);
+                const int slot = (t_r + k) % ring_R;
+                rings->win[0][r][slot] = ld;
+                rings->win[1][r][slot] = pv;
+            }
+        }
+    }
+    __syncthreads();
+    if (!kWS || tid < MG_TILE) {   // ---------------- owners (and, without the role split, emitters too) ----------------
+        const bool owner = tid < n_rows;
+        const int e = e0 + tid;
+        const MgConfig *__restrict__ c = P.cfg;
+        EnvRegs s;
+        s.t = 0; s.charge = 0.0; s.cs = s.gs = s.up = s.dn = 0;
+        int final_step = 0, ring_base = 0, buf = 0;
+        bool ring_env = false;
+        double rsum = 0.0;
+        uint32_t fsum = 0;
+        if (owner) {
+            c = P.cfg + __ldg(G.cfg_index + e);
+            s.t = G.step[e];
+            s.charge = G.charge[e];
+            if (G.has_genset) unpack_genset(G.genset[e], s);
+            final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
+            if (kRing) {
+                ring_env = env_is_special(c, G);
+                ring_base = min(s.t, P.T) % ring_R;
+            }
+        }
+        const uint32_t img_a = smem_u32(mg_dyn_smem) + (uint32_t)(warp * NB * RC * x.row_bytes);   // (not used by owners of the split)
+        for (int step = 0; step < P.n_steps; ++step) {
+            const int ebuf = step & 1;
+            double my_reward = 0.0;
+            StepInputs in;
+            in.valid = false;
+            if (owner) in = fetch_inputs<kHetero>(P, G, c, e, step, s.t);
+            if (kWS && step >= 2) named_bar_sync(BAR_EMPTY0, ebuf);   // the emitters are done with env[ebuf] of step - 2
+            if (owner) {
+                double reward;
+                int done;
+                uint32_t flags;
+                owner_step(P, G, c, s, in, final_step, nullptr, reward, done, flags);
+                G.reward[(size_t)step * G.out_step_stride + e] = reward;
+                G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)done;
+                rsum += reward;
+                fsum |= flags;
+                my_reward = reward;
+                publish_env<kHetero>(S.env[ebuf][tid], (kHetero && !kRing) ? HeteroStorage<kHetero && !kRing>::rows(SH, ebuf) + tid : nullptr, c, G, s, P.T, P.Tp);
+                if (kRing && ring_env) {
+                    if (in.valid) {   // the step counter moved from t to t + 1 <= T: the window gains index t + 1 + H
+                        ring_base = ring_base + 1 == ring_R ? 0 : ring_base + 1;
+                        double ld, pv;
+                        series_obs_value(P, c, s.t + G.horizon, ld, pv);
+                        int slot = ring_base + G.horizon;
+                        if (slot >= ring_R) slot -= ring_R;
+                        rings->win[0][tid][slot] = ld;
+                        rings->win[1][tid][slot] = pv;
+                    }
+                    publish_ring(S.env[ebuf][tid], c, G, e, ring_base);
+                }
+            }
+            if (G.reward_total && tid < MG_TILE) add_reward_total(G.reward_total + step, my_reward, owner);
+            if (kWS) {
+                __threadfence_block();   // the tile record is visible before the emitters are released
+                named_bar_arrive(BAR_FULL0, ebuf);
+            } else {
+                // one barrier per step: the records of step s live in env[s & 1]; a warp can only reach the barrier of
+                // step s+1 after it has finished reading env[s & 1], so the owners may overwrite it at step s+2
+                __syncthreads();
+                double *obs_tile = G.obs + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim;
+                warp_emit_rows_img<RC, NB, GB, kHetero, kRing>(P, G, x, smem_u32(S.env[ebuf]), HeteroStorage<kHetero && !kRing>::rows(SH, ebuf), ring_a,
+                                                             img_a, buf, obs_tile, n_rows, warp * MG_ROWS_PER_WARP, MG_ROWS_PER_WARP, e0);
+                if (P.ring == 1 && (tid & 31) == 0) bulk_wait_all();   // the next step rewrites the same rows: keep the order
+            }
+        }
+        if (owner) {
+            G.step[e] = s.t;
+            G.charge[e] = s.charge;
+            if (G.has_genset) G.genset[e] = pack_genset(s);
+            if (G.reward_sum) G.reward_sum[e] = rsum;
+            if (G.flags) G.flags[e] = fsum;
+        }
+        if (!kWS && (tid & 31) == 0) bulk_wait_read<0>();   // shared memory must outlive the last bulk stores' reads
+    } else {               // ---------------- emitters (kWS) ----------------
+        const int half = warp - 2;   // 0 or 1: rows [32 half, 32 half + 32)
+        const uint32_t img_a = smem_u32(mg_dyn_smem) + (uint32_t)(half * NB * RC * x.row_bytes);
+        int buf = 0;
+        for (int step = 0; step < P.n_steps; ++step) {
+            const int ebuf = step & 1;
+            named_bar_sync(BAR_FULL0, ebuf);
+            double *obs_tile = G.obs + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim;
+            warp_emit_rows_img<RC, NB, GB, kHetero, kRing>(P, G, x, smem_u32(S.env[ebuf]), HeteroStorage<kHetero && !kRing>::rows(SH, ebuf), ring_a, img_a,
+                                                         buf, obs_tile, n_rows, 32 * half, 32, e0);
+            if (P.ring == 1 && (tid & 31) == 0) bulk_wait_all();
+            __threadfence_block();   // every read of env[ebuf] / het[ebuf] has completed before the owners may overwrite them
+            named_bar_arrive(BAR_EMPTY0, ebuf);
+        }
+        if ((tid & 31) == 0) bulk_wait_read<0>();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // table construction (mg_create): bounds + normalised, end-padded observation tables
 //   load / pv : low = min(ts), high = max(ts), pulled to include 0 (base_timeseries_module.py:81-88)
 //   grid cols : per-column min / max                               (grid_module.py:125-132)
@@ -1413,6 +1811,8 @@ struct MgHandle {
     bool obs_f32;           // observation buffers are float32 (MG_LAYOUT_OBS_F32)
     bool rollout_specialised;   // MG_OPT_ROLLOUT_SPECIALISED
     bool rollout_ring;          // MG_OPT_ROLLOUT_RING
+    int emit_image;             // MG_OPT_EMIT_IMAGE: 0 LSU row emitters, 1 image + TMA bulk stores (default)
+    int image_shape;            // MG_OPT_IMAGE_SHAPE: index into the instantiated (rows per bulk store, buffers) shapes
     struct HostStage *stage;    // mg_rollout_host: streams, events and device staging (lazy)
     const double *soc_reported[MG_MAX_GROUPS];   // mg_set_reported_soc; dropped by the first step / rollout
 };
@@ -1538,6 +1938,8 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
     h->obs_f32 = (L->flags & MG_LAYOUT_OBS_F32) != 0;
     h->rollout_specialised = true;
     h->rollout_ring = true;
+    h->emit_image = 1;
+    h->image_shape = 0;
     h->stage = nullptr;
     h->last_stream = nullptr;
     for (int g = 0; g < MG_MAX_GROUPS; ++g) h->last_obs[g] = nullptr;
@@ -1571,6 +1973,9 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
         layout_segments(g, d);
         if (obs_dim > MG_MAX_IMG) d.tma_ok = 0;
         d.long_path = (obs_dim > MG_MAX_IMG) || (d.state_start & 1);
+        d.img_ok = rows <= 32;
+        for (int q = 0; q < d.n_seg; ++q)
+            if (d.seg_kind[q] == KIND_GRID && (d.seg_start[q] & 1)) d.img_ok = 0;
         if (d.long_path && g.grid_status_bits) { delete h; return fail(MG_E_UNSUPPORTED, "mg_create: per-env grid status needs the staged row path (obs_dim <= 192, even forecast rows)"); }
         d.step = g.step; d.charge = g.charge; d.genset = g.genset; d.cfg_index = g.cfg_index;
         d.env_initial = g.env_initial_step; d.env_final = g.env_final_step;
@@ -1661,7 +2066,73 @@ extern "C" int mg_set_option(MgHandle *h, int option, int value) {
         h->rollout_ring = value != 0;
         return MG_OK;
     }
+    if (option == MG_OPT_EMIT_IMAGE) {
+        h->emit_image = value != 0;
+        return MG_OK;
+    }
+    if (option == MG_OPT_IMAGE_SHAPE) {
+        if (value < 0 || value >= MG_N_IMAGE_SHAPES) return fail(MG_E_INVALID, "mg_set_option: image shape out of range");
+        h->image_shape = value;
+        return MG_OK;
+    }
     return fail(MG_E_INVALID, "mg_set_option: unknown option");
+}
+
+// ---- image-emitter kernels: (rows per bulk store, buffers per warp) shapes instantiated for mg_set_option(MG_OPT_IMAGE_SHAPE)
+typedef void (*ImgKernel)(const LaunchParams);
+static void img_kernel_for(bool hetero, bool ring, bool ws, int shape, ImgKernel *k, int *rc, int *nb) {
+    // (rows per bulk store, image buffers per emitting warp, rows gathered together)
+    static const int shapes[MG_N_IMAGE_SHAPES][2] = {{4, 2}, {2, 2}, {4, 2}, {8, 2}};
+    *rc = shapes[shape][0];
+    *nb = shapes[shape][1];
+#define MG_IMG_PICK(RC, NB, GB)                                                                                  \
+    do {                                                                                                         \
+        if (ring) *k = ws ? mg_rollout_img_kernel<RC, NB, GB, true, true, true> : mg_rollout_img_kernel<RC, NB, GB, true, true, false>;   \
+        else if (hetero) *k = ws ? mg_rollout_img_kernel<RC, NB, GB, true, false, true> : mg_rollout_img_kernel<RC, NB, GB, true, false, false>; \
+        else *k = ws ? mg_rollout_img_kernel<RC, NB, GB, false, false, true> : mg_rollout_img_kernel<RC, NB, GB, false, false, false>;    \
+    } while (0)
+    switch (shape) {
+        case 1: MG_IMG_PICK(2, 2, 2); break;
+        case 2: MG_IMG_PICK(4, 2, 4); break;
+        case 3: MG_IMG_PICK(8, 2, 2); break;
+        default: MG_IMG_PICK(4, 2, 2); break;
+    }
+#undef MG_IMG_PICK
+}
+
+static void img_step_kernel_for(bool hetero, int shape, ImgKernel *k, int *rc, int *nb) {
+    ImgKernel unused;
+    img_kernel_for(false, false, false, shape, &unused, rc, nb);
+    switch (shape) {
+        case 1: *k = hetero ? mg_step_img_kernel<2, 2, 2, true> : mg_step_img_kernel<2, 2, 2, false>; break;
+        case 2: *k = hetero ? mg_step_img_kernel<4, 2, 4, true> : mg_step_img_kernel<4, 2, 4, false>; break;
+        case 3: *k = hetero ? mg_step_img_kernel<8, 2, 2, true> : mg_step_img_kernel<8, 2, 2, false>; break;
+        default: *k = hetero ? mg_step_img_kernel<4, 2, 2, true> : mg_step_img_kernel<4, 2, 2, false>; break;
+    }
+}
+
+// opt a kernel into `bytes` of dynamic shared memory on the current device (once per kernel, device and size)
+static int ensure_dynamic_smem(const void *func, size_t bytes) {
+    struct Entry { const void *func; int device; size_t bytes; };
+    static Entry seen[64];
+    static int n_seen = 0;
+    static std::mutex lock;
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    std::lock_guard<std::mutex> guard(lock);
+    for (int i = 0; i < n_seen; ++i)
+        if (seen[i].func == func && seen[i].device == device) {
+            if (seen[i].bytes >= bytes) return MG_OK;
+            e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute (dynamic shared memory)");
+            seen[i].bytes = bytes;
+            return MG_OK;
+        }
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute (dynamic shared memory)");
+    if (n_seen < 64) seen[n_seen++] = Entry{func, device, bytes};
+    return MG_OK;
 }
 
 static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized, void *stream) {
@@ -1699,8 +2170,25 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = overlap ? 1 : 0;
+    // image emitter: every group that writes observations has an image-compatible f64 row layout
+    bool image = h->emit_image != 0 && !h->obs_f32, any_obs = false;
+    int max_dim = 0;
+    for (int g = 0; g < P.n_groups; ++g) {
+        if (!P.g[g].obs) continue;
+        any_obs = true;
+        if (!P.g[g].img_ok) image = false;
+        if (P.g[g].obs_dim > max_dim) max_dim = P.g[g].obs_dim;
+    }
     cudaError_t e;
-    if (h->obs_f32) e = h->hetero ? cudaLaunchKernelEx(&cfg, mg_step_kernel<true, float>, P) : cudaLaunchKernelEx(&cfg, mg_step_kernel<false, float>, P);
+    if (image && any_obs) {
+        ImgKernel k;
+        int rc, nb;
+        img_step_kernel_for(h->hetero, h->image_shape, &k, &rc, &nb);
+        cfg.dynamicSmemBytes = (size_t)MG_WARPS * nb * rc * max_dim * sizeof(double);
+        const int rcode = ensure_dynamic_smem((const void *)k, cfg.dynamicSmemBytes);
+        if (rcode != MG_OK) return rcode;
+        e = cudaLaunchKernelEx(&cfg, k, P);
+    } else if (h->obs_f32) e = h->hetero ? cudaLaunchKernelEx(&cfg, mg_step_kernel<true, float>, P) : cudaLaunchKernelEx(&cfg, mg_step_kernel<false, float>, P);
     else e = h->hetero ? cudaLaunchKernelEx(&cfg, mg_step_kernel<true, double>, P) : cudaLaunchKernelEx(&cfg, mg_step_kernel<false, double>, P);
     if (e != cudaSuccess) return cuda_fail(e, "step kernel launch");
     if (mode == MODE_STEP || mode == MODE_DISCRETE) memset(h->soc_reported, 0, sizeof h->soc_reported);   // every battery updates
@@ -1752,8 +2240,27 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
     // per-env series: keep the sliding windows in shared memory when every group's ring fits (H <= 24) and rows are staged
     bool use_ring = h->hetero && h->rollout_ring;
     for (int g = 0; g < P.n_groups; ++g)
-        if (!P.g[g].obs || P.g[g].long_path || P.g[g].horizon + 2 > MG_RING_MAX) use_ring = false;
-    if (ws) {
+        if (!P.g[g].obs || P.g[g].horizon + 2 > MG_RING_MAX) use_ring = false;
+    // image emitter (rows leave as TMA bulk stores): every group writes f64 observations with an image-compatible layout
+    bool image = h->emit_image != 0 && !h->obs_f32;
+    int max_dim = 0;
+    for (int g = 0; g < P.n_groups; ++g) {
+        if (!P.g[g].obs || !P.g[g].img_ok) image = false;
+        if (P.g[g].obs_dim > max_dim) max_dim = P.g[g].obs_dim;
+    }
+    if (!image)
+        for (int g = 0; g < P.n_groups; ++g)
+            if (P.g[g].long_path) use_ring = false;
+    if (image) {
+        const bool ws_img = h->rollout_specialised;
+        ImgKernel k;
+        int rc, nb;
+        img_kernel_for(h->hetero, use_ring, ws_img, h->image_shape, &k, &rc, &nb);
+        const size_t dyn = (size_t)(ws_img ? 2 : MG_WARPS) * nb * rc * max_dim * sizeof(double);
+        const int rcode = ensure_dynamic_smem((const void *)k, dyn);
+        if (rcode != MG_OK) return rcode;
+        k<<<P.total_tiles, MG_THREADS, dyn, (cudaStream_t)stream>>>(P);
+    } else if (ws) {
         if (h->obs_f32) mg_rollout_ws_kernel<false, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
         else mg_rollout_ws_kernel<false, double><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
     } else if (use_ring) {

@@ -649,9 +649,9 @@ class BatchedMicrogrid:
         if self._soc_pristine and any(g.soc_reported is not None for g in self.groups):
             socs = (C.c_void_p * len(self.groups))(*[_ptr(g.soc_reported) or None for g in self.groups])
             _cabi.check(self._lib.mg_set_reported_soc(h, socs), "mg_set_reported_soc")
-        # envs with their own episode windows do not advance in lock-step: the plain persistent kernel is faster there
-        ragged = any(g.env_initial_step is not None for g in self.groups)
-        self.set_rollout_specialised(not ragged)
+        # tuning options survive a re-creation of the handle
+        for option, value in getattr(self, "_options", {}).items():
+            _cabi.check(self._lib.mg_set_option(self._handle, option, value), "mg_set_option")
 
     def _mark_stepped(self):
         """Called by everything that steps (or binds a stepping launcher): the handle drops the constructed-with soc values at
@@ -689,16 +689,30 @@ class BatchedMicrogrid:
         _cabi.check(self._lib.mg_forecast_noise(self._handle, records.data_ptr(), ptrs, bases, seed, self._noise_calls,
                                                 self._stream()), "mg_forecast_noise")
 
+    def _set_option(self, option, value):
+        if not hasattr(self, "_options"):
+            self._options = {}
+        self._options[option] = int(value)
+        _cabi.check(self._lib.mg_set_option(self._handle, option, int(value)), "mg_set_option")
+
     def set_rollout_specialised(self, on):
-        """Owner / emitter warp-specialised persistent kernel for `rollout` (default: on unless per-env trajectory windows
-        are installed).  Best when the envs of a tile are at the same step; turn it off for batches whose envs were
-        started at unrelated steps."""
-        _cabi.check(self._lib.mg_set_option(self._handle, _cabi.MG_OPT_ROLLOUT_SPECIALISED, int(bool(on))), "mg_set_option")
+        """Owner / emitter warp-specialised persistent kernel for `rollout` (default on): two warps run the physics one step
+        ahead while the other two emit the observation rows."""
+        self._set_option(_cabi.MG_OPT_ROLLOUT_SPECIALISED, bool(on))
 
     def set_rollout_ring(self, on):
         """Batches with per-env series (MicrogridGenerator grids): keep every env's normalised load / pv windows in shared
         memory across the steps of `rollout` (default on; MG_OPT_ROLLOUT_RING).  Off = normalise whole windows per row."""
-        _cabi.check(self._lib.mg_set_option(self._handle, _cabi.MG_OPT_ROLLOUT_RING, int(bool(on))), "mg_set_option")
+        self._set_option(_cabi.MG_OPT_ROLLOUT_RING, bool(on))
+
+    def set_emit_image(self, on):
+        """Observation rows leave the SM as TMA bulk stores of several rows assembled in shared memory (default on,
+        MG_OPT_EMIT_IMAGE); off = the per-lane 16-byte store emitters."""
+        self._set_option(_cabi.MG_OPT_EMIT_IMAGE, bool(on))
+
+    def set_image_shape(self, index):
+        """Which instantiated (rows per bulk store, buffers per warp) shape the image kernels use (MG_OPT_IMAGE_SHAPE)."""
+        self._set_option(_cabi.MG_OPT_IMAGE_SHAPE, int(index))
 
     def __del__(self):
         try:

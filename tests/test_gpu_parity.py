@@ -313,6 +313,110 @@ def test_batch_vs_oracle_ragged_state(order):
         np.testing.assert_array_equal(np.array([s[2:] for s in st]), gen)
 
 
+EMITTER_VARIANTS = [("lsu", 0, True), ("lsu", 0, False)] + [("image", shape, ws) for shape in range(4) for ws in (True, False)]
+
+
+def set_emitter(bm, emit, shape, specialised):
+    bm.set_emit_image(emit == "image")
+    bm.set_image_shape(shape)
+    bm.set_rollout_specialised(specialised)
+
+
+@pytest.mark.parametrize("emit,shape,specialised", EMITTER_VARIANTS)
+def test_row_emitters_agree_on_ragged_batches(emit, shape, specialised):
+    """Every row emitter (per-lane 16-byte stores; shared-memory images + TMA bulk stores in each instantiated shape, with and
+    without the owner / emitter warp split) writes the same bytes: 3 001 envs (a partial last tile in every group) at
+    unrelated steps, some inside the last steps of the year; the persistent kernel cut into two launches (ring 1 and ring
+    5), single steps, observe and masked reset, against the C oracle."""
+    rng = np.random.default_rng(23)
+    configs = [load_pymgrid25(n) for n in range(25)]
+    B, n_steps = 3001, 11
+    env_config = rng.integers(0, 25, B)
+    bm = engine(configs, env_config)
+    set_emitter(bm, emit, shape, specialised)
+    plist = randomise_state(bm, rng, configs, env_config, 8740)
+    for e in range(0, B, 5):          # (n_steps more steps end at the last valid step of the year at the latest)
+        plist[e].current_step = int(rng.integers(8738, 8749))
+    for g in bm.groups:
+        g.step.copy_(torch.tensor([plist[e].current_step for e in g.env_ids], dtype=torch.int32))
+    ob = OracleBatch(plist)
+    padded = np.zeros((n_steps, B, 4))
+    for e in range(B):
+        padded[:, e, :plist[e].n_act] = rng.random((n_steps, plist[e].n_act))
+    acts = [torch.from_numpy(np.ascontiguousarray(padded[:, g.env_ids, :g.n_act])).cuda() for g in bm.groups]
+    o_rew, o_done, o_obs = ob.rollout(padded[:4], n_threads=4)
+    out = bm.rollout([a[:4].contiguous() for a in acts], ring=1)
+    for g, r in zip(bm.groups, out):
+        np.testing.assert_array_equal(r["reward"].cpu().numpy(), o_rew[:, g.env_ids])
+        np.testing.assert_array_equal(r["done"].cpu().numpy(), o_done[:, g.env_ids])
+        np.testing.assert_array_equal(r["obs_ring"][0].cpu().numpy(), o_obs[g.env_ids][:, :g.obs_dim])
+    o_rew, o_done, o_obs = ob.rollout(padded[4:10], n_threads=4)
+    out = bm.rollout([a[4:10].contiguous() for a in acts], ring=5)
+    for g, r in zip(bm.groups, out):
+        np.testing.assert_array_equal(r["reward"].cpu().numpy(), o_rew[:, g.env_ids])
+        np.testing.assert_array_equal(r["obs_ring"][5 % 5].cpu().numpy(), o_obs[g.env_ids][:, :g.obs_dim])
+    o_rew, o_done, o_obs = ob.rollout(padded[10:11], n_threads=4)
+    obs, reward, done, _ = as_lists(bm.step([a[10].contiguous() for a in acts]))
+    for g, o, r in zip(bm.groups, obs, reward):
+        np.testing.assert_array_equal(r.cpu().numpy(), o_rew[0, g.env_ids])
+        np.testing.assert_array_equal(o.cpu().numpy(), o_obs[g.env_ids][:, :g.obs_dim])
+    stepped = [o.clone() for o in obs]
+    for o in obs:
+        o.zero_()
+    for o, want in zip(bm.observe(), stepped):
+        assert torch.equal(o, want)
+    # masked reset: the selected envs go back to their initial step, every row is rewritten
+    masks = [torch.from_numpy((rng.random(g.n_envs) < 0.5).astype(np.uint8)).cuda() for g in bm.groups]
+    before = [g.step.clone() for g in bm.groups]
+    rows = bm.reset(mask=masks)
+    ref = engine(configs, env_config)
+    ref.set_emit_image(False)
+    ref.load_state_dict(bm.state_dict())
+    for g, gr, m, b0, row in zip(bm.groups, ref.groups, masks, before, rows):
+        assert torch.equal(g.step, torch.where(m.bool(), torch.zeros_like(b0), b0))
+        assert torch.equal(row, ref.observe()[ref.groups.index(gr)])
+
+
+@pytest.mark.parametrize("emit,shape,specialised", EMITTER_VARIANTS)
+def test_row_emitters_agree_on_generator_grids(emit, shape, specialised):
+    """The same for heterogeneous MicrogridGenerator grids (per-env series in shared-memory rings, per-env grid-status bits):
+    2 500 grids started at unrelated steps incl. the end of the year, persistent kernel and single steps against the oracle."""
+    from pymgrid_b200 import generator
+    from tests.test_generator import pv_first
+    gb = generator.sample(2500, seed=5)
+    bm = generator.engine_from_batch(gb, device="cuda:0", action_order=CONTAINER)
+    set_emitter(bm, emit, shape, specialised)
+    rng = np.random.default_rng(9)
+    plist = [gb.to_params(i) for i in range(gb.n)]
+    starts = rng.integers(0, 8700, gb.n)
+    starts[::4] = rng.integers(8740, 8752, len(starts[::4]))
+    for p, s0 in zip(plist, starts):
+        p.current_step = int(s0)
+    for g in bm.groups:
+        g.step.copy_(torch.from_numpy(starts[g.env_ids].astype(np.int32)))
+    ob = OracleBatch(plist)
+    n_steps = 9
+    padded = np.zeros((n_steps, gb.n, 4))
+    for e, p in enumerate(plist):
+        padded[:, e, :p.n_act] = rng.random((n_steps, p.n_act))
+    acts = [torch.from_numpy(np.ascontiguousarray(padded[:, g.env_ids, :g.n_act])).cuda() for g in bm.groups]
+    o_rew, o_done, o_obs = ob.rollout(padded[:8], n_threads=4)
+    out = bm.rollout([a[:8].contiguous() for a in acts], ring=3)
+    for g, r in zip(bm.groups, out):
+        np.testing.assert_array_equal(r["reward"].cpu().numpy(), o_rew[:, g.env_ids])
+        np.testing.assert_array_equal(r["done"].cpu().numpy(), o_done[:, g.env_ids])
+        got = r["obs_ring"][7 % 3].cpu().numpy()
+        for slot, e in enumerate(g.env_ids):
+            np.testing.assert_array_equal(got[slot], pv_first(o_obs[e, :g.obs_dim], plist[e]), err_msg=f"env {e}")
+    o_rew, o_done, o_obs = ob.rollout(padded[8:9], n_threads=4)
+    obs, reward, done, _ = as_lists(bm.step([a[8].contiguous() for a in acts]))
+    for g, o, r in zip(bm.groups, obs, reward):
+        np.testing.assert_array_equal(r.cpu().numpy(), o_rew[0, g.env_ids])
+        got = o.cpu().numpy()
+        for slot, e in enumerate(g.env_ids):
+            np.testing.assert_array_equal(got[slot], pv_first(o_obs[e, :g.obs_dim], plist[e]), err_msg=f"env {e}")
+
+
 @pytest.mark.parametrize("specialised", [True, False])
 def test_rollout_kernel_equals_repeated_steps(specialised):
     """mg_rollout (persistent kernel, state in registers; warp-specialised or plain, MG_OPT_ROLLOUT_SPECIALISED)

@@ -1,0 +1,40 @@
+#!/bin/bash
+# One gpurun session: everything lands in gpurun_out/<tag>_*.  Usage: tools/gpu_session.sh <tag> <stage...>
+tag=$1; shift
+out=gpurun_out
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/${tag}_gpu.txt 2>&1
+for stage in "$@"; do
+  case $stage in
+    microbench)
+      timeout 120 ./tools/microbench_store 131072 200 > $out/${tag}_microbench.txt 2>&1 ;;
+    composed)
+      timeout 300 python bench.py --workload composed --steps 512 --warmup 5 > $out/${tag}_bench_composed.json 2> $out/${tag}_bench_composed.err
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:mgc_kernel -s 2 -c 1 -o $out/${tag}_mgc \
+        python bench.py --workload composed --steps 8 --warmup 3 --no-cpu > $out/${tag}_ncu_composed.log 2>&1 ;;
+    tests)
+      timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_gpu_tests.log 2>&1 ;;
+    bench)
+      timeout 600 python bench.py > $out/${tag}_bench_default.json 2> $out/${tag}_bench_default.err ;;
+    bench20)
+      timeout 600 python bench.py --steps 20 --warmup 3 > $out/${tag}_bench_steps20.json 2> $out/${tag}_bench_steps20.err ;;
+    generator)
+      timeout 300 python bench.py --workload generator --steps 500 --warmup 5 --single-path --no-cpu > $out/${tag}_bench_generator.json 2> $out/${tag}_bench_generator.err ;;
+    ragged)
+      timeout 300 python bench.py --ragged --steps 500 --warmup 5 --single-path --no-cpu > $out/${tag}_bench_ragged.json 2> $out/${tag}_bench_ragged.err ;;
+    emit_tests)
+      timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --maxfail=6 -k "row_emitters or rollout_kernel_equals or generator_grids_rollout or vectorised_generator" > $out/${tag}_emit_tests.log 2>&1 ;;
+    tune)
+      timeout 900 python tools/tune_emitters.py --steps 400 --step-path > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
+    tune_default)
+      timeout 900 python tools/tune_emitters.py --steps 400 --variants default > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
+    ncu_gen)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:mg_rollout -s 1 -c 1 -o $out/${tag}_gen \
+        python bench.py --workload generator --steps 24 --warmup 3 --preheat 0 --single-path --no-cpu $BENCH_EXTRA > $out/${tag}_ncu_gen.log 2>&1 ;;
+    ncu_default)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:mg_rollout -s 1 -c 1 -o $out/${tag}_default \
+        python bench.py --steps 64 --warmup 3 --preheat 0 --single-path --no-cpu $BENCH_EXTRA > $out/${tag}_ncu_default.log 2>&1 ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done
+ls -la $out | tail -30
