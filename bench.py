@@ -13,10 +13,16 @@ done, state and the FULL normalised observation.  A "step" is one pass of the ho
              timed region (observations stay on the device, where a policy consumes them).
   roofline   HBM: algorithmic bytes per launch (SURVEY.md 8d per-env-step figure x envs) / average launch time
              measured with CUDA events in this run, against MEASURED_PEAKS.json's copy bandwidth.
-  cpu_baseline  the C oracle port of the reference step (oracle/mg_oracle.c) on this box's host cores, bounded sample.
+  cpu_baseline  the C oracle port of the reference step (oracle/mg_oracle.c) on this box's host cores, bounded sample;
+             `python_reference` beside it is the unmodified Python reference timed in the build container
+             (tools/time_python_reference.py -> profiles/python_reference_timing.json; it cannot travel to the GPU box).
+  configs    short in-run measurements of BASELINE configs[1], [3] and the per-GPU shard of [4] (value, us/step, roofline
+             fraction), so that the driver-run line carries every config; under torchrun every rank runs its shard.
 
-`--impl reference` times that CPU port alone (the reference itself is pure Python and cannot travel to the GPU
-box; its measured 1e3 steps/s/core is quoted in BASELINE.md).
+A timed region that would last less than MIN_TIMED_MS is repeated (state restored and a fresh action block between
+repetitions, both untimed) and the MEDIAN is reported, with `repeats` in the line: `--steps 20` is 0.2 ms of GPU work.
+
+`--impl reference` times the CPU port alone.
 """
 import argparse
 import json
@@ -35,6 +41,9 @@ BATCH_PER_GPU = 65536
 METRIC = "microgrid env-steps/sec at batch 65536 (pymgrid25)"
 UNIT = "env-steps/s"
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+MIN_TIMED_MS = 50.0           # a timed region shorter than this is repeated and the median reported
+MAX_REPEATS = 400
+L2_BYTES = 126e6
 
 
 def algorithmic_bytes(has_genset, has_grid, horizon, discrete=False, obs_bytes=8):
@@ -328,6 +337,353 @@ def run_reference(args):
     return 0
 
 
+def python_reference_figure():
+    """The unmodified Python reference's Microgrid.run rate, measured in the build container (it cannot travel)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "python_reference_timing.json")) as f:
+            d = json.load(f)
+        return {"value": d["env_steps_per_s_per_core"], "unit": UNIT + " per core", "cores": 1,
+                "where": "build container (no GPU), tools/time_python_reference.py -> profiles/python_reference_timing.json",
+                "what": d["what"]}
+    except Exception:
+        return {"value": None, "note": "profiles/python_reference_timing.json missing; BASELINE.md quotes ~1e3 env-steps/s/core"}
+
+
+def pin_rank_to_gpu_cpus(local_rank, world):
+    """Multi-GPU runs: keep this rank (and the pinned host buffers it is about to allocate) on the cores next to its GPU.
+    The ranks whose GPUs report the same CPU set split it evenly.  Returns a description for the JSON line."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        n_cpu = os.cpu_count() or 1
+        words = (n_cpu + 63) // 64
+
+        def cpus_of(i):
+            mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(i), words)
+            return tuple(c for c in range(n_cpu) if (mask[c // 64] >> (c % 64)) & 1)
+        sets = [cpus_of(i) for i in range(world)]
+        mine = sets[local_rank]
+        allowed = set(os.sched_getaffinity(0))
+        mine = tuple(c for c in mine if c in allowed)
+        sharers = [i for i in range(world) if sets[i] == sets[local_rank]]
+        k, n = sharers.index(local_rank), len(sharers)
+        chunk = mine[k * len(mine) // n:(k + 1) * len(mine) // n]
+        if len(chunk) < 2:
+            return {"pinned": False, "reason": f"only {len(mine)} cores for {n} ranks"}
+        os.sched_setaffinity(0, chunk)
+        return {"pinned": True, "cores": len(chunk), "first_core": chunk[0], "ranks_sharing_the_cpu_set": n, "source": "nvmlDeviceGetCpuAffinity"}
+    except Exception as ex:
+        return {"pinned": False, "reason": f"{type(ex).__name__}: {ex}"}
+
+
+class Harness:
+    """Process-group plumbing and the timing discipline shared by every measurement of this file."""
+
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.rank, self.local_rank, self.world = dist_env()
+        self.affinity = pin_rank_to_gpu_cpus(self.local_rank, self.world)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{self.local_rank}"))
+            self.dist = dist
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device(f"cuda:{self.local_rank}")
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.ev0, self.ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.args = args
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def timed(self, run, prepare, min_ms=MIN_TIMED_MS, max_reps=MAX_REPEATS):
+        """Time `run(rep)` (enqueues EXACTLY the K steps on self.stream) between barrier + synchronize on both sides, CUDA
+        events on the launching stream, max over ranks; `prepare(rep)` (state restore, untimed) precedes every repetition.
+        Repeats until the timed regions add up to min_ms; returns (median ms, all ms)."""
+        times, total = [], 0.0
+        while True:
+            rep = len(times)
+            prepare(rep)
+            self.barrier()
+            self.ev0.record(self.stream)
+            run(rep)
+            self.ev1.record(self.stream)
+            self.barrier()
+            ms = self.max_over_ranks(self.ev0.elapsed_time(self.ev1))      # identical on every rank: so is the loop count
+            times.append(ms)
+            total += ms
+            if total >= min_ms or len(times) >= max_reps:
+                break
+        return float(np.median(times)), times
+
+    def finish(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def measure_workload(hx, workload, B, K, W, R, paths=("rollout", "graph", "eager"), with_e2e=True, ragged=False, min_ms=MIN_TIMED_MS):
+    """One workload on this rank's shard: the persistent-rollout path, the graph-replayed and the eager single-step paths,
+    and (with_e2e) the host-buffer legs.  Returns a dict; every collective inside is executed by every rank."""
+    torch, args, dev, world, rank, stream = hx.torch, hx.args, hx.dev, hx.world, hx.rank, hx.stream
+    discrete = workload == "discrete"
+    bm = build_engine(B, dev, rank, world, workload, args.obs_f32)
+    if args.no_ring:
+        bm.set_rollout_ring(False)
+    if args.emit != "auto":
+        bm.set_emit_image(args.emit == "image")
+    if args.image_shape is not None:
+        bm.set_image_shape(args.image_shape)
+    if ragged:
+        bm.set_ragged(True)                    # (what set_trajectories / a masked reset do on their own)
+    if args.no_specialised or (args.emit == "lsu" and ragged):
+        bm.set_rollout_specialised(False)      # (LSU emitters, envs at unrelated steps: the plain persistent kernel is the faster one)
+    groups = bm.groups
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2 + rank)
+
+    def rand_actions(steps, g):
+        if discrete:
+            return torch.randint(0, g.n_actions, (steps, g.n_envs), dtype=torch.int32, device=dev, generator=gen)
+        return torch.rand((steps, g.n_envs, g.n_act), dtype=torch.float64, device=dev, generator=gen)
+    rings = [torch.empty((R, g.n_envs, g.obs_dim), dtype=bm.obs_dtype, device=dev) for g in groups]
+    ring_bytes = sum(r.numel() * r.element_size() for r in rings)
+    if ragged:
+        for g in groups:
+            hi = 8760 - 2 * (W + K) - 64 if 2 * (W + K) < 4000 else 100
+            g.step.copy_(torch.randint(0, hi, (g.n_envs,), dtype=torch.int32, device=dev, generator=gen))
+    state0 = bm.state_dict()
+    step_bytes = sum(g.n_envs * (4 if discrete else 8 * g.n_act) for g in groups)      # action bytes of one step
+    # Action blocks of Kc steps: every repetition of a timed region reads a block that the previous repetitions did not
+    # leave in L2 (the blocks together exceed 2 x L2), every step its own actions.
+    Kc = min(K, 2048)
+    n_blocks = int(min(16, max(2, -(-2 * L2_BYTES // (Kc * step_bytes)))))
+    blocks = [[rand_actions(Kc, g) for g in groups] for _ in range(n_blocks)]
+    act_bytes = n_blocks * Kc * step_bytes
+    chunks = [Kc] * (K // Kc) + ([K % Kc] if K % Kc else [])
+    out = {"batch_per_gpu": B, "l2": f"inputs larger than L2: obs ring of {R} buffers = {ring_bytes / 1e6:.0f} MB, {n_blocks} action blocks of "
+                                     f"{Kc} steps = {act_bytes / 1e6:.0f} MB per GPU, rotated between repetitions (L2 126 MB)"}
+
+    launchers = {}
+
+    def one_step(s):      # single-step launch s: actions of step s % (n_blocks Kc), obs slot s % R
+        key = (s % (n_blocks * Kc), s % R)
+        if key not in launchers:
+            b, k = divmod(key[0], Kc)
+            launchers[key] = bm.prepare_step([a[k] for a in blocks[b]], obs=[r[key[1]] for r in rings], discrete=discrete)
+        launchers[key]()
+
+    def restore(rep=0):
+        bm.load_state_dict(state0)
+
+    results = {}
+    with torch.cuda.stream(stream):
+        if args.preheat > 0:     # untimed: bring the clocks to their loaded state
+            t0, s = time.perf_counter(), 0
+            while time.perf_counter() - t0 < args.preheat:
+                for _ in range(32):
+                    one_step(s % 64)
+                    s += 1
+                stream.synchronize()
+        for path in paths:
+            restore()
+            if path == "rollout":    # persistent kernel: the K steps run in ceil(K / 2048) launches
+                bm.rollout([a[:max(W, 3)] for a in blocks[0]], ring=R, keep_obs=True, discrete=discrete)         # warm-up steps
+                outs = {n: bm.rollout([a[:n] for a in blocks[0]], ring=R, keep_obs=True, discrete=discrete) for n in set(chunks)}
+                outs = {n: (o if isinstance(o, list) else [o]) for n, o in outs.items()}
+                # untimed: bind the argument blocks, so that a timed launch is one C call
+                binds = {(b, n): bm.prepare_rollout([a[:n] for a in blocks[b]], ring=R, keep_obs=True, discrete=discrete, out=outs[n])
+                         for b in range(n_blocks) for n in set(chunks)}
+                launch0 = bm.launch_count
+
+                def run(rep):
+                    for n in chunks:
+                        binds[rep % n_blocks, n]()
+                per_rep = len(chunks)
+            elif path == "graph":    # one mg_step launch per step, replayed from a CUDA graph
+                chunk = K if K <= 256 else max(d for d in range(1, 257) if K % d == 0)
+                for s in range(W + chunk):      # make every launcher of the chunk exist before capture
+                    one_step(s)
+                restore()
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    for s in range(W, W + chunk):
+                        one_step(s)
+                restore()
+                for s in range(W):
+                    one_step(s)
+
+                def run(rep):
+                    for _ in range(K // chunk):
+                        graph.replay()
+                per_rep = K
+            else:                    # eager: one mg_step launch per step from Python
+                for s in range(W + min(K, 256)):
+                    one_step(s)
+                restore()
+                for s in range(W):
+                    one_step(s)
+
+                def run(rep):
+                    for s in range(W, W + K):
+                        one_step(s)
+                per_rep = K
+            sampler = ClockSampler(hx.local_rank)
+            sampler.start()
+            ms, all_ms = hx.timed(run, restore, min_ms=min_ms if path != "eager" else min(min_ms, 20.0))
+            clocks = sampler.stop()
+            results[path] = {"ms": ms, "repeats": len(all_ms), "ms_min": min(all_ms), "ms_max": max(all_ms), "launches": per_rep, "clocks": clocks,
+                             "kernel": bm.last_kernel}
+    out["paths"] = results
+    nbytes = sum(g.n_envs * algorithmic_bytes(*g.arch, discrete=discrete, obs_bytes=4 if args.obs_f32 else 8) for g in groups)
+    out["bytes_per_step"] = nbytes
+    out["cfg_bytes_single_step"] = sum(g.n_envs * (336 + 8 * g.arch[1]) for g in groups) if workload == "generator" else 0
+    out["obs_dims"] = [g.obs_dim for g in groups]
+
+    if not with_e2e:
+        del bm
+        return out
+    # ---- end to end through the public API with host buffers -------------------------------------------------
+    # (1) HostIO.step(): one step per call -- actions pinned-host -> device (one copy), fused kernel, reward + done
+    #     device -> pinned-host (one copy), serialised on one stream: the figure a host-side control loop sees.
+    Ke = min(K, 200)
+    restore()
+    hio = bm.host_io(normalized=True, obs=[r[0] for r in rings], discrete=discrete)
+    for a, g in zip(hio.actions, groups):          # the caller's actions, in pinned host memory
+        a.copy_(torch.randint(0, g.n_actions, tuple(a.shape), dtype=torch.int32) if discrete else torch.rand(tuple(a.shape), dtype=torch.float64))
+    with torch.cuda.stream(stream):
+        for s in range(3):
+            hio.step()
+
+        def run_hio(rep):
+            for s in range(Ke):
+                hio.step()
+        ms_hio, reps_hio = hx.timed(run_hio, restore, min_ms=min(min_ms, 30.0), max_reps=50)
+    h2d, d2h = hio.h2d_bytes, hio.d2h_bytes
+    e2e_step_value = world * B * Ke / (ms_hio * 1e-3)
+    e2e = {"value": e2e_step_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke, "repeats": len(reps_hio),
+           "api": "BatchedMicrogrid.host_io().step()",
+           "note": "actions written into pinned host memory by the caller, one H2D copy, fused kernel, one D2H copy of "
+                   "reward+done, every step; observations stay on the device"}
+    # (1b) the same loop with the observations ALSO copied to the host every step (a host-side consumer of obs): PCIe-bound
+    obs_host = None
+    try:
+        h_obs = [torch.empty((g.n_envs, g.obs_dim), dtype=bm.obs_dtype, pin_memory=True) for g in groups]
+        n_o = min(Ke, 24)
+        with torch.cuda.stream(stream):
+            def run_obs(rep):
+                for s in range(n_o):
+                    hio.step()
+                    for h, r in zip(h_obs, rings):
+                        h.copy_(r[0], non_blocking=True)
+            ms_o, _ = hx.timed(run_obs, restore, min_ms=min(min_ms, 30.0), max_reps=5)
+        obs_bytes = sum(h.numel() * h.element_size() for h in h_obs)
+        obs_host = {"value": world * B * n_o / (ms_o * 1e-3), "unit": UNIT, "d2h_bytes_per_step": d2h + obs_bytes, "steps": n_o,
+                    "note": "HostIO.step() plus a device -> pinned-host copy of EVERY observation row each step: what a host-side "
+                            "consumer of the observations would see (the obs are 97% of the bytes; PCIe is the bound)"}
+        del h_obs
+    except Exception as ex:
+        obs_host = {"error": f"{type(ex).__name__}: {ex}"}
+    # (2) HostRollout.run(): the workload's own call (a year rollout with pre-generated actions) with HOST buffers --
+    #     every step's actions cross the bus host -> device and every step's reward + done come back, in chunks of
+    #     `chunk` steps, the copies of neighbouring chunks overlapped with the persistent kernel on three streams.
+    #     Same bytes per step as (1); this is the headline e2e figure when it runs (any failure keeps (1) and says so).
+    # Collectives (barrier, max over ranks) stay outside the try blocks so that a failure on one rank cannot hang the others.
+    Kr = min(K, 1024)
+    chunk = max(1, min(64, Kr // 4))           # at least four chunks: the three-stream pipeline is exercised at any K
+    del hio
+    errors = {}
+    for pipeline in ("native", "torch"):       # mg_rollout_host (one C-ABI call); else the same schedule from torch streams
+        err, hr, launch_e = None, None, 0
+        try:
+            restore()
+            hr = bm.host_rollout(Kr, chunk=chunk, normalized=True, discrete=discrete, ring=R, pipeline=pipeline)
+            for a, g in zip(hr.actions, groups):
+                if discrete:
+                    a.copy_(torch.randint(0, g.n_actions, tuple(a.shape), dtype=torch.int32))
+                else:
+                    a.uniform_(0.0, 1.0)
+            with torch.cuda.stream(stream):
+                hr.run(min(Kr, 3 * chunk) if Kr % chunk == 0 else Kr)      # warm-up (untimed)
+                restore()
+        except Exception as ex:      # keep the per-step figure; never lose the bench line to this path
+            err = f"{type(ex).__name__}: {ex}"
+        ok = hx.max_over_ranks(0.0 if err is None else 1.0) == 0.0
+        ms_e, reps_e = float("inf"), []
+        if ok:
+            state = {"err": None}
+
+            def run_hr(rep):
+                if state["err"] is None:
+                    try:
+                        hr.run()
+                    except Exception as ex:
+                        state["err"] = f"{type(ex).__name__}: {ex}"
+            with torch.cuda.stream(stream):
+                launch_e = bm.launch_count
+                ms_e, reps_e = hx.timed(run_hr, restore, min_ms=min_ms, max_reps=20)
+                launch_e = (bm.launch_count - launch_e) // max(len(reps_e), 1)
+            err = state["err"]
+            if err is None and not all(bool(torch.isfinite(r).all()) for r in hr.reward):
+                err = "non-finite reward came back from the host rollout"
+            ok = hx.max_over_ranks(0.0 if err is None else 1.0) == 0.0
+        if ok:
+            name = "mg_rollout_host" if pipeline == "native" else "mg_rollout + torch streams"
+            e2e = {"value": world * B * Kr / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": hr.h2d_bytes_per_step,
+                   "d2h_bytes_per_step": hr.d2h_bytes_per_step, "steps": Kr, "chunk_steps": chunk, "repeats": len(reps_e),
+                   "gpu_launches": launch_e, "us_per_step": 1e3 * ms_e / Kr,
+                   "pcie_gbs": {"h2d": hr.h2d_bytes_per_step * Kr / (ms_e * 1e-3) / 1e9, "d2h": hr.d2h_bytes_per_step * Kr / (ms_e * 1e-3) / 1e9,
+                                "note": "per rank (GB/s of this rank's host <-> device copies; the slowest rank sets the time)"},
+                   "api": f"BatchedMicrogrid.host_rollout(n_steps).run() -> {name}",
+                   "note": "year-rollout call with HOST buffers: every step's actions go pinned-host -> device and every step's "
+                           f"reward + done come back device -> pinned-host inside the timed region, in chunks of {chunk} steps; copy-in, "
+                           "persistent kernel and copy-out of neighbouring chunks overlap on three streams (PCIe-bound); "
+                           "observations stay in the device ring (97% of the bytes: see obs_to_host for a host-side consumer of them)",
+                   "per_step_call": {"value": e2e_step_value, "api": "BatchedMicrogrid.host_io().step()", "steps": Ke,
+                                     "note": "one H2D + kernel + one D2H per step, serialised (a host-side control loop)"}}
+        else:
+            errors[pipeline] = err or "failed on another rank"
+        hr = None
+        if ok:
+            break
+    if errors:
+        e2e["host_rollout_errors"] = errors
+    e2e["obs_to_host"] = obs_host
+    out["e2e"] = e2e
+    del bm
+    return out
+
+
+def roofline_block(m, path, K, args, workload):
+    """roofline object of one measured path: algorithmic bytes per launch / average launch duration, vs the measured copy peak"""
+    r = m["paths"][path]
+    peak, peak_src = measured_peak()
+    per_step = m["bytes_per_step"] + (m["cfg_bytes_single_step"] if path != "rollout" else 0)
+    # (+ the env's own parameter record and status word(s), re-read by every single-step launch of the generator workload:
+    #  SURVEY.md 8d; inside the persistent kernel they stay cache-resident and are not counted)
+    launches = r["launches"]
+    steps_per_launch = K / max(launches, 1)
+    achieved = per_step * K / (r["ms"] * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+            "kernel": r["kernel"],
+            "bytes_per_launch": per_step * steps_per_launch, "bytes_per_step": per_step, "steps_per_launch": steps_per_launch}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,7 +696,8 @@ def main():
     ap.add_argument("--path", default="rollout", choices=("rollout", "graph", "eager"),
                     help="headline path: the persistent rollout kernel (BASELINE configs[2] is a year rollout with pre-generated "
                          "actions), one mg_step launch per step replayed from a CUDA graph, or plain launches from Python")
-    ap.add_argument("--single-path", action="store_true", help="time only the headline path")
+    ap.add_argument("--single-path", action="store_true", help="time only the headline path (no other paths, no e2e, no configs block)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the in-run measurements of the other BASELINE configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--obs-f32", action="store_true",
                     help="NON-CANONICAL secondary mode: observations written as float32 (half the dominant bytes); reported with dtype f64+f32obs")
@@ -349,10 +706,12 @@ def main():
     ap.add_argument("--no-ring", action="store_true",
                     help="per-env series batches (generator workload): use the persistent kernel that normalises whole windows per "
                          "row instead of the one that keeps sliding windows in shared memory (A/B)")
-    ap.add_argument("--emit", default="image", choices=("image", "lsu"),
-                    help="row emitter: shared-memory images + TMA bulk stores (default) or the per-lane 16-byte store emitters (A/B)")
+    ap.add_argument("--emit", default="auto", choices=("auto", "image", "lsu"),
+                    help="row emitter: the library's choice per launch (default), shared-memory images + TMA bulk stores, or the per-lane "
+                         "16-byte store emitters (A/B)")
     ap.add_argument("--image-shape", type=int, default=None, help="MG_OPT_IMAGE_SHAPE index (tuning)")
     ap.add_argument("--no-specialised", action="store_true", help="persistent kernel without the owner / emitter warp split (A/B)")
+    ap.add_argument("--min-timed-ms", type=float, default=MIN_TIMED_MS, help="repeat a timed region until it adds up to this much")
     ap.add_argument("--preheat", type=float, default=0.2, help="seconds of untimed steps before the warm-up (0 under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -362,272 +721,72 @@ def main():
     if args.workload == "composed":
         return run_composed(args)
 
-    import torch
-    rank, local_rank, world = dist_env()
-    if world > 1:
-        import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device(f"cuda:{local_rank}")
+    hx = Harness(args)
+    rank, world = hx.rank, hx.world
     if args.batch is None:
         args.batch = {"replicas": 4096, "generator": 131072}.get(args.workload, BATCH_PER_GPU)
     B, K, W, R = args.batch, args.steps, args.warmup, args.ring
-    discrete = args.workload == "discrete"
-
-    bm = build_engine(B, dev, rank, world, args.workload, args.obs_f32)
-    if args.no_ring:
-        bm.set_rollout_ring(False)
-    if args.emit == "lsu":
-        bm.set_emit_image(False)
-    if args.image_shape is not None:
-        bm.set_image_shape(args.image_shape)
-    if args.no_specialised or (args.emit == "lsu" and args.ragged):
-        bm.set_rollout_specialised(False)      # (LSU emitters, envs at unrelated steps: the plain persistent kernel is the faster one)
-    groups = bm.groups
-
-    def rand_actions(steps, g):
-        if discrete:
-            return torch.randint(0, g.n_actions, (steps, g.n_envs), dtype=torch.int32, device=dev, generator=gen)
-        return torch.rand((steps, g.n_envs, g.n_act), dtype=torch.float64, device=dev, generator=gen)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(2 + rank)
-    # every step reads its own actions from HBM: a ring of A steps (> 2x L2) reused cyclically
-    A = min(W + K, 256)
-    acts = [rand_actions(A, g) for g in groups]
-    rings = [torch.empty((R, g.n_envs, g.obs_dim), dtype=bm.obs_dtype, device=dev) for g in groups]
-    ring_bytes = sum(r.numel() * r.element_size() for r in rings)
-    act_bytes = sum(a.numel() * 8 for a in acts)
-    if args.ragged:
-        for g in groups:
-            g.step.copy_(torch.randint(0, 8760 - 2 * (W + K) - 64 if 2 * (W + K) < 4000 else 100, (g.n_envs,), dtype=torch.int32, device=dev, generator=gen))
-    state0 = bm.state_dict()
-    launchers = {}   # one pre-bound launcher per (action slot, obs slot)
-
-    def one_step(s):
-        key = (s % A, s % R)
-        if key not in launchers:
-            launchers[key] = bm.prepare_step([a[key[0]] for a in acts], obs=[r[key[1]] for r in rings], discrete=discrete)
-        launchers[key]()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    stream = torch.cuda.Stream(device=dev)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    def max_over_ranks(ms):
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
-
-    def time_path(path):
-        """W untimed warm-up steps, then EXACTLY K timed steps between barrier + synchronize; returns (ms, launches, clocks)."""
-        bm.load_state_dict(state0)
-        if path == "rollout":    # persistent kernel: the K steps run in ceil(K / 2048) launches
-            Kc = min(K, 2048)
-            gen.manual_seed(3 + rank)
-            timed = [rand_actions(Kc, g) for g in groups]
-            chunks = [Kc] * (K // Kc) + ([K % Kc] if K % Kc else [])
-            bm.rollout([a[:max(W, 3)] for a in timed], ring=R, keep_obs=True, discrete=discrete)             # warm-up steps
-            # untimed: allocate the outputs and bind the argument blocks, so that a timed launch is one C call
-            binds = {n: bm.prepare_rollout([a[:n] for a in timed], ring=R, keep_obs=True, discrete=discrete) for n in set(chunks)}
-            bm.load_state_dict(state0)
-            barrier()
-            sampler = ClockSampler(local_rank)
-            sampler.start()
-            launch0 = bm.launch_count
-            ev0.record(stream)
-            for n in chunks:
-                binds[n]()
-            ev1.record(stream)
-        elif path == "graph":    # one mg_step launch per step, replayed from a CUDA graph
-            chunk = K if K <= 256 else max(d for d in range(1, 257) if K % d == 0)
-            for s in range(W + chunk):      # make every launcher of the chunk exist before capture
-                one_step(s)
-            bm.load_state_dict(state0)
-            torch.cuda.synchronize()
-            launch0 = bm.launch_count
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=stream):
-                for s in range(W, W + chunk):
-                    one_step(s)
-            captured = bm.launch_count - launch0
-            bm.load_state_dict(state0)
-            for s in range(W):
-                one_step(s)
-            barrier()
-            sampler = ClockSampler(local_rank)
-            sampler.start()
-            launch0 = bm.launch_count - captured * (K // chunk)
-            ev0.record(stream)
-            for _ in range(K // chunk):
-                graph.replay()
-            ev1.record(stream)
-        else:                    # eager: one mg_step launch per step from Python
-            for s in range(W + min(K, A * R)):
-                one_step(s)
-            bm.load_state_dict(state0)
-            for s in range(W):
-                one_step(s)
-            barrier()
-            sampler = ClockSampler(local_rank)
-            sampler.start()
-            launch0 = bm.launch_count
-            ev0.record(stream)
-            for s in range(W, W + K):
-                one_step(s)
-            ev1.record(stream)
-        barrier()
-        clocks = sampler.stop()
-        return max_over_ranks(ev0.elapsed_time(ev1)), bm.launch_count - launch0, clocks
-
-    with torch.cuda.stream(stream):
-        if args.preheat > 0:     # untimed: bring the clocks to their loaded state
-            t0 = time.perf_counter()
-            s = 0
-            while time.perf_counter() - t0 < args.preheat:
-                for _ in range(64):
-                    one_step(s)
-                    s += 1
-                stream.synchronize()
-        ms, launches, clocks = time_path(args.path)
-        others = {}
-        if not args.single_path:
-            for p in ("rollout", "graph", "eager"):
-                if p != args.path:
-                    ms_p, l_p, _ = time_path(p)
-                    others[p] = {"value": world * B * K / (ms_p * 1e-3), "us_per_step": 1e3 * ms_p / K, "gpu_launches": l_p}
-    value = world * B * K / (ms * 1e-3)
-
-    # ---- end to end through the public API with host buffers -------------------------------------------------
-    # (1) HostIO.step(): one step per call -- actions pinned-host -> device (one copy), fused kernel, reward + done
-    #     device -> pinned-host (one copy), serialised on one stream: the figure a host-side control loop sees.
-    Ke = min(K, 200)
-    bm.load_state_dict(state0)
-    hio = bm.host_io(normalized=True, obs=[r[0] for r in rings], discrete=discrete)
-    for a, g in zip(hio.actions, groups):          # the caller's actions, in pinned host memory
-        a.copy_(torch.randint(0, g.n_actions, tuple(a.shape), dtype=torch.int32) if discrete else torch.rand(tuple(a.shape), dtype=torch.float64))
-    with torch.cuda.stream(stream):
-        for s in range(3):
-            hio.step()
-        barrier()
-        ev0.record(stream)
-        for s in range(Ke):
-            hio.step()
-        ev1.record(stream)
-        barrier()
-    h2d, d2h = hio.h2d_bytes, hio.d2h_bytes
-    e2e_step_value = world * B * Ke / (max_over_ranks(ev0.elapsed_time(ev1)) * 1e-3)
-    e2e = {"value": e2e_step_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-           "api": "BatchedMicrogrid.host_io().step()",
-           "note": "actions written into pinned host memory by the caller, one H2D copy, fused kernel, one D2H copy of "
-                   "reward+done, every step; observations stay on the device"}
-    # (2) HostRollout.run(): the workload's own call (a year rollout with pre-generated actions) with HOST buffers --
-    #     every step's actions cross the bus host -> device and every step's reward + done come back, in chunks of
-    #     `chunk` steps, the copies of neighbouring chunks overlapped with the persistent kernel on three streams.
-    #     Same bytes per step as (1); this is the headline e2e figure when it runs (any failure keeps (1) and says so).
-    # Collectives (barrier, max over ranks) stay outside the try blocks so that a failure on one rank cannot hang the others.
-    Kr, chunk = min(K, 1024), 64
-    del hio
-    errors = {}
-    for pipeline in ("native", "torch"):       # mg_rollout_host (one C-ABI call); else the same schedule from torch streams
-        err, hr, ms_local, launch_e = None, None, float("inf"), 0
-        try:
-            bm.load_state_dict(state0)
-            hr = bm.host_rollout(Kr, chunk=chunk, normalized=True, discrete=discrete, ring=R, pipeline=pipeline)
-            for a, g in zip(hr.actions, groups):
-                if discrete:
-                    a.copy_(torch.randint(0, g.n_actions, tuple(a.shape), dtype=torch.int32))
-                else:
-                    a.uniform_(0.0, 1.0)
-            with torch.cuda.stream(stream):
-                hr.run(min(Kr, 3 * chunk) if Kr % chunk == 0 else Kr)      # warm-up (untimed)
-                bm.load_state_dict(state0)
-        except Exception as ex:      # keep the per-step figure; never lose the bench line to this path
-            err = f"{type(ex).__name__}: {ex}"
-        barrier()
-        if err is None:
+    paths = (args.path,) if args.single_path else (args.path,) + tuple(p for p in ("rollout", "graph", "eager") if p != args.path)
+    m = measure_workload(hx, args.workload, B, K, W, R, paths=paths, with_e2e=not args.single_path, ragged=args.ragged, min_ms=args.min_timed_ms)
+    head = m["paths"][args.path]
+    value = world * B * K / (head["ms"] * 1e-3)
+    # ---- the other BASELINE configs, measured briefly in the same run (every rank runs its shard) ----------------------
+    configs = None
+    if args.workload == "pymgrid25" and not args.single_path and not args.no_configs and not args.ragged and not args.obs_f32:
+        configs = {}
+        Kc = min(K, 256)
+        for name, wl, Bc, cpaths in (("configs[1]", "replicas", 4096, ("graph", "rollout")), ("configs[3]", "discrete", BATCH_PER_GPU, ("rollout", "graph")),
+                                     ("configs[4]", "generator", 131072, ("rollout",))):
             try:
-                with torch.cuda.stream(stream):
-                    launch_e = bm.launch_count
-                    ev0.record(stream)
-                    hr.run()
-                    ev1.record(stream)
-                torch.cuda.synchronize()
-                launch_e = bm.launch_count - launch_e
-                if not all(bool(torch.isfinite(r).all()) for r in hr.reward):
-                    raise RuntimeError("non-finite reward came back from the host rollout")
-                ms_local = ev0.elapsed_time(ev1)
-            except Exception as ex:
-                err = f"{type(ex).__name__}: {ex}"
-                ms_local = float("inf")
-        barrier()
-        ms_e = max_over_ranks(ms_local)
-        if ms_e != float("inf"):
-            name = "mg_rollout_host" if pipeline == "native" else "mg_rollout + torch streams"
-            e2e = {"value": world * B * Kr / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": hr.h2d_bytes_per_step,
-                   "d2h_bytes_per_step": hr.d2h_bytes_per_step, "steps": Kr, "chunk_steps": chunk,
-                   "gpu_launches": launch_e, "us_per_step": 1e3 * ms_e / Kr,
-                   "pcie_gbs": {"h2d": hr.h2d_bytes_per_step * Kr / (ms_e * 1e-3) / 1e9, "d2h": hr.d2h_bytes_per_step * Kr / (ms_e * 1e-3) / 1e9},
-                   "api": f"BatchedMicrogrid.host_rollout(n_steps).run() -> {name}",
-                   "note": "year-rollout call with HOST buffers: every step's actions go pinned-host -> device and every step's "
-                           "reward + done come back device -> pinned-host inside the timed region, in chunks of 64 steps; copy-in, "
-                           "persistent kernel and copy-out of neighbouring chunks overlap on three streams (PCIe-bound); "
-                           "observations go to the device ring",
-                   "per_step_call": {"value": e2e_step_value, "api": "BatchedMicrogrid.host_io().step()", "steps": Ke,
-                                     "note": "one H2D + kernel + one D2H per step, serialised (a host-side control loop)"}}
-        else:
-            errors[pipeline] = err or "failed on another rank"
-        hr = None
-        if ms_e != float("inf"):
-            break
-    if errors:
-        e2e["host_rollout_errors"] = errors
+                mc = measure_workload(hx, wl, Bc, Kc, W, R, paths=cpaths, with_e2e=False, min_ms=min(args.min_timed_ms, 30.0))
+                entry = {"workload": WORKLOADS[wl], "batch_per_gpu": Bc, "global_batch": world * Bc, "steps": Kc}
+                for pth in cpaths:
+                    r = mc["paths"][pth]
+                    rb = roofline_block(mc, pth, Kc, args, wl)
+                    entry[pth] = {"value": world * Bc * Kc / (r["ms"] * 1e-3), "unit": UNIT, "us_per_step": 1e3 * r["ms"] / Kc, "repeats": r["repeats"],
+                                  "kernel": r["kernel"],
+                                  "roofline_frac": rb["frac"], "achieved_gbs": rb["achieved"], "bytes_per_step": rb["bytes_per_step"]}
+                entry["headline_path"] = cpaths[0]
+                configs[name] = entry
+            except Exception as ex:      # (collectives inside measure_workload are unconditional; a failure here is deterministic on every rank)
+                configs[name] = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank == 0:
-        bytes_per_launch = sum(g.n_envs * algorithmic_bytes(*g.arch, discrete=discrete, obs_bytes=4 if args.obs_f32 else 8) for g in groups)
-        if args.workload == "generator" and args.path != "rollout":
-            # + the env's own parameter record and status word(s), re-read by every single-step launch (SURVEY.md 8d: +~176 B
-            # there, 336 B with this engine's record); inside the persistent kernel they stay cache-resident and are not counted
-            bytes_per_launch += sum(g.n_envs * (336 + 8 * g.arch[1]) for g in groups)
-        peak, peak_src = measured_peak()
-        bytes_per_step = bytes_per_launch
-        steps_per_launch = K / max(launches, 1)
-        bytes_per_launch = bytes_per_step * steps_per_launch
-        achieved = bytes_per_launch / (ms * 1e-3 / max(launches, 1)) / 1e9
+        roof = roofline_block(m, args.path, K, args, args.workload)
         traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                tr = json.load(f)["mg_rollout_kernel" if args.path == "rollout" else "mg_step_kernel"]
+                tr = json.load(f)[roof["kernel"].split(" ")[0]]
             if tr["dram_bytes_per_step"] and B == BATCH_PER_GPU and args.workload == "pymgrid25" and not args.obs_f32 and not args.ragged:
-                traffic, traffic_src = tr["dram_bytes_per_step"] * steps_per_launch, tr["source"]
+                traffic, traffic_src = tr["dram_bytes_per_step"] * roof["steps_per_launch"], tr["source"]
         except Exception:
             pass
+        roof.update({"traffic": traffic, "traffic_source": traffic_src, "write_only_ceilings_gbs": {"lsu_16_byte_stores": 5780.0, "tma_bulk_stores_4_rows": 7200.0},
+                     "note": "peak is the read+write copy bandwidth (torch copy); this path is ~97% stores: tools/microbench_store.cu measured 5.78 TB/s "
+                             "for per-lane 16-byte stores and 7.2 TB/s for TMA bulk stores of 4 rows on this GPU (profiles/r02_microbench_store.txt)"})
+        others = {p: {"value": world * B * K / (r["ms"] * 1e-3), "us_per_step": 1e3 * r["ms"] / K, "gpu_launches": r["launches"], "repeats": r["repeats"]}
+                  for p, r in m["paths"].items() if p != args.path}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": head["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if not args.obs_f32 else "f64 arithmetic, f32 observation output (non-canonical)",
             "data": "pymgrid25 scenario parameters + series (bundled), synthetic U[0,1) actions",
+            "repeats": head["repeats"],
+            "timing": {"rule": f"the K-step timed region is repeated until the repetitions add up to {args.min_timed_ms:.0f} ms (state restored and a fresh "
+                               "action block in between, untimed); value / ms_per_step are the MEDIAN repetition, max over ranks each",
+                       "ms_min": head["ms_min"], "ms_median": head["ms"], "ms_max": head["ms_max"]},
             "config": {"workload": WORKLOADS[args.workload],
-                       "batch_per_gpu": B, "global_batch": world * B, "forecast_horizon": 23, "path": args.path, "ragged_steps": bool(args.ragged), "emit": args.emit, "image_shape": args.image_shape, "specialised": not args.no_specialised,
-                       "l2": f"inputs larger than L2: obs ring of {R} buffers = {ring_bytes / 1e6:.0f} MB and action ring = {act_bytes / 1e6:.0f} MB per GPU (L2 126 MB)",
-                       "parallelism": f"batch sharded over {world} GPU(s), no collective on the step path"},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "e2e": e2e,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "mg_step_kernel" if args.path != "rollout" else "mg_rollout_kernel",
-                         "bytes_per_launch": bytes_per_launch, "bytes_per_step": bytes_per_step, "steps_per_launch": steps_per_launch,
-                         "write_only_ceiling_gbs": 5450.0,
-                         "note": "peak is the read+write copy bandwidth; this path is ~97% stores, plain 16-byte stores measured 5.45 TB/s on this GPU (tools/microbench.py)"},
+                       "batch_per_gpu": B, "global_batch": world * B, "forecast_horizon": 23, "path": args.path, "ragged_steps": bool(args.ragged),
+                       "emit": args.emit, "image_shape": args.image_shape, "specialised": not args.no_specialised, "l2": m["l2"],
+                       "parallelism": f"batch sharded over {world} GPU(s), no collective on the step path", "cpu_affinity": hx.affinity},
+            "gpu_launches": head["launches"],
+            "clocks": head["clocks"],
+            "e2e": m.get("e2e"),
+            "roofline": roof,
             "other_paths": others,
         }
+        if configs is not None:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             n_envs, n_steps, reps = 16384, 250, 20          # 81.9e6 env-steps: ~20 s of CPU work at ~4e6 steps/s/core
@@ -638,10 +797,9 @@ def main():
                                     "sample": f"{n_envs} envs x {n_steps * reps} steps of the same workload = {n_envs * n_steps * reps / 1e6:.1f}e6 "
                                               f"env-steps in {dt:.2f} s wall on {threads} threads (C oracle port of Microgrid.run, full obs every step)",
                                     "single_core": rate1,
-                                    "python_reference_note": "the unmodified Python reference measures ~1e3 env-steps/s/core (BASELINE.md); it cannot travel to this box"}
+                                    "python_reference": python_reference_figure()}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    hx.finish()
     return 0
 
 

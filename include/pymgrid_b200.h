@@ -316,17 +316,23 @@ int mg_forecast_noise(MgHandle *h, const MgForecastNoise *noise /* DEVICE [n_cfg
  * kernel when every group writes observations.  It wins when the envs of a tile advance in lock-step (11.5 vs 12.4
  * us/step at 65 536 envs) and loses when every env is at its own step (39.6 vs 29 us/step): hosts that install per-env
  * trajectory windows turn it off. */
-enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2, MG_OPT_EMIT_IMAGE = 3, MG_OPT_IMAGE_SHAPE = 4 };
+enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2, MG_OPT_EMIT_IMAGE = 3, MG_OPT_IMAGE_SHAPE = 4, MG_OPT_RAGGED_HINT = 5 };
 /* MG_OPT_ROLLOUT_RING (default 1): batches with per-env series (MG_LAYOUT_SCALED_SERIES / grid_status_bits) run mg_rollout
  * with every env's normalised load / pv windows held in shared memory (H + 2 slots per env and series; one new value per
  * env, series and step instead of a whole window per row) when all horizons are <= 24.  0 selects the kernel that
  * normalises whole windows per row (the one mg_step uses). */
-/* MG_OPT_EMIT_IMAGE (default 1): observation rows are assembled in shared-memory images and leave the SM as TMA bulk stores
- * (cp.async.bulk shared -> global, several rows per store) instead of per-lane 16-byte stores; applies when rows are f64,
- * 1 + H <= 32 and the grid block starts at an even element, else the LSU emitters run.  0 selects the LSU emitters.
- * MG_OPT_IMAGE_SHAPE (default 0): which instantiated (rows per bulk store, image buffers per emitting warp, rows gathered
- * together) shape the image kernels use -- 0: (4, 2, 2), 1: (2, 2, 2), 2: (4, 2, 4), 3: (8, 2, 2); a tuning knob, results
- * do not depend on it. */
+/* MG_OPT_EMIT_IMAGE: how observation rows leave the SM.  1 = assembled in shared-memory images and stored with TMA bulk
+ * stores (cp.async.bulk shared -> global, several rows per store; needs f64 rows, 1 + H <= 32 and a grid block that starts
+ * at an even element, else the other emitters run); 0 = per-lane 16-byte stores with run detection (rows of a tile that
+ * read the same windows fetch them once); 2 (default) = the library chooses per launch from what was measured: images for
+ * per-env series, for envs at unrelated steps (MG_OPT_RAGGED_HINT), for batches of at most two tiles per multiprocessor and
+ * for persistent launches over rows with an even forecast horizon; per-lane stores for large table-backed batches in
+ * lock-step.  Results never depend on the choice.
+ * MG_OPT_IMAGE_SHAPE (default -1 = the library's choice): which instantiated (rows per bulk store, image buffers per
+ * emitting warp, rows gathered together) shape the image kernels use -- 0: (4, 2, 2), 1: (2, 2, 2), 2: (4, 2, 4),
+ * 3: (8, 2, 2); a tuning knob.
+ * MG_OPT_RAGGED_HINT (default 0): tell the library that the envs of a tile are at unrelated steps (independent resets,
+ * per-env episode windows), where no two rows share a window. */
 int mg_set_option(MgHandle *h, int option, int value);
 
 /*
@@ -344,6 +350,8 @@ int mg_set_reported_soc(MgHandle *h, const double *const *soc);
 
 /* number of kernel launches this handle has enqueued since creation (bench.py's gpu_launches claim) */
 int64_t mg_launch_count(const MgHandle *h);
+/* name of the kernel family the last mg_step* / mg_rollout* call on the handle launched (which emitters MG_OPT_EMIT_IMAGE = 2 chose) */
+const char *mg_last_kernel(const MgHandle *h);
 
 #ifdef __cplusplus
 }

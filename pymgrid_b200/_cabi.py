@@ -18,6 +18,7 @@ MG_OPT_ROLLOUT_SPECIALISED = 1
 MG_OPT_ROLLOUT_RING = 2
 MG_OPT_EMIT_IMAGE = 3
 MG_OPT_IMAGE_SHAPE = 4
+MG_OPT_RAGGED_HINT = 5
 
 FLAG_NAMES = {
     1 << 0: "GENSET_GOAL_RANGE", 1 << 1: "GENSET_AS_SINK", 1 << 2: "BALANCE", 1 << 3: "BATTERY_MIN_CAP",
@@ -129,6 +130,8 @@ def lib():
     L.mg_set_reported_soc.argtypes = [_vp, C.POINTER(_vp)]
     L.mg_launch_count.argtypes = [_vp]
     L.mg_launch_count.restype = C.c_int64
+    L.mg_last_kernel.argtypes = [_vp]
+    L.mg_last_kernel.restype = C.c_char_p
     if L.mg_abi_version() != MG_ABI_VERSION:
         raise EngineError(f"ABI mismatch: library {L.mg_abi_version()} vs binding {MG_ABI_VERSION}")
     for which, struct in enumerate((MgConfig, MgPriorityList, MgGroup, MgLayout, MgStepIO, MgRolloutIO, MgForecastNoise,
@@ -141,7 +144,7 @@ def lib():
 
 EXPORTED_SYMBOLS = ("mg_abi_version", "mg_sizeof", "mg_build_info", "mg_last_error", "mg_create", "mg_destroy",
                     "mg_step", "mg_step_discrete", "mg_reset", "mg_observe", "mg_rollout", "mg_rollout_discrete",
-                    "mg_rollout_host", "mg_launch_count", "mg_set_option", "mg_forecast_noise", "mg_set_reported_soc")
+                    "mg_rollout_host", "mg_launch_count", "mg_last_kernel", "mg_set_option", "mg_forecast_noise", "mg_set_reported_soc")
 
 
 def check(code, what):

@@ -106,6 +106,20 @@ __device__ __forceinline__ void st_global_v2(float *p, double a, double b) {
     asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(__double2float_rn(a)), "f"(__double2float_rn(b)) : "memory");
 }
 
+// Role timers (debug builds, -DMG_ROLE_TIMERS): where the warps of the persistent image kernels spend their cycles.
+//   [0] owners: inputs + physics + publish   [1] owners: waiting for EMPTY   [2] emitters: waiting for FULL
+//   [3] emitters: waiting for an image buffer (bulk_wait_read)   [4] emitters: gather + scatter + fence + issue   [5] warp-steps counted
+#ifdef MG_ROLE_TIMERS
+__device__ unsigned long long mg_role_cycles[8];
+#define MG_T0() const long long t0_ = clock64()
+#define MG_TACC(var) do { const long long t1_ = clock64(); var += t1_ - t0_; } while (0)
+extern "C" int mg_debug_role_cycles(unsigned long long *out, int reset) {
+    cudaMemcpyFromSymbol(out, mg_role_cycles, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(mg_role_cycles, z, sizeof z); }
+    return 0;
+}
+#endif
+
 // ---- TMA (cp.async.bulk, SASS UBLKCP) and mbarrier wrappers -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -155,6 +169,15 @@ __device__ __forceinline__ void add_reward_total(double *total, double reward, b
 // programmatic dependent launch (PDL): wait for the preceding grid's trigger / let the following grid start
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// IEEE f64 division with the zero numerator peeled off.  CUDA's div.rn.f64 sends a zero (or denormal) numerator to an
+// out-of-line slow path of ~100 instructions, and zero numerators are the common case here (no discharge, no sun at
+// night, an empty battery): measured, the slow path was 13% of all instructions of the per-env-series rollout kernel.
+// +-0 / den = +-0 (the numerator itself) for every den > 0, so the shortcut is bit-exact; anything else divides.
+__device__ __forceinline__ double div_f64(double num, double den) {
+    if (num == 0.0 && den > 0.0) return num;
+    return num / den;
+}
 
 __device__ __forceinline__ bool np_isclose(double a, double b, double rtol, double atol) {
     return fabs(a - b) <= (atol + rtol * fabs(b));
@@ -251,7 +274,7 @@ __device__ __forceinline__ uint32_t priority_control(const MgPriorityList pl, co
             if (mod == MG_MOD_GENSET) energy = 0.0;
             else {
                 const double mc = (mod == MG_MOD_BATTERY)
-                                      ? fmin(c->bat_max_charge, c->bat_max_capacity - s.charge) / c->bat_efficiency
+                                      ? div_f64(fmin(c->bat_max_charge, c->bat_max_capacity - s.charge), c->bat_efficiency)
                                       : c->grid_max_export * raw.status;
                 if (!(mc >= 0)) flags |= MG_FLAG_NEGATIVE_ABSORB;
                 if (-1 * remaining > mc) energy = -1.0 * mc;
@@ -320,13 +343,13 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
             double p;
             if (a > mp) { p = mp; flags |= MG_FLAG_CLIP_BATTERY; }
             else p = a;
-            internal = (-1.0 * p) / c->bat_efficiency;
+            internal = div_f64(-1.0 * p, c->bat_efficiency);
             provided += p;
             i_dis = p;
         } else {
             flags |= MG_FLAG_BATTERY_SINK;
             double e = -1.0 * a;
-            const double mc = fmin(c->bat_max_charge, c->bat_max_capacity - s.charge) / c->bat_efficiency;
+            const double mc = div_f64(fmin(c->bat_max_charge, c->bat_max_capacity - s.charge), c->bat_efficiency);
             if (e > mc) { e = mc; flags |= MG_FLAG_CLIP_BATTERY; }
             if (!(e >= 0)) flags |= MG_FLAG_NEGATIVE_ABSORB;
             internal = e * c->bat_efficiency;
@@ -480,17 +503,17 @@ __device__ __forceinline__ void publish_env(TileEnv &te, HeteroEnv *het, const M
         het->scaled = c->series_scaled; het->weak = c->grid_status_weak;
     }
     // battery_module.py:323-330, genset_module.py:503-509, utils/space.py:207-218
-    const double soc = s.charge / c->bat_max_capacity;
-    const double b0 = (soc - c->bat_soc_low) / c->bat_soc_spread;
-    const double b1 = (s.charge - c->bat_min_capacity) / c->bat_charge_spread;
+    const double soc = div_f64(s.charge, c->bat_max_capacity);
+    const double b0 = div_f64(soc - c->bat_soc_low, c->bat_soc_spread);
+    const double b1 = div_f64(s.charge - c->bat_min_capacity, c->bat_charge_spread);
     if (!G.has_genset) {
         te.state[0] = b0; te.state[1] = b1;
         return;
     }
     const double g0 = ((double)s.cs - 0.0) / 1.0;
     const double g1 = ((double)s.gs - 0.0) / 1.0;
-    const double g2 = ((double)s.up - 0.0) / c->gen_up_spread;
-    const double g3 = ((double)s.dn - 0.0) / c->gen_down_spread;
+    const double g2 = div_f64((double)s.up - 0.0, c->gen_up_spread);
+    const double g3 = div_f64((double)s.dn - 0.0, c->gen_down_spread);
     if (G.state_genset_first) {   // container order: genset, battery
         te.state[0] = g0; te.state[1] = g1; te.state[2] = g2; te.state[3] = g3; te.state[4] = b0; te.state[5] = b1;
     } else {                      // gym order: battery, genset
@@ -563,14 +586,53 @@ __device__ __forceinline__ void series_obs_value(const LaunchParams &P, const Mg
         const bool in = idx < P.T;
         const double rp = in ? __ldg(P.pv_raw + (size_t)c->pv_series * P.T + idx) : 0.0;
         const double rl = in ? __ldg(P.load_raw + (size_t)c->load_series * P.T + idx) : 0.0;
-        const double np_ = (rp * c->pv_scale - c->pv_low) / c->pv_spread;
-        const double nl = (rl * c->load_scale - c->load_low) / c->load_spread;
+        const double np_ = div_f64(rp * c->pv_scale - c->pv_low, c->pv_spread);
+        const double nl = div_f64(rl * c->load_scale - c->load_low, c->load_spread);
         pv = in ? np_ : c->pv_fill_nrm;
         ld = in ? nl : c->load_fill_nrm;
     } else {
         pv = __ldg(P.pv_nrm + (size_t)c->pv_series * P.Tp + idx);
         ld = __ldg(P.load_nrm + (size_t)c->load_series * P.Tp + idx);
     }
+}
+
+// series_obs_value in two halves, so that a caller can issue the loads long before it needs the values
+struct SeriesRaw {
+    double a, b;      // scaled series: raw pv / load profile values; table-backed: the normalised pv / load values
+    bool in;
+};
+__device__ __forceinline__ SeriesRaw series_obs_fetch(const LaunchParams &P, const MgConfig *__restrict__ c, int idx) {
+    SeriesRaw r;
+    if (c->series_scaled) {
+        r.in = idx < P.T;
+        r.a = r.in ? __ldg(P.pv_raw + (size_t)c->pv_series * P.T + idx) : 0.0;
+        r.b = r.in ? __ldg(P.load_raw + (size_t)c->load_series * P.T + idx) : 0.0;
+    } else {
+        r.in = true;
+        r.a = __ldg(P.pv_nrm + (size_t)c->pv_series * P.Tp + idx);
+        r.b = __ldg(P.load_nrm + (size_t)c->load_series * P.Tp + idx);
+    }
+    return r;
+}
+__device__ __forceinline__ void series_obs_finish(const MgConfig *__restrict__ c, const SeriesRaw &r, double &ld, double &pv) {
+    if (c->series_scaled) {
+        const double np_ = div_f64(r.a * c->pv_scale - c->pv_low, c->pv_spread);
+        const double nl = div_f64(r.b * c->load_scale - c->load_low, c->load_spread);
+        pv = r.in ? np_ : c->pv_fill_nrm;
+        ld = r.in ? nl : c->load_fill_nrm;
+    } else {
+        pv = r.a;
+        ld = r.b;
+    }
+}
+// status_window in two halves
+__device__ __forceinline__ uint2 status_words_fetch(const DevGroup &G, int e, int t_obs) {
+    const uint32_t *bits = G.status_bits + (size_t)e * G.status_words;
+    const int i = t_obs >> 5;
+    uint2 w;
+    w.x = __ldg(bits + i);
+    w.y = (i + 1 < G.status_words) ? __ldg(bits + i + 1) : 0u;
+    return w;
 }
 
 // the 32 grid-status bits of env e starting at step t_obs (bit k = status at t_obs + k)
@@ -672,8 +734,8 @@ __device__ __forceinline__ void emit_row_hetero(const LaunchParams &P, const Dev
             const bool in = idx < P.T;
             const double rp = in ? __ldg(P.pv_raw + hv.pv_base + idx) : 0.0;
             const double rl = in ? __ldg(P.load_raw + hv.load_base + idx) : 0.0;
-            const double np_ = (rp * hv.pv_scale - hv.pv_low) / hv.pv_spread;
-            const double nl = (rl * hv.load_scale - hv.load_low) / hv.load_spread;
+            const double np_ = div_f64(rp * hv.pv_scale - hv.pv_low, hv.pv_spread);
+            const double nl = div_f64(rl * hv.load_scale - hv.load_low, hv.load_spread);
             pv = in ? np_ : hv.pv_fill;
             ld = in ? nl : hv.load_fill;
         } else {
@@ -919,30 +981,47 @@ struct ImgRow {     // what one lane holds of one row between the gather and the
     double2 g0, g1;
     double pv, load, state;
 };
+struct ImgShared {  // the parts of the previous row that following rows of the same run reuse (table values, unpatched)
+    double2 g0, g1;
+    double pv, load;
+};
 
-// gather this lane's share of row r (tile record at shared address env_a + 64 r): every load is unconditional (clamped
-// addresses) and nothing diverges between lanes
+// Gather this lane's share of row r (tile record at shared address env_a + 64 r).  Every load is unconditional (clamped
+// addresses) and nothing diverges between lanes; need_grid / need_win are warp-uniform: false where the row's grid window /
+// load + pv windows equal the previous row's (same table offsets), which `sh` still holds -- the whole tile in lock-step.
 template <bool kHetero, bool kRing>
 __device__ __forceinline__ ImgRow img_gather(const LaunchParams &P, const DevGroup &G, const ImgCtx &x, uint32_t env_a,
-                                             const HeteroEnv *__restrict__ het, uint32_t ring_a, int r, int e_base) {
+                                             const HeteroEnv *__restrict__ het, uint32_t ring_a, int r, int e_base, bool need_grid,
+                                             bool need_win, ImgShared &sh) {
     static_assert(sizeof(TileEnv) == 64, "the emitter addresses tile records by hand");
     ImgRow v;
     const uint32_t rec = env_a + 64u * (uint32_t)r;
-    const int4 hd = lds_v4s32(rec);      // off_grid, off_load, off_pv, special
+    int4 hd = make_int4(0, 0, 0, -1);
+    if (kHetero || need_grid || need_win) hd = lds_v4s32(rec);      // off_grid, off_load, off_pv, special
     const int off_grid = hd.x, off_load = hd.y, off_pv = hd.z, special = kHetero ? hd.w : -1;
     if (x.has_grid) {   // group-uniform
-        v.g0 = __ldg(x.g0_src + (off_grid >> 1));
-        v.g1 = __ldg(x.g1_src + (off_grid >> 1));
+        if (need_grid) {
+            sh.g0 = __ldg(x.g0_src + (off_grid >> 1));
+            sh.g1 = __ldg(x.g1_src + (off_grid >> 1));
+        }
+        v.g0 = sh.g0;
+        v.g1 = sh.g1;
         if (kHetero && x.own_status && special >= 0) {   // warp-uniform
-            // bounds of the status column: (0, 1) on a weak grid, (1, 1) -> spread 1 otherwise (utils/space.py:204-205)
+            // The env's own status column.  Bounds (0, 1) on a weak grid, (1, 1) -> spread 1 otherwise (utils/space.py:204-205):
+            // a grid without outages reports 0.0, which is what the shared table holds, so only weak grids patch.
             uint32_t w;
             bool weak;
             if (kRing) { w = (uint32_t)off_load; weak = (off_pv >> 16) != 0; }
-            else { w = status_window(G, e_base + r, special); weak = het[r].weak != 0; }
-            const double s0 = weak ? (special + x.k0 < x.T ? (double)((w >> x.k0) & 1u) : 0.5) : 0.0;
-            const double s1 = weak ? (special + x.k1 < x.T ? (double)((w >> (x.k1 & 31)) & 1u) : 0.5) : 0.0;
-            v.g0.y = x.patch_lane ? s0 : v.g0.y;
-            v.g1.y = x.patch_lane ? s1 : v.g1.y;
+            else { weak = het[r].weak != 0; w = weak ? status_window(G, e_base + r, special) : 0u; }
+            if (weak) {
+                double s0 = (double)((w >> x.k0) & 1u), s1 = (double)((w >> (x.k1 & 31)) & 1u);
+                if (special + 32 > x.T) {   // the window runs past the end of the series: the forecaster's fill
+                    s0 = special + x.k0 < x.T ? s0 : 0.5;
+                    s1 = special + x.k1 < x.T ? s1 : 0.5;
+                }
+                v.g0.y = x.patch_lane ? s0 : v.g0.y;
+                v.g1.y = x.patch_lane ? s1 : v.g1.y;
+            }
         }
     } else {
         v.g0 = v.g1 = make_double2(0.0, 0.0);
@@ -960,13 +1039,17 @@ __device__ __forceinline__ ImgRow img_gather(const LaunchParams &P, const DevGro
         const bool in = idx < x.T;
         const double rp = in ? __ldg(P.pv_raw + hv.pv_base + idx) : 0.0;
         const double rl = in ? __ldg(P.load_raw + hv.load_base + idx) : 0.0;
-        const double np_ = (rp * hv.pv_scale - hv.pv_low) / hv.pv_spread;
-        const double nl = (rl * hv.load_scale - hv.load_low) / hv.load_spread;
+        const double np_ = div_f64(rp * hv.pv_scale - hv.pv_low, hv.pv_spread);
+        const double nl = div_f64(rl * hv.load_scale - hv.load_low, hv.load_spread);
         v.pv = in ? np_ : hv.pv_fill;
         v.load = in ? nl : hv.load_fill;
     } else {
-        v.pv = __ldg(x.pv_src + off_pv);
-        v.load = __ldg(x.load_src + off_load);
+        if (need_win) {
+            sh.pv = __ldg(x.pv_src + off_pv);
+            sh.load = __ldg(x.load_src + off_load);
+        }
+        v.pv = sh.pv;
+        v.load = sh.load;
     }
     v.state = lds_f64(rec + x.s_state);
     return v;
@@ -982,7 +1065,8 @@ __device__ __forceinline__ void img_scatter(const ImgCtx &x, uint32_t row_a, con
 }
 
 // env_a / ring_a / img_a: shared-memory addresses of the tile records of this step, of the RingShared block and of the
-// calling warp's NB image buffers (warp-uniform values, so that the bulk store's operands stay in uniform registers)
+// calling warp's NB image buffers (warp-uniform values, so that the bulk store's operands stay in uniform registers).
+// r_count <= 32 rows per call.
 template <int RC, int NB, int GB, bool kHetero, bool kRing>
 __device__ __forceinline__ void warp_emit_rows_img(const LaunchParams &P, const DevGroup &G, const ImgCtx &x, uint32_t env_a,
                                                    const HeteroEnv *__restrict__ het, uint32_t ring_a, uint32_t img_a, int &buf,
@@ -990,11 +1074,35 @@ __device__ __forceinline__ void warp_emit_rows_img(const LaunchParams &P, const 
     const int lane = threadIdx.x & 31;
     const int r_end = min(r_begin + r_count, n_rows);
     const uint32_t buf_bytes = (uint32_t)(RC * x.row_bytes);
+    // Per-env series batches: run boundaries of this call's rows in two votes -- bit i set <=> row r_begin + i has a grid
+    // window / load + pv windows of its own (different table offsets than the row before it, or per-env windows); the other
+    // rows reuse `sh` (envs are laid out by grid table, so most rows of a tile continue the previous row's grid window).
+    // Table-backed batches come here when their envs are at unrelated steps (in lock-step the run emitters of
+    // warp_emit_rows_t are the faster ones): every row gathers its own windows, with no run bookkeeping in the way.
+    uint32_t new_grid = 0xffffffffu, new_win = 0xffffffffu;
+    if (kHetero) {
+        const int rr = min(r_begin + lane, max(r_end - 1, r_begin));
+        const int4 me = lds_v4s32(env_a + 64u * (uint32_t)rr);
+        const int4 pr = lds_v4s32(env_a + 64u * (uint32_t)max(rr - 1, r_begin));
+        const bool first = lane == 0;
+        new_grid = __ballot_sync(0xffffffffu, first || me.x != pr.x);
+        new_win = __ballot_sync(0xffffffffu, first || me.y != pr.y || me.z != pr.z || me.w >= 0 || pr.w >= 0);
+    }
+    ImgShared sh;
+    sh.g0 = sh.g1 = make_double2(0.0, 0.0);
+    sh.pv = sh.load = 0.0;
 #pragma unroll 1
     for (int r = r_begin; r < r_end; r += RC) {
         const uint32_t im = img_a + (uint32_t)buf * buf_bytes;
+        const uint32_t ng = kHetero ? new_grid >> (r - r_begin) : 0xffffffffu, nw = kHetero ? new_win >> (r - r_begin) : 0xffffffffu;
+#ifdef MG_ROLE_TIMERS
+        const long long tw0 = clock64();
+#endif
         if (lane == 0) bulk_wait_read<NB - 1>();    // the bulk store that last read this buffer is done with it
         __syncwarp();
+#ifdef MG_ROLE_TIMERS
+        if (lane == 0) atomicAdd(&mg_role_cycles[3], (unsigned long long)(clock64() - tw0));
+#endif
         int n = RC;
         if (r + RC <= r_end) {                      // full chunk, GB rows at a time: their gathers are all in flight before the first image store
             static_assert(RC % GB == 0, "gather batches tile the chunk");
@@ -1002,7 +1110,8 @@ __device__ __forceinline__ void warp_emit_rows_img(const LaunchParams &P, const 
             for (int b = 0; b < RC; b += GB) {
                 ImgRow v[GB];
 #pragma unroll
-                for (int q = 0; q < GB; ++q) v[q] = img_gather<kHetero, kRing>(P, G, x, env_a, het, ring_a, r + b + q, e_base);
+                for (int q = 0; q < GB; ++q)
+                    v[q] = img_gather<kHetero, kRing>(P, G, x, env_a, het, ring_a, r + b + q, e_base, (ng >> (b + q)) & 1u, (nw >> (b + q)) & 1u, sh);
 #pragma unroll
                 for (int q = 0; q < GB; ++q) img_scatter(x, im + (uint32_t)((b + q) * x.row_bytes), v[q]);
             }
@@ -1010,7 +1119,8 @@ __device__ __forceinline__ void warp_emit_rows_img(const LaunchParams &P, const 
             n = r_end - r;
 #pragma unroll 1
             for (int q = 0; q < n; ++q)
-                img_scatter(x, im + (uint32_t)(q * x.row_bytes), img_gather<kHetero, kRing>(P, G, x, env_a, het, ring_a, r + q, e_base));
+                img_scatter(x, im + (uint32_t)(q * x.row_bytes),
+                            img_gather<kHetero, kRing>(P, G, x, env_a, het, ring_a, r + q, e_base, (ng >> q) & 1u, (nw >> q) & 1u, sh));
         }
         fence_proxy_async();
         __syncwarp();
@@ -1388,6 +1498,7 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
         for (int step = 0; step < P.n_steps; ++step) {
             const int ebuf = step & 1;
             double my_reward = 0.0;
+            int my_done = 0;
             StepInputs in;
             in.valid = false;
             if (owner) in = fetch_inputs<kHetero>(P, G, c, e, step, s.t);
@@ -1397,15 +1508,21 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
                 int done;
                 uint32_t flags;
                 owner_step(P, G, c, s, in, final_step, nullptr, reward, done, flags);
-                G.reward[(size_t)step * G.out_step_stride + e] = reward;
-                G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)done;
                 rsum += reward;
                 fsum |= flags;
                 my_reward = reward;
+                my_done = done;
                 publish_env<kHetero>(S.env[ebuf][tid], kHetero ? HeteroStorage<kHetero>::rows(SH, ebuf) + tid : nullptr, c, G, s, P.T, P.Tp);
             }
-            __threadfence_block();   // the tile record is visible before the emitters are released
+            // Hand the tile record over: when the barrier completes, this thread's prior shared-memory writes are performed
+            // for the threads that sync on it (PTX barrier semantics), so no fence.  The step's global results are stored
+            // AFTER the hand-over: a fence or barrier between them and the arrive would wait for their acknowledgement, which
+            // takes microseconds while the observation stream saturates the memory system (it set the pace of the kernel).
             named_bar_arrive(BAR_FULL0, ebuf);
+            if (owner) {
+                G.reward[(size_t)step * G.out_step_stride + e] = my_reward;
+                G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)my_done;
+            }
             if (G.reward_total) add_reward_total(G.reward_total + step, my_reward, owner);
         }
         if (owner) {
@@ -1426,7 +1543,8 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
 #pragma unroll 1
             for (int q = 0; q < 2; ++q)
                 warp_emit_rows<kHetero, TO>(P, G, S, het, ebuf, obs_tile, n_rows, e0, phase, 32 * half + MG_ROWS_PER_WARP * q);
-            __threadfence_block();   // every read of env[ebuf] / het[ebuf] has completed before the owners may overwrite them
+            // (every read of env[ebuf] / het[ebuf] has returned: the stores that carry the values were issued; no fence, which
+            //  would wait for those stores to be acknowledged)
             named_bar_arrive(BAR_EMPTY0, ebuf);
         }
     }
@@ -1444,6 +1562,9 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
 #define MG_IMG_MIN_CTAS 3
 #endif
 extern __shared__ __align__(128) unsigned char mg_dyn_smem[];
+#define MG_MAX_SMS 256
+__device__ uint32_t mg_sm_cta_count[MG_MAX_SMS];   // CTAs of the role-split kernels seen by each SM so far (only the parity is used)
+
 
 struct ImgTileShared {
     TileEnv env[2][MG_TILE];   // double buffered across steps
@@ -1527,10 +1648,21 @@ __global__ void __launch_bounds__(MG_THREADS, !kWS ? MG_IMG_MIN_CTAS : !kHetero 
     const DevGroup &G = P.g[gi];
     const int e0 = (blockIdx.x - G.tile_begin) * MG_TILE;
     const int n_rows = min(MG_TILE, G.n_envs - e0);
-    // Role-relative thread id: owners are rtid < 64.  With the role split, odd CTAs give the owner role to warps 2-3: a warp's
-    // scheduler is its index mod 4, so without the flip every emitting warp of the SM would sit on the same two of the four
-    // schedulers (measured: those two saturate at ~85 issue slots per row while the other two idle).
-    const int tid = kWS ? (int)(threadIdx.x ^ ((blockIdx.x & 1u) << 6)) : (int)threadIdx.x;
+    // Role-relative thread id: owners are tid < 64.  With the role split, every other CTA of an SM gives the owner role to
+    // warps 2-3: a warp's scheduler is its index mod 4, so without the flip every emitting warp of the SM would sit on the same
+    // two of the four schedulers.
+    // (The CTAs of one SM are counted through a per-SM counter: block indices alone do not alternate on an SM -- the
+    //  hardware deals consecutive indices to consecutive SMs, and the SM count is even.)
+    __shared__ uint32_t role_flip;
+    if (kWS) {
+        if (threadIdx.x == 0) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            role_flip = atomicAdd(&mg_sm_cta_count[smid & (MG_MAX_SMS - 1)], 1u) & 1u;
+        }
+        __syncthreads();
+    }
+    const int tid = kWS ? (int)(threadIdx.x ^ (role_flip << 6)) : (int)threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (provably warp-uniform: bulk-store operands in uniform registers)
     const ImgCtx x = img_ctx(P, G);
     const uint32_t ring_a = kRing ? smem_u32(rings) : 0u;
@@ -1556,7 +1688,18 @@ __global__ void __launch_bounds__(MG_THREADS, !kWS ? MG_IMG_MIN_CTAS : !kHetero 
     if (!kWS || tid < MG_TILE) {   // ---------------- owners (and, without the role split, emitters too) ----------------
         const bool owner = tid < n_rows;
         const int e = e0 + tid;
-        const MgConfig *__restrict__ c = P.cfg;
+        // Per-env parameter records (one MgConfig per env: MicrogridGenerator grids) are copied out of the 336-byte-stride
+        // array once, into a per-thread copy that the compiler keeps in registers (or, where they run out, in this thread's
+        // local memory: coalesced across the warp, L1 resident) -- instead of 32 different cache lines per field and warp
+        // from L2, every step.  Table-backed batches share a few records per tile and read them through L1.
+        MgConfig cl;
+        const MgConfig *__restrict__ const c = kHetero ? &cl : P.cfg + (owner ? __ldg(G.cfg_index + e) : 0);
+        if (kHetero) {
+            const double2 *__restrict__ src = reinterpret_cast<const double2 *>(P.cfg + (owner ? __ldg(G.cfg_index + e) : 0));
+            double2 *dst = reinterpret_cast<double2 *>(&cl);
+#pragma unroll
+            for (int q = 0; q < (int)(sizeof(MgConfig) / sizeof(double2)); ++q) dst[q] = __ldg(src + q);
+        }
         EnvRegs s;
         s.t = 0; s.charge = 0.0; s.cs = s.gs = s.up = s.dn = 0;
         int final_step = 0, ring_base = 0, buf = 0;
@@ -1564,7 +1707,6 @@ __global__ void __launch_bounds__(MG_THREADS, !kWS ? MG_IMG_MIN_CTAS : !kHetero 
         double rsum = 0.0;
         uint32_t fsum = 0;
         if (owner) {
-            c = P.cfg + __ldg(G.cfg_index + e);
             s.t = G.step[e];
             s.charge = G.charge[e];
             if (G.has_genset) unpack_genset(G.genset[e], s);
@@ -1575,42 +1717,90 @@ __global__ void __launch_bounds__(MG_THREADS, !kWS ? MG_IMG_MIN_CTAS : !kHetero 
             }
         }
         const uint32_t img_a = smem_u32(mg_dyn_smem) + (uint32_t)(warp * NB * RC * x.row_bytes);   // (not used by owners of the split)
+#ifdef MG_ROLE_TIMERS
+        long long tm_phys = 0, tm_empty = 0;
+#endif
+        // The inputs of a step depend only on its index and on the env's step counter, which moves by one per valid step:
+        // they are requested one step ahead (at the top of step s for step s + 1), so that their memory latency -- several
+        // dependent trips to L2 / HBM that take microseconds while the stores saturate the memory system -- overlaps the
+        // physics of step s.  A counter that did not move as predicted (rejected discrete action) re-fetches.
+        StepInputs in_next;
+        in_next.valid = false;
+        if (kHetero && owner) in_next = fetch_inputs<kHetero>(P, G, c, e, 0, s.t);
         for (int step = 0; step < P.n_steps; ++step) {
             const int ebuf = step & 1;
             double my_reward = 0.0;
-            StepInputs in;
-            in.valid = false;
-            if (owner) in = fetch_inputs<kHetero>(P, G, c, e, step, s.t);
+            int my_done = 0;
+            // (table-backed batches run under a 72-register budget -- 7 CTAs per SM keep all 1 024 tiles of the 65 536-env
+            //  batch resident -- where holding a second set of inputs spills: they fetch at the top of the step)
+            if (!kHetero && owner) in_next = fetch_inputs<kHetero>(P, G, c, e, step, s.t);
+            const StepInputs in = in_next;
+#ifdef MG_ROLE_TIMERS
+            const long long tp0 = clock64();
+#endif
+            const int t_pred = s.t + (in.valid ? 1 : 0);
+            SeriesRaw ring_raw;
+            uint2 status_w = make_uint2(0u, 0u);
+            ring_raw.a = ring_raw.b = 0.0; ring_raw.in = false;
+            if (owner) {
+                if (kHetero && step + 1 < P.n_steps) in_next = fetch_inputs<kHetero>(P, G, c, e, step + 1, t_pred);
+                if (kRing && ring_env) {    // this step's ring append and status window, requested before the physics
+                    if (in.valid) ring_raw = series_obs_fetch(P, c, t_pred + G.horizon);
+                    if (G.has_grid && G.status_bits) status_w = status_words_fetch(G, e, min(t_pred, P.T));
+                }
+            }
+#ifdef MG_ROLE_TIMERS
+            const long long te0 = clock64();
+#endif
             if (kWS && step >= 2) named_bar_sync(BAR_EMPTY0, ebuf);   // the emitters are done with env[ebuf] of step - 2
+#ifdef MG_ROLE_TIMERS
+            const long long te1 = clock64();
+            tm_empty += te1 - te0;
+#endif
             if (owner) {
                 double reward;
                 int done;
                 uint32_t flags;
                 owner_step(P, G, c, s, in, final_step, nullptr, reward, done, flags);
-                G.reward[(size_t)step * G.out_step_stride + e] = reward;
-                G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)done;
                 rsum += reward;
                 fsum |= flags;
                 my_reward = reward;
+                my_done = done;
+                if (kHetero && s.t != t_pred && step + 1 < P.n_steps) in_next = fetch_inputs<kHetero>(P, G, c, e, step + 1, s.t);
                 publish_env<kHetero>(S.env[ebuf][tid], (kHetero && !kRing) ? HeteroStorage<kHetero && !kRing>::rows(SH, ebuf) + tid : nullptr, c, G, s, P.T, P.Tp);
                 if (kRing && ring_env) {
                     if (in.valid) {   // the step counter moved from t to t + 1 <= T: the window gains index t + 1 + H
                         ring_base = ring_base + 1 == ring_R ? 0 : ring_base + 1;
                         double ld, pv;
-                        series_obs_value(P, c, s.t + G.horizon, ld, pv);
+                        series_obs_finish(c, ring_raw, ld, pv);
                         int slot = ring_base + G.horizon;
                         if (slot >= ring_R) slot -= ring_R;
                         rings->win[0][tid][slot] = ld;
                         rings->win[1][tid][slot] = pv;
                     }
-                    publish_ring(S.env[ebuf][tid], c, G, e, ring_base);
+                    // TileEnv of a ring row: see publish_ring (the status window word comes from the words requested above)
+                    TileEnv &te = S.env[ebuf][tid];
+                    te.off_load = (G.has_grid && G.status_bits) ? (int32_t)__funnelshift_r(status_w.x, status_w.y, te.special & 31) : 0;
+                    te.off_pv = ring_base | (c->grid_status_weak ? (1 << 16) : 0);
                 }
             }
-            if (G.reward_total && tid < MG_TILE) add_reward_total(G.reward_total + step, my_reward, owner);
+#ifdef MG_ROLE_TIMERS
+            tm_phys += (clock64() - tp0) - (te1 - te0);
+#endif
             if (kWS) {
-                __threadfence_block();   // the tile record is visible before the emitters are released
+                // hand-over first, global results after it (see mg_rollout_ws_kernel)
                 named_bar_arrive(BAR_FULL0, ebuf);
+                if (owner) {
+                    G.reward[(size_t)step * G.out_step_stride + e] = my_reward;
+                    G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)my_done;
+                }
+                if (G.reward_total && tid < MG_TILE) add_reward_total(G.reward_total + step, my_reward, owner);
             } else {
+                if (owner) {
+                    G.reward[(size_t)step * G.out_step_stride + e] = my_reward;
+                    G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)my_done;
+                }
+                if (G.reward_total && tid < MG_TILE) add_reward_total(G.reward_total + step, my_reward, owner);
                 // one barrier per step: the records of step s live in env[s & 1]; a warp can only reach the barrier of
                 // step s+1 after it has finished reading env[s & 1], so the owners may overwrite it at step s+2
                 __syncthreads();
@@ -1628,20 +1818,46 @@ __global__ void __launch_bounds__(MG_THREADS, !kWS ? MG_IMG_MIN_CTAS : !kHetero 
             if (G.flags) G.flags[e] = fsum;
         }
         if (!kWS && (tid & 31) == 0) bulk_wait_read<0>();   // shared memory must outlive the last bulk stores' reads
+#ifdef MG_ROLE_TIMERS
+        if (kWS && (tid & 31) == 0) {
+            atomicAdd(&mg_role_cycles[0], (unsigned long long)tm_phys);
+            atomicAdd(&mg_role_cycles[1], (unsigned long long)tm_empty);
+            atomicAdd(&mg_role_cycles[5], (unsigned long long)P.n_steps);
+        }
+#endif
     } else {               // ---------------- emitters (kWS) ----------------
         const int half = warp - 2;   // 0 or 1: rows [32 half, 32 half + 32)
         const uint32_t img_a = smem_u32(mg_dyn_smem) + (uint32_t)(half * NB * RC * x.row_bytes);
         int buf = 0;
+#ifdef MG_ROLE_TIMERS
+        long long tm_full = 0, tm_emit = 0;
+#endif
         for (int step = 0; step < P.n_steps; ++step) {
             const int ebuf = step & 1;
+#ifdef MG_ROLE_TIMERS
+            const long long tf0 = clock64();
+#endif
             named_bar_sync(BAR_FULL0, ebuf);
+#ifdef MG_ROLE_TIMERS
+            const long long tf1 = clock64();
+            tm_full += tf1 - tf0;
+#endif
             double *obs_tile = G.obs + (size_t)(step % P.ring) * G.obs_slot_stride + (size_t)e0 * G.obs_dim;
             warp_emit_rows_img<RC, NB, GB, kHetero, kRing>(P, G, x, smem_u32(S.env[ebuf]), HeteroStorage<kHetero && !kRing>::rows(SH, ebuf), ring_a, img_a,
                                                          buf, obs_tile, n_rows, 32 * half, 32, e0);
             if (P.ring == 1 && (tid & 31) == 0) bulk_wait_all();
-            __threadfence_block();   // every read of env[ebuf] / het[ebuf] has completed before the owners may overwrite them
+            // (every read of env[ebuf] / het[ebuf] / the rings has returned: the values are in the images)
+#ifdef MG_ROLE_TIMERS
+            tm_emit += clock64() - tf1;
+#endif
             named_bar_arrive(BAR_EMPTY0, ebuf);
         }
+#ifdef MG_ROLE_TIMERS
+        if ((tid & 31) == 0) {
+            atomicAdd(&mg_role_cycles[2], (unsigned long long)tm_full);
+            atomicAdd(&mg_role_cycles[4], (unsigned long long)tm_emit);
+        }
+#endif
         if ((tid & 31) == 0) bulk_wait_read<0>();
     }
 }
@@ -1811,7 +2027,10 @@ struct MgHandle {
     bool obs_f32;           // observation buffers are float32 (MG_LAYOUT_OBS_F32)
     bool rollout_specialised;   // MG_OPT_ROLLOUT_SPECIALISED
     bool rollout_ring;          // MG_OPT_ROLLOUT_RING
-    int emit_image;             // MG_OPT_EMIT_IMAGE: 0 LSU row emitters, 1 image + TMA bulk stores (default)
+    int emit_image;             // MG_OPT_EMIT_IMAGE: 0 LSU row emitters, 1 image + TMA bulk stores, 2 choose per launch (default)
+    bool ragged_hint;           // MG_OPT_RAGGED_HINT: the envs of a tile are (probably) at unrelated steps
+    int n_sms;                  // multiprocessors of the device the handle was created on
+    const char *last_kernel;    // mg_last_kernel
     int image_shape;            // MG_OPT_IMAGE_SHAPE: index into the instantiated (rows per bulk store, buffers) shapes
     struct HostStage *stage;    // mg_rollout_host: streams, events and device staging (lazy)
     const double *soc_reported[MG_MAX_GROUPS];   // mg_set_reported_soc; dropped by the first step / rollout
@@ -1938,8 +2157,15 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
     h->obs_f32 = (L->flags & MG_LAYOUT_OBS_F32) != 0;
     h->rollout_specialised = true;
     h->rollout_ring = true;
-    h->emit_image = 1;
-    h->image_shape = 0;
+    h->emit_image = 2;
+    h->image_shape = -1;
+    h->ragged_hint = false;
+    h->last_kernel = "";
+    h->n_sms = 148;
+    {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) h->n_sms = n;
+    }
     h->stage = nullptr;
     h->last_stream = nullptr;
     for (int g = 0; g < MG_MAX_GROUPS; ++g) h->last_obs[g] = nullptr;
@@ -2008,6 +2234,7 @@ extern "C" int mg_destroy(MgHandle *h) {
 }
 
 extern "C" int64_t mg_launch_count(const MgHandle *h) { return h ? h->launches : 0; }
+extern "C" const char *mg_last_kernel(const MgHandle *h) { return h ? h->last_kernel : ""; }
 
 extern "C" int mg_set_reported_soc(MgHandle *h, const double *const *soc) {
     if (!h) return fail(MG_E_INVALID, "mg_set_reported_soc: null handle");
@@ -2067,12 +2294,17 @@ extern "C" int mg_set_option(MgHandle *h, int option, int value) {
         return MG_OK;
     }
     if (option == MG_OPT_EMIT_IMAGE) {
-        h->emit_image = value != 0;
+        if (value < 0 || value > 2) return fail(MG_E_INVALID, "mg_set_option: MG_OPT_EMIT_IMAGE takes 0, 1 or 2");
+        h->emit_image = value;
         return MG_OK;
     }
     if (option == MG_OPT_IMAGE_SHAPE) {
-        if (value < 0 || value >= MG_N_IMAGE_SHAPES) return fail(MG_E_INVALID, "mg_set_option: image shape out of range");
+        if (value < -1 || value >= MG_N_IMAGE_SHAPES) return fail(MG_E_INVALID, "mg_set_option: image shape out of range");
         h->image_shape = value;
+        return MG_OK;
+    }
+    if (option == MG_OPT_RAGGED_HINT) {
+        h->ragged_hint = value != 0;
         return MG_OK;
     }
     return fail(MG_E_INVALID, "mg_set_option: unknown option");
@@ -2135,6 +2367,35 @@ static int ensure_dynamic_smem(const void *func, size_t bytes) {
     return MG_OK;
 }
 
+// Which emitters a launch uses when the caller left the choice to the library (MG_OPT_EMIT_IMAGE = 2), from what was
+// measured on B200 (profiles/r02_emitters.md): the image + TMA bulk-store emitters win wherever rows share no window with
+// their neighbours (per-env series, envs at unrelated steps) and on batches too small to fill the GPU with tiles; the
+// per-lane store emitters with their run detection keep a small lead on large table-backed batches in lock-step, except
+// for rows with an odd number of forecast steps, where the un-split image kernel leads.
+struct EmitChoice {
+    bool image, split;
+    int shape;
+};
+static EmitChoice choose_emitters(const MgHandle *h, const LaunchParams &P, bool persistent) {
+    EmitChoice c;
+    c.split = h->rollout_specialised;
+    c.shape = h->image_shape >= 0 ? h->image_shape : (h->hetero && !persistent ? 1 : 0);
+    if (h->emit_image != 2) {
+        c.image = h->emit_image == 1;
+        return c;
+    }
+    bool odd_rows = false;
+    for (int g = 0; g < P.n_groups; ++g)
+        if (P.g[g].has_grid && (P.g[g].horizon & 1) == 0) odd_rows = true;
+    c.image = h->hetero || h->ragged_hint || P.total_tiles <= 2 * h->n_sms;
+    if (!c.image && odd_rows && persistent) {
+        c.image = true;
+        c.split = false;
+        if (h->image_shape < 0) c.shape = 2;
+    }
+    return c;
+}
+
 static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized, void *stream) {
     if (!h || !io) return fail(MG_E_INVALID, "step: null argument");
     LaunchParams P = h->base;
@@ -2171,7 +2432,8 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
     cfg.attrs = attr;
     cfg.numAttrs = overlap ? 1 : 0;
     // image emitter: every group that writes observations has an image-compatible f64 row layout
-    bool image = h->emit_image != 0 && !h->obs_f32, any_obs = false;
+    const EmitChoice choice = choose_emitters(h, P, false);
+    bool image = choice.image && !h->obs_f32, any_obs = false;
     int max_dim = 0;
     for (int g = 0; g < P.n_groups; ++g) {
         if (!P.g[g].obs) continue;
@@ -2183,14 +2445,16 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
     if (image && any_obs) {
         ImgKernel k;
         int rc, nb;
-        img_step_kernel_for(h->hetero, h->image_shape, &k, &rc, &nb);
+        img_step_kernel_for(h->hetero, choice.shape, &k, &rc, &nb);
         cfg.dynamicSmemBytes = (size_t)MG_WARPS * nb * rc * max_dim * sizeof(double);
         const int rcode = ensure_dynamic_smem((const void *)k, cfg.dynamicSmemBytes);
         if (rcode != MG_OK) return rcode;
         e = cudaLaunchKernelEx(&cfg, k, P);
+        h->last_kernel = "mg_step_img_kernel";
     } else if (h->obs_f32) e = h->hetero ? cudaLaunchKernelEx(&cfg, mg_step_kernel<true, float>, P) : cudaLaunchKernelEx(&cfg, mg_step_kernel<false, float>, P);
     else e = h->hetero ? cudaLaunchKernelEx(&cfg, mg_step_kernel<true, double>, P) : cudaLaunchKernelEx(&cfg, mg_step_kernel<false, double>, P);
     if (e != cudaSuccess) return cuda_fail(e, "step kernel launch");
+    if (!(image && any_obs)) h->last_kernel = "mg_step_kernel";
     if (mode == MODE_STEP || mode == MODE_DISCRETE) memset(h->soc_reported, 0, sizeof h->soc_reported);   // every battery updates
     h->launches += 1;
     h->last_was_step = true;
@@ -2242,7 +2506,8 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
     for (int g = 0; g < P.n_groups; ++g)
         if (!P.g[g].obs || P.g[g].horizon + 2 > MG_RING_MAX) use_ring = false;
     // image emitter (rows leave as TMA bulk stores): every group writes f64 observations with an image-compatible layout
-    bool image = h->emit_image != 0 && !h->obs_f32;
+    const EmitChoice choice = choose_emitters(h, P, true);
+    bool image = choice.image && !h->obs_f32;
     int max_dim = 0;
     for (int g = 0; g < P.n_groups; ++g) {
         if (!P.g[g].obs || !P.g[g].img_ok) image = false;
@@ -2252,24 +2517,29 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
         for (int g = 0; g < P.n_groups; ++g)
             if (P.g[g].long_path) use_ring = false;
     if (image) {
-        const bool ws_img = h->rollout_specialised;
+        const bool ws_img = choice.split;
         ImgKernel k;
         int rc, nb;
-        img_kernel_for(h->hetero, use_ring, ws_img, h->image_shape, &k, &rc, &nb);
+        img_kernel_for(h->hetero, use_ring, ws_img, choice.shape, &k, &rc, &nb);
         const size_t dyn = (size_t)(ws_img ? 2 : MG_WARPS) * nb * rc * max_dim * sizeof(double);
         const int rcode = ensure_dynamic_smem((const void *)k, dyn);
         if (rcode != MG_OK) return rcode;
         k<<<P.total_tiles, MG_THREADS, dyn, (cudaStream_t)stream>>>(P);
+        h->last_kernel = ws_img ? "mg_rollout_img_kernel (owner / emitter warps)" : "mg_rollout_img_kernel";
     } else if (ws) {
+        h->last_kernel = "mg_rollout_ws_kernel";
         if (h->obs_f32) mg_rollout_ws_kernel<false, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
         else mg_rollout_ws_kernel<false, double><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
     } else if (use_ring) {
+        h->last_kernel = "mg_rollout_kernel (rings)";
         if (h->obs_f32) mg_rollout_kernel<true, float, true><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
         else mg_rollout_kernel<true, double, true><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
     } else if (h->obs_f32) {
+        h->last_kernel = "mg_rollout_kernel";
         if (h->hetero) mg_rollout_kernel<true, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
         else mg_rollout_kernel<false, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
     } else {
+        h->last_kernel = "mg_rollout_kernel";
         if (h->hetero) mg_rollout_kernel<true, double><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
         else mg_rollout_kernel<false, double><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
     }

@@ -554,9 +554,10 @@ class BatchedMicrogrid:
         n_actions_cfg = None if isinstance(action_tables, dict) else np.array([len(t) for t in action_tables])
         for gi, arch in enumerate(order):
             ids = np.nonzero(env_arch == gi)[0]
-            # envs of one config sit next to each other so that a 64-env tile shares its time-series windows
-            # (the kernel stages them once per run of rows that are at the same step)
-            ids = ids[np.argsort(env_config[ids], kind="stable")]
+            # envs of one config sit next to each other so that a 64-env tile shares its time-series windows, and configs
+            # that share a grid table (the four tariff x CO2 tables of MicrogridGenerator grids) are neighbours too: the
+            # emitters fetch a window once per run of rows that read it at the same step
+            ids = ids[np.lexsort((env_config[ids], cfg_np["grid_series"][env_config[ids]]))]
             self.env_slot[ids] = np.arange(len(ids))
             has_genset, has_grid, H = arch
             n_act = 1 + has_grid + 2 * has_genset
@@ -706,13 +707,20 @@ class BatchedMicrogrid:
         self._set_option(_cabi.MG_OPT_ROLLOUT_RING, bool(on))
 
     def set_emit_image(self, on):
-        """Observation rows leave the SM as TMA bulk stores of several rows assembled in shared memory (default on,
-        MG_OPT_EMIT_IMAGE); off = the per-lane 16-byte store emitters."""
-        self._set_option(_cabi.MG_OPT_EMIT_IMAGE, bool(on))
+        """How observation rows leave the SM (MG_OPT_EMIT_IMAGE): True = shared-memory images + TMA bulk stores, False = per-lane
+        16-byte stores with run detection, "auto" (default) = the library chooses per launch (include/pymgrid_b200.h)."""
+        self._set_option(_cabi.MG_OPT_EMIT_IMAGE, 2 if on == "auto" else int(bool(on)))
 
     def set_image_shape(self, index):
-        """Which instantiated (rows per bulk store, buffers per warp) shape the image kernels use (MG_OPT_IMAGE_SHAPE)."""
+        """Which instantiated (rows per bulk store, buffers per warp, rows gathered together) shape the image kernels use
+        (MG_OPT_IMAGE_SHAPE; -1 = the library's choice)."""
         self._set_option(_cabi.MG_OPT_IMAGE_SHAPE, int(index))
+
+    def set_ragged(self, on=True):
+        """Tell the library that the envs of a tile are at unrelated steps (independent resets, per-env episode windows):
+        no two rows share a window, and the image emitters are the faster ones (MG_OPT_RAGGED_HINT).  Set automatically by
+        `set_trajectories` and by masked resets."""
+        self._set_option(_cabi.MG_OPT_RAGGED_HINT, bool(on))
 
     def __del__(self):
         try:
@@ -729,6 +737,7 @@ class BatchedMicrogrid:
             g.env_initial_step = torch.from_numpy(initial_step[g.env_ids]).to(self.device)
             g.env_final_step = torch.from_numpy(final_step[g.env_ids]).to(self.device)
         self._create()
+        self.set_ragged(True)
 
     # ------------------------------------------------------------------------------------------------------
     @property
@@ -823,6 +832,8 @@ class BatchedMicrogrid:
     def reset(self, mask=None, obs=True):
         """Microgrid.reset (reference microgrid.py:205-225): step = initial_step; battery / genset state is kept."""
         io, obs_bufs = self._io(obs=obs, mask=mask)
+        if mask is not None and getattr(self, "_options", {}).get(_cabi.MG_OPT_RAGGED_HINT) is None:
+            self.set_ragged(True)      # some envs restart while the others go on: the batch leaves lock-step
         _cabi.check(self._lib.mg_reset(self._handle, io, self._stream()), "mg_reset")
         self._apply_noise(obs_bufs)
         return obs_bufs[0] if self.single_group else obs_bufs
@@ -917,6 +928,11 @@ class BatchedMicrogrid:
     @property
     def launch_count(self):
         return int(self._lib.mg_launch_count(self._handle))
+
+    @property
+    def last_kernel(self):
+        """name of the kernel family the last step / rollout launched (which emitters the library chose)"""
+        return self._lib.mg_last_kernel(self._handle).decode()
 
     def state_dict(self):
         """The reference's serialisable state (base_module.py:852-868, genset_module.py:426-427), per group."""

@@ -417,6 +417,31 @@ def test_row_emitters_agree_on_generator_grids(emit, shape, specialised):
             np.testing.assert_array_equal(got[slot], pv_first(o_obs[e, :g.obs_dim], plist[e]), err_msg=f"env {e}")
 
 
+def test_automatic_emitter_choice():
+    """MG_OPT_EMIT_IMAGE = 2 (the default): the library picks the emitters per launch and says which kernel ran
+    (mg_last_kernel).  Large table-backed batches in lock-step keep the per-lane store emitters, the ragged hint (set by a
+    masked reset) and small batches switch to the image emitters; results are the same either way (tests above)."""
+    configs = [load_pymgrid25(n) for n in range(25)]
+    big = engine(configs, np.arange(20000) % 25, with_info=False)          # 313+ tiles > 2 per SM
+    acts = [torch.rand((2, g.n_envs, g.n_act), dtype=torch.float64, device="cuda") for g in big.groups]
+    big.rollout(acts, ring=1)
+    assert big.last_kernel == "mg_rollout_ws_kernel"
+    big.step([a[0].contiguous() for a in acts])
+    assert big.last_kernel == "mg_step_kernel"
+    big.reset(mask=[torch.ones(g.n_envs, dtype=torch.uint8, device="cuda") for g in big.groups])      # leaves lock-step
+    big.rollout(acts, ring=1)
+    assert big.last_kernel.startswith("mg_rollout_img_kernel")
+    big.step([a[0].contiguous() for a in acts])
+    assert big.last_kernel == "mg_step_img_kernel"
+    small = engine(configs, np.arange(3000) % 25, with_info=False)
+    acts = [torch.rand((2, g.n_envs, g.n_act), dtype=torch.float64, device="cuda") for g in small.groups]
+    small.rollout(acts, ring=1)
+    assert small.last_kernel.startswith("mg_rollout_img_kernel")
+    small.set_emit_image(False)
+    small.rollout(acts, ring=1)
+    assert small.last_kernel == "mg_rollout_ws_kernel"
+
+
 @pytest.mark.parametrize("specialised", [True, False])
 def test_rollout_kernel_equals_repeated_steps(specialised):
     """mg_rollout (persistent kernel, state in registers; warp-specialised or plain, MG_OPT_ROLLOUT_SPECIALISED)

@@ -7,7 +7,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $o
 for stage in "$@"; do
   case $stage in
     microbench)
-      timeout 120 ./tools/microbench_store 131072 200 > $out/${tag}_microbench.txt 2>&1 ;;
+      timeout 120 ./tools/microbench_store 131072 200 > $out/${tag}_microbench.txt 2>&1
+      timeout 120 ./tools/microbench_store 65536 400 > $out/${tag}_microbench_65536.txt 2>&1 ;;
     composed)
       timeout 300 python bench.py --workload composed --steps 512 --warmup 5 > $out/${tag}_bench_composed.json 2> $out/${tag}_bench_composed.err
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:mgc_kernel -s 2 -c 1 -o $out/${tag}_mgc \
@@ -23,13 +24,22 @@ for stage in "$@"; do
     ragged)
       timeout 300 python bench.py --ragged --steps 500 --warmup 5 --single-path --no-cpu > $out/${tag}_bench_ragged.json 2> $out/${tag}_bench_ragged.err ;;
     emit_tests)
-      timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --maxfail=6 -k "row_emitters or rollout_kernel_equals or generator_grids_rollout or vectorised_generator" > $out/${tag}_emit_tests.log 2>&1 ;;
+      timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --maxfail=6 -k "row_emitters or rollout_kernel_equals or generator_grids_rollout or vectorised_generator or automatic_emitter" > $out/${tag}_emit_tests.log 2>&1 ;;
     tune)
       timeout 900 python tools/tune_emitters.py --steps 400 --step-path > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
+    tune_roles)
+      timeout 900 python tools/tune_emitters.py --steps 400 --variants image_ws --workloads pymgrid25,ragged,generator > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
+    tune_const)
+      MG_DEBUG_CONST_ACTIONS=1 timeout 900 python tools/tune_emitters.py --steps 400 --variants default --workloads pymgrid25,ragged,generator > $out/${tag}_tune_const.jsonl 2> $out/${tag}_tune_const.err ;;
+    tune_gen)
+      timeout 900 python tools/tune_emitters.py --steps 400 --variants image_ws --workloads generator > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
     tune_default)
       timeout 900 python tools/tune_emitters.py --steps 400 --variants default > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
     ncu_gen)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:mg_rollout -s 1 -c 1 -o $out/${tag}_gen \
+        python bench.py --workload generator --steps 24 --warmup 3 --preheat 0 --single-path --no-cpu $BENCH_EXTRA > $out/${tag}_ncu_gen.log 2>&1 ;;
+    ncu_gen_src)
+      timeout 600 ncu --section SourceCounters --section InstructionStats --section WarpStateStats --section LaunchStats --section Occupancy --clock-control none --import-source on -k regex:mg_rollout -s 1 -c 1 -o $out/${tag}_gen \
         python bench.py --workload generator --steps 24 --warmup 3 --preheat 0 --single-path --no-cpu $BENCH_EXTRA > $out/${tag}_ncu_gen.log 2>&1 ;;
     ncu_default)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:mg_rollout -s 1 -c 1 -o $out/${tag}_default \

@@ -47,25 +47,27 @@ __global__ void __launch_bounds__(THREADS) k_lsu(double *out, size_t slot_stride
 }
 
 // MODE 1 tma, 2 fill, 3 real
-template <int R, int B, int MODE>
+template <int R, int B, int MODE, int EW>
 __global__ void __launch_bounds__(THREADS) k_img(double *out, size_t slot_stride, int n_rows, int steps, const double *__restrict__ table,
                                                int table_rows, int ragged) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *img = reinterpret_cast<double *>(smem) + (size_t)warp * B * R * D;
-    double *ring = reinterpret_cast<double *>(smem) + (size_t)4 * B * R * D;   // [2][TILE][26] (MODE 3)
-    const int r0 = blockIdx.x * TILE + warp * 16;
+    constexpr int RW = TILE / EW;   // rows per emitting warp and step (EW = 2: the other two warps idle, like the owner warps of the split kernels)
+    double *img = reinterpret_cast<double *>(smem) + (size_t)(warp % EW) * B * R * D;
+    double *ring = reinterpret_cast<double *>(smem) + (size_t)EW * B * R * D;   // [2][TILE][26] (MODE 3)
+    const int r0 = blockIdx.x * TILE + (warp % EW) * RW;
     if (MODE == 3)
         for (int i = threadIdx.x; i < 2 * TILE * 26; i += THREADS) ring[i] = i * 0.25;
     for (int i = lane; i < B * R * D; i += 32) img[i] = i;
     __syncthreads();
+    if (warp >= EW) return;
     fence_async();
     double v0 = lane, v1 = lane + 0.5;
     int buf = 0;
     for (int s = 0; s < steps; ++s) {
         double *o = out + (size_t)(s & 3) * slot_stride + (size_t)r0 * D;
 #pragma unroll 1
-        for (int c = 0; c < 16 / R; ++c) {
+        for (int c = 0; c < RW / R; ++c) {
             double *im = img + (size_t)buf * R * D;
             if (MODE >= 2) {
                 if (lane == 0) bulk_wait_read<B - 1>();   // the store that last read this buffer has drained it
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(THREADS) k_img(double *out, size_t slot_stride
                         const double2 *gs = reinterpret_cast<const double2 *>(table + ((size_t)(row_id & 3) * table_rows + t) * 4);
                         g[r][0] = __ldg(gs + lane);
                         g[r][1] = lane < 16 ? __ldg(gs + 32 + lane) : make_double2(0, 0);
-                        const int e = warp * 16 + c * R + r;
+                        const int e = (warp % EW) * RW + c * R + r;
                         int slot = (s % 26) + lane;
                         if (slot >= 26) slot -= 26;
                         w[r][0] = lane < 24 ? ring[e * 26 + slot] : ring[e * 26 + (lane - 24)];
@@ -146,17 +148,17 @@ static size_t g_smem;
 static void launch_lsu(int steps) { k_lsu<<<g_tiles, THREADS>>>(g_out, g_slot, g_rows, steps); }
 static void launch_img(int steps) { g_k<<<g_tiles, THREADS, g_smem + g_pad>>>(g_out, g_slot, g_rows, steps, g_table, g_table_rows, g_ragged); }
 
-template <int R, int B, int MODE>
+template <int R, int B, int MODE, int EW = 4>
 static void run_img(const char *name, int steps, int pad_kb) {
-    g_k = k_img<R, B, MODE>;
-    g_smem = (size_t)4 * B * R * ROW_BYTES + (MODE == 3 ? 2 * TILE * 26 * 8 : 0);
+    g_k = k_img<R, B, MODE, EW>;
+    g_smem = (size_t)EW * B * R * ROW_BYTES + (MODE == 3 ? 2 * TILE * 26 * 8 : 0);
     g_pad = pad_kb * 1024;
     cudaFuncSetAttribute(g_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(g_smem + g_pad));
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_k, THREADS, g_smem + g_pad);
     const float ms = time_kernel(launch_img, steps);
     const double us = 1e3 * ms / steps;
-    printf("%-5s R=%2d B=%d ragged=%d smem=%6.1f KB ctas/sm=%2d : %7.2f us/step  %6.3f TB/s\n", name, R, B, g_ragged, (g_smem + g_pad) / 1024.0, occ, us,
+    printf("%-5s R=%2d B=%d EW=%d ragged=%d smem=%6.1f KB ctas/sm=%2d : %7.2f us/step  %6.3f TB/s\n", name, R, B, EW, g_ragged, (g_smem + g_pad) / 1024.0, occ, us,
            (double)g_rows * ROW_BYTES / us / 1e6);
 }
 
@@ -196,6 +198,14 @@ int main(int argc, char **argv) {
         run_img<8, 2, 3>("real", steps, 0);
     }
     g_ragged = 0;
+    // two emitting warps per CTA (the warp-specialised kernels), with enough padding to cap the CTAs at 7 per SM
+    run_img<4, 2, 1, 2>("tma", steps, 0);
+    run_img<4, 2, 2, 2>("fill", steps, 0);
+    run_img<4, 2, 3, 2>("real", steps, 0);
+    run_img<2, 2, 3, 2>("real", steps, 0);
+    run_img<4, 4, 3, 2>("real", steps, 0);
+    run_img<4, 2, 2, 2>("fill", steps, 12);
+    run_img<4, 2, 3, 2>("real", steps, 8);
     // occupancy sensitivity of the best candidates (pad shared memory to cap the resident CTAs)
     run_img<2, 2, 3>("real", steps, 16);
     run_img<2, 2, 3>("real", steps, 32);

@@ -30,6 +30,8 @@ def main():
     torch.cuda.set_device(dev)
     peak, _ = bench.measured_peak()
     variants = [("lsu", 0, True), ("lsu", 0, False)] + [("image", s, ws) for s in range(4) for ws in (True, False)]
+    if args.variants == "image_ws":
+        variants = [("image", s, True) for s in range(3)]
     if args.variants == "default":
         variants = [("lsu", 0, True), ("image", 0, True), ("image", 0, False)]
     K = args.steps
@@ -75,6 +77,9 @@ def main():
                 bm.rollout([a[:8] for a in acts], ring=4, discrete=discrete)
                 bm.load_state_dict(state0)
                 torch.cuda.synchronize()
+                if hasattr(bm._lib, "mg_debug_role_cycles"):
+                    import ctypes
+                    bm._lib.mg_debug_role_cycles((ctypes.c_ulonglong * 8)(), 1)
                 ev0.record()
                 launch()
                 ev1.record()
@@ -82,6 +87,14 @@ def main():
                 us = 1e3 * ev0.elapsed_time(ev1) / K
                 line = {"workload": wl, "batch": B, "path": "rollout", "emit": emit, "shape": shape, "specialised": ws, "ring": ring,
                         "us_per_step": round(us, 3), "tbs": round(nbytes / us / 1e6, 3), "frac": round(nbytes / us / 1e3 / peak, 3)}
+                if hasattr(bm._lib, "mg_debug_role_cycles"):     # -DMG_ROLE_TIMERS build: average cycles per warp-step by role
+                    import ctypes
+                    buf = (ctypes.c_ulonglong * 8)()
+                    bm._lib.mg_debug_role_cycles(buf, 1)
+                    n = max(buf[5], 1)
+                    line["role_cycles_per_warp_step"] = {"owner_physics": round(buf[0] / n), "owner_wait_empty": round(buf[1] / n),
+                                                         "emitter_wait_full": round(buf[2] / n), "emitter_wait_buffer": round(buf[3] / n),
+                                                         "emitter_busy_incl_buffer_wait": round(buf[4] / n)}
             except Exception as ex:     # a variant that cannot launch (shared memory) must not lose the others
                 line = {"workload": wl, "emit": emit, "shape": shape, "specialised": ws, "error": f"{type(ex).__name__}: {ex}"}
             print(json.dumps(line), flush=True)
