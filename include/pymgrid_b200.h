@@ -330,7 +330,8 @@ enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2, MG_OPT_EMIT_IMAG
  * lock-step.  Results never depend on the choice.
  * MG_OPT_IMAGE_SHAPE (default -1 = the library's choice): which instantiated (rows per bulk store, image buffers per
  * emitting warp, rows gathered together) shape the image kernels use -- 0: (4, 2, 2), 1: (2, 2, 2), 2: (4, 2, 4),
- * 3: (8, 2, 2); a tuning knob.
+ * 3: (4, 4, 2), 4: (4, 4, 4), 5: (8, 2, 4); 3-5 run the per-env-series persistent kernel at three CTAs per SM with 168
+ * registers.  A tuning knob.
  * MG_OPT_RAGGED_HINT (default 0): tell the library that the envs of a tile are at unrelated steps (independent resets,
  * per-env episode windows), where no two rows share a window. */
 int mg_set_option(MgHandle *h, int option, int value);

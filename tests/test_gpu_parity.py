@@ -313,7 +313,7 @@ def test_batch_vs_oracle_ragged_state(order):
         np.testing.assert_array_equal(np.array([s[2:] for s in st]), gen)
 
 
-EMITTER_VARIANTS = [("lsu", 0, True), ("lsu", 0, False)] + [("image", shape, ws) for shape in range(4) for ws in (True, False)]
+EMITTER_VARIANTS = [("lsu", 0, True), ("lsu", 0, False)] + [("image", shape, ws) for shape in range(6) for ws in (True, False)]
 
 
 def set_emitter(bm, emit, shape, specialised):

@@ -29,9 +29,9 @@ def main():
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     peak, _ = bench.measured_peak()
-    variants = [("lsu", 0, True), ("lsu", 0, False)] + [("image", s, ws) for s in range(4) for ws in (True, False)]
+    variants = [("lsu", 0, True), ("lsu", 0, False)] + [("image", s, ws) for s in range(6) for ws in (True, False)]
     if args.variants == "image_ws":
-        variants = [("image", s, True) for s in range(3)]
+        variants = [("image", s, True) for s in (0, 3, 4, 5)]
     if args.variants == "default":
         variants = [("lsu", 0, True), ("image", 0, True), ("image", 0, False)]
     K = args.steps
@@ -65,7 +65,7 @@ def main():
         print(json.dumps({"workload": wl, "batch": B, "path": "rollout, no observations", "us_per_step": round(1e3 * ev0.elapsed_time(ev1) / K, 3)}), flush=True)
         wl_variants = [v + (True,) for v in variants]
         if name == "generator":      # per-env series: also without the shared-memory rings (whole windows normalised per row)
-            wl_variants += [v + (False,) for v in variants if v[0] == "image"]
+            wl_variants += [v + (False,) for v in variants if v[0] == "image" and v[1] == 0]
         for emit, shape, ws, ring in wl_variants:
             bm.set_emit_image(emit == "image")
             bm.set_image_shape(shape)
