@@ -349,6 +349,15 @@ int mg_set_option(MgHandle *h, int option, int value);
  */
 int mg_set_reported_soc(MgHandle *h, const double *const *soc);
 
+/*
+ * mg_set_trajectories -- per-env episode windows (microgrid/trajectory/*.py; Microgrid._set_trajectory, microgrid.py:221-225,
+ * which rewrites every module's initial_step / final_step on reset).  `initial_step` / `final_step`: HOST arrays of n_groups
+ * DEVICE pointers ([n] int32 each), replacing MgGroup.env_initial_step / env_final_step of every group for the calls that
+ * follow; an entry, or a whole array, may be NULL = the configs' own window.  The handle stays the same object: launchers
+ * bound earlier, options and the staging of mg_rollout_host are unaffected.  The arrays stay owned by the caller.
+ */
+int mg_set_trajectories(MgHandle *h, const int32_t *const *initial_step, const int32_t *const *final_step);
+
 /* number of kernel launches this handle has enqueued since creation (bench.py's gpu_launches claim) */
 int64_t mg_launch_count(const MgHandle *h);
 /* name of the kernel family the last mg_step* / mg_rollout* call on the handle launched (which emitters MG_OPT_EMIT_IMAGE = 2 chose) */

@@ -130,6 +130,8 @@ def lib():
     L.mg_set_reported_soc.argtypes = [_vp, C.POINTER(_vp)]
     L.mg_launch_count.argtypes = [_vp]
     L.mg_launch_count.restype = C.c_int64
+    L.mg_set_trajectories.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp)]
+    L.mg_set_trajectories.restype = C.c_int
     L.mg_last_kernel.argtypes = [_vp]
     L.mg_last_kernel.restype = C.c_char_p
     if L.mg_abi_version() != MG_ABI_VERSION:
@@ -144,7 +146,7 @@ def lib():
 
 EXPORTED_SYMBOLS = ("mg_abi_version", "mg_sizeof", "mg_build_info", "mg_last_error", "mg_create", "mg_destroy",
                     "mg_step", "mg_step_discrete", "mg_reset", "mg_observe", "mg_rollout", "mg_rollout_discrete",
-                    "mg_rollout_host", "mg_launch_count", "mg_last_kernel", "mg_set_option", "mg_forecast_noise", "mg_set_reported_soc")
+                    "mg_rollout_host", "mg_launch_count", "mg_last_kernel", "mg_set_trajectories", "mg_set_option", "mg_forecast_noise", "mg_set_reported_soc")
 
 
 def check(code, what):

@@ -17,8 +17,7 @@ path:
   ComposedLogRecorder  reference-format log for a subset of a batch
   StandaloneModule   a module stepped on its own (mgc_modules_step): what `module.step(action)` of pymgrid_b200.modules runs on
 
-No CPU fallback: without the CUDA extension or a CUDA device, construction raises.  (`_library` is the test suite's hook
-for the host build of the same C source, tests/hostsim/.)
+No CPU fallback: without the CUDA extension or a CUDA device, construction raises (`_open_device_library`).
 """
 import ctypes as C
 import warnings
@@ -357,9 +356,21 @@ class Composition:
 
 
 # ---- the batch ----------------------------------------------------------------------------------------------------------
+def _open_device_library(device=None):
+    """The CUDA extension bound for the composed entry points, and the CUDA device a batch lives on.  The only way in:
+    there is no CPU execution path in this package -- a missing extension or a missing GPU raises EngineError."""
+    L = bind(_cabi.lib())       # raises EngineError when the CUDA extension is missing
+    if not torch.cuda.is_available():
+        raise _cabi.EngineError("ComposedBatch needs a CUDA device: there is no CPU fallback")
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.type != "cuda":
+        raise _cabi.EngineError("ComposedBatch runs on CUDA devices only")
+    return L, dev
+
+
 class ComposedBatch:
     def __init__(self, microgrids, env_config=None, device=None, obs_order="gym_sorted", with_info=False,
-                 microgrid_kwargs=None, prenormalised=True, observation_keys=(), _library=None):
+                 microgrid_kwargs=None, prenormalised=True, observation_keys=()):
         """`microgrids`: list of module lists (one per parameter set; all with the same composition) or ready
         `Composition`s; `env_config[e]`: which one env e is (default: one env per entry)."""
         kw = dict(microgrid_kwargs or {})
@@ -371,16 +382,7 @@ class ComposedBatch:
             if c.signature != comp.signature:
                 raise ValueError("the microgrids of one ComposedBatch must share one composition (module names, kinds, "
                                  "forecast horizons, series length); build one batch per composition")
-        if _library is None:
-            self._L = bind(_cabi.lib())       # raises EngineError when the CUDA extension is missing
-            if not torch.cuda.is_available():
-                raise _cabi.EngineError("ComposedBatch needs a CUDA device: there is no CPU fallback")
-            self.device = torch.device(device if device is not None else "cuda")
-            if self.device.type != "cuda":
-                raise _cabi.EngineError("ComposedBatch runs on CUDA devices only")
-        else:                                 # tests/hostsim: the same C source built for the host
-            self._L = bind(_library)
-            self.device = torch.device("cpu")
+        self._L, self.device = _open_device_library(device)
         env_config = np.arange(len(self.compositions)) if env_config is None else np.asarray(env_config, dtype=np.int64)
         if env_config.ndim != 1 or len(env_config) < 1 or env_config.min() < 0 or env_config.max() >= len(self.compositions):
             raise ValueError("env_config must index the microgrid list")
@@ -1043,7 +1045,7 @@ class ComposedMicrogrid:
     reference's clip semantics -- the engine reports events, it does not unwind."""
 
     def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2.,
-                 reward_shaping_func=None, trajectory_func=None, device=None, obs_order="gym_sorted", _library=None):
+                 reward_shaping_func=None, trajectory_func=None, device=None, obs_order="gym_sorted"):
         if reward_shaping_func is not None and not callable(reward_shaping_func):
             raise TypeError("reward_shaping_func must be callable: f(energy_info, cost_info) -> float (microgrid/utils/step.py:41-46)")
         # B = 1: the shaper is the caller's Python function of the step's info dict, evaluated on the host exactly where
@@ -1051,8 +1053,7 @@ class ComposedMicrogrid:
         self.reward_shaping_func = reward_shaping_func
         comp = Composition(modules, add_unbalanced_module, loss_load_cost, overgeneration_cost, obs_order=obs_order)
         self.composition = comp
-        self._library = _library
-        self._batch = ComposedBatch([comp], device=device, obs_order=obs_order, with_info=True, _library=_library)
+        self._batch = ComposedBatch([comp], device=device, obs_order=obs_order, with_info=True)
         self._modules = ComposedContainer()
         for s, r in zip(comp.slots, comp.records):
             self._modules.setdefault(s.name, ModuleList()).append(ComposedModuleView(self, s, r))
@@ -1063,28 +1064,9 @@ class ComposedMicrogrid:
         self.trajectory_func = self._check_trajectory_func(trajectory_func)
 
     def _check_trajectory_func(self, trajectory_func):
-        """reference: Microgrid._check_trajectory_func (microgrid.py:167-199), same errors"""
-        if trajectory_func is None:
-            return trajectory_func
-        if not callable(trajectory_func):
-            raise TypeError('trajectory_func must be callable.')
-        output = trajectory_func(self._initial_step, self._final_step)
-        try:
-            initial_step, final_step = output
-            if not (isinstance(initial_step, int) and isinstance(final_step, int)):
-                raise ValueError
-        except (TypeError, ValueError):
-            raise TypeError(f'trajectory func must return two integer values, not {output}')
-        if initial_step < self._initial_step:
-            raise ValueError(f'trajectory_func returned initial_step value ({initial_step}) less than env\'s initial '
-                             f'step: ({self._initial_step})')
-        if final_step > self._final_step:
-            raise ValueError(f'trajectory_func returned final_step value ({final_step}) greater than env\'s final step:'
-                             f' ({self._final_step})')
-        if initial_step >= final_step:
-            raise ValueError(f'trajectory_func returned values ({initial_step}, {final_step}) such that initial_step'
-                             f'was greater than or equal to final_step.')
-        return trajectory_func
+        """reference: Microgrid._check_trajectory_func (microgrid.py:167-199): see trajectory.validated"""
+        from .trajectory import validated
+        return validated(trajectory_func, self._initial_step, self._final_step)
 
     def _set_window(self, initial_step, final_step):
         """the modules' episode window (microgrid.py:221-225, 652-684): the env's entry of the batch's per-env window arrays"""
@@ -1256,7 +1238,7 @@ class ComposedMicrogrid:
         comp = self.composition
         named = [(s.name, r) for s, r in zip(comp.slots, comp.records)]
         other = ComposedMicrogrid(named, add_unbalanced_module=False, device=self._batch.device if self._batch.device.type == "cuda" else None,
-                                  obs_order=comp.obs_order, _library=self._library)
+                                  obs_order=comp.obs_order)
         for a in ("step_counter", "fstate", "istate", "env_initial_step", "env_final_step"):
             getattr(other._batch, a).copy_(getattr(self._batch, a))
         other.reward_shaping_func, other.trajectory_func = self.reward_shaping_func, self.trajectory_func
@@ -1361,7 +1343,7 @@ class ComposedMicrogrid:
         state = {a: getattr(old, a).clone() for a in ("step_counter", "fstate", "istate", "env_initial_step", "env_final_step")}
         keep = (self._log_rows, self.reward_shaping_func, self.trajectory_func, self._initial_step, self._final_step)
         ComposedMicrogrid.__init__(self, named, add_unbalanced_module=False, device=old.device if old.device.type == "cuda" else None,
-                                   obs_order=comp.obs_order, _library=self._library)
+                                   obs_order=comp.obs_order)
         self._log_rows, self.reward_shaping_func, self.trajectory_func, self._initial_step, self._final_step = keep
         for a, v in state.items():
             getattr(self._batch, a).copy_(v)
@@ -1436,7 +1418,7 @@ class _ComposedEnv:
 
     def __init__(self, modules, add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2., reward_shaping_func=None,
                  trajectory_func=None, flat_spaces=True, observation_keys=(), batch=None, device=None, obs_order="gym_sorted",
-                 _library=None):
+                 ):
         from .envs import Box
         if not flat_spaces:
             raise NotImplementedError("flat_spaces=False (nested gym spaces) is not part of the batched surface")
@@ -1445,7 +1427,7 @@ class _ComposedEnv:
             raise NotImplementedError("batched composed envs: a reward_shaping_func is a Python callable and runs for single "
                                       "microgrids only (the fused module set has on-device shapers)")
         self._mg = ComposedMicrogrid(modules, add_unbalanced_module, loss_load_cost, overgeneration_cost, reward_shaping_func,
-                                     trajectory_func, device=device, obs_order=obs_order, _library=_library) \
+                                     trajectory_func, device=device, obs_order=obs_order) \
             if not isinstance(modules, ComposedMicrogrid) else modules
         self.trajectory_func = self._mg.trajectory_func
         comp = self.composition = self._mg.composition
@@ -1453,12 +1435,13 @@ class _ComposedEnv:
             self.batch = self._mg._batch
         else:
             self.batch = ComposedBatch([comp], np.zeros(int(batch), dtype=np.int64), device=device, obs_order=comp.obs_order,
-                                       observation_keys=observation_keys, _library=self._mg._library)
+                                       observation_keys=observation_keys)
             for a in ("step_counter", "fstate", "istate"):      # replicas start from the microgrid's live state
                 getattr(self.batch, a).copy_(getattr(self._mg._batch, a).expand_as(getattr(self.batch, a)))
         self.n_envs = self.batch.n_envs
         # observation_keys (base.py:109-163, 211-218): a batch writes only the selected elements (ComposedBatch); a single
         # microgrid keeps its full row for Microgrid.run's dicts and the env picks the selected elements out of it
+        observation_keys = observation_keys or ()      # (None is the reference DiscreteMicrogridEnv's own default)
         self.observation_keys = [observation_keys] if isinstance(observation_keys, str) else list(observation_keys)
         self._take = None
         if self.observation_keys:
@@ -1503,13 +1486,9 @@ class _ComposedEnv:
     def _draw_windows(self, mask):
         """one (initial_step, final_step) pair per env being reset; the vectorised classes of pymgrid_b200.trajectory draw all
         of them in one call (`n=`), a plain reference-style callable is called once per env"""
+        from .trajectory import draw
         lo, hi, n = self._mg.initial_step, self._mg.final_step, self.n_envs
-        try:
-            initial, final = self.trajectory_func(lo, hi, n=n)
-        except TypeError:
-            pairs = [self.trajectory_func(lo, hi) for _ in range(n)]
-            initial, final = np.array([p[0] for p in pairs]), np.array([p[1] for p in pairs])
-        initial, final = np.asarray(initial, dtype=np.int32).reshape(n).copy(), np.asarray(final, dtype=np.int32).reshape(n).copy()
+        initial, final = draw(self.trajectory_func, lo, hi, n)
         if mask is not None:                      # envs that keep running keep their window
             keep = ~np.asarray(mask.cpu() if hasattr(mask, "cpu") else mask, dtype=bool).reshape(n)
             initial[keep] = self.batch.env_initial_step.cpu().numpy()[keep]
@@ -1643,9 +1622,6 @@ class ComposedRuleBasedControl:
 
 
 # ---- a module on its own: the reference's operator API (BaseMicrogridModule.step / reset / state) ------------------------
-_STANDALONE_LIBRARY = None      # test hook: the host build of the C source (tests/hostsim); None = the CUDA library
-
-
 class StandaloneModule:
     """`module.step(action, normalized)` without a Microgrid around it (modules/base/base_module.py:95-159; the reference's
     module-level tests use its modules this way): a batch of one holding just this module, stepped by mgc_modules_step.
@@ -1653,8 +1629,7 @@ class StandaloneModule:
 
     def __init__(self, record, device=None):
         name = record.module_type[0]
-        self.mg = ComposedMicrogrid([(name, record)], add_unbalanced_module=False, obs_order="container", device=device,
-                                    _library=_STANDALONE_LIBRARY)
+        self.mg = ComposedMicrogrid([(name, record)], add_unbalanced_module=False, obs_order="container", device=device)
         self.view = self.mg.modules[name][0]
         self.kind = record.module_type[0]
         self.width = 2 if self.kind == "genset" else 0 if self.kind == "load" else 1

@@ -2242,6 +2242,18 @@ extern "C" int mg_set_reported_soc(MgHandle *h, const double *const *soc) {
     return MG_OK;
 }
 
+extern "C" int mg_set_trajectories(MgHandle *h, const int32_t *const *initial_step, const int32_t *const *final_step) {
+    if (!h) return fail(MG_E_INVALID, "mg_set_trajectories: null handle");
+    for (int g = 0; g < h->base.n_groups; ++g) {
+        const int32_t *lo = initial_step ? initial_step[g] : nullptr, *hi = final_step ? final_step[g] : nullptr;
+        h->base.g[g].env_initial = lo;
+        h->base.g[g].env_final = hi;
+        h->layout.groups[g].env_initial_step = lo;
+        h->layout.groups[g].env_final_step = hi;
+    }
+    return MG_OK;
+}
+
 extern "C" int mg_forecast_noise(MgHandle *h, const MgForecastNoise *noise, void *const *obs, const int64_t *env_base,
                                  uint64_t seed, uint64_t call, void *stream) {
     if (!h || !noise || !obs) return fail(MG_E_INVALID, "mg_forecast_noise: null argument");

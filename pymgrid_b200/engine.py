@@ -730,13 +730,22 @@ class BatchedMicrogrid:
             pass
 
     def set_trajectories(self, initial_step, final_step):
-        """Per-env episode windows (reference: microgrid/trajectory/*, Microgrid._set_trajectory microgrid.py:221-225)."""
+        """Per-env episode windows (reference: microgrid/trajectory/*, Microgrid._set_trajectory microgrid.py:221-225).
+        The handle is kept (mg_set_trajectories swaps the window arrays in place): launchers bound earlier by
+        `prepare_step` / `prepare_rollout` / `host_io` / `host_rollout` stay valid and see the new windows."""
         initial_step = np.asarray(initial_step, dtype=np.int32)
         final_step = np.asarray(final_step, dtype=np.int32)
+        previous = [(g.env_initial_step, g.env_final_step) for g in self.groups]
         for g in self.groups:
-            g.env_initial_step = torch.from_numpy(initial_step[g.env_ids]).to(self.device)
-            g.env_final_step = torch.from_numpy(final_step[g.env_ids]).to(self.device)
-        self._create()
+            g.env_initial_step = torch.from_numpy(np.ascontiguousarray(initial_step[g.env_ids])).to(self.device)
+            g.env_final_step = torch.from_numpy(np.ascontiguousarray(final_step[g.env_ids])).to(self.device)
+        lo = (C.c_void_p * len(self.groups))(*[_ptr(g.env_initial_step) for g in self.groups])
+        hi = (C.c_void_p * len(self.groups))(*[_ptr(g.env_final_step) for g in self.groups])
+        _cabi.check(self._lib.mg_set_trajectories(self._handle, lo, hi), "mg_set_trajectories")
+        # kernels already enqueued may still read the previous arrays: release them only once the device has caught up
+        self._retired_windows = previous
+        torch.cuda.current_stream(self.device).synchronize()
+        self._retired_windows = None
         self.set_ragged(True)
 
     # ------------------------------------------------------------------------------------------------------

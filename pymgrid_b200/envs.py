@@ -75,7 +75,7 @@ class _BaseEnv:
 
     def __init__(self, configs, env_config=None, batch=None, device=None, obs_order="gym_sorted", with_info=False,
                  add_unbalanced_module=True, loss_load_cost=10., overgeneration_cost=2., reward_shaping_func=None,
-                 trajectory_func=None, flat_spaces=True, observation_keys=()):
+                 trajectory_func=None, flat_spaces=True, observation_keys=(), remove_redundant_gensets=True):
         """`configs`: one MicrogridParams, a list of them, or -- the reference's call, BaseMicrogridEnv(modules,
         add_unbalanced_module, loss_load_cost, overgeneration_cost, reward_shaping_func, trajectory_func)
         (envs/base/base.py:84-110) -- a list of `pymgrid_b200.modules` objects / (name, module) tuples."""
@@ -98,6 +98,7 @@ class _BaseEnv:
             raise ValueError("an env batch holds one architecture (use BatchedMicrogrid directly for mixed batches)")
         self.engine = BatchedMicrogrid(configs, env_config, device=device, obs_order=obs_order,
                                        with_info=with_info or self.single, with_flags=True,
+                                       remove_redundant_gensets=remove_redundant_gensets,
                                        action_order=None if obs_order == "gym_sorted" else views.CONTROL_ORDER)
         self.group = self.engine.groups[0]
         self.params = configs[0]
@@ -108,6 +109,7 @@ class _BaseEnv:
         # observation_keys (base.py:109-163, 211-218): the observation is state_series(normalized=True).loc[:, :, keys] -- for
         # every key in the order given, the modules that have such a field in listing order.  The fused kernels write full
         # rows; the env gathers the selected columns (composed batches write only the selected elements, compose.py)
+        observation_keys = observation_keys or ()      # (None is the reference DiscreteMicrogridEnv's own default)
         self.observation_keys = [observation_keys] if isinstance(observation_keys, str) else list(observation_keys)
         self._take = self._take_dev = None
         if self.observation_keys:
@@ -126,27 +128,9 @@ class _BaseEnv:
         self.trajectory_func = self._check_trajectory_func(trajectory_func)
 
     def _check_trajectory_func(self, trajectory_func):
-        """reference: Microgrid._check_trajectory_func (microgrid.py:167-199): one validating call, same errors"""
-        if trajectory_func is None:
-            return trajectory_func
-        if not callable(trajectory_func):
-            raise TypeError('trajectory_func must be callable.')
-        lo, hi = self.params.initial_step, self.params.final_step
-        output = trajectory_func(lo, hi)
-        try:
-            initial_step, final_step = output
-            if not (isinstance(initial_step, (int, np.integer)) and isinstance(final_step, (int, np.integer))):
-                raise ValueError
-        except (TypeError, ValueError):
-            raise TypeError(f'trajectory func must return two integer values, not {output}')
-        if initial_step < lo:
-            raise ValueError(f'trajectory_func returned initial_step value ({initial_step}) less than env\'s initial step: ({lo})')
-        if final_step > hi:
-            raise ValueError(f'trajectory_func returned final_step value ({final_step}) greater than env\'s final step: ({hi})')
-        if initial_step >= final_step:
-            raise ValueError(f'trajectory_func returned values ({initial_step}, {final_step}) such that initial_step'
-                             f'was greater than or equal to final_step.')
-        return trajectory_func
+        """reference: Microgrid._check_trajectory_func (microgrid.py:167-199): see trajectory.validated"""
+        from .trajectory import validated
+        return validated(trajectory_func, self.params.initial_step, self.params.final_step, integer_types=(int, np.integer))
 
     @classmethod
     def from_scenario(cls, microgrid_number=0, batch=None, **kw):
@@ -229,13 +213,9 @@ class _BaseEnv:
     def _draw_windows(self, mask):
         """One (initial_step, final_step) pair per env that is being reset, from `trajectory_func(initial, final)`; the
         vectorised trajectory classes of pymgrid_b200.trajectory draw all of them in one call (`n=`)."""
+        from .trajectory import draw
         lo, hi, n = self.params.initial_step, self.params.final_step, self.n_envs
-        try:
-            initial, final = self.trajectory_func(lo, hi, n=n)
-        except TypeError:                          # a plain reference-style callable: one call per env
-            pairs = [self.trajectory_func(lo, hi) for _ in range(n)]
-            initial, final = np.array([p[0] for p in pairs]), np.array([p[1] for p in pairs])
-        initial, final = np.asarray(initial, dtype=np.int32).reshape(n), np.asarray(final, dtype=np.int32).reshape(n)
+        initial, final = draw(self.trajectory_func, lo, hi, n)
         if (initial < lo).any() or (final > hi).any() or (initial >= final).any():
             raise ValueError(f"trajectory_func returned a window outside [{lo}, {hi}] or an empty one")   # microgrid.py:184-197
         if mask is not None and getattr(self, "_windows", None) is not None:     # envs that keep running keep their window
@@ -250,8 +230,12 @@ class _BaseEnv:
         if not self.single:
             return self._select(obs), reward, done, ({} if info is None else {"info_block": info, "flags": self.group.flags})
         flags = int(self.group.flags[0].item()) & 0xffffffff
+        # one microgrid: the reference raises where the engine flags (a batch keeps the flags and a NaN reward per env instead);
+        # like Microgrid.run, the exception comes after the step has been applied to the state
+        from .microgrid import raise_for_flags
+        raise_for_flags(flags, self.params, False, step=None if pre is None else pre["t"])
         info_row, r = info[0].cpu().numpy(), float(reward[0].item())
-        if pre is not None and not flags & (1 << 5):        # a step past the end logs nothing (the reference raises there)
+        if pre is not None:
             self._log_step(pre, info_row, r, action)
         return (self._select(obs[0].cpu().numpy()), r, bool(done[0].item()),
                 views.caller_names(views.info_row_to_dict(info_row, flags, self.params), self.params))
@@ -264,7 +248,8 @@ class DiscreteMicrogridEnv(_BaseEnv):
     """Action = index of a priority list (reference: envs/discrete/discrete.py:60-143)."""
 
     def __init__(self, configs, env_config=None, batch=None, remove_redundant_gensets=True, **kw):
-        super().__init__(configs, env_config, batch, **kw)
+        # (the flag decides which priority lists exist, i.e. what an action index means: discrete.py:60-80, priority_list.py:15-67)
+        super().__init__(configs, env_config, batch, remove_redundant_gensets=remove_redundant_gensets, **kw)
         from .algos import _elements
         # the reference's form (envs/discrete/discrete.py:60-80): one tuple of PriorityListElement per action
         self.actions_list = [tuple(_elements(self.params, pl)) for pl in self.engine.action_tables[0]]

@@ -374,6 +374,30 @@ def _has_attr(m, a):
         return False
 
 
+def raise_for_flags(flags, params, raise_errors=False, step=None):
+    """Turn the engine's per-env event flags of one step into the exception the reference raises at that point
+    (include/pymgrid_b200.h, MG_FLAG_*): used by the single-microgrid surfaces (Microgrid.run, the env classes with one env)."""
+    if flags & (1 << 5):        # load_module.py:111: the time series is indexed past its end
+        where = "" if step is None else f"index {step} is out of bounds for axis 0 with size {len(params)}"
+        raise IndexError(where or "step past the end of the time series")
+    err = flags & FLAG_ERROR_MASK
+    if err:
+        names = [n for bit, n in FLAG_NAMES.items() if err & bit]
+        if err & (1 << 1):      # a genset asked to absorb: as_sink compares with max_consumption, which a source-only
+            # module does not implement (base_module.py:265, :604-619)
+            raise TypeError("'>' not supported between instances of 'float' and 'NotImplementedType'")
+        if err & (1 << 2):
+            raise RuntimeError("Microgrid modules unable to balance energy production with consumption.\n")
+        raise AssertionError(f"step rejected: {names}")
+    mask = FLAG_CLIP_MASK
+    by_module = params.meta.get("raise_errors_by_module")
+    if by_module is not None:       # built from modules: only a module constructed with raise_errors=True raises for ITS clip
+        mask = sum(bit for bit, key in ((1 << 8, "genset"), (1 << 9, "battery"), (1 << 10, "grid")) if by_module.get(key))
+    if raise_errors and flags & mask:
+        names = [n for bit, n in FLAG_NAMES.items() if flags & mask & bit]
+        raise ValueError(f"requested value outside the module's limits: {names}")    # base_module.py:79-93
+
+
 class Microgrid:
     def __new__(cls, modules=None, *args, **kw):
         """Module lists outside the fused kernels' scope (several loads / renewables / batteries / gensets / grids, no
@@ -428,28 +452,9 @@ class Microgrid:
         return self.params.renewable_name
 
     def _check_trajectory_func(self, trajectory_func):
-        """reference: Microgrid._check_trajectory_func (microgrid.py:167-199), same errors."""
-        if trajectory_func is None:
-            return trajectory_func
-        if not callable(trajectory_func):
-            raise TypeError('trajectory_func must be callable.')
-        output = trajectory_func(self._initial_step, self._final_step)
-        try:
-            initial_step, final_step = output
-            if not (isinstance(initial_step, int) and isinstance(final_step, int)):
-                raise ValueError
-        except (TypeError, ValueError):
-            raise TypeError(f'trajectory func must return two integer values, not {output}')
-        if initial_step < self._initial_step:
-            raise ValueError(f'trajectory_func returned initial_step value ({initial_step}) less than env\'s initial '
-                             f'step: ({self._initial_step})')
-        if final_step > self._final_step:
-            raise ValueError(f'trajectory_func returned final_step value ({final_step}) greater than env\'s final step:'
-                             f' ({self._final_step})')
-        if initial_step >= final_step:
-            raise ValueError(f'trajectory_func returned values ({initial_step}, {final_step}) such that initial_step'
-                             f'was greater than or equal to final_step.')
-        return trajectory_func
+        """reference: Microgrid._check_trajectory_func (microgrid.py:167-199): see trajectory.validated"""
+        from .trajectory import validated
+        return validated(trajectory_func, self._initial_step, self._final_step)
 
     def _caller_name(self, kind):
         """engine key -> the caller's name of that module: only the renewable ('pv' in pymgrid25, 'renewable' by default,
@@ -580,22 +585,7 @@ class Microgrid:
         return n
 
     def _raise_for_flags(self, flags):
-        err = flags & FLAG_ERROR_MASK
-        if err:
-            names = [n for bit, n in FLAG_NAMES.items() if err & bit]
-            if err & (1 << 1):      # a genset asked to absorb: as_sink compares with max_consumption, which a source-only
-                # module does not implement (base_module.py:265, :604-619)
-                raise TypeError("'>' not supported between instances of 'float' and 'NotImplementedType'")
-            if err & (1 << 2):
-                raise RuntimeError("Microgrid modules unable to balance energy production with consumption.\n")
-            raise AssertionError(f"step rejected: {names}")
-        mask = FLAG_CLIP_MASK
-        by_module = self.params.meta.get("raise_errors_by_module")
-        if by_module is not None:       # built from modules: only a module constructed with raise_errors=True raises for ITS clip
-            mask = sum(bit for bit, key in ((1 << 8, "genset"), (1 << 9, "battery"), (1 << 10, "grid")) if by_module.get(key))
-        if self.raise_errors and flags & mask:
-            names = [n for bit, n in FLAG_NAMES.items() if flags & mask & bit]
-            raise ValueError(f"requested value outside the module's limits: {names}")    # base_module.py:79-93
+        raise_for_flags(flags, self.params, self.raise_errors)
 
     def reset(self):
         """reference: Microgrid.reset (microgrid.py:205-225): step = initial_step, logs flushed, battery / genset kept."""
@@ -753,15 +743,22 @@ class Microgrid:
 
     # ---- introspection -----------------------------------------------------------------------------------
     def state_dict(self, normalized=False):
+        """reference: Microgrid.state_dict (microgrid.py:412-421): {module name: [module.state_dict(normalized)]}"""
+        if normalized:      # every module through its own observation space (base_module.py:65-77, utils/space.py:207-218)
+            return {name: [dict(views_list[0].state_dict(normalized=True))] for name, views_list in self._modules.items()}
         st = self._state()
         sd = views.state_dict(self.params, st["t"], st["charge"], st["genset"], st["soc"])
         return {name: [dict(d)] for name, d in self._named(sd).items()}
 
     def state_series(self, normalized=False):
+        """reference: Microgrid.state_series (microgrid.py:423-432): the same values as one MultiIndex Series"""
         import pandas as pd
-        st = self._state()
-        sd = views.state_dict(self.params, st["t"], st["charge"], st["genset"], st["soc"])
-        data = OrderedDict(((name, 0, k), v) for name, d in self._named(sd).items() for k, v in d.items())
+        if normalized:
+            sd = {name: d[0] for name, d in self.state_dict(normalized=True).items()}
+        else:
+            st = self._state()
+            sd = self._named(views.state_dict(self.params, st["t"], st["charge"], st["genset"], st["soc"]))
+        data = OrderedDict(((name, 0, k), v) for name, d in sd.items() for k, v in d.items())
         return pd.Series(data)
 
     def get_log(self, as_frame=True, drop_singleton_key=False):

@@ -8,6 +8,7 @@ import torch
 from oracle.compose import ComposedOracle
 from pymgrid_b200.compose import ComposedBatch, ComposedMicrogrid
 from tests.compose_cases import BALANCE_COLS, load_cases
+from tests.hostsim import select as hostsim_select
 
 CASES = load_cases()
 
@@ -25,7 +26,8 @@ def host(t):
 
 
 def check_microgrid_reproduces_reference(case, order, lib):
-    mg = ComposedMicrogrid(case.modules(), obs_order=order, _library=lib, **case.microgrid_kwargs, **case.callable_kwargs)
+    hostsim_select(lib)
+    mg = ComposedMicrogrid(case.modules(), obs_order=order, **case.microgrid_kwargs, **case.callable_kwargs)
     assert [(s.name, s.index) for s in mg.composition.slots] == [(n, j) for n, j, _ in case.names]
     assert {k: len(v) for k, v in mg.get_empty_action().items()} == case.json("empty_action")
     reset = mg.reset()
@@ -80,6 +82,7 @@ def check_microgrid_reproduces_reference(case, order, lib):
 
 def _batch_case(lib, label, n_envs, seed):
     """a batch whose envs are re-parameterised copies of one golden composition, and the oracle twin of every env"""
+    hostsim_select(lib)
     case = next(c for c in CASES if c.label == label)
     rng = np.random.default_rng(seed)
     configs = []
@@ -94,13 +97,13 @@ def _batch_case(lib, label, n_envs, seed):
                 m.init_soc = m.init_charge / m.max_capacity
         configs.append(mods)
     env_config = rng.integers(0, 3, n_envs)
-    batch = ComposedBatch(configs, env_config, obs_order="container", with_info=True, microgrid_kwargs=case.microgrid_kwargs,
-                          _library=lib)
+    batch = ComposedBatch(configs, env_config, obs_order="container", with_info=True, microgrid_kwargs=case.microgrid_kwargs)
     oracles = [ComposedOracle(configs[c], **case.microgrid_kwargs) for c in env_config]
     return case, batch, oracles
 
 
 def check_batch_matches_oracle_and_rollout_matches_steps(label, lib, n_envs=131, T=9):
+    hostsim_select(lib)
     case, batch, oracles = _batch_case(lib, label, n_envs, 7)
     comp = batch.comp
     rng = np.random.default_rng(3)
@@ -129,8 +132,7 @@ def check_batch_matches_oracle_and_rollout_matches_steps(label, lib, n_envs=131,
     assert np.array_equal(obs.cpu().numpy(), want_obs)
     assert np.array_equal(batch2.fstate.cpu().numpy(), batch.fstate.cpu().numpy()) and np.array_equal(batch2.istate.cpu().numpy(), batch.istate.cpu().numpy())
     # the same rows when the kernel normalises the series itself instead of gathering from the pre-normalised pool
-    batch3 = ComposedBatch([c for c in batch.compositions], batch.env_config, obs_order="container", prenormalised=False,
-                           **({} if lib is None else {"_library": lib}))
+    batch3 = ComposedBatch([c for c in batch.compositions], batch.env_config, obs_order="container", prenormalised=False)
     for a in ("fstate", "istate"):
         getattr(batch3, a).copy_(getattr(_batch_case(lib, label, n_envs, 7)[1], a))
     out3 = batch3.rollout(torch.from_numpy(actions).to(batch3.device), ring=2)
@@ -157,8 +159,9 @@ DISCRETE_CASES = load_cases("compose_discrete.npz")
 
 
 def check_discrete_env_and_rbc(case, lib):
+    hostsim_select(lib)
     from pymgrid_b200.compose import ComposedDiscreteEnv, ComposedRuleBasedControl
-    kw = {} if lib is None else {"_library": lib}
+    kw = {}
     rows = lambda pls: [[[el.module[0], el.module[1], el.module_actions, el.action] for el in pl] for pl in pls]     # noqa: E731
     # the action tables, with and without the redundant genset lists
     for flag in (0, 1):
@@ -224,6 +227,7 @@ def check_discrete_env_and_rbc(case, lib):
 def check_quickstart_notebook(lib):
     """notebooks/quick-start.ipynb against pymgrid_b200: same cells (tests/golden/make_quickstart.py: notebook()), same
     displays, same log -- including the ten `sample_action(strict_bound=True)` steps under np.random.seed(0)"""
+    hostsim_select(lib)
     import json
     import os
     import pymgrid_b200
@@ -233,7 +237,7 @@ def check_quickstart_notebook(lib):
     start, end = src.index("def notebook("), src.index("def main():")
     ns = {"np": np}
     exec(compile(src[start:end], "quickstart_notebook", "exec"), ns)      # the notebook cells only, not the reference loader
-    kw = {} if lib is None else {"_library": lib}
+    kw = {}
     got = ns["notebook"](pymgrid_b200.Microgrid, BatteryModule, LoadModule, RenewableModule, GridModule, obs_order="container", **kw)
     want = np.load(os.path.join(here, "golden", "quickstart.npz"))
     for key, value in got.items():
@@ -249,9 +253,10 @@ def check_quickstart_notebook(lib):
 def check_batch_trajectory_windows(lib):
     """per-env episode windows on a composed batch: reset puts every env at its own initial step, done fires at its own
     final_step - 1 (base_timeseries_module.py:124-125), and every env equals the oracle run with that window"""
+    hostsim_select(lib)
     from pymgrid_b200.compose import ComposedContinuousEnv
     case = next(c for c in CASES if c.label == "trajectory_window")
-    kw = {} if lib is None else {"_library": lib}
+    kw = {}
     n, T = 9, 12
     rng = np.random.default_rng(21)
     windows = [(int(a), int(a + b)) for a, b in zip(rng.integers(0, 20, n), rng.integers(3, 30, n))]
@@ -289,6 +294,7 @@ def check_batch_trajectory_windows(lib):
 
 def check_set_forecaster(lib, golden_dir=None):
     """Microgrid.set_forecaster on the quick-start notebook's two-battery grid (tests/golden/make_set_forecaster.py)"""
+    hostsim_select(lib)
     import os
     import pymgrid_b200
     from pymgrid_b200 import modules as M
@@ -298,7 +304,7 @@ def check_set_forecaster(lib, golden_dir=None):
     mods = [M.BatteryModule(10, 100, 50, 50, 0.9, init_soc=0.2), M.BatteryModule(10, 1000, 10, 10, 0.7, init_soc=0.2),
             ("pv", M.RenewableModule(time_series=pv)), M.LoadModule(time_series=load),
             M.GridModule(100, 100, [0.2, 0.1, 0.5] * np.ones((200, 3)))]
-    kw = {} if lib is None else {"_library": lib}
+    kw = {}
     mg = pymgrid_b200.Microgrid(mods, **kw)
     _set_forecaster_flow(mg, z, "quick", ["load"])
     with pytest.raises(AttributeError):
@@ -346,6 +352,7 @@ def _set_forecaster_flow(m, z, prefix, names):
 def check_observation_keys(lib):
     """observation_keys on a composed env: a single microgrid picks the selected elements out of its row, a batch has the
     kernel write only those (MgcLayout.obs_select); both equal the live reference's recorded observations"""
+    hostsim_select(lib)
     import importlib.util
     import os
     from pymgrid_b200 import modules as M
@@ -355,7 +362,7 @@ def check_observation_keys(lib):
     mk = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mk)
     z = np.load(os.path.join(here, "golden", "observation_keys.npz"))
-    kw = {} if lib is None else {"_library": lib}
+    kw = {}
     env = DiscreteMicrogridEnv(mk.composed_modules(M), observation_keys=mk.COMPOSED_KEYS, **kw)
     assert env.observation_space.shape == (z["composed_obs"].shape[1],)
     rows, rewards = mk.flow(env, mk.COMPOSED_ACTIONS)
@@ -383,6 +390,7 @@ def check_observation_keys(lib):
 def check_standalone_module_steps(lib):
     """module.step(action, normalized) on pymgrid_b200.modules' objects without a Microgrid, against the live reference's
     recorded outputs (tests/golden/make_module_steps.py): observation, reward, done, info, state, exception type"""
+    hostsim_select(lib)
     import importlib.util
     import os
     import pymgrid_b200.compose as cp
@@ -392,7 +400,6 @@ def check_standalone_module_steps(lib):
     mk = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mk)
     z = np.load(os.path.join(here, "golden", "module_steps.npz"))
-    saved, cp._STANDALONE_LIBRARY = cp._STANDALONE_LIBRARY, lib
     try:
         rng = np.random.default_rng(5)
         for label, cls, kwargs in mk.specs():
@@ -448,13 +455,14 @@ def check_standalone_module_steps(lib):
                     g.step(np.array([goal, 0.0]), normalized=False)
                     assert g.current_status == predicted, (U, D, init, goals)
     finally:
-        cp._STANDALONE_LIBRARY = saved
+        pass
 
 
 def check_microgrid_helpers(lib):
     """get_forecast_horizon, to_normalized / from_normalized (round trip, module spaces), the grid's price / status columns"""
+    hostsim_select(lib)
     from pymgrid_b200 import modules as M
-    kw = {} if lib is None else {"_library": lib}
+    kw = {}
     rng = np.random.default_rng(3)
     load, pv = 100 + 100 * rng.random(60), 200 * rng.random(60)
     g = np.stack([rng.uniform(0.05, 0.9, 60), rng.uniform(0, 0.4, 60), rng.uniform(0, 0.6, 60)], axis=1)
@@ -483,7 +491,8 @@ def check_microgrid_helpers(lib):
 def check_batch_log_recorder(lib):
     """ComposedBatch.recorder(env_ids): the reference-format log of selected envs of a batch == the get_log() of a single
     microgrid stepped with the same actions (continuous and discrete steps, a masked reset in between)"""
-    kw = {} if lib is None else {"_library": lib}
+    hostsim_select(lib)
+    kw = {}
     case, batch, _ = _batch_case(lib, "several_of_each", 9, 13)
     rec = batch.recorder([0, 4, 8])
     singles = {e: ComposedMicrogrid(batch.compositions[int(batch.env_config[e])].records_named(), add_unbalanced_module=False,
@@ -522,10 +531,11 @@ def check_forecast_noise(lib):
     """Gaussian-noise forecasters on a composed batch (mgc_forecast_noise): the per-element standard deviations equal the
     reference-pinned restatement of GaussianNoiseForecaster (oracle/forecast_noise.py), and every noisy observation equals
     clip(clean + z * sigma * scale) with z from the numpy restatement of the kernel's Philox / Box-Muller stream."""
+    hostsim_select(lib)
     from oracle.forecast_noise import NoisyModule
     from pymgrid_b200 import modules as M
     from tests.helpers import engine_noise_normals
-    kw = {} if lib is None else {"_library": lib}
+    kw = {}
     rng = np.random.default_rng(8)
     T = 40
     load, pv = 100 + 100 * rng.random(T), 200 * rng.random(T)
@@ -598,8 +608,9 @@ def check_forecast_noise(lib):
 
 def check_modules_step_batch(lib):
     """mgc_modules_step on a batch spanning several tiles: every env equals a batch of one stepped with the same actions"""
+    hostsim_select(lib)
     case = next(c for c in CASES if c.label == "several_of_each")
-    kw = {} if lib is None else {"_library": lib}
+    kw = {}
     make = lambda k: ComposedBatch([case.modules()], np.zeros(k, dtype=np.int64), obs_order="container", with_info=True,      # noqa: E731
                                    microgrid_kwargs=case.microgrid_kwargs, **kw)
     n = 300
@@ -629,9 +640,10 @@ def check_modules_step_batch(lib):
 def check_control_dict_conventions(lib):
     """Microgrid.run's control conventions (microgrid.py:262-284): a bare scalar stands for [scalar], unknown keys warn,
     a missing controllable module raises ValueError"""
+    hostsim_select(lib)
     import warnings
     from pymgrid_b200 import modules as M
-    kw = {} if lib is None else {"_library": lib}
+    kw = {}
     rng = np.random.default_rng(1)
 
     def build():

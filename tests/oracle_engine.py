@@ -23,7 +23,7 @@ FLAG_BAD_ACTION = 1 << 6
 
 class OracleBackedEngine:
     def __init__(self, configs, env_config, device=None, obs_order="gym_sorted", with_info=False, with_flags=False,
-                 action_order=None, **_):
+                 action_order=None, remove_redundant_gensets=True, **_):
         self.configs, self.env_config = list(configs), np.asarray(env_config, dtype=np.int64)
         if len({c.arch for c in self.configs}) != 1:
             raise NotImplementedError("the CPU stand-in holds one architecture group")
@@ -44,7 +44,8 @@ class OracleBackedEngine:
             col += 2 if m == "genset" else 1
         n = self.n_envs
         self.action_tables = [PL.priority_lists(c.has_genset, c.has_grid,
-                                                c.genset.running_min_production if c.has_genset else None) for c in self.configs]
+                                                c.genset.running_min_production if c.has_genset else None,
+                                                remove_redundant_gensets) for c in self.configs]
         self._g = SimpleNamespace(
             arch=p.arch, env_ids=np.arange(n), n_act=p.n_act, obs_dim=p.obs_dim, act_cols=cols, n_envs=n,
             step=torch.zeros(n, dtype=torch.int32), charge=torch.zeros(n, dtype=torch.float64),

@@ -60,7 +60,9 @@ class Variant:
         modules += [RenewableModule(time_series=ts) for ts in split_positive(rng, self.pv, self.n_pvs)]
         if callable(library):          # resolved when a test runs, not when the module is collected
             library = library()
-        kw = {} if library is None else {"_library": library}
+        from tests.hostsim import select
+        select(library)        # the host build of the kernel source (CPU suite) or, with None, the product's CUDA library
+        kw = {}
         self.microgrid = pymgrid_b200.Microgrid(modules, **kw)
         if shaped:      # rebuilt from the first microgrid's own modules, slack module included
             self.microgrid = pymgrid_b200.Microgrid(self.microgrid.modules.to_tuples(), add_unbalanced_module=False,

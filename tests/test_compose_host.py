@@ -16,9 +16,13 @@ from tests.compose_checks import CASES
 
 
 
-@pytest.fixture(scope="module")
+@pytest.fixture
 def lib():
-    return ctypes.CDLL(hostsim.build())
+    """the host build of the kernel source, selected for the duration of one test (tests/hostsim.select)"""
+    L = ctypes.CDLL(hostsim.build())
+    hostsim.select(L)
+    yield L
+    hostsim.select(None)
 
 
 @pytest.mark.parametrize("order", ["container", "gym_sorted"])
@@ -29,8 +33,8 @@ def test_composed_microgrid_reproduces_reference(case, order, lib):
 
 def test_gym_sorted_order_is_a_permutation_by_name(lib):
     case = next(c for c in CASES if c.label == "custom_names")
-    a = ComposedMicrogrid(case.modules(), obs_order="container", _library=lib, **case.microgrid_kwargs)
-    b = ComposedMicrogrid(case.modules(), obs_order="gym_sorted", _library=lib, **case.microgrid_kwargs)
+    a = ComposedMicrogrid(case.modules(), obs_order="container", **case.microgrid_kwargs)
+    b = ComposedMicrogrid(case.modules(), obs_order="gym_sorted", **case.microgrid_kwargs)
     # capital letters sort first: 'Abat', 'PV', then 'unbalanced_energy' (empty), 'wind', 'zload'
     assert [s.name for s in sorted(b.composition.slots, key=lambda s: s.obs_off) if s.obs_len] == ["Abat", "PV", "wind", "zload"]
     ra, rb = a._batch.observe()[0].numpy(), b._batch.observe()[0].numpy()
@@ -49,11 +53,11 @@ def test_layout_validation_and_scope(lib):
     fused = next(c for c in CASES if c.label == "past_the_end")
     assert in_fused_scope(fused.modules(), add_unbalanced_module=False)
     with pytest.raises(ValueError):     # different compositions in one batch
-        ComposedBatch([case.modules(), next(c for c in CASES if c.label == "load_only").modules()], _library=lib)
+        ComposedBatch([case.modules(), next(c for c in CASES if c.label == "load_only").modules()])
     comp = Composition(case.modules(), obs_order="container")
     assert comp.n_act == 4 and comp.obs_dim == 4 + 1 + 2 + 4 + 4 * 6
     assert [s.kind for s in comp.dispatch] == ["load", "genset", "battery", "grid", "renewable", "balancing"]
-    b = ComposedBatch([comp], _library=lib)
+    b = ComposedBatch([comp])
     with pytest.raises(ValueError):
         b.step(np.zeros((1, 3)))
     # a module table the library must refuse: dispatch order broken
@@ -68,9 +72,10 @@ def test_layout_validation_and_scope(lib):
 
 
 def test_product_path_needs_cuda():
-    """no _library, no GPU in this container: constructing the product path must fail loudly, never fall back"""
+    """no host library selected, no GPU in this container: constructing the product path must fail loudly, never fall back"""
     if torch.cuda.is_available():
         pytest.skip("CUDA device present")
+    hostsim.select(None)
     case = next(c for c in CASES if c.label == "load_pv")
     with pytest.raises(_cabi.EngineError):
         ComposedMicrogrid(case.modules())
@@ -91,19 +96,19 @@ def test_env_and_controller_constructors_route_to_the_composed_path(lib):
     from pymgrid_b200.compose import ComposedContinuousEnv, ComposedDiscreteEnv, ComposedRuleBasedControl
     from pymgrid_b200.envs import ContinuousMicrogridEnv, DiscreteMicrogridEnv
     case = next(c for c in K.DISCRETE_CASES if c.label == "two_batteries_grid")
-    env = DiscreteMicrogridEnv(case.modules(), _library=lib)
+    env = DiscreteMicrogridEnv(case.modules())
     assert isinstance(env, ComposedDiscreteEnv) and env.action_space.n == 6
     obs = env.reset()
     assert obs.shape == env.observation_space.shape and ((0 <= obs) & (obs <= 1)).all()
     obs, reward, done, info = env.step(env.sample_action())
     assert isinstance(reward, float) and isinstance(done, bool) and set(info) == {"load", "renewable", "battery", "grid", "balancing"}
-    cenv = ContinuousMicrogridEnv(case.modules(), batch=7, _library=lib)
+    cenv = ContinuousMicrogridEnv(case.modules(), batch=7)
     assert isinstance(cenv, ComposedContinuousEnv) and cenv.action_space.shape == (3,)
     assert cenv.action_layout == {("battery", 0): 0, ("battery", 1): 1, ("grid", 0): 2}
     obs, reward, done, _ = cenv.step(cenv.sample_action())
     assert obs.shape == (7, cenv.observation_space.shape[0]) and reward.shape == (7,)
-    single = ContinuousMicrogridEnv(case.modules(), _library=lib)
-    mg = pymgrid_b200.Microgrid(case.modules(), _library=lib)
+    single = ContinuousMicrogridEnv(case.modules())
+    mg = pymgrid_b200.Microgrid(case.modules())
     a = np.array([0.3, 0.8, 0.55])
     o1, r1, d1, _ = single.step(a)
     _, r2, d2, _ = mg.run({"battery": [0.3, 0.8], "grid": [0.55]})

@@ -77,6 +77,7 @@ def test_random_compositions_against_the_live_reference():
     from pymgrid_b200 import modules as M
     from pymgrid_b200.compose import ComposedMicrogrid
     lib = ctypes.CDLL(hostsim.build())
+    hostsim.select(lib)
     checked_steps = raised = built = logs = 0
     kinds = set()
     for g in range(N_GRIDS):
@@ -89,7 +90,7 @@ def test_random_compositions_against_the_live_reference():
                 continue
             mods = draw(np.random.default_rng(9000 + g), M, T)
             orc = ComposedOracle(mods, add_unbalanced_module=False)
-            ours = ComposedMicrogrid(mods, add_unbalanced_module=False, obs_order="container", _library=lib)
+            ours = ComposedMicrogrid(mods, add_unbalanced_module=False, obs_order="container")
         built += 1
         order = [(name, j) for name, lst in ref.modules.iterdict() for j in range(len(lst))]
         assert order == [(m.name, m.index) for m in orc.listing] == [(s.name, s.index) for s in ours.composition.slots], g
@@ -156,6 +157,7 @@ def test_random_compositions_priority_lists_against_the_live_reference():
     from pymgrid_b200 import modules as M
     from pymgrid_b200.compose import MAX_PRIORITY_ELEMENTS, ComposedDiscreteEnv, ComposedMicrogrid
     lib = ctypes.CDLL(hostsim.build())
+    hostsim.select(lib)
     rows = lambda pls: [[(el.module[0], el.module[1], el.module_actions, el.action) for el in pl] for pl in pls]      # noqa: E731
     compared = steps = 0
     for g in range(40):
@@ -173,7 +175,7 @@ def test_random_compositions_priority_lists_against_the_live_reference():
             except Exception:      # noqa: BLE001
                 continue
             ours_env = {f: ComposedDiscreteEnv(draw(np.random.default_rng(7000 + g), M, T), add_unbalanced_module=False,
-                                               remove_redundant_gensets=f, obs_order="container", _library=lib) for f in (False, True)}
+                                               remove_redundant_gensets=f, obs_order="container") for f in (False, True)}
         assert n_el <= MAX_PRIORITY_ELEMENTS
         for f in (False, True):
             assert rows(ours_env[f].actions_list) == rows(ref_env[f].actions_list), (g, f)
@@ -200,7 +202,7 @@ def test_random_compositions_priority_lists_against_the_live_reference():
             warnings.simplefilter("ignore")
             ref_rbc = RuleBasedControl(pymgrid.Microgrid(draw(np.random.default_rng(7000 + g), R, T), add_unbalanced_module=False))
             ours_rbc = pymgrid_b200.algos.RuleBasedControl(ComposedMicrogrid(draw(np.random.default_rng(7000 + g), M, T),
-                                                                            add_unbalanced_module=False, _library=lib))
+                                                                            add_unbalanced_module=False))
         assert rows([ours_rbc.priority_list]) == rows([ref_rbc.priority_list]), g
         try:
             want = ref_rbc.run(max_steps=12)
@@ -224,7 +226,7 @@ def test_random_modules_on_their_own_against_the_live_reference():
     import pymgrid.modules as R
     import pymgrid_b200.compose as cp
     from pymgrid_b200 import modules as M
-    saved, cp._STANDALONE_LIBRARY = cp._STANDALONE_LIBRARY, ctypes.CDLL(hostsim.build())
+    hostsim.select(ctypes.CDLL(hostsim.build()))
     compared = raised = 0
     try:
         for g in range(25):
@@ -262,7 +264,7 @@ def test_random_modules_on_their_own_against_the_live_reference():
                     assert np.array_equal(np.asarray(o0, dtype=np.float64).ravel(), o1), (g, kind, k)
                     compared += 1
     finally:
-        cp._STANDALONE_LIBRARY = saved
+        hostsim.select(None)
     print(f"{compared} module steps compared, {raised} runs ended where the reference raised")
     assert compared > 2000 and raised > 20
 
@@ -282,6 +284,7 @@ def test_composed_module_views_against_the_live_reference():
              "co2_per_kwh", "grid_status", "forecast_horizon", "max_capacity", "efficiency", "running_max_production", "max_import",
              "loss_load_cost", "current_load", "current_renewable")
     lib = ctypes.CDLL(hostsim.build())
+    hostsim.select(lib)
     compared = 0
     for g in range(30):
         T = 30
@@ -291,7 +294,7 @@ def test_composed_module_views_against_the_live_reference():
                 ref = pymgrid.Microgrid(draw(np.random.default_rng(3000 + g), R, T), add_unbalanced_module=False)
             except Exception:      # noqa: BLE001
                 continue
-            ours = ComposedMicrogrid(draw(np.random.default_rng(3000 + g), M, T), add_unbalanced_module=False, _library=lib)
+            ours = ComposedMicrogrid(draw(np.random.default_rng(3000 + g), M, T), add_unbalanced_module=False)
         rng = np.random.default_rng(g)
         for k in range(3):
             a = {name: [rng.random(m.action_space.shape[0]) if m.action_space.shape[0] > 1 else rng.random() for m in lst]

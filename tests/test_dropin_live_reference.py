@@ -65,6 +65,13 @@ def test_microgrid_surface_against_the_live_reference(n):
     assert np.array_equal(s1.to_numpy(dtype=np.float64), s2.to_numpy(dtype=np.float64))
     sd1, sd2 = ref.state_dict(), ours.state_dict()
     assert {k: [dict(d) for d in v] for k, v in sd1.items()} == {k: [dict(d) for d in v] for k, v in sd2.items()}
+    # normalized=True (what BaseMicrogridEnv._get_obs reads, envs/base/base.py:211-218): every module through its own space
+    n1, n2 = ref.state_dict(normalized=True), ours.state_dict(normalized=True)
+    assert {k: [{f: float(x) for f, x in d.items()} for d in v] for k, v in n1.items()} == \
+           {k: [{f: float(x) for f, x in d.items()} for d in v] for k, v in n2.items()}, (n, "state_dict(normalized=True)")
+    t1, t2 = ref.state_series(normalized=True), ours.state_series(normalized=True)
+    assert [tuple(map(str, i)) for i in t1.index] == [tuple(map(str, i)) for i in t2.index]
+    assert np.array_equal(t1.to_numpy(dtype=np.float64), t2.to_numpy(dtype=np.float64)), (n, "state_series(normalized=True)")
     c1, c2 = ref.get_cost_info(), ours.get_cost_info()
     assert {k: [dict(d) for d in v] for k, v in c1.items()} == {k: [dict(d) for d in v] for k, v in c2.items()}
     r1, r2 = ref.reset(), ours.reset()
@@ -136,7 +143,8 @@ def test_random_fused_microgrids_built_from_modules_against_the_live_reference(g
     from pymgrid_b200.compose import in_fused_scope
     from tests import hostsim
     T = 40
-    extra = lambda mods: {} if in_fused_scope(mods) else {"_library": ctypes.CDLL(hostsim.build())}      # noqa: E731
+    hostsim.select(ctypes.CDLL(hostsim.build()))      # lists outside the fused scope run on the host build of the composed kernel
+    extra = lambda mods: {}      # noqa: E731
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         m1, kw = draw_fused(np.random.default_rng(600 + g), R, T)
@@ -201,7 +209,8 @@ def test_random_fused_discrete_envs_against_the_live_reference(g):
         m2, _ = draw_fused(np.random.default_rng(800 + g), M, T)
         if any(isinstance(m, tuple) and m[0] == "PV" for m in m2) and in_fused_scope(m2):
             pytest.skip("the CPU stand-in has no 'PV'-first observation order (the engine has: MG_OBS_GYM_SORTED_PV_FIRST)")
-        extra = {} if in_fused_scope(m2) else {"_library": ctypes.CDLL(hostsim.build())}
+        hostsim.select(ctypes.CDLL(hostsim.build()))
+        extra = {}
         ref, ours = RefEnv(m1, **kw), DiscreteMicrogridEnv(m2, **extra, **kw)
     rows = lambda pls: [[(el.module, el.module_actions, el.action, el.marginal_cost) for el in pl] for pl in pls]      # noqa: E731
     assert rows(ref.actions_list) == rows(ours.actions_list) and ref.action_space.n == ours.action_space.n
@@ -323,3 +332,68 @@ def test_random_fused_microgrids_with_shaper_and_trajectory_against_the_live_ref
         assert (s1 == s2 or (np.isnan(s1) and np.isnan(s2))) and d1 == d2, (g, k, s1, s2)
         assert d1 == (5 + k >= 24)
         same_nested(o1, o2, (g, k, "obs"))
+
+
+def test_discrete_env_keeps_redundant_genset_lists_when_asked():
+    """DiscreteMicrogridEnv(remove_redundant_gensets=False) (envs/discrete/discrete.py:60-80; priority_list.py:15-67): a genset
+    whose running_min_production is 0 makes the genset-off lists redundant -- with the flag off they stay, so the action
+    space, and what an action index means, match the reference's."""
+    from oracle.ref_loader import load_reference
+    load_reference()
+    import pymgrid
+    from pymgrid import envs as ref_envs
+    import pymgrid_b200.modules as M
+    from pymgrid_b200.envs import DiscreteMicrogridEnv
+
+    def modules(lib):
+        rng = np.random.default_rng(4)
+        load, pv = 40 + 20 * rng.random(60), 30 * rng.random(60)
+        return [lib.LoadModule(time_series=load), lib.RenewableModule(time_series=pv),
+                lib.GensetModule(running_min_production=0, running_max_production=60, genset_cost=0.4),
+                lib.BatteryModule(min_capacity=10, max_capacity=100, max_charge=30, max_discharge=30, efficiency=0.9, init_soc=0.5)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for flag in (True, False):
+            ref = ref_envs.DiscreteMicrogridEnv(modules(pymgrid.modules), remove_redundant_gensets=flag)
+            ours = DiscreteMicrogridEnv(modules(M), remove_redundant_gensets=flag)
+            assert ref.action_space.n == ours.action_space.n, flag
+            assert [[(e.module, e.module_actions, e.action) for e in a] for a in ref.actions_list] == \
+                   [[(e.module, e.module_actions, e.action) for e in a] for a in ours.actions_list], flag
+            ref.reset(), ours.reset()
+            for a in range(ref.action_space.n):
+                o1, r1, d1, _ = ref.step(a)
+                o2, r2, d2, _ = ours.step(a)
+                assert r1 == r2 and d1 == d2, (flag, a)
+                assert np.array_equal(np.asarray(o1, dtype=np.float64), np.asarray(o2, dtype=np.float64)), (flag, a)
+
+
+def test_single_env_raises_where_the_reference_raises():
+    """One microgrid behind an env: stepping past the end of the series raises IndexError like the reference's env (a batch
+    reports the event per env through `flags` and a NaN reward instead); observation_keys=None is the reference's default."""
+    from oracle.ref_loader import load_reference
+    load_reference()
+    import pymgrid
+    from pymgrid import envs as ref_envs
+    import pymgrid_b200.modules as M
+    from pymgrid_b200.envs import DiscreteMicrogridEnv
+
+    def modules(lib):
+        rng = np.random.default_rng(6)
+        load, pv = 40 + 20 * rng.random(30), 30 * rng.random(30)
+        return [lib.LoadModule(time_series=load), lib.RenewableModule(time_series=pv),
+                lib.GensetModule(running_min_production=5, running_max_production=60, genset_cost=0.4),
+                lib.BatteryModule(min_capacity=10, max_capacity=100, max_charge=30, max_discharge=30, efficiency=0.9, init_soc=0.5)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ref_envs.DiscreteMicrogridEnv(modules(pymgrid.modules))
+        ours = DiscreteMicrogridEnv(modules(M), observation_keys=None)
+    ref.reset(), ours.reset()
+    for k in range(30):
+        _, r1, d1, _ = ref.step(k % ref.action_space.n)
+        _, r2, d2, _ = ours.step(k % ours.action_space.n)
+        assert r1 == r2 and d1 == d2, k
+    assert d1 and d2
+    with pytest.raises(IndexError):
+        ref.step(0)
+    with pytest.raises(IndexError):
+        ours.step(0)

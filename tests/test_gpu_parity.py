@@ -594,6 +594,46 @@ def test_trajectory_windows_and_masked_reset():
     np.testing.assert_array_equal(after[1::2], before.cpu().numpy()[1::2])
 
 
+def test_set_trajectories_keeps_the_handle_and_bound_launchers():
+    """mg_set_trajectories swaps the per-env window arrays inside the handle: a launcher bound BEFORE the windows change (what
+    HostIO / HostRollout / prepare_step keep) stays valid and honours the new windows, options survive, and the launch
+    counter keeps counting (the handle used to be destroyed and re-created here: a use-after-free for bound launchers)."""
+    p = load_pymgrid25(1)
+    B = 200
+    bm = engine([p], np.zeros(B, dtype=np.int64))
+    bm.set_image_shape(1)
+    acts = torch.rand((B, 4), dtype=torch.float64, device="cuda")
+    launch = bm.prepare_step(acts)                       # bound to the handle as it is now
+    hio = bm.host_io()
+    handle_before, launches_before = bm._handle.value, bm.launch_count
+    launch()
+    rng = np.random.default_rng(3)
+    initial = rng.integers(100, 8000, B).astype(np.int32)
+    length = rng.integers(2, 6, B).astype(np.int32)
+    bm.set_trajectories(initial, initial + length)
+    assert bm._handle.value == handle_before and bm.launch_count == launches_before + 1
+    assert bm._options[4] == 1                            # MG_OPT_IMAGE_SHAPE kept
+    bm.reset()
+    assert torch.equal(bm.groups[0].step.cpu(), torch.from_numpy(initial))
+    steps_to_done, alive = np.zeros(B, dtype=np.int64), np.ones(B, dtype=bool)
+    for k in range(6):
+        launch()                                          # the OLD launcher
+        d = bm.groups[0].done.cpu().numpy().astype(bool)
+        steps_to_done[alive & d] = k + 1
+        alive &= ~d
+    np.testing.assert_array_equal(steps_to_done, length)
+    hio.actions[0].uniform_(0, 1)
+    hio.step()
+    hio.sync()
+    assert bm.last_kernel == "mg_step_img_kernel"         # windows installed: the ragged hint switched the emitters
+    # a second change of windows, then back to the configs' own window
+    bm.set_trajectories(np.zeros(B, dtype=np.int32), np.full(B, 3, dtype=np.int32))
+    bm.reset()
+    for k in range(3):
+        launch()
+    assert bool(bm.groups[0].done.all()) and int(bm.groups[0].step.max()) == 3
+
+
 def test_bad_discrete_action_is_flagged():
     p = load_pymgrid25(0)
     bm = engine([p], np.zeros(4, dtype=np.int64))

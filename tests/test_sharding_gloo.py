@@ -83,7 +83,8 @@ def _composed_worker(rank, world, port, global_batch, n_steps, out_q):
     case = next(c for c in load_cases() if c.label == "several_of_each")
     configs = [case.modules(), case.modules()]
     env_config, ids = shard_env_config(np.arange(global_batch) % 2, rank, world)
-    batch = ComposedBatch(configs, env_config, microgrid_kwargs=case.microgrid_kwargs, _library=ctypes.CDLL(hostsim.build()))
+    hostsim.select(ctypes.CDLL(hostsim.build()))
+    batch = ComposedBatch(configs, env_config, microgrid_kwargs=case.microgrid_kwargs)
     actions = np.random.default_rng(5).random((n_steps, global_batch, batch.comp.n_act))[:, ids]
     out = batch.rollout(torch.from_numpy(np.ascontiguousarray(actions)), obs=False)
     per_step = out["reward"].sum(dim=1)
@@ -112,8 +113,8 @@ def test_two_rank_composed_batch_matches_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     case = next(c for c in load_cases() if c.label == "several_of_each")
-    batch = ComposedBatch([case.modules(), case.modules()], np.arange(global_batch) % 2, microgrid_kwargs=case.microgrid_kwargs,
-                          _library=ctypes.CDLL(hostsim.build()))
+    hostsim.select(ctypes.CDLL(hostsim.build()))
+    batch = ComposedBatch([case.modules(), case.modules()], np.arange(global_batch) % 2, microgrid_kwargs=case.microgrid_kwargs)
     actions = np.random.default_rng(5).random((n_steps, global_batch, batch.comp.n_act))
     want = batch.rollout(torch.from_numpy(actions), obs=False)["reward"].numpy()
     assert np.array_equal(rank0_rewards, want[:, rank0_ids])     # a shard computes exactly its slice of the global batch
