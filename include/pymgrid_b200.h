@@ -27,10 +27,11 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 1
+#define MG_ABI_VERSION 2
 #define MG_MAX_GROUPS 8
 #define MG_N_INFO 16
 #define MG_PLIST_WIDTH 3
+#define MG_N_LOG 24
 
 /* return codes */
 enum {
@@ -208,7 +209,21 @@ typedef struct MgRolloutIO {
     uint32_t *flags;         /* [n] OR over the rollout, or NULL                                              */
     int64_t dactions_const;  /* != 0: the same priority list every step -- rule-based control (algos/rbc/rbc.py:64-93) */
     double *reward_total;    /* [n_steps] or NULL: [s] += sum over the group of step s's rewards (see MgStepIO)        */
+    /* Per-step log of SELECTED envs, written inside the persistent kernel (the reference's Microgrid.get_log, microgrid.py:
+       434-475, and ModularLogger, utils/logger.py:18-28; a full log of every env is 169-176 columns per env-step and cannot
+       be always-on at batch scale).  log_slot: [n] int32, -1 = not logged, else the env's row r of `log`;
+       log: [n_logged, n_steps, MG_N_LOG] f64, columns MG_LOG_* -- what the host needs to rebuild the reference's log row:
+       the state BEFORE the step (step counter, battery charge, packed genset status), the genset status AFTER it (the
+       reference logs that one, genset_module.py:148-149), reward, done, flags and the MG_N_INFO info columns.  NULL = no log. */
+    const int32_t *log_slot;
+    double *log;
 } MgRolloutIO;
+
+/* columns of one log record (MgRolloutIO.log) */
+enum {
+    MG_LOG_STEP = 0, MG_LOG_CHARGE = 1, MG_LOG_GENSET_BEFORE = 2, MG_LOG_GENSET_AFTER = 3, MG_LOG_REWARD = 4, MG_LOG_DONE = 5,
+    MG_LOG_FLAGS = 6, /* 7 reserved */ MG_LOG_INFO = 8 /* .. 23: MG_INFO_* */
+};
 
 typedef struct MgHandle MgHandle;
 

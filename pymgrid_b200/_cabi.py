@@ -8,9 +8,11 @@ import os
 
 from . import build as _build
 
-MG_ABI_VERSION = 1
+MG_ABI_VERSION = 2
 MG_MAX_GROUPS = 8
 MG_N_INFO = 16
+MG_N_LOG = 24
+MG_LOG_STEP, MG_LOG_CHARGE, MG_LOG_GENSET_BEFORE, MG_LOG_GENSET_AFTER, MG_LOG_REWARD, MG_LOG_DONE, MG_LOG_FLAGS, MG_LOG_INFO = 0, 1, 2, 3, 4, 5, 6, 8
 MG_PLIST_WIDTH = 3
 MG_OBS_GYM_SORTED, MG_OBS_CONTAINER, MG_OBS_GYM_SORTED_PV_FIRST = 0, 1, 2
 MG_MOD_NONE, MG_MOD_GENSET, MG_MOD_BATTERY, MG_MOD_GRID = -1, 0, 1, 2
@@ -79,7 +81,8 @@ class MgStepIO(C.Structure):
 
 class MgRolloutIO(C.Structure):
     _fields_ = [("actions", _vp), ("dactions", _vp), ("obs_ring", _vp), ("reward", _vp), ("done", _vp),
-                ("reward_sum", _vp), ("flags", _vp), ("dactions_const", C.c_int64), ("reward_total", _vp)]
+                ("reward_sum", _vp), ("flags", _vp), ("dactions_const", C.c_int64), ("reward_total", _vp),
+                ("log_slot", _vp), ("log", _vp)]
 
 
 class MgHostRolloutIO(C.Structure):

@@ -83,6 +83,8 @@ struct DevGroup {
     // rollout io
     double *reward_sum;
     int64_t act_step_stride, out_step_stride, obs_slot_stride, dact_step_stride;
+    const int32_t *log_slot;            // rollout log of selected envs (MgRolloutIO.log_slot / log)
+    double *log;
 };
 
 struct LaunchParams {
@@ -1162,6 +1164,27 @@ __device__ __forceinline__ uint32_t pack_genset(const EnvRegs &s) {
     return (uint32_t)s.cs | ((uint32_t)s.gs << 8) | ((uint32_t)s.up << 16) | ((uint32_t)s.dn << 24);
 }
 
+// Rollout log of selected envs (MgRolloutIO.log): log_open writes the state BEFORE the step and returns the record (or
+// nullptr: env not logged), whose info block owner_step fills; log_close adds what is known after the step.
+__device__ __forceinline__ double *log_open(const DevGroup &G, int slot, int step, int n_steps, const EnvRegs &s) {
+    if (slot < 0) return nullptr;
+    double *rec = G.log + ((size_t)slot * n_steps + step) * MG_N_LOG;
+    rec[MG_LOG_STEP] = (double)s.t;
+    rec[MG_LOG_CHARGE] = s.charge;
+    rec[MG_LOG_GENSET_BEFORE] = (double)pack_genset(s);
+    return rec;
+}
+__device__ __forceinline__ void log_close(double *rec, const EnvRegs &s, double reward, int done, uint32_t flags, bool valid) {
+    if (!rec) return;
+    rec[MG_LOG_GENSET_AFTER] = (double)pack_genset(s);
+    rec[MG_LOG_REWARD] = reward;
+    rec[MG_LOG_DONE] = (double)done;
+    rec[MG_LOG_FLAGS] = (double)flags;
+    rec[7] = 0.0;
+    if (!valid)      // a rejected step (past the end, bad action) logs nothing in the reference: the info block stays empty
+        for (int q = 0; q < MG_N_INFO; ++q) rec[MG_LOG_INFO + q] = 0.0;
+}
+
 __device__ __forceinline__ int find_group(const LaunchParams &P, int tile) {
     int g = 0;
 #pragma unroll
@@ -1354,12 +1377,14 @@ __global__ void __launch_bounds__(MG_THREADS, kRing ? MG_MIN_CTAS_RING : kHetero
     uint32_t fsum = 0;
     uint32_t phase = 0;
     if ((tid & 31) == 0 && G.obs) mbar_init(&S.bar[tid >> 5], 1);
+    int log_slot = -1;
     if (owner) {
         c = P.cfg + __ldg(G.cfg_index + e);
         s.t = G.step[e];
         s.charge = G.charge[e];
         if (G.has_genset) unpack_genset(G.genset[e], s);
         final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
+        if (G.log_slot && G.log) log_slot = __ldg(G.log_slot + e);
     }
     // ring variant: fill every special env's windows for its current step [t, t + H], one env per warp pass, lane k = window
     // element k (the only place where a whole window is normalised); the owner then appends one value per step
@@ -1396,7 +1421,9 @@ __global__ void __launch_bounds__(MG_THREADS, kRing ? MG_MIN_CTAS_RING : kHetero
             double reward;
             int done;
             uint32_t flags;
-            owner_step(P, G, c, s, in, final_step, nullptr, reward, done, flags);
+            double *const log_rec = log_open(G, log_slot, step, P.n_steps, s);
+                owner_step(P, G, c, s, in, final_step, log_rec ? log_rec + MG_LOG_INFO : nullptr, reward, done, flags);
+                log_close(log_rec, s, reward, done, flags, in.valid);
             G.reward[(size_t)step * G.out_step_stride + e] = reward;
             G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)done;
             rsum += reward;
@@ -1488,12 +1515,14 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
         int final_step = 0;
         double rsum = 0.0;
         uint32_t fsum = 0;
+        int log_slot = -1;
         if (owner) {
             c = P.cfg + __ldg(G.cfg_index + e);
             s.t = G.step[e];
             s.charge = G.charge[e];
             if (G.has_genset) unpack_genset(G.genset[e], s);
             final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
+            if (G.log_slot && G.log) log_slot = __ldg(G.log_slot + e);
         }
         for (int step = 0; step < P.n_steps; ++step) {
             const int ebuf = step & 1;
@@ -1507,7 +1536,9 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
                 double reward;
                 int done;
                 uint32_t flags;
-                owner_step(P, G, c, s, in, final_step, nullptr, reward, done, flags);
+                double *const log_rec = log_open(G, log_slot, step, P.n_steps, s);
+                owner_step(P, G, c, s, in, final_step, log_rec ? log_rec + MG_LOG_INFO : nullptr, reward, done, flags);
+                log_close(log_rec, s, reward, done, flags, in.valid);
                 rsum += reward;
                 fsum |= flags;
                 my_reward = reward;
@@ -1706,11 +1737,13 @@ __global__ void __launch_bounds__(MG_THREADS, MINB ? MINB : !kWS ? MG_IMG_MIN_CT
         bool ring_env = false;
         double rsum = 0.0;
         uint32_t fsum = 0;
+        int log_slot = -1;
         if (owner) {
             s.t = G.step[e];
             s.charge = G.charge[e];
             if (G.has_genset) unpack_genset(G.genset[e], s);
             final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
+            if (G.log_slot && G.log) log_slot = __ldg(G.log_slot + e);
             if (kRing) {
                 ring_env = env_is_special(c, G);
                 ring_base = min(s.t, P.T) % ring_R;
@@ -1761,7 +1794,9 @@ __global__ void __launch_bounds__(MG_THREADS, MINB ? MINB : !kWS ? MG_IMG_MIN_CT
                 double reward;
                 int done;
                 uint32_t flags;
-                owner_step(P, G, c, s, in, final_step, nullptr, reward, done, flags);
+                double *const log_rec = log_open(G, log_slot, step, P.n_steps, s);
+                owner_step(P, G, c, s, in, final_step, log_rec ? log_rec + MG_LOG_INFO : nullptr, reward, done, flags);
+                log_close(log_rec, s, reward, done, flags, in.valid);
                 rsum += reward;
                 fsum |= flags;
                 my_reward = reward;
@@ -2422,6 +2457,7 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
         d.actions = io[g].actions; d.dactions = io[g].dactions; d.obs = io[g].obs; d.reward = io[g].reward;
         d.done = io[g].done; d.info = io[g].info; d.flags = io[g].flags; d.mask = io[g].mask;
         d.reward_total = io[g].reward_total;
+        d.log_slot = nullptr; d.log = nullptr;
         d.soc_reported = (mode == MODE_OBSERVE || mode == MODE_RESET) ? h->soc_reported[g] : nullptr;
         if (mode == MODE_STEP && !d.actions) return fail(MG_E_INVALID, "mg_step: null actions");
         if (mode == MODE_DISCRETE && (!d.dactions || !P.plist)) return fail(MG_E_INVALID, "mg_step_discrete: null actions or priority lists");
@@ -2502,6 +2538,8 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
         d.actions = io[g].actions; d.dactions = io[g].dactions; d.obs = io[g].obs_ring; d.reward = io[g].reward;
         d.done = io[g].done; d.reward_sum = io[g].reward_sum; d.flags = io[g].flags; d.info = nullptr; d.mask = nullptr;
         d.reward_total = io[g].reward_total;
+        d.log_slot = io[g].log_slot; d.log = io[g].log;
+        if ((d.log_slot != nullptr) != (d.log != nullptr)) return fail(MG_E_INVALID, "rollout: log_slot and log go together");
         d.act_step_stride = (int64_t)d.n_envs * d.n_act;
         d.out_step_stride = d.n_envs;
         d.dact_step_stride = io[g].dactions_const ? 0 : d.n_envs;

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import (MgForecastNoise, MG_ABI_VERSION, MG_MAX_GROUPS, MG_N_INFO, MG_OBS_CONTAINER, MG_OBS_GYM_SORTED, EngineError,
+from ._cabi import (MgForecastNoise, MG_ABI_VERSION, MG_MAX_GROUPS, MG_N_INFO, MG_N_LOG, MG_OBS_CONTAINER, MG_OBS_GYM_SORTED, EngineError,
                     MgConfig, MgHostRolloutIO, MgLayout, MgPriorityList, MgRolloutIO, MgStepIO)
 from .params import REWARD_SHAPERS, MicrogridParams
 from .priority_list import priority_lists
@@ -413,6 +413,42 @@ class LogRecorder:
     def flush(self):
         self.rows = {e: [] for e in self.env_ids}
         self.first_step = {}
+
+
+class RolloutLog:
+    """The reference-format log of the envs selected with `rollout(..., log_envs=ids)`: the persistent kernel wrote one
+    record per selected env and step into a device buffer ([n_logged, n_steps, MG_N_LOG] per group: state before the step,
+    genset status after it, reward, done, flags, info columns -- include/pymgrid_b200.h, MG_LOG_*); `get_log(env_id)`
+    brings that env's records to the host in ONE copy and builds the DataFrame `Microgrid.get_log()` returns
+    (microgrid/microgrid.py:434-475: same MultiIndex columns, same values, index = the steps taken)."""
+
+    def __init__(self, bm, env_ids, buffers, rows, n_steps, pristine):
+        self.bm, self.env_ids, self.n_steps = bm, [int(e) for e in env_ids], n_steps
+        self._buffers, self._rows, self._pristine = buffers, rows, pristine      # per group tensors; env id -> (group, row)
+
+    def records(self, env_id):
+        """[n_steps, MG_N_LOG] numpy array of one env (columns MG_LOG_*)"""
+        gi, row = self._rows[int(env_id)]
+        return self._buffers[gi][row].cpu().numpy()
+
+    def get_log(self, env_id, drop_singleton_key=False):
+        from . import views
+        if self.bm.configs is None:
+            raise ValueError("get_log needs per-config MicrogridParams (array-form batches: use records())")
+        rec = self.records(env_id)
+        p = self.bm.configs[self.bm.env_config[int(env_id)]]
+        unpack = lambda w: (int(w) & 0xff, (int(w) >> 8) & 0xff, (int(w) >> 16) & 0xff, (int(w) >> 24) & 0xff)   # noqa: E731
+        rows = []
+        for k in range(len(rec)):
+            r = rec[k]
+            if int(r[_cabi.MG_LOG_FLAGS]) & ((1 << 5) | (1 << 6)):      # a rejected step logs nothing (the reference raises there)
+                break
+            state = views.state_dict(p, int(r[_cabi.MG_LOG_STEP]), float(r[_cabi.MG_LOG_CHARGE]), unpack(r[_cabi.MG_LOG_GENSET_BEFORE]),
+                                     p.battery.soc if (self._pristine and k == 0) else None)
+            rows.append(views.log_row(p, state, r[_cabi.MG_LOG_INFO:_cabi.MG_LOG_INFO + MG_N_INFO], float(r[_cabi.MG_LOG_REWARD]),
+                                      unpack(r[_cabi.MG_LOG_GENSET_AFTER])))
+        stop = int(rec[len(rows) - 1][_cabi.MG_LOG_STEP]) + 1 if rows else 0
+        return views.log_frame(rows, stop, drop_singleton_key)
 
 
 class BatchedMicrogrid:
@@ -872,10 +908,12 @@ class BatchedMicrogrid:
         return self.rollout(actions, bind_only=True, **kw)
 
     def rollout(self, actions, normalized=True, discrete=False, ring=1, keep_obs=True, reward_sum=False, out=None,
-                constant_actions=False, n_steps=None, reward_total=None, bind_only=False):
+                constant_actions=False, n_steps=None, reward_total=None, bind_only=False, log_envs=None):
         """n_steps consecutive steps in one persistent kernel.  actions: per group [n_steps, n, n_act] float64
         (or [n_steps, n] int32 when discrete).  Returns dict(reward=[n_steps, n], done=..., obs_ring=[ring, n, D]);
-        pass a previous return value (list of dicts) as `out` to reuse its buffers."""
+        pass a previous return value (list of dicts) as `out` to reuse its buffers.
+        log_envs: global ids of envs whose per-step log the kernel records (reference: Microgrid.get_log); the log comes
+        back as `self.last_log` (a RolloutLog: `.get_log(env_id)` is the reference's DataFrame)."""
         if out is not None and isinstance(out, dict):
             out = [out]
         acts = self._per_group(actions, "actions")
@@ -904,6 +942,24 @@ class BatchedMicrogrid:
             io[gi].obs_ring, io[gi].reward, io[gi].done = _ptr(r["obs_ring"]), _ptr(r["reward"]), _ptr(r["done"])
             io[gi].reward_sum, io[gi].flags = _ptr(r["reward_sum"]), _ptr(g.flags)
             io[gi].reward_total = _ptr(reward_total)
+        log_keep = None
+        if log_envs is not None:
+            log_envs = [int(e) for e in log_envs]
+            rows, buffers, slots = {}, [], []
+            for gi, g in enumerate(self.groups):
+                mine = [e for e in log_envs if self.env_group[e] == gi]
+                slot = np.full(g.n_envs, -1, dtype=np.int32)
+                for r, e in enumerate(mine):
+                    slot[int(self.env_slot[e])] = r
+                    rows[e] = (gi, r)
+                buf = torch.zeros((max(len(mine), 1), n_steps, MG_N_LOG), dtype=torch.float64, device=self.device)
+                slot_dev = torch.from_numpy(slot).to(self.device)
+                if mine:
+                    io[gi].log_slot, io[gi].log = _ptr(slot_dev), _ptr(buf)
+                buffers.append(buf)
+                slots.append(slot_dev)
+            self.last_log = RolloutLog(self, log_envs, buffers, rows, n_steps, self._soc_pristine)
+            log_keep = (buffers, slots)
         lib, handle, norm, dev = self._lib, self._handle, int(bool(normalized)), self.device
         self._mark_stepped()
 
@@ -915,9 +971,10 @@ class BatchedMicrogrid:
                 _cabi.check(rc, "mg_rollout")
         result = outs[0] if self.single_group else outs
         if bind_only:      # the caller launches (repeatedly) with minimal host overhead; buffers are kept alive here
-            launch.keepalive = (io, acts, outs, reward_total)
+            launch.keepalive = (io, acts, outs, reward_total, log_keep)
             launch.result = result
             return launch
+        launch.keepalive = (io, acts, outs, reward_total, log_keep)
         launch()
         return result
 

@@ -522,3 +522,57 @@ def test_module_views_on_the_engine(golden, n):
     if m.params.has_genset:
         assert env.modules.genset[0].current_status == m.modules.genset[0].current_status
 
+
+
+@pytest.mark.parametrize("emit", ["lsu", "image"])
+def test_rollout_log_matches_reference_log(golden, emit):
+    """the persistent kernel records the log of SELECTED envs in a device buffer (MgRolloutIO.log) while it
+    rolls the whole batch; `RolloutLog.get_log(env)` rebuilds the reference's get_log() DataFrame -- columns, index, values
+    -- for envs of all three architectures in a mixed batch (both persistent kernel families)."""
+    from pymgrid_b200.engine import BatchedMicrogrid
+    z = golden["log"]
+    configs = [load_pymgrid25(n) for n in (0, 1, 2)]
+    B = 300
+    env_config = np.arange(B) % 3
+    bm = BatchedMicrogrid(configs, env_config, device="cuda:0", action_order=("genset", "battery", "grid"))
+    bm.set_emit_image(emit == "image")
+    watched = [0, 1, 2, 150, 151, 152, 299]
+    rng = np.random.default_rng(0)
+    n_steps = len(z["s0_actions"])
+    acts = []
+    for g in bm.groups:
+        a = rng.random((n_steps, g.n_envs, g.n_act))
+        for slot, e in enumerate(g.env_ids):
+            if e in watched:
+                a[:, slot] = z[f"s{env_config[e]}_actions"][:n_steps]
+        acts.append(torch.from_numpy(a).cuda())
+    bm.rollout(acts, ring=2, log_envs=watched)
+    log = bm.last_log
+    for e in watched:
+        n = env_config[e]
+        df = log.get_log(e)
+        assert ["|".join(map(str, c)) for c in df.columns] == list(z[f"s{n}_columns"])
+        np.testing.assert_array_equal(df.values.astype(float), z[f"s{n}_values"])
+        np.testing.assert_array_equal(df.index.values, z[f"s{n}_index"])
+    # the records themselves: the state before each step chains up with the step counter
+    rec = log.records(150)
+    np.testing.assert_array_equal(rec[:, 0], np.arange(n_steps))
+    assert rec.shape == (n_steps, 24)
+
+
+def test_full_year_rule_based_rollout_with_log(golden):
+    """A whole year of rule-based control in ONE persistent launch with the log of one env recorded on the device: 8 759
+    rows whose balance-reward column is the live reference's RuleBasedControl run (tests/golden/rbc.npz, total
+    -956 059.66), while 4 095 other envs roll along unlogged."""
+    from pymgrid_b200.engine import BatchedMicrogrid
+    z = golden["rbc"]
+    configs = [load_pymgrid25(n) for n in (0, 1, 2)]
+    B = 4096
+    bm = BatchedMicrogrid(configs, np.arange(B) % 3, device="cuda:0")
+    res = bm.rollout_rbc(8759, keep_obs=False, reward_sum=True, log_envs=[0, 3])
+    df = bm.last_log.get_log(0)
+    assert len(df) == 8759 and df.index[0] == 0 and df.index[-1] == 8758
+    np.testing.assert_array_equal(df[("balance", 0, "reward")].values.astype(float), z["s0_rewards"])
+    assert float(df[("balance", 0, "reward")].sum()) == float(z["s0_rewards"].sum())
+    same = bm.last_log.get_log(3)                      # env 3 is another replica of scenario 0
+    np.testing.assert_array_equal(same.values.astype(float), df.values.astype(float))
