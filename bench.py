@@ -605,7 +605,7 @@ def measure_workload(hx, workload, B, K, W, R, paths=("rollout", "graph", "eager
     #     Same bytes per step as (1); this is the headline e2e figure when it runs (any failure keeps (1) and says so).
     # Collectives (barrier, max over ranks) stay outside the try blocks so that a failure on one rank cannot hang the others.
     Kr = min(K, 1024)
-    chunk = max(1, min(64, Kr // 4))           # at least four chunks: the three-stream pipeline is exercised at any K
+    chunk = max(1, min(64, Kr // 8))           # at least eight chunks: the three-stream pipeline is exercised at any K
     del hio
     errors = {}
     for pipeline in ("native", "torch"):       # mg_rollout_host (one C-ABI call); else the same schedule from torch streams

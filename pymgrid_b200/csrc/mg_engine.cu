@@ -172,15 +172,6 @@ __device__ __forceinline__ void add_reward_total(double *total, double reward, b
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// IEEE f64 division with the zero numerator peeled off.  CUDA's div.rn.f64 sends a zero (or denormal) numerator to an
-// out-of-line slow path of ~100 instructions, and zero numerators are the common case here (no discharge, no sun at
-// night, an empty battery): measured, the slow path was 13% of all instructions of the per-env-series rollout kernel.
-// +-0 / den = +-0 (the numerator itself) for every den > 0, so the shortcut is bit-exact; anything else divides.
-__device__ __forceinline__ double div_f64(double num, double den) {
-    if (num == 0.0 && den > 0.0) return num;
-    return num / den;
-}
-
 __device__ __forceinline__ bool np_isclose(double a, double b, double rtol, double atol) {
     return fabs(a - b) <= (atol + rtol * fabs(b));
 }
@@ -276,7 +267,7 @@ __device__ __forceinline__ uint32_t priority_control(const MgPriorityList pl, co
             if (mod == MG_MOD_GENSET) energy = 0.0;
             else {
                 const double mc = (mod == MG_MOD_BATTERY)
-                                      ? div_f64(fmin(c->bat_max_charge, c->bat_max_capacity - s.charge), c->bat_efficiency)
+                                      ? fmin(c->bat_max_charge, c->bat_max_capacity - s.charge) / c->bat_efficiency
                                       : c->grid_max_export * raw.status;
                 if (!(mc >= 0)) flags |= MG_FLAG_NEGATIVE_ABSORB;
                 if (-1 * remaining > mc) energy = -1.0 * mc;
@@ -345,13 +336,13 @@ __device__ __forceinline__ void env_step(const MgConfig *__restrict__ c, const D
             double p;
             if (a > mp) { p = mp; flags |= MG_FLAG_CLIP_BATTERY; }
             else p = a;
-            internal = div_f64(-1.0 * p, c->bat_efficiency);
+            internal = (-1.0 * p) / c->bat_efficiency;
             provided += p;
             i_dis = p;
         } else {
             flags |= MG_FLAG_BATTERY_SINK;
             double e = -1.0 * a;
-            const double mc = div_f64(fmin(c->bat_max_charge, c->bat_max_capacity - s.charge), c->bat_efficiency);
+            const double mc = fmin(c->bat_max_charge, c->bat_max_capacity - s.charge) / c->bat_efficiency;
             if (e > mc) { e = mc; flags |= MG_FLAG_CLIP_BATTERY; }
             if (!(e >= 0)) flags |= MG_FLAG_NEGATIVE_ABSORB;
             internal = e * c->bat_efficiency;
@@ -505,17 +496,17 @@ __device__ __forceinline__ void publish_env(TileEnv &te, HeteroEnv *het, const M
         het->scaled = c->series_scaled; het->weak = c->grid_status_weak;
     }
     // battery_module.py:323-330, genset_module.py:503-509, utils/space.py:207-218
-    const double soc = div_f64(s.charge, c->bat_max_capacity);
-    const double b0 = div_f64(soc - c->bat_soc_low, c->bat_soc_spread);
-    const double b1 = div_f64(s.charge - c->bat_min_capacity, c->bat_charge_spread);
+    const double soc = s.charge / c->bat_max_capacity;
+    const double b0 = (soc - c->bat_soc_low) / c->bat_soc_spread;
+    const double b1 = (s.charge - c->bat_min_capacity) / c->bat_charge_spread;
     if (!G.has_genset) {
         te.state[0] = b0; te.state[1] = b1;
         return;
     }
     const double g0 = ((double)s.cs - 0.0) / 1.0;
     const double g1 = ((double)s.gs - 0.0) / 1.0;
-    const double g2 = div_f64((double)s.up - 0.0, c->gen_up_spread);
-    const double g3 = div_f64((double)s.dn - 0.0, c->gen_down_spread);
+    const double g2 = ((double)s.up - 0.0) / c->gen_up_spread;
+    const double g3 = ((double)s.dn - 0.0) / c->gen_down_spread;
     if (G.state_genset_first) {   // container order: genset, battery
         te.state[0] = g0; te.state[1] = g1; te.state[2] = g2; te.state[3] = g3; te.state[4] = b0; te.state[5] = b1;
     } else {                      // gym order: battery, genset
@@ -588,8 +579,8 @@ __device__ __forceinline__ void series_obs_value(const LaunchParams &P, const Mg
         const bool in = idx < P.T;
         const double rp = in ? __ldg(P.pv_raw + (size_t)c->pv_series * P.T + idx) : 0.0;
         const double rl = in ? __ldg(P.load_raw + (size_t)c->load_series * P.T + idx) : 0.0;
-        const double np_ = div_f64(rp * c->pv_scale - c->pv_low, c->pv_spread);
-        const double nl = div_f64(rl * c->load_scale - c->load_low, c->load_spread);
+        const double np_ = (rp * c->pv_scale - c->pv_low) / c->pv_spread;
+        const double nl = (rl * c->load_scale - c->load_low) / c->load_spread;
         pv = in ? np_ : c->pv_fill_nrm;
         ld = in ? nl : c->load_fill_nrm;
     } else {
@@ -618,8 +609,8 @@ __device__ __forceinline__ SeriesRaw series_obs_fetch(const LaunchParams &P, con
 }
 __device__ __forceinline__ void series_obs_finish(const MgConfig *__restrict__ c, const SeriesRaw &r, double &ld, double &pv) {
     if (c->series_scaled) {
-        const double np_ = div_f64(r.a * c->pv_scale - c->pv_low, c->pv_spread);
-        const double nl = div_f64(r.b * c->load_scale - c->load_low, c->load_spread);
+        const double np_ = (r.a * c->pv_scale - c->pv_low) / c->pv_spread;
+        const double nl = (r.b * c->load_scale - c->load_low) / c->load_spread;
         pv = r.in ? np_ : c->pv_fill_nrm;
         ld = r.in ? nl : c->load_fill_nrm;
     } else {
@@ -736,8 +727,8 @@ __device__ __forceinline__ void emit_row_hetero(const LaunchParams &P, const Dev
             const bool in = idx < P.T;
             const double rp = in ? __ldg(P.pv_raw + hv.pv_base + idx) : 0.0;
             const double rl = in ? __ldg(P.load_raw + hv.load_base + idx) : 0.0;
-            const double np_ = div_f64(rp * hv.pv_scale - hv.pv_low, hv.pv_spread);
-            const double nl = div_f64(rl * hv.load_scale - hv.load_low, hv.load_spread);
+            const double np_ = (rp * hv.pv_scale - hv.pv_low) / hv.pv_spread;
+            const double nl = (rl * hv.load_scale - hv.load_low) / hv.load_spread;
             pv = in ? np_ : hv.pv_fill;
             ld = in ? nl : hv.load_fill;
         } else {
@@ -1041,8 +1032,8 @@ __device__ __forceinline__ ImgRow img_gather(const LaunchParams &P, const DevGro
         const bool in = idx < x.T;
         const double rp = in ? __ldg(P.pv_raw + hv.pv_base + idx) : 0.0;
         const double rl = in ? __ldg(P.load_raw + hv.load_base + idx) : 0.0;
-        const double np_ = div_f64(rp * hv.pv_scale - hv.pv_low, hv.pv_spread);
-        const double nl = div_f64(rl * hv.load_scale - hv.load_low, hv.load_spread);
+        const double np_ = (rp * hv.pv_scale - hv.pv_low) / hv.pv_spread;
+        const double nl = (rl * hv.load_scale - hv.load_low) / hv.load_spread;
         v.pv = in ? np_ : hv.pv_fill;
         v.load = in ? nl : hv.load_fill;
     } else {
@@ -1355,7 +1346,10 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
 // ------------------------------------------------------------------------------------------------------------------
 // persistent multi-step kernel: every CTA owns its tile for all n_steps; env state stays in registers
 // ------------------------------------------------------------------------------------------------------------------
-template <bool kHetero, typename TO, bool kRing = false>
+// kLog: record the per-step log of selected envs (MgRolloutIO.log).  Only this kernel family logs: the info block keeps ~16
+// more doubles alive through the physics, which the register budgets of the role-split kernels have no room for -- a
+// launch that asks for a log runs here.
+template <bool kHetero, typename TO, bool kRing = false, bool kLog = false>
 __global__ void __launch_bounds__(MG_THREADS, kRing ? MG_MIN_CTAS_RING : kHetero ? MG_MIN_CTAS_HETERO : MG_MIN_CTAS) mg_rollout_kernel(const __grid_constant__ LaunchParams P) {
     static_assert(!kRing || kHetero, "the ring path is a variant of the per-env series kernels");
     __shared__ TileShared S;
@@ -1384,7 +1378,7 @@ __global__ void __launch_bounds__(MG_THREADS, kRing ? MG_MIN_CTAS_RING : kHetero
         s.charge = G.charge[e];
         if (G.has_genset) unpack_genset(G.genset[e], s);
         final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
-        if (G.log_slot && G.log) log_slot = __ldg(G.log_slot + e);
+        if (kLog && G.log_slot && G.log) log_slot = __ldg(G.log_slot + e);
     }
     // ring variant: fill every special env's windows for its current step [t, t + H], one env per warp pass, lane k = window
     // element k (the only place where a whole window is normalised); the owner then appends one value per step
@@ -1421,9 +1415,9 @@ __global__ void __launch_bounds__(MG_THREADS, kRing ? MG_MIN_CTAS_RING : kHetero
             double reward;
             int done;
             uint32_t flags;
-            double *const log_rec = log_open(G, log_slot, step, P.n_steps, s);
-                owner_step(P, G, c, s, in, final_step, log_rec ? log_rec + MG_LOG_INFO : nullptr, reward, done, flags);
-                log_close(log_rec, s, reward, done, flags, in.valid);
+            double *const log_rec = kLog ? log_open(G, log_slot, step, P.n_steps, s) : nullptr;
+            owner_step(P, G, c, s, in, final_step, (kLog && log_rec) ? log_rec + MG_LOG_INFO : nullptr, reward, done, flags);
+            if (kLog) log_close(log_rec, s, reward, done, flags, in.valid);
             G.reward[(size_t)step * G.out_step_stride + e] = reward;
             G.done[(size_t)step * G.out_step_stride + e] = (uint8_t)done;
             rsum += reward;
@@ -1515,14 +1509,12 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
         int final_step = 0;
         double rsum = 0.0;
         uint32_t fsum = 0;
-        int log_slot = -1;
         if (owner) {
             c = P.cfg + __ldg(G.cfg_index + e);
             s.t = G.step[e];
             s.charge = G.charge[e];
             if (G.has_genset) unpack_genset(G.genset[e], s);
             final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
-            if (G.log_slot && G.log) log_slot = __ldg(G.log_slot + e);
         }
         for (int step = 0; step < P.n_steps; ++step) {
             const int ebuf = step & 1;
@@ -1536,9 +1528,7 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
                 double reward;
                 int done;
                 uint32_t flags;
-                double *const log_rec = log_open(G, log_slot, step, P.n_steps, s);
-                owner_step(P, G, c, s, in, final_step, log_rec ? log_rec + MG_LOG_INFO : nullptr, reward, done, flags);
-                log_close(log_rec, s, reward, done, flags, in.valid);
+                owner_step(P, G, c, s, in, final_step, nullptr, reward, done, flags);
                 rsum += reward;
                 fsum |= flags;
                 my_reward = reward;
@@ -1737,13 +1727,11 @@ __global__ void __launch_bounds__(MG_THREADS, MINB ? MINB : !kWS ? MG_IMG_MIN_CT
         bool ring_env = false;
         double rsum = 0.0;
         uint32_t fsum = 0;
-        int log_slot = -1;
         if (owner) {
             s.t = G.step[e];
             s.charge = G.charge[e];
             if (G.has_genset) unpack_genset(G.genset[e], s);
             final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
-            if (G.log_slot && G.log) log_slot = __ldg(G.log_slot + e);
             if (kRing) {
                 ring_env = env_is_special(c, G);
                 ring_base = min(s.t, P.T) % ring_R;
@@ -1794,9 +1782,7 @@ __global__ void __launch_bounds__(MG_THREADS, MINB ? MINB : !kWS ? MG_IMG_MIN_CT
                 double reward;
                 int done;
                 uint32_t flags;
-                double *const log_rec = log_open(G, log_slot, step, P.n_steps, s);
-                owner_step(P, G, c, s, in, final_step, log_rec ? log_rec + MG_LOG_INFO : nullptr, reward, done, flags);
-                log_close(log_rec, s, reward, done, flags, in.valid);
+                owner_step(P, G, c, s, in, final_step, nullptr, reward, done, flags);
                 rsum += reward;
                 fsum |= flags;
                 my_reward = reward;
@@ -2567,6 +2553,10 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
         if (!P.g[g].obs || !P.g[g].img_ok) image = false;
         if (P.g[g].obs_dim > max_dim) max_dim = P.g[g].obs_dim;
     }
+    bool any_log = false;
+    for (int g = 0; g < P.n_groups; ++g)
+        if (P.g[g].log) any_log = true;
+    if (any_log) image = ws = false;          // the logging kernels are instantiations of mg_rollout_kernel
     if (!image)
         for (int g = 0; g < P.n_groups; ++g)
             if (P.g[g].long_path) use_ring = false;
@@ -2584,6 +2574,19 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
         h->last_kernel = "mg_rollout_ws_kernel";
         if (h->obs_f32) mg_rollout_ws_kernel<false, float><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
         else mg_rollout_ws_kernel<false, double><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);
+    } else if (any_log) {
+        h->last_kernel = "mg_rollout_kernel (log)";
+        const dim3 grid(P.total_tiles), block(MG_THREADS);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (h->obs_f32) {
+            if (use_ring) mg_rollout_kernel<true, float, true, true><<<grid, block, 0, st>>>(P);
+            else if (h->hetero) mg_rollout_kernel<true, float, false, true><<<grid, block, 0, st>>>(P);
+            else mg_rollout_kernel<false, float, false, true><<<grid, block, 0, st>>>(P);
+        } else {
+            if (use_ring) mg_rollout_kernel<true, double, true, true><<<grid, block, 0, st>>>(P);
+            else if (h->hetero) mg_rollout_kernel<true, double, false, true><<<grid, block, 0, st>>>(P);
+            else mg_rollout_kernel<false, double, false, true><<<grid, block, 0, st>>>(P);
+        }
     } else if (use_ring) {
         h->last_kernel = "mg_rollout_kernel (rings)";
         if (h->obs_f32) mg_rollout_kernel<true, float, true><<<P.total_tiles, MG_THREADS, 0, (cudaStream_t)stream>>>(P);

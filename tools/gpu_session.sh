@@ -17,6 +17,8 @@ for stage in "$@"; do
       timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_gpu_tests.log 2>&1 ;;
     bench)
       timeout 600 python bench.py > $out/${tag}_bench_default.json 2> $out/${tag}_bench_default.err ;;
+    bench256)
+      timeout 600 python bench.py --steps 256 --warmup 5 --no-cpu --no-configs > $out/${tag}_bench_steps256.json 2> $out/${tag}_bench_steps256.err ;;
     bench20)
       timeout 600 python bench.py --steps 20 --warmup 3 > $out/${tag}_bench_steps20.json 2> $out/${tag}_bench_steps20.err ;;
     generator)
@@ -44,6 +46,17 @@ for stage in "$@"; do
     ncu_default)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:mg_rollout -s 1 -c 1 -o $out/${tag}_default \
         python bench.py --steps 64 --warmup 3 --preheat 0 --single-path --no-cpu $BENCH_EXTRA > $out/${tag}_ncu_default.log 2>&1 ;;
+    scale*)
+      # scale2 / scale4 / scale8 / scale1248: the default bench (headline + configs block incl. the config-5 shard) on N GPUs of this box
+      for n in $(echo ${stage#scale} | sed 's/1248/1 2 4 8/'); do
+        if [ "$n" = "1" ]; then
+          timeout 600 python bench.py --gpus 1 --steps 256 --warmup 5 --no-cpu > $out/${tag}_scale_n1.json 2> $out/${tag}_scale_n1.err
+        else
+          timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) \
+            bench.py --gpus $n --steps 256 --warmup 5 > $out/${tag}_scale_n$n.json 2> $out/${tag}_scale_n$n.err
+        fi
+      done
+      nvidia-smi topo -m > $out/${tag}_topo.txt 2>&1 ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
