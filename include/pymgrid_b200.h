@@ -326,6 +326,13 @@ typedef struct MgForecastNoise {
 int mg_forecast_noise(MgHandle *h, const MgForecastNoise *noise /* DEVICE [n_cfg] */, void *const *obs /* [n_groups] */,
                       const int64_t *env_base /* HOST [n_groups] or NULL -> 0, n_0, n_0 + n_1, ... */,
                       uint64_t seed, uint64_t call, void *stream);
+/* The same for rows that were written at an EARLIER step than the env's current one -- the slots of mg_rollout's observation
+ * ring: the row of group g's env e observes step min(step_base[g][e] + step_add, T), with step_base the env's step counter
+ * before the rollout (DEVICE [n] int32 per group, HOST array of n_groups pointers; a NULL entry skips the group) and step_add
+ * the number of steps taken when the slot was written.  With call numbers that continue the per-step sequence, a rollout's
+ * ring then holds exactly the noisy rows that mg_step + mg_forecast_noise would have produced step by step. */
+int mg_forecast_noise_at(MgHandle *h, const MgForecastNoise *noise, void *const *obs, const int64_t *env_base, uint64_t seed,
+                         uint64_t call, const int32_t *const *step_base, int32_t step_add, void *stream);
 
 /* Tuning knobs.  MG_OPT_ROLLOUT_SPECIALISED (default 1): run mg_rollout with the owner / emitter warp-specialised
  * kernel when every group writes observations.  It wins when the envs of a tile advance in lock-step (11.5 vs 12.4

@@ -130,6 +130,8 @@ def lib():
     L.mg_rollout_host.argtypes = [_vp, C.POINTER(MgHostRolloutIO), _i32, _i32, _i32, C.c_int, C.c_int, _vp]
     L.mg_set_option.argtypes = [_vp, C.c_int, C.c_int]
     L.mg_forecast_noise.argtypes = [_vp, _vp, C.POINTER(_vp), C.POINTER(C.c_int64), C.c_uint64, C.c_uint64, _vp]
+    L.mg_forecast_noise_at.argtypes = [_vp, _vp, C.POINTER(_vp), C.POINTER(C.c_int64), C.c_uint64, C.c_uint64, C.POINTER(_vp), C.c_int32, _vp]
+    L.mg_forecast_noise_at.restype = C.c_int
     L.mg_set_reported_soc.argtypes = [_vp, C.POINTER(_vp)]
     L.mg_launch_count.argtypes = [_vp]
     L.mg_launch_count.restype = C.c_int64
@@ -149,7 +151,7 @@ def lib():
 
 EXPORTED_SYMBOLS = ("mg_abi_version", "mg_sizeof", "mg_build_info", "mg_last_error", "mg_create", "mg_destroy",
                     "mg_step", "mg_step_discrete", "mg_reset", "mg_observe", "mg_rollout", "mg_rollout_discrete",
-                    "mg_rollout_host", "mg_launch_count", "mg_last_kernel", "mg_set_trajectories", "mg_set_option", "mg_forecast_noise", "mg_set_reported_soc")
+                    "mg_rollout_host", "mg_launch_count", "mg_last_kernel", "mg_set_trajectories", "mg_set_option", "mg_forecast_noise", "mg_forecast_noise_at", "mg_set_reported_soc")
 
 
 def check(code, what):

@@ -1960,10 +1960,12 @@ struct NoiseGroup {
     int32_t n_envs, obs_dim, horizon, has_grid, load_start, pv_start, grid_start, first_block;
     int64_t env_base;
     const int32_t *step, *cfg_index;
+    const int32_t *step_base;           // mg_forecast_noise_at: the env's step counter before a rollout, or NULL
     void *obs;
 };
 struct NoiseParams {
     int32_t n_groups, T;
+    int32_t step_add, _pad0;            // with step_base: the row observes step min(step_base[e] + step_add, T)
     uint32_t k0, k1, c3, _pad;
     const MgForecastNoise *noise;
     NoiseGroup g[MG_MAX_GROUPS];
@@ -1994,7 +1996,9 @@ __global__ void __launch_bounds__(128) mg_forecast_noise_kernel(const __grid_con
     const int e = ((int)blockIdx.x - G.first_block) * 4 + (int)(threadIdx.x >> 5);
     if (e >= G.n_envs) return;
     const int lane = threadIdx.x & 31;
-    const int t = G.step[e];                  // the step the row observes (post-step state)
+    // the step the row observes (post-step state): the env's counter, or -- for a slot of a rollout's observation ring --
+    // what the counter was when the slot was written (it moves by one per step and stops at the end of the series)
+    const int t = G.step_base ? min(G.step_base[e] + P.step_add, P.T) : G.step[e];
     const int H = G.horizon;
     int n_real = P.T - (t + 1);               // forecast rows that exist in the series: t + 1 + k < T
     n_real = n_real < 0 ? 0 : (n_real > H ? H : n_real);
@@ -2275,11 +2279,26 @@ extern "C" int mg_set_trajectories(MgHandle *h, const int32_t *const *initial_st
     return MG_OK;
 }
 
+static int launch_noise(MgHandle *h, const MgForecastNoise *noise, void *const *obs, const int64_t *env_base, uint64_t seed,
+                        uint64_t call, const int32_t *const *step_base, int32_t step_add, void *stream);
+
 extern "C" int mg_forecast_noise(MgHandle *h, const MgForecastNoise *noise, void *const *obs, const int64_t *env_base,
                                  uint64_t seed, uint64_t call, void *stream) {
+    return launch_noise(h, noise, obs, env_base, seed, call, nullptr, 0, stream);
+}
+
+extern "C" int mg_forecast_noise_at(MgHandle *h, const MgForecastNoise *noise, void *const *obs, const int64_t *env_base,
+                                    uint64_t seed, uint64_t call, const int32_t *const *step_base, int32_t step_add, void *stream) {
+    if (!step_base) return fail(MG_E_INVALID, "mg_forecast_noise_at: null step_base");
+    return launch_noise(h, noise, obs, env_base, seed, call, step_base, step_add, stream);
+}
+
+static int launch_noise(MgHandle *h, const MgForecastNoise *noise, void *const *obs, const int64_t *env_base, uint64_t seed,
+                        uint64_t call, const int32_t *const *step_base, int32_t step_add, void *stream) {
     if (!h || !noise || !obs) return fail(MG_E_INVALID, "mg_forecast_noise: null argument");
     NoiseParams P;
     memset(&P, 0, sizeof P);
+    P.step_add = step_add;
     P.n_groups = h->base.n_groups;
     P.T = h->base.T;
     P.k0 = (uint32_t)seed;
@@ -2302,6 +2321,8 @@ extern "C" int mg_forecast_noise(MgHandle *h, const MgForecastNoise *noise, void
         n.first_block = blocks;
         n.env_base = env_base ? env_base[g] : base;
         n.step = d.step; n.cfg_index = d.cfg_index; n.obs = obs[g];
+        n.step_base = step_base ? step_base[g] : nullptr;
+        if (step_base && !n.step_base) n.n_envs = 0;
         blocks += (n.n_envs + 3) / 4;
         base += d.n_envs;
     }

@@ -702,7 +702,8 @@ class BatchedMicrogrid:
         (`mg_forecast_noise`).  The draw is a pure function of (seed, call number, env, the env's step, element);
         `env_offset` shifts the env ids so that shards of one batch on different GPUs draw differently.
         `records`: optional explicit list of MgForecastNoise, one per config (array-form front ends).
-        `mg_rollout` keeps the oracle forecast: its observation ring is written inside the persistent kernel."""
+        `rollout` applies the same noise to the slots of its observation ring once the persistent kernel has written them
+        (mg_forecast_noise_at, one call number per step): the ring holds what step-by-step stepping would have produced."""
         if records is None:
             records = [forecast_noise_record(p) for p in self.configs]
         raw = np.frombuffer(bytes((MgForecastNoise * len(records))(*records)), dtype=np.uint8).copy()
@@ -969,6 +970,24 @@ class BatchedMicrogrid:
                   else lib.mg_rollout(handle, io, n_steps, ring, norm, st))
             if rc:
                 _cabi.check(rc, "mg_rollout")
+        if self._noise is not None and keep_obs:
+            plain_launch, engine = launch, self
+
+            def launch():
+                # Gaussian-noise forecasts: the persistent kernel writes the oracle rows; the slots that survive in the ring
+                # then get the noise of THEIR step (call numbers continue the per-step sequence, so the ring equals what
+                # n_steps x (mg_step + mg_forecast_noise) leaves behind)
+                base = [g.step.clone() for g in engine.groups]
+                plain_launch()
+                records, seed, bases = engine._noise
+                first_call = engine._noise_calls
+                engine._noise_calls += n_steps
+                step_base = (C.c_void_p * len(base))(*[_ptr(b) for b in base])
+                for s_idx in range(max(0, n_steps - ring), n_steps):
+                    ptrs = (C.c_void_p * len(outs))(*[_ptr(r["obs_ring"][s_idx % ring]) for r in outs])
+                    _cabi.check(engine._lib.mg_forecast_noise_at(engine._handle, records.data_ptr(), ptrs, bases, seed, first_call + s_idx + 1,
+                                                                 step_base, s_idx + 1, engine._stream()), "mg_forecast_noise_at")
+                launch.keepalive_noise = base
         result = outs[0] if self.single_group else outs
         if bind_only:      # the caller launches (repeatedly) with minimal host overhead; buffers are kept alive here
             launch.keepalive = (io, acts, outs, reward_total, log_keep)

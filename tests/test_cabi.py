@@ -18,7 +18,7 @@ def declared_functions():
 def test_header_declares_the_documented_entry_points():
     names = declared_functions()
     for must in ("mg_create", "mg_destroy", "mg_step", "mg_step_discrete", "mg_reset", "mg_observe", "mg_rollout",
-                 "mg_rollout_discrete", "mg_last_error", "mg_abi_version", "mg_sizeof", "mg_launch_count", "mg_last_kernel", "mg_set_trajectories", "mg_set_option", "mg_forecast_noise"):
+                 "mg_rollout_discrete", "mg_last_error", "mg_abi_version", "mg_sizeof", "mg_launch_count", "mg_last_kernel", "mg_set_trajectories", "mg_set_option", "mg_forecast_noise", "mg_forecast_noise_at"):
         assert must in names
 
 

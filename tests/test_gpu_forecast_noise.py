@@ -150,3 +150,37 @@ def test_f32_observations_take_noise_too():
     assert oa.dtype == torch.float32
     # f32 rows start from the rounded clean value, so they agree with the f64 path to f32 precision
     assert torch.allclose(oa.double(), ob, rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("emit", ["auto", "image"])
+def test_rollout_ring_carries_the_noise_of_each_step(emit):
+    """`rollout` with Gaussian-noise forecasters: the persistent kernel writes the oracle rows and mg_forecast_noise_at gives
+    every surviving ring slot the noise of ITS step (call numbers continue the per-step sequence) -- the ring equals, bit for
+    bit, the rows that the same engine produces step by step with mg_step + mg_forecast_noise; also across the end of the
+    series, where forecast rows turn into padding and carry no noise."""
+    configs = [noisy_params(n, t0) for n in (0, 1, 2) for t0 in (0, 8740)]
+    B, n_steps, ring = 300, 12, 5
+    env_config = np.arange(B) % len(configs)
+    a, b = engine(configs, env_config), engine(configs, env_config)
+    for bm in (a, b):
+        bm.set_forecast_noise(seed=77, env_offset=9)
+        if emit == "image":
+            bm.set_emit_image(True)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(4)
+    acts = [torch.rand((n_steps, g.n_envs, g.n_act), dtype=torch.float64, device="cuda", generator=gen) for g in a.groups]
+    out = a.rollout(acts, ring=ring)
+    rows = []
+    for k in range(n_steps):
+        obs, _, _, _ = b.step([x[k].contiguous() for x in acts])
+        rows.append([o.clone() for o in obs])
+    noisy_somewhere = False
+    for gi in range(len(a.groups)):
+        for k in range(n_steps - ring, n_steps):
+            assert torch.equal(out[gi]["obs_ring"][k % ring], rows[k][gi]), (gi, k)
+        clean = engine([jump_to(load_pymgrid25(n), t0) for n in (0, 1, 2) for t0 in (0, 8740)], env_config)
+    clean_out = clean.rollout(acts, ring=ring)
+    for gi in range(len(a.groups)):
+        noisy_somewhere |= not torch.equal(clean_out[gi]["obs_ring"], out[gi]["obs_ring"])
+        assert torch.equal(clean_out[gi]["reward"], out[gi]["reward"])        # the physics never sees the noise
+    assert noisy_somewhere and a._noise_calls == b._noise_calls == n_steps
