@@ -43,6 +43,14 @@ for stage in "$@"; do
     ncu_gen_src)
       timeout 600 ncu --section SourceCounters --section InstructionStats --section WarpStateStats --section LaunchStats --section Occupancy --clock-control none --import-source on -k regex:mg_rollout -s 1 -c 1 -o $out/${tag}_gen \
         python bench.py --workload generator --steps 24 --warmup 3 --preheat 0 --single-path --no-cpu $BENCH_EXTRA > $out/${tag}_ncu_gen.log 2>&1 ;;
+    ncu_ragged)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:mg_rollout -s 1 -c 1 -o $out/${tag}_ragged \
+        python bench.py --ragged --steps 64 --warmup 3 --preheat 0 --single-path --no-cpu $BENCH_EXTRA > $out/${tag}_ncu_ragged.log 2>&1 ;;
+    launch_list)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
+        python bench.py --steps 20 --warmup 3 --preheat 0 --no-cpu --min-timed-ms 1 > $out/${tag}_launch_list_bench.log 2>&1 ;;
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1 ;;
     ncu_default)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:mg_rollout -s 1 -c 1 -o $out/${tag}_default \
         python bench.py --steps 64 --warmup 3 --preheat 0 --single-path --no-cpu $BENCH_EXTRA > $out/${tag}_ncu_default.log 2>&1 ;;

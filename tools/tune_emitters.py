@@ -31,7 +31,7 @@ def main():
     peak, _ = bench.measured_peak()
     variants = [("lsu", 0, True), ("lsu", 0, False)] + [("image", s, ws) for s in range(6) for ws in (True, False)]
     if args.variants == "image_ws":
-        variants = [("image", s, True) for s in (0, 3, 4, 5)]
+        variants = [("image", s, True) for s in range(6)]
     if args.variants == "default":
         variants = [("lsu", 0, True), ("image", 0, True), ("image", 0, False)]
     K = args.steps
