@@ -417,6 +417,52 @@ def test_row_emitters_agree_on_generator_grids(emit, shape, specialised):
             np.testing.assert_array_equal(got[slot], pv_first(o_obs[e, :g.obs_dim], plist[e]), err_msg=f"env {e}")
 
 
+@pytest.mark.parametrize("horizon", (1, 3, 8, 24, 31, 40))
+@pytest.mark.parametrize("order", ("gym_sorted", "container"))
+def test_row_emitters_over_horizons_and_row_layouts(horizon, order):
+    """Both emitter families over the row layouts they must handle: forecast horizons from 1 (windows much shorter than a warp)
+    through 24 (odd number of forecast rows) and 31 (a full warp of window elements) to 40 (no image layout: the library falls
+    back to the per-lane emitters on its own), both observation orders, the three architectures in one batch with partial
+    last tiles, envs at unrelated steps -- against the C oracle, bit for bit."""
+    rng = np.random.default_rng(100 + horizon)
+    configs = []
+    for n in (0, 1, 2, 5, 9):
+        p = copy.copy(load_pymgrid25(n))
+        p.forecast_horizon = horizon
+        configs.append(p)
+    B, n_steps = 777, 6
+    env_config = rng.integers(0, len(configs), B)
+    outs = {}
+    for emit in ("lsu", "image", "auto"):
+        bm = engine(configs, env_config, obs_order=order)
+        if emit != "auto":
+            bm.set_emit_image(emit == "image")
+        plist = randomise_state(bm, rng if emit == "lsu" else np.random.default_rng(5), configs, env_config, 8700)
+        if emit == "lsu":
+            state = bm.state_dict()
+            ob = OracleBatch(plist, order=0 if order == "gym_sorted" else 1)
+            padded = np.zeros((n_steps, B, 4))
+            for e in range(B):
+                padded[:, e, :plist[e].n_act] = rng.random((n_steps, plist[e].n_act))
+            o_rew, o_done, o_obs = ob.rollout(padded, n_threads=4)
+        else:
+            bm.load_state_dict(state)
+        acts = [torch.from_numpy(np.ascontiguousarray(padded[:, g.env_ids, :g.n_act])).cuda() for g in bm.groups]
+        out = bm.rollout([a[:n_steps - 1].contiguous() for a in acts], ring=2)
+        obs, reward, done, _ = as_lists(bm.step([a[n_steps - 1].contiguous() for a in acts]))
+        for g, r, o, rw in zip(bm.groups, out, obs, reward):
+            np.testing.assert_array_equal(r["reward"].cpu().numpy(), o_rew[:n_steps - 1, g.env_ids], err_msg=emit)
+            np.testing.assert_array_equal(rw.cpu().numpy(), o_rew[n_steps - 1, g.env_ids], err_msg=emit)
+            np.testing.assert_array_equal(o.cpu().numpy(), o_obs[g.env_ids][:, :g.obs_dim], err_msg=emit)
+        outs[emit] = [r["obs_ring"].clone() for r in out]
+        if emit == "image" and horizon <= 31:
+            assert bm.last_kernel == "mg_step_img_kernel"
+        if horizon > 31:
+            assert bm.last_kernel == "mg_step_kernel"          # no image layout for these rows
+    for a, b, c in zip(outs["lsu"], outs["image"], outs["auto"]):
+        assert torch.equal(a, b) and torch.equal(a, c)
+
+
 def test_automatic_emitter_choice():
     """MG_OPT_EMIT_IMAGE = 2 (the default): the library picks the emitters per launch and says which kernel ran
     (mg_last_kernel).  Large table-backed batches in lock-step keep the per-lane store emitters, the ragged hint (set by a
