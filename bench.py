@@ -411,15 +411,25 @@ class Harness:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return t.item()
 
-    def timed(self, run, prepare, min_ms=MIN_TIMED_MS, max_reps=MAX_REPEATS):
+    def timed(self, run, prepare, min_ms=MIN_TIMED_MS, max_reps=MAX_REPEATS, gate=False):
         """Time `run(rep)` (enqueues EXACTLY the K steps on self.stream) between barrier + synchronize on both sides, CUDA
         events on the launching stream, max over ranks; `prepare(rep)` (state restore, untimed) precedes every repetition.
-        Repeats until the timed regions add up to min_ms; returns (median ms, all ms)."""
+        Repeats until the timed regions add up to min_ms; returns (median ms, all ms).
+        gate=True (device-timed paths): an untimed ~0.1 ms spin kernel runs in front of the start event, so that the event and
+        the first launch are both queued before the GPU reaches them -- the region then holds the device's time for the K
+        steps, not the host's latency between `record` and the first launch call (10-20 us of Python per call, which is as
+        long as a whole step).  The host-buffer legs are timed without it: there the host's work is part of the metric."""
         times, total = [], 0.0
         while True:
             rep = len(times)
             prepare(rep)
             self.barrier()
+            if gate:
+                try:
+                    with self.torch.cuda.stream(self.stream):
+                        self.torch.cuda._sleep(200000)
+                except Exception:
+                    pass
             self.ev0.record(self.stream)
             run(rep)
             self.ev1.record(self.stream)
@@ -545,7 +555,7 @@ def measure_workload(hx, workload, B, K, W, R, paths=("rollout", "graph", "eager
                 per_rep = K
             sampler = ClockSampler(hx.local_rank)
             sampler.start()
-            ms, all_ms = hx.timed(run, restore, min_ms=min_ms if path != "eager" else min(min_ms, 20.0))
+            ms, all_ms = hx.timed(run, restore, min_ms=min_ms if path != "eager" else min(min_ms, 20.0), gate=True)
             clocks = sampler.stop()
             results[path] = {"ms": ms, "repeats": len(all_ms), "ms_min": min(all_ms), "ms_max": max(all_ms), "launches": per_rep, "clocks": clocks,
                              "kernel": bm.last_kernel}
@@ -604,8 +614,9 @@ def measure_workload(hx, workload, B, K, W, R, paths=("rollout", "graph", "eager
     #     `chunk` steps, the copies of neighbouring chunks overlapped with the persistent kernel on three streams.
     #     Same bytes per step as (1); this is the headline e2e figure when it runs (any failure keeps (1) and says so).
     # Collectives (barrier, max over ranks) stay outside the try blocks so that a failure on one rank cannot hang the others.
-    Kr = min(K, 1024)
-    chunk = max(1, min(64, Kr // 8))           # at least eight chunks: the three-stream pipeline is exercised at any K
+    Kr = min(max(K, 256), 1024)      # its own length: a host-buffer rollout shorter than ~256 steps measures pipeline fill and drain
+    chunk = max(1, min(64, Kr // (8 if Kr >= 128 else 4)))     # >= 4-8 chunks: the three-stream pipeline is exercised at any K
+    # (short rollouts take fewer, larger chunks: a chunk costs ~12 API calls on the host, which must stay ahead of the GPU)
     del hio
     errors = {}
     for pipeline in ("native", "torch"):       # mg_rollout_host (one C-ABI call); else the same schedule from torch streams
@@ -734,7 +745,7 @@ def main():
     configs = None
     if args.workload == "pymgrid25" and not args.single_path and not args.no_configs and not args.ragged and not args.obs_f32:
         configs = {}
-        Kc = min(K, 256)
+        Kc = 256      # (their own length, whatever --steps: a 20-step launch of the per-env-series kernel is half prologue)
         for name, wl, Bc, cpaths in (("configs[1]", "replicas", 4096, ("graph", "rollout")), ("configs[3]", "discrete", BATCH_PER_GPU, ("rollout", "graph")),
                                      ("configs[4]", "generator", 131072, ("rollout",))):
             try:
@@ -773,7 +784,8 @@ def main():
             "data": "pymgrid25 scenario parameters + series (bundled), synthetic U[0,1) actions",
             "repeats": head["repeats"],
             "timing": {"rule": f"the K-step timed region is repeated until the repetitions add up to {args.min_timed_ms:.0f} ms (state restored and a fresh "
-                               "action block in between, untimed); value / ms_per_step are the MEDIAN repetition, max over ranks each",
+                               "action block in between, untimed); value / ms_per_step are the MEDIAN repetition, max over ranks each; an untimed "
+                               "0.1 ms spin kernel in front of the start event keeps the host's launch latency out of the device-timed regions",
                        "ms_min": head["ms_min"], "ms_median": head["ms"], "ms_max": head["ms_max"]},
             "config": {"workload": WORKLOADS[args.workload],
                        "batch_per_gpu": B, "global_batch": world * B, "forecast_horizon": 23, "path": args.path, "ragged_steps": bool(args.ragged),

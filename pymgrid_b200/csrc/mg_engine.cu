@@ -28,6 +28,13 @@
 #ifndef MG_TILE
 #define MG_TILE 64          // envs per CTA tile
 #endif
+// (debug builds, -DMG_DEBUG_NOSTORE: the image emitters do everything but issue their bulk stores -- what the kernels cost
+//  without the write traffic; results are then meaningless)
+#ifdef MG_DEBUG_NOSTORE
+#define MG_BULK_STORE_ENABLED 0
+#else
+#define MG_BULK_STORE_ENABLED 1
+#endif
 #define MG_STR2(x) #x
 #define MG_STR(x) MG_STR2(x)
 #define MG_WARPS (MG_THREADS / 32)
@@ -1118,8 +1125,9 @@ __device__ __forceinline__ void warp_emit_rows_img(const LaunchParams &P, const 
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(obs_tile + (size_t)r * (x.row_bytes >> 3)), "r"(im),
-                         "r"((uint32_t)(n * x.row_bytes)) : "memory");
+            if (MG_BULK_STORE_ENABLED)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(obs_tile + (size_t)r * (x.row_bytes >> 3)), "r"(im),
+                             "r"((uint32_t)(n * x.row_bytes)) : "memory");
             bulk_commit();
         }
         buf = buf + 1 == NB ? 0 : buf + 1;

@@ -49,6 +49,18 @@ for stage in "$@"; do
     launch_list)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
         python bench.py --steps 20 --warmup 3 --preheat 0 --no-cpu --min-timed-ms 1 > $out/${tag}_launch_list_bench.log 2>&1 ;;
+    sanitizer)
+      timeout 600 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_memcheck_smoke.log 2>&1
+      timeout 900 compute-sanitizer --tool racecheck python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_racecheck_smoke.log 2>&1
+      timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "generator_grids_rollout or automatic_emitter" > $out/${tag}_racecheck_generator.log 2>&1 ;;
+    final_benches)
+      timeout 600 python bench.py > $out/${tag}_bench_default.json 2> $out/${tag}_bench_default.err
+      timeout 600 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_steps20.json 2> $out/${tag}_bench_steps20.err
+      timeout 300 python bench.py --workload generator --steps 500 --warmup 5 --no-cpu > $out/${tag}_bench_generator.json 2> $out/${tag}_bench_generator.err
+      timeout 300 python bench.py --ragged --steps 500 --warmup 5 --no-cpu --no-configs > $out/${tag}_bench_ragged.json 2> $out/${tag}_bench_ragged.err
+      timeout 300 python bench.py --workload discrete --steps 500 --warmup 5 --no-cpu > $out/${tag}_bench_discrete.json 2> $out/${tag}_bench_discrete.err
+      timeout 300 python bench.py --workload replicas --steps 500 --warmup 5 --no-cpu > $out/${tag}_bench_replicas.json 2> $out/${tag}_bench_replicas.err
+      timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err ;;
     smoke)
       timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1 ;;
     ncu_default)

@@ -6,6 +6,7 @@
 //   lsu        lanes store their 3 pairs per row straight from registers (st.global.cs.v2.f64)           -- the round-1 emitter
 //   tma R B    warp image of R rows in shared memory, B buffers; one cp.async.bulk S2G per R rows, image never rewritten
 //   fill R B   as tma, but every row is first written into the image with STS.128 from registers (3 pairs per lane)
+//   hyb R B    as fill, but every other chunk of R rows is written with per-lane 16-byte stores instead (both store paths at once)
 //   real R B   as fill, but the row is gathered the way a per-env row is: 48 grid pairs by LDG.128 from an L2-resident table
 //              (row-dependent offset), 2 x 24 window values from a shared-memory ring (LDS.64), 6 state values
 #include <cuda_runtime.h>
@@ -69,10 +70,21 @@ __global__ void __launch_bounds__(THREADS) k_img(double *out, size_t slot_stride
 #pragma unroll 1
         for (int c = 0; c < RW / R; ++c) {
             double *im = img + (size_t)buf * R * D;
+            if (MODE == 4 && (c & 1)) {      // hybrid: this chunk leaves through the LSU
+                double *ol = o + (size_t)c * R * D + 2 * lane;
+#pragma unroll
+                for (int r = 0; r < R; ++r, ol += D) {
+                    st_cs(ol, v0, v1);
+                    st_cs(ol + 64, v1, v0);
+                    if (lane < 11) st_cs(ol + 128, v0, v0);
+                    v0 += 1.0;
+                }
+                continue;
+            }
             if (MODE >= 2) {
                 if (lane == 0) bulk_wait_read<B - 1>();   // the store that last read this buffer has drained it
                 __syncwarp();
-                if (MODE == 2) {
+                if (MODE == 2 || MODE == 4) {
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         double2 *row = reinterpret_cast<double2 *>(im + r * D);
@@ -198,6 +210,13 @@ int main(int argc, char **argv) {
         run_img<8, 2, 3>("real", steps, 0);
     }
     g_ragged = 0;
+    // hybrid: TMA bulk stores and per-lane stores alternate chunk by chunk
+    run_img<4, 2, 4, 4>("hyb", steps, 0);
+    run_img<4, 2, 4, 2>("hyb", steps, 0);
+    run_img<4, 2, 4, 2>("hyb", steps, 12);
+    run_img<2, 2, 4, 2>("hyb", steps, 0);
+    run_img<4, 1, 4, 2>("hyb", steps, 0);
+    run_img<8, 1, 4, 2>("hyb", steps, 0);
     // two emitting warps per CTA (the warp-specialised kernels), with enough padding to cap the CTAs at 7 per SM
     run_img<4, 2, 1, 2>("tma", steps, 0);
     run_img<4, 2, 2, 2>("fill", steps, 0);
