@@ -312,13 +312,16 @@ def cpu_port_rate(n_envs, n_steps, threads, reps=1, seed=7):
 
 
 def run_reference(args):
+    """The reference arm: the CPU implementation of the path (the C port of Microgrid.run, all host threads) on the headline
+    workload's own configuration -- 65 536 envs tiled over the 25 pymgrid25 scenarios, full observation every step -- one
+    bench step = a bounded sample of 125 consecutive env steps of that batch."""
     rank, local_rank, world = dist_env()
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    n_envs, n_steps = 16384, 250         # one "step" of this arm = 4 096 000 env-steps of the workload (~1 CPU-second)
+    n_envs, n_steps = BATCH_PER_GPU, 125         # one "step" of this arm = 8 192 000 env-steps of the workload
     for _ in range(args.warmup):
-        cpu_port_rate(n_envs, 25, threads)
+        cpu_port_rate(n_envs, 10, threads)
     total, total_t = 0, 0.0
     for k in range(args.steps):
         _, dt = cpu_port_rate(n_envs, n_steps, threads)
@@ -330,8 +333,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "pymgrid25 scenario parameters + series (bundled), synthetic U[0,1) actions",
-        "config": {"workload": "pymgrid25 tiled, CPU port of Microgrid.run (C oracle), bounded sample", "batch": n_envs},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOADS["pymgrid25"], "batch_per_gpu": n_envs, "global_batch": n_envs, "forecast_horizon": 23,
+                   "implementation": "CPU port of Microgrid.run (C oracle, oracle/mg_oracle.c), all host threads, bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "python_reference": python_reference_figure()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
     return 0

@@ -2434,10 +2434,12 @@ static int ensure_dynamic_smem(const void *func, size_t bytes) {
 }
 
 // Which emitters a launch uses when the caller left the choice to the library (MG_OPT_EMIT_IMAGE = 2), from what was
-// measured on B200 (profiles/r02_emitters.md): the image + TMA bulk-store emitters win wherever rows share no window with
-// their neighbours (per-env series, envs at unrelated steps) and on batches too small to fill the GPU with tiles; the
-// per-lane store emitters with their run detection keep a small lead on large table-backed batches in lock-step, except
-// for rows with an odd number of forecast steps, where the un-split image kernel leads.
+// measured on B200 (profiles/r02_emitters.md): the image + TMA bulk-store emitters wherever rows share no window with their
+// neighbours (per-env series: 31.8 vs 76 us/step; envs at unrelated steps, MG_OPT_RAGGED_HINT: 15.3 vs 34-40), on batches of
+// at most two tiles per SM (2.7-4.1 vs 6.8) and, for persistent launches, on rows with an even forecast horizon (14.1 vs
+// 15.2; deeper image queues there and for per-env series); the per-lane store emitters with their run detection for large
+// table-backed batches in lock-step -- level with the image kernels in tools/tune_emitters.py (11.44 both), 0.5 us/step
+// ahead inside bench.py's longer launches, and 3 us/step ahead for single steps (16.4 vs 19.3).
 struct EmitChoice {
     bool image, split;
     int shape;
@@ -2445,20 +2447,12 @@ struct EmitChoice {
 static EmitChoice choose_emitters(const MgHandle *h, const LaunchParams &P, bool persistent) {
     EmitChoice c;
     c.split = h->rollout_specialised;
-    c.shape = h->image_shape >= 0 ? h->image_shape : (h->hetero ? (persistent ? 4 : 1) : 0);
-    if (h->emit_image != 2) {
-        c.image = h->emit_image == 1;
-        return c;
-    }
     bool odd_rows = false;
     for (int g = 0; g < P.n_groups; ++g)
         if (P.g[g].has_grid && (P.g[g].horizon & 1) == 0) odd_rows = true;
-    c.image = h->hetero || h->ragged_hint || P.total_tiles <= 2 * h->n_sms;
-    if (!c.image && odd_rows && persistent) {
-        c.image = true;
-        c.split = false;
-        if (h->image_shape < 0) c.shape = 2;
-    }
+    c.shape = h->image_shape >= 0 ? h->image_shape : persistent ? ((h->hetero || odd_rows) ? 4 : 0) : (h->hetero ? 1 : 0);
+    if (h->emit_image != 2) c.image = h->emit_image == 1;
+    else c.image = h->hetero || h->ragged_hint || P.total_tiles <= 2 * h->n_sms || (persistent && odd_rows);
     return c;
 }
 

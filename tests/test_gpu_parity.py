@@ -476,7 +476,7 @@ def test_automatic_emitter_choice():
     assert big.last_kernel == "mg_step_kernel"
     big.reset(mask=[torch.ones(g.n_envs, dtype=torch.uint8, device="cuda") for g in big.groups])      # leaves lock-step
     big.rollout(acts, ring=1)
-    assert big.last_kernel.startswith("mg_rollout_img_kernel")
+    assert big.last_kernel == "mg_rollout_img_kernel (owner / emitter warps)"
     big.step([a[0].contiguous() for a in acts])
     assert big.last_kernel == "mg_step_img_kernel"
     small = engine(configs, np.arange(3000) % 25, with_info=False)
@@ -610,6 +610,53 @@ def test_full_size_properties():
                     assert r[slot].item() == o_rew[0, j]
                     np.testing.assert_array_equal(o[slot].cpu().numpy(), o_obs[j, :g.obs_dim])
     assert bm.launch_count == 1 + n_steps
+
+
+def test_full_size_generator_shard_properties():
+    """BASELINE config 5, one GPU's shard at full size (131 072 heterogeneous MicrogridGenerator grids): size-independent
+    properties of a 24-step persistent rollout through the kernel the library picks (images + bulk stores, rings, role split):
+    (1) the same batch through the round-1 kernel family (per-lane stores) gives the same rewards, flags and rows, bit for bit;
+    (2) rewards are finite, observations lie in [0, 1], step counters advance by the number of steps;
+    (3) 192 sampled grids (every architecture, weak grids included) equal the C oracle on their explicit form."""
+    from pymgrid_b200 import generator
+    from tests.test_generator import pv_first
+    B, n_steps = 131072, 24
+    gb = generator.sample(B, seed=77)
+    gen = torch.Generator(device="cuda")
+    outs, engines = {}, {}
+    for emit in ("auto", "lsu"):
+        bm = generator.engine_from_batch(gb, device="cuda:0", action_order=CONTAINER, with_flags=True)
+        if emit == "lsu":
+            bm.set_emit_image(False)
+        gen.manual_seed(12)
+        acts = [torch.rand((n_steps, g.n_envs, g.n_act), dtype=torch.float64, device="cuda", generator=gen) for g in bm.groups]
+        outs[emit] = bm.rollout(acts, ring=2)
+        engines[emit] = (bm, acts)
+        assert bm.last_kernel.startswith("mg_rollout_img_kernel" if emit == "auto" else "mg_rollout_kernel")
+    bm, acts = engines["auto"]
+    for g, a, b in zip(bm.groups, outs["auto"], outs["lsu"]):
+        assert torch.equal(a["reward"], b["reward"]) and torch.equal(a["done"], b["done"]) and torch.equal(a["obs_ring"], b["obs_ring"])
+        assert bool(torch.isfinite(a["reward"]).all())
+        assert bool((a["obs_ring"] >= 0).all()) and bool((a["obs_ring"] <= 1).all())
+        assert bool((g.step == n_steps).all())
+    rng = np.random.default_rng(3)
+    sample = np.sort(rng.choice(B, 192, replace=False))
+    plist = [gb.to_params(int(i)) for i in sample]
+    ob = OracleBatch(plist)
+    padded = np.zeros((n_steps, len(sample), 4))
+    for gi, g in enumerate(bm.groups):
+        a = acts[gi].cpu().numpy()
+        for j, e in enumerate(sample):
+            if bm.env_group[e] == gi:
+                padded[:, j, :g.n_act] = a[:, bm.env_slot[e]]
+    o_rew, o_done, o_obs = ob.rollout(padded, n_threads=4)
+    for gi, (g, r) in enumerate(zip(bm.groups, outs["auto"])):
+        rew, rows = r["reward"].cpu().numpy(), r["obs_ring"][(n_steps - 1) % 2].cpu().numpy()
+        for j, e in enumerate(sample):
+            if bm.env_group[e] == gi:
+                slot = bm.env_slot[e]
+                np.testing.assert_array_equal(rew[:, slot], o_rew[:, j], err_msg=f"grid {e}")
+                np.testing.assert_array_equal(rows[slot], pv_first(o_obs[j, :g.obs_dim], plist[j]), err_msg=f"grid {e}")
 
 
 def test_trajectory_windows_and_masked_reset():

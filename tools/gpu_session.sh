@@ -28,7 +28,7 @@ for stage in "$@"; do
     emit_tests)
       timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --maxfail=6 -k "row_emitters or rollout_kernel_equals or generator_grids_rollout or vectorised_generator or automatic_emitter or set_trajectories or trajectory_windows" > $out/${tag}_emit_tests.log 2>&1 ;;
     tune)
-      timeout 900 python tools/tune_emitters.py --steps 400 --step-path > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
+      timeout 1200 python tools/tune_emitters.py --steps 400 --step-path > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
     tune_roles)
       timeout 900 python tools/tune_emitters.py --steps 400 --variants image_ws --workloads pymgrid25,ragged,generator > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
     tune_const)
@@ -53,6 +53,8 @@ for stage in "$@"; do
       timeout 600 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_memcheck_smoke.log 2>&1
       timeout 900 compute-sanitizer --tool racecheck python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_racecheck_smoke.log 2>&1
       timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "generator_grids_rollout or automatic_emitter" > $out/${tag}_racecheck_generator.log 2>&1 ;;
+    bench_discrete)
+      timeout 300 python bench.py --workload discrete --steps 500 --warmup 5 --no-cpu > $out/${tag}_bench_discrete.json 2> $out/${tag}_bench_discrete.err ;;
     final_benches)
       timeout 600 python bench.py > $out/${tag}_bench_default.json 2> $out/${tag}_bench_default.err
       timeout 600 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_steps20.json 2> $out/${tag}_bench_steps20.err
