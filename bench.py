@@ -68,6 +68,8 @@ class ClockSampler(threading.Thread):
     timed region lasts only tens of milliseconds); falls back to the nvidia-smi query of B200_PROFILING.md."""
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
+    PERIOD_S = 0.0005
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.sm, self.reasons, self._halt = index, [], set(), threading.Event()
@@ -109,7 +111,7 @@ class ClockSampler(threading.Thread):
                 self._poll_nvml() if self._nv else self._poll_smi()
             except Exception:
                 pass
-            self._halt.wait(0.0005 if self._nv else 0.1)
+            self._halt.wait(self.PERIOD_S if self._nv else 0.1)
 
     def stop(self):
         self._halt.set()
@@ -529,7 +531,12 @@ def measure_workload(hx, workload, B, K, W, R, paths=("rollout", "graph", "eager
                     for n in chunks:
                         binds[rep % n_blocks, n]()
                 per_rep = len(chunks)
-            elif path == "graph":    # one mg_step launch per step, replayed from a CUDA graph
+            elif path in ("graph", "graph_overlap2"):    # one mg_step launch per step, replayed from a CUDA graph
+                # ("graph": the library's default chaining of consecutive step launches, MG_OPT_STEP_OVERLAP = 1 -- the next
+                #  launch's physics runs under this launch's observation stream; "graph_overlap2": the observation streams
+                #  overlap too, which the rotating observation buffers of this loop allow)
+                bm.set_step_overlap(2 if path == "graph_overlap2" else 1)
+                launchers.clear()
                 chunk = K if K <= 256 else max(d for d in range(1, 257) if K % d == 0)
                 for s in range(W + chunk):      # make every launcher of the chunk exist before capture
                     one_step(s)
@@ -564,6 +571,9 @@ def measure_workload(hx, workload, B, K, W, R, paths=("rollout", "graph", "eager
             clocks = sampler.stop()
             results[path] = {"ms": ms, "repeats": len(all_ms), "ms_min": min(all_ms), "ms_max": max(all_ms), "launches": per_rep, "clocks": clocks,
                              "kernel": bm.last_kernel}
+            if path == "graph_overlap2":
+                bm.set_step_overlap(1)
+                launchers.clear()
     out["paths"] = results
     nbytes = sum(g.n_envs * algorithmic_bytes(*g.arch, discrete=discrete, obs_bytes=4 if args.obs_f32 else 8) for g in groups)
     out["bytes_per_step"] = nbytes
@@ -709,7 +719,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="envs per GPU (default 65536; replicas 4096; generator 131072)")
     ap.add_argument("--workload", default="pymgrid25", choices=tuple(WORKLOADS), help="default = the BASELINE metric's workload")
     ap.add_argument("--ring", type=int, default=4, help="observation buffers rotated so stores reach HBM")
-    ap.add_argument("--path", default="rollout", choices=("rollout", "graph", "eager"),
+    ap.add_argument("--path", default="rollout", choices=("rollout", "graph", "graph_overlap2", "eager"),
                     help="headline path: the persistent rollout kernel (BASELINE configs[2] is a year rollout with pre-generated "
                          "actions), one mg_step launch per step replayed from a CUDA graph, or plain launches from Python")
     ap.add_argument("--single-path", action="store_true", help="time only the headline path (no other paths, no e2e, no configs block)")
@@ -728,10 +738,12 @@ def main():
     ap.add_argument("--image-shape", type=int, default=None, help="MG_OPT_IMAGE_SHAPE index (tuning)")
     ap.add_argument("--no-specialised", action="store_true", help="persistent kernel without the owner / emitter warp split (A/B)")
     ap.add_argument("--min-timed-ms", type=float, default=MIN_TIMED_MS, help="repeat a timed region until it adds up to this much")
+    ap.add_argument("--clock-period-ms", type=float, default=0.5, help="NVML polling period of the clock sampler during timed regions")
     ap.add_argument("--preheat", type=float, default=0.2, help="seconds of untimed steps before the warm-up (0 under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    ClockSampler.PERIOD_S = args.clock_period_ms * 1e-3
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "composed":
@@ -742,7 +754,7 @@ def main():
     if args.batch is None:
         args.batch = {"replicas": 4096, "generator": 131072}.get(args.workload, BATCH_PER_GPU)
     B, K, W, R = args.batch, args.steps, args.warmup, args.ring
-    paths = (args.path,) if args.single_path else (args.path,) + tuple(p for p in ("rollout", "graph", "eager") if p != args.path)
+    paths = (args.path,) if args.single_path else (args.path,) + tuple(p for p in ("rollout", "graph", "graph_overlap2", "eager") if p != args.path)
     m = measure_workload(hx, args.workload, B, K, W, R, paths=paths, with_e2e=not args.single_path, ragged=args.ragged, min_ms=args.min_timed_ms)
     head = m["paths"][args.path]
     value = world * B * K / (head["ms"] * 1e-3)

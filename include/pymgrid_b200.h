@@ -338,7 +338,7 @@ int mg_forecast_noise_at(MgHandle *h, const MgForecastNoise *noise, void *const 
  * kernel when every group writes observations.  It wins when the envs of a tile advance in lock-step (11.5 vs 12.4
  * us/step at 65 536 envs) and loses when every env is at its own step (39.6 vs 29 us/step): hosts that install per-env
  * trajectory windows turn it off. */
-enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2, MG_OPT_EMIT_IMAGE = 3, MG_OPT_IMAGE_SHAPE = 4, MG_OPT_RAGGED_HINT = 5 };
+enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2, MG_OPT_EMIT_IMAGE = 3, MG_OPT_IMAGE_SHAPE = 4, MG_OPT_RAGGED_HINT = 5, MG_OPT_STEP_OVERLAP = 6 };
 /* MG_OPT_ROLLOUT_RING (default 1): batches with per-env series (MG_LAYOUT_SCALED_SERIES / grid_status_bits) run mg_rollout
  * with every env's normalised load / pv windows held in shared memory (H + 2 slots per env and series; one new value per
  * env, series and step instead of a whole window per row) when all horizons are <= 24.  0 selects the kernel that
@@ -355,7 +355,13 @@ enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2, MG_OPT_EMIT_IMAG
  * 3: (4, 4, 2), 4: (4, 4, 4), 5: (8, 2, 4); 3-5 run the per-env-series persistent kernel at three CTAs per SM with 168
  * registers.  A tuning knob.
  * MG_OPT_RAGGED_HINT (default 0): tell the library that the envs of a tile are at unrelated steps (independent resets,
- * per-env episode windows), where no two rows share a window. */
+ * per-env episode windows), where no two rows share a window.
+ * MG_OPT_STEP_OVERLAP (default 1): chain consecutive mg_step* launches on one stream with programmatic dependent launch
+ * (griddepcontrol): a launch starts as soon as every CTA of the previous one has written and fenced the state it hands on,
+ * so its latency-bound part (state, inputs, physics) runs under the previous launch's observation stream.  1: its own rows
+ * wait for the previous launch to complete (safe for any choice of observation buffers); 2: the row streams overlap too
+ * (only launches whose observation buffers differ from those of the two launches before are chained).  Anything else
+ * enqueued between two steps (a policy's kernels, copies) simply breaks the chain: ordering is the stream's, as always. */
 int mg_set_option(MgHandle *h, int option, int value);
 
 /*

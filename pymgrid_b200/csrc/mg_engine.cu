@@ -40,9 +40,6 @@
 #define MG_WARPS (MG_THREADS / 32)
 #define MG_ROWS_PER_WARP (MG_TILE / MG_WARPS)
 #define MG_MAX_IMG 192      // longest observation row (in f64) on the staged path (3 pairs per lane); longer rows use the element-wise path
-#ifndef MG_PDL
-#define MG_PDL 0            // programmatic dependent launch between consecutive step launches: measured SLOWER (18.6 vs 16.9 us/step), off
-#endif
 #ifndef MG_ROLLOUT_WS
 #define MG_ROLLOUT_WS 1     // persistent kernel: owner warps / emitter warps pipeline (see mg_rollout_ws_kernel)
 #endif
@@ -96,6 +93,7 @@ struct DevGroup {
 
 struct LaunchParams {
     int32_t n_groups, total_tiles, T, Tp, mode, normalized, n_steps, ring;
+    int32_t pdl, _pad_pdl;      // single-step launches: chain consecutive launches with programmatic dependent launch (MG_OPT_STEP_OVERLAP)
     const MgConfig *cfg;
     const double *load_raw, *pv_raw, *grid_raw;
     const double *load_nrm, *pv_nrm, *grid_nrm;
@@ -1294,16 +1292,19 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
     const int tid = threadIdx.x;
     const int e = e0 + tid;
     if ((tid & 31) == 0 && G.obs) mbar_init(&S.bar[tid >> 5], 1);
-    pdl_wait();   // nothing above touches global memory; everything below may read what the previous launch wrote
+    // Step overlap (P.pdl, MG_OPT_STEP_OVERLAP): this grid may have started while the previous step launch is still streaming
+    // its observation rows -- the hardware only starts it once EVERY CTA of that launch has passed its trigger below, i.e.
+    // has written (and fenced) the state, reward and done this launch reads and overwrites.  The state is read past L1
+    // (ld.global.cg): an SM may still hold lines an earlier launch cached.
     double my_reward = 0.0;
     bool stepped = false;
     if (tid < n_rows) {
         const MgConfig *__restrict__ c = P.cfg + __ldg(G.cfg_index + e);
         EnvRegs s;
-        s.t = G.step[e];
-        s.charge = G.charge[e];
+        s.t = __ldcg(G.step + e);
+        s.charge = __ldcg(G.charge + e);
         s.cs = s.gs = s.up = s.dn = 0;
-        if (G.has_genset) unpack_genset(G.genset[e], s);
+        if (G.has_genset) unpack_genset(__ldcg(G.genset + e), s);
         if (P.mode == MODE_STEP || P.mode == MODE_DISCRETE) {
             const StepInputs in = fetch_inputs<kHetero>(P, G, c, e, 0, s.t);
             const int final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
@@ -1338,17 +1339,27 @@ __global__ void __launch_bounds__(MG_THREADS, kHetero ? MG_MIN_CTAS_HETERO : MG_
         }
     }
     if (G.reward_total && tid < MG_TILE) add_reward_total(G.reward_total, my_reward, stepped);   // warps 0..1, uniformly
-    // Every write a following step depends on (state, reward, done, flags, info) is issued: let the next launch's CTAs
-    // start their latency-bound part on SMs as they free up while this grid is still streaming observation rows.
-    // The host only opts the next launch into this when it writes different observation buffers (launch_step).
-    pdl_launch_dependents();
-    if (G.obs) {   // CTA-uniform
-        __syncthreads();
+    if (G.obs) __syncthreads();   // CTA-uniform: the tile records are published
+    // Every write a following step depends on (state, reward, done, flags, info) is issued: once they are visible device-wide
+    // (the fence; only the owner warps have anything pending) the trigger lets the next launch's CTAs start their
+    // latency-bound part on SMs as they free up while this grid is still streaming observation rows.  The host only chains
+    // launches that write different observation buffers (launch_step).
+    if (P.pdl) {
+        if (tid < MG_TILE) __threadfence();
+        pdl_launch_dependents();
+        // mode 1: this launch's rows wait for the launch it overlapped with to complete -- its physics ran under that
+        // launch's row stream, the row streams themselves never overlap, so any choice of observation buffers is safe
+        if (P.pdl == 1) pdl_wait();
+    }
+    if (G.obs) {
         uint32_t phase = 0;
         TO *obs_tile = reinterpret_cast<TO *>(G.obs) + (size_t)e0 * G.obs_dim;
         if (!G.long_path) warp_emit_rows<kHetero, TO>(P, G, S, het0, 0, obs_tile, n_rows, e0, phase, (tid >> 5) * MG_ROWS_PER_WARP);
         else warp_emit_rows_long<TO>(P, G, S, 0, obs_tile, n_rows);
     }
+    // mode 2: row streams of consecutive launches overlap too (the host chains only launches whose observation buffers differ
+    // from those of the two launches before); complete in launch order all the same
+    if (P.pdl == 2) pdl_wait();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1616,10 +1627,10 @@ __global__ void __launch_bounds__(MG_THREADS, 5) mg_step_img_kernel(const __grid
     if (tid < n_rows) {
         const MgConfig *__restrict__ c = P.cfg + __ldg(G.cfg_index + e);
         EnvRegs s;
-        s.t = G.step[e];
-        s.charge = G.charge[e];
+        s.t = __ldcg(G.step + e);            // (read past L1: see mg_step_kernel on step overlap)
+        s.charge = __ldcg(G.charge + e);
         s.cs = s.gs = s.up = s.dn = 0;
-        if (G.has_genset) unpack_genset(G.genset[e], s);
+        if (G.has_genset) unpack_genset(__ldcg(G.genset + e), s);
         if (P.mode == MODE_STEP || P.mode == MODE_DISCRETE) {
             const StepInputs in = fetch_inputs<kHetero>(P, G, c, e, 0, s.t);
             const int final_step = G.env_final ? __ldg(G.env_final + e) : c->final_step;
@@ -1653,8 +1664,13 @@ __global__ void __launch_bounds__(MG_THREADS, 5) mg_step_img_kernel(const __grid
         }
     }
     if (G.reward_total && tid < MG_TILE) add_reward_total(G.reward_total, my_reward, stepped);   // warps 0..1, uniformly
-    if (G.obs) {   // CTA-uniform
-        __syncthreads();
+    if (G.obs) __syncthreads();   // CTA-uniform: the tile records are published
+    if (P.pdl) {   // step overlap, as in mg_step_kernel: hand the state on, then (mode 1) let the previous launch finish its rows
+        if (tid < MG_TILE) __threadfence();
+        pdl_launch_dependents();
+        if (P.pdl == 1) pdl_wait();
+    }
+    if (G.obs) {
         const ImgCtx x = img_ctx(P, G);
         int buf = 0;
         const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (provably warp-uniform: bulk-store operands in uniform registers)
@@ -1663,6 +1679,7 @@ __global__ void __launch_bounds__(MG_THREADS, 5) mg_step_img_kernel(const __grid
                                                    warp * MG_ROWS_PER_WARP, MG_ROWS_PER_WARP, e0);
         if ((tid & 31) == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores' reads
     }
+    if (P.pdl == 2) pdl_wait();
 }
 
 template <int RC, int NB, int GB, bool kHetero, bool kRing, bool kWS, int MINB = 0>
@@ -2062,6 +2079,8 @@ struct MgHandle {
     bool rollout_ring;          // MG_OPT_ROLLOUT_RING
     int emit_image;             // MG_OPT_EMIT_IMAGE: 0 LSU row emitters, 1 image + TMA bulk stores, 2 choose per launch (default)
     bool ragged_hint;           // MG_OPT_RAGGED_HINT: the envs of a tile are (probably) at unrelated steps
+    int step_overlap;           // MG_OPT_STEP_OVERLAP: consecutive mg_step launches overlap (programmatic dependent launch): 0, 1, 2
+    const double *prev_obs[MG_MAX_GROUPS];   // observation buffers of the launch before the last one
     int n_sms;                  // multiprocessors of the device the handle was created on
     const char *last_kernel;    // mg_last_kernel
     int image_shape;            // MG_OPT_IMAGE_SHAPE: index into the instantiated (rows per bulk store, buffers) shapes
@@ -2193,6 +2212,8 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
     h->emit_image = 2;
     h->image_shape = -1;
     h->ragged_hint = false;
+    h->step_overlap = 1;
+    for (int g = 0; g < MG_MAX_GROUPS; ++g) h->prev_obs[g] = nullptr;
     h->last_kernel = "";
     h->n_sms = 148;
     {
@@ -2369,6 +2390,11 @@ extern "C" int mg_set_option(MgHandle *h, int option, int value) {
         h->ragged_hint = value != 0;
         return MG_OK;
     }
+    if (option == MG_OPT_STEP_OVERLAP) {
+        if (value < 0 || value > 2) return fail(MG_E_INVALID, "mg_set_option: MG_OPT_STEP_OVERLAP takes 0, 1 or 2");
+        h->step_overlap = value;
+        return MG_OK;
+    }
     return fail(MG_E_INVALID, "mg_set_option: unknown option");
 }
 
@@ -2439,7 +2465,8 @@ static int ensure_dynamic_smem(const void *func, size_t bytes) {
 // at most two tiles per SM (2.7-4.1 vs 6.8) and, for persistent launches, on rows with an even forecast horizon (14.1 vs
 // 15.2; deeper image queues there and for per-env series); the per-lane store emitters with their run detection for large
 // table-backed batches in lock-step -- level with the image kernels in tools/tune_emitters.py (11.44 both), 0.5 us/step
-// ahead inside bench.py's longer launches, and 3 us/step ahead for single steps (16.4 vs 19.3).
+// ahead inside bench.py's longer launches, and 3-4 us/step ahead for single steps (14.6 vs 18.9 with step overlap).  Single
+// steps use two-row bulk stores (shape 1: 21.2 vs 23.0 us/step at unrelated steps, 78.5 vs 106.8 for per-env series).
 struct EmitChoice {
     bool image, split;
     int shape;
@@ -2450,7 +2477,7 @@ static EmitChoice choose_emitters(const MgHandle *h, const LaunchParams &P, bool
     bool odd_rows = false;
     for (int g = 0; g < P.n_groups; ++g)
         if (P.g[g].has_grid && (P.g[g].horizon & 1) == 0) odd_rows = true;
-    c.shape = h->image_shape >= 0 ? h->image_shape : persistent ? ((h->hetero || odd_rows) ? 4 : 0) : (h->hetero ? 1 : 0);
+    c.shape = h->image_shape >= 0 ? h->image_shape : persistent ? ((h->hetero || odd_rows) ? 4 : 0) : 1;
     if (h->emit_image != 2) c.image = h->emit_image == 1;
     else c.image = h->hetero || h->ragged_hint || P.total_tiles <= 2 * h->n_sms || (persistent && odd_rows);
     return c;
@@ -2461,6 +2488,7 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
     LaunchParams P = h->base;
     P.mode = mode;
     P.normalized = normalized;
+    P.pdl = h->step_overlap;
     for (int g = 0; g < P.n_groups; ++g) {
         DevGroup &d = P.g[g];
         d.actions = io[g].actions; d.dactions = io[g].dactions; d.obs = io[g].obs; d.reward = io[g].reward;
@@ -2478,10 +2506,13 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
     }
     // Overlap with the previous step launch (PDL) only when that launch cannot still be writing the observation
     // buffers this one writes: the previous kernel releases its dependents before it streams its rows.
-    bool overlap = MG_PDL && h->last_was_step && h->last_stream == stream;
-    for (int g = 0; g < P.n_groups && overlap; ++g)
+    // Chain this launch to the previous one (it may start once every CTA of that launch has passed its trigger) when both
+    // are single-step launches on the same stream; in mode 2 the row streams overlap as well, so the observation buffers
+    // must differ from those of the two launches before this one.
+    bool overlap = h->step_overlap != 0 && h->last_was_step && h->last_stream == stream;
+    for (int g = 0; g < P.n_groups && overlap && h->step_overlap == 2; ++g)
         for (int q = 0; q < P.n_groups; ++q)
-            if (P.g[g].obs && P.g[g].obs == h->last_obs[q]) overlap = false;
+            if (P.g[g].obs && (P.g[g].obs == h->last_obs[q] || P.g[g].obs == h->prev_obs[q])) overlap = false;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(P.total_tiles);
@@ -2518,9 +2549,12 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
     if (!(image && any_obs)) h->last_kernel = "mg_step_kernel";
     if (mode == MODE_STEP || mode == MODE_DISCRETE) memset(h->soc_reported, 0, sizeof h->soc_reported);   // every battery updates
     h->launches += 1;
-    h->last_was_step = true;
+    h->last_was_step = P.pdl != 0;
     h->last_stream = stream;
-    for (int g = 0; g < MG_MAX_GROUPS; ++g) h->last_obs[g] = g < P.n_groups ? P.g[g].obs : nullptr;
+    for (int g = 0; g < MG_MAX_GROUPS; ++g) {
+        h->prev_obs[g] = h->last_obs[g];
+        h->last_obs[g] = g < P.n_groups ? P.g[g].obs : nullptr;
+    }
     return MG_OK;
 }
 

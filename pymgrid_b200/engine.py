@@ -753,6 +753,12 @@ class BatchedMicrogrid:
         (MG_OPT_IMAGE_SHAPE; -1 = the library's choice)."""
         self._set_option(_cabi.MG_OPT_IMAGE_SHAPE, int(index))
 
+    def set_step_overlap(self, mode):
+        """Chain consecutive single-step launches with programmatic dependent launch (MG_OPT_STEP_OVERLAP): 0 off, 1 the next
+        launch's physics runs under this launch's observation stream, 2 the observation streams overlap as well (needs
+        rotating observation buffers: three or more)."""
+        self._set_option(_cabi.MG_OPT_STEP_OVERLAP, int(mode))
+
     def set_ragged(self, on=True):
         """Tell the library that the envs of a tile are at unrelated steps (independent resets, per-env episode windows):
         no two rows share a window, and the image emitters are the faster ones (MG_OPT_RAGGED_HINT).  Set automatically by

@@ -738,30 +738,48 @@ def test_bad_discrete_action_is_flagged():
     assert bm.groups[0].step.cpu().tolist() == [1, 1, 0, 0]
 
 
-def test_overlapped_launches_equal_serial():
-    """Consecutive step launches that write DIFFERENT observation buffers overlap (programmatic dependent launch: the
-    next launch's physics starts while the previous one is still streaming rows).  Same results as serial launches."""
+@pytest.mark.parametrize("mode,graph", [(1, False), (2, False), (1, True), (2, True)])
+def test_overlapped_launches_equal_serial(mode, graph):
+    """MG_OPT_STEP_OVERLAP: consecutive step launches chained with programmatic dependent launch -- the next launch's
+    physics starts while the previous one is still streaming rows (mode 1), and the row streams overlap too when the
+    observation buffers rotate (mode 2) -- issued back to back with nothing in between, directly and replayed from a CUDA
+    graph.  Same state, rewards and rows as fully serialised launches."""
     configs = [load_pymgrid25(n) for n in range(25)]
-    B, n_steps, R = 65536, 24, 3
+    B, n_steps, R = 65536, 24, 4
     env_config = np.arange(B) % 25
     a = engine(configs, env_config, with_info=False)
     b = engine(configs, env_config, with_info=False)
+    a.set_step_overlap(mode)
+    b.set_step_overlap(0)
     gen = torch.Generator(device="cuda")
     gen.manual_seed(4)
     acts = [torch.rand((n_steps, g.n_envs, g.n_act), dtype=torch.float64, device="cuda", generator=gen) for g in a.groups]
     rings = [torch.empty((R, g.n_envs, g.obs_dim), dtype=torch.float64, device="cuda") for g in a.groups]
-    rew_a = []
-    for k in range(n_steps):       # rotating observation buffers -> overlapped launches
-        _, r, _, _ = as_lists(a.step([x[k] for x in acts], obs=[ring[k % R] for ring in rings]))
-        rew_a.append(torch.cat([x.clone() for x in r]))
+    launchers = [a.prepare_step([x[k] for x in acts], obs=[ring[k % R] for ring in rings]) for k in range(n_steps)]
+    state0 = a.state_dict()
+    if graph:
+        for f in launchers[:2]:
+            f()
+        a.load_state_dict(state0)
+        torch.cuda.synchronize()
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_):
+            for f in launchers:
+                f()
+        a.load_state_dict(state0)
+        g_.replay()
+    else:
+        for f in launchers:       # back to back: the chain is never broken
+            f()
     torch.cuda.synchronize()
-    for k in range(n_steps):       # one fixed buffer -> fully serialised launches
+    assert a.last_kernel == "mg_step_kernel"
+    for k in range(n_steps):       # one fixed buffer, a clone between the steps -> fully serialised launches
         obs_b, r, _, _ = as_lists(b.step([x[k] for x in acts]))
-        assert torch.equal(rew_a[k], torch.cat(r)), k
         if k >= n_steps - R:
             for gi in range(len(a.groups)):
                 assert torch.equal(rings[gi][k % R], obs_b[gi]), (k, gi)
     for ga, gb in zip(a.groups, b.groups):
+        assert torch.equal(ga.reward, gb.reward) and torch.equal(ga.done, gb.done)
         assert torch.equal(ga.step, gb.step) and torch.equal(ga.charge, gb.charge)
         if ga.genset is not None:
             assert torch.equal(ga.genset, gb.genset)

@@ -26,7 +26,7 @@ for stage in "$@"; do
     ragged)
       timeout 300 python bench.py --ragged --steps 500 --warmup 5 --single-path --no-cpu > $out/${tag}_bench_ragged.json 2> $out/${tag}_bench_ragged.err ;;
     emit_tests)
-      timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --maxfail=6 -k "row_emitters or rollout_kernel_equals or generator_grids_rollout or vectorised_generator or automatic_emitter or set_trajectories or trajectory_windows" > $out/${tag}_emit_tests.log 2>&1 ;;
+      timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --maxfail=6 -k "row_emitters or rollout_kernel_equals or generator_grids_rollout or vectorised_generator or automatic_emitter or set_trajectories or trajectory_windows or overlapped_launches" > $out/${tag}_emit_tests.log 2>&1 ;;
     tune)
       timeout 1200 python tools/tune_emitters.py --steps 400 --step-path > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
     tune_roles)
@@ -35,6 +35,8 @@ for stage in "$@"; do
       MG_DEBUG_CONST_ACTIONS=1 timeout 900 python tools/tune_emitters.py --steps 400 --variants default --workloads pymgrid25,ragged,generator > $out/${tag}_tune_const.jsonl 2> $out/${tag}_tune_const.err ;;
     tune_gen)
       timeout 900 python tools/tune_emitters.py --steps 400 --variants image_ws --workloads generator > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
+    tune_steps)
+      timeout 900 python tools/tune_emitters.py --steps 256 --variants lsu_ws --step-path --workloads pymgrid25,ragged,replicas,discrete,generator > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
     tune_default)
       timeout 900 python tools/tune_emitters.py --steps 400 --variants default > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
     ncu_gen)

@@ -32,6 +32,8 @@ def main():
     variants = [("lsu", 0, True), ("lsu", 0, False)] + [("image", s, ws) for s in range(6) for ws in (True, False)]
     if args.variants == "image_ws":
         variants = [("image", s, True) for s in range(6)]
+    if args.variants == "lsu_ws":
+        variants = [("lsu", 0, True), ("image", 0, True), ("image", 1, True)]
     if args.variants == "default":
         variants = [("lsu", 0, True), ("image", 0, True), ("image", 0, False)]
     K = args.steps
@@ -98,8 +100,9 @@ def main():
             except Exception as ex:     # a variant that cannot launch (shared memory) must not lose the others
                 line = {"workload": wl, "emit": emit, "shape": shape, "specialised": ws, "error": f"{type(ex).__name__}: {ex}"}
             print(json.dumps(line), flush=True)
-            if args.step_path and ws and ring:
+            for overlap in (0, 1, 2) if (args.step_path and ws and ring) else ():
                 try:
+                    bm.set_step_overlap(overlap)
                     bm.load_state_dict(state0)
                     n = min(K, 128)
                     launchers = [bm.prepare_step([a[s] for a in acts], obs=[r[s % 4] for r in rings], discrete=discrete) for s in range(n)]
@@ -120,11 +123,12 @@ def main():
                     ev1.record()
                     torch.cuda.synchronize()
                     us = 1e3 * ev0.elapsed_time(ev1) / n
-                    line = {"workload": wl, "batch": B, "path": "graph", "emit": emit, "shape": shape,
+                    line = {"workload": wl, "batch": B, "path": f"graph, step overlap {overlap}", "emit": emit, "shape": shape,
                             "us_per_step": round(us, 3), "tbs": round(nbytes / us / 1e6, 3), "frac": round(nbytes / us / 1e3 / peak, 3)}
                 except Exception as ex:
                     line = {"workload": wl, "path": "graph", "emit": emit, "shape": shape, "error": f"{type(ex).__name__}: {ex}"}
                 print(json.dumps(line), flush=True)
+                bm.set_step_overlap(1)
         del bm, acts, rings
         torch.cuda.empty_cache()
 
