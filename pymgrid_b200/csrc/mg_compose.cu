@@ -20,6 +20,7 @@
 // package (pymgrid_b200/_cabi.py loads libpymgrid_b200.so only and fails loudly without it).
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -48,6 +49,12 @@ struct MgcLaunch {
     int32_t n_plist, plist_width;
     const int32_t *env_initial, *env_final;
     const int32_t *elem;        // [obs_dim] module << 16 | offset inside the module's block (device copy owned by the handle)
+    // the gather form of the same table (device build): an observation row is series windows plus a few state elements
+    const int32_t *elem2;       // [obs_dim][2]: series element -> (module | 0x100 | forecast row << 9, offset in the block);
+                                //               state element -> (0, index q into `nts`)
+    const int32_t *nts;         // [n_nts] module << 16 | offset of the elements that are NOT series values (battery, genset)
+    int32_t n_nts, gather;      // gather: the launch stages per-env window bases / state elements in shared memory
+    int32_t hmax;               // the longest forecast horizon of the row (rows with step + hmax < T never need a fill value)
     // per call
     MgcIO io;
     int32_t mode, n_steps, ring, normalized;
@@ -131,20 +138,157 @@ MGC_DEV void mgc_emit_row(const MgcLaunch &P, double *obs, int e, int lane) {
 }
 
 #ifndef MGC_HOSTSIM
+// ---- gather emission (device build) ---------------------------------------------------------------------------------
+// The decode of mgc_emit_row is the same for every row of a batch (one composition); only the window a series element
+// comes from differs per env.  When the launch has `gather` set, the thread that has just stepped env e leaves in shared
+// memory what the emitters need for its row: the env's step, for every series module the pool index of the window's first
+// element (series_off[series_index] + t * C: two dependent loads the owner's step has just made), and the values of the
+// few elements that come from module state (battery soc / charge, the four genset integers: mgc_obs_element, one thread).
+// An emitter lane is then table entry -> base -> one load from the pre-normalised pool -> one streaming store, four
+// elements in flight per lane, and it reads no per-env state from global memory.  Rows past the end of the series take
+// mgc_obs_element (the fill row), like before.
+#define MGC_STR (MGC_TILE + 1)      // row stride of the staged tables: owners write, emitters read without bank conflicts
+
+struct MgcStage {
+    int64_t *base;      // [n_mod][MGC_STR]: address of element (t, column 0) of the module's pre-normalised series
+    double *val;        // [n_nts][MGC_STR]
+    int32_t *t;         // [MGC_TILE]
+};
+
+__device__ __forceinline__ MgcStage mgc_stage(const MgcLaunch &P, unsigned char *smem) {
+    MgcStage S;
+    S.base = reinterpret_cast<int64_t *>(smem);
+    S.val = reinterpret_cast<double *>(smem) + (size_t)P.n_mod * MGC_STR;
+    S.t = reinterpret_cast<int32_t *>(S.val + (size_t)P.n_nts * MGC_STR);
+    return S;
+}
+static size_t mgc_stage_bytes(const MgcLaunch &P) {
+    return sizeof(double) * (size_t)(P.n_mod + P.n_nts) * MGC_STR + sizeof(int32_t) * MGC_TILE;
+}
+
+__device__ __forceinline__ void mgc_stage_env(const MgcLaunch &P, const MgcStage &S, int e, int tid) {
+    const MgcView V = mgc_view(P, e);
+    const int t = P.step[e];
+    S.t[tid] = t;
+    for (int m = 0; m < P.n_mod; ++m) {
+        const int kind = P.mod[m].kind;
+        if (!mgc_is_timeseries(kind)) continue;
+        const int C = (kind == MGC_GRID) ? 4 : 1;
+        S.base[m * MGC_STR + tid] = (int64_t)(P.series_nrm + (P.series_off[(int)V.cfg[P.mod[m].param_off]] + (int64_t)t * C));
+    }
+    const double *fstate = P.fstate + (int64_t)e * P.n_fstate;
+    const int32_t *istate = P.istate + (int64_t)e * P.n_istate;
+    for (int q = 0; q < P.n_nts; ++q) {
+        const int32_t d = __ldg(P.nts + q);
+        S.val[q * MGC_STR + tid] = mgc_obs_element(V, d >> 16, d & 0xffff, t, fstate, istate);
+    }
+}
+
+// one warp, rows r0, r0 + 4, ... of the tile.  NP > 0: the lane's table entries (elements lane, lane + 32, ... < 32 NP) are
+// decoded ONCE, into the word of the staged tables the element starts from (a window base or a state value: the two
+// tables are one array of 8-byte words) and its offset inside the window; a row whose whole horizon lies inside the series
+// (t + hmax < T, one test per row) is then NP x (shared load, add, global load, streaming store) with nothing decoded.
+// Rows that touch the end of the series, and rows longer than 256 elements (NP = 0: the table is re-read in blocks of
+// four entries), decide per element.
+template <int NP>
+__device__ __forceinline__ void mgc_emit_rows_gather(const MgcLaunch &P, const MgcStage &S, double *obs, int e0, int n_tile,
+                                                     int r0, int lane) {
+    constexpr int NU = NP > 0 ? NP : 4;
+    const int2 *tab = reinterpret_cast<const int2 *>(P.elem2);
+    const int64_t *words = S.base;      // base[n_mod][STR] followed by val[n_nts][STR]
+    int2 d[NU];
+    int word[NU];
+    uint32_t is_series = 0, active = 0;
+    if (NP > 0) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int j = lane + 32 * u;
+            d[u] = (j < P.obs_dim) ? __ldg(tab + j) : make_int2(0, -1);
+            if (d[u].x & 0x100) is_series |= 1u << u;
+            if (d[u].x != 0 || d[u].y >= 0) active |= 1u << u;
+            word[u] = (d[u].x & 0x100) ? (d[u].x & 0xff) * MGC_STR : (d[u].y >= 0 ? (P.n_mod + d[u].y) * MGC_STR : 0);
+        }
+    }
+    for (int r = r0; r < n_tile; r += MGC_TILE / 32) {
+        const int t = S.t[r];
+        double *row = obs + (int64_t)(e0 + r) * P.obs_dim + lane;
+        if (NP > 0 && t + P.hmax < P.T) {
+            int64_t w[NU];
+            double v[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) w[u] = words[word[u] + r];
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+                v[u] = (is_series & (1u << u)) ? __ldg(reinterpret_cast<const double *>(w[u]) + d[u].y) : __longlong_as_double(w[u]);
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+                if (active & (1u << u)) __stcs(row + 32 * u, v[u]);
+            continue;
+        }
+        for (int j0 = 0; j0 < (NP > 0 ? 1 : P.obs_dim); j0 += 32 * NU) {
+            double v[NU];
+            uint32_t fill = 0;
+            if (NP == 0) {
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const int j = j0 + lane + 32 * u;
+                    d[u] = (j < P.obs_dim) ? __ldg(tab + j) : make_int2(0, -1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                v[u] = 0.0;
+                if (d[u].x & 0x100) {
+                    const int m = d[u].x & 0xff, h = d[u].x >> 9;
+                    if (t < P.T && t + h < P.T) v[u] = __ldg(reinterpret_cast<const double *>(S.base[m * MGC_STR + r]) + d[u].y);
+                    else fill |= 1u << u;
+                } else if (d[u].y >= 0) {
+                    v[u] = S.val[d[u].y * MGC_STR + r];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                if (fill & (1u << u))      // past the end of the series: the fill row, per element (rare)
+                    v[u] = mgc_obs_element(mgc_view(P, e0 + r), d[u].x & 0xff, d[u].y, t, nullptr, nullptr);
+                if (d[u].x != 0 || d[u].y >= 0) __stcs(row + j0 + 32 * u, v[u]);
+            }
+        }
+    }
+}
+
+// NP < 0: per-element decode (mgc_emit_row); otherwise the gather emitters above
+template <int NP>
 __global__ void __launch_bounds__(MGC_TILE) mgc_kernel(const __grid_constant__ MgcLaunch P) {
+    extern __shared__ __align__(16) unsigned char mgc_smem[];
+    constexpr bool kGather = NP >= 0;
     const int e0 = blockIdx.x * MGC_TILE;
     const int n_tile = min(MGC_TILE, P.n_envs - e0);
     const int e = e0 + threadIdx.x;
     const int n_steps = (P.mode == MGC_MODE_RUN || P.mode == MGC_MODE_RUN_DISCRETE) ? P.n_steps : 1;
+    MgcStage S;
+    if (kGather) S = mgc_stage(P, mgc_smem);
     for (int s = 0; s < n_steps; ++s) {
-        if (threadIdx.x < n_tile) mgc_owner(P, e, s);
+        if (threadIdx.x < n_tile) {
+            mgc_owner(P, e, s);
+            if (kGather && P.io.obs) mgc_stage_env(P, S, e, threadIdx.x);
+        }
         __syncthreads();      // the tile's state rows (global memory, written by their owners) are read by every thread below
         if (P.io.obs) {
             double *obs = P.io.obs + (int64_t)(s % P.ring) * P.n_envs * P.obs_dim;
-            for (int r = threadIdx.x >> 5; r < n_tile; r += MGC_TILE / 32) mgc_emit_row(P, obs, e0 + r, threadIdx.x & 31);
+            if (kGather) {
+                mgc_emit_rows_gather<(NP >= 0 ? NP : 0)>(P, S, obs, e0, n_tile, threadIdx.x >> 5, threadIdx.x & 31);
+            } else {
+                for (int r = threadIdx.x >> 5; r < n_tile; r += MGC_TILE / 32) mgc_emit_row(P, obs, e0 + r, threadIdx.x & 31);
+            }
         }
         __syncthreads();      // the next step's owners overwrite the state this step's emitters have just read
     }
+}
+
+typedef void (*MgcKernel)(const MgcLaunch);
+static MgcKernel mgc_gather_kernel_for(int obs_dim) {
+    const int np = (obs_dim + 31) / 32;
+    return np <= 2 ? mgc_kernel<2> : np <= 4 ? mgc_kernel<4> : np <= 8 ? mgc_kernel<8> : mgc_kernel<0>;
 }
 #else
 static void mgc_kernel_host(const MgcLaunch &P) {
@@ -194,6 +338,8 @@ struct MgcHandle {
     MgcLaunch base;
     int64_t launches;
     int32_t *elem;      // the element table: device memory (host memory in the host build), owned by the handle
+    int32_t *elem2, *nts;       // its gather form (device build only; see mgc_emit_row_gather)
+    int gather_smem;            // dynamic shared memory of the gather kernel, 0 = the staged tables do not fit: decode per element
 };
 
 static int32_t *mgc_table_upload(const int32_t *host, int n) {
@@ -347,11 +493,60 @@ extern "C" int mgc_create(const MgcLayout *L, MgcHandle **out) {
     MgcHandle *h = new (std::nothrow) MgcHandle();
     if (!h) { delete[] tab; return mgc_fail(MG_E_INVALID, "mgc_create: out of host memory"); }
     h->elem = mgc_table_upload(tab, L->obs_dim);
+    h->elem2 = h->nts = nullptr;
+    h->gather_smem = 0;
+    int n_nts = 0, hmax_row = 0;
+#ifndef MGC_HOSTSIM
+    const char *gather_env = getenv("PYMGRID_B200_COMPOSE_GATHER");      // "0": keep the per-element decode (A/B and tests)
+    if (h->elem && L->series_nrm && L->obs_dim > 0 && !(gather_env && gather_env[0] == '0')) {
+        // gather form: series elements carry (module, forecast row, offset), the others index the list of state elements
+        int32_t *tab2 = new (std::nothrow) int32_t[3 * (size_t)L->obs_dim];
+        if (!tab2) { delete[] tab; mgc_table_free(h->elem); delete h; return mgc_fail(MG_E_INVALID, "mgc_create: out of host memory"); }
+        int32_t *list = tab2 + 2 * (size_t)L->obs_dim;
+        bool fits = true;
+        int hmax = 0;
+        for (int j = 0; j < L->obs_dim; ++j) {
+            const int m = tab[j] >> 16, k = tab[j] & 0xffff;
+            const int kind = L->modules[m].kind;
+            if (mgc_is_timeseries(kind)) {
+                const int row = k / ((kind == MGC_GRID) ? 4 : 1);
+                if (row >= (1 << 22)) fits = false;
+                if (row > hmax) hmax = row;
+                tab2[2 * j] = m | 0x100 | (row << 9);
+                tab2[2 * j + 1] = k;
+            } else {
+                tab2[2 * j] = 0;
+                tab2[2 * j + 1] = n_nts;
+                list[n_nts++] = tab[j];
+            }
+        }
+        MgcLaunch probe;
+        probe.n_mod = L->n_modules;
+        probe.n_nts = n_nts;
+        const size_t bytes = mgc_stage_bytes(probe);
+        if (fits && bytes <= 96 * 1024) {
+            h->elem2 = mgc_table_upload(tab2, 2 * L->obs_dim);
+            h->nts = mgc_table_upload(list, n_nts);
+            if (h->elem2 && h->nts &&
+                cudaFuncSetAttribute(mgc_gather_kernel_for(L->obs_dim), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) == cudaSuccess) {
+                h->gather_smem = (int)bytes;
+            } else {
+                cudaGetLastError();
+                mgc_table_free(h->elem2);
+                mgc_table_free(h->nts);
+                h->elem2 = h->nts = nullptr;
+            }
+        }
+        hmax_row = hmax;
+        delete[] tab2;
+    }
+#endif
     delete[] tab;
     if (!h->elem) { delete h; return mgc_fail(MG_E_CUDA, "mgc_create: could not allocate the element table on the device"); }
     MgcLaunch &B = h->base;
     memset(&B, 0, sizeof B);
     B.elem = h->elem;
+    B.elem2 = h->elem2; B.nts = h->nts; B.n_nts = n_nts; B.gather = h->gather_smem > 0; B.hmax = hmax_row;
     for (int m = 0; m < L->n_modules; ++m)
         B.n_act_modules += (L->modules[m].kind == MGC_GENSET) ? 2 : (L->modules[m].kind == MGC_LOAD) ? 0 : 1;
     memcpy(B.mod, L->modules, sizeof(MgcModule) * (size_t)L->n_modules);
@@ -367,7 +562,11 @@ extern "C" int mgc_create(const MgcLayout *L, MgcHandle **out) {
 }
 
 extern "C" int mgc_destroy(MgcHandle *h) {
-    if (h) mgc_table_free(h->elem);
+    if (h) {
+        mgc_table_free(h->elem);
+        mgc_table_free(h->elem2);
+        mgc_table_free(h->nts);
+    }
     delete h;
     return MG_OK;
 }
@@ -399,7 +598,8 @@ static int mgc_launch(MgcHandle *h, const MgcIO *io, int mode, int32_t n_steps, 
     mgc_kernel_host(P);
 #else
     const int tiles = (P.n_envs + MGC_TILE - 1) / MGC_TILE;
-    mgc_kernel<<<tiles, MGC_TILE, 0, (cudaStream_t)stream>>>(P);
+    if (P.gather) mgc_gather_kernel_for(P.obs_dim)<<<tiles, MGC_TILE, h->gather_smem, (cudaStream_t)stream>>>(P);
+    else mgc_kernel<-1><<<tiles, MGC_TILE, 0, (cudaStream_t)stream>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         char msg[256];

@@ -128,3 +128,46 @@ def test_modules_step_batch_on_gpu():
 
 def test_control_dict_conventions_on_gpu():
     K.check_control_dict_conventions(None)
+
+
+def _wide_row_modules(rng, horizon):
+    """378 observation elements at horizon 30: longer than the 256 the register-resident decode covers"""
+    from pymgrid_b200 import modules as M
+    T = 120
+    ts = dict(forecaster="oracle", forecast_horizon=horizon)
+    grid_ts = np.column_stack([rng.random(T) + 0.1, rng.random(T) * 0.5, rng.random(T), (rng.random(T) > 0.2).astype(float)])
+    return ([M.LoadModule(10 + 5 * rng.random(T), **ts) for _ in range(4)] + [M.RenewableModule(8 * rng.random(T), **ts) for _ in range(4)]
+            + [M.BatteryModule(min_capacity=2, max_capacity=20, max_charge=5, max_discharge=5, efficiency=0.9, init_soc=0.5),
+               M.GensetModule(1, 12, 0.4, 2, 0.1), M.GridModule(30, 30, grid_ts, **ts)])
+
+
+@pytest.mark.parametrize("label", ["several_of_each", "pairwise_sums", "load_pv_genset", "wide_row_h30", "narrow_row_h0"])
+def test_gather_emission_equals_per_element_decode(label, monkeypatch):
+    """the staged-gather emitters (default) and the per-element decode (PYMGRID_B200_COMPOSE_GATHER=0) write the same rows,
+    rewards and states -- per-env windows that start at different steps and run past the end of the series (fill rows,
+    forecaster.py:120-149) included; rows of 378 elements (table re-read in blocks) and of 18 (one pass)"""
+    from pymgrid_b200.compose import ComposedBatch
+    from tests.compose_checks import _batch_case
+    n, T = 391, 12
+    outs = []
+    for gather in ("1", "0"):
+        monkeypatch.setenv("PYMGRID_B200_COMPOSE_GATHER", gather)
+        if label.startswith(("wide_row", "narrow_row")):
+            batch = ComposedBatch([_wide_row_modules(np.random.default_rng(4), 30 if label.startswith("wide") else 0)],
+                                  np.zeros(n, dtype=np.int64))
+        else:
+            _, batch, _ = _batch_case(None, label, n, 5)
+        comp = batch.comp
+        final = int(comp.final_step)
+        rng = np.random.default_rng(9)
+        start = rng.integers(max(final - 30, 0), final - 2, n).astype(np.int32)      # the horizon crosses the end for most envs
+        batch.step_counter.copy_(torch.from_numpy(start).to(batch.device))
+        actions = torch.from_numpy(rng.random((T, n, comp.n_act))).to(batch.device)
+        out = batch.rollout(actions, ring=3)
+        torch.cuda.synchronize()
+        outs.append((out["reward"].cpu().numpy(), out["obs_ring"].cpu().numpy(), out["done"].cpu().numpy(),
+                     batch.fstate.cpu().numpy(), batch.istate.cpu().numpy(), batch.step_counter.cpu().numpy()))
+    assert outs[0][1].shape[2] == {"wide_row_h30": 378, "narrow_row_h0": 18}.get(label, outs[0][1].shape[2])
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert outs[0][2].any()      # some envs did reach the end of their window

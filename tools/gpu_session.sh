@@ -31,6 +31,10 @@ for stage in "$@"; do
       timeout 1200 python tools/tune_emitters.py --steps 400 --step-path > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
     tune_roles)
       timeout 900 python tools/tune_emitters.py --steps 400 --variants image_ws --workloads pymgrid25,ragged,generator > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err ;;
+    tune_composed)
+      timeout 600 python tools/tune_composed.py > $out/${tag}_tune_composed.txt 2> $out/${tag}_tune_composed.err ;;
+    compose_tests)
+      timeout 900 python -m pytest tests/test_zz_gpu_compose.py -x -q -m gpu > $out/${tag}_compose_tests.log 2>&1 ;;
     tune_const)
       MG_DEBUG_CONST_ACTIONS=1 timeout 900 python tools/tune_emitters.py --steps 400 --variants default --workloads pymgrid25,ragged,generator > $out/${tag}_tune_const.jsonl 2> $out/${tag}_tune_const.err ;;
     tune_gen)
