@@ -636,6 +636,65 @@ class ComposedBatch:
             self._check(self._L.mgc_run(self._handle, C.byref(io), T, int(ring), int(bool(normalized)), self._stream()), "mgc_run")
         return dict(reward=reward, done=done, obs_ring=ring_buf, flags=self.flags)
 
+    def host_rollout(self, actions, reward, done, chunk=32, normalized=True, ring=1, obs=True):
+        """`rollout` with HOST buffers: `actions` [T, B, n_act] f64, `reward` [T, B] f64 and `done` [T, B] uint8 are pinned
+        host tensors.  The steps run in launches of `chunk` steps; the host -> device copy of the next chunk's actions, the
+        kernel of the current chunk and the device -> host copy of the previous chunk's rewards overlap on three streams
+        (two device buffers each way).  Returns dict(obs_ring, flags): the ring as the LAST launch left it (slot s % ring of
+        that launch) and the event bits OR-ed over all steps.  The caller's stream is synchronised with the copies on
+        return; the host buffers are complete after `torch.cuda.current_stream().synchronize()`."""
+        comp = self.comp
+        T = int(reward.shape[0])
+        if tuple(reward.shape) != (T, self.n_envs) or tuple(done.shape) != (T, self.n_envs):
+            raise ValueError(f"reward / done must have shape ({T}, {self.n_envs})")
+        if comp.n_act and tuple(actions.shape) != (T, self.n_envs, comp.n_act):
+            raise ValueError(f"actions must have shape ({T}, {self.n_envs}, {comp.n_act})")
+        if reward.dtype != torch.float64 or done.dtype != torch.uint8 or (comp.n_act and actions.dtype != torch.float64):
+            raise ValueError("host_rollout: actions / reward are float64, done is uint8")
+        chunk = max(1, min(int(chunk), T))
+        key = (chunk, int(ring), bool(obs))
+        st = getattr(self, "_host_rollout_state", None)
+        if st is None or st["key"] != key:
+            with self._on_device():
+                dev = self.device
+                st = dict(key=key, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev),
+                          act=[torch.empty((chunk, self.n_envs, comp.n_act), dtype=torch.float64, device=dev) for _ in range(2)],
+                          rew=[torch.empty((chunk, self.n_envs), dtype=torch.float64, device=dev) for _ in range(2)],
+                          done=[torch.empty((chunk, self.n_envs), dtype=torch.uint8, device=dev) for _ in range(2)],
+                          ring=torch.zeros((ring, self.n_envs, self.obs_dim), dtype=torch.float64, device=dev) if obs else None,
+                          flags=torch.zeros_like(self.flags),
+                          in_ready=[torch.cuda.Event() for _ in range(2)], in_free=[torch.cuda.Event() for _ in range(2)],
+                          out_ready=[torch.cuda.Event() for _ in range(2)], out_free=[torch.cuda.Event() for _ in range(2)])
+            self._host_rollout_state = st
+        with self._on_device():
+            cur = torch.cuda.current_stream(self.device)
+            st["s_in"].wait_stream(cur)
+            st["s_out"].wait_stream(cur)
+            st["flags"].zero_()
+            for c, k0 in enumerate(range(0, T, chunk)):
+                n, b = min(chunk, T - k0), c & 1
+                if comp.n_act:
+                    with torch.cuda.stream(st["s_in"]):
+                        if c >= 2:
+                            st["s_in"].wait_event(st["in_free"][b])         # the launch that read this buffer has finished
+                        st["act"][b][:n].copy_(actions[k0:k0 + n], non_blocking=True)
+                        st["in_ready"][b].record(st["s_in"])
+                    cur.wait_event(st["in_ready"][b])
+                if c >= 2:
+                    cur.wait_event(st["out_free"][b])                       # its rewards have left the device
+                out = dict(reward=st["rew"][b][:n], done=st["done"][b][:n], obs_ring=st["ring"])
+                self.rollout(st["act"][b][:n] if comp.n_act else None, n_steps=n, normalized=normalized, ring=ring, obs=obs, out=out)
+                st["flags"] |= self.flags
+                st["in_free"][b].record(cur)
+                st["out_ready"][b].record(cur)
+                with torch.cuda.stream(st["s_out"]):
+                    st["s_out"].wait_event(st["out_ready"][b])
+                    reward[k0:k0 + n].copy_(st["rew"][b][:n], non_blocking=True)
+                    done[k0:k0 + n].copy_(st["done"][b][:n], non_blocking=True)
+                    st["out_free"][b].record(st["s_out"])
+            cur.wait_stream(st["s_out"])
+        return dict(obs_ring=st["ring"], flags=st["flags"])
+
     def reset(self, mask=None):
         """Microgrid.reset (microgrid.py:205-225) for the masked envs (default all); returns every env's observation"""
         m = None if mask is None else torch.as_tensor(mask, dtype=torch.uint8, device=self.device).contiguous()

@@ -54,33 +54,26 @@ MGC_HD bool mgc_isclose(double a, double b) { return fabs(a - b) <= (1e-8 + 1e-5
  * from 0.0 below 8 addends; from 8 on, eight running sums over the full blocks of eight, combined pairwise, then the
  * remaining n % 8 values added one by one (valid up to 128 addends, where numpy starts to recurse; a microgrid has at most
  * MGC_MAX_MODULES = 64).  microgrid/utils/step.py:33-36 sums the provided / absorbed energy lists with it after the fixed,
- * after the controllable and after the flex modules, so the sum is needed at three lengths of the same list: the eight
- * running sums and the pending block are kept instead of the list (16 doubles instead of 64).
+ * after the controllable and after the flex modules, so the sum is needed at three lengths of the same list.  Kept instead
+ * of the list: the eight running sums (entry j receives every addend whose position is j mod 8, as it arrives -- the same
+ * additions in the same order as adding a completed block at once) and `seq`, numpy's result for the current length: the
+ * plain left-to-right sum while the list is shorter than 8, the pairwise combination of the running sums whenever a block
+ * of eight completes, plus the addends of the incomplete block one by one.  Reading the sum is then free.
  */
 struct MgcSum {
-    double r[8];      /* running sums over the completed blocks of eight */
-    double pend[8];   /* the current, incomplete block (the whole list while it is shorter than 8) */
+    double r[8];      /* running sums; entries at or past n % 8 still lack the current block's addend */
+    double seq;       /* numpy.sum of the first n addends */
     int n;
 };
-MGC_HD void mgc_sum_init(MgcSum &S) { S.n = 0; }
+MGC_HD void mgc_sum_init(MgcSum &S) { S.n = 0; S.seq = 0.0; }
 MGC_HD void mgc_sum_append(MgcSum &S, double v) {
-    S.pend[S.n & 7] = v;
+    const int j = S.n & 7;
+    S.r[j] = (S.n < 8) ? v : S.r[j] + v;
     S.n += 1;
-    if ((S.n & 7) == 0) {
-        if (S.n == 8) {
-            for (int j = 0; j < 8; ++j) S.r[j] = S.pend[j];
-        } else {
-            for (int j = 0; j < 8; ++j) S.r[j] += S.pend[j];
-        }
-    }
+    if ((S.n & 7) == 0) S.seq = ((S.r[0] + S.r[1]) + (S.r[2] + S.r[3])) + ((S.r[4] + S.r[5]) + (S.r[6] + S.r[7]));
+    else S.seq += v;
 }
-MGC_HD double mgc_sum_value(const MgcSum &S) {
-    const int tail = S.n & 7;
-    double res = 0.0;
-    if (S.n >= 8) res = ((S.r[0] + S.r[1]) + (S.r[2] + S.r[3])) + ((S.r[4] + S.r[5]) + (S.r[6] + S.r[7]));
-    for (int i = 0; i < tail; ++i) res += S.pend[i];
-    return res;
-}
+MGC_HD double mgc_sum_value(const MgcSum &S) { return S.seq; }
 
 /* genset_module.py:216-233 */
 MGC_HD void mgc_genset_reset_times(int cs, int U, int D, int &up, int &dn) {

@@ -141,20 +141,21 @@ def _wide_row_modules(rng, horizon):
                M.GensetModule(1, 12, 0.4, 2, 0.1), M.GridModule(30, 30, grid_ts, **ts)])
 
 
-@pytest.mark.parametrize("label", ["several_of_each", "pairwise_sums", "load_pv_genset", "wide_row_h30", "narrow_row_h0"])
+@pytest.mark.parametrize("label", ["several_of_each", "pairwise_sums", "load_pv_genset", "wide_row_h30", "narrow_row_h0", "odd_row_h2"])
 def test_gather_emission_equals_per_element_decode(label, monkeypatch):
     """the staged-gather emitters (default) and the per-element decode (PYMGRID_B200_COMPOSE_GATHER=0) write the same rows,
     rewards and states -- per-env windows that start at different steps and run past the end of the series (fill rows,
-    forecaster.py:120-149) included; rows of 378 elements (table re-read in blocks) and of 18 (one pass)"""
+    forecaster.py:120-149) included; rows of 378 elements (table re-read in blocks), of 18 (one pass)
+    and of 39 (two passes, the second partial)"""
     from pymgrid_b200.compose import ComposedBatch
     from tests.compose_checks import _batch_case
     n, T = 391, 12
     outs = []
     for gather in ("1", "0"):
         monkeypatch.setenv("PYMGRID_B200_COMPOSE_GATHER", gather)
-        if label.startswith(("wide_row", "narrow_row")):
-            batch = ComposedBatch([_wide_row_modules(np.random.default_rng(4), 30 if label.startswith("wide") else 0)],
-                                  np.zeros(n, dtype=np.int64))
+        if label.startswith(("wide_row", "narrow_row", "odd_row")):
+            mods = _wide_row_modules(np.random.default_rng(4), int(label.rsplit("_h", 1)[1]))
+            batch = ComposedBatch([mods[1:] if label.startswith("odd") else mods], np.zeros(n, dtype=np.int64))
         else:
             _, batch, _ = _batch_case(None, label, n, 5)
         comp = batch.comp
@@ -167,7 +168,36 @@ def test_gather_emission_equals_per_element_decode(label, monkeypatch):
         torch.cuda.synchronize()
         outs.append((out["reward"].cpu().numpy(), out["obs_ring"].cpu().numpy(), out["done"].cpu().numpy(),
                      batch.fstate.cpu().numpy(), batch.istate.cpu().numpy(), batch.step_counter.cpu().numpy()))
-    assert outs[0][1].shape[2] == {"wide_row_h30": 378, "narrow_row_h0": 18}.get(label, outs[0][1].shape[2])
+    assert outs[0][1].shape[2] == {"wide_row_h30": 378, "narrow_row_h0": 18, "odd_row_h2": 39}.get(label, outs[0][1].shape[2])
     for a, b in zip(*outs):
         assert np.array_equal(a, b, equal_nan=True)
     assert outs[0][2].any()      # some envs did reach the end of their window
+
+
+@pytest.mark.parametrize("chunk", [4, 5, 64])
+def test_host_rollout_equals_rollout(chunk):
+    """ComposedBatch.host_rollout (pinned host buffers, chunked launches overlapped with the copies) returns what one
+    device-side rollout returns: every reward, every done, the final state, the OR of the flags, the last rows"""
+    from tests.compose_checks import _batch_case
+    n, T = 777, 23
+    _, ref, _ = _batch_case(None, "several_of_each", n, 5)
+    _, batch, _ = _batch_case(None, "several_of_each", n, 5)
+    comp = ref.comp
+    rng = np.random.default_rng(21)
+    h_act = torch.from_numpy(rng.random((T, n, comp.n_act)) * 1.3 - 0.1).pin_memory()      # some actions out of range: flags
+    want = ref.rollout(h_act.to(ref.device), ring=1)
+    h_rew = torch.full((T, n), np.nan, dtype=torch.float64).pin_memory()
+    h_done = torch.full((T, n), 7, dtype=torch.uint8).pin_memory()
+    for _ in range(2):                                       # the second call reuses streams and buffers
+        for a in ("step_counter", "fstate", "istate"):
+            getattr(batch, a).copy_(getattr(_batch_case(None, "several_of_each", n, 5)[1], a))
+        got = batch.host_rollout(h_act, h_rew, h_done, chunk=chunk, ring=1)
+        torch.cuda.synchronize()
+        assert np.array_equal(h_rew.numpy(), want["reward"].cpu().numpy(), equal_nan=True)
+        assert np.array_equal(h_done.numpy(), want["done"].cpu().numpy())
+        assert torch.equal(got["obs_ring"], want["obs_ring"])
+        assert torch.equal(got["flags"], want["flags"]) and bool(want["flags"].any())
+        assert torch.equal(batch.fstate, ref.fstate) and torch.equal(batch.istate, ref.istate)
+        assert torch.equal(batch.step_counter, ref.step_counter)
+    with pytest.raises(ValueError):
+        batch.host_rollout(h_act[:3], h_rew, h_done)
