@@ -184,6 +184,22 @@ __device__ __forceinline__ void mgc_stage_env(const MgcLaunch &P, const MgcStage
     }
 }
 
+// a series element: the windows of neighbouring envs and steps overlap -- keep their lines in L1 ahead of everything else
+__device__ __forceinline__ double mgc_load_series(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// a row element: written once, never read by this kernel -- the store must not claim L1 lines the gathers live on
+__device__ __forceinline__ void mgc_store_row(double *p, double v) {
+#ifdef MGC_STORE_CS
+    __stcs(p, v);
+#else
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+#endif
+}
+
 // one warp, rows r0, r0 + 4, ... of the tile.  NP > 0: the lane's table entries (elements lane, lane + 32, ... < 32 NP) are
 // decoded ONCE, into the word of the staged tables the element starts from (a window base or a state value: the two
 // tables are one array of 8-byte words) and its offset inside the window; a row whose whole horizon lies inside the series
@@ -219,10 +235,10 @@ __device__ __forceinline__ void mgc_emit_rows_gather(const MgcLaunch &P, const M
             for (int u = 0; u < NU; ++u) w[u] = words[word[u] + r];
 #pragma unroll
             for (int u = 0; u < NU; ++u)
-                v[u] = (is_series & (1u << u)) ? __ldg(reinterpret_cast<const double *>(w[u]) + d[u].y) : __longlong_as_double(w[u]);
+                v[u] = (is_series & (1u << u)) ? mgc_load_series(reinterpret_cast<const double *>(w[u]) + d[u].y) : __longlong_as_double(w[u]);
 #pragma unroll
             for (int u = 0; u < NU; ++u)
-                if (active & (1u << u)) __stcs(row + 32 * u, v[u]);
+                if (active & (1u << u)) mgc_store_row(row + 32 * u, v[u]);
             continue;
         }
         for (int j0 = 0; j0 < (NP > 0 ? 1 : P.obs_dim); j0 += 32 * NU) {
@@ -250,7 +266,7 @@ __device__ __forceinline__ void mgc_emit_rows_gather(const MgcLaunch &P, const M
             for (int u = 0; u < NU; ++u) {
                 if (fill & (1u << u))      // past the end of the series: the fill row, per element (rare)
                     v[u] = mgc_obs_element(mgc_view(P, e0 + r), d[u].x & 0xff, d[u].y, t, nullptr, nullptr);
-                if (d[u].x != 0 || d[u].y >= 0) __stcs(row + j0 + 32 * u, v[u]);
+                if (d[u].x != 0 || d[u].y >= 0) mgc_store_row(row + j0 + 32 * u, v[u]);
             }
         }
     }
