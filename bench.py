@@ -691,6 +691,45 @@ def measure_workload(hx, workload, B, K, W, R, paths=("rollout", "graph", "eager
             break
     if errors:
         e2e["host_rollout_errors"] = errors
+    # (3) the same host-buffer rollout with FLOAT32 actions (what a policy network emits; widened exactly on the device, the
+    #     arithmetic stays f64: bm.set_action_dtype) -- half the host -> device bytes.  Reported beside the f64 figure, which
+    #     stays the headline (the reference's callers pass float64).
+    if not discrete:
+        err, hr = None, None
+        try:
+            restore()
+            bm.set_action_dtype(torch.float32)
+            hr = bm.host_rollout(Kr, chunk=chunk, normalized=True, ring=R)
+            for a in hr.actions:
+                a.uniform_(0.0, 1.0)
+            with torch.cuda.stream(stream):
+                hr.run(min(Kr, 3 * chunk) if Kr % chunk == 0 else Kr)
+                restore()
+        except Exception as ex:
+            err = f"{type(ex).__name__}: {ex}"
+        if hx.max_over_ranks(0.0 if err is None else 1.0) == 0.0:
+            state = {"err": None}
+
+            def run_f32(rep):
+                if state["err"] is None:
+                    try:
+                        hr.run()
+                    except Exception as ex:
+                        state["err"] = f"{type(ex).__name__}: {ex}"
+            with torch.cuda.stream(stream):
+                ms_f, reps_f = hx.timed(run_f32, restore, min_ms=min_ms, max_reps=20)
+            err = state["err"]
+            if err is None:
+                e2e["float32_actions"] = {"value": world * B * Kr / (ms_f * 1e-3), "unit": UNIT,
+                                          "h2d_bytes_per_step": hr.h2d_bytes_per_step, "d2h_bytes_per_step": hr.d2h_bytes_per_step,
+                                          "steps": Kr, "chunk_steps": chunk, "repeats": len(reps_f),
+                                          "note": "the same call after set_action_dtype(torch.float32): the actions cross the bus as "
+                                                  "float32 and are widened exactly on the device (bit-identical to float64 actions of "
+                                                  "the same values)"}
+        if err is not None:
+            e2e["float32_actions"] = {"error": err}
+        hr = None
+        bm.set_action_dtype(torch.float64)
     e2e["obs_to_host"] = obs_host
     out["e2e"] = e2e
     del bm

@@ -186,7 +186,7 @@ typedef struct MgLayout {
 
 /* per-group arguments of one step */
 typedef struct MgStepIO {
-    const double *actions;   /* [n, n_act] f64: normalised in [0,1] or unnormalised (mg_step)                  */
+    const double *actions;   /* [n, n_act] f64 (float32 under MG_OPT_ACTIONS_F32): normalised in [0,1] or unnormalised */
     const int32_t *dactions; /* [n] int32 priority-list index (mg_step_discrete)                              */
     double *obs;             /* [n, obs_dim] normalised post-step observation (float* with MG_LAYOUT_OBS_F32), or NULL to skip */
     double *reward;          /* [n]                                                                           */
@@ -200,7 +200,7 @@ typedef struct MgStepIO {
 
 /* per-group arguments of a multi-step rollout: leading dimension is the step */
 typedef struct MgRolloutIO {
-    const double *actions;   /* [n_steps, n, n_act] (mg_rollout)                                              */
+    const double *actions;   /* [n_steps, n, n_act] (mg_rollout); float32 under MG_OPT_ACTIONS_F32             */
     const int32_t *dactions; /* [n_steps, n]        (mg_rollout_discrete); [n] when dactions_const != 0         */
     double *obs_ring;        /* [ring, n, obs_dim]: step s writes slot s % ring; NULL to skip observations    */
     double *reward;          /* [n_steps, n]                                                                  */
@@ -289,7 +289,7 @@ int mg_rollout_discrete(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, int
  * DEVICE ring (every chunk restarts at slot 0: step s of a chunk writes slot s % ring).
  */
 typedef struct MgHostRolloutIO {
-    const double *actions;   /* HOST [n_steps, n, n_act] f64 (discrete == 0)                                  */
+    const double *actions;   /* HOST [n_steps, n, n_act] f64 (discrete == 0); float32 under MG_OPT_ACTIONS_F32 */
     const int32_t *dactions; /* HOST [n_steps, n] int32 priority-list index (discrete != 0)                   */
     double *reward;          /* HOST [n_steps, n]                                                             */
     uint8_t *done;           /* HOST [n_steps, n]                                                             */
@@ -338,7 +338,8 @@ int mg_forecast_noise_at(MgHandle *h, const MgForecastNoise *noise, void *const 
  * kernel when every group writes observations.  It wins when the envs of a tile advance in lock-step (11.5 vs 12.4
  * us/step at 65 536 envs) and loses when every env is at its own step (39.6 vs 29 us/step): hosts that install per-env
  * trajectory windows turn it off. */
-enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2, MG_OPT_EMIT_IMAGE = 3, MG_OPT_IMAGE_SHAPE = 4, MG_OPT_RAGGED_HINT = 5, MG_OPT_STEP_OVERLAP = 6 };
+enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2, MG_OPT_EMIT_IMAGE = 3, MG_OPT_IMAGE_SHAPE = 4, MG_OPT_RAGGED_HINT = 5, MG_OPT_STEP_OVERLAP = 6,
+       MG_OPT_ACTIONS_F32 = 7 };
 /* MG_OPT_ROLLOUT_RING (default 1): batches with per-env series (MG_LAYOUT_SCALED_SERIES / grid_status_bits) run mg_rollout
  * with every env's normalised load / pv windows held in shared memory (H + 2 slots per env and series; one new value per
  * env, series and step instead of a whole window per row) when all horizons are <= 24.  0 selects the kernel that
@@ -361,7 +362,11 @@ enum { MG_OPT_ROLLOUT_SPECIALISED = 1, MG_OPT_ROLLOUT_RING = 2, MG_OPT_EMIT_IMAG
  * so its latency-bound part (state, inputs, physics) runs under the previous launch's observation stream.  1: its own rows
  * wait for the previous launch to complete (safe for any choice of observation buffers); 2: the row streams overlap too
  * (only launches whose observation buffers differ from those of the two launches before are chained).  Anything else
- * enqueued between two steps (a policy's kernels, copies) simply breaks the chain: ordering is the stream's, as always. */
+ * enqueued between two steps (a policy's kernels, copies) simply breaks the chain: ordering is the stream's, as always.
+ * MG_OPT_ACTIONS_F32 (default 0): every `actions` pointer given to mg_step / mg_rollout / mg_rollout_host afterwards holds
+ * float32 values in the same shape (a policy network's output as it is; half the bytes over PCIe for mg_rollout_host).  Each
+ * value is widened to f64 exactly and the step computes what the reference computes for np.float64(action): all arithmetic
+ * stays f64.  Rows of four must be 16-byte aligned, rows of two 8-byte. */
 int mg_set_option(MgHandle *h, int option, int value);
 
 /*

@@ -22,6 +22,7 @@ MG_OPT_EMIT_IMAGE = 3
 MG_OPT_IMAGE_SHAPE = 4
 MG_OPT_RAGGED_HINT = 5
 MG_OPT_STEP_OVERLAP = 6
+MG_OPT_ACTIONS_F32 = 7
 
 FLAG_NAMES = {
     1 << 0: "GENSET_GOAL_RANGE", 1 << 1: "GENSET_AS_SINK", 1 << 2: "BALANCE", 1 << 3: "BATTERY_MIN_CAP",

@@ -69,6 +69,7 @@ struct DevGroup {
     int32_t state_start, state_genset_first;   // the battery + genset run: first element and order
     int32_t long_path;                         // rows too long for the staged path, or a state run at an odd element
     int32_t img_ok;                            // rows can be assembled by the image emitter (even grid offset, 1 + H <= 32)
+    int32_t act_f32;                           // `actions` points at float32 values (MG_OPT_ACTIONS_F32)
     int32_t *step;
     double *charge;
     uint32_t *genset;
@@ -1194,28 +1195,39 @@ struct ActionRegs {
     double goal, gen, bat, grid;
 };
 
-// read one env's action row into the four logical controls (coalesced 16-byte loads where rows allow it)
-__device__ __forceinline__ ActionRegs read_action(const DevGroup &G, const double *__restrict__ row) {
+// read one env's action row into the four logical controls (one or two vector loads where rows allow it); T = double, or
+// float when the caller's actions are float32 (MG_OPT_ACTIONS_F32: widened exactly, the arithmetic stays f64)
+template <typename T> struct ActVec;
+template <> struct ActVec<double> { typedef double2 v2; };
+template <> struct ActVec<float> { typedef float2 v2; };
+template <typename T>
+__device__ __forceinline__ ActionRegs read_action_t(const DevGroup &G, const T *__restrict__ row) {
+    typedef typename ActVec<T>::v2 V2;
     ActionRegs a;
     a.goal = a.gen = a.grid = 0.0;
-    if (G.n_act == 2) {          // battery + grid in either order: one 16-byte load
-        const double2 v = __ldg(reinterpret_cast<const double2 *>(row));
-        a.bat = G.act_col_battery == 0 ? v.x : v.y;
-        a.grid = G.act_col_grid == 0 ? v.x : v.y;
-    } else if (G.n_act == 4) {   // two 16-byte loads
-        const double2 v0 = __ldg(reinterpret_cast<const double2 *>(row));
-        const double2 v1 = __ldg(reinterpret_cast<const double2 *>(row) + 1);
+    if (G.n_act == 2) {          // battery + grid in either order: one vector load
+        const V2 v = __ldg(reinterpret_cast<const V2 *>(row));
+        a.bat = G.act_col_battery == 0 ? (double)v.x : (double)v.y;
+        a.grid = G.act_col_grid == 0 ? (double)v.x : (double)v.y;
+    } else if (G.n_act == 4) {   // two vector loads
+        const V2 v0 = __ldg(reinterpret_cast<const V2 *>(row));
+        const V2 v1 = __ldg(reinterpret_cast<const V2 *>(row) + 1);
+        const double x0 = v0.x, y0 = v0.y, x1 = v1.x, y1 = v1.y;
         const int cg = G.act_col_genset, cb = G.act_col_battery, cr = G.act_col_grid;
-        a.goal = cg == 0 ? v0.x : cg == 1 ? v0.y : v1.x;
-        a.gen = cg == 0 ? v0.y : cg == 1 ? v1.x : v1.y;
-        a.bat = cb == 0 ? v0.x : cb == 1 ? v0.y : cb == 2 ? v1.x : v1.y;
-        a.grid = cr == 0 ? v0.x : cr == 1 ? v0.y : cr == 2 ? v1.x : v1.y;
+        a.goal = cg == 0 ? x0 : cg == 1 ? y0 : x1;
+        a.gen = cg == 0 ? y0 : cg == 1 ? x1 : y1;
+        a.bat = cb == 0 ? x0 : cb == 1 ? y0 : cb == 2 ? x1 : y1;
+        a.grid = cr == 0 ? x0 : cr == 1 ? y0 : cr == 2 ? x1 : y1;
     } else {
-        a.bat = __ldg(row + G.act_col_battery);
-        if (G.has_genset) { a.goal = __ldg(row + G.act_col_genset); a.gen = __ldg(row + G.act_col_genset + 1); }
-        if (G.has_grid) a.grid = __ldg(row + G.act_col_grid);
+        a.bat = (double)__ldg(row + G.act_col_battery);
+        if (G.has_genset) { a.goal = (double)__ldg(row + G.act_col_genset); a.gen = (double)__ldg(row + G.act_col_genset + 1); }
+        if (G.has_grid) a.grid = (double)__ldg(row + G.act_col_grid);
     }
     return a;
+}
+__device__ __forceinline__ ActionRegs read_action(const DevGroup &G, size_t elem) {      // elem: index of the row's first element
+    if (G.act_f32) return read_action_t<float>(G, reinterpret_cast<const float *>(G.actions) + elem);
+    return read_action_t<double>(G, G.actions + elem);
 }
 
 // Inputs of one env-step, fetched by the owner thread BEFORE the tile's observation rows are streamed out so that
@@ -1244,7 +1256,7 @@ __device__ __forceinline__ StepInputs fetch_inputs(const LaunchParams &P, const 
             in.invalid_flag = MG_FLAG_BAD_ACTION;
         }
     } else {
-        in.act = read_action(G, G.actions + (size_t)step * G.act_step_stride + (size_t)e * G.n_act);
+        in.act = read_action(G, (size_t)step * G.act_step_stride + (size_t)e * G.n_act);
     }
     if (in.valid) in.raw = gather_raw<kHetero>(P, G, c, e, t);
     else in.raw.load = in.raw.pv = in.raw.imp = in.raw.exp_ = in.raw.co2 = in.raw.status = 0.0;
@@ -2079,6 +2091,7 @@ struct MgHandle {
     bool rollout_ring;          // MG_OPT_ROLLOUT_RING
     int emit_image;             // MG_OPT_EMIT_IMAGE: 0 LSU row emitters, 1 image + TMA bulk stores, 2 choose per launch (default)
     bool ragged_hint;           // MG_OPT_RAGGED_HINT: the envs of a tile are (probably) at unrelated steps
+    int actions_f32;            // MG_OPT_ACTIONS_F32: every `actions` pointer the handle is given holds float32
     int step_overlap;           // MG_OPT_STEP_OVERLAP: consecutive mg_step launches overlap (programmatic dependent launch): 0, 1, 2
     const double *prev_obs[MG_MAX_GROUPS];   // observation buffers of the launch before the last one
     int n_sms;                  // multiprocessors of the device the handle was created on
@@ -2213,6 +2226,7 @@ extern "C" int mg_create(const MgLayout *L, void *stream, MgHandle **out) {
     h->image_shape = -1;
     h->ragged_hint = false;
     h->step_overlap = 1;
+    h->actions_f32 = 0;
     for (int g = 0; g < MG_MAX_GROUPS; ++g) h->prev_obs[g] = nullptr;
     h->last_kernel = "";
     h->n_sms = 148;
@@ -2390,6 +2404,10 @@ extern "C" int mg_set_option(MgHandle *h, int option, int value) {
         h->ragged_hint = value != 0;
         return MG_OK;
     }
+    if (option == MG_OPT_ACTIONS_F32) {
+        h->actions_f32 = value != 0;
+        return MG_OK;
+    }
     if (option == MG_OPT_STEP_OVERLAP) {
         if (value < 0 || value > 2) return fail(MG_E_INVALID, "mg_set_option: MG_OPT_STEP_OVERLAP takes 0, 1 or 2");
         h->step_overlap = value;
@@ -2501,8 +2519,9 @@ static int launch_step(MgHandle *h, const MgStepIO *io, int mode, int normalized
         if ((mode == MODE_STEP || mode == MODE_DISCRETE) && (!d.reward || !d.done)) return fail(MG_E_INVALID, "step: null reward / done");
         if ((mode == MODE_OBSERVE) && !d.obs) return fail(MG_E_INVALID, "mg_observe: null obs");
         if (d.obs && (((uintptr_t)d.obs) & 15)) return fail(MG_E_INVALID, "step: obs must be 16-byte aligned");
-        if (d.actions && (d.n_act == 2 || d.n_act == 4) && (((uintptr_t)d.actions) & 15))
-            return fail(MG_E_INVALID, "step: actions must be 16-byte aligned");
+        d.act_f32 = h->actions_f32;
+        if (d.actions && (d.n_act == 2 || d.n_act == 4) && (((uintptr_t)d.actions) & (d.act_f32 ? 4 * d.n_act - 1 : 15)))
+            return fail(MG_E_INVALID, "step: actions must be 16-byte aligned (float32 rows of two: 8-byte)");
     }
     // Overlap with the previous step launch (PDL) only when that launch cannot still be writing the observation
     // buffers this one writes: the previous kernel releases its dependents before it streams its rows.
@@ -2591,8 +2610,12 @@ static int launch_rollout(MgHandle *h, const MgRolloutIO *io, int32_t n_steps, i
         if (mode == MODE_DISCRETE && (!d.dactions || !P.plist)) return fail(MG_E_INVALID, "mg_rollout_discrete: null actions or priority lists");
         if (!d.reward || !d.done) return fail(MG_E_INVALID, "rollout: null reward / done");
         if (d.obs && (((uintptr_t)d.obs) & 15)) return fail(MG_E_INVALID, "rollout: obs_ring must be 16-byte aligned");
-        if (d.actions && (d.n_act == 2 || d.n_act == 4) && ((((uintptr_t)d.actions) & 15) || ((d.act_step_stride * 8) & 15)))
-            return fail(MG_E_INVALID, "rollout: action rows must stay 16-byte aligned across steps");
+        d.act_f32 = h->actions_f32;
+        if (d.actions && (d.n_act == 2 || d.n_act == 4)) {
+            const uintptr_t mask = d.act_f32 ? 4 * d.n_act - 1 : 15;
+            if ((((uintptr_t)d.actions) & mask) || ((d.act_step_stride * (d.act_f32 ? 4 : 8)) & mask))
+                return fail(MG_E_INVALID, "rollout: action rows must stay 16-byte aligned across steps (float32 rows of two: 8-byte)");
+        }
     }
     // per-env series rows are expensive to assemble: four emitting warps beat two there (98 vs 120 us/step measured)
     bool ws = MG_ROLLOUT_WS != 0 && !h->hetero && h->rollout_specialised;
@@ -2695,7 +2718,8 @@ extern "C" int mg_rollout_host(MgHandle *h, const MgHostRolloutIO *io, int32_t n
         const DevGroup &d = h->base.g[g];
         if (discrete ? !io[g].dactions : !io[g].actions) return fail(MG_E_INVALID, "mg_rollout_host: null host actions");
         if (!io[g].reward || !io[g].done) return fail(MG_E_INVALID, "mg_rollout_host: null host reward / done");
-        act_row[g] = discrete ? (size_t)d.n_envs * sizeof(int32_t) : (size_t)d.n_envs * d.n_act * sizeof(double);   // bytes per step
+        act_row[g] = discrete ? (size_t)d.n_envs * sizeof(int32_t)
+                              : (size_t)d.n_envs * d.n_act * (h->actions_f32 ? sizeof(float) : sizeof(double));   // bytes per step
         in_off[g] = in_bytes;
         in_bytes += align256(act_row[g] * chunk);
         rew_off[g] = out_bytes;

@@ -164,7 +164,7 @@ def _ptr(t):
 class HostIO:
     """Host-side view of one step for callers whose actions live in host memory (the reference's callers all do).
 
-    `actions` (list of pinned [n, n_act] float64 host tensors, one per group; int32 [n] when discrete) is filled by
+    `actions` (list of pinned [n, n_act] host tensors of `bm.action_dtype`, one per group; int32 [n] when discrete) is filled by
     the caller; `step()` uploads them with ONE host->device copy, launches the fused kernel and brings reward + done
     back with ONE device->host copy; `reward` / `done` are pinned host views valid after `sync()`.  Observations stay
     on the device (`bm.groups[g].obs`) unless `fetch_obs()` is called.
@@ -173,8 +173,8 @@ class HostIO:
     def __init__(self, bm, normalized=True, discrete=False, obs=True, use_graph=False):
         self.bm = bm
         self._use_graph, self._graph = use_graph, None
-        dt = torch.int32 if discrete else torch.float64
-        item = 4 if discrete else 8
+        dt = torch.int32 if discrete else bm.action_dtype
+        item = 4 if discrete else dt.itemsize
         sizes = [g.n_envs * (1 if discrete else g.n_act) for g in bm.groups]
         offs, total = [], 0
         for n in sizes:
@@ -227,7 +227,7 @@ class HostRollout:
         current stream :  mg_rollout(chunk c) .. mg_rollout(chunk c+1)      (persistent kernel, `chunk` steps per launch)
         copy-out stream:  D2H reward/done c-1 .. D2H reward/done c ....
 
-    `actions[g]`: pinned float64 [n_steps, n_g, n_act] (int32 [n_steps, n_g] when discrete), filled by the caller;
+    `actions[g]`: pinned [n_steps, n_g, n_act] of `bm.action_dtype` (int32 [n_steps, n_g] when discrete), filled by the caller;
     `reward[g]` / `done[g]`: pinned [n_steps, n_g] float64 / uint8, valid after `sync()`.  Per step the same bytes cross
     the bus as in `HostIO.step()` (all actions in, reward + done out); observations go to a device ring of `ring`
     buffers (`obs_ring[g]`; every chunk restarts at slot 0: step s of a chunk writes slot s % ring), where a policy or a
@@ -249,14 +249,14 @@ class HostRollout:
         self.bm, self.n_steps, self.chunk, self.ring = bm, int(n_steps), int(min(chunk, n_steps)), int(ring)
         self.discrete, self.normalized, self.pipeline = bool(discrete), bool(normalized), pipeline
         dev, C = bm.device, self.chunk
-        adt = torch.int32 if discrete else torch.float64
+        adt = torch.int32 if discrete else bm.action_dtype
         ashape = (lambda g: (g.n_envs,)) if discrete else (lambda g: (g.n_envs, g.n_act))
         self.actions = [torch.empty((self.n_steps,) + ashape(g), dtype=adt, pin_memory=True) for g in bm.groups]
         self.reward = [torch.empty((self.n_steps, g.n_envs), dtype=torch.float64, pin_memory=True) for g in bm.groups]
         self.done = [torch.empty((self.n_steps, g.n_envs), dtype=torch.uint8, pin_memory=True) for g in bm.groups]
         self.obs_ring = [torch.empty((ring, g.n_envs, g.obs_dim), dtype=bm.obs_dtype, device=dev) if keep_obs else None
                          for g in bm.groups]
-        item = 4 if discrete else 8
+        item = 4 if discrete else adt.itemsize
         self.h2d_bytes_per_step = sum(a[0].numel() * item for a in self.actions)
         self.d2h_bytes_per_step = 9 * bm.n_envs
         self._launch0 = bm.launch_count
@@ -759,6 +759,20 @@ class BatchedMicrogrid:
         rotating observation buffers: three or more)."""
         self._set_option(_cabi.MG_OPT_STEP_OVERLAP, int(mode))
 
+    @property
+    def action_dtype(self):
+        return torch.float32 if getattr(self, "_options", {}).get(_cabi.MG_OPT_ACTIONS_F32) else torch.float64
+
+    def set_action_dtype(self, dtype):
+        """The element type of every continuous `actions` tensor given to step / rollout / HostIO / HostRollout from now on:
+        torch.float64 (default, the reference's) or torch.float32 -- a policy network's output as it is, and half the bytes
+        over PCIe for host-resident actions.  float32 values are widened exactly; the arithmetic stays f64, so the step is
+        the reference's step for `np.float64(action)` (MG_OPT_ACTIONS_F32).  Launchers bound earlier (`prepare_step`,
+        HostIO, HostRollout) keep the tensors they were built with: build them after this call."""
+        if dtype not in (torch.float64, torch.float32):
+            raise ValueError("action dtype must be torch.float64 or torch.float32")
+        self._set_option(_cabi.MG_OPT_ACTIONS_F32, dtype == torch.float32)
+
     def set_ragged(self, on=True):
         """Tell the library that the envs of a tile are at unrelated steps (independent resets, per-env episode windows):
         no two rows share a window, and the image emitters are the faster ones (MG_OPT_RAGGED_HINT).  Set automatically by
@@ -816,8 +830,9 @@ class BatchedMicrogrid:
         for gi, g in enumerate(self.groups):
             a, d, m, o = acts[gi], dacts[gi], masks[gi], obs_bufs[gi]
             if a is not None:
-                if a.dtype != torch.float64 or a.shape != (g.n_envs, g.n_act) or not a.is_contiguous() or a.device != self.device:
-                    raise ValueError(f"group {gi}: actions must be a contiguous float64 [{g.n_envs}, {g.n_act}] tensor on {self.device}")
+                if a.dtype != self.action_dtype or a.shape != (g.n_envs, g.n_act) or not a.is_contiguous() or a.device != self.device:
+                    raise ValueError(f"group {gi}: actions must be a contiguous {self.action_dtype} [{g.n_envs}, {g.n_act}] tensor on "
+                                     f"{self.device}")
             if d is not None:
                 if d.dtype != torch.int32 or d.shape != (g.n_envs,) or not d.is_contiguous() or d.device != self.device:
                     raise ValueError(f"group {gi}: discrete actions must be a contiguous int32 [{g.n_envs}] tensor on {self.device}")
@@ -935,8 +950,8 @@ class BatchedMicrogrid:
             a = acts[gi]
             io[gi].dactions_const = int(constant_actions)
             want = (g.n_envs,) if constant_actions else (n_steps, g.n_envs) if discrete else (n_steps, g.n_envs, g.n_act)
-            if tuple(a.shape) != want or a.dtype != (torch.int32 if discrete else torch.float64) or not a.is_contiguous():
-                raise ValueError(f"group {gi}: rollout actions must be contiguous {want}")
+            if tuple(a.shape) != want or a.dtype != (torch.int32 if discrete else self.action_dtype) or not a.is_contiguous():
+                raise ValueError(f"group {gi}: rollout actions must be contiguous {want} of {torch.int32 if discrete else self.action_dtype}")
             r = out[gi] if out is not None else dict(reward=torch.empty((n_steps, g.n_envs), dtype=torch.float64, device=self.device),
                      done=torch.empty((n_steps, g.n_envs), dtype=torch.uint8, device=self.device),
                      obs_ring=torch.empty((ring, g.n_envs, g.obs_dim), dtype=self.obs_dtype, device=self.device) if keep_obs else None,

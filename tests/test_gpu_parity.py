@@ -976,3 +976,58 @@ def test_reward_shapers_golden_and_oracle(golden):
             assert (int(flags[e]) & 0xffff) == (err & 0xffff), (e, k)
             n_flagged += bool(err & (1 << 7))
     assert n_flagged > 20
+
+
+@pytest.mark.parametrize("emit", ["lsu", "image"])
+def test_float32_actions_equal_their_float64_widening(emit):
+    """set_action_dtype(torch.float32): a policy's float32 actions are widened exactly on the device, so steps, rollouts,
+    HostIO and HostRollout give bit for bit what the float64 path gives for `actions.double()` -- all three action widths
+    (2, 3 and 4 columns: vector and scalar loads), normalised and not, partial tiles."""
+    rng = np.random.default_rng(31)
+    configs = [load_pymgrid25(n) for n in range(25)]
+    B, T = 1733, 9
+    env_config = rng.integers(0, 25, B)
+    ref, bm = engine(configs, env_config), engine(configs, env_config)
+    for e in (ref, bm):
+        e.set_emit_image(emit == "image")
+    bm.set_action_dtype(torch.float32)
+    assert bm.action_dtype == torch.float32 and ref.action_dtype == torch.float64
+    a32 = [torch.from_numpy(rng.random((T, g.n_envs, g.n_act)).astype(np.float32)).cuda() for g in bm.groups]
+    a64 = [a.double() for a in a32]
+    assert sorted({g.n_act for g in bm.groups}) == [2, 3, 4]
+    # persistent rollout
+    want, got = ref.rollout([a[:5].contiguous() for a in a64], ring=2), bm.rollout([a[:5].contiguous() for a in a32], ring=2)
+    for w, g in zip(want, got):
+        for k in ("reward", "done", "obs_ring"):
+            assert torch.equal(w[k], g[k]), k
+    # single steps, normalised and unnormalised
+    for k, normalized in ((5, True), (6, False)):
+        w = as_lists(ref.step([a[k].contiguous() for a in a64], normalized=normalized))
+        g = as_lists(bm.step([a[k].contiguous() for a in a32], normalized=normalized))
+        for wo, go, wr, gr in zip(w[0], g[0], w[1], g[1]):
+            assert torch.equal(wo, go) and torch.equal(wr, gr)
+    # host-resident actions: one step, then a pipelined rollout in chunks of two
+    hio_w, hio_g = ref.host_io(), bm.host_io()
+    for hw, hg, aw, ag in zip(hio_w.actions, hio_g.actions, a64, a32):
+        hw.copy_(aw[7].cpu())
+        hg.copy_(ag[7].cpu())
+    hio_w.step(); hio_g.step()
+    hio_w.sync(); hio_g.sync()
+    assert torch.equal(hio_w.reward, hio_g.reward) and torch.equal(hio_w.done, hio_g.done)
+    hr_w, hr_g = ref.host_rollout(2, chunk=1), bm.host_rollout(2, chunk=1)
+    assert hr_g.h2d_bytes_per_step * 2 == hr_w.h2d_bytes_per_step
+    for hw, hg, aw, ag in zip(hr_w.actions, hr_g.actions, a64, a32):
+        hw.copy_(aw[7:9].cpu())
+        hg.copy_(ag[7:9].cpu())
+    hr_w.run(); hr_g.run()
+    hr_w.sync(); hr_g.sync()
+    for rw, rg, dw, dg in zip(hr_w.reward, hr_g.reward, hr_w.done, hr_g.done):
+        assert torch.equal(rw, rg) and torch.equal(dw, dg)
+    for gw, gg in zip(ref.groups, bm.groups):
+        assert torch.equal(gw.charge, gg.charge) and torch.equal(gw.step, gg.step)
+        assert gw.genset is None or torch.equal(gw.genset, gg.genset)
+    # the wrong element type is refused
+    with pytest.raises(ValueError):
+        bm.step([a[0].contiguous() for a in a64])
+    bm.set_action_dtype(torch.float64)
+    bm.step([a[0].contiguous() for a in a64])
