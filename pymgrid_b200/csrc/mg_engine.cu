@@ -106,8 +106,14 @@ struct LaunchParams {
 // small helpers
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void st_global_v2(double *p, double a, double b) {
-    // 16-byte streaming store: observation rows are written once and never re-read by this kernel
+    // 16-byte store of row elements: written once, never re-read by this kernel, and not allowed to claim L1 lines the series
+    // gathers live on (same-box ABAB against st.global.cs, profiles/r02_store_hint_abab.txt: 11.48 vs 11.66 us/step on the
+    // lock-step headline, no difference elsewhere; -DMG_STORE_CS builds the evict-first form)
+#ifdef MG_STORE_CS
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+#else
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+#endif
 }
 // float32 observation rows (MG_LAYOUT_OBS_F32): the f64 value rounded to nearest, 8-byte stores
 __device__ __forceinline__ void st_global_v2(float *p, double a, double b) {

@@ -35,6 +35,15 @@ for stage in "$@"; do
       timeout 600 python tools/tune_composed.py > $out/${tag}_tune_composed.txt 2> $out/${tag}_tune_composed.err ;;
     compose_tests)
       timeout 900 python -m pytest tests/test_zz_gpu_compose.py -x -q -m gpu > $out/${tag}_compose_tests.log 2>&1 ;;
+    tune_store_hint)      # same-box ABAB of the row-store cache hint (default .L1::no_allocate vs st.global.cs, -DMG_STORE_CS)
+      cp pymgrid_b200/_lib/libpymgrid_b200.so /tmp/lib_na.so
+      PYMGRID_B200_NVCC_EXTRA=-DMG_STORE_CS timeout 300 python -m pymgrid_b200.build > $out/${tag}_build_cs.log 2>&1
+      cp pymgrid_b200/_lib/libpymgrid_b200.so /tmp/lib_cs.so
+      for round in 1 2 3; do for v in cs na; do
+        cp /tmp/lib_$v.so pymgrid_b200/_lib/libpymgrid_b200.so
+        timeout 300 python tools/tune_emitters.py --steps 400 --variants lsu_ws --workloads pymgrid25,discrete > $out/${tag}_tune_${v}_$round.jsonl 2> $out/${tag}_tune_${v}_$round.err
+      done; done
+      cp /tmp/lib_na.so pymgrid_b200/_lib/libpymgrid_b200.so ;;
     tune_const)
       MG_DEBUG_CONST_ACTIONS=1 timeout 900 python tools/tune_emitters.py --steps 400 --variants default --workloads pymgrid25,ragged,generator > $out/${tag}_tune_const.jsonl 2> $out/${tag}_tune_const.err ;;
     tune_gen)
