@@ -156,6 +156,7 @@ def run_composed(args):
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
@@ -399,7 +400,8 @@ class Harness:
         if self.world > 1:
             import torch.distributed as dist
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-                os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+                os.environ["NCCL_DEBUG"] = "WARN"      # errors only ...
+                os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # ... and off stdout (the version banner too): rank 0 prints ONE JSON line
             dist.init_process_group("nccl", device_id=torch.device(f"cuda:{self.local_rank}"))
             self.dist = dist
         torch.cuda.set_device(self.local_rank)
