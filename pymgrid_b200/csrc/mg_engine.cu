@@ -2029,6 +2029,8 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
     }
 }
 
+#define MG_NOISE_ROWS 16      // rows per CTA of the noise post-pass: (row, element pair) items are dealt to the 128 threads in turn
+
 template <typename TO>
 __global__ void __launch_bounds__(128) mg_forecast_noise_kernel(const __grid_constant__ NoiseParams P) {
     int gi = 0;
@@ -2036,21 +2038,39 @@ __global__ void __launch_bounds__(128) mg_forecast_noise_kernel(const __grid_con
     for (int q = 1; q < MG_MAX_GROUPS; ++q)
         if (q < P.n_groups && (int)blockIdx.x >= P.g[q].first_block) gi = q;
     const NoiseGroup &G = P.g[gi];
-    const int e = ((int)blockIdx.x - G.first_block) * 4 + (int)(threadIdx.x >> 5);
-    if (e >= G.n_envs) return;
-    const int lane = threadIdx.x & 31;
-    // the step the row observes (post-step state): the env's counter, or -- for a slot of a rollout's observation ring --
-    // what the counter was when the slot was written (it moves by one per step and stops at the end of the series)
-    const int t = G.step_base ? min(G.step_base[e] + P.step_add, P.T) : G.step[e];
     const int H = G.horizon;
-    int n_real = P.T - (t + 1);               // forecast rows that exist in the series: t + 1 + k < T
-    n_real = n_real < 0 ? 0 : (n_real > H ? H : n_real);
-    if (n_real == 0) return;                  // past the end everything is padding (base_timeseries_module.py:113-116)
-    const MgForecastNoise *__restrict__ nz = P.noise + G.cfg_index[e];
-    TO *__restrict__ row = reinterpret_cast<TO *>(G.obs) + (size_t)e * G.obs_dim;
+    // increase_uncertainty: the scale of forecast row k, 1 + log(1 + k) (forecaster.py:244-248), depends on k alone -- one
+    // evaluation per CTA instead of one f64 logarithm per element (the same expression, so the same bits)
+    __shared__ double s_scale[128];
+    __shared__ int s_t[MG_NOISE_ROWS], s_real[MG_NOISE_ROWS];
+    const int tid = threadIdx.x;
+    const int e0 = ((int)blockIdx.x - G.first_block) * MG_NOISE_ROWS;
+    if (tid < H) s_scale[tid] = 1.0 + log(1.0 + (double)tid);
+    if (tid < MG_NOISE_ROWS) {
+        int t = 0, n_real = 0;
+        if (e0 + tid < G.n_envs) {
+            // the step the row observes (post-step state): the env's counter, or -- for a slot of a rollout's observation ring --
+            // what the counter was when the slot was written (it moves by one per step and stops at the end of the series)
+            t = G.step_base ? min(G.step_base[e0 + tid] + P.step_add, P.T) : G.step[e0 + tid];
+            n_real = P.T - (t + 1);           // forecast rows that exist in the series: t + 1 + k < T
+            n_real = n_real < 0 ? 0 : (n_real > H ? H : n_real);      // past the end everything is padding (base_timeseries_module.py:113-116)
+        }
+        s_t[tid] = t;
+        s_real[tid] = n_real;
+    }
+    __syncthreads();
     const int n_fc = H * (2 + 4 * G.has_grid);
-    const uint64_t env = (uint64_t)(G.env_base + e);
-    for (int p = lane; 2 * p < n_fc; p += 32) {
+    const int n_pairs = (n_fc + 1) >> 1;
+    // one Philox block = two normals = two neighbouring forecast elements of one row; a row's pairs rarely fill whole warps
+    // (69 at H = 23), so the (row, pair) items of the CTA's rows are flattened over its threads
+    for (int i = tid; i < MG_NOISE_ROWS * n_pairs; i += 128) {
+        const int r = i / n_pairs, p = i - r * n_pairs;
+        const int n_real = s_real[r];
+        if (n_real == 0) continue;
+        const int e = e0 + r, t = s_t[r];
+        const MgForecastNoise *__restrict__ nz = P.noise + G.cfg_index[e];
+        TO *__restrict__ row = reinterpret_cast<TO *>(G.obs) + (size_t)e * G.obs_dim;
+        const uint64_t env = (uint64_t)(G.env_base + e);
         uint32_t c[4] = {(uint32_t)env, ((uint32_t)(env >> 32) & 0xffffu) | ((uint32_t)p << 16), (uint32_t)t, P.c3};
         philox4x32_10(c, P.k0, P.k1);
         // two 53-bit uniforms, u1 in (0, 1], u2 in [0, 1); Box-Muller
@@ -2072,7 +2092,7 @@ __global__ void __launch_bounds__(128) mg_forecast_noise_kernel(const __grid_con
                 k = q >> 2; off = G.grid_start + 4 + q; sigma = nz->grid_sigma[q & 3]; inc = nz->grid_increase;
             }
             if (k >= n_real || sigma == 0.0) continue;
-            if (inc) sigma = sigma * (1.0 + log(1.0 + (double)k));      // forecaster.py:244-248
+            if (inc) sigma = sigma * (k < 128 ? s_scale[k] : 1.0 + log(1.0 + (double)k));
             double v = (double)row[off] + (radius * (h ? sn : cs)) * sigma;
             v = fmin(fmax(v, 0.0), 1.0);                                // the clip to [low, high] in normalised units
             row[off] = (TO)v;
@@ -2372,7 +2392,7 @@ static int launch_noise(MgHandle *h, const MgForecastNoise *noise, void *const *
         n.step = d.step; n.cfg_index = d.cfg_index; n.obs = obs[g];
         n.step_base = step_base ? step_base[g] : nullptr;
         if (step_base && !n.step_base) n.n_envs = 0;
-        blocks += (n.n_envs + 3) / 4;
+        blocks += (n.n_envs + MG_NOISE_ROWS - 1) / MG_NOISE_ROWS;
         base += d.n_envs;
     }
     if (blocks == 0) return MG_OK;
