@@ -127,8 +127,12 @@ int32_t mgc_param_count(int kind); /* doubles a module of this kind takes in a c
 
 /* mgc_create -- replaces Microgrid.__init__ for a batch (microgrid.py:100-165): validates the composition (dispatch order,
  * blocks inside their rows and not overlapping, listing a permutation) and uploads one small table to the CURRENT device
- * (obs_dim int32: observation element -> module, offset) -- the only device memory a handle owns, released by mgc_destroy.
- * Every other array stays owned by the caller. */
+ * (obs_dim int32: observation element -> module, offset; with series_nrm also its gather form, 3 more int32 per element)
+ * -- the only device memory a handle owns, released by mgc_destroy.  Every other array stays owned by the caller.
+ * With series_nrm given, observation rows are written by the staged-gather emitters (mg_compose.cu: per-env window bases and
+ * state elements staged in shared memory by the thread that stepped the env, <= 96 KB per 128-env tile; layouts that need
+ * more keep the per-element decode).  The environment variable PYMGRID_B200_COMPOSE_GATHER=0, read here, forces the
+ * per-element decode: same bytes, kept for A/B measurements and the parity test between the two. */
 int mgc_create(const MgcLayout *layout, MgcHandle **out);
 int mgc_destroy(MgcHandle *h);
 
